@@ -1,0 +1,335 @@
+"""ctypes front-end of the CPU oracle (oracle/tci_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product never imports it.
+All matrices are column-major float64, all indices 1-based (Julia conventions).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+i64 = C.c_int64
+f64 = C.c_double
+P_i64 = C.POINTER(C.c_int64)
+P_f64 = C.POINTER(C.c_double)
+I64MAX = 2**63 - 1
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libtci_oracle.so")
+    src = os.path.join(_HERE, "tci_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "tci_targets.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libtci_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libtci_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_last_error.restype = C.c_char_p
+        _LIB.orc_target_builtin.restype = C.c_void_p
+        _LIB.orc_tt_create.restype = C.c_void_p
+        _LIB.orc_mpo_pair_create.restype = C.c_void_p
+        _LIB.orc_crossinterpolate2.restype = C.c_void_p
+        _LIB.orc_eval_point.restype = f64
+        _LIB.orc_tt_evaluate.restype = f64
+        _LIB.orc_tt_sum.restype = f64
+        _LIB.orc_tci_maxsamplevalue.restype = f64
+        _LIB.orc_tci_evaluate.restype = f64
+        _LIB.orc_tci_sum.restype = f64
+        for name in ("orc_tci_niter", "orc_tci_npivoterrors", "orc_tci_indexset", "orc_tci_tracelen",
+                     "orc_target_nevals"):
+            getattr(_LIB, name).restype = i64
+    return _LIB
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise OracleError(lib().orc_last_error().decode())
+
+
+def _f(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _pf(a):
+    return a.ctypes.data_as(P_f64)
+
+
+def _pi(a):
+    return a.ctypes.data_as(P_i64)
+
+
+def _flat_idx(lst, length=None):
+    """list of multi-indices -> (len x count) column-major int64 array"""
+    if len(lst) == 0:
+        return np.zeros((length or 0, 0), dtype=np.int64, order="F")
+    a = np.asarray(lst, dtype=np.int64).reshape(len(lst), -1)
+    return np.asfortranarray(a.T)
+
+
+class LU:
+    pass
+
+
+def rrlu(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True):
+    A = _f(A)
+    m, n = A.shape
+    maxrank = I64MAX if maxrank is None else int(maxrank)
+    mr = max(0, min(maxrank, m, n))
+    rowperm = np.zeros(m, dtype=np.int64)
+    colperm = np.zeros(n, dtype=np.int64)
+    npiv = i64(0)
+    err = f64(0.0)
+    L = np.zeros(m * mr, dtype=np.float64)
+    U = np.zeros(mr * n, dtype=np.float64)
+    pe = np.zeros(min(m, n) + 1, dtype=np.float64)
+    _check(lib().orc_rrlu(_pf(A), i64(m), i64(n), i64(maxrank), f64(reltol), f64(abstol), C.c_int(int(leftorthogonal)),
+                          _pi(rowperm), _pi(colperm), C.byref(npiv), C.byref(err), _pf(L), _pf(U), _pf(pe)))
+    r = npiv.value
+    out = LU()
+    out.rowpermutation, out.colpermutation = rowperm, colperm
+    out.npivot, out.error = r, err.value
+    out.L = L[: m * r].reshape((m, r), order="F")
+    out.U = U[: r * n].reshape((r, n), order="F")
+    out.pivoterrors = pe[: r + 1].copy()
+    out.leftorthogonal = leftorthogonal
+    return out
+
+
+def luci(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True):
+    A = _f(A)
+    m, n = A.shape
+    maxrank = I64MAX if maxrank is None else int(maxrank)
+    mr = max(0, min(maxrank, m, n))
+    rowperm = np.zeros(m, dtype=np.int64)
+    colperm = np.zeros(n, dtype=np.int64)
+    npiv = i64(0)
+    left = np.zeros(m * mr, dtype=np.float64)
+    right = np.zeros(mr * n, dtype=np.float64)
+    pe = np.zeros(min(m, n) + 1, dtype=np.float64)
+    _check(lib().orc_luci(_pf(A), i64(m), i64(n), i64(maxrank), f64(reltol), f64(abstol), C.c_int(int(leftorthogonal)),
+                          _pi(rowperm), _pi(colperm), C.byref(npiv), _pf(pe), _pf(left), _pf(right)))
+    r = npiv.value
+    out = LU()
+    out.rowpermutation, out.colpermutation, out.npivot = rowperm, colperm, r
+    out.rowindices, out.colindices = rowperm[:r].copy(), colperm[:r].copy()
+    out.left = left[: m * r].reshape((m, r), order="F")
+    out.right = right[: r * n].reshape((r, n), order="F")
+    out.pivoterrors = pe[: r + 1].copy()
+    return out
+
+
+def argmax_abs2(A, k=1):
+    A = _f(A)
+    r, c = i64(0), i64(0)
+    lib().orc_argmax_abs2(_pf(A), i64(A.shape[0]), i64(A.shape[1]), i64(k), C.byref(r), C.byref(c))
+    return r.value, c.value
+
+
+def _core_ptrs(cores):
+    keep = [np.asfortranarray(c, dtype=np.float64) for c in cores]
+    arr = (P_f64 * len(keep))(*[_pf(c) for c in keep])
+    return keep, arr
+
+
+def _dims(cores, nd):
+    return np.ascontiguousarray(np.array([c.shape for c in cores], dtype=np.int64).reshape(len(cores), nd))
+
+
+class Target:
+    def __init__(self, handle, localdims, keep=None):
+        self.h = C.c_void_p(handle)
+        self.localdims = [int(d) for d in localdims]
+        self._keep = keep
+
+    @classmethod
+    def builtin(cls, kind, params, localdims):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ld = np.ascontiguousarray(localdims, dtype=np.int64)
+        h = lib().orc_target_builtin(C.c_int(kind), _pf(p), i64(p.size), _pi(ld), i64(ld.size))
+        return cls(h, ld)
+
+    @classmethod
+    def tt(cls, cores):
+        keep, arr = _core_ptrs(cores)
+        d = _dims(keep, 3)
+        h = lib().orc_tt_create(i64(len(keep)), _pi(d), arr)
+        return cls(h, d[:, 1])
+
+    @classmethod
+    def mpo_pair(cls, A, B):
+        ka, pa = _core_ptrs(A)
+        kb, pb = _core_ptrs(B)
+        da, db = _dims(ka, 4), _dims(kb, 4)
+        h = lib().orc_mpo_pair_create(i64(len(ka)), _pi(da), pa, _pi(db), pb)
+        return cls(h, da[:, 1] * db[:, 2])
+
+    def __del__(self):
+        try:
+            lib().orc_target_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, idx):
+        v = np.ascontiguousarray(idx, dtype=np.int64)
+        return lib().orc_eval_point(self.h, _pi(v))
+
+    def pi_eval(self, I, J, M, maxabs=None):
+        """Returns the (nI, d..., nJ) array (Fortran order) and the updated max-abs."""
+        n = len(self.localdims)
+        if len(I) == 0 or len(J) == 0:
+            return np.zeros((0,) * (M + 2), order="F"), maxabs
+        Ia, Ja = _flat_idx(I), _flat_idx(J)
+        nl, nI = Ia.shape
+        nr, nJ = Ja.shape
+        assert nl + M + nr == n
+        cd = self.localdims[nl:nl + M]
+        out = np.zeros(nI * int(np.prod(cd, dtype=np.int64)) * nJ, dtype=np.float64)
+        ma = f64(0.0 if maxabs is None else maxabs)
+        _check(lib().orc_pi_eval(self.h, _pi(Ia), i64(nl), i64(nI), _pi(Ja), i64(nr), i64(nJ), i64(M), _pf(out),
+                                 C.byref(ma)))
+        return out.reshape((nI, *cd, nJ), order="F"), ma.value
+
+    @property
+    def nevals(self):
+        return lib().orc_target_nevals(self.h)
+
+
+def tt_evaluate(cores, idx):
+    keep, arr = _core_ptrs(cores)
+    d = _dims(keep, 3)
+    v = np.ascontiguousarray(idx, dtype=np.int64)
+    return lib().orc_tt_evaluate(i64(len(keep)), _pi(d), arr, _pi(v))
+
+
+def tt_sum(cores):
+    keep, arr = _core_ptrs(cores)
+    d = _dims(keep, 3)
+    return lib().orc_tt_sum(i64(len(keep)), _pi(d), arr)
+
+
+def start_points(seed, it, nsearch, localdims):
+    ld = np.ascontiguousarray(localdims, dtype=np.int64)
+    out = np.zeros((ld.size, nsearch), dtype=np.int64, order="F")
+    lib().orc_start_points(C.c_uint64(seed), i64(it), i64(nsearch), _pi(ld), i64(ld.size), _pi(out))
+    return out
+
+
+def globalsearch(target, cores, starts, abstol, tolmargin=10.0, maxn=5):
+    keep, arr = _core_ptrs(cores)
+    d = _dims(keep, 3)
+    starts = np.asfortranarray(starts, dtype=np.int64)
+    n, nsearch = starts.shape
+    piv = np.zeros((n, max(nsearch, 1)), dtype=np.int64, order="F")
+    errs = np.zeros(max(nsearch, 1), dtype=np.float64)
+    nf = i64(0)
+    _check(lib().orc_globalsearch(target.h, i64(n), _pi(d), arr, _pi(starts), i64(nsearch), f64(abstol),
+                                  f64(tolmargin), i64(maxn), _pi(piv), _pf(errs), C.byref(nf)))
+    return [piv[:, q].tolist() for q in range(nf.value)], errs[: nf.value].copy()
+
+
+def convergencecriterion(ranks, errors, nglobalpivots, tol, maxbonddim, ncheckhistory, checkconvglobalpivot=True):
+    r = np.ascontiguousarray(ranks, dtype=np.int64)
+    e = np.ascontiguousarray(errors, dtype=np.float64)
+    g = np.ascontiguousarray(nglobalpivots, dtype=np.int64)
+    return bool(lib().orc_convergencecriterion(_pi(r), _pf(e), _pi(g), i64(r.size), f64(tol), i64(maxbonddim),
+                                               i64(ncheckhistory), C.c_int(int(checkconvglobalpivot))))
+
+
+class _Options(C.Structure):
+    _fields_ = [("tolerance", f64), ("maxbonddim", i64), ("maxiter", i64), ("sweepstrategy", C.c_int),
+                ("normalizeerror", C.c_int), ("ncheckhistory", i64), ("maxnglobalpivot", i64),
+                ("nsearchglobalpivot", i64), ("tolmarginglobalsearch", f64), ("strictlynested", C.c_int),
+                ("checkconvglobalpivot", C.c_int), ("seed", C.c_uint64)]
+
+
+_STRATEGY = {"backandforth": 0, "forward": 1, "backward": 2}
+
+
+class TCIResult:
+    def __init__(self, h, n):
+        self.h = C.c_void_p(h)
+        self.n = n
+        L = lib()
+        k = L.orc_tci_niter(self.h)
+        self.ranks = np.zeros(k, dtype=np.int64)
+        self.errors = np.zeros(k, dtype=np.float64)
+        self.nglobalpivots = np.zeros(k, dtype=np.int64)
+        L.orc_tci_history(self.h, _pi(self.ranks), _pf(self.errors), _pi(self.nglobalpivots))
+        self.maxsamplevalue = L.orc_tci_maxsamplevalue(self.h)
+        self.pivoterrors = np.zeros(L.orc_tci_npivoterrors(self.h), dtype=np.float64)
+        self.bonderrors = np.zeros(n - 1, dtype=np.float64)
+        L.orc_tci_pivoterrors(self.h, _pf(self.pivoterrors), _pf(self.bonderrors))
+        self.Iset, self.Jset = [], []
+        for which, dst in ((0, self.Iset), (1, self.Jset)):
+            for b in range(n):
+                cnt = L.orc_tci_indexset(self.h, C.c_int(which), i64(b), None)
+                ln = b if which == 0 else n - 1 - b
+                buf = np.zeros((ln, cnt), dtype=np.int64, order="F")
+                if ln * cnt:
+                    L.orc_tci_indexset(self.h, C.c_int(which), i64(b), _pi(buf))
+                dst.append([tuple(buf[:, q].tolist()) for q in range(cnt)])
+        self.sitetensors = []
+        for b in range(n):
+            d3 = np.zeros(3, dtype=np.int64)
+            L.orc_tci_coredims(self.h, i64(b), _pi(d3))
+            core = np.zeros(int(np.prod(d3)), dtype=np.float64)
+            L.orc_tci_core(self.h, i64(b), _pf(core))
+            self.sitetensors.append(core.reshape(tuple(d3), order="F"))
+        tl = L.orc_tci_tracelen(self.h)
+        self.trace = np.zeros((tl, 5), dtype=np.int64)
+        if tl:
+            L.orc_tci_trace(self.h, _pi(self.trace))
+
+    @property
+    def linkdims(self):
+        return [len(self.Iset[b + 1]) for b in range(self.n - 1)]
+
+    def evaluate(self, idx):
+        v = np.ascontiguousarray(idx, dtype=np.int64)
+        return lib().orc_tci_evaluate(self.h, _pi(v))
+
+    def sum(self):
+        return lib().orc_tci_sum(self.h)
+
+    def __del__(self):
+        try:
+            lib().orc_tci_destroy(self.h)
+        except Exception:
+            pass
+
+
+def crossinterpolate2(target, localdims, initialpivots=None, tolerance=1e-8, maxbonddim=None, maxiter=20,
+                      sweepstrategy="backandforth", normalizeerror=True, ncheckhistory=3, maxnglobalpivot=5,
+                      nsearchglobalpivot=5, tolmarginglobalsearch=10.0, strictlynested=False,
+                      checkconvglobalpivot=True, seed=1):
+    ld = np.ascontiguousarray(localdims, dtype=np.int64)
+    n = ld.size
+    if initialpivots is None:
+        initialpivots = [[1] * n]
+    pv = _flat_idx(initialpivots, n)
+    o = _Options(tolerance, I64MAX if maxbonddim is None else int(maxbonddim), maxiter, _STRATEGY[sweepstrategy],
+                 int(normalizeerror), ncheckhistory, maxnglobalpivot, nsearchglobalpivot, tolmarginglobalsearch,
+                 int(strictlynested), int(checkconvglobalpivot), seed)
+    st = C.c_int(0)
+    h = lib().orc_crossinterpolate2(target.h, _pi(ld), i64(n), _pi(pv), i64(pv.shape[1]), C.byref(o), C.byref(st))
+    if st.value != 0:
+        msg = lib().orc_last_error().decode()
+        lib().orc_tci_destroy(C.c_void_p(h))
+        raise OracleError(msg)
+    return TCIResult(h, n)
