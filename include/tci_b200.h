@@ -1,0 +1,150 @@
+/*
+ * tci_b200.h -- C ABI of libtci_b200.so, the B200 (sm_100a) drop-in for the
+ * TensorCI2 two-site update hot path of TensorCrossInterpolation.jl v0.9.19.
+ *
+ * The reference is pure Julia and has no FFI; its extension points are Julia
+ * dispatch.  Each entry point below names the reference interface it stands in
+ * for (file:line under /root/reference/src); INTEGRATION.md shows the Julia
+ * `ccall` shim that binds them.
+ *
+ * Conventions (Julia's): matrices are column-major Float64; sizes are int64_t;
+ * multi-indices and permutations are 1-based; index sets are passed flattened,
+ * (len x count) column-major, i.e. multi-index q occupies I[len*q .. len*q+len).
+ * Host buffers belong to the caller and are only used during the call.
+ * Library objects are opaque handles with explicit destroy functions.
+ * Every function returns TCI_OK (0) or a tci_status; tci_last_error(ctx) gives
+ * the message (texts follow the reference's exceptions where one exists).
+ * A tci_ctx is bound to one GPU and must be used by one caller at a time
+ * (one process per GPU; multi-GPU sharding is done by the host layer).
+ */
+#ifndef TCI_B200_H
+#define TCI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tci_ctx tci_ctx;
+typedef struct tci_dmat tci_dmat; /* device matrix (m x n, leading dimension ld) */
+typedef struct tci_lu tci_lu;     /* device-resident rrLU factorisation          */
+
+typedef enum {
+    TCI_OK = 0,
+    TCI_ERR_CUDA = 1,        /* CUDA runtime failure                              */
+    TCI_ERR_ARG = 2,         /* invalid argument                                  */
+    TCI_ERR_NAN_L = 3,       /* "lu.L contains NaNs"  matrixlu.jl:164-166         */
+    TCI_ERR_NAN_U = 4,       /* "lu.U contains NaNs"  matrixlu.jl:167-169         */
+    TCI_ERR_CENTRE = 5,      /* "Invalid number of central indices" tensorci2.jl:307 */
+    TCI_ERR_NO_DEVICE = 6,   /* no CUDA device: the library has no CPU fallback   */
+    TCI_ERR_BUSY = 7,        /* context entered concurrently                      */
+    TCI_ERR_UNSUPPORTED = 8
+} tci_status;
+
+int tci_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+int tci_ctx_create(int device_id, tci_ctx **out);
+void tci_ctx_destroy(tci_ctx *ctx);
+const char *tci_last_error(tci_ctx *ctx); /* ctx may be NULL: last create error */
+/* number of kernels this context launched since creation (bench gpu_launches) */
+int64_t tci_ctx_launches(tci_ctx *ctx);
+/* accumulated CUDA-event time per stage in ms; stages: 0 pi_eval, 1 rrlu, 2 luci,
+ * 3 tt/mpo environments, 4 globalsearch, 5 gemm, 6 h2d, 7 d2h.  Stands in for the
+ * time_ns() pairs around "Computing Pi"/"LU" (tensorci2.jl:530-550).              */
+int tci_timers(tci_ctx *ctx, double *out, int64_t n, int reset);
+
+/* ---- device matrices ---------------------------------------------------- */
+int tci_dmat_create(tci_ctx *ctx, int64_t m, int64_t n, const double *host /* nullable */, tci_dmat **out);
+int tci_dmat_shape(tci_dmat *a, int64_t *m, int64_t *n, int64_t *ld);
+void *tci_dmat_ptr(tci_dmat *a); /* raw device pointer, for collectives on the host layer */
+int tci_dmat_fetch(tci_dmat *a, double *host /* m x n, tight */);
+int tci_dmat_destroy(tci_dmat *a);
+
+/* ---- targets: the function f being interpolated ------------------------- */
+/* Replaces the Julia closure / BatchEvaluator object `f` (cachedtensortrain.jl:1,
+ * batcheval.jl:67-83, docs/src/index.md:174-241).  kind_id: tci_targets.h.       */
+int tci_target_builtin(tci_ctx *ctx, int kind_id, const double *params, int64_t nparams, const int64_t *localdims,
+                       int64_t nsites, int64_t *target_id);
+/* TTCache(tt) (cachedtensortrain.jl:9-30): cores[s] is (dims3[3s], dims3[3s+1], dims3[3s+2]). */
+int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
+                  int64_t *target_id);
+/* Contraction(a, b) (contraction.jl:35-62): A[s] is (Da,s1,s2,Da'), B[s] is (Db,s2,s3,Db'). */
+int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,
+                        const int64_t *dimsB4, const double *const *B, int64_t *target_id);
+int tci_target_destroy(tci_ctx *ctx, int64_t target_id);
+/* f(x) for `count` full multi-indices (nsites x count): the scalar call
+ * (bf::BatchEvaluatorAdapter)(indexset) batcheval.jl:11-13, TTCache/Contraction
+ * evaluate cachedtensortrain.jl:130-146, contraction.jl:189-207.                  */
+int tci_target_eval(tci_ctx *ctx, int64_t target_id, const int64_t *idx, int64_t count, double *out);
+
+/* ---- (a) batched Pi / T evaluation --------------------------------------- */
+/* filltensor / _batchevaluate_dispatch (tensorci2.jl:290-312, batcheval.jl:32-83)
+ * and batchevaluate of TTCache / Contraction (cachedtensortrain.jl:151-215,
+ * contraction.jl:236-335).  out[i, c, j] = f(I_i ++ c ++ J_j); M centre sites
+ * nl+1..nl+M are expanded on the device, first centre index fastest; layout is
+ * column-major (nI, d_{nl+1}, ..., d_{nl+M}, nJ).  nI*nJ == 0 is not an error
+ * (empty result, batcheval.jl:40-42).  *maxabs (nullable) receives
+ * max(|out|), NaN-propagating, i.e. maxabs(0, out) of util.jl:1-10.
+ * out_host (nullable) receives the tight array; out_dev (nullable) receives a
+ * device matrix of shape (nI*C) x nJ that can be handed to tci_rrlu.             */
+int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs);
+
+/* ---- (b) rank-revealing LU / MatrixLUCI ---------------------------------- */
+/* rrlu(A; maxrank, reltol, abstol, leftorthogonal) (matrixlu.jl:194-225) with the
+ * full-pivot search and Schur updates of matrixlu.jl:1-32,98-181.  Exactly one of
+ * A_host / A_dev is non-NULL; A_dev is factorised IN PLACE and owned by *factors
+ * afterwards (do not destroy it separately when factors != NULL).
+ * maxrank <= 0 or > min(m,n) means min(m,n).  exact_mode = 1 reproduces the
+ * reference arithmetic (rounded multiply, rounded subtract, true division);
+ * exact_mode = 0 uses fused multiply-add.
+ * Outputs: rowperm[m], colperm[n] (1-based, = lu.rowpermutation/colpermutation),
+ * *npivot, *error (= lu.error), pivoterrors[npivot+1] (caller provides
+ * min(m,n)+1 doubles; = pivoterrors(lu) matrixlu.jl:394-416).                     */
+int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int64_t m, int64_t n, int64_t maxrank,
+             double reltol, double abstol, int leftorthogonal, int exact_mode, int64_t *rowperm, int64_t *colperm,
+             int64_t *npivot, double *error, double *pivoterrors, tci_lu **factors /* nullable */);
+/* lu.L (m x r) and lu.U (r x n), i.e. left/right(lu; permute=false) matrixlu.jl:374-392 */
+int tci_lu_fetch(tci_lu *lu, double *L /* nullable */, double *U /* nullable */);
+/* left(luci) (m x r) / right(luci) (r x n)  matrixluci.jl:40-84 */
+int tci_luci_left(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+int tci_luci_right(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+int tci_lu_destroy(tci_lu *lu);
+
+/* ---- dense FP64 GEMM on device matrices (building block of (b),(c)) ------- */
+/* C = alpha * op(A) * op(B) + beta * C ; host arrays, column-major, tight.  Exposed
+ * for benchmarks and tests of the kernel that replaces OpenBLAS dgemm in
+ * matrixluci.jl:41,45, cachedtensortrain.jl:207,212 and contraction.jl:92.        */
+int tci_dgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                   const double *A, const double *B, double beta, double *C);
+
+/* ---- (c) contraction ------------------------------------------------------ */
+/* One zip-up step (contraction.jl:455-464): R (chi,Da,Db), A (Da,s1,s2,Da'),
+ * B (Db,s2,s3,Db') -> C as the (chi*s1*s3) x (Da'*Db') matrix that is factorised next. */
+int tci_contract_zipup_site(tci_ctx *ctx, const double *R, int64_t chi, int64_t Da, int64_t Db, const double *A,
+                            int64_t s1, int64_t s2, int64_t Dan, const double *B, int64_t s3, int64_t Dbn,
+                            double *C_host /* nullable */, tci_dmat **C_dev /* nullable */);
+/* _contractsitetensors (contraction.jl:338-349): out (Da*Db, s1, s3, Da'*Db') */
+int tci_contract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s1, int64_t s2, int64_t Dan,
+                            const double *B, int64_t Db, int64_t s3, int64_t Dbn, double *out_host);
+
+/* ---- global pivot search --------------------------------------------------- */
+/* DefaultGlobalPivotFinder call (globalpivotfinder.jl:143-195) with the start
+ * points drawn by the caller's rng (n x nsearch): for every start the star of
+ * sum_p d_p probes |f(x) - tt(x)|, first maximum kept, accepted if > threshold
+ * (= abstol * tolmarginglobalsearch), truncated to the first maxn in start order.
+ * cores: the current tensor train (host, dims3 as in tci_tt_create).
+ * pivots_out: n x maxn, errs_out: maxn.                                           */
+int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
+                     const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
+                     int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *nfound);
+/* evaluate(tt, x) for `count` points, left-to-right (abstracttensortrain.jl:124-132) */
+int tci_tt_evaluate(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
+                    const int64_t *idx, int64_t count, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCI_B200_H */

@@ -1,0 +1,20 @@
+"""tci_b200: B200 (sm_100a) drop-in for the TensorCI2 two-site update hot path of
+TensorCrossInterpolation.jl.  `csrc/` holds the CUDA kernels and the C ABI
+(include/tci_b200.h -> libtci_b200.so); the Python modules mirror the reference's host
+interface for this path (same names and keyword arguments) and call the ABI via ctypes.
+There is no CPU fallback anywhere in this package."""
+from ._lib import Context, DeviceMatrix, TCIError, default_context, lib  # noqa: F401
+from .batcheval import (GKCOSEXP, LORENTZ, QUANTICS1D, QUANTICS2D, SEPCOS, SUM, TABLE, BatchEvaluator,  # noqa: F401
+                        BuiltinTarget, makebatchevaluatable)
+from .cachedtensortrain import TTCache, isbatchevaluable  # noqa: F401
+from .contraction import (Contraction, _contractsitetensors, _factorize, contract, contract_naive,  # noqa: F401
+                          contract_TCI, contract_zipup)
+from .globalpivotfinder import (AbstractGlobalPivotFinder, DefaultGlobalPivotFinder,  # noqa: F401
+                                GlobalPivotSearchInput)
+from .matrixlu import (MatrixLUCI, colindices, lastpivoterror, left, npivots, pivoterrors, right,  # noqa: F401
+                       rowindices, rrLU, rrlu, size)
+from .tensorci2 import (TensorCI2, addglobalpivots, convergencecriterion, crossinterpolate2, evaluate,  # noqa: F401
+                        fillsitetensors, filltensor, linkdims, optimize, pivoterror, rank, sweep1site, sweep2site,
+                        tci_sum, updatepivots)
+from .tensortrain import TensorTrain, evaluate_points, fulltensor, sitedims, tt_sum  # noqa: F401
+from .util import CounterRNG, forwardsweep, kronecker_left, kronecker_right  # noqa: F401

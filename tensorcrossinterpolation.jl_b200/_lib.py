@@ -1,0 +1,205 @@
+"""ctypes binding of libtci_b200.so (include/tci_b200.h).
+
+This is the same ABI a Julia `ccall` shim binds.  There is no CPU
+fallback: if the shared library is missing, or no CUDA device is present when a context
+is created, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtci_b200.so")
+
+i64 = C.c_int64
+f64 = C.c_double
+P_i64 = C.POINTER(C.c_int64)
+P_f64 = C.POINTER(C.c_double)
+VP = C.c_void_p
+PP_f64 = C.POINTER(P_f64)
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "tci_version": (C.c_int, []),
+    "tci_ctx_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
+    "tci_ctx_destroy": (None, [VP]),
+    "tci_last_error": (C.c_char_p, [VP]),
+    "tci_ctx_launches": (i64, [VP]),
+    "tci_timers": (C.c_int, [VP, P_f64, i64, C.c_int]),
+    "tci_dmat_create": (C.c_int, [VP, i64, i64, P_f64, C.POINTER(VP)]),
+    "tci_dmat_shape": (C.c_int, [VP, P_i64, P_i64, P_i64]),
+    "tci_dmat_ptr": (VP, [VP]),
+    "tci_dmat_fetch": (C.c_int, [VP, P_f64]),
+    "tci_dmat_destroy": (C.c_int, [VP]),
+    "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
+    "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
+    "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
+    "tci_target_destroy": (C.c_int, [VP, i64]),
+    "tci_target_eval": (C.c_int, [VP, i64, P_i64, i64, P_f64]),
+    "tci_pi_eval": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, P_f64, C.POINTER(VP), P_f64]),
+    "tci_rrlu": (C.c_int, [VP, P_f64, VP, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64, P_i64, P_i64, P_f64,
+                           P_f64, C.POINTER(VP)]),
+    "tci_lu_fetch": (C.c_int, [VP, P_f64, P_f64]),
+    "tci_luci_left": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
+    "tci_luci_right": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
+    "tci_lu_destroy": (C.c_int, [VP]),
+    "tci_dgemm_host": (C.c_int, [VP, C.c_int, C.c_int, i64, i64, i64, f64, P_f64, P_f64, f64, P_f64]),
+    "tci_contract_zipup_site": (C.c_int, [VP, P_f64, i64, i64, i64, P_f64, i64, i64, i64, P_f64, i64, i64, P_f64,
+                                          C.POINTER(VP)]),
+    "tci_contract_naive_site": (C.c_int, [VP, P_f64, i64, i64, i64, i64, P_f64, i64, i64, i64, P_f64]),
+    "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, PP_f64, P_i64, i64, f64, i64, P_i64, P_f64, P_i64]),
+    "tci_tt_evaluate": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, i64, P_f64]),
+}
+
+TCI_OK, TCI_ERR_CUDA, TCI_ERR_ARG, TCI_ERR_NAN_L, TCI_ERR_NAN_U, TCI_ERR_CENTRE, TCI_ERR_NO_DEVICE = range(7)
+
+_lib = None
+
+
+class TCIError(RuntimeError):
+    """ErrorException of the Julia shim: carries the library's status code."""
+
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libtci_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def pf(a):
+    return a.ctypes.data_as(P_f64) if a is not None else None
+
+
+def pi(a):
+    return a.ctypes.data_as(P_i64) if a is not None else None
+
+
+def core_ptrs(cores):
+    keep = [np.asfortranarray(c, dtype=np.float64) for c in cores]
+    arr = (P_f64 * len(keep))(*[pf(c) for c in keep])
+    return keep, arr
+
+
+class Context:
+    """tci_ctx: one GPU, one caller at a time."""
+
+    def __init__(self, device=0):
+        self.h = VP()
+        rc = lib().tci_ctx_create(int(device), C.byref(self.h))
+        if rc != 0:
+            raise TCIError(rc, lib().tci_last_error(None).decode())
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            msg = lib().tci_last_error(self.h).decode()
+            if rc == TCI_ERR_ARG:
+                raise ValueError(msg)
+            raise TCIError(rc, msg)
+
+    @property
+    def launches(self):
+        return int(lib().tci_ctx_launches(self.h))
+
+    def timers(self, reset=False):
+        out = np.zeros(8, dtype=np.float64)
+        lib().tci_timers(self.h, pf(out), 8, int(reset))
+        names = ["pi_eval", "rrlu", "luci", "env", "globalsearch", "gemm", "h2d", "d2h"]
+        return dict(zip(names, out.tolist()))
+
+    def close(self):
+        if self.h:
+            lib().tci_ctx_destroy(self.h)
+            self.h = VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = None
+
+
+def default_context():
+    global _default
+    if _default is None:
+        _default = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
+
+
+class DeviceMatrix:
+    """tci_dmat handle (column-major m x n with leading dimension ld on the GPU)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = VP(handle) if not isinstance(handle, VP) else handle
+        self._owned = True
+
+    @classmethod
+    def from_host(cls, ctx, a):
+        a = np.asfortranarray(a, dtype=np.float64)
+        h = VP()
+        ctx.check(lib().tci_dmat_create(ctx.h, a.shape[0], a.shape[1], pf(a), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def empty(cls, ctx, m, n):
+        h = VP()
+        ctx.check(lib().tci_dmat_create(ctx.h, m, n, None, C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def shape(self):
+        m, n, ld = i64(), i64(), i64()
+        lib().tci_dmat_shape(self.h, C.byref(m), C.byref(n), C.byref(ld))
+        return m.value, n.value
+
+    @property
+    def ld(self):
+        m, n, ld = i64(), i64(), i64()
+        lib().tci_dmat_shape(self.h, C.byref(m), C.byref(n), C.byref(ld))
+        return ld.value
+
+    @property
+    def ptr(self):
+        return lib().tci_dmat_ptr(self.h)
+
+    @property
+    def __cuda_array_interface__(self):  # padded (ld x n) view for torch.as_tensor / collectives
+        m, n = self.shape
+        return {"shape": (n, self.ld), "typestr": "<f8", "data": (int(self.ptr or 0), False), "version": 2}
+
+    def to_host(self):
+        m, n = self.shape
+        out = np.zeros((m, n), dtype=np.float64, order="F")
+        if m * n:
+            self.ctx.check(lib().tci_dmat_fetch(self.h, pf(out)))
+        return out
+
+    def release(self):
+        """Give up ownership (the handle was consumed by tci_rrlu)."""
+        self._owned = False
+
+    def __del__(self):
+        try:
+            if self._owned and self.h:
+                lib().tci_dmat_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,103 @@
+"""Host mirror of the BatchEvaluator interface (src/cachedtensortrain.jl:1,
+src/batcheval.jl:4-83, docs/src/index.md:174-241): objects that are callable on one
+multi-index and on (leftindexset, rightindexset, M).  All of them evaluate on the GPU
+through tci_pi_eval / tci_target_eval; none of them can run without the library."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceMatrix, lib, pf, pi
+from .util import as_indexset
+
+LORENTZ, SUM, QUANTICS2D, SEPCOS, TABLE, QUANTICS1D, GKCOSEXP = 1, 2, 3, 4, 5, 6, 7
+
+
+class BatchEvaluator:
+    """abstract type BatchEvaluator{V} (cachedtensortrain.jl:1) bound to a device target id."""
+
+    def __init__(self, ctx, target_id, localdims):
+        self.ctx = ctx
+        self.id = int(target_id)
+        self.localdims = [int(d) for d in localdims]
+        self.nevals = 0
+
+    def __len__(self):
+        return len(self.localdims)
+
+    # f(indexset) -- batcheval.jl:11-13
+    def __call__(self, *args):
+        if len(args) == 3:
+            return self.batchevaluate(*args)
+        (indexset,) = args
+        return float(self.evaluate_points([indexset])[0])
+
+    def evaluate_points(self, points):
+        pts = as_indexset(points, len(self.localdims))
+        out = np.zeros(pts.shape[0], dtype=np.float64)
+        if pts.shape[0]:
+            self.ctx.check(lib().tci_target_eval(self.ctx.h, self.id, pi(pts), pts.shape[0], pf(out)))
+        self.nevals += pts.shape[0]
+        return out
+
+    def _pi(self, Iset, Jset, M, want_host, want_dev):
+        n = len(self.localdims)
+        nI, nJ = len(Iset), len(Jset)
+        if nI * nJ == 0:  # batcheval.jl:40-42
+            return np.zeros((0,) * (M + 2), order="F"), None, 0.0
+        I, J = as_indexset(Iset), as_indexset(Jset)
+        nl, nr = I.shape[1], J.shape[1]
+        if nl + M + nr != n:
+            raise RuntimeError("Invalid number of central indices")  # tensorci2.jl:307
+        cd = self.localdims[nl:nl + M]
+        Csz = int(np.prod(cd, dtype=np.int64)) if M else 1
+        host = np.zeros(nI * Csz * nJ, dtype=np.float64) if want_host else None
+        dev = C.c_void_p()
+        mx = C.c_double(0.0)
+        self.ctx.check(lib().tci_pi_eval(self.ctx.h, self.id, pi(I), nl, nI, pi(J), nr, nJ, M, pf(host),
+                                         C.byref(dev) if want_dev else None, C.byref(mx)))
+        self.nevals += nI * Csz * nJ
+        if want_host:
+            host = host.reshape((nI, *cd, nJ), order="F")
+        return host, (DeviceMatrix(self.ctx, dev) if want_dev else None), mx.value
+
+    # f(leftindexset, rightindexset, Val(M)) -- batcheval.jl:15-24, cachedtensortrain.jl:219-225
+    def batchevaluate(self, leftindexset, rightindexset, M):
+        return self._pi(leftindexset, rightindexset, M, True, False)[0]
+
+    def batchevaluate_device(self, leftindexset, rightindexset, M):
+        """Pi stays in HBM: returns (DeviceMatrix of shape (nI*prod(d_centre)) x nJ, max|Pi|)."""
+        _, dev, mx = self._pi(leftindexset, rightindexset, M, False, True)
+        return dev, mx
+
+    def __del__(self):
+        try:
+            lib().tci_target_destroy(self.ctx.h, self.id)
+        except Exception:
+            pass
+
+
+class BuiltinTarget(BatchEvaluator):
+    """A device-resident analytic target registered by kind id (include/tci_targets.h)."""
+
+    def __init__(self, kind, params, localdims, ctx=None):
+        ctx = ctx or _lib.default_context()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ld = np.ascontiguousarray(localdims, dtype=np.int64)
+        tid = C.c_int64(0)
+        ctx.check(lib().tci_target_builtin(ctx.h, int(kind), pf(p) if p.size else None, p.size, pi(ld), ld.size,
+                                           C.byref(tid)))
+        super().__init__(ctx, tid.value, ld.tolist())
+        self.kind = kind
+
+
+def makebatchevaluatable(kind, params, localdims, ctx=None):  # batcheval.jl:9
+    return BuiltinTarget(kind, params, localdims, ctx)
+
+
+def _batchevaluate_dispatch(f, localdims, Iset, Jset, M):  # batcheval.jl:67-83
+    if len(Iset) * len(Jset) == 0:
+        return np.zeros((0,) * (M + 2), order="F")
+    if not isinstance(f, BatchEvaluator):
+        raise TypeError("Function `f` is not batch evaluatable")  # tensorci2.jl:726-728
+    return f(Iset, Jset, M)

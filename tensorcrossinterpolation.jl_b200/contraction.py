@@ -1,0 +1,159 @@
+"""Host mirror of src/contraction.jl: the MPO x MPO product as a target (Contraction) and the
+contract() dispatcher (:TCI, :naive, :zipup).  Environments, the batched Pi and the site
+contractions run on the GPU (K5/K6, csrc/mpo.cu)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceMatrix, core_ptrs, lib, pf, pi
+from .batcheval import BatchEvaluator
+from .matrixlu import MatrixLUCI, left, npivots, right, rrlu
+from .tensortrain import TensorTrain
+from .tensorci2 import crossinterpolate2
+
+I64MAX = 2**63 - 1
+
+
+class Contraction(BatchEvaluator):
+    """struct Contraction (contraction.jl:5-62); f (elementwise function) is not supported on device."""
+
+    def __init__(self, a, b, f=None, ctx=None):
+        ctx = ctx or _lib.default_context()
+        if f is not None:
+            raise NotImplementedError("Contraction with an elementwise function f is not available on the device")
+        A = a.sitetensors if hasattr(a, "sitetensors") else list(a)
+        B = b.sitetensors if hasattr(b, "sitetensors") else list(b)
+        if len(A) != len(B):
+            raise ValueError("Tensor trains must have the same length.")  # :41-43
+        for n in range(len(A)):
+            if A[n].shape[2] != B[n].shape[1]:
+                raise RuntimeError(f"Tensor trains must share the identical index at n={n + 1}!")  # :44-48
+        ka, pa = core_ptrs(A)
+        kb, pb = core_ptrs(B)
+        da = np.ascontiguousarray(np.array([c.shape for c in ka], dtype=np.int64))
+        db = np.ascontiguousarray(np.array([c.shape for c in kb], dtype=np.int64))
+        tid = C.c_int64(0)
+        ctx.check(lib().tci_mpo_pair_create(ctx.h, len(ka), pi(da), pa, pi(db), pb, C.byref(tid)))
+        self.sitedims = [[int(x.shape[1]), int(y.shape[2])] for x, y in zip(ka, kb)]
+        super().__init__(ctx, tid.value, [s[0] * s[1] for s in self.sitedims])
+        self.mpo = (ka, kb)
+
+
+def _contractsitetensors(a, b, ctx=None):  # contraction.jl:338-349
+    ctx = ctx or _lib.default_context()
+    a = np.asfortranarray(a, dtype=np.float64)
+    b = np.asfortranarray(b, dtype=np.float64)
+    Da, s1, s2, Dan = a.shape
+    Db, s2b, s3, Dbn = b.shape
+    if s2 != s2b:
+        raise ValueError("shared site dimension mismatch")
+    out = np.zeros(Da * Db * s1 * s3 * Dan * Dbn, dtype=np.float64)
+    ctx.check(lib().tci_contract_naive_site(ctx.h, pf(a), Da, s1, s2, Dan, pf(b), Db, s3, Dbn, pf(out)))
+    return out.reshape((Da * Db, s1, s3, Dan * Dbn), order="F")
+
+
+def _factorize(A, method, tolerance, maxbonddim, leftorthogonal=False, normalizeerror=True, ctx=None):
+    """_factorize (tensortrain.jl:95-137).  A: host matrix or DeviceMatrix.  :LU/:CI on the GPU (K2/K3);
+    :SVD on the host (LAPACK), as in the reference -- recompression is outside the hot path."""
+    reltol, abstol = 1e-14, 0.0
+    if normalizeerror:
+        reltol = tolerance
+    else:
+        abstol = tolerance
+    mr = None if maxbonddim >= I64MAX else maxbonddim
+    if method in ("LU", "CI"):
+        fac = MatrixLUCI(A, abstol=abstol, reltol=reltol, maxrank=mr, leftorthogonal=leftorthogonal, ctx=ctx) \
+            if not isinstance(A, DeviceMatrix) else MatrixLUCI(A, abstol=abstol, reltol=reltol, maxrank=mr,
+                                                               leftorthogonal=leftorthogonal)
+        if method == "CI":
+            return fac.left(), fac.right(), fac.npivot
+        return left(fac.lu), right(fac.lu), npivots(fac.lu)
+    if method == "SVD":
+        if isinstance(A, DeviceMatrix):
+            A = A.to_host()
+        U, S, Vt = np.linalg.svd(A, full_matrices=False)
+        err = np.array([np.sum(S[n + 1:] ** 2) for n in range(len(S))])
+        nerr = err / np.sum(S ** 2)
+
+        def first(cond, default):
+            w = np.nonzero(cond)[0]
+            return int(w[0]) + 1 if w.size else default
+
+        trunci = min(first(err < abstol ** 2, len(err)), first(nerr < reltol ** 2, len(nerr)), maxbonddim)
+        if leftorthogonal:
+            return U[:, :trunci], np.diag(S[:trunci]) @ Vt[:trunci, :], trunci
+        return U[:, :trunci] * S[:trunci], Vt[:trunci, :], trunci
+    raise RuntimeError("Not implemented yet.")
+
+
+def contract_naive(a, b, tolerance=0.0, maxbonddim=I64MAX, ctx=None):  # contraction.jl:351-372
+    tt = TensorTrain([_contractsitetensors(x, y, ctx) for x, y in zip(a.sitetensors, b.sitetensors)])
+    if tolerance > 0 or maxbonddim < I64MAX:
+        raise NotImplementedError("SVD recompression (compress!) is outside the accelerated path (SURVEY 8f-3)")
+    return tt
+
+
+def contract_zipup(A, B, tolerance=1e-12, method="SVD", maxbonddim=I64MAX, ctx=None):
+    """contract_zipup (contraction.jl:442-486)."""
+    ctx = ctx or _lib.default_context()
+    if len(A) != len(B):
+        raise ValueError("Cannot contract tensor trains with different length.")
+    R = np.ones((1, 1, 1), order="F")
+    out = []
+    N = len(A)
+    for n in range(N):
+        a = np.asfortranarray(A[n], dtype=np.float64)
+        b = np.asfortranarray(B[n], dtype=np.float64)
+        chi, Da, Db = R.shape
+        _, s1, s2, Dan = a.shape
+        _, _, s3, Dbn = b.shape
+        Rf = np.asfortranarray(R)
+        if n == N - 1:
+            Cm = np.zeros(chi * s1 * s3 * Dan * Dbn, dtype=np.float64)
+            ctx.check(lib().tci_contract_zipup_site(ctx.h, pf(Rf), chi, Da, Db, pf(a), s1, s2, Dan, pf(b), s3, Dbn,
+                                                    pf(Cm), None))
+            out.append(Cm.reshape((chi, s1, s3, 1), order="F"))
+            break
+        h = C.c_void_p()
+        ctx.check(lib().tci_contract_zipup_site(ctx.h, pf(Rf), chi, Da, Db, pf(a), s1, s2, Dan, pf(b), s3, Dbn, None,
+                                                C.byref(h)))
+        Cdev = DeviceMatrix(ctx, h)
+        lft, rgt, newdim = _factorize(Cdev, method, tolerance=tolerance, maxbonddim=maxbonddim)
+        out.append(np.asfortranarray(lft).reshape((chi, s1, s3, newdim), order="F"))
+        R = np.asfortranarray(rgt).reshape((newdim, Dan, Dbn), order="F")
+    return TensorTrain(out)
+
+
+def contract_TCI(A, B, initialpivots=None, f=None, ctx=None, **kwargs):
+    """contract_TCI (contraction.jl:399-436); initial pivots must be given explicitly or default to
+    the all-ones index (the reference draws them with Julia's rng, :386-397)."""
+    if len(A) != len(B):
+        raise ValueError("Cannot contract tensor trains with different length.")
+    for i in range(len(A)):
+        if A[i].shape[2] != B[i].shape[1]:
+            raise ValueError("Cannot contract tensor trains with non-matching site dimensions.")
+    mp = Contraction(A, B, f=f, ctx=ctx)
+    localdims = mp.localdims
+    if initialpivots is None:
+        initialpivots = [[1] * len(localdims)]
+    tci, ranks, errors = crossinterpolate2(mp, localdims, initialpivots, **kwargs)
+    cores = [t.reshape((t.shape[0], sd[0], sd[1], t.shape[-1]), order="F") for t, sd in
+             zip(tci.sitetensors, mp.sitedims)]
+    return TensorTrain(cores)
+
+
+def contract(A, B, algorithm="TCI", tolerance=1e-12, maxbonddim=I64MAX, f=None, **kwargs):  # :515-542
+    if algorithm == "TCI":
+        return contract_TCI(A, B, tolerance=tolerance, maxbonddim=maxbonddim, f=f, **kwargs)
+    if algorithm == "naive":
+        if f is not None:
+            raise RuntimeError("Naive contraction implementation cannot contract matrix product with a function. "
+                               "Use algorithm=:TCI instead.")
+        return contract_naive(A, B, tolerance=tolerance, maxbonddim=maxbonddim)
+    if algorithm == "zipup":
+        if f is not None:
+            raise RuntimeError("Zipup contraction implementation cannot contract matrix product with a function. "
+                               "Use algorithm=:TCI instead.")
+        return contract_zipup(A, B, tolerance=tolerance, maxbonddim=maxbonddim, **kwargs)
+    raise ValueError(f"Unknown algorithm {algorithm}.")

@@ -1,0 +1,229 @@
+// dgemm.cu -- FP64 GEMM on the DFMA pipe: C = alpha * op(A) * op(B) + beta * C.
+//
+// Replaces the OpenBLAS dgemm calls behind matrixluci.jl:41,45 (colmatrix/rowmatrix),
+// cachedtensortrain.jl:207,212, contraction.jl:92 (_contract) on the hot path.
+// tcgen05 has no FP64 path; B200's FP64 peak is the DFMA pipe (64 FMA/clk/SM), so this
+// is a shared-memory tiled, register blocked kernel: BMxBNx16 tiles, 256 threads, each
+// thread an (BM/16)x(BN/16) micro tile made of 2-wide strips 32 apart so that every
+// LDS.128 of a quarter warp is conflict free and C stores are 256 B contiguous.
+// The next k-tile is prefetched into registers while the current one is consumed.
+#include "tci_internal.h"
+
+#define GK 16
+
+template <int BM, int BN, bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+    k_dgemm(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
+            const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
+            i64 strideC, const i64 *__restrict__ offA, const i64 *__restrict__ offB)
+{
+    constexpr int TM = BM / 16, TN = BN / 16;       // micro tile
+    constexpr int SM = TM / 2, SN = TN / 2;         // number of 2-wide strips
+    constexpr int LA = BM * GK / 256, LB = BN * GK / 256; // elements each thread stages per tile
+    __shared__ __align__(16) double As[GK][BM];
+    __shared__ __align__(16) double Bs[GK][BN];
+
+    A += strideA * blockIdx.z + (offA ? offA[blockIdx.z] : 0);
+    B += strideB * blockIdx.z + (offB ? offB[blockIdx.z] : 0);
+    C += strideC * blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const i64 m0 = (i64)blockIdx.x * BM, n0 = (i64)blockIdx.y * BN;
+
+    double acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+
+    double ra[LA], rb[LB];
+    auto gload = [&](i64 k0) {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            int e = tid + q * 256;
+            int mm, kk;
+            if (!TA) { // A is M x K: m contiguous
+                mm = e % BM;
+                kk = e / BM;
+            } else { // A is K x M: k contiguous
+                kk = e % GK;
+                mm = e / GK;
+            }
+            i64 gm = m0 + mm, gk = k0 + kk;
+            ra[q] = (gm < M && gk < K) ? (TA ? A[gk + lda * gm] : A[gm + lda * gk]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            int e = tid + q * 256;
+            int nn, kk;
+            if (!TB) { // B is K x N: k contiguous
+                kk = e % GK;
+                nn = e / GK;
+            } else { // B is N x K: n contiguous
+                nn = e % BN;
+                kk = e / BN;
+            }
+            i64 gn = n0 + nn, gk = k0 + kk;
+            rb[q] = (gn < N && gk < K) ? (TB ? B[gn + ldb * gk] : B[gk + ldb * gn]) : 0.0;
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            int e = tid + q * 256;
+            int mm = TA ? e / GK : e % BM, kk = TA ? e % GK : e / BM;
+            As[kk][mm] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            int e = tid + q * 256;
+            int nn = TB ? e % BN : e / GK, kk = TB ? e / BN : e % GK;
+            Bs[kk][nn] = rb[q];
+        }
+    };
+
+    gload(0);
+    for (i64 k0 = 0; k0 < K; k0 += GK) {
+        __syncthreads();
+        sstore();
+        __syncthreads();
+        if (k0 + GK < K) gload(k0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double av[TM], bv[TN];
+#pragma unroll
+            for (int s = 0; s < SM; ++s) {
+                double2 t = *reinterpret_cast<const double2 *>(&As[kk][2 * tx + 32 * s]);
+                av[2 * s] = t.x;
+                av[2 * s + 1] = t.y;
+            }
+#pragma unroll
+            for (int s = 0; s < SN; ++s) {
+                double2 t = *reinterpret_cast<const double2 *>(&Bs[kk][2 * ty + 32 * s]);
+                bv[2 * s] = t.x;
+                bv[2 * s + 1] = t.y;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int sj = 0; sj < SN; ++sj)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            i64 gn = n0 + 2 * ty + 32 * sj + jj;
+            if (gn >= N) continue;
+#pragma unroll
+            for (int si = 0; si < SM; ++si)
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    i64 gm = m0 + 2 * tx + 32 * si + ii;
+                    if (gm >= M) continue;
+                    double v = alpha * acc[2 * si + ii][2 * sj + jj];
+                    double *c = C + gm + ldc * gn;
+                    *c = (beta == 0.0) ? v : fma(beta, *c, v);
+                }
+        }
+}
+
+template <int BM, int BN>
+static void launch_dgemm(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                         i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, i64 batch,
+                         const i64 *offA, const i64 *offB)
+{
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch);
+    if (!tA && !tB)
+        k_dgemm<BM, BN, false, false><<<grid, 256, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else if (tA && !tB)
+        k_dgemm<BM, BN, true, false><<<grid, 256, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else if (!tA && tB)
+        k_dgemm<BM, BN, false, true><<<grid, 256, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else
+        k_dgemm<BM, BN, true, true><<<grid, 256, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    ctx->launches++;
+}
+
+__global__ void k_scale(double *C, i64 M, i64 N, i64 ldc, i64 strideC, double beta)
+{
+    double *c = C + strideC * blockIdx.z;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < M * N; e += (i64)gridDim.x * blockDim.x) {
+        i64 i = e % M, j = e / M;
+        c[i + ldc * j] = beta == 0.0 ? 0.0 : beta * c[i + ldc * j];
+    }
+}
+
+int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                          i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB)
+{
+    if (M <= 0 || N <= 0 || batch <= 0) return TCI_OK;
+    if (batch > 65535) { // gridDim.z limit
+        for (i64 b0 = 0; b0 < batch; b0 += 65535) {
+            i64 nb = std::min<i64>(65535, batch - b0);
+            int rc = dgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A + strideA * b0, lda, strideA,
+                                           B + strideB * b0, ldb, strideB, beta, C + strideC * b0, ldc, strideC, nb,
+                                           offA ? offA + b0 : nullptr, offB ? offB + b0 : nullptr);
+            if (rc) return rc;
+        }
+        return TCI_OK;
+    }
+    if (K <= 0) {
+        dim3 grid((unsigned)std::min<i64>((M * N + 255) / 256, 1024), 1, (unsigned)batch);
+        k_scale<<<grid, 256, 0, ctx->stream>>>(C, M, N, ldc, strideC, beta);
+        ctx->launches++;
+    } else {
+        i64 big_ctas = ((M + 127) / 128) * ((N + 127) / 128) * batch;
+        if (big_ctas >= ctx->sm_count && M >= 96 && N >= 96)
+            launch_dgemm<128, 128>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                   strideC, batch, offA, offB);
+        else
+            launch_dgemm<64, 64>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                                 batch, offA, offB);
+    }
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
+int dgemm_dev_batched(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                      i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc, i64 strideC,
+                      i64 batch)
+{
+    return dgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+                                 batch, nullptr, nullptr);
+}
+
+int dgemm_dev(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+              const double *B, i64 ldb, double beta, double *C, i64 ldc)
+{
+    return dgemm_dev_batched(ctx, tA, tB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1);
+}
+
+extern "C" int tci_dgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                              const double *A, const double *B, double beta, double *C)
+{
+    TCI_ENTER(ctx);
+    if (M < 0 || N < 0 || K < 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_dgemm_host: negative size");
+    if (M * N == 0) return TCI_OK;
+    const i64 lda = transA ? K : M, ldb = transB ? N : K;
+    DevBuf<double> dA(ctx), dB(ctx), dC(ctx);
+    {
+        StageTimer tm(ctx, ST_H2D);
+        TCI_CUDA(ctx, dA.upload(A, (size_t)(M * K)));
+        TCI_CUDA(ctx, dB.upload(B, (size_t)(K * N)));
+        if (beta != 0.0)
+            TCI_CUDA(ctx, dC.upload(C, (size_t)(M * N)));
+        else
+            TCI_CUDA(ctx, dC.alloc((size_t)(M * N)));
+    }
+    {
+        StageTimer tm(ctx, ST_GEMM);
+        int rc = dgemm_dev(ctx, transA != 0, transB != 0, M, N, K, alpha, dA.p, lda ? lda : 1, dB.p, ldb ? ldb : 1,
+                           beta, dC.p, M);
+        if (rc) return rc;
+    }
+    StageTimer tm(ctx, ST_D2H);
+    TCI_CUDA(ctx, cudaMemcpyAsync(C, dC.p, M * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
+}

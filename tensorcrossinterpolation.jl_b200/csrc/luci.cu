@@ -1,0 +1,191 @@
+// luci.cu -- K3: left(luci) / right(luci) of MatrixLUCI (matrixluci.jl:40-84) from the
+// device-resident factorisation: unit-triangular TRSM (blocked: 32-wide diagonal solves
+// in shared memory + DGEMM updates), triangular products as DGEMM, and the final row /
+// column un-permutation (matrixluci.jl:55,66; matrixlu.jl:374-392).
+#include "tci_internal.h"
+
+int lu_extract(tci_lu *lu, double *dL, i64 ldl, double *dU, i64 ldu); // rrlu.cu
+
+#define TB_NB 32
+#define TB_THREADS 128
+
+// X[:, 0:nb] * T = X[:, 0:nb] with T (nb x nb) unit lower triangular:
+// x_j -= sum_{k>j} x_k T[k,j], j = nb-1 .. 0.  One thread per row of X.
+__global__ void __launch_bounds__(TB_THREADS)
+    k_trsm_rl_block(double *__restrict__ X, i64 rows, i64 ldx, const double *__restrict__ T, i64 ldt, int nb)
+{
+    __shared__ double Ts[TB_NB][TB_NB + 1];
+    __shared__ double xs[TB_NB][TB_THREADS];
+    for (int e = threadIdx.x; e < nb * nb; e += TB_THREADS) Ts[e % nb][e / nb] = T[(e % nb) + ldt * (e / nb)];
+    __syncthreads();
+    i64 row = blockIdx.x * (i64)TB_THREADS + threadIdx.x;
+    if (row >= rows) return;
+    for (int j = 0; j < nb; ++j) xs[j][threadIdx.x] = X[row + ldx * j];
+    for (int j = nb - 1; j >= 0; --j) {
+        double acc = xs[j][threadIdx.x];
+        for (int k = j + 1; k < nb; ++k) acc = fma(-xs[k][threadIdx.x], Ts[k][j], acc);
+        xs[j][threadIdx.x] = acc;
+    }
+    for (int j = 0; j < nb; ++j) X[row + ldx * j] = xs[j][threadIdx.x];
+}
+
+// T * X[0:nb, :] = X[0:nb, :] with T (nb x nb) unit upper triangular:
+// x_i -= sum_{k>i} T[i,k] x_k, i = nb-1 .. 0.  One thread per column of X.
+__global__ void __launch_bounds__(TB_THREADS)
+    k_trsm_lu_block(double *__restrict__ X, i64 cols, i64 ldx, const double *__restrict__ T, i64 ldt, int nb)
+{
+    __shared__ double Ts[TB_NB][TB_NB + 1];
+    __shared__ double xs[TB_NB][TB_THREADS];
+    for (int e = threadIdx.x; e < nb * nb; e += TB_THREADS) Ts[e % nb][e / nb] = T[(e % nb) + ldt * (e / nb)];
+    __syncthreads();
+    i64 col = blockIdx.x * (i64)TB_THREADS + threadIdx.x;
+    if (col >= cols) return;
+    for (int i = 0; i < nb; ++i) xs[i][threadIdx.x] = X[i + ldx * col];
+    for (int i = nb - 1; i >= 0; --i) {
+        double acc = xs[i][threadIdx.x];
+        for (int k = i + 1; k < nb; ++k) acc = fma(-Ts[i][k], xs[k][threadIdx.x], acc);
+        xs[i][threadIdx.x] = acc;
+    }
+    for (int i = 0; i < nb; ++i) X[i + ldx * col] = xs[i][threadIdx.x];
+}
+
+// out[perm[i], :] = src[i, :]  (rows)   or   out[:, perm[q]] = src[:, q]  (cols)
+__global__ void k_scatter_rows(const double *__restrict__ src, i64 lds, i64 m, i64 r, const i64 *__restrict__ perm,
+                               double *__restrict__ out, i64 ldo, int identity_top)
+{
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= m * r) return;
+    i64 i = e % m, c = e / m;
+    double v = (identity_top && i < r) ? (i == c ? 1.0 : 0.0) : src[i + lds * c];
+    out[perm[i] + ldo * c] = v;
+}
+__global__ void k_scatter_cols(const double *__restrict__ src, i64 lds, i64 r, i64 n, const i64 *__restrict__ perm,
+                               double *__restrict__ out, i64 ldo, int identity_left)
+{
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= r * n) return;
+    i64 i = e % r, q = e / r;
+    double v = (identity_left && q < r) ? (i == q ? 1.0 : 0.0) : src[i + lds * q];
+    out[i + ldo * perm[q]] = v;
+}
+
+static int finish(tci_ctx *ctx, tci_dmat *res, double *out_host, tci_dmat **out_dev)
+{
+    if (out_host && res->m * res->n > 0) {
+        StageTimer tm(ctx, ST_D2H);
+        TCI_CUDA(ctx, cudaMemcpy2DAsync(out_host, res->m * sizeof(double), res->p, res->ld * sizeof(double),
+                                        res->m * sizeof(double), res->n, cudaMemcpyDeviceToHost, ctx->stream));
+        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (out_dev)
+        *out_dev = res;
+    else
+        tci_dmat_destroy(res);
+    return TCI_OK;
+}
+
+extern "C" int tci_luci_left(tci_lu *lu, double *out_host, tci_dmat **out_dev)
+{
+    if (!lu) return TCI_ERR_ARG;
+    tci_ctx *ctx = lu->ctx;
+    TCI_ENTER(ctx);
+    if (out_dev) *out_dev = nullptr;
+    const i64 m = lu->m, r = lu->r;
+    tci_dmat *res = nullptr;
+    int rc = dmat_alloc(ctx, m, r, &res);
+    if (rc) return rc;
+    if (r == 0) return finish(ctx, res, out_host, out_dev);
+    {
+        StageTimer tm(ctx, ST_LUCI);
+        DevBuf<double> L(ctx), U(ctx), Y(ctx);
+        TCI_CUDA(ctx, L.alloc((size_t)(m * r)));
+        if (lu->leftorthogonal) { // colstimespivotinv  matrixluci.jl:48-57
+            rc = lu_extract(lu, L.p, m, nullptr, 0);
+            const i64 rows = m - r;
+            double *X = L.p + r;
+            for (i64 j1 = r; j1 > 0 && !rc && rows > 0; j1 -= TB_NB) {
+                const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
+                if (j1 < r) // X[:, j0:j1] -= X[:, j1:r] * L11[j1:r, j0:j1]
+                    rc = dgemm_dev(ctx, false, false, rows, nb, r - j1, -1.0, X + m * j1, m, L.p + j1 + m * j0, m, 1.0,
+                                   X + m * j0, m);
+                k_trsm_rl_block<<<(unsigned)((rows + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
+                    X + m * j0, rows, m, L.p + j0 + m * j0, m, (int)nb);
+                ctx->launches++;
+            }
+            if (!rc) {
+                k_scatter_rows<<<(unsigned)((m * r + 255) / 256), 256, 0, ctx->stream>>>(L.p, m, m, r, lu->d_rowperm,
+                                                                                        res->p, res->ld, 1);
+                ctx->launches++;
+            }
+        } else { // colmatrix  matrixluci.jl:40-42 : left(lu) * U[:, 1:r]
+            TCI_CUDA(ctx, U.alloc((size_t)(r * lu->n)));
+            TCI_CUDA(ctx, Y.alloc((size_t)(m * r)));
+            rc = lu_extract(lu, L.p, m, U.p, r);
+            if (!rc) rc = dgemm_dev(ctx, false, false, m, r, r, 1.0, L.p, m, U.p, r, 0.0, Y.p, m);
+            if (!rc) {
+                k_scatter_rows<<<(unsigned)((m * r + 255) / 256), 256, 0, ctx->stream>>>(Y.p, m, m, r, lu->d_rowperm,
+                                                                                        res->p, res->ld, 0);
+                ctx->launches++;
+            }
+        }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "luci_left launch failed");
+    }
+    if (rc) {
+        tci_dmat_destroy(res);
+        return rc;
+    }
+    return finish(ctx, res, out_host, out_dev);
+}
+
+extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
+{
+    if (!lu) return TCI_ERR_ARG;
+    tci_ctx *ctx = lu->ctx;
+    TCI_ENTER(ctx);
+    if (out_dev) *out_dev = nullptr;
+    const i64 m = lu->m, n = lu->n, r = lu->r;
+    tci_dmat *res = nullptr;
+    int rc = dmat_alloc(ctx, r, n, &res);
+    if (rc) return rc;
+    if (r == 0) return finish(ctx, res, out_host, out_dev);
+    {
+        StageTimer tm(ctx, ST_LUCI);
+        DevBuf<double> L(ctx), U(ctx), Y(ctx);
+        TCI_CUDA(ctx, U.alloc((size_t)(r * n)));
+        if (lu->leftorthogonal) { // rowmatrix  matrixluci.jl:44-46 : L[1:r, :] * right(lu)
+            TCI_CUDA(ctx, L.alloc((size_t)(m * r)));
+            TCI_CUDA(ctx, Y.alloc((size_t)(r * n)));
+            rc = lu_extract(lu, L.p, m, U.p, r);
+            if (!rc) rc = dgemm_dev(ctx, false, false, r, n, r, 1.0, L.p, m, U.p, r, 0.0, Y.p, r);
+            if (!rc) {
+                k_scatter_cols<<<(unsigned)((r * n + 255) / 256), 256, 0, ctx->stream>>>(Y.p, r, r, n, lu->d_colperm,
+                                                                                        res->p, res->ld, 0);
+                ctx->launches++;
+            }
+        } else { // pivotinvtimesrows  matrixluci.jl:59-68 : U11 \ U12
+            rc = lu_extract(lu, nullptr, 0, U.p, r);
+            const i64 cols = n - r;
+            double *X = U.p + r * r;
+            for (i64 i1 = r; i1 > 0 && !rc && cols > 0; i1 -= TB_NB) {
+                const i64 i0 = std::max<i64>(0, i1 - TB_NB), nb = i1 - i0;
+                if (i1 < r) // X[i0:i1, :] -= U11[i0:i1, i1:r] * X[i1:r, :]
+                    rc = dgemm_dev(ctx, false, false, nb, cols, r - i1, -1.0, U.p + i0 + r * i1, r, X + i1, r, 1.0,
+                                   X + i0, r);
+                k_trsm_lu_block<<<(unsigned)((cols + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
+                    X + i0, cols, r, U.p + i0 + r * i0, r, (int)nb);
+                ctx->launches++;
+            }
+            if (!rc) {
+                k_scatter_cols<<<(unsigned)((r * n + 255) / 256), 256, 0, ctx->stream>>>(U.p, r, r, n, lu->d_colperm,
+                                                                                        res->p, res->ld, 1);
+                ctx->launches++;
+            }
+        }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "luci_right launch failed");
+    }
+    if (rc) {
+        tci_dmat_destroy(res);
+        return rc;
+    }
+    return finish(ctx, res, out_host, out_dev);
+}

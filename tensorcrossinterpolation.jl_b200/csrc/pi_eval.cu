@@ -1,0 +1,355 @@
+// pi_eval.cu -- K1: batched evaluation of the Pi / T tensors for analytic targets
+// (replaces the triple loop of batcheval.jl:50-58 and the max-abs pass of
+// util.jl:1-10, fused), plus the tci_pi_eval / tci_target_eval entry points.
+//
+// Layout (Appendix A.1 of SURVEY.md): out[i + nI*c + ld*j] = f(I_i ++ c ++ J_j),
+// centre multi-index c enumerated first-index-fastest.  The kernel is bound by
+// the 8 B/evaluation HBM write for cheap targets: every thread owns two
+// consecutive rows (one 16 B store) and walks a tile of columns, so a warp writes
+// 512 contiguous bytes per column.
+#include "tci_internal.h"
+
+#define PI_THREADS 256
+#define PI_TCOLS 32
+
+// per-index state: st[k * count + q] = state_k of multi-index q over sites [site0, site0+len)
+__global__ void k_states(tci_analytic_t t, const i64 *__restrict__ idx, int len, i64 count, int site0, int from_init,
+                         double *__restrict__ st)
+{
+    i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    double s[TCI_MAX_STATE];
+    if (from_init)
+        tci_target_init(&t, s);
+    else
+        for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = 0.0;
+    for (int k = 0; k < len; ++k) tci_target_accum(&t, site0 + k, idx[(i64)len * q + k], s);
+    for (int k = 0; k < t.nstate; ++k) st[(i64)k * count + q] = s[k];
+}
+
+// centre combos: c -> (sigma_1 fastest, ...), state over sites [site0, site0+M)
+__global__ void k_centre_states(tci_analytic_t t, int M, i64 C, int site0, double *__restrict__ st,
+                                int *__restrict__ csig /* M x C, nullable */)
+{
+    i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s[TCI_MAX_STATE];
+    for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = 0.0;
+    i64 rem = c;
+    for (int k = 0; k < M; ++k) {
+        i64 d = t.localdims[site0 + k];
+        i64 sig = rem % d + 1;
+        rem /= d;
+        tci_target_accum(&t, site0 + k, sig, s);
+        if (csig) csig[(i64)k * C + c] = (int)sig;
+    }
+    for (int k = 0; k < t.nstate; ++k) st[(i64)k * C + c] = s[k];
+}
+
+__device__ __forceinline__ unsigned long long absbits(double v)
+{ // |v| as an ordered integer; NaN sorts above +Inf, so an integer max propagates NaN like Julia's max
+    return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
+__device__ __forceinline__ void block_max_commit(unsigned long long mx, unsigned long long *gmax)
+{
+    __shared__ unsigned long long wm[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) wm[w] = mx;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        mx = l < nw ? wm[l] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = other > mx ? other : mx;
+        }
+        if (l == 0 && mx) atomicMax(gmax, mx);
+    }
+}
+
+// Exact targets: state(I ++ c ++ J) = rowstate + centrestate + colstate, bit-identical to
+// the sequential definition because all partial sums are exact.
+template <int NS>
+__global__ void __launch_bounds__(PI_THREADS)
+    k_pi_exact(tci_analytic_t t, const double *__restrict__ rs, i64 nI, const double *__restrict__ cs, i64 C,
+               const double *__restrict__ js, i64 nJ, double *__restrict__ out, i64 ld, unsigned long long *gmax)
+{
+    __shared__ double colst[NS][PI_TCOLS];
+    __shared__ i64 coloff[PI_TCOLS];
+    const i64 ncols = C * nJ;
+    const i64 q0 = (i64)blockIdx.y * PI_TCOLS;
+    if (threadIdx.x < PI_TCOLS) {
+        i64 q = q0 + threadIdx.x;
+        if (q < ncols) {
+            i64 c = q % C, j = q / C;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) colst[k][threadIdx.x] = TCI_ADD(cs[(i64)k * C + c], js[(i64)k * nJ + j]);
+            coloff[threadIdx.x] = nI * c + ld * j;
+        }
+    }
+    __syncthreads();
+    const i64 r0 = ((i64)blockIdx.x * PI_THREADS + threadIdx.x) * 2;
+    unsigned long long mx = 0ull;
+    if (r0 < nI) {
+        const bool two = r0 + 1 < nI;
+        double a0[NS], a1[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            a0[k] = rs[(i64)k * nI + r0];
+            a1[k] = two ? rs[(i64)k * nI + r0 + 1] : 0.0;
+        }
+        const int nq = (int)(ncols - q0 < PI_TCOLS ? ncols - q0 : PI_TCOLS);
+#pragma unroll 4
+        for (int qq = 0; qq < nq; ++qq) {
+            double s0[NS], s1[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                double cst = colst[k][qq];
+                s0[k] = TCI_ADD(a0[k], cst);
+                s1[k] = TCI_ADD(a1[k], cst);
+            }
+            double v0 = tci_target_finalize(&t, s0);
+            unsigned long long b0 = absbits(v0);
+            mx = b0 > mx ? b0 : mx;
+            double *dst = out + coloff[qq] + r0;
+            if (two) {
+                double v1 = tci_target_finalize(&t, s1);
+                unsigned long long b1 = absbits(v1);
+                mx = b1 > mx ? b1 : mx;
+                if ((((size_t)dst) & 15) == 0)
+                    __stcs(reinterpret_cast<double2 *>(dst), make_double2(v0, v1));
+                else {
+                    dst[0] = v0;
+                    dst[1] = v1;
+                }
+            } else
+                dst[0] = v0;
+        }
+    }
+    block_max_commit(mx, gmax);
+}
+
+// Non-exact targets: the state of row i is the sequential prefix over the left sites;
+// every element continues the accumulation over the centre and right sites in site order,
+// which is exactly the scalar definition tci_target_eval.
+__global__ void __launch_bounds__(PI_THREADS)
+    k_pi_sequential(tci_analytic_t t, const double *__restrict__ rs, i64 nI, int nl, int M, i64 C,
+                    const int *__restrict__ csig, const i64 *__restrict__ J, int nr, i64 nJ, double *__restrict__ out,
+                    i64 ld, unsigned long long *gmax)
+{
+    const i64 ncols = C * nJ;
+    const i64 q0 = (i64)blockIdx.y * PI_TCOLS;
+    const i64 r = (i64)blockIdx.x * PI_THREADS + threadIdx.x;
+    unsigned long long mx = 0ull;
+    if (r < nI) {
+        double a[TCI_MAX_STATE];
+        for (int k = 0; k < TCI_MAX_STATE; ++k) a[k] = k < t.nstate ? rs[(i64)k * nI + r] : 0.0;
+        const int nq = (int)(ncols - q0 < PI_TCOLS ? ncols - q0 : PI_TCOLS);
+        for (int qq = 0; qq < nq; ++qq) {
+            i64 q = q0 + qq, c = q % C, j = q / C;
+            double s[TCI_MAX_STATE];
+            for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = a[k];
+            for (int k = 0; k < M; ++k) tci_target_accum(&t, nl + k, csig[(i64)k * C + c], s);
+            for (int k = 0; k < nr; ++k) tci_target_accum(&t, nl + M + k, J[(i64)nr * j + k], s);
+            double v = tci_target_finalize(&t, s);
+            unsigned long long b = absbits(v);
+            mx = b > mx ? b : mx;
+            out[nI * c + ld * j + r] = v;
+        }
+    }
+    block_max_commit(mx, gmax);
+}
+
+template <int NS>
+static void launch_exact(tci_ctx *ctx, const tci_analytic_t &an, const double *rs, i64 nI, const double *cs, i64 C,
+                         const double *js, i64 nJ, double *out, i64 ld, unsigned long long *gmax)
+{
+    dim3 grid((unsigned)((nI + 2 * PI_THREADS - 1) / (2 * PI_THREADS)), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
+    k_pi_exact<NS><<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs, nI, cs, C, js, nJ, out, ld, gmax);
+    ctx->launches++;
+}
+
+int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                     tci_dmat *out, unsigned long long *d_maxbits)
+{
+    const tci_analytic_t &an = t.an;
+    const int NS = an.nstate;
+    i64 C = 1;
+    for (i64 k = 0; k < M; ++k) C *= t.localdims[nl + k];
+    const bool exact = tci_target_exact(an.kind) != 0;
+    DevBuf<double> rs(ctx), cs(ctx), js(ctx);
+    DevBuf<int> csig(ctx);
+    TCI_CUDA(ctx, rs.alloc((size_t)NS * nI));
+    TCI_CUDA(ctx, cs.alloc((size_t)NS * C));
+    const int TB = 128;
+    k_states<<<(unsigned)((nI + TB - 1) / TB), TB, 0, ctx->stream>>>(an, dI, (int)nl, nI, 0, 1, rs.p);
+    ctx->launches++;
+    if (!exact) TCI_CUDA(ctx, csig.alloc((size_t)(M > 0 ? M : 1) * C));
+    k_centre_states<<<(unsigned)((C + TB - 1) / TB), TB, 0, ctx->stream>>>(an, (int)M, C, (int)nl, cs.p,
+                                                                           exact ? nullptr : csig.p);
+    ctx->launches++;
+    if (exact) {
+        TCI_CUDA(ctx, js.alloc((size_t)NS * nJ));
+        k_states<<<(unsigned)((nJ + TB - 1) / TB), TB, 0, ctx->stream>>>(an, dJ, (int)nr, nJ, (int)(nl + M), 0, js.p);
+        ctx->launches++;
+        switch (NS) {
+        case 1: launch_exact<1>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        case 2: launch_exact<2>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        case 3: launch_exact<3>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        case 4: launch_exact<4>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        case 5: launch_exact<5>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        case 6: launch_exact<6>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
+        default: return tci_fail(ctx, TCI_ERR_ARG, "target has an unsupported number of state sums");
+        }
+    } else {
+        dim3 grid((unsigned)((nI + PI_THREADS - 1) / PI_THREADS), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
+        k_pi_sequential<<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs.p, nI, (int)nl, (int)M, C, csig.p, dJ, (int)nr,
+                                                              nJ, out->p, out->ld, d_maxbits);
+        ctx->launches++;
+    }
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
+// max |x| over an m x n matrix (for targets whose Pi comes out of a GEMM)
+__global__ void k_maxabs(const double *__restrict__ p, i64 m, i64 n, i64 ld, unsigned long long *gmax)
+{
+    unsigned long long mx = 0ull;
+    i64 total = m * n;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        i64 i = e % m, j = e / m;
+        unsigned long long b = absbits(p[i + ld * j]);
+        mx = b > mx ? b : mx;
+    }
+    block_max_commit(mx, gmax);
+}
+
+int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits)
+{
+    i64 total = m * n;
+    unsigned blocks = (unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8);
+    k_maxabs<<<blocks ? blocks : 1, 256, 0, ctx->stream>>>(p, m, n, ld, d_maxbits);
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
+extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                           int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs)
+{
+    TCI_ENTER(ctx);
+    if (out_dev) *out_dev = nullptr;
+    auto it = ctx->targets.find(target_id);
+    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    TargetDev &t = *it->second;
+    if (nI < 0 || nJ < 0 || nl < 0 || nr < 0 || M < 0) return tci_fail(ctx, TCI_ERR_ARG, "negative size");
+    if (nI * nJ == 0) { // batcheval.jl:40-42: empty result, not an error
+        if (maxabs) *maxabs = 0.0;
+        if (out_dev) return dmat_alloc(ctx, 0, 0, out_dev);
+        return TCI_OK;
+    }
+    if (nl + M + nr != t.nsites) return tci_fail(ctx, TCI_ERR_CENTRE, "Invalid number of central indices");
+    if ((nl > 0 && !I) || (nr > 0 && !J)) return tci_fail(ctx, TCI_ERR_ARG, "index sets missing");
+    i64 C = 1;
+    for (i64 k = 0; k < M; ++k) C *= t.localdims[nl + k];
+
+    DevBuf<i64> dI(ctx), dJ(ctx);
+    DevBuf<unsigned long long> dmax(ctx);
+    {
+        StageTimer tm(ctx, ST_H2D);
+        TCI_CUDA(ctx, dI.upload(I, (size_t)(nl * nI)));
+        TCI_CUDA(ctx, dJ.upload(J, (size_t)(nr * nJ)));
+        TCI_CUDA(ctx, dmax.alloc(1));
+        TCI_CUDA(ctx, cudaMemsetAsync(dmax.p, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    tci_dmat *out = nullptr;
+    int rc = dmat_alloc(ctx, nI * C, nJ, &out);
+    if (rc) return rc;
+    {
+        StageTimer tm(ctx, ST_PI);
+        switch (t.kind) {
+        case 0: rc = pi_eval_analytic(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, dmax.p); break;
+        case 1:
+            rc = pi_eval_tt(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out);
+            if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
+            break;
+        default:
+            rc = pi_eval_mpo(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out);
+            if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
+            break;
+        }
+    }
+    if (rc) {
+        tci_dmat_destroy(out);
+        return rc;
+    }
+    {
+        StageTimer tm(ctx, ST_D2H);
+        if (maxabs) {
+            unsigned long long bits = 0;
+            TCI_CUDA(ctx, cudaMemcpyAsync(&bits, dmax.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+            TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            double v;
+            memcpy(&v, &bits, sizeof(v));
+            *maxabs = v;
+        }
+        if (out_host) {
+            TCI_CUDA(ctx, cudaMemcpy2DAsync(out_host, out->m * sizeof(double), out->p, out->ld * sizeof(double),
+                                            out->m * sizeof(double), out->n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (out_dev)
+        *out_dev = out;
+    else
+        tci_dmat_destroy(out);
+    return TCI_OK;
+}
+
+// ---- scalar evaluation f(x) for a batch of full multi-indices ---------------
+__global__ void k_eval_points(tci_analytic_t t, const i64 *__restrict__ idx, i64 count, double *__restrict__ out)
+{
+    i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    out[q] = tci_target_eval(&t, idx + (i64)t.nsites * q);
+}
+
+int target_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out);  // tt.cu
+int target_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out); // mpo.cu
+
+int target_eval_dev(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out)
+{
+    if (count == 0) return TCI_OK;
+    switch (t.kind) {
+    case 0:
+        k_eval_points<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t.an, d_idx, count, d_out);
+        ctx->launches++;
+        TCI_CUDA(ctx, cudaGetLastError());
+        return TCI_OK;
+    case 1: return target_eval_tt(ctx, t, d_idx, count, d_out);
+    default: return target_eval_mpo(ctx, t, d_idx, count, d_out);
+    }
+}
+
+extern "C" int tci_target_eval(tci_ctx *ctx, int64_t target_id, const int64_t *idx, int64_t count, double *out)
+{
+    TCI_ENTER(ctx);
+    auto it = ctx->targets.find(target_id);
+    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    if (count <= 0) return TCI_OK;
+    TargetDev &t = *it->second;
+    DevBuf<i64> d_idx(ctx);
+    DevBuf<double> d_out(ctx);
+    TCI_CUDA(ctx, d_idx.upload(idx, (size_t)(t.nsites * count)));
+    TCI_CUDA(ctx, d_out.alloc((size_t)count));
+    int rc = target_eval_dev(ctx, t, d_idx.p, count, d_out.p);
+    if (rc) return rc;
+    TCI_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
+}

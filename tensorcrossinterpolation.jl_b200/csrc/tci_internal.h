@@ -1,0 +1,173 @@
+// tci_internal.h -- shared declarations of libtci_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tci_b200.h"
+#include "../../include/tci_targets.h"
+
+typedef int64_t i64;
+
+enum { ST_PI = 0, ST_RRLU = 1, ST_LUCI = 2, ST_ENV = 3, ST_GSEARCH = 4, ST_GEMM = 5, ST_H2D = 6, ST_D2H = 7, ST_COUNT = 8 };
+
+struct tci_dmat {
+    tci_ctx *ctx = nullptr;
+    double *p = nullptr;
+    i64 m = 0, n = 0, ld = 0;
+    bool owned = true;
+};
+
+struct TargetDev {
+    int kind = 0; // 0 analytic, 1 TT, 2 MPO pair
+    i64 nsites = 0;
+    std::vector<i64> localdims;
+    // analytic
+    tci_analytic_t an{};     // params/localdims are DEVICE pointers
+    double *d_params = nullptr;
+    i64 *d_localdims = nullptr;
+    // TT: cores on device, dims (Dl, d, Dr)
+    std::vector<double *> cores;
+    std::vector<i64> dl, d, dr;
+    // MPO pair
+    std::vector<double *> A, B;
+    std::vector<i64> adl, as1, as2, adr, bdl, bs1, bs2, bdr;
+};
+
+struct tci_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::mutex mu;
+    bool busy = false;
+    i64 launches = 0;
+    double stage_ms[ST_COUNT] = {0};
+    std::map<i64, std::unique_ptr<TargetDev>> targets;
+    i64 next_target = 1;
+    // reusable scratch for the rrLU persistent kernel
+    void *rr_scratch = nullptr;
+    size_t rr_scratch_bytes = 0;
+    unsigned *rr_barrier = nullptr;
+};
+
+struct tci_lu {
+    tci_ctx *ctx = nullptr;
+    tci_dmat *A = nullptr; // factorised in place (rows physically permuted, columns virtually)
+    i64 m = 0, n = 0, r = 0;
+    bool leftorthogonal = true;
+    i64 *d_rowperm = nullptr; // 0-based, device
+    i64 *d_colperm = nullptr; // position -> physical column, 0-based, device
+    int *d_colpos = nullptr;  // physical column -> position
+};
+
+int tci_fail(tci_ctx *ctx, int code, const std::string &msg);
+
+#define TCI_CUDA(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return tci_fail((ctx), TCI_ERR_CUDA,                                                        \
+                            std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                std::to_string(__LINE__) + ")");                                        \
+    } while (0)
+
+struct CtxGuard { // single-caller contract (SURVEY 8b "Threading")
+    tci_ctx *c;
+    bool ok;
+    explicit CtxGuard(tci_ctx *ctx) : c(ctx), ok(false)
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (!c->busy) {
+            c->busy = true;
+            ok = true;
+        }
+    }
+    ~CtxGuard()
+    {
+        if (ok) {
+            std::lock_guard<std::mutex> g(c->mu);
+            c->busy = false;
+        }
+    }
+};
+#define TCI_ENTER(ctx)                                                          \
+    if (!(ctx)) return TCI_ERR_ARG;                                             \
+    CtxGuard guard__(ctx);                                                      \
+    if (!guard__.ok) return tci_fail((ctx), TCI_ERR_BUSY, "context is in use"); \
+    cudaSetDevice((ctx)->device)
+
+struct StageTimer {
+    tci_ctx *c;
+    int stage;
+    StageTimer(tci_ctx *ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->ev0, c->stream); }
+    void stop()
+    {
+        if (!c) return;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stage_ms[stage] += ms;
+        c = nullptr;
+    }
+    ~StageTimer() { stop(); }
+};
+
+static inline i64 round_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
+
+// stream-ordered scratch allocations on the context stream (pool never trimmed)
+static inline cudaError_t dev_alloc(tci_ctx *ctx, void **p, size_t bytes)
+{
+    return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+}
+static inline void dev_free(tci_ctx *ctx, void *p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+template <typename T> struct DevBuf { // RAII scratch buffer
+    tci_ctx *ctx;
+    T *p = nullptr;
+    DevBuf(tci_ctx *c) : ctx(c) {}
+    cudaError_t alloc(size_t count) { return dev_alloc(ctx, (void **)&p, count * sizeof(T)); }
+    cudaError_t upload(const T *host, size_t count)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    ~DevBuf() { dev_free(ctx, p); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// device allocation helpers (dmat.cu)
+int dmat_alloc(tci_ctx *ctx, i64 m, i64 n, tci_dmat **out);
+
+// dgemm.cu: C(MxN, ldc) = alpha * op(A) * op(B) + beta * C on the context stream
+int dgemm_dev(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+              const double *B, i64 ldb, double beta, double *C, i64 ldc);
+// batched variant: pointers advance by strideA/B/C per batch entry
+int dgemm_dev_batched(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                      i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
+                      i64 strideC, i64 batch);
+
+// per-batch element offsets added to A / B (device arrays, nullable)
+int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                          i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB);
+
+// pi_eval.cu / tt.cu / mpo.cu
+int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                     tci_dmat *out, unsigned long long *d_maxbits);
+int pi_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+               tci_dmat *out);
+int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                tci_dmat *out);
+int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits);

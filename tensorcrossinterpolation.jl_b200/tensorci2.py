@@ -1,0 +1,396 @@
+"""Host mirror of src/tensorci2.jl: the TCI2 driver.  In the deployed system this code is
+the reference's own (unchanged) Julia; here it is restated in Python so that the C-ABI can
+be driven and tested end to end without a Julia runtime.  It keeps the reference's names,
+keyword arguments, defaults and error texts, and it only ever computes through the GPU
+library: Pi / T tensors by tci_pi_eval (kept in HBM and handed straight to tci_rrlu),
+factorisations by tci_rrlu / tci_luci_*, global search by tci_globalsearch.
+
+Index sets are int64 arrays (count, len), the array form of Vector{MultiIndex}.
+"""
+import time
+
+import numpy as np
+
+from .batcheval import BatchEvaluator
+from .globalpivotfinder import AbstractGlobalPivotFinder, DefaultGlobalPivotFinder, GlobalPivotSearchInput
+from .matrixlu import MatrixLUCI, colindices, pivoterrors, rowindices
+from .tensortrain import TensorTrain, evaluate_points, tt_sum
+from .util import (CounterRNG, as_indexset, forwardsweep, jl_max, kronecker_left, kronecker_right, pushunique, union)
+
+I64MAX = 2**63 - 1
+
+
+class TensorCI2:
+    """mutable struct TensorCI2 (tensorci2.jl:6-40)."""
+
+    def __init__(self, func_or_localdims, localdims=None, initialpivots=None, Iset=None, Jset=None):
+        if localdims is None:
+            func, localdims = None, func_or_localdims
+        else:
+            func = func_or_localdims
+        if len(localdims) <= 1:
+            raise RuntimeError("localdims should have at least 2 elements!")  # :27
+        n = len(localdims)
+        self.localdims = [int(d) for d in localdims]
+        self.Iset = [np.zeros((0, b), dtype=np.int64) for b in range(n)]
+        self.Jset = [np.zeros((0, n - 1 - b), dtype=np.int64) for b in range(n)]
+        self.sitetensors = [np.zeros((0, d, 0), order="F") for d in self.localdims]
+        self.pivoterrors = np.zeros(0)
+        self.bonderrors = np.zeros(n - 1)
+        self.maxsamplevalue = 0.0
+        self.Iset_history = []
+        self.Jset_history = []
+        if func is None:
+            return
+        if Iset is not None:  # tensorci2.jl:58-72
+            self.Iset = [as_indexset(s, b) for b, s in enumerate(Iset)]
+            self.Jset = [as_indexset(s, n - 1 - b) for b, s in enumerate(Jset)]
+            pivots = reconstractglobalpivotsfromijset(self.localdims, self.Iset, self.Jset)
+        else:  # :42-53
+            if initialpivots is None:
+                initialpivots = [[1] * n]
+            pivots = as_indexset(initialpivots, n)
+            addglobalpivots(self, pivots)
+        vals = func.evaluate_points(pivots)
+        self.maxsamplevalue = float(np.max(np.abs(vals))) if len(vals) else 0.0
+        if not abs(self.maxsamplevalue) > 0.0:
+            raise RuntimeError("maxsamplevalue is zero!")
+        invalidatesitetensors(self)
+
+    def __len__(self):
+        return len(self.localdims)
+
+    def linkdims(self):  # :83-85
+        return [self.Iset[b + 1].shape[0] for b in range(len(self) - 1)]
+
+    def __call__(self, indexset):
+        return evaluate(self, indexset)
+
+
+def linkdims(tci):
+    return tci.linkdims()
+
+
+def rank(tci):
+    return max(tci.linkdims())
+
+
+def invalidatesitetensors(tci):  # :90-95
+    for b in range(len(tci)):
+        tci.sitetensors[b] = np.zeros((0, 0, 0), order="F")
+
+
+def issitetensorsavailable(tci):  # :100-102
+    return all(t.size != 0 for t in tci.sitetensors)
+
+
+def updatebonderror(tci, b, error):
+    tci.bonderrors[b] = error
+
+
+def maxbonderror(tci):
+    return float(np.max(tci.bonderrors))
+
+
+def pivoterror(tci):  # :157-159
+    return maxbonderror(tci)
+
+
+def updatepivoterror(tci, errors):  # :143-150 elementwise max with zero padding
+    L = max(len(tci.pivoterrors), len(errors))
+    a = np.zeros(L)
+    a[: len(tci.pivoterrors)] = tci.pivoterrors
+    b = np.zeros(L)
+    b[: len(errors)] = errors
+    out = np.where(np.isnan(a) | np.isnan(b), np.nan, np.maximum(a, b))
+    tci.pivoterrors = out
+
+
+def flushpivoterror(tci):
+    tci.pivoterrors = np.zeros(0)
+
+
+def updateerrors(tci, b, errors):  # :161-169
+    updatebonderror(tci, b, errors[-1])
+    updatepivoterror(tci, errors)
+
+
+def reconstractglobalpivotsfromijset(localdims, Isets, Jsets):  # :171-188
+    seen, out = set(), []
+    for i in range(len(Isets)):
+        for I in Isets[i]:
+            for J in Jsets[i]:
+                for j in range(1, localdims[i] + 1):
+                    p = tuple(I.tolist()) + (j,) + tuple(J.tolist())
+                    if p not in seen:
+                        seen.add(p)
+                        out.append(p)
+    return as_indexset(out, len(localdims))
+
+
+def addglobalpivots(tci, pivots):  # :193-213
+    pivots = as_indexset(pivots, len(tci))
+    if pivots.shape[0] and pivots.shape[1] != len(tci):
+        raise ValueError("Please specify a pivot as one index per leg of the MPS.")
+    n = len(tci)
+    for p in pivots:
+        for b in range(n):
+            tci.Iset[b] = pushunique(tci.Iset[b], p[:b])
+            tci.Jset[b] = pushunique(tci.Jset[b], p[b + 1:])
+    if pivots.shape[0] > 0:
+        invalidatesitetensors(tci)
+
+
+def filltensor(f, localdims, Iset, Jset, M, device=False):
+    """filltensor (tensorci2.jl:290-312).  device=True keeps the result in HBM and returns
+    (DeviceMatrix (|I|*prod d) x |J|, max|.|); otherwise the host array (|I|, d..., |J|)."""
+    if len(Iset) * len(Jset) == 0:
+        return (None, 0.0) if device else np.zeros((0,) * (M + 2), order="F")
+    if not isinstance(f, BatchEvaluator):
+        raise TypeError("Function `f` is not batch evaluatable")
+    N = len(localdims)
+    if N - Iset.shape[1] - Jset.shape[1] != M:
+        raise RuntimeError("Invalid number of central indices")  # :307
+    if device:
+        return f.batchevaluate_device(Iset, Jset, M)
+    return f(Iset, Jset, M)
+
+
+def setsitetensor(tci, b, T):  # :329-338
+    tci.sitetensors[b] = np.asfortranarray(T).reshape(
+        (tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]), order="F")
+
+
+def updatemaxsample(tci, mx):  # :397-399 with the max-abs fused into the evaluation kernel
+    tci.maxsamplevalue = jl_max(tci.maxsamplevalue, mx)
+
+
+def setsitetensor_fill(tci, f, b):
+    """setsitetensor!(tci, f, b) (tensorci2.jl:367-394): T_b = Pi1 * P^-1, solved on the host by
+    LAPACK gesv exactly as the reference's `\\` does."""
+    n = len(tci)
+    Pi1, mx = f._pi(tci.Iset[b], tci.Jset[b], 1, True, False)[::2]
+    nI, d, nJ = tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]
+    Pi1 = Pi1.reshape((nI * d, nJ), order="F")
+    updatemaxsample(tci, mx)
+    if b == n - 1:
+        tci.sitetensors[b] = Pi1.reshape((nI, d, nJ), order="F")
+        return tci.sitetensors[b]
+    P = f(tci.Iset[b + 1], tci.Jset[b], 0)
+    k = tci.Iset[b + 1].shape[0]
+    if k != nJ:
+        raise RuntimeError(f"Pivot matrix at bond {b + 1} is not square!")  # :388
+    Tmat = np.linalg.solve(P.T, Pi1.T).T  # transpose(transpose(P) \ transpose(Pi1))  :391
+    tci.sitetensors[b] = np.asfortranarray(Tmat).reshape((nI, d, k), order="F")
+    return tci.sitetensors[b]
+
+
+def fillsitetensors(tci, f):  # globalsearch.jl:97-103
+    for b in range(len(tci)):
+        setsitetensor_fill(tci, f, b)
+
+
+def _sanitycheck(tci):  # globalsearch.jl:106-112
+    for b in range(len(tci) - 1):
+        if tci.Iset[b + 1].shape[0] != tci.Jset[b].shape[0]:
+            raise RuntimeError(f"Pivot matrix at bond {b + 1} is not square!")
+    return True
+
+
+def sweep1site(tci, f, sweepdirection="forward", reltol=1e-14, abstol=0.0, maxbonddim=I64MAX, updatetensors=True):
+    """sweep1site! (tensorci2.jl:402-461)."""
+    flushpivoterror(tci)
+    invalidatesitetensors(tci)
+    if sweepdirection not in ("forward", "backward"):
+        raise ValueError(f"Unknown sweep direction {sweepdirection}: choose between :forward, :backward.")
+    fwd = sweepdirection == "forward"
+    n = len(tci)
+    for b in (range(n - 1) if fwd else range(n - 1, 0, -1)):
+        Is = kronecker_left(tci.Iset[b], tci.localdims[b]) if fwd else tci.Iset[b]
+        Js = tci.Jset[b] if fwd else kronecker_right(tci.localdims[b], tci.Jset[b])
+        Pi, mx = filltensor(f, tci.localdims, tci.Iset[b], tci.Jset[b], 1, device=True)
+        updatemaxsample(tci, mx)
+        if fwd:  # (|I|*d) x |J| is already the matrix shape
+            luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX), leftorthogonal=True)
+        else:  # |I| x (d*|J|): same memory, different fold -> refold through the host
+            host = Pi.to_host().reshape((len(Is), len(Js)), order="F")
+            luci = MatrixLUCI(host, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
+                              leftorthogonal=False, ctx=f.ctx)
+        nIb, nJb = tci.Iset[b].shape[0], tci.Jset[b].shape[0]
+        if fwd:
+            tci.Iset[b + 1] = Is[rowindices(luci) - 1]
+            tci.Jset[b] = Js[colindices(luci) - 1]
+        else:
+            tci.Iset[b] = Is[rowindices(luci) - 1]
+            tci.Jset[b - 1] = Js[colindices(luci) - 1]
+        if updatetensors:
+            T = luci.left() if fwd else luci.right()
+            shape = (nIb, tci.localdims[b], luci.npivot) if fwd else (luci.npivot, tci.localdims[b], nJb)
+            tci.sitetensors[b] = np.asfortranarray(T).reshape(shape, order="F")
+            if np.isnan(tci.sitetensors[b]).any():
+                raise RuntimeError(f"Error: NaN in tensor T[{b + 1}]")  # :439-441
+        updateerrors(tci, b if fwd else b - 1, pivoterrors(luci))
+    if updatetensors:  # :448-459
+        last = n - 1 if fwd else 0
+        T = f(tci.Iset[last], tci.Jset[last], 1)
+        tci.sitetensors[last] = np.asfortranarray(T).reshape(
+            (tci.Iset[last].shape[0], tci.localdims[last], tci.Jset[last].shape[0]), order="F")
+
+
+def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim=I64MAX, sweepdirection="forward",
+                 pivotsearch="full", verbosity=0, extraIset=None, extraJset=None, set_sitetensors=False):
+    """updatepivots! (tensorci2.jl:510-607), pivotsearch = :full.  b is 0-based here."""
+    invalidatesitetensors(tci)
+    n = len(tci)
+    if extraIset is None:
+        extraIset = np.zeros((0, b + 1), dtype=np.int64)
+    if extraJset is None:
+        extraJset = np.zeros((0, n - 1 - b), dtype=np.int64)
+    Icombined = union(kronecker_left(tci.Iset[b], tci.localdims[b]), extraIset)
+    Jcombined = union(kronecker_right(tci.localdims[b + 1], tci.Jset[b + 1]), extraJset)
+    if pivotsearch != "full":
+        if pivotsearch == "rook":
+            raise NotImplementedError("pivotsearch=:rook is listed as next in SURVEY 8(f); use :full")
+        raise ValueError(f"Unknown pivot search strategy {pivotsearch}. Choose from :rook, :full.")
+    t1 = time.perf_counter()
+    Pi, mx = filltensor(f, tci.localdims, Icombined, Jcombined, 0, device=True)
+    t2 = time.perf_counter()
+    updatemaxsample(tci, mx)
+    luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
+                      leftorthogonal=leftorthogonal)
+    t3 = time.perf_counter()
+    if verbosity > 2:
+        print(f"    Computing Pi ({len(Icombined)} x {len(Jcombined)}) at bond {b + 1}: {t2 - t1} sec, "
+              f"LU: {t3 - t2} sec")
+    tci.Iset[b + 1] = Icombined[rowindices(luci) - 1]
+    tci.Jset[b] = Jcombined[colindices(luci) - 1]
+    if set_sitetensors and len(extraIset) == 0 and len(extraJset) == 0:  # :601-604
+        setsitetensor(tci, b, luci.left())
+        setsitetensor(tci, b + 1, luci.right())
+    updateerrors(tci, b, pivoterrors(luci))
+    if hasattr(tci, "trace"):
+        tci.trace.append((b + 1, len(Icombined), len(Jcombined), luci.npivot))
+
+
+def convergencecriterion(ranks, errors, nglobalpivots, tolerance, maxbonddim, ncheckhistory,
+                         checkconvglobalpivot=True):  # :609-628
+    if len(errors) < ncheckhistory:
+        return False
+    lastranks = ranks[-ncheckhistory:]
+    lastng = nglobalpivots[-ncheckhistory:]
+    return bool((all(e < tolerance for e in errors[-ncheckhistory:])
+                 and (all(g == 0 for g in lastng) if checkconvglobalpivot else True)
+                 and min(lastranks) == lastranks[-1])
+                or all(r >= maxbonddim for r in lastranks))
+
+
+def sweep2site(tci, f, niter, iter1=1, abstol=1e-8, maxbonddim=I64MAX, sweepstrategy="backandforth",
+               pivotsearch="full", verbosity=0, strictlynested=False, fillsitetensors_=True):
+    """sweep2site! (tensorci2.jl:855-916)."""
+    invalidatesitetensors(tci)
+    n = len(tci)
+    for it in range(iter1, iter1 + niter):
+        extraI = [np.zeros((0, b), dtype=np.int64) for b in range(n)]
+        extraJ = [np.zeros((0, n - 1 - b), dtype=np.int64) for b in range(n)]
+        if not strictlynested and len(tci.Iset_history) > 0:
+            extraI = tci.Iset_history[-1]
+            extraJ = tci.Jset_history[-1]
+        tci.Iset_history.append([s.copy() for s in tci.Iset])
+        tci.Jset_history.append([s.copy() for s in tci.Jset])
+        if len(tci.Iset_history) > 2:  # only history[end] is ever read (:874-877)
+            tci.Iset_history = tci.Iset_history[-2:]
+            tci.Jset_history = tci.Jset_history[-2:]
+        flushpivoterror(tci)
+        fwd = forwardsweep(sweepstrategy, it)
+        for b in (range(n - 1) if fwd else range(n - 2, -1, -1)):
+            updatepivots(tci, b, f, fwd, abstol=abstol, maxbonddim=maxbonddim,
+                         sweepdirection="forward" if fwd else "backward", pivotsearch=pivotsearch,
+                         verbosity=verbosity, extraIset=extraI[b + 1], extraJset=extraJ[b])
+    if fillsitetensors_:
+        fillsitetensors(tci, f)
+
+
+def optimize(tci, f, tolerance=None, pivottolerance=None, maxbonddim=I64MAX, maxiter=20,
+             sweepstrategy="backandforth", pivotsearch="full", verbosity=0, loginterval=10, normalizeerror=True,
+             ncheckhistory=3, globalpivotfinder=None, maxnglobalpivot=5, nsearchglobalpivot=5,
+             tolmarginglobalsearch=10.0, strictlynested=False, checkbatchevaluatable=False,
+             checkconvglobalpivot=True, rng=None):
+    """optimize! (tensorci2.jl:700-850).  Returns (ranks, errors ./ normalisation)."""
+    errors, ranks, nglobalpivots = [], [], []
+    if checkbatchevaluatable and not isinstance(f, BatchEvaluator):
+        raise RuntimeError("Function `f` is not batch evaluatable")
+    if nsearchglobalpivot > 0 and nsearchglobalpivot < maxnglobalpivot:
+        raise RuntimeError("nsearchglobalpivot < maxnglobalpivot!")
+    if pivottolerance is not None:
+        if tolerance is not None and tolerance != pivottolerance:
+            raise ValueError("Got different values for pivottolerance and tolerance in optimize!(TCI2). For TCI2, "
+                             "both of these options have the same meaning. Please assign only `tolerance`.")
+        import warnings
+        warnings.warn("The option `pivottolerance` of `optimize!(tci::TensorCI2, f)` is deprecated. Please update "
+                      "your code to use `tolerance`, as `pivottolerance` will be removed in the future.")
+        tol = pivottolerance
+    elif tolerance is not None:
+        tol = tolerance
+    else:
+        tol = 1e-8
+    tstart = time.perf_counter()
+    if maxbonddim >= I64MAX and tol <= 0:
+        raise ValueError("Specify either tolerance > 0 or some maxbonddim; otherwise, the convergence criterion is "
+                         "not reachable!")
+    finder = globalpivotfinder if globalpivotfinder is not None else DefaultGlobalPivotFinder(
+        nsearch=nsearchglobalpivot, maxnglobalpivot=maxnglobalpivot, tolmarginglobalsearch=tolmarginglobalsearch)
+    if not isinstance(finder, AbstractGlobalPivotFinder) and not callable(finder):
+        raise TypeError("globalpivotfinder must be an AbstractGlobalPivotFinder")
+    rng = rng if rng is not None else CounterRNG(1)
+    for it in range(1, maxiter + 1):
+        errornormalization = tci.maxsamplevalue if normalizeerror else 1.0
+        abstol = tol * errornormalization
+        if verbosity > 1:
+            print(f"  Walltime {time.perf_counter() - tstart} sec: starting 2site sweep", flush=True)
+        sweep2site(tci, f, 2, iter1=1, abstol=abstol, maxbonddim=maxbonddim, pivotsearch=pivotsearch,
+                   strictlynested=strictlynested, verbosity=verbosity, sweepstrategy=sweepstrategy,
+                   fillsitetensors_=True)
+        errors.append(pivoterror(tci))
+        if verbosity > 1:
+            print(f"  Walltime {time.perf_counter() - tstart} sec: start searching global pivots", flush=True)
+        inp = GlobalPivotSearchInput(tci.localdims, TensorTrain(tci.sitetensors), tci.maxsamplevalue, tci.Iset,
+                                     tci.Jset)
+        globalpivots = finder(inp, f, abstol, verbosity=verbosity, rng=rng)
+        addglobalpivots(tci, globalpivots)
+        nglobalpivots.append(len(globalpivots))
+        if verbosity > 1:
+            print(f"  Walltime {time.perf_counter() - tstart} sec: done searching global pivots", flush=True)
+        ranks.append(rank(tci))
+        if verbosity > 0 and it % loginterval == 0:
+            print(f"iteration = {it}, rank = {ranks[-1]}, error= {errors[-1]}, maxsamplevalue= "
+                  f"{tci.maxsamplevalue}, nglobalpivot={len(globalpivots)}", flush=True)
+        if convergencecriterion(ranks, errors, nglobalpivots, abstol, maxbonddim, ncheckhistory,
+                                checkconvglobalpivot=checkconvglobalpivot):
+            break
+    errornormalization = tci.maxsamplevalue if normalizeerror else 1.0
+    abstol = tol * errornormalization
+    sweep1site(tci, f, abstol=abstol, maxbonddim=maxbonddim)
+    _sanitycheck(tci)
+    tci.nglobalpivots_history = nglobalpivots
+    return ranks, [e / errornormalization for e in errors]
+
+
+def crossinterpolate2(f, localdims, initialpivots=None, **kwargs):
+    """crossinterpolate2(ValueType, f, localdims, initialpivots; kwargs...) (tensorci2.jl:943-953) for
+    ValueType = Float64.  Returns (tci, ranks, errors)."""
+    tci = TensorCI2(f, localdims, initialpivots)
+    tci.trace = []
+    ranks, errors = optimize(tci, f, **kwargs)
+    return tci, ranks, errors
+
+
+def evaluate(tci, indexset):
+    """tci(indexset): evaluate of abstracttensortrain.jl:124-132 on the site tensors."""
+    if len(indexset) != len(tci):
+        raise ValueError(f"To evaluate a tt of length {len(tci)}, you have to provide {len(tci)} indices, but there "
+                         f"were {len(indexset)}.")
+    return float(evaluate_points(TensorTrain(tci.sitetensors), [indexset])[0])
+
+
+def tci_sum(tci):
+    return tt_sum(TensorTrain(tci.sitetensors))

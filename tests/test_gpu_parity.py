@@ -1,0 +1,476 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes binding of
+include/tci_b200.h), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): pivot index sets / permutations / ranks bit-identical;
+rrLU factors bit-identical in exact mode (same operation order, no FMA); Pi tensors of the
+built-in analytic targets bit-identical; everything that goes through a GEMM/TRSM (LUCI
+left/right, TT and MPO targets, site tensors) within 1e-10 relative.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from tests.golden import reference_fixtures as G
+
+pytestmark = pytest.mark.gpu
+
+LORENTZ, SUM, Q2D, SEPCOS, TABLE, Q1D, GK = 1, 2, 3, 4, 5, 6, 7
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def T():
+    import tci_b200
+    return tci_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(T):
+    return T.default_context()
+
+
+def sepcos_params(n, seed=4, nterms=4):
+    """BASELINE config 4 parameters: dyadic so that all partial sums are exact."""
+    rng = np.random.default_rng(seed)
+    w = rng.integers(1, 1025, n) / 256.0
+    a = rng.integers(-512, 513, nterms) / 1024.0
+    om = rng.integers(-1024, 1025, (nterms, n)) / 32.0
+    return np.concatenate([[nterms], w, a, om.flatten()])
+
+
+def gk_params():
+    xgk = [0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+           0.864864423359769072789712788640926, 0.741531185599394439863864773280788,
+           0.586087235467691130294144838258730, 0.405845151377397166906606412076961,
+           0.207784955007898467600689403773245, 0.0]
+    wgk = [0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+           0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+           0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+           0.204432940075298892414161999234649, 0.209482141084727828012999174891714]
+    return [15] + [-x for x in xgk] + xgk[-2::-1] + wgk + wgk[-2::-1]
+
+
+TARGETS = [
+    ("lorentz", LORENTZ, [1.0], [10] * 6),
+    ("sum", SUM, [], [2, 3, 4, 3, 2]),
+    ("q2d_fused", Q2D, [0, 8], [4] * 8),
+    ("q2d_interleaved", Q2D, [1, 6], [2] * 12),
+    ("sepcos", SEPCOS, None, [64] * 5),
+    ("table", TABLE, "table", [3, 4, 2, 3]),
+    ("q1d", Q1D, [10, 1], [2] * 10),
+    ("gk", GK, gk_params(), [15] * 5),
+]
+
+
+def make_target(T, oracle, kind, params, ld):
+    if params is None:
+        params = sepcos_params(len(ld))
+    elif isinstance(params, str):
+        params = np.random.default_rng(11).standard_normal(int(np.prod(ld)))
+    return T.BuiltinTarget(kind, params, ld), oracle.Target.builtin(kind, params, ld)
+
+
+def rand_indexset(rng, dims, count):
+    if len(dims) == 0:
+        return np.zeros((1, 0), dtype=np.int64)
+    return np.stack([rng.integers(1, d + 1, count) for d in dims], axis=1).astype(np.int64)
+
+
+# ------------------------------------------------------------------ K1 ------
+@pytest.mark.parametrize("name,kind,params,ld", TARGETS, ids=[t[0] for t in TARGETS])
+def test_pi_eval_bit_exact(T, oracle, name, kind, params, ld):
+    f, o = make_target(T, oracle, kind, params, ld)
+    rng = np.random.default_rng(5)
+    n = len(ld)
+    for nl, M in [(1, 0), (2, 0), (n - 1, 0), (1, 1), (2, 1), (0, 1), (1, 2), (n - 2, 2), (0, 2), (n, 0), (0, 0)]:
+        nr = n - nl - M
+        if nr < 0:
+            continue
+        I = rand_indexset(rng, ld[:nl], 37 if nl else 1)
+        J = rand_indexset(rng, ld[n - nr:], 29 if nr else 1)
+        got, dev, mx = f._pi(I, J, M, True, True)
+        ref, omx = o.pi_eval(I.tolist(), J.tolist(), M, 0.0)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), f"{name} nl={nl} M={M}"
+        assert mx == omx
+        assert np.array_equal(dev.to_host().reshape(ref.shape, order="F"), ref)
+    pts = rand_indexset(rng, ld, 50)
+    assert np.array_equal(f.evaluate_points(pts), np.array([o(p) for p in pts]))
+
+
+def test_pi_eval_layout_and_empty(T):  # test_batcheval.jl:13-46
+    f = T.BuiltinTarget(SUM, [], [2, 2, 2, 2, 2])
+    left = [[1, 1]] * 100
+    right = [[1, 1]] * 100
+    res = f(left, right, 1)
+    ref = np.array([[[sum(l) + c + sum(r) for r in right] for c in (1, 2)] for l in left], dtype=float)
+    assert res.shape == (100, 2, 100) and np.array_equal(res, ref)
+    g = T.BuiltinTarget(SUM, [], [3, 3, 3, 3])
+    assert g([[1], [2]], [[1], [2]], 1).shape == (2, 3, 2)
+    assert g([], [[1]], 1).size == 0
+    with pytest.raises(RuntimeError, match="Invalid number of central indices"):
+        g([[1]], [[1]], 1)
+
+
+def test_pi_eval_large_odd_shapes(T, oracle):
+    ld = [10] * 8
+    f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
+    rng = np.random.default_rng(6)
+    I = rand_indexset(rng, ld[:3], 1031)
+    J = rand_indexset(rng, ld[5:], 517)
+    got = f(I, J, 2)
+    ref, _ = o.pi_eval(I.tolist(), J.tolist(), 2)
+    assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ K2 ------
+def assert_lu_equal(lu, ref, bitexact=True):
+    assert lu.npivot == ref.npivot
+    assert np.array_equal(lu.rowpermutation, ref.rowpermutation)
+    assert np.array_equal(lu.colpermutation, ref.colpermutation)
+    if bitexact:
+        assert lu.error == ref.error or (np.isnan(lu.error) and np.isnan(ref.error))
+        assert np.array_equal(lu.L, ref.L)
+        assert np.array_equal(lu.U, ref.U)
+        assert np.array_equal(lu._pivoterrors, ref.pivoterrors)
+    else:
+        np.testing.assert_allclose(lu.L, ref.L, rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(lu.U, ref.U, rtol=RTOL, atol=1e-300)
+
+
+FIXTURES = [
+    ("4x4", G.RRLU_4x4, {}),
+    ("8x6_maxrank4", G.RRLU_8x6, {"maxrank": 4}),
+    ("lowrank", G.LOWRANK_P @ G.LOWRANK_Q, {}),
+    ("eye2", np.eye(2), {}),
+    ("5x5_maxrank2", G.RRLU_5x5, {"maxrank": 2}),
+    ("5x5_abstol", G.RRLU_5x5, {"abstol": 0.5}),
+    ("5x5_full", G.RRLU_5x5, {"abstol": 0.0}),
+    ("tiny", G.RRLU_TINY, {"abstol": 1e-3}),
+    ("unit", np.diag([1.0, 0.0, 0.0]), {}),
+    ("argmaxA", G.ARGMAX_A, {}),
+]
+
+
+@pytest.mark.parametrize("leftorth", [True, False])
+@pytest.mark.parametrize("name,A,kw", FIXTURES, ids=[f[0] for f in FIXTURES])
+def test_rrlu_reference_fixtures(T, oracle, name, A, kw, leftorth):  # test_matrixlu.jl:54-211
+    lu = T.rrlu(A, leftorthogonal=leftorth, **kw)
+    ref = oracle.rrlu(A, leftorthogonal=leftorth, **kw)
+    assert_lu_equal(lu, ref)
+    if name == "eye2":
+        assert T.pivoterrors(lu).tolist() == [1.0, 1.0, 0.0] and T.lastpivoterror(lu) == 0.0
+    if name == "lowrank":
+        assert T.npivots(lu) == 3
+        np.testing.assert_allclose(T.left(lu) @ T.right(lu), A, rtol=1.5e-8)
+    if name == "unit":
+        assert lu.npivot == 1
+
+
+def lowrank_matrix(m, n, r, seed, decay=40.0):
+    """BASELINE config 2: A = sum_k s_k p_k q_k^T, p,q ~ U(0,1), s_k = 2^(-decay k / r)."""
+    rng = np.random.default_rng(seed)
+    p = rng.random((m, r))
+    q = rng.random((r, n))
+    s = 2.0 ** (-decay * np.arange(1, r + 1) / r)
+    return (p * s) @ q
+
+
+SHAPES = [(1, 1, 1), (1, 7, 1), (9, 1, 1), (2, 3, 2), (17, 33, 9), (64, 64, 20), (100, 37, 30), (37, 100, 30),
+          (130, 257, 40), (300, 300, 64), (513, 700, 48), (1000, 600, 32)]
+
+
+@pytest.mark.parametrize("leftorth", [True, False])
+@pytest.mark.parametrize("m,n,r", SHAPES)
+def test_rrlu_random_lowrank_bit_exact(T, oracle, m, n, r, leftorth):
+    A = lowrank_matrix(m, n, r, seed=m * 1000 + n)
+    lu = T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=leftorth)
+    ref = oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=leftorth)
+    assert_lu_equal(lu, ref)
+
+
+@pytest.mark.parametrize("m,n", [(50, 50), (120, 80), (257, 300)])
+def test_rrlu_full_rank_random(T, oracle, m, n):  # benchmark/rrlu.jl:12-17 shape
+    A = np.random.default_rng(m).random((m, n))
+    lu = T.rrlu(A)
+    ref = oracle.rrlu(A)
+    assert_lu_equal(lu, ref)
+    assert lu.npivot == min(m, n) and lu.error == 0.0
+
+
+def test_rrlu_exact_ties(T, oracle):
+    """Symmetric targets make many entries bit-equal; the winner is defined by scan order
+    (columns outer, rows inner, strict >) on the swapped matrix."""
+    rng = np.random.default_rng(3)
+    A = rng.integers(-3, 4, (60, 45)).astype(float)
+    assert_lu_equal(T.rrlu(A), oracle.rrlu(A))
+    v = np.arange(1, 41, dtype=float)
+    L = 1.0 / (1.0 + v[:, None] ** 2 + v[None, :] ** 2)  # symmetric Lorentzian slice
+    assert_lu_equal(T.rrlu(L, reltol=1e-13), oracle.rrlu(L, reltol=1e-13))
+    assert_lu_equal(T.rrlu(np.ones((33, 65))), oracle.rrlu(np.ones((33, 65))))
+    assert_lu_equal(T.rrlu(np.zeros((5, 4)) + 2.0, maxrank=1), oracle.rrlu(np.zeros((5, 4)) + 2.0, maxrank=1))
+
+
+def test_rrlu_nan_and_errors(T):
+    A = np.zeros((3, 3))
+    with pytest.raises(T.TCIError, match="contains NaNs"):  # matrixlu.jl:164-169 (0/0 in the first column)
+        T.rrlu(A)
+    B = np.random.default_rng(0).random((6, 6))
+    B[2, 3] = np.nan
+    with pytest.raises(T.TCIError, match="contains NaNs"):
+        T.rrlu(B)
+
+
+def test_rrlu_fast_mode_same_pivots(T, oracle):
+    A = lowrank_matrix(200, 180, 30, seed=9)
+    lu = T.rrlu(A, maxrank=30, reltol=1e-12, exact=False)
+    ref = oracle.rrlu(A, maxrank=30, reltol=1e-12)
+    assert_lu_equal(lu, ref, bitexact=False)
+
+
+def test_rrlu_device_input_from_pi_eval(T, oracle):
+    ld = [10] * 6
+    f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
+    rng = np.random.default_rng(8)
+    I = rand_indexset(rng, ld[:3], 200)
+    J = rand_indexset(rng, ld[3:], 150)
+    dev, mx = f.batchevaluate_device(I, J, 0)
+    Pi, omx = o.pi_eval(I.tolist(), J.tolist(), 0, 0.0)
+    luci = T.MatrixLUCI(dev, reltol=1e-14, abstol=1e-10 * mx, maxrank=40, leftorthogonal=True)
+    ref = oracle.luci(Pi, reltol=1e-14, abstol=1e-10 * omx, maxrank=40, leftorthogonal=True)
+    assert luci.npivot == ref.npivot
+    assert np.array_equal(T.rowindices(luci), ref.rowindices)
+    assert np.array_equal(T.colindices(luci), ref.colindices)
+    assert np.array_equal(T.pivoterrors(luci), ref.pivoterrors)
+
+
+# ------------------------------------------------------------------ K3 ------
+@pytest.mark.parametrize("leftorth", [True, False])
+@pytest.mark.parametrize("m,n,r", [(8, 6, 4), (40, 70, 33), (300, 200, 64), (129, 515, 100), (700, 90, 90)])
+def test_luci_left_right(T, oracle, m, n, r, leftorth):  # test_matrixluci.jl:6-74
+    A = G.LUCI_8x6 if (m, n) == (8, 6) else lowrank_matrix(m, n, r, seed=m + n, decay=20.0)
+    luci = T.MatrixLUCI(A, maxrank=r, leftorthogonal=leftorth)
+    ref = oracle.luci(A, maxrank=r, leftorthogonal=leftorth)
+    assert luci.npivot == ref.npivot
+    Lg, Rg = T.left(luci), T.right(luci)
+    scale_l, scale_r = np.max(np.abs(ref.left)), np.max(np.abs(ref.right))
+    assert np.max(np.abs(Lg - ref.left)) <= RTOL * scale_l
+    assert np.max(np.abs(Rg - ref.right)) <= RTOL * scale_r
+    Ld = luci.left(device=True).to_host()
+    assert np.array_equal(Ld, Lg)
+
+
+def test_dgemm_kernel(T, ctx):
+    import ctypes as C
+    from tci_b200 import _lib
+    rng = np.random.default_rng(1)
+    for (M, N, K), (ta, tb) in itertools.product([(1, 1, 1), (5, 130, 17), (257, 129, 300), (64, 64, 64), (300, 7, 513)],
+                                                 [(0, 0), (1, 0), (0, 1), (1, 1)]):
+        A = np.asfortranarray(rng.standard_normal((K, M) if ta else (M, K)))
+        B = np.asfortranarray(rng.standard_normal((N, K) if tb else (K, N)))
+        Cm = np.asfortranarray(rng.standard_normal((M, N)))
+        ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - 2.0 * Cm
+        out = Cm.copy(order="F")
+        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, ta, tb, M, N, K, 0.5, _lib.pf(A), _lib.pf(B), -2.0, _lib.pf(out)))
+        assert np.max(np.abs(out - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))) * K
+
+
+# ------------------------------------------------------------- K4 / K5 ------
+def _rand_tt(rng, bonds, dims):
+    return [np.asfortranarray(rng.random((bonds[i], dims[i], bonds[i + 1])) - 0.3) for i in range(len(dims))]
+
+
+def test_tt_target_all_splits(T, oracle):  # test_tensortrain.jl:113-140, test_cachedtensortrain.jl:8-65
+    rng = np.random.default_rng(3)
+    dims = [2, 3, 3, 2, 4]
+    cores = _rand_tt(rng, [1, 2, 5, 3, 2, 1], dims)
+    f = T.TTCache(T.TensorTrain(cores))
+    o = oracle.Target.tt(cores)
+    N = len(dims)
+    pts = np.array(list(itertools.product(*[range(1, d + 1) for d in dims])), dtype=np.int64)
+    got = f.evaluate_points(pts)
+    ref = np.array([o(p) for p in pts])
+    assert np.array_equal(got, ref)  # same operation order -> bit exact
+    ev = T.evaluate_points(T.TensorTrain(cores), pts)
+    assert np.array_equal(ev, np.array([oracle.tt_evaluate(cores, p) for p in pts]))
+    for nl in range(N + 1):
+        for nr in range(N - nl + 1):
+            M = N - nl - nr
+            I = rand_indexset(rng, dims[:nl], 11 if nl else 1)
+            J = rand_indexset(rng, dims[N - nr:], 7 if nr else 1)
+            res = f(I, J, M)
+            oref, _ = o.pi_eval(I.tolist(), J.tolist(), M)
+            np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-14)
+
+
+def _rand_mpo(rng, bonds, d1, d2):
+    return [np.asfortranarray(rng.random((bonds[i], d1[i], d2[i], bonds[i + 1])) - 0.5) for i in range(len(d1))]
+
+
+def test_mpo_target(T, oracle):  # test_contraction.jl:68-146 (real-valued)
+    rng = np.random.default_rng(5)
+    N = 5
+    d1, d2, d3 = [2, 2, 3, 2, 2], [2, 3, 2, 2, 3], [3, 2, 2, 2, 2]
+    A = _rand_mpo(rng, [1, 2, 3, 4, 2, 1], d1, d2)
+    B = _rand_mpo(rng, [1, 3, 2, 3, 3, 1], d2, d3)
+    f = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    o = oracle.Target.mpo_pair(A, B)
+    ld = f.localdims
+    assert ld == o.localdims
+    pts = rand_indexset(rng, ld, 64)
+    np.testing.assert_allclose(f.evaluate_points(pts), np.array([o(p) for p in pts]), rtol=RTOL, atol=1e-14)
+    for nl, nr in ((1, 1), (0, 2), (2, 0), (1, 2), (2, 2), (0, 0), (2, 3), (3, 2), (4, 1), (0, 5), (5, 0)):
+        M = N - nl - nr
+        I = rand_indexset(rng, ld[:nl], 9 if nl else 1)
+        J = rand_indexset(rng, ld[N - nr:], 6 if nr else 1)
+        res = f(I, J, M)
+        oref, _ = o.pi_eval(I.tolist(), J.tolist(), M)
+        np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
+
+
+def test_zipup_and_naive_site(T):  # contraction.jl:338-349, 455-464
+    import ctypes as C
+    from tci_b200 import _lib
+    rng = np.random.default_rng(7)
+    chi, Da, Db, s1, s2, s3, Dan, Dbn = 5, 4, 3, 2, 3, 2, 6, 5
+    R = np.asfortranarray(rng.standard_normal((chi, Da, Db)))
+    A = np.asfortranarray(rng.standard_normal((Da, s1, s2, Dan)))
+    B = np.asfortranarray(rng.standard_normal((Db, s2, s3, Dbn)))
+    ctx = T.default_context()
+    out = np.zeros(chi * s1 * s3 * Dan * Dbn)
+    ctx.check(_lib.lib().tci_contract_zipup_site(ctx.h, _lib.pf(R), chi, Da, Db, _lib.pf(A), s1, s2, Dan, _lib.pf(B),
+                                                 s3, Dbn, _lib.pf(out), None))
+    ref = np.einsum("cab,axhn,bhzm->cxznm", R, A, B)
+    np.testing.assert_allclose(out.reshape((chi, s1, s3, Dan, Dbn), order="F"), ref, rtol=1e-12, atol=1e-13)
+    nv = T._contractsitetensors(A, B)
+    refn = np.einsum("axhn,bhzm->abxznm", A, B).reshape((Da * Db, s1, s3, Dan * Dbn), order="F")
+    np.testing.assert_allclose(nv, refn, rtol=1e-12, atol=1e-13)
+
+
+def test_contract_zipup_and_tci_vs_dense(T):  # test_contraction.jl:68-99, 185-195
+    rng = np.random.default_rng(9)
+    N = 4
+    d1, d2, d3 = [2, 2, 2, 2], [2, 3, 2, 2], [2, 2, 3, 2]
+    A = _rand_mpo(rng, [1, 2, 3, 2, 1], d1, d2)
+    B = _rand_mpo(rng, [1, 3, 2, 3, 1], d2, d3)
+
+    def dense(cores):
+        out = cores[0]
+        for c in cores[1:]:
+            out = np.tensordot(out, c, axes=([-1], [0]))
+        return out[0, ..., 0]
+
+    a, b = dense(A), dense(B)
+    la = "".join(chr(97 + 2 * s) + chr(97 + 2 * s + 1) for s in range(N))
+    lb = "".join(chr(97 + 2 * s + 1) + chr(65 + s) for s in range(N))
+    lc = "".join(chr(97 + 2 * s) + chr(65 + s) for s in range(N))
+    ref = np.einsum(f"{la},{lb}->{lc}", a, b)
+    for method in ("LU", "SVD"):
+        tt = T.contract_zipup(T.TensorTrain(A), T.TensorTrain(B), tolerance=1e-13, method=method)
+        np.testing.assert_allclose(dense(tt.sitetensors), ref, rtol=1e-8, atol=1e-10)
+    tt = T.contract(T.TensorTrain(A), T.TensorTrain(B), algorithm="TCI", tolerance=1e-12, maxbonddim=60)
+    np.testing.assert_allclose(dense(tt.sitetensors), ref, rtol=1e-8, atol=1e-10)
+    ttn = T.contract(T.TensorTrain(A), T.TensorTrain(B), algorithm="naive", tolerance=0.0)
+    np.testing.assert_allclose(dense(ttn.sitetensors), ref, rtol=1e-10, atol=1e-12)
+
+
+# ------------------------------------------------------- K7 + the driver ----
+def test_globalsearch_matches_oracle(T, oracle):  # test_globalsearch.jl:7-36
+    R = 10
+    f, o = make_target(T, oracle, Q1D, [R, 1], [2] * R)
+    res = oracle.crossinterpolate2(o, [2] * R, [[1] * R, [1] + [2] * (R - 1)], tolerance=1e-4, maxbonddim=1,
+                                   normalizeerror=False)
+    starts = oracle.start_points(7, 1, 20, [2] * R)  # (n, nsearch)
+    piv, errs = oracle.globalsearch(o, res.sitetensors, starts, abstol=1e-9, tolmargin=1.0, maxn=20)
+    finder = T.DefaultGlobalPivotFinder(nsearch=20, maxnglobalpivot=20, tolmarginglobalsearch=1.0)
+    inp = T.GlobalPivotSearchInput([2] * R, T.TensorTrain(res.sitetensors), res.maxsamplevalue, None, None)
+    got = finder(inp, f, 1e-9, rng=np.ascontiguousarray(starts.T))
+    assert got.tolist() == piv
+    assert np.array_equal(finder.last_errors, errs)
+
+
+def compare_tci(tci, ranks, errors, res, T):
+    n = len(tci)
+    assert [int(r) for r in ranks] == res.ranks.tolist()
+    for b in range(n):
+        assert [tuple(x) for x in tci.Iset[b].tolist()] == res.Iset[b], f"Iset[{b}]"
+        assert [tuple(x) for x in tci.Jset[b].tolist()] == res.Jset[b], f"Jset[{b}]"
+    np.testing.assert_allclose(errors, res.errors, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(tci.pivoterrors, res.pivoterrors, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(tci.bonderrors, res.bonderrors, rtol=1e-9, atol=1e-300)
+    assert tci.maxsamplevalue == res.maxsamplevalue
+    for b in range(n):
+        ref = res.sitetensors[b]
+        assert tci.sitetensors[b].shape == ref.shape
+        assert np.max(np.abs(tci.sitetensors[b] - ref)) <= RTOL * max(1.0, np.max(np.abs(ref)))
+    s_ref = res.sum()
+    assert abs(T.tci_sum(tci) - s_ref) <= RTOL * abs(s_ref)
+
+
+def test_crossinterpolate2_pivoterrors_diag(T):  # test_tensorci2.jl:27-39
+    table = np.diag(G.PIVOTERRORS_DIAGS).flatten(order="F")
+    f = T.BuiltinTarget(TABLE, table, [3, 3])
+    tci, ranks, errors = T.crossinterpolate2(f, [3, 3], [[1, 1]], tolerance=1e-8)
+    assert tci.pivoterrors.tolist() == G.PIVOTERRORS_DIAGS
+
+
+def test_crossinterpolate2_lorentz_matches_oracle(T, oracle):  # README.md:21-29 (config 1, 6 sites here)
+    ld = [10] * 6
+    f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, tolerance=1e-8, rng=T.CounterRNG(1))
+    res = oracle.crossinterpolate2(o, ld, tolerance=1e-8, seed=1)
+    compare_tci(tci, ranks, errors, res, T)
+    for v in itertools.product(range(1, 4), repeat=6):  # test_tensorci2.jl:335-339
+        fv = 1.0 / (1.0 + sum(x * x for x in v))
+        assert abs(tci(list(v)) - fv) <= 1e-6 * fv
+
+
+@pytest.mark.parametrize("strategy", ["backandforth", "forward"])
+def test_crossinterpolate2_quantics2d_matches_oracle(T, oracle, strategy):  # config 3, reduced to R=8
+    ld = [4] * 8
+    f, o = make_target(T, oracle, Q2D, [0, 8], ld)
+    kw = dict(tolerance=1e-9, maxbonddim=40, maxiter=6, sweepstrategy=strategy)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, **kw, rng=T.CounterRNG(3))
+    res = oracle.crossinterpolate2(o, ld, seed=3, **kw)
+    compare_tci(tci, ranks, errors, res, T)
+
+
+def test_crossinterpolate2_sepcos_matches_oracle(T, oracle):  # config 4 family, reduced
+    ld = [8] * 5
+    p = sepcos_params(5)
+    f, o = T.BuiltinTarget(SEPCOS, p, ld), oracle.Target.builtin(SEPCOS, p, ld)
+    kw = dict(tolerance=1e-10, maxbonddim=30, maxiter=5)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, **kw, rng=T.CounterRNG(4))
+    res = oracle.crossinterpolate2(o, ld, seed=4, **kw)
+    compare_tci(tci, ranks, errors, res, T)
+
+
+def test_crossinterpolate2_ttcache(T, oracle):  # test_tensorci2.jl:477-502
+    rng = np.random.default_rng(4)
+    dims = [2, 3, 3, 2]
+    cores = _rand_tt(rng, [1, 2, 3, 2, 1], dims)
+    f = T.TTCache(T.TensorTrain(cores))
+    tci, ranks, errors = T.crossinterpolate2(f, dims, tolerance=1e-10, maxbonddim=10)
+    full = T.fulltensor(T.TensorTrain(cores))
+    rec = T.fulltensor(T.TensorTrain(tci.sitetensors))
+    np.testing.assert_allclose(rec, full, rtol=1.5e-8, atol=1e-12)
+
+
+def test_integration_10d_known_answer(T):  # test_integration.jl:61-70
+    f = T.BuiltinTarget(GK, gk_params(), [15] * 10)
+    tci, ranks, errors = T.crossinterpolate2(f, [15] * 10, tolerance=1e-8, nsearchglobalpivot=10)
+    assert abs(T.tci_sum(tci) / 15.0**10 - G.INTEGRAL_10D_REF) < 1e-3
+
+
+def test_argument_errors(T):  # test_tensorci2.jl:215-245
+    f = T.BuiltinTarget(SUM, [], [2, 2, 2])
+    with pytest.raises(ValueError, match="convergence criterion is not reachable"):
+        T.crossinterpolate2(f, [2, 2, 2], tolerance=0.0)
+    with pytest.raises(RuntimeError, match="nsearchglobalpivot < maxnglobalpivot!"):
+        T.crossinterpolate2(f, [2, 2, 2], nsearchglobalpivot=2, maxnglobalpivot=5)
+    with pytest.raises(RuntimeError, match="at least 2 elements"):
+        T.TensorCI2(f, [2])
+    z = T.BuiltinTarget(TABLE, np.zeros(4), [2, 2])
+    with pytest.raises(RuntimeError, match="maxsamplevalue is zero!"):
+        T.TensorCI2(z, [2, 2])
