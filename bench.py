@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the TCI2 two-site hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Headline (BASELINE.json configs[1]): standalone full-pivot rrLU of a synthetic low-rank
+Float64 matrix, 8192 x 8192, maxrank 1024 (the largest single-GPU case of that config).
+A "step" is one rrlu(A; maxrank, reltol) of a fresh matrix that is already in HBM.
+`value` is GFLOP/s of the reference algorithm's flop count sum_k 2(m-k)(n-k).
+The per-bond rrLU does not shard (north_star: "stays on one GPU"), so with N > 1 every rank
+factorises its own replica (weak scaling, no data-path collective); the stages that do shard
+(Pi evaluation column blocks) are reported under "extra".
+
+One JSON line is printed by rank 0.  --impl reference times the CPU oracle (the restatement
+of the reference's Julia path; Julia itself cannot run in this image) on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE, RANK = 8192, 1024
+CPU_SAMPLE = (4096, 256)  # bounded CPU sample: ~12 s on one core
+REF_SAMPLE = (2048, 128)  # per-step sample of the reference arm
+
+
+def rrlu_flops(m, n, r):
+    return float(sum(2 * (m - k) * (n - k) for k in range(1, r + 1)))
+
+
+def rrlu_bytes(m, n, r):
+    """Algorithmic HBM bytes of one factorisation when the matrix is not on chip:
+    8mn for the first arg-max scan + 16 (m-k)(n-k) for every trailing update that is needed
+    (the update after the last pivot never reaches L or U and is skipped)."""
+    return float(8 * m * n + sum(16 * (m - k) * (n - k) for k in range(1, r)))
+
+
+def factors(m, n, r, seed):
+    rng = np.random.default_rng(seed)
+    p = rng.random((m, r))
+    q = rng.random((r, n))
+    s = 2.0 ** (-40.0 * np.arange(1, r + 1) / r)
+    return p * s, q
+
+
+def lowrank_host(m, n, r, seed):
+    p, q = factors(m, n, r, seed)
+    return np.asfortranarray(p @ q)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of matrixlu.jl (single thread, as the Julia loops are)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    m, r = REF_SAMPLE
+    A = lowrank_host(m, m, r, 2)
+    for _ in range(max(1, min(args.warmup, 1))):
+        orc.rrlu(A, maxrank=r, reltol=1e-12)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lu = orc.rrlu(A, maxrank=r, reltol=1e-12)
+    dt = time.perf_counter() - t0
+    assert lu.npivot == r
+    val = args.steps * rrlu_flops(m, m, r) / dt / 1e9
+    sample = f"rrlu {m}x{m} maxrank {r} per step (same generator as the {SIZE}x{SIZE} r={RANK} workload)"
+    out = {"metric": "rrLU FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Mevals/s; contraction in extra)",
+           "value": val, "unit": "GFLOP/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"rrlu standalone, synthetic low-rank Float64 {SIZE}x{SIZE}, maxrank {RANK}, "
+                                  "reltol 1e-12 (BASELINE configs[1])", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--rank", type=int, default=RANK)
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import tci_b200 as T
+    ctx = T.default_context()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    m = n = args.size
+    r = args.rank
+    K, W = args.steps, max(args.warmup, 3)
+    # synthetic input: p (m x r) * q (r x n) formed on the device in FP64 (input generation, untimed)
+    p, q = factors(m, n, r, 2 + rank)
+    Ad = (torch.from_numpy(p).cuda() @ torch.from_numpy(q).cuda()).t().contiguous()  # column-major m x n
+    torch.cuda.synchronize()
+    A_host_t = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+    A_host_t.copy_(Ad)
+    A_host = A_host_t.numpy().T  # Fortran-ordered view of pinned memory
+    del Ad
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg: K fresh matrices already in HBM -----------------
+    mats = [T.DeviceMatrix.from_host(ctx, A_host) for _ in range(K + W)]
+    for i in range(W):
+        lu = T.rrlu(mats[i], maxrank=r, reltol=1e-12)
+        del lu
+    ctx.timers(reset=True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    npiv = 0
+    for i in range(W, W + K):
+        lu = T.rrlu(mats[i], maxrank=r, reltol=1e-12)
+        npiv = lu.npivot
+        del lu
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.finish()
+    launches = ctx.launches - launches0
+    tm = ctx.timers(reset=True)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert npiv == r, (npiv, r)
+    flops = rrlu_flops(m, n, r)
+    value = world * K * flops / (ms * 1e-3) / 1e9
+    kernel_ms = tm["rrlu_kernel"] / K
+    peak, which = peaks()
+    achieved = rrlu_bytes(m, n, r) / (kernel_ms * 1e-3) / 1e9
+    del mats
+
+    # ---------------- end to end: host buffers through the C ABI, copies inside -------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        lu = T.rrlu(A_host, maxrank=r, reltol=1e-12)
+        L, U = lu.L, lu.U
+        del lu
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * K * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(8 * m * n),
+           "d2h_bytes_per_step": int(8 * (m * r + r * n) + 8 * (m + n) + 8 * (r + 1)),
+           "ms_per_step": e2e_s / K * 1e3}
+    del L, U
+
+    extra = {}
+    if not args.no_extra:
+        extra = run_extra(T, ctx, torch, dist, rank, world, stream)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        cm, cr = CPU_SAMPLE
+        Ac = lowrank_host(cm, cm, cr, 2)
+        t0 = time.perf_counter()
+        ref = orc.rrlu(Ac, maxrank=cr, reltol=1e-12)
+        dt = time.perf_counter() - t0
+        cpu = {"value": rrlu_flops(cm, cm, cr) / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+               "sample": f"one rrlu {cm}x{cm} maxrank {cr} (same generator), {dt:.1f} s on one host core; "
+                         f"the reference's loops are single threaded (matrixlu.jl)"}
+        # the same sample on the GPU must give the same pivots
+        lu = T.rrlu(Ac, maxrank=cr, reltol=1e-12)
+        cpu["pivots_identical_to_gpu"] = bool(np.array_equal(lu.rowpermutation, ref.rowpermutation) and
+                                              np.array_equal(lu.colpermutation, ref.colpermutation))
+    if rank == 0:
+        out = {"metric": "rrLU FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Mevals/s; contraction in extra)",
+               "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"rrlu standalone, synthetic low-rank Float64 {m}x{n}, maxrank {r}, "
+                                      "reltol 1e-12 (BASELINE configs[1])",
+                          "l2": "input 537 MB per step exceeds the 126 MB L2; every step uses a fresh matrix",
+                          "parallelism": "replicas only (rrLU does not shard)" if world > 1 else "single GPU",
+                          "exact_mode": True},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": which,
+                            "kernel": "k_rrlu<true>", "kernel_ms": kernel_ms,
+                            "algorithmic_bytes": rrlu_bytes(m, n, r),
+                            "fp64_gflops_kernel": flops / (kernel_ms * 1e-3) / 1e9},
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+               "stage_ms_per_step": {k: v / K for k, v in tm.items()}, "extra": extra}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extra(T, ctx, torch, dist, rank, world, stream):
+    """Secondary numbers of the composite metric: Pi-eval Mevals/s (config 4 shape, column blocks
+    sharded over ranks), DGEMM GFLOP/s (the contraction building block), and the README config 1
+    crossinterpolate2 time-to-tolerance."""
+    extra = {}
+    rng = np.random.default_rng(7)
+    # --- Pi-eval, 12 sites d=64, Lorentzian (cheap target: HBM-write bound) ---
+    ld = [64] * 12
+    nI, nJ = 16384, 16384
+    I = np.stack([rng.integers(1, 65, nI) for _ in range(6)], axis=1).astype(np.int64)
+    J = np.stack([rng.integers(1, 65, nJ) for _ in range(6)], axis=1).astype(np.int64)
+    Jloc = np.ascontiguousarray(J[rank::world])
+    for name, kind, params in (("lorentz", T.LORENTZ, [1.0]), ("sepcos", T.SEPCOS, None)):
+        if params is None:
+            g = np.random.default_rng(4)
+            params = np.concatenate([[4], g.integers(1, 1025, 12) / 256.0, g.integers(-512, 513, 4) / 1024.0,
+                                     (g.integers(-1024, 1025, (4, 12)) / 32.0).flatten()])
+        f = T.BuiltinTarget(kind, params, ld)
+        for _ in range(3):
+            dev, mx = f.batchevaluate_device(I, Jloc, 0)
+            del dev
+        ctx.timers(reset=True)
+        reps = 5
+        for _ in range(reps):
+            dev, mx = f.batchevaluate_device(I, Jloc, 0)
+            del dev
+        ms = ctx.timers(reset=True)["pi_eval"] / reps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        evals = nI * nJ
+        extra[f"pi_eval_{name}"] = {"mevals_per_s": evals / (ms * 1e-3) / 1e6, "ms": ms,
+                                    "shape": [nI, nJ], "hbm_gbs": 8 * evals / (ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": 8 * evals / (ms * 1e-3) / 1e9 / peaks()[0] / world}
+    # --- DGEMM 4096^3 through the device path (GEMM inside tci_dgemm_host is timed by stage) ---
+    if rank == 0:
+        N = 4096
+        A = np.asfortranarray(rng.standard_normal((N, N)))
+        B = np.asfortranarray(rng.standard_normal((N, N)))
+        C = np.zeros((N, N), order="F")
+        from tci_b200 import _lib
+        for _ in range(2):
+            ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
+        ctx.timers(reset=True)
+        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
+        ms = ctx.timers(reset=True)["gemm"]
+        extra["dgemm_4096"] = {"gflops": 2.0 * N ** 3 / (ms * 1e-3) / 1e9, "ms": ms}
+        a = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        b = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            c = a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            c = a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        extra["cublas_dgemm_4096_gflops"] = 5 * 2.0 * N ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        # --- config 1: README 8-d Lorentzian, time to tolerance 1e-8 ---
+        f = T.BuiltinTarget(T.LORENTZ, [1.0], [10] * 8)
+        T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
+        t0 = time.perf_counter()
+        tci, ranks, errors = T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
+        extra["crossinterpolate2_config1"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks[-1]),
+                                              "iterations": len(ranks), "error": float(errors[-1])}
+    return extra
+
+
+if __name__ == "__main__":
+    main()

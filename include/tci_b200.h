@@ -50,8 +50,10 @@ void tci_ctx_destroy(tci_ctx *ctx);
 const char *tci_last_error(tci_ctx *ctx); /* ctx may be NULL: last create error */
 /* number of kernels this context launched since creation (bench gpu_launches) */
 int64_t tci_ctx_launches(tci_ctx *ctx);
+/* the cudaStream_t all work of this context is issued on (for event timing by the host layer) */
+void *tci_ctx_stream(tci_ctx *ctx);
 /* accumulated CUDA-event time per stage in ms; stages: 0 pi_eval, 1 rrlu, 2 luci,
- * 3 tt/mpo environments, 4 globalsearch, 5 gemm, 6 h2d, 7 d2h.  Stands in for the
+ * 3 tt/mpo environments, 4 globalsearch, 5 gemm, 6 h2d, 7 d2h, 8 the rrLU kernel alone.  Stands in for the
  * time_ns() pairs around "Computing Pi"/"LU" (tensorci2.jl:530-550).              */
 int tci_timers(tci_ctx *ctx, double *out, int64_t n, int reset);
 

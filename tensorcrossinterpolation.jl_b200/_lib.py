@@ -26,6 +26,7 @@ SYMBOLS = {
     "tci_ctx_destroy": (None, [VP]),
     "tci_last_error": (C.c_char_p, [VP]),
     "tci_ctx_launches": (i64, [VP]),
+    "tci_ctx_stream": (VP, [VP]),
     "tci_timers": (C.c_int, [VP, P_f64, i64, C.c_int]),
     "tci_dmat_create": (C.c_int, [VP, i64, i64, P_f64, C.POINTER(VP)]),
     "tci_dmat_shape": (C.c_int, [VP, P_i64, P_i64, P_i64]),
@@ -113,13 +114,18 @@ class Context:
             raise TCIError(rc, msg)
 
     @property
+    def stream(self):
+        """cudaStream_t of this context as an integer (wrap with torch.cuda.ExternalStream)."""
+        return int(lib().tci_ctx_stream(self.h) or 0)
+
+    @property
     def launches(self):
         return int(lib().tci_ctx_launches(self.h))
 
     def timers(self, reset=False):
-        out = np.zeros(8, dtype=np.float64)
-        lib().tci_timers(self.h, pf(out), 8, int(reset))
-        names = ["pi_eval", "rrlu", "luci", "env", "globalsearch", "gemm", "h2d", "d2h"]
+        out = np.zeros(9, dtype=np.float64)
+        lib().tci_timers(self.h, pf(out), 9, int(reset))
+        names = ["pi_eval", "rrlu", "luci", "env", "globalsearch", "gemm", "h2d", "d2h", "rrlu_kernel"]
         return dict(zip(names, out.tolist()))
 
     def close(self):

@@ -36,6 +36,7 @@ extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
         cudaMalloc(&c->rr_barrier, 64 * sizeof(unsigned)) != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
         delete c;
@@ -70,6 +71,8 @@ extern "C" void tci_ctx_destroy(tci_ctx *ctx)
     cudaFree(ctx->rr_barrier);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev2);
+    cudaEventDestroy(ctx->ev3);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -77,6 +80,8 @@ extern "C" void tci_ctx_destroy(tci_ctx *ctx)
 extern "C" const char *tci_last_error(tci_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int64_t tci_ctx_launches(tci_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void *tci_ctx_stream(tci_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int tci_timers(tci_ctx *ctx, double *out, int64_t n, int reset)
 {

@@ -458,7 +458,9 @@ static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bo
     void *kargs[] = {&args};
     const void *fn = exact ? (const void *)k_rrlu<true> : (const void *)k_rrlu<false>;
     TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(ctx->ev2, ctx->stream);
     TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), kargs, smem, ctx->stream));
+    cudaEventRecord(ctx->ev3, ctx->stream);
     ctx->launches++;
     return TCI_OK;
 }
@@ -552,6 +554,10 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         TCI_CUDA(ctx, cudaMemcpyAsync(res, result.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TCI_CUDA(ctx, cudaMemcpyAsync(&lu_error, d_err.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        {
+            float kms = 0.f;
+            if (cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_RRLU_KERNEL] += kms;
+        }
         const int r = res[0];
         unsigned blocks = (unsigned)std::min<i64>((m * n + 255) / 256, (i64)ctx->sm_count * 8);
         k_nancheck<<<blocks, 256, 0, ctx->stream>>>(A->p, m, n, A->ld, colpos.p, r, result.p + 2);

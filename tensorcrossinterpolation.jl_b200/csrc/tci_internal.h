@@ -14,7 +14,7 @@
 
 typedef int64_t i64;
 
-enum { ST_PI = 0, ST_RRLU = 1, ST_LUCI = 2, ST_ENV = 3, ST_GSEARCH = 4, ST_GEMM = 5, ST_H2D = 6, ST_D2H = 7, ST_COUNT = 8 };
+enum { ST_PI = 0, ST_RRLU = 1, ST_LUCI = 2, ST_ENV = 3, ST_GSEARCH = 4, ST_GEMM = 5, ST_H2D = 6, ST_D2H = 7, ST_RRLU_KERNEL = 8, ST_COUNT = 9 };
 
 struct tci_dmat {
     tci_ctx *ctx = nullptr;
@@ -43,7 +43,7 @@ struct tci_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     std::mutex mu;
     bool busy = false;
