@@ -42,11 +42,13 @@
 #define TCI_ADD(a, b) __dadd_rn((a), (b))
 #define TCI_SUB(a, b) __dsub_rn((a), (b))
 #define TCI_DIV(a, b) __ddiv_rn((a), (b))
+#define TCI_RCP(a) __drcp_rn((a))
 #else
 #define TCI_MUL(a, b) ((a) * (b))
 #define TCI_ADD(a, b) ((a) + (b))
 #define TCI_SUB(a, b) ((a) - (b))
 #define TCI_DIV(a, b) ((a) / (b))
+#define TCI_RCP(a) (1.0 / (a))
 #endif
 
 #define TCI_MAX_STATE 6
@@ -268,7 +270,9 @@ TCI_HD double tci_target_finalize(const tci_analytic_t *t, const double *s)
     switch (t->kind) {
     case TCI_TARGET_LORENTZ: {
         double coeff = (t->nparams > 0) ? p[0] : 1.0;
-        return TCI_DIV(coeff, TCI_ADD(s[0], 1.0));
+        double den = TCI_ADD(s[0], 1.0);
+        /* 1/den correctly rounded is the same number whichever way it is computed */
+        return coeff == 1.0 ? TCI_RCP(den) : TCI_DIV(coeff, den);
     }
     case TCI_TARGET_SUM:
         return s[0];

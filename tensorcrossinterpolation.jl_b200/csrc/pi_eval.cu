@@ -74,13 +74,15 @@ __device__ __forceinline__ void block_max_commit(unsigned long long mx, unsigned
 
 // Exact targets: state(I ++ c ++ J) = rowstate + centrestate + colstate, bit-identical to
 // the sequential definition because all partial sums are exact.
-template <int NS>
+template <int NS, int KIND>
 __global__ void __launch_bounds__(PI_THREADS)
-    k_pi_exact(tci_analytic_t t, const double *__restrict__ rs, i64 nI, const double *__restrict__ cs, i64 C,
+    k_pi_exact(tci_analytic_t targ, const double *__restrict__ rs, i64 nI, const double *__restrict__ cs, i64 C,
                const double *__restrict__ js, i64 nJ, double *__restrict__ out, i64 ld, unsigned long long *gmax)
 {
     __shared__ double colst[NS][PI_TCOLS];
     __shared__ i64 coloff[PI_TCOLS];
+    tci_analytic_t t = targ;
+    t.kind = KIND; // compile-time kind: the switch in tci_target_finalize folds away
     const i64 ncols = C * nJ;
     const i64 q0 = (i64)blockIdx.y * PI_TCOLS;
     if (threadIdx.x < PI_TCOLS) {
@@ -165,12 +167,12 @@ __global__ void __launch_bounds__(PI_THREADS)
     block_max_commit(mx, gmax);
 }
 
-template <int NS>
+template <int NS, int KIND>
 static void launch_exact(tci_ctx *ctx, const tci_analytic_t &an, const double *rs, i64 nI, const double *cs, i64 C,
                          const double *js, i64 nJ, double *out, i64 ld, unsigned long long *gmax)
 {
     dim3 grid((unsigned)((nI + 2 * PI_THREADS - 1) / (2 * PI_THREADS)), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
-    k_pi_exact<NS><<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs, nI, cs, C, js, nJ, out, ld, gmax);
+    k_pi_exact<NS, KIND><<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs, nI, cs, C, js, nJ, out, ld, gmax);
     ctx->launches++;
 }
 
@@ -197,15 +199,27 @@ int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, 
         TCI_CUDA(ctx, js.alloc((size_t)NS * nJ));
         k_states<<<(unsigned)((nJ + TB - 1) / TB), TB, 0, ctx->stream>>>(an, dJ, (int)nr, nJ, (int)(nl + M), 0, js.p);
         ctx->launches++;
-        switch (NS) {
-        case 1: launch_exact<1>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        case 2: launch_exact<2>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        case 3: launch_exact<3>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        case 4: launch_exact<4>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        case 5: launch_exact<5>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        case 6: launch_exact<6>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits); break;
-        default: return tci_fail(ctx, TCI_ERR_ARG, "target has an unsupported number of state sums");
+#define PI_LAUNCH(NSV, KINDV) launch_exact<NSV, KINDV>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits)
+        switch (an.kind) {
+        case TCI_TARGET_LORENTZ: PI_LAUNCH(1, TCI_TARGET_LORENTZ); break;
+        case TCI_TARGET_SUM: PI_LAUNCH(1, TCI_TARGET_SUM); break;
+        case TCI_TARGET_QUANTICS2D: PI_LAUNCH(2, TCI_TARGET_QUANTICS2D); break;
+        case TCI_TARGET_TABLE: PI_LAUNCH(1, TCI_TARGET_TABLE); break;
+        case TCI_TARGET_QUANTICS1D: PI_LAUNCH(1, TCI_TARGET_QUANTICS1D); break;
+        case TCI_TARGET_SEPCOS:
+            switch (NS) {
+            case 1: PI_LAUNCH(1, TCI_TARGET_SEPCOS); break;
+            case 2: PI_LAUNCH(2, TCI_TARGET_SEPCOS); break;
+            case 3: PI_LAUNCH(3, TCI_TARGET_SEPCOS); break;
+            case 4: PI_LAUNCH(4, TCI_TARGET_SEPCOS); break;
+            case 5: PI_LAUNCH(5, TCI_TARGET_SEPCOS); break;
+            case 6: PI_LAUNCH(6, TCI_TARGET_SEPCOS); break;
+            default: return tci_fail(ctx, TCI_ERR_ARG, "target has an unsupported number of state sums");
+            }
+            break;
+        default: return tci_fail(ctx, TCI_ERR_ARG, "unknown exact target kind");
         }
+#undef PI_LAUNCH
     } else {
         dim3 grid((unsigned)((nI + PI_THREADS - 1) / PI_THREADS), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
         k_pi_sequential<<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs.p, nI, (int)nl, (int)M, C, csig.p, dJ, (int)nr,

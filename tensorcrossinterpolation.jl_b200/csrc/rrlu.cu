@@ -32,6 +32,7 @@
 
 #define RR_MAX_THREADS 1024
 #define RR_XS_CAP 24576 // doubles of shared memory for the pivot column
+#define RR_U 4          // 16-byte loads in flight per lane in the trailing update
 
 struct __align__(16) RRCand {
     double v;   // abs2 of the candidate
@@ -269,48 +270,55 @@ template <bool EXACT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrl
         double bv = -INFINITY;
         int bcp = 0x7fffffff, brow = 0x7fffffff, bcol = -1;
         if (nact > 0) {
-            const int ncw = nact < nwarps ? nact : nwarps;
-            const int nrw = nwarps / ncw;
-            const int wc = warp % ncw, wr = warp / ncw;
-            if (wr < nrw) {
-                const i64 i0 = lo & ~1;
-                const i64 npairs = (m - i0 + 1) >> 1;
-                for (i64 pp = (i64)wr * 32 + lane; pp < npairs; pp += (i64)nrw * 32) {
-                    const i64 i = i0 + 2 * pp;
-                    const bool v0ok = i >= lo, v1ok = i + 1 < m;
-                    double x0 = 0.0, x1 = 0.0;
-                    if (do_update) {
-                        if (a.xs_in_smem) {
-                            x0 = v0ok ? xs[i] : 0.0;
-                            x1 = v1ok ? xs[i + 1] : 0.0;
-                        } else {
-                            x0 = v0ok ? __ldcg(xw + (i == pr ? s : i)) : 0.0;
-                            x1 = v1ok ? __ldcg(xw + (i + 1 == pr ? s : i + 1)) : 0.0;
-                        }
-                    }
-#pragma unroll 4
-                    for (int e = wc; e < nact; e += ncw) {
-                        double2 *p = reinterpret_cast<double2 *>(A + (size_t)ld * actc[e] + i);
-                        double2 d = *p;
+            // Tiles of RR_U*64 rows x 1 column are dealt round-robin to the warps; a lane issues its
+            // RR_U 16-byte loads back to back so that enough bytes are in flight to cover HBM latency.
+            const i64 i0 = lo & ~1;
+            const int ntr = (int)((m - i0 + RR_U * 64 - 1) / (RR_U * 64));
+            const i64 ntiles = (i64)nact * ntr;
+            for (i64 t = warp; t < ntiles; t += nwarps) {
+                const int e = (int)(t / ntr);
+                const int rt = (int)(t - (i64)e * ntr);
+                const int col = actc[e], cp = actp[e];
+                const double y = do_update ? ys[e] : 0.0;
+                double *const cptr = A + (size_t)ld * col;
+                const i64 base = i0 + (i64)rt * (RR_U * 64) + 2 * lane;
+                double2 d[RR_U];
+#pragma unroll
+                for (int u = 0; u < RR_U; ++u) {
+                    const i64 i = base + u * 64;
+                    if (i < m) d[u] = *reinterpret_cast<const double2 *>(cptr + i);
+                }
+#pragma unroll
+                for (int u = 0; u < RR_U; ++u) {
+                    const i64 i = base + u * 64;
+                    if (i < m) {
+                        const bool v0ok = i >= lo, v1ok = i + 1 < m;
                         if (do_update) {
-                            const double y = ys[e];
-                            if (v0ok) d.x = schur<EXACT>(d.x, x0, y);
-                            if (v1ok) d.y = schur<EXACT>(d.y, x1, y);
-                            *p = d;
+                            double x0, x1;
+                            if (a.xs_in_smem) {
+                                const double2 xx = *reinterpret_cast<const double2 *>(xs + i);
+                                x0 = xx.x;
+                                x1 = xx.y;
+                            } else {
+                                x0 = v0ok ? __ldcg(xw + (i == pr ? s : i)) : 0.0;
+                                x1 = v1ok ? __ldcg(xw + (i + 1 == pr ? s : i + 1)) : 0.0;
+                            }
+                            if (v0ok) d[u].x = schur<EXACT>(d[u].x, x0, y);
+                            if (v1ok) d[u].y = schur<EXACT>(d[u].y, x1, y);
+                            *reinterpret_cast<double2 *>(cptr + i) = d[u];
                         }
-                        const int cp = actp[e];
-                        const double q0 = d.x * d.x, q1 = d.y * d.y;
+                        const double q0 = d[u].x * d[u].x, q1 = d[u].y * d[u].y;
                         if (v0ok && q0 >= bv && cand_better(q0, cp, (int)i, bv, bcp, brow)) {
                             bv = q0;
                             bcp = cp;
                             brow = (int)i;
-                            bcol = actc[e];
+                            bcol = col;
                         }
                         if (v1ok && q1 >= bv && cand_better(q1, cp, (int)i + 1, bv, bcp, brow)) {
                             bv = q1;
                             bcp = cp;
                             brow = (int)i + 1;
-                            bcol = actc[e];
+                            bcol = col;
                         }
                     }
                 }
