@@ -283,7 +283,9 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
     nI, nJ = 16384, 16384
     I = np.stack([rng.integers(1, 65, nI) for _ in range(6)], axis=1).astype(np.int64)
     J = np.stack([rng.integers(1, 65, nJ) for _ in range(6)], axis=1).astype(np.int64)
-    Jloc = np.ascontiguousarray(J[rank::world])
+    from tci_b200.parallel import column_blocks, gather_column_blocks
+    blk, ranges = column_blocks(nJ, world)
+    Jloc = np.ascontiguousarray(J[ranges[rank][0]:ranges[rank][1]])
     for name, kind, params in (("lorentz", T.LORENTZ, [1.0]), ("sepcos", T.SEPCOS, None)):
         if params is None:
             g = np.random.default_rng(4)
@@ -306,7 +308,29 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         evals = nI * nJ
         extra[f"pi_eval_{name}"] = {"mevals_per_s": evals / (ms * 1e-3) / 1e6, "ms": ms,
                                     "shape": [nI, nJ], "hbm_gbs": 8 * evals / (ms * 1e-3) / 1e9,
-                                    "frac_of_hbm_peak": 8 * evals / (ms * 1e-3) / 1e9 / peaks()[0] / world}
+                                    "frac_of_hbm_peak": 8 * evals / (ms * 1e-3) / 1e9 / peaks()[0] / world,
+                                    "sharding": f"column blocks over {world} rank(s), kernel time only"}
+        if world > 1 and name == "lorentz":
+            # the same evaluation written into the shared buffer + ONE in-place NCCL all-gather
+            full = T.DeviceMatrix.empty(ctx, nI, blk * world)
+            fv = torch.as_tensor(full, device=torch.device("cuda", ctx.device))
+            for it in range(4):
+                if it == 1:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                f.batchevaluate_into(full, rank * blk, I, Jloc, 0)
+                gather_column_blocks(dist, torch, fv, blk, rank)
+                torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            extra["pi_eval_lorentz_sharded_gathered"] = {
+                "mevals_per_s": evals / dt / 1e6, "ms": dt * 1e3,
+                "allgather_bytes_per_rank": int(8 * fv.shape[1] * blk * (world - 1)),
+                "note": "evaluate own column block + all-gather so that every rank holds Pi"}
+            del full, fv
     # --- DGEMM 4096^3 through the device path (GEMM inside tci_dgemm_host is timed by stage) ---
     if rank == 0:
         N = 4096

@@ -63,6 +63,8 @@ int tci_dmat_shape(tci_dmat *a, int64_t *m, int64_t *n, int64_t *ld);
 void *tci_dmat_ptr(tci_dmat *a); /* raw device pointer, for collectives on the host layer */
 int tci_dmat_fetch(tci_dmat *a, double *host /* m x n, tight */);
 int tci_dmat_destroy(tci_dmat *a);
+/* shrink the logical column count (n <= allocated columns); used after an all-gather of padded blocks */
+int tci_dmat_resize_cols(tci_dmat *a, int64_t n);
 
 /* ---- targets: the function f being interpolated ------------------------- */
 /* Replaces the Julia closure / BatchEvaluator object `f` (cachedtensortrain.jl:1,
@@ -93,6 +95,12 @@ int tci_target_eval(tci_ctx *ctx, int64_t target_id, const int64_t *idx, int64_t
  * device matrix of shape (nI*C) x nJ that can be handed to tci_rrlu.             */
 int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
                 int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs);
+
+/* Same evaluation written into columns [col0, col0+nJ) of an existing device matrix whose row count
+ * is nI*C: the column-block form used when Pi is sharded over GPUs; every rank fills its
+ * own block of the buffer that is all-gathered for the rrLU owner.                                  */
+int tci_pi_eval_into(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                     int64_t nr, int64_t nJ, int64_t M, tci_dmat *dst, int64_t col0, double *maxabs);
 
 /* ---- (b) rank-revealing LU / MatrixLUCI ---------------------------------- */
 /* rrlu(A; maxrank, reltol, abstol, leftorthogonal) (matrixlu.jl:194-225) with the
@@ -138,10 +146,11 @@ int tci_contract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s
  * sum_p d_p probes |f(x) - tt(x)|, first maximum kept, accepted if > threshold
  * (= abstol * tolmarginglobalsearch), truncated to the first maxn in start order.
  * cores: the current tensor train (host, dims3 as in tci_tt_create).
- * pivots_out: n x maxn, errs_out: maxn.                                           */
+ * pivots_out: n x maxn, errs_out: maxn, start_idx_out (nullable): maxn, the 0-based start each
+ * accepted pivot came from (lets the host merge the candidates of sharded searches in start order). */
 int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
                      const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
-                     int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *nfound);
+                     int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out, int64_t *nfound);
 /* evaluate(tt, x) for `count` points, left-to-right (abstracttensortrain.jl:124-132) */
 int tci_tt_evaluate(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
                     const int64_t *idx, int64_t count, double *out);

@@ -33,12 +33,14 @@ SYMBOLS = {
     "tci_dmat_ptr": (VP, [VP]),
     "tci_dmat_fetch": (C.c_int, [VP, P_f64]),
     "tci_dmat_destroy": (C.c_int, [VP]),
+    "tci_dmat_resize_cols": (C.c_int, [VP, i64]),
     "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
     "tci_target_destroy": (C.c_int, [VP, i64]),
     "tci_target_eval": (C.c_int, [VP, i64, P_i64, i64, P_f64]),
     "tci_pi_eval": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, P_f64, C.POINTER(VP), P_f64]),
+    "tci_pi_eval_into": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, VP, i64, P_f64]),
     "tci_rrlu": (C.c_int, [VP, P_f64, VP, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64, P_i64, P_i64, P_f64,
                            P_f64, C.POINTER(VP)]),
     "tci_lu_fetch": (C.c_int, [VP, P_f64, P_f64]),
@@ -49,7 +51,7 @@ SYMBOLS = {
     "tci_contract_zipup_site": (C.c_int, [VP, P_f64, i64, i64, i64, P_f64, i64, i64, i64, P_f64, i64, i64, P_f64,
                                           C.POINTER(VP)]),
     "tci_contract_naive_site": (C.c_int, [VP, P_f64, i64, i64, i64, i64, P_f64, i64, i64, i64, P_f64]),
-    "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, PP_f64, P_i64, i64, f64, i64, P_i64, P_f64, P_i64]),
+    "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, PP_f64, P_i64, i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),
     "tci_tt_evaluate": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, i64, P_f64]),
 }
 
@@ -198,6 +200,9 @@ class DeviceMatrix:
         if m * n:
             self.ctx.check(lib().tci_dmat_fetch(self.h, pf(out)))
         return out
+
+    def resize_cols(self, n):
+        self.ctx.check(lib().tci_dmat_resize_cols(self.h, int(n)))
 
     def release(self):
         """Give up ownership (the handle was consumed by tci_rrlu)."""

@@ -70,6 +70,16 @@ class BatchEvaluator:
         _, dev, mx = self._pi(leftindexset, rightindexset, M, False, True)
         return dev, mx
 
+    def batchevaluate_into(self, dst, col0, leftindexset, rightindexset, M):
+        """Column-block form (tci_pi_eval_into): fills dst[:, col0:col0+len(J)], returns max|block|."""
+        I, J = as_indexset(leftindexset), as_indexset(rightindexset)
+        if len(I) * len(J) == 0:
+            return 0.0
+        mx = C.c_double(0.0)
+        self.ctx.check(lib().tci_pi_eval_into(self.ctx.h, self.id, pi(I), I.shape[1], I.shape[0], pi(J), J.shape[1],
+                                              J.shape[0], M, dst.h, int(col0), C.byref(mx)))
+        return mx.value
+
     def __del__(self):
         try:
             lib().tci_target_destroy(self.ctx.h, self.id)

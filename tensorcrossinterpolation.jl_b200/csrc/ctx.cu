@@ -99,6 +99,7 @@ int dmat_alloc(tci_ctx *ctx, i64 m, i64 n, tci_dmat **out)
     a->ctx = ctx;
     a->m = m;
     a->n = n;
+    a->ncap = n;
     a->ld = round_up(m > 0 ? m : 1, 16); // every column starts on a 128 B boundary
     size_t bytes = (size_t)a->ld * (size_t)(n > 0 ? n : 1) * sizeof(double);
     cudaError_t e = dev_alloc(ctx, (void **)&a->p, bytes);
@@ -137,6 +138,13 @@ extern "C" int tci_dmat_shape(tci_dmat *a, int64_t *m, int64_t *n, int64_t *ld)
     if (m) *m = a->m;
     if (n) *n = a->n;
     if (ld) *ld = a->ld;
+    return TCI_OK;
+}
+
+extern "C" int tci_dmat_resize_cols(tci_dmat *a, int64_t n)
+{
+    if (!a || n < 0 || n > a->ncap) return TCI_ERR_ARG;
+    a->n = n;
     return TCI_OK;
 }
 

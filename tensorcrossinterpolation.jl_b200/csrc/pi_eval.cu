@@ -253,10 +253,10 @@ int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned lon
     return TCI_OK;
 }
 
-extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
-                           int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs)
+static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                        int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, tci_dmat *dst,
+                        int64_t col0, double *maxabs)
 {
-    TCI_ENTER(ctx);
     if (out_dev) *out_dev = nullptr;
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
@@ -271,6 +271,8 @@ extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, in
     if ((nl > 0 && !I) || (nr > 0 && !J)) return tci_fail(ctx, TCI_ERR_ARG, "index sets missing");
     i64 C = 1;
     for (i64 k = 0; k < M; ++k) C *= t.localdims[nl + k];
+    if (dst && (dst->m != nI * C || col0 < 0 || col0 + nJ > dst->ncap))
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_eval_into: destination block does not fit");
 
     DevBuf<i64> dI(ctx), dJ(ctx);
     DevBuf<unsigned long long> dmax(ctx);
@@ -282,8 +284,18 @@ extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, in
         TCI_CUDA(ctx, cudaMemsetAsync(dmax.p, 0, sizeof(unsigned long long), ctx->stream));
     }
     tci_dmat *out = nullptr;
-    int rc = dmat_alloc(ctx, nI * C, nJ, &out);
-    if (rc) return rc;
+    tci_dmat view; // column block of dst
+    int rc = 0;
+    if (dst) {
+        view = *dst;
+        view.p = dst->p + dst->ld * col0;
+        view.n = nJ;
+        view.owned = false;
+        out = &view;
+    } else {
+        rc = dmat_alloc(ctx, nI * C, nJ, &out);
+        if (rc) return rc;
+    }
     {
         StageTimer tm(ctx, ST_PI);
         switch (t.kind) {
@@ -299,7 +311,7 @@ extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, in
         }
     }
     if (rc) {
-        tci_dmat_destroy(out);
+        if (!dst) tci_dmat_destroy(out);
         return rc;
     }
     {
@@ -318,11 +330,28 @@ extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, in
         }
         TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (dst) return TCI_OK;
     if (out_dev)
         *out_dev = out;
     else
         tci_dmat_destroy(out);
     return TCI_OK;
+}
+
+extern "C" int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                           int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs)
+{
+    TCI_ENTER(ctx);
+    return pi_eval_core(ctx, target_id, I, nl, nI, J, nr, nJ, M, out_host, out_dev, nullptr, 0, maxabs);
+}
+
+extern "C" int tci_pi_eval_into(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI,
+                                const int64_t *J, int64_t nr, int64_t nJ, int64_t M, tci_dmat *dst, int64_t col0,
+                                double *maxabs)
+{
+    TCI_ENTER(ctx);
+    if (!dst) return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_eval_into: dst missing");
+    return pi_eval_core(ctx, target_id, I, nl, nI, J, nr, nJ, M, nullptr, nullptr, dst, col0, maxabs);
 }
 
 // ---- scalar evaluation f(x) for a batch of full multi-indices ---------------

@@ -20,6 +20,7 @@ struct tci_dmat {
     tci_ctx *ctx = nullptr;
     double *p = nullptr;
     i64 m = 0, n = 0, ld = 0;
+    i64 ncap = 0; // allocated columns
     bool owned = true;
 };
 

@@ -258,7 +258,8 @@ __global__ void k_abs_diff(const double *__restrict__ f, const double *__restric
 
 extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
                                 const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
-                                int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *nfound)
+                                int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out,
+                                int64_t *nfound)
 {
     TCI_ENTER(ctx);
     if (!nfound) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: nfound missing");
@@ -314,6 +315,7 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites,
             const i64 *x = bestq >= 0 ? pts.data() + bestq * nsites : starts + s * nsites;
             for (i64 k = 0; k < nsites; ++k) pivots_out[k + found * nsites] = x[k];
             errs_out[found] = best;
+            if (start_idx_out) start_idx_out[found] = s;
             ++found;
         }
     }

@@ -47,14 +47,28 @@ class DefaultGlobalPivotFinder(AbstractGlobalPivotFinder):  # :100-195
         keep, arr = core_ptrs([c.reshape((c.shape[0], -1, c.shape[-1]), order="F")
                                for c in input.current_tt.sitetensors])
         d3 = _dims3(keep)
+        world, rank = getattr(f, "world", 1), getattr(f, "rank", 0)
+        mine = np.arange(rank, starts.shape[0], world)  # independent starts, dealt round-robin
+        local = np.ascontiguousarray(starts[mine])
         # the reference collects every accepted point and then truncates (:186-188)
-        piv = np.zeros((self.maxnglobalpivot, n), dtype=np.int64)
-        errs = np.zeros(self.maxnglobalpivot, dtype=np.float64)
+        cap = max(len(mine), 1) if world > 1 else self.maxnglobalpivot
+        piv = np.zeros((cap, n), dtype=np.int64)
+        errs = np.zeros(cap, dtype=np.float64)
+        acc = np.zeros(cap, dtype=np.int64)
         nf = C.c_int64(0)
         ctx = f.ctx
-        ctx.check(lib().tci_globalsearch(ctx.h, f.id, n, pi(d3), arr, pi(starts), starts.shape[0],
-                                         float(abstol) * self.tolmarginglobalsearch, self.maxnglobalpivot, pi(piv),
-                                         pf(errs), C.byref(nf)))
+        if len(mine):
+            ctx.check(lib().tci_globalsearch(ctx.h, f.id, n, pi(d3), arr, pi(local), local.shape[0],
+                                             float(abstol) * self.tolmarginglobalsearch, cap, pi(piv), pf(errs),
+                                             pi(acc), C.byref(nf)))
+        if world > 1:
+            from .parallel import allgather_candidates, select_global_pivots
+            cands = [(int(mine[acc[q]]), piv[q].tolist(), float(errs[q])) for q in range(nf.value)]
+            pts, es = select_global_pivots(allgather_candidates(f.dist, cands, f.group), self.maxnglobalpivot)
+            self.last_errors = np.asarray(es, dtype=np.float64)
+            if verbosity > 0:
+                print(f"Found {len(pts)} global pivots")
+            return np.asarray(pts, dtype=np.int64).reshape(len(pts), n)
         if verbosity > 0:
             print(f"Found {nf.value} global pivots")
         self.last_errors = errs[: nf.value].copy()

@@ -1,0 +1,128 @@
+"""Multi-GPU sharding of the stages that shard: one process per GPU,
+`torch.distributed` (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+* Pi evaluation: contiguous column blocks of Jcombined.  Every rank evaluates its block with
+  K1/K4/K5 straight into its slice of the full buffer (tci_pi_eval_into), ONE in-place
+  all-gather assembles Pi on every rank, and an 8-byte all-reduce(max) combines max|Pi|.
+* The per-bond rrLU stays on one GPU (rank `owner`), which broadcasts the chosen pivots
+  (npivot, row/column indices, pivot errors) -- the only other collective of a bond update.
+* Global pivot search: the independent start points are dealt round-robin; the accepted
+  (start index, point, error) candidates are all-gathered and the reference's selection
+  (start order, truncation to maxnglobalpivot, globalpivotfinder.jl:186-188) is replayed
+  identically on every rank, so no further broadcast is needed.
+
+The collectives move torch tensors that alias the library's device buffers
+(`__cuda_array_interface__`); no matrix data passes through the host on the GPU path.
+"""
+import numpy as np
+
+from .batcheval import BatchEvaluator
+
+
+def column_blocks(ncols, world):
+    """Equal-width contiguous column blocks (the last ones may be short or empty)."""
+    blk = (ncols + world - 1) // world if ncols else 0
+    return blk, [(min(r * blk, ncols), min((r + 1) * blk, ncols)) for r in range(world)]
+
+
+def maxabs_allreduce(dist, torch, value, device, group=None):
+    """NaN-propagating max of |x| over ranks: integer max on the bit pattern (NaN sorts above Inf),
+    the same trick the evaluation kernel uses (util.jl:1-10 semantics)."""
+    if value != value:
+        bits = np.array([0x7FF8000000000000], dtype=np.int64)
+    else:
+        bits = np.array([abs(value)], dtype=np.float64).view(np.int64).copy()
+    t = torch.from_numpy(bits).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.cpu().numpy().view(np.float64)[0])
+
+
+def gather_column_blocks(dist, torch, full, blk, rank, group=None):
+    """full: tensor (world*blk, ld), this rank's block already sits in rows [rank*blk, (rank+1)*blk).
+    After the call every rank holds all blocks."""
+    if blk == 0 or dist.get_world_size(group) == 1:
+        return
+    mine = full[rank * blk:(rank + 1) * blk]
+    if full.device.type == "cpu":
+        mine = mine.clone()  # gloo: no in-place aliasing
+    dist.all_gather_into_tensor(full, mine, group=group)
+
+
+def select_global_pivots(candidates, maxn):
+    """candidates: iterable of (start_index, point, error) from all ranks -> reference order:
+    found pivots are kept in start order and truncated to the first maxn (no dedup)."""
+    ordered = sorted(candidates, key=lambda c: c[0])[:maxn]
+    return [list(c[1]) for c in ordered], [c[2] for c in ordered]
+
+
+def allgather_candidates(dist, local, group=None):
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    return [c for part in out for c in part]
+
+
+class PivotResult:
+    """What the host driver needs from one bond factorisation (tensorci2.jl:599-605)."""
+
+    def __init__(self, npivot, rowindices, colindices, pivoterrors):
+        self.npivot = int(npivot)
+        self.rowindices = np.asarray(rowindices, dtype=np.int64)
+        self.colindices = np.asarray(colindices, dtype=np.int64)
+        self.pivoterrors = np.asarray(pivoterrors, dtype=np.float64)
+
+
+def broadcast_pivots(dist, result, owner, group=None):
+    """owner -> everyone: the chosen pivots of one bond update."""
+    obj = [result if dist.get_rank(group) == owner else None]
+    dist.broadcast_object_list(obj, src=owner, group=group)
+    return obj[0]
+
+
+class ShardedEvaluator(BatchEvaluator):
+    """Wraps a BatchEvaluator for world_size > 1: Pi is evaluated in column blocks (GPU path)."""
+
+    def __init__(self, f, dist, torch, owner=0, group=None):
+        self.f, self.dist, self.torch, self.owner, self.group = f, dist, torch, owner, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.ctx = f.ctx
+        self.localdims = f.localdims
+        self.id = f.id
+        self.gather_ms = 0.0
+        self.nevals = 0
+
+    def __del__(self):  # the wrapped evaluator owns the device target
+        pass
+
+    def evaluate_points(self, pts):
+        return self.f.evaluate_points(pts)
+
+    def __call__(self, *args):
+        return self.f(*args)
+
+    def _pi(self, *a):
+        return self.f._pi(*a)
+
+    def batchevaluate_device(self, Iset, Jset, M):
+        from ._lib import DeviceMatrix
+        from .util import as_indexset
+        torch, dist = self.torch, self.dist
+        I, J = as_indexset(Iset), as_indexset(Jset)
+        nJ = len(J)
+        blk, ranges = column_blocks(nJ, self.world)
+        lo, hi = ranges[self.rank]
+        nl = I.shape[1]
+        rows = len(I) * int(np.prod(self.localdims[nl:nl + M], dtype=np.int64))
+        full = DeviceMatrix.empty(self.ctx, rows, blk * self.world)
+        mx = self.f.batchevaluate_into(full, self.rank * blk, I, J[lo:hi], M) if hi > lo else 0.0
+        dev = torch.device("cuda", self.ctx.device)
+        fv = torch.as_tensor(full, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gather_column_blocks(dist, torch, fv, blk, self.rank, self.group)
+        e1.record()
+        torch.cuda.current_stream().synchronize()
+        self.gather_ms += e0.elapsed_time(e1)
+        full.resize_cols(nJ)
+        mx = maxabs_allreduce(dist, torch, mx, dev, self.group)
+        return full, mx

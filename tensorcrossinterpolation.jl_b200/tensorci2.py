@@ -14,6 +14,7 @@ import numpy as np
 from .batcheval import BatchEvaluator
 from .globalpivotfinder import AbstractGlobalPivotFinder, DefaultGlobalPivotFinder, GlobalPivotSearchInput
 from .matrixlu import MatrixLUCI, colindices, pivoterrors, rowindices
+from .parallel import PivotResult, broadcast_pivots
 from .tensortrain import TensorTrain, evaluate_points, tt_sum
 from .util import (CounterRNG, as_indexset, forwardsweep, jl_max, kronecker_left, kronecker_right, pushunique, union)
 
@@ -256,20 +257,29 @@ def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim
     Pi, mx = filltensor(f, tci.localdims, Icombined, Jcombined, 0, device=True)
     t2 = time.perf_counter()
     updatemaxsample(tci, mx)
-    luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
-                      leftorthogonal=leftorthogonal)
+    world = getattr(f, "world", 1)
+    luci = None
+    if world == 1 or f.rank == f.owner:  # the per-bond rrLU stays on one GPU
+        luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
+                          leftorthogonal=leftorthogonal)
+        res = PivotResult(luci.npivot, rowindices(luci), colindices(luci), pivoterrors(luci))
+    else:
+        res = None
+        del Pi
+    if world > 1:
+        res = broadcast_pivots(f.dist, res, f.owner, f.group)
     t3 = time.perf_counter()
     if verbosity > 2:
         print(f"    Computing Pi ({len(Icombined)} x {len(Jcombined)}) at bond {b + 1}: {t2 - t1} sec, "
               f"LU: {t3 - t2} sec")
-    tci.Iset[b + 1] = Icombined[rowindices(luci) - 1]
-    tci.Jset[b] = Jcombined[colindices(luci) - 1]
-    if set_sitetensors and len(extraIset) == 0 and len(extraJset) == 0:  # :601-604
+    tci.Iset[b + 1] = Icombined[res.rowindices - 1]
+    tci.Jset[b] = Jcombined[res.colindices - 1]
+    if set_sitetensors and luci is not None and len(extraIset) == 0 and len(extraJset) == 0:  # :601-604
         setsitetensor(tci, b, luci.left())
         setsitetensor(tci, b + 1, luci.right())
-    updateerrors(tci, b, pivoterrors(luci))
+    updateerrors(tci, b, res.pivoterrors)
     if hasattr(tci, "trace"):
-        tci.trace.append((b + 1, len(Icombined), len(Jcombined), luci.npivot))
+        tci.trace.append((b + 1, len(Icombined), len(Jcombined), res.npivot))
 
 
 def convergencecriterion(ranks, errors, nglobalpivots, tolerance, maxbonddim, ncheckhistory,

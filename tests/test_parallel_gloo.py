@@ -1,0 +1,107 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in parallel.py: column-block sharding
+of Pi with an all-gather, NaN-propagating max all-reduce, candidate gather + reference-order selection
+of the sharded global search, and the pivot broadcast.  The per-rank "local evaluator" is the CPU
+oracle here (checker role only); on the GPU box the same functions move device buffers over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        import tci_b200  # noqa: F401  (loads the package; no GPU needed for parallel.py)
+        from tci_b200 import parallel as P
+        from oracle import oracle as orc
+        res = {}
+        # ---- sharded Pi: column blocks + all-gather ----
+        ld = [10] * 6
+        o = orc.Target.builtin(1, [1.0], ld)
+        rng = np.random.default_rng(0)
+        I = np.stack([rng.integers(1, 11, 23) for _ in range(3)], axis=1)
+        J = np.stack([rng.integers(1, 11, 17) for _ in range(3)], axis=1)
+        ref, refmx = o.pi_eval(I.tolist(), J.tolist(), 0, 0.0)
+        blk, ranges = P.column_blocks(len(J), world)
+        lo, hi = ranges[rank]
+        ldm = 32
+        full = torch.zeros((blk * world, ldm), dtype=torch.float64)
+        mine, mx = o.pi_eval(I.tolist(), J[lo:hi].tolist(), 0, 0.0)
+        full[rank * blk:rank * blk + (hi - lo), :23] = torch.from_numpy(np.ascontiguousarray(mine.T))
+        P.gather_column_blocks(dist, torch, full, blk, rank)
+        got = full[:len(J), :23].numpy().T
+        res["pi_equal"] = bool(np.array_equal(got, ref))
+        res["maxabs"] = P.maxabs_allreduce(dist, torch, mx, "cpu") == refmx
+        nanmax = P.maxabs_allreduce(dist, torch, float("nan") if rank == 1 else 1.0, "cpu")
+        res["nan"] = nanmax != nanmax
+        # ---- sharded global search ----
+        R = 10
+        t = orc.Target.builtin(6, [R, 1], [2] * R)
+        tci = orc.crossinterpolate2(t, [2] * R, [[1] * R, [1] + [2] * (R - 1)], tolerance=1e-4, maxbonddim=1,
+                                    normalizeerror=False)
+        starts = orc.start_points(7, 1, 12, [2] * R)  # (n, nsearch)
+        piv_ref, err_ref = orc.globalsearch(t, tci.sitetensors, starts, abstol=1e-9, tolmargin=1.0, maxn=5)
+        mine_idx = np.arange(rank, starts.shape[1], world)
+        cands = []
+        for s in mine_idx:  # one start at a time so that the accepted start index is known
+            pv, er = orc.globalsearch(t, tci.sitetensors, starts[:, [s]], abstol=1e-9, tolmargin=1.0, maxn=1)
+            if pv:
+                cands.append((int(s), pv[0], float(er[0])))
+        pts, es = P.select_global_pivots(P.allgather_candidates(dist, cands), 5)
+        res["gs_points"] = pts == piv_ref
+        res["gs_errs"] = bool(np.array_equal(np.array(es), err_ref))
+        # ---- pivot broadcast ----
+        pr = P.PivotResult(3, [4, 1, 2], [2, 3, 1], [1.0, 0.5, 0.25, 0.0]) if rank == 0 else None
+        pr = P.broadcast_pivots(dist, pr, 0)
+        res["bcast"] = pr.npivot == 3 and pr.rowindices.tolist() == [4, 1, 2] and pr.pivoterrors[-1] == 0.0
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_logic_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in range(world):
+        rank, res = q.get(timeout=300)
+        out[rank] = res
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert all(out[rank].values()), (rank, out[rank])
+
+
+def test_column_blocks():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tci_b200  # noqa: F401
+    from tci_b200.parallel import column_blocks, select_global_pivots
+    assert column_blocks(10, 4) == (3, [(0, 3), (3, 6), (6, 9), (9, 10)])
+    assert column_blocks(2, 4) == (1, [(0, 1), (1, 2), (2, 2), (2, 2)])
+    assert column_blocks(0, 2) == (0, [(0, 0), (0, 0)])
+    pts, es = select_global_pivots([(3, [1, 1], 0.3), (0, [2, 2], 0.1), (2, [1, 2], 0.2)], 2)
+    assert pts == [[2, 2], [1, 2]] and es == [0.1, 0.2]
