@@ -26,7 +26,8 @@
 //
 // HBM traffic is the algorithmic 16 B per trailing element per pivot (one read, one
 // write); for matrices up to ~100 MB the trailing matrix is L2 resident.
-#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "tci_internal.h"
 
@@ -34,14 +35,16 @@
 #define RR_XS_CAP 24576 // doubles of shared memory for the pivot column
 #define RR_U 4          // 16-byte loads in flight per lane in the trailing update
 
+// One candidate record = ONE aligned 16-byte word, written with a single 16-byte store and polled
+// with single 16-byte loads: the phase bit (top bit of rowphase) flips every second step, so a
+// reader can tell a fresh record from the one left two steps earlier in the same parity buffer
+// without a separate flag word and without a second round trip through L2.
 struct __align__(16) RRCand {
-    double v;   // abs2 of the candidate
-    double val; // its value
-    int row;
-    int colpos;
-    int physcol;
-    int valid;
+    double val;        // value of the candidate (abs2 is recomputed by the reader)
+    unsigned rowphase; // row | phase << 31
+    int colpos;        // column position, -1: this CTA has no finite candidate
 };
+#define RR_MAXQ 5 // candidate records per lane of the polling warp (G <= 160)
 
 struct RRArgs {
     double *A;
@@ -53,39 +56,32 @@ struct RRArgs {
     i64 *rowperm;    // [m] 0-based
     i64 *colperm;    // [n] position -> physical column
     double *pivvals; // [maxrank]
-    RRCand *cand;    // [2][G]
+    int *pivrows;    // [maxrank] row picked at every step
+    RRCand *cand;    // [2][G], zero initialised
     double *xbuf;    // [2][G][ldx]
     i64 ldx;
     int *result;        // [0] npivot, [1] flags (1: no finite candidate left)
     double *result_err; // lu.error
-    unsigned *barrier;  // [0] arrivals, [1] generation
     int xs_in_smem;
     int maxown;
+    i64 lds; // leading dimension of the shared-memory resident columns (RES mode)
+    long long *dbg; // optional per-phase cycle counters (TCI_RRLU_DEBUG)
+    int dbg_cta;
 };
 
-__device__ __forceinline__ bool cand_better(double v, int cp, int row, double bv, int bcp, int brow)
+__device__ __forceinline__ void ld_relaxed_16(const RRCand *p, double &val, unsigned &rowphase, int &colpos)
 {
-    return v > bv || (v == bv && (cp < bcp || (cp == bcp && row < brow)));
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    val = __longlong_as_double((long long)a);
+    rowphase = (unsigned)(b & 0xffffffffull);
+    colpos = (int)(b >> 32);
 }
-
-__device__ __forceinline__ void grid_barrier(unsigned *bar, int G, unsigned &gen)
+__device__ __forceinline__ void st_relaxed_16(RRCand *p, double val, unsigned rowphase, int colpos)
 {
-    __syncthreads();
-    if (G > 1 && threadIdx.x == 0) {
-        __threadfence();
-        unsigned target = gen + 1;
-        if (atomicAdd(&bar[0], 1u) == (unsigned)(G - 1)) {
-            atomicExch(&bar[0], 0u);
-            __threadfence();
-            atomicExch(&bar[1], target);
-        } else {
-            while (*((volatile unsigned *)&bar[1]) != target) {
-            }
-        }
-        __threadfence();
-    }
-    gen++;
-    __syncthreads();
+    unsigned long long a = (unsigned long long)__double_as_longlong(val);
+    unsigned long long b = (unsigned long long)rowphase | ((unsigned long long)(unsigned)colpos << 32);
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
 template <bool EXACT> __device__ __forceinline__ double schur(double a, double x, double y)
@@ -94,35 +90,92 @@ template <bool EXACT> __device__ __forceinline__ double schur(double a, double x
     return fma(-x, y, a);
 }
 
-template <bool EXACT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrlu(RRArgs a)
+// abs2 value -> ordered integer (0 = no candidate); squares are >= 0 so the bit pattern is monotonic
+__device__ __forceinline__ unsigned long long vbits(double v)
 {
+    return v == -INFINITY ? 0ull : (unsigned long long)__double_as_longlong(v) + 1ull;
+}
+// Warp arg-max with the reference's tie-break: max value bits, then min key.  Four REDUX operations
+// instead of a five-step shuffle tree; every lane returns the winner.
+__device__ __forceinline__ void warp_argmax(unsigned long long &vb, unsigned long long &key)
+{
+    const unsigned hi = (unsigned)(vb >> 32), lo = (unsigned)vb;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool top = hi == mhi && lo == mlo;
+    const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+    const unsigned nhi = __reduce_min_sync(0xffffffffu, top ? khi : 0xffffffffu);
+    const unsigned nlo = __reduce_min_sync(0xffffffffu, (top && khi == nhi) ? klo : 0xffffffffu);
+    vb = ((unsigned long long)mhi << 32) | mlo;
+    key = ((unsigned long long)nhi << 32) | nlo;
+}
+
+#define RR_MARK(ph)                                                      \
+    do {                                                                 \
+        if (a.dbg && g == a.dbg_cta && tid == 0) {                       \
+            long long now__ = clock64();                                 \
+            dbg_acc[ph] += now__ - tmark;                                \
+            tmark = now__;                                               \
+        }                                                                \
+    } while (0)
+
+// MODE 0: single CTA, matrix resident in its shared memory, no global synchronisation at all
+// MODE 1: columns resident in the shared memory of G CTAs (matrices up to ~30 MB over 148 SMs)
+// MODE 2: columns streamed from L2 / HBM, pivot column staged in shared memory
+// MODE 3: as 2 for m > RR_XS_CAP, pivot column read from L2
+// The variants are separate instantiations so that the per-pivot loop stays inside the 32 KB
+// instruction cache (a single generic kernel was 61 KB of SASS and refetched itself every step).
+template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrlu(RRArgs a)
+{
+    constexpr bool RES = MODE <= 1, SINGLE = MODE == 0, XS = MODE != 3;
+    constexpr int U = RES ? 2 : RR_U; // 16-byte accesses in flight per lane (deep only when streaming)
+    long long tmark = clock64();
+    __shared__ long long dbg_acc[16];
+    if (threadIdx.x < 16) dbg_acc[threadIdx.x] = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int G = gridDim.x, g = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+    const int G = SINGLE ? 1 : gridDim.x, g = SINGLE ? 0 : blockIdx.x, T = blockDim.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    const i64 m = a.m, n = a.n, ld = a.ld;
-    double *const A = a.A;
+    const int m = (int)a.m, n = (int)a.n;
+    const i64 cld = RES ? a.lds : a.ld; // column stride of the working copy
 
     double *xs = reinterpret_cast<double *>(smem_raw);
-    double *ys = xs + (a.xs_in_smem ? ((m + 1) & ~(i64)1) : 0);
-    int *actc = reinterpret_cast<int *>(ys + a.maxown); // physical column of active entry
-    int *actp = actc + a.maxown;                        // its position
+    double *ys = xs + (XS ? ((m + 1) & ~1) : 0);
+    double *cols = ys + ((a.maxown + 1) & ~1);                                          // RES: maxown * lds doubles
+    int *acto = reinterpret_cast<int *>(cols + (RES ? (size_t)a.maxown * a.lds : 0)); // own slot of active entry
+    int *actp = acto + a.maxown;                                                       // its position
+    // own slot o <-> physical column g + o*G ; working copy of that column:
+    double *const W = RES ? cols : a.A + (size_t)a.ld * g;
+    const i64 wstride = RES ? cld : cld * G;
+#define RR_COL(o) (W + (size_t)wstride * (o))
 
-    __shared__ double red_v[32];
-    __shared__ int red_cp[32], red_row[32], red_col[32];
-    __shared__ RRCand win;
-    __shared__ int sh_nact;
+    __shared__ unsigned long long red_v[32], red_key[32];
+    __shared__ int red_slot;
+    __shared__ double win_val;
+    __shared__ int win_row, win_colpos, win_cta;
+    __shared__ int sh_nact, sh_removed;
 
-    const int nown = (g < n) ? (int)((n - g + G - 1) / G) : 0;
-    for (int e = tid; e < nown; e += T) {
-        int j = g + e * G;
-        actc[e] = j;
+    const int nown = (g < n) ? (n - g + G - 1) / G : 0;
+    _Pragma("unroll 1") for (int e = tid; e < nown; e += T) {
+        const int j = g + e * G;
+        acto[e] = e;
         actp[e] = j;
         a.colpos[j] = j;
     }
-    if (tid == 0) sh_nact = nown;
+    if (tid == 0) {
+        sh_nact = nown;
+        sh_removed = -1;
+    }
     if (g == 0)
-        for (i64 i = tid; i < m; i += T) a.rowperm[i] = i;
-    unsigned gen = *((volatile unsigned *)&a.barrier[1]);
+        _Pragma("unroll 1") for (int i = tid; i < m; i += T) a.rowperm[i] = i;
+    if (RES) { // stage the own columns
+#pragma unroll 1
+        for (int o = warp; o < nown; o += nwarps) {
+            const double *src = a.A + (size_t)a.ld * (g + o * G);
+            double *dst = cols + (size_t)a.lds * o;
+            for (int i = 2 * lane; i < m; i += 64)
+                *reinterpret_cast<double2 *>(dst + i) = *reinterpret_cast<const double2 *>(src + i);
+        }
+    }
     __syncthreads();
 
     double maxerror = 0.0;
@@ -131,292 +184,335 @@ template <bool EXACT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrl
     int flags = 0;
 
     // s = -1 is the initial arg-max scan (no update); s >= 0 are pivot steps.
+#pragma unroll 1
     for (int s = -1; s < a.maxrank; ++s) {
         int nact = sh_nact;
         const double *xw = nullptr; // winner's posted column (global)
         int pr = 0;
         bool do_update = false;
         if (s >= 0) {
-            // ---- 1. reduce the posted candidates --------------------------------
-            if (warp == 0) {
-                const RRCand *cd = a.cand + (size_t)(s & 1) * G;
-                double bv = -INFINITY, bval = 0.0;
-                int bcp = 0x7fffffff, brow = 0x7fffffff, bcol = -1, bcta = -1;
-                for (int q = lane; q < G; q += 32) {
-                    const double2 d0 = __ldcg(reinterpret_cast<const double2 *>(cd + q));
-                    const int4 d1 = __ldcg(reinterpret_cast<const int4 *>(cd + q) + 1);
-                    if (d1.w && cand_better(d0.x, d1.y, d1.x, bv, bcp, brow)) {
-                        bv = d0.x;
-                        bval = d0.y;
-                        brow = d1.x;
-                        bcp = d1.y;
-                        bcol = d1.z;
-                        bcta = q;
+            // ---- 1. wait for / reduce the posted candidates ----------------------
+            if (!SINGLE) {
+                if (warp == 0) {
+                    const RRCand *cd = a.cand + (size_t)(s & 1) * G;
+                    const unsigned phase = (((unsigned)s >> 1) & 1u) ^ 1u;
+                    double cv[RR_MAXQ];
+                    unsigned crp[RR_MAXQ];
+                    int ccp[RR_MAXQ];
+                    for (;;) { // all records of this lane in flight together; polling them is the grid barrier
+                        bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < RR_MAXQ; ++k) {
+                            const int q = lane + 32 * k;
+                            if (q < G) ld_relaxed_16(cd + q, cv[k], crp[k], ccp[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < RR_MAXQ; ++k) {
+                            const int q = lane + 32 * k;
+                            if (q < G) ok = ok && ((crp[k] >> 31) == phase);
+                        }
+                        if (__all_sync(0xffffffffu, ok)) break;
                     }
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    double oval = __shfl_xor_sync(0xffffffffu, bval, o);
-                    int ocp = __shfl_xor_sync(0xffffffffu, bcp, o);
-                    int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-                    int ocol = __shfl_xor_sync(0xffffffffu, bcol, o);
-                    int octa = __shfl_xor_sync(0xffffffffu, bcta, o);
-                    if (octa >= 0 && (bcta < 0 || cand_better(ov, ocp, orow, bv, bcp, brow))) {
-                        bv = ov;
-                        bval = oval;
-                        bcp = ocp;
-                        brow = orow;
-                        bcol = ocol;
-                        bcta = octa;
+                    RR_MARK(7); // poll until all records are fresh
+#ifdef RR_ACQUIRE_FENCE
+                    __threadfence(); // formal acquire; the posted column is read with ld.cg at an address that
+#endif                               // depends on these records, after the writer's release fence
+                    unsigned long long vb = 0ull, key = ~0ull;
+#pragma unroll
+                    for (int k = 0; k < RR_MAXQ; ++k) {
+                        const int q = lane + 32 * k;
+                        if (q < G && ccp[k] >= 0) {
+                            const unsigned long long v = vbits(cv[k] * cv[k]);
+                            const unsigned long long kk =
+                                ((unsigned long long)(unsigned)ccp[k] << 32) | (crp[k] & 0x7fffffffu);
+                            if (v > vb || (v == vb && kk < key)) {
+                                vb = v;
+                                key = kk;
+                            }
+                        }
                     }
+                    warp_argmax(vb, key);
+                    if (vb == 0ull) {
+                        if (lane == 0) win_cta = -1; // no CTA has a finite candidate
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RR_MAXQ; ++k) {
+                            const int q = lane + 32 * k;
+                            if (q < G && ccp[k] == (int)(key >> 32) && (crp[k] & 0x7fffffffu) == (unsigned)key) {
+                                win_val = cv[k];
+                                win_row = (int)(unsigned)key;
+                                win_colpos = ccp[k];
+                                win_cta = q;
+                            }
+                        }
+                    }
+                    RR_MARK(9);
                 }
-                if (lane == 0) {
-                    win.v = bv;
-                    win.val = bval;
-                    win.row = brow;
-                    win.colpos = bcp;
-                    win.physcol = bcol;
-                    win.valid = bcta; // CTA index of the winner, -1 if none
-                }
+                __syncthreads();
             }
-            __syncthreads();
-            const int wcta = win.valid;
+            RR_MARK(0);
+            const int wcta = win_cta;
             if (wcta < 0) { // nothing but NaNs left in the trailing block
                 flags |= 1;
                 break;
             }
-            const double val = win.val;
-            pr = win.row;
-            const int jp = win.physcol, pcpos = win.colpos;
+            const double val = win_val;
+            pr = win_row;
+            const int pcpos = win_colpos;
             // ---- 2. stop rule  matrixlu.jl:153-158 -----------------------------
             const double err = fabs(val);
             lasterr = err;
             if (s > 0 && (err < a.reltol * maxerror || err < a.abstol)) break;
             maxerror = (isnan(maxerror) || isnan(err)) ? nan("") : (err > maxerror ? err : maxerror);
             npiv = s + 1;
-            if (g == 0 && tid == 0) {
-                i64 t0 = a.rowperm[s];
-                a.rowperm[s] = a.rowperm[pr];
-                a.rowperm[pr] = t0;
+            if (g == 0 && tid == 0) { // row swaps are replayed into rowperm after the loop
+                a.pivrows[s] = pr;
                 a.pivvals[s] = val;
             }
             do_update = (s + 1 < a.maxrank);
             xw = a.xbuf + ((size_t)(s & 1) * G + wcta) * a.ldx;
 
-            // ---- 3. row swap in own columns, column bookkeeping, y ---------------
+            // ---- 3. row swap in own columns, column bookkeeping, pivot column ------
             if (pr != s)
-                for (int e = tid; e < nown; e += T) {
-                    double *col = A + (size_t)ld * (g + e * G);
-                    double t0 = col[s];
+                _Pragma("unroll 1") for (int o = tid; o < nown; o += T) {
+                    double *col = RR_COL(o);
+                    const double t0 = col[s];
                     col[s] = col[pr];
                     col[pr] = t0;
                 }
-            // position swap: the column sitting at position s moves to the pivot's old position
-            int removed = -1;
-            for (int e = tid; e < nact; e += T) {
-                if (actc[e] == jp) {
-                    removed = e;
+            // the pivot column sits at position pcpos; the column at position s takes that position
+            _Pragma("unroll 1") for (int e = tid; e < nact; e += T) {
+                if (actp[e] == pcpos) {
+                    sh_removed = e; // exactly one thread of the owning CTA
                 } else if (actp[e] == s) {
                     actp[e] = pcpos;
-                    a.colpos[actc[e]] = pcpos;
+                    a.colpos[g + acto[e] * G] = pcpos;
                 }
             }
-            if (removed >= 0) { // exactly one thread of the owning CTA
-                a.colpos[jp] = s;
-                a.colperm[s] = jp;
-                sh_nact = -(removed + 1); // signal, resolved after the barrier below
+            // pivot column x (posted by the winner; SINGLE: already in xs from the previous step)
+            if (!SINGLE && XS) {
+                if (do_update || LEFT)
+                    _Pragma("unroll 1") for (int i = s + 1 + tid; i < m; i += T) xs[i] = __ldcg(xw + (i == pr ? s : i));
+            } else if (SINGLE && pr > s) {
+                // xs was formed before the row swap: entry pr takes the value of entry s (never read again)
+                if (tid == 0) xs[pr] = xs[s];
             }
             __syncthreads();
-            if (sh_nact < 0) { // owner: drop the pivot column from the active list (swap with last)
-                if (tid == 0) {
-                    int e = -sh_nact - 1;
-                    int last = nact - 1;
-                    actc[e] = actc[last];
-                    actp[e] = actp[last];
+            RR_MARK(1);
+            const int rem = sh_removed;
+            int oslot = -1; // own slot of the pivot column if this CTA owns it
+            if (rem >= 0) {
+                oslot = acto[rem];
+                __syncthreads();
+                if (tid == 0) { // drop the pivot column from the active list (swap with last)
+                    const int jp = g + oslot * G;
+                    a.colpos[jp] = s;
+                    a.colperm[s] = jp;
+                    const int last = nact - 1;
+                    acto[rem] = acto[last];
+                    actp[rem] = actp[last];
                     sh_nact = last;
+                    sh_removed = -1;
                 }
                 __syncthreads();
             }
-            const bool owner = (jp % G) == g;
             nact = sh_nact;
-            if (do_update || !a.leftorth) {
-                for (int e = tid; e < nact; e += T) {
-                    double *p = A + (size_t)ld * actc[e] + s;
+            if (do_update || !LEFT) {
+                _Pragma("unroll 1") for (int e = tid; e < nact; e += T) {
+                    double *p = RR_COL(acto[e]) + s;
                     double y = *p;
-                    if (!a.leftorth) { // matrixlu.jl:122
+                    if (!LEFT) { // matrixlu.jl:122
                         y = __ddiv_rn(y, val);
                         *p = y;
                     }
                     ys[e] = y;
                 }
             }
-            // ---- 4. pivot column ------------------------------------------------
-            if (a.xs_in_smem && (do_update || (owner && a.leftorth))) {
-                for (i64 i = s + 1 + tid; i < m; i += T) xs[i] = __ldcg(xw + (i == pr ? s : i));
+            if (LEFT && oslot >= 0) { // L column: A[k+1:end, k] ./= A[k, k]  matrixlu.jl:120
+                double *col = RR_COL(oslot);
+                if (XS)
+                    _Pragma("unroll 1") for (int i = s + 1 + tid; i < m; i += T) col[i] = xs[i];
+                else
+                    _Pragma("unroll 1") for (int i = s + 1 + tid; i < m; i += T) col[i] = __ldcg(xw + (i == pr ? s : i));
             }
             __syncthreads();
-            if (owner && a.leftorth) { // L column: A[k+1:end, k] ./= A[k, k]  matrixlu.jl:120
-                double *col = A + (size_t)ld * jp;
-                if (a.xs_in_smem)
-                    for (i64 i = s + 1 + tid; i < m; i += T) col[i] = xs[i];
-                else
-                    for (i64 i = s + 1 + tid; i < m; i += T) col[i] = __ldcg(xw + (i == pr ? s : i));
-            }
+            RR_MARK(2);
             if (!do_update) break; // the last Schur update never reaches L or U
         }
 
         // ---- 5. trailing update fused with the arg-max for the next pivot --------
         const int lo = s + 1; // first trailing row
-        double bv = -INFINITY;
-        int bcp = 0x7fffffff, brow = 0x7fffffff, bcol = -1;
+        // This thread's best candidate: ordered value bits (0 = none), column position, row.  Order: larger
+        // abs2, then smaller column position, then smaller row.  All compares are on integers (the squares
+        // are non-negative, so their bit patterns are ordered) and the eight elements of a tile are reduced
+        // as a tree, which keeps the dependent chain short.
+        unsigned long long bvb = 0ull;
+        int bcpv = 0x7fffffff, browv = 0x7fffffff;
         if (nact > 0) {
             // Tiles of RR_U*64 rows x 1 column are dealt round-robin to the warps; a lane issues its
             // RR_U 16-byte loads back to back so that enough bytes are in flight to cover HBM latency.
-            const i64 i0 = lo & ~1;
-            const int ntr = (int)((m - i0 + RR_U * 64 - 1) / (RR_U * 64));
-            const i64 ntiles = (i64)nact * ntr;
-            for (i64 t = warp; t < ntiles; t += nwarps) {
-                const int e = (int)(t / ntr);
-                const int rt = (int)(t - (i64)e * ntr);
-                const int col = actc[e], cp = actp[e];
+            const int i0 = lo & ~1;
+            const int ntr = (m - i0 + U * 64 - 1) / (U * 64);
+            int e = warp / ntr, rt = warp - e * ntr; // tile t = e*ntr + rt, advanced by nwarps without divisions
+            const int de = nwarps / ntr, dr = nwarps - de * ntr;
+#pragma unroll 1
+            while (e < nact) {
+                const int cp = actp[e];
                 const double y = do_update ? ys[e] : 0.0;
-                double *const cptr = A + (size_t)ld * col;
-                const i64 base = i0 + (i64)rt * (RR_U * 64) + 2 * lane;
-                double2 d[RR_U];
+                double *const cptr = RR_COL(acto[e]);
+                const int base = i0 + rt * (U * 64) + 2 * lane;
+                double2 d[U];
+                unsigned long long ob[2 * U];
 #pragma unroll
-                for (int u = 0; u < RR_U; ++u) {
-                    const i64 i = base + u * 64;
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * 64;
                     if (i < m) d[u] = *reinterpret_cast<const double2 *>(cptr + i);
                 }
 #pragma unroll
-                for (int u = 0; u < RR_U; ++u) {
-                    const i64 i = base + u * 64;
-                    if (i < m) {
-                        const bool v0ok = i >= lo, v1ok = i + 1 < m;
-                        if (do_update) {
-                            double x0, x1;
-                            if (a.xs_in_smem) {
-                                const double2 xx = *reinterpret_cast<const double2 *>(xs + i);
-                                x0 = xx.x;
-                                x1 = xx.y;
-                            } else {
-                                x0 = v0ok ? __ldcg(xw + (i == pr ? s : i)) : 0.0;
-                                x1 = v1ok ? __ldcg(xw + (i + 1 == pr ? s : i + 1)) : 0.0;
-                            }
-                            if (v0ok) d[u].x = schur<EXACT>(d[u].x, x0, y);
-                            if (v1ok) d[u].y = schur<EXACT>(d[u].y, x1, y);
-                            *reinterpret_cast<double2 *>(cptr + i) = d[u];
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * 64;
+                    const bool v0ok = i >= lo && i < m, v1ok = i + 1 < m;
+                    if (do_update && i < m) {
+                        double x0, x1;
+                        if (XS) {
+                            const double2 xx = *reinterpret_cast<const double2 *>(xs + i);
+                            x0 = xx.x;
+                            x1 = xx.y;
+                        } else {
+                            x0 = v0ok ? __ldcg(xw + (i == pr ? s : i)) : 0.0;
+                            x1 = v1ok ? __ldcg(xw + (i + 1 == pr ? s : i + 1)) : 0.0;
                         }
-                        const double q0 = d[u].x * d[u].x, q1 = d[u].y * d[u].y;
-                        if (v0ok && q0 >= bv && cand_better(q0, cp, (int)i, bv, bcp, brow)) {
-                            bv = q0;
-                            bcp = cp;
-                            brow = (int)i;
-                            bcol = col;
-                        }
-                        if (v1ok && q1 >= bv && cand_better(q1, cp, (int)i + 1, bv, bcp, brow)) {
-                            bv = q1;
-                            bcp = cp;
-                            brow = (int)i + 1;
-                            bcol = col;
-                        }
+                        if (v0ok) d[u].x = schur<EXACT>(d[u].x, x0, y);
+                        if (v1ok) d[u].y = schur<EXACT>(d[u].y, x1, y);
+                        *reinterpret_cast<double2 *>(cptr + i) = d[u]; // masked entries are written back unchanged
                     }
+                    const double q0 = d[u].x * d[u].x, q1 = d[u].y * d[u].y;
+                    ob[2 * u] = (v0ok && q0 == q0) ? (unsigned long long)__double_as_longlong(q0) + 1ull : 0ull;
+                    ob[2 * u + 1] = (v1ok && q1 == q1) ? (unsigned long long)__double_as_longlong(q1) + 1ull : 0ull;
+                }
+                // tree arg-max over the 2*RR_U elements, lower element index (= smaller row) wins ties
+                unsigned long long tb = ob[0];
+                int tj = 0;
+                {
+                    unsigned long long v1[U];
+                    int j1[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool hi = ob[2 * u + 1] > ob[2 * u];
+                        v1[u] = hi ? ob[2 * u + 1] : ob[2 * u];
+                        j1[u] = hi ? 2 * u + 1 : 2 * u;
+                    }
+#pragma unroll
+                    for (int w = 1; w < U; w *= 2)
+#pragma unroll
+                        for (int u = 0; u + w < U; u += 2 * w) {
+                            const bool hi = v1[u + w] > v1[u];
+                            v1[u] = hi ? v1[u + w] : v1[u];
+                            j1[u] = hi ? j1[u + w] : j1[u];
+                        }
+                    tb = v1[0];
+                    tj = j1[0];
+                }
+                const int trow = base + (tj >> 1) * 64 + (tj & 1);
+                if (tb > bvb || (tb == bvb && tb != 0ull && (cp < bcpv || (cp == bcpv && trow < browv)))) {
+                    bvb = tb;
+                    bcpv = cp;
+                    browv = trow;
+                }
+                e += de;
+                rt += dr;
+                if (rt >= ntr) {
+                    rt -= ntr;
+                    ++e;
                 }
             }
         }
-        // block reduction of the candidate
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            int ocp = __shfl_xor_sync(0xffffffffu, bcp, o);
-            int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-            int ocol = __shfl_xor_sync(0xffffffffu, bcol, o);
-            if (ocol >= 0 && (bcol < 0 || cand_better(ov, ocp, orow, bv, bcp, brow))) {
-                bv = ov;
-                bcp = ocp;
-                brow = orow;
-                bcol = ocol;
-            }
-        }
+        unsigned long long bkey = ((unsigned long long)(unsigned)bcpv << 32) | (unsigned)browv;
+        RR_MARK(3);
+        // block reduction of the candidate (value bits, key)
+        unsigned long long vb = bvb;
+        warp_argmax(vb, bkey);
         if (lane == 0) {
-            red_v[warp] = bv;
-            red_cp[warp] = bcp;
-            red_row[warp] = brow;
-            red_col[warp] = bcol;
+            red_v[warp] = vb;
+            red_key[warp] = bkey;
         }
+        if (tid == 0) red_slot = -1;
         __syncthreads();
-        if (warp == 0) {
-            bv = lane < nwarps ? red_v[lane] : -INFINITY;
-            bcp = lane < nwarps ? red_cp[lane] : 0x7fffffff;
-            brow = lane < nwarps ? red_row[lane] : 0x7fffffff;
-            bcol = lane < nwarps ? red_col[lane] : -1;
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int ocp = __shfl_xor_sync(0xffffffffu, bcp, o);
-                int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-                int ocol = __shfl_xor_sync(0xffffffffu, bcol, o);
-                if (ocol >= 0 && (bcol < 0 || cand_better(ov, ocp, orow, bv, bcp, brow))) {
-                    bv = ov;
-                    bcp = ocp;
-                    brow = orow;
-                    bcol = ocol;
-                }
-            }
-            if (lane == 0) {
-                red_v[0] = bv;
-                red_cp[0] = bcp;
-                red_row[0] = brow;
-                red_col[0] = bcol;
-            }
-        }
+        vb = lane < nwarps ? red_v[lane] : 0ull; // every warp reduces the per-warp results itself
+        bkey = lane < nwarps ? red_key[lane] : ~0ull;
+        warp_argmax(vb, bkey);
+        const int bcp = (int)(bkey >> 32), brow = (int)(bkey & 0xffffffffull);
+        if (vb != 0ull) // own slot of the column that sits at position bcp
+            _Pragma("unroll 1") for (int e = tid; e < nact; e += T)
+                if (actp[e] == bcp) red_slot = acto[e];
         __syncthreads();
+        const int bslot = red_slot;
+        RR_MARK(4);
         // ---- 6. post the candidate and its column for step s+1 -------------------
-        {
-            const int nxt = (s + 1) & 1;
-            bv = red_v[0];
-            bcp = red_cp[0];
-            brow = red_row[0];
-            bcol = red_col[0];
-            RRCand *slot = a.cand + (size_t)nxt * G + g;
-            if (bcol >= 0) {
-                const double *col = A + (size_t)ld * bcol;
+        if (SINGLE) { // the winner is the own candidate, its column goes straight to xs
+            if (bslot >= 0) {
+                const double *col = RR_COL(bslot);
                 const double cval = col[brow];
-                double *xo = a.xbuf + ((size_t)nxt * G + g) * a.ldx;
-                if (a.leftorth)
-                    for (i64 i = lo + tid; i < m; i += T) xo[i] = __ddiv_rn(col[i], cval);
-                else
-                    for (i64 i = lo + tid; i < m; i += T) xo[i] = col[i];
+                _Pragma("unroll 1") for (int i = lo + tid; i < m; i += T) xs[i] = LEFT ? __ddiv_rn(col[i], cval) : col[i];
                 if (tid == 0) {
-                    slot->v = bv;
-                    slot->val = cval;
-                    slot->row = brow;
-                    slot->colpos = bcp;
-                    slot->physcol = bcol;
-                    slot->valid = 1;
+                    win_val = cval;
+                    win_row = brow;
+                    win_colpos = bcp;
+                    win_cta = 0;
                 }
-            } else if (tid == 0) {
-                slot->v = -INFINITY;
-                slot->val = 0.0;
-                slot->row = 0;
-                slot->colpos = 0;
-                slot->physcol = -1;
-                slot->valid = 0;
+            } else if (tid == 0)
+                win_cta = -1;
+            __syncthreads();
+        } else {
+            const int nxt = (s + 1) & 1;
+            RRCand *slot = a.cand + (size_t)nxt * G + g;
+            double cval = 0.0;
+            if (bslot >= 0) {
+                const double *col = RR_COL(bslot);
+                cval = col[brow];
+                double *xo = a.xbuf + ((size_t)nxt * G + g) * a.ldx;
+                _Pragma("unroll 1") for (int i = lo + tid; i < m; i += T) xo[i] = LEFT ? __ddiv_rn(col[i], cval) : col[i];
             }
+            __syncthreads(); // all column stores of the CTA are ordered before the release below
+            RR_MARK(5);
+            if (tid == 0) {
+                const unsigned phase = ((((unsigned)(s + 1)) >> 1) & 1u) ^ 1u;
+                __threadfence(); // fence + relaxed store = release
+                st_relaxed_16(slot, cval, (unsigned)(bslot >= 0 ? brow : 0) | (phase << 31), bslot >= 0 ? bcp : -1);
+            }
+            RR_MARK(6);
         }
-        grid_barrier(a.barrier, G, gen);
     }
 
-    // remaining (unpicked) columns keep the positions the reference's swaps gave them
     __syncthreads();
+    if (RES) { // write the factors back
+#pragma unroll 1
+        for (int o = warp; o < nown; o += nwarps) {
+            double *dst = a.A + (size_t)a.ld * (g + o * G);
+            const double *src = cols + (size_t)a.lds * o;
+            for (int i = 2 * lane; i < m; i += 64)
+                *reinterpret_cast<double2 *>(dst + i) = *reinterpret_cast<const double2 *>(src + i);
+        }
+    }
+    if (a.dbg && g == a.dbg_cta && tid < 16) a.dbg[tid] = dbg_acc[tid];
+    // remaining (unpicked) columns keep the positions the reference's swaps gave them
     {
         const int nact = sh_nact;
-        for (int e = tid; e < nact; e += T) a.colperm[actp[e]] = actc[e];
+        _Pragma("unroll 1") for (int e = tid; e < nact; e += T) a.colperm[actp[e]] = g + acto[e] * G;
     }
     if (g == 0 && tid == 0) {
+        for (int q = 0; q < npiv; ++q) { // swaprow! bookkeeping, matrixlu.jl:99-100
+            const int pq = a.pivrows[q];
+            const i64 t0 = a.rowperm[q];
+            a.rowperm[q] = a.rowperm[pq];
+            a.rowperm[pq] = t0;
+        }
         a.result[0] = npiv;
         a.result[1] = flags;
-        const i64 mn = m < n ? m : n;
+        const int mn = m < n ? m : n;
         *a.result_err = (npiv >= mn) ? 0.0 : lasterr; // matrixlu.jl:176-178
     }
+#undef RR_COL
 }
 
 // any NaN in L = tril(A[:,1:r]) or U = triu(A[1:r,:]) (matrixlu.jl:164-169); flags bit0 L, bit1 U
@@ -461,10 +557,24 @@ __global__ void k_extract_U(const double *__restrict__ A, i64 n, i64 ld, const i
     U[i + ldu * q] = v;
 }
 
-static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bool exact)
+template <bool EXACT, int MODE> static const void *rrlu_fn(bool left)
+{
+    return left ? (const void *)k_rrlu<EXACT, MODE, true> : (const void *)k_rrlu<EXACT, MODE, false>;
+}
+template <bool EXACT> static const void *rrlu_fn_mode(int mode, bool left)
+{
+    switch (mode) {
+    case 0: return rrlu_fn<EXACT, 0>(left);
+    case 1: return rrlu_fn<EXACT, 1>(left);
+    case 2: return rrlu_fn<EXACT, 2>(left);
+    default: return rrlu_fn<EXACT, 3>(left);
+    }
+}
+
+static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bool exact, int mode)
 {
     void *kargs[] = {&args};
-    const void *fn = exact ? (const void *)k_rrlu<true> : (const void *)k_rrlu<false>;
+    const void *fn = exact ? rrlu_fn_mode<true>(mode, args.leftorth != 0) : rrlu_fn_mode<false>(mode, args.leftorth != 0);
     TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(ctx->ev2, ctx->stream);
     TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), kargs, smem, ctx->stream));
@@ -509,12 +619,31 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         return TCI_OK;
     }
 
-    int G = (int)std::min<i64>(ctx->sm_count, std::max<i64>(1, n / 4));
-    int T = m >= 1024 ? 1024 : (m >= 384 ? 512 : 256);
-    const int maxown = (int)((n + G - 1) / G);
+    // Grid / residency policy.  A matrix that fits one CTA's shared memory is factorised by a single
+    // CTA without any global synchronisation; up to ~30 MB the columns are spread over the SMs'
+    // shared memory (RES); beyond that they are streamed from L2 / HBM.
+    const size_t SMEM_BUDGET = 220 * 1024;
+    const i64 lds = (m + 1) & ~(i64)1;
     const int xs_in_smem = m <= RR_XS_CAP;
-    size_t smem = (xs_in_smem ? (size_t)((m + 1) & ~(i64)1) : 0) * sizeof(double) + (size_t)maxown * sizeof(double) +
-                  2 * (size_t)maxown * sizeof(int) + 16;
+    auto smem_need = [&](int Gq, bool resq) {
+        const i64 mo = (n + Gq - 1) / Gq;
+        return (size_t)(xs_in_smem ? lds : 0) * 8 + (size_t)((mo + 1) & ~(i64)1) * 8 + (size_t)mo * 8 +
+               (resq ? (size_t)mo * lds * 8 : 0) + 64;
+    };
+    int G;
+    bool resident = false;
+    if (smem_need(1, true) <= SMEM_BUDGET) {
+        G = 1;
+        resident = true;
+    } else {
+        G = (int)std::min<i64>(std::min<i64>(ctx->sm_count, 32 * RR_MAXQ), std::max<i64>(1, n / 2));
+        resident = xs_in_smem && smem_need(G, true) <= SMEM_BUDGET;
+    }
+    if (getenv("TCI_RRLU_NO_RES")) resident = false;
+    const i64 per_cta = m * ((n + G - 1) / G);
+    int T = (m >= 1024 || per_cta >= 32768) ? 1024 : ((m >= 384 || per_cta >= 8192) ? 512 : 256);
+    const int maxown = (int)((n + G - 1) / G);
+    size_t smem = smem_need(G, resident);
 
     RRArgs args{};
     args.A = A->p;
@@ -528,9 +657,9 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     args.ldx = round_up(m, 16);
     args.xs_in_smem = xs_in_smem;
     args.maxown = maxown;
-    args.barrier = ctx->rr_barrier;
+    args.lds = lds;
 
-    DevBuf<int> colpos(ctx), result(ctx);
+    DevBuf<int> colpos(ctx), result(ctx), pivrows(ctx);
     DevBuf<i64> d_rowperm(ctx), d_colperm(ctx);
     DevBuf<double> pivvals(ctx), xbuf(ctx), d_err(ctx);
     DevBuf<RRCand> cand(ctx);
@@ -539,25 +668,36 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     TCI_CUDA(ctx, d_rowperm.alloc(m));
     TCI_CUDA(ctx, d_colperm.alloc(n));
     TCI_CUDA(ctx, pivvals.alloc(mr));
+    TCI_CUDA(ctx, pivrows.alloc(mr));
     TCI_CUDA(ctx, xbuf.alloc((size_t)2 * G * args.ldx));
     TCI_CUDA(ctx, d_err.alloc(1));
     TCI_CUDA(ctx, cand.alloc((size_t)2 * G));
+    TCI_CUDA(ctx, cudaMemsetAsync(cand.p, 0, (size_t)2 * G * sizeof(RRCand), ctx->stream));
     TCI_CUDA(ctx, cudaMemsetAsync(result.p, 0, 4 * sizeof(int), ctx->stream));
     args.colpos = colpos.p;
     args.rowperm = d_rowperm.p;
     args.colperm = d_colperm.p;
     args.pivvals = pivvals.p;
+    args.pivrows = pivrows.p;
     args.cand = cand.p;
     args.xbuf = xbuf.p;
     args.result = result.p;
     args.result_err = d_err.p;
 
+    DevBuf<long long> dbg(ctx);
+    const char *dbgenv = getenv("TCI_RRLU_DEBUG");
+    if (dbgenv) {
+        TCI_CUDA(ctx, dbg.alloc(16));
+        TCI_CUDA(ctx, cudaMemsetAsync(dbg.p, 0, 16 * sizeof(long long), ctx->stream));
+        args.dbg = dbg.p;
+        args.dbg_cta = atoi(dbgenv) % G;
+    }
     int res[4] = {0, 0, 0, 0};
     double lu_error = 0.0;
     std::vector<double> pv;
     {
         StageTimer tm(ctx, ST_RRLU);
-        int rc = rrlu_launch(ctx, args, G, T, smem, exact_mode != 0);
+        int rc = rrlu_launch(ctx, args, G, T, smem, exact_mode != 0, G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
         if (rc) return rc;
         TCI_CUDA(ctx, cudaMemcpyAsync(res, result.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         TCI_CUDA(ctx, cudaMemcpyAsync(&lu_error, d_err.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -565,6 +705,13 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         {
             float kms = 0.f;
             if (cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_RRLU_KERNEL] += kms;
+        }
+        if (dbgenv) {
+            long long h[16];
+            cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[rrlu dbg] m=%lld n=%lld r=%d G=%d T=%d res=%d cycles/pivot: wait+reduce %lld (poll %lld acqfence %lld payload %lld) | swap+x %lld | ys+L %lld | update %lld | blockreduce %lld | post %lld | fence %lld\n",
+                    (long long)m, (long long)n, res[0], G, T, (int)resident, h[0] / (res[0] + 1), h[7] / (res[0] + 1), h[8] / (res[0] + 1), h[9] / (res[0] + 1), h[1] / (res[0] + 1), h[2] / (res[0] + 1),
+                    h[3] / (res[0] + 1), h[4] / (res[0] + 1), h[5] / (res[0] + 1), h[6] / (res[0] + 1));
         }
         const int r = res[0];
         unsigned blocks = (unsigned)std::min<i64>((m * n + 255) / 256, (i64)ctx->sm_count * 8);

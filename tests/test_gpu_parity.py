@@ -190,6 +190,25 @@ def test_rrlu_random_lowrank_bit_exact(T, oracle, m, n, r, leftorth):
     assert_lu_equal(lu, ref)
 
 
+@pytest.mark.parametrize("leftorth", [True, False])
+@pytest.mark.parametrize("m,n,r", [(2100, 2050, 24), (3000, 500, 16)])
+def test_rrlu_streaming_regime(T, oracle, m, n, r, leftorth):
+    """Too large for the shared-memory resident mode: columns are streamed from L2 / HBM."""
+    A = lowrank_matrix(m, n, r, seed=m + n)
+    assert_lu_equal(T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=leftorth),
+                    oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=leftorth))
+
+
+@pytest.mark.parametrize("m,n,r", [(17, 33, 9), (130, 257, 40), (513, 700, 48)])
+def test_rrlu_streaming_forced(T, oracle, m, n, r, monkeypatch):
+    """Same kernels with residency switched off (every size takes the global-memory path)."""
+    monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
+    A = lowrank_matrix(m, n, r, seed=m * 1000 + n)
+    for lo in (True, False):
+        assert_lu_equal(T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo),
+                        oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo))
+
+
 @pytest.mark.parametrize("m,n", [(50, 50), (120, 80), (257, 300)])
 def test_rrlu_full_rank_random(T, oracle, m, n):  # benchmark/rrlu.jl:12-17 shape
     A = np.random.default_rng(m).random((m, n))
