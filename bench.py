@@ -343,7 +343,7 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         ctx.timers(reset=True)
         ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
         ms = ctx.timers(reset=True)["gemm"]
-        extra["dgemm_4096"] = {"gflops": 2.0 * N ** 3 / (ms * 1e-3) / 1e9, "ms": ms}
+        extra["dgemm_4096"] = {"gflops": 2.0 * N ** 3 / (ms * 1e-3) / 1e9, "ms": ms, "kernel": "k_dgemm_mma (DMMA m8n8k4)"}
         a = torch.randn(N, N, dtype=torch.float64, device="cuda")
         b = torch.randn(N, N, dtype=torch.float64, device="cuda")
         for _ in range(2):
@@ -356,6 +356,37 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         e1.record()
         torch.cuda.synchronize()
         extra["cublas_dgemm_4096_gflops"] = 5 * 2.0 * N ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        # --- config 5 shape: MPO x MPO target, 40 sites, bond 256, site dims 2x2: Pi over the middle bond ---
+        nsites, Dm = 40, 256
+        g5, g6 = np.random.default_rng(5), np.random.default_rng(6)
+
+        def mpo(g):
+            bonds = [1] + [Dm] * (nsites - 1) + [1]
+            return [np.asfortranarray((g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(nsites)]
+
+        fm = T.Contraction(T.TensorTrain(mpo(g5)), T.TensorTrain(mpo(g6)))
+        nL = nR = 256
+        Il = np.stack([rng.integers(1, 5, nL) for _ in range(19)], axis=1).astype(np.int64)
+        Jr = np.stack([rng.integers(1, 5, nR) for _ in range(19)], axis=1).astype(np.int64)
+        dev, mx = fm.batchevaluate_device(Il, Jr, 2)
+        del dev
+        ctx.timers(reset=True)
+        l0 = ctx.launches
+        dev, mx = fm.batchevaluate_device(Il, Jr, 2)
+        ms = ctx.timers(reset=True)["pi_eval"]
+        step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm  # one environment extension (contraction.jl:103-109)
+        fl = (nL + nR) * 18 * step + 2 * (nL * (2.0 * Dm * Dm * 8 * Dm) + nL * 4 * 8 * 2.0 * Dm * Dm * Dm / 4) \
+            + 2.0 * nL * 16 * Dm * Dm * nR
+        extra["mpo_pi_eval_config5"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms, "launches": ctx.launches - l0,
+                                        "shape": f"40 sites, bonds 256, nL=nR={nL}, M=2 (Pi {nL * 16} x {nR})",
+                                        "flop_model": "env extensions + centre folds + final product"}
+        del dev, fm
+        # --- config 3: quantics 2-D, R=20 fused (20 sites d=4), maxbonddim 256, tolerance 1e-10 ---
+        f3 = T.BuiltinTarget(T.QUANTICS2D, [0, 20], [4] * 20)
+        t0 = time.perf_counter()
+        tci3, ranks3, errors3 = T.crossinterpolate2(f3, [4] * 20, tolerance=1e-10, maxbonddim=256, rng=T.CounterRNG(1))
+        extra["crossinterpolate2_config3"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks3[-1]),
+                                              "iterations": len(ranks3), "error": float(errors3[-1])}
         # --- config 1: README 8-d Lorentzian, time to tolerance 1e-8 ---
         f = T.BuiltinTarget(T.LORENTZ, [1.0], [10] * 8)
         T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))

@@ -7,6 +7,8 @@
 // thread an (BM/16)x(BN/16) micro tile made of 2-wide strips 32 apart so that every
 // LDS.128 of a quarter warp is conflict free and C stores are 256 B contiguous.
 // The next k-tile is prefetched into registers while the current one is consumed.
+#include <cstdlib>
+
 #include "tci_internal.h"
 
 #define GK 16
@@ -127,6 +129,131 @@ __global__ void __launch_bounds__(256)
         }
 }
 
+// ---- FP64 tensor-core variant: mma.sync.m8n8k4.f64 (SASS DMMA) ------------------------------
+// tcgen05 has no FP64 kind; DMMA through mma.sync is the only tensor path for doubles on sm_100a.
+// CTA tile 128x128x16, 8 warps as 2 (M) x 4 (N), warp tile 64x32 = 8 x 4 DMMA tiles (64 accumulator
+// doubles per thread).  Operands are staged as As[m][k] / Bs[n][k] with the k-row padded to 20 doubles,
+// which makes the per-lane 8-byte fragment loads (row = lane/4, k = lane%4) bank-conflict free.
+#define MK 16
+#define MKP 20
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int NWM, int NWN, bool TA, bool TB>
+__global__ void __launch_bounds__(32 * NWM * NWN)
+    k_dgemm_mma(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
+                const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
+                i64 strideC, const i64 *__restrict__ offA, const i64 *__restrict__ offB)
+{
+    constexpr int NT = 32 * NWM * NWN;            // threads
+    constexpr int TI = BM / NWM / 8, TJ = BN / NWN / 8; // DMMA tiles per warp
+    constexpr int LA = BM * MK / NT, LB = BN * MK / NT;
+    __shared__ __align__(16) double As[BM][MKP];
+    __shared__ __align__(16) double Bs[BN][MKP];
+    A += strideA * blockIdx.z + (offA ? offA[blockIdx.z] : 0);
+    B += strideB * blockIdx.z + (offB ? offB[blockIdx.z] : 0);
+    C += strideC * blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp % NWM) * (BM / NWM), wn = (warp / NWM) * (BN / NWN); // warp tile origin
+    const int fr = lane >> 2, fk = lane & 3;                                  // fragment row / k index
+    const i64 m0 = (i64)blockIdx.x * BM, n0 = (i64)blockIdx.y * BN;
+
+    double acc[TI][TJ][2];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    double ra[LA], rb[LB];
+    auto gload = [&](i64 k0) {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            const int e = tid + q * NT;
+            const int mm = TA ? e / MK : e % BM, kk = TA ? e % MK : e / BM;
+            const i64 gm = m0 + mm, gk = k0 + kk;
+            ra[q] = (gm < M && gk < K) ? (TA ? A[gk + lda * gm] : A[gm + lda * gk]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const int e = tid + q * NT;
+            const int nn = TB ? e % BN : e / MK, kk = TB ? e / BN : e % MK;
+            const i64 gn = n0 + nn, gk = k0 + kk;
+            rb[q] = (gn < N && gk < K) ? (TB ? B[gn + ldb * gk] : B[gk + ldb * gn]) : 0.0;
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int q = 0; q < LA; ++q) {
+            const int e = tid + q * NT;
+            As[TA ? e / MK : e % BM][TA ? e % MK : e / BM] = ra[q];
+        }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const int e = tid + q * NT;
+            Bs[TB ? e % BN : e / MK][TB ? e / BN : e % MK] = rb[q];
+        }
+    };
+
+    gload(0);
+    for (i64 k0 = 0; k0 < K; k0 += MK) {
+        __syncthreads();
+        sstore();
+        __syncthreads();
+        if (k0 + MK < K) gload(k0 + MK);
+#pragma unroll
+        for (int k4 = 0; k4 < MK; k4 += 4) {
+            double af[TI], bf[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i) af[i] = As[wm + 8 * i + fr][k4 + fk];
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) bf[j] = Bs[wn + 8 * j + fr][k4 + fk];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    // accumulator fragment: row = lane/4, columns 2*(lane%4) + {0,1}
+#pragma unroll
+    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const i64 gn = n0 + wn + 8 * j + 2 * fk + c;
+            if (gn >= N) continue;
+#pragma unroll
+            for (int i = 0; i < TI; ++i) {
+                const i64 gm = m0 + wm + 8 * i + fr;
+                if (gm >= M) continue;
+                const double v = alpha * acc[i][j][c];
+                double *cp = C + gm + ldc * gn;
+                *cp = (beta == 0.0) ? v : fma(beta, *cp, v);
+            }
+        }
+}
+
+template <int BM, int BN, int NWM, int NWN>
+static void launch_dgemm_mma(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A,
+                             i64 lda, i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc,
+                             i64 sC, i64 batch, const i64 *offA, const i64 *offB)
+{
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch);
+    constexpr int NT = 32 * NWM * NWN;
+    if (!tA && !tB)
+        k_dgemm_mma<BM, BN, NWM, NWN, false, false><<<grid, NT, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else if (tA && !tB)
+        k_dgemm_mma<BM, BN, NWM, NWN, true, false><<<grid, NT, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else if (!tA && tB)
+        k_dgemm_mma<BM, BN, NWM, NWN, false, true><<<grid, NT, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    else
+        k_dgemm_mma<BM, BN, NWM, NWN, true, true><<<grid, NT, 0, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    ctx->launches++;
+}
+
 template <int BM, int BN>
 static void launch_dgemm(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
                          i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, i64 batch,
@@ -174,7 +301,15 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         ctx->launches++;
     } else {
         i64 big_ctas = ((M + 127) / 128) * ((N + 127) / 128) * batch;
-        if (big_ctas >= ctx->sm_count && M >= 96 && N >= 96)
+        static const int use_mma = getenv("TCI_DGEMM_NO_MMA") ? 0 : 1;
+        const i64 mid_ctas = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+        if (use_mma && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96)
+            launch_dgemm_mma<128, 128, 2, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C,
+                                             ldc, strideC, batch, offA, offB);
+        else if (use_mma && mid_ctas >= 16 && M >= 32 && N >= 32)
+            launch_dgemm_mma<64, 64, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                           strideC, batch, offA, offB);
+        else if (big_ctas >= ctx->sm_count && M >= 96 && N >= 96)
             launch_dgemm<128, 128>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
                                    strideC, batch, offA, offB);
         else

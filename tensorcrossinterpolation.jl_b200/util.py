@@ -44,20 +44,28 @@ def kronecker_right(localdim, Jset):  # kronecker(d, Jset)  tensorci2.jl:322-327
     return out
 
 
+def _rowkeys(a):
+    """One hashable key per row (the raw bytes of the row)."""
+    a = np.ascontiguousarray(a)
+    return a.view(np.dtype((np.void, 8 * a.shape[1]))).ravel().tolist()
+
+
 def union(a, b):
-    """Base.union(a, b) on vectors of multi-indices: order preserving, duplicates dropped."""
+    """Base.union(a, b) on vectors of multi-indices: order preserving, duplicates dropped.  `a` is a
+    kronecker product of a duplicate-free set (tensorci2.jl:526-527), hence already duplicate free."""
     if b.shape[0] == 0:
-        c = a
-    else:
-        c = np.concatenate([a, b], axis=0)
-    if c.shape[0] <= 1:
-        return c
-    if c.shape[1] == 0:
-        return c[:1]
-    _, first = np.unique(c, axis=0, return_index=True)
-    if first.size == c.shape[0]:
-        return c
-    return c[np.sort(first)]
+        return a
+    if a.shape[1] == 0:
+        return a[:1] if a.shape[0] else b[:1]
+    seen = set(_rowkeys(a))
+    keep = []
+    for i, k in enumerate(_rowkeys(b)):
+        if k not in seen:
+            seen.add(k)
+            keep.append(i)
+    if not keep:
+        return a
+    return np.concatenate([a, b[keep]], axis=0)
 
 
 def pushunique(arr, item):  # util.jl:16-20 on an index-set array
