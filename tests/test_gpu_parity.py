@@ -199,6 +199,47 @@ def test_rrlu_streaming_regime(T, oracle, m, n, r, leftorth):
                     oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=leftorth))
 
 
+def test_rrlu_pivot_column_from_l2(T, oracle):
+    """m > 24576: the pivot column no longer fits shared memory and is read from L2 (kernel mode 3)."""
+    A = lowrank_matrix(25000, 300, 12, seed=77)
+    assert_lu_equal(T.rrlu(A, maxrank=12, reltol=1e-12), oracle.rrlu(A, maxrank=12, reltol=1e-12))
+
+
+def test_rrlu_config2_full_size_vs_oracle(T, oracle):
+    """BASELINE config 2 at its largest size, 8192 x 8192 (537 MB, HBM streamed), truncated at 32 pivots so
+    that the single-threaded oracle finishes in seconds; permutations and factors are bit-identical."""
+    A = lowrank_matrix(8192, 8192, 64, seed=2)
+    lu = T.rrlu(A, maxrank=32, reltol=1e-12)
+    ref = oracle.rrlu(A, maxrank=32, reltol=1e-12)
+    assert_lu_equal(lu, ref)
+
+
+def test_rrlu_config2_full_rank_properties(T):
+    """Size-independent properties at 8192 x 8192, maxrank 1024 (no oracle run: ~100 s on a CPU core):
+    L unit lower / U upper, permutations are permutations, full-pivoting bound |L| <= 1, sampled
+    reconstruction error below the last pivot error."""
+    m = n = 8192
+    r = 1024
+    rng = np.random.default_rng(2)
+    p = rng.random((m, r)) * 2.0 ** (-40.0 * np.arange(1, r + 1) / r)
+    q = rng.random((r, n))
+    A = np.asfortranarray(p @ q)
+    lu = T.rrlu(A, maxrank=r, reltol=1e-12)
+    assert lu.npivot == r
+    assert sorted(lu.rowpermutation.tolist()) == list(range(1, m + 1))
+    assert sorted(lu.colpermutation.tolist()) == list(range(1, n + 1))
+    L, U = lu.L, lu.U
+    assert np.all(L == np.tril(L)) and np.all(U == np.triu(U)) and np.all(np.diag(L) == 1.0)
+    assert np.max(np.abs(L)) <= 1.0  # every multiplier is a ratio to the largest entry
+    pe = T.pivoterrors(lu)
+    assert np.all(np.diff(np.abs(np.diag(U))) <= 1e-9 * pe[0] + 2.0 * np.abs(np.diag(U))[:-1])
+    rows = rng.integers(0, m, 200)
+    cols = rng.integers(0, n, 200)
+    Ap = A[lu.rowpermutation - 1][:, lu.colpermutation - 1]
+    rec = np.einsum("ik,ki->i", L[rows, :], U[:, cols])
+    assert np.max(np.abs(rec - Ap[rows, cols])) <= 50 * max(lu.error, 1e-16 * pe[0])
+
+
 @pytest.mark.parametrize("m,n,r", [(17, 33, 9), (130, 257, 40), (513, 700, 48)])
 def test_rrlu_streaming_forced(T, oracle, m, n, r, monkeypatch):
     """Same kernels with residency switched off (every size takes the global-memory path)."""
