@@ -303,7 +303,17 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         i64 big_ctas = ((M + 127) / 128) * ((N + 127) / 128) * batch;
         static const int use_mma = getenv("TCI_DGEMM_NO_MMA") ? 0 : 1;
         const i64 mid_ctas = ((M + 63) / 64) * ((N + 63) / 64) * batch;
-        if (use_mma && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96)
+        static const int force_tile = getenv("TCI_DGEMM_TILE") ? atoi(getenv("TCI_DGEMM_TILE")) : 0;
+        if (use_mma && force_tile == 64)
+            launch_dgemm_mma<64, 64, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                           strideC, batch, offA, offB);
+        else if (use_mma && force_tile == 12864)
+            launch_dgemm_mma<128, 64, 4, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                            strideC, batch, offA, offB);
+        else if (use_mma && force_tile == 6432)
+            launch_dgemm_mma<64, 32, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                           strideC, batch, offA, offB);
+        else if (use_mma && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96)
             launch_dgemm_mma<128, 128, 2, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C,
                                              ldc, strideC, batch, offA, offB);
         else if (use_mma && mid_ctas >= 16 && M >= 32 && N >= 32)

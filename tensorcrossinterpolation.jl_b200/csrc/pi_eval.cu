@@ -12,38 +12,40 @@
 #define PI_THREADS 256
 #define PI_TCOLS 32
 
-// per-index state: st[k * count + q] = state_k of multi-index q over sites [site0, site0+len)
-__global__ void k_states(tci_analytic_t t, const i64 *__restrict__ idx, int len, i64 count, int site0, int from_init,
-                         double *__restrict__ st)
+// Row, centre and column states in ONE launch: thread q < nI handles left multi-index q (prefix state
+// from tci_target_init), the next C threads the centre combinations (first centre index fastest), the last
+// nJ threads the right multi-indices.  st[k * count + q] = state component k of entry q.
+__global__ void k_states_all(tci_analytic_t t, const i64 *__restrict__ I, int nl, i64 nI, int M, i64 C,
+                             const i64 *__restrict__ J, int nr, i64 nJ, double *__restrict__ rs,
+                             double *__restrict__ cs, double *__restrict__ js, int *__restrict__ csig)
 {
     i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (q >= count) return;
     double s[TCI_MAX_STATE];
-    if (from_init)
+    if (q < nI) {
         tci_target_init(&t, s);
-    else
-        for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = 0.0;
-    for (int k = 0; k < len; ++k) tci_target_accum(&t, site0 + k, idx[(i64)len * q + k], s);
-    for (int k = 0; k < t.nstate; ++k) st[(i64)k * count + q] = s[k];
-}
-
-// centre combos: c -> (sigma_1 fastest, ...), state over sites [site0, site0+M)
-__global__ void k_centre_states(tci_analytic_t t, int M, i64 C, int site0, double *__restrict__ st,
-                                int *__restrict__ csig /* M x C, nullable */)
-{
-    i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s[TCI_MAX_STATE];
-    for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = 0.0;
-    i64 rem = c;
-    for (int k = 0; k < M; ++k) {
-        i64 d = t.localdims[site0 + k];
-        i64 sig = rem % d + 1;
-        rem /= d;
-        tci_target_accum(&t, site0 + k, sig, s);
-        if (csig) csig[(i64)k * C + c] = (int)sig;
+        for (int k = 0; k < nl; ++k) tci_target_accum(&t, k, I[(i64)nl * q + k], s);
+        for (int k = 0; k < t.nstate; ++k) rs[(i64)k * nI + q] = s[k];
+        return;
     }
-    for (int k = 0; k < t.nstate; ++k) st[(i64)k * C + c] = s[k];
+    q -= nI;
+    for (int k = 0; k < TCI_MAX_STATE; ++k) s[k] = 0.0;
+    if (q < C) {
+        i64 rem = q;
+        for (int k = 0; k < M; ++k) {
+            const i64 d = t.localdims[nl + k];
+            const i64 sig = rem % d + 1;
+            rem /= d;
+            tci_target_accum(&t, nl + k, sig, s);
+            if (csig) csig[(i64)k * C + q] = (int)sig;
+        }
+        for (int k = 0; k < t.nstate; ++k) cs[(i64)k * C + q] = s[k];
+        return;
+    }
+    q -= C;
+    if (q < nJ && js) {
+        for (int k = 0; k < nr; ++k) tci_target_accum(&t, nl + M + k, J[(i64)nr * q + k], s);
+        for (int k = 0; k < t.nstate; ++k) js[(i64)k * nJ + q] = s[k];
+    }
 }
 
 __device__ __forceinline__ unsigned long long absbits(double v)
@@ -184,21 +186,22 @@ int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, 
     i64 C = 1;
     for (i64 k = 0; k < M; ++k) C *= t.localdims[nl + k];
     const bool exact = tci_target_exact(an.kind) != 0;
-    DevBuf<double> rs(ctx), cs(ctx), js(ctx);
-    DevBuf<int> csig(ctx);
-    TCI_CUDA(ctx, rs.alloc((size_t)NS * nI));
-    TCI_CUDA(ctx, cs.alloc((size_t)NS * C));
+    // one scratch allocation: [rs NS*nI][cs NS*C][js NS*nJ][csig M*C ints]
+    DevBuf<double> st(ctx);
+    const size_t n_rs = (size_t)NS * nI, n_cs = (size_t)NS * C, n_js = exact ? (size_t)NS * nJ : 0;
+    TCI_CUDA(ctx, st.alloc(n_rs + n_cs + n_js + (exact ? 0 : ((size_t)(M > 0 ? M : 1) * C + 1) / 2 + 1)));
+    struct {
+        double *p;
+    } rs{st.p}, cs{st.p + n_rs}, js{st.p + n_rs + n_cs};
+    struct {
+        int *p;
+    } csig{exact ? nullptr : reinterpret_cast<int *>(st.p + n_rs + n_cs + n_js)};
     const int TB = 128;
-    k_states<<<(unsigned)((nI + TB - 1) / TB), TB, 0, ctx->stream>>>(an, dI, (int)nl, nI, 0, 1, rs.p);
-    ctx->launches++;
-    if (!exact) TCI_CUDA(ctx, csig.alloc((size_t)(M > 0 ? M : 1) * C));
-    k_centre_states<<<(unsigned)((C + TB - 1) / TB), TB, 0, ctx->stream>>>(an, (int)M, C, (int)nl, cs.p,
-                                                                           exact ? nullptr : csig.p);
+    const i64 nthreads = nI + C + (exact ? nJ : 0);
+    k_states_all<<<(unsigned)((nthreads + TB - 1) / TB), TB, 0, ctx->stream>>>(
+        an, dI, (int)nl, nI, (int)M, C, dJ, (int)nr, nJ, rs.p, cs.p, exact ? js.p : nullptr, csig.p);
     ctx->launches++;
     if (exact) {
-        TCI_CUDA(ctx, js.alloc((size_t)NS * nJ));
-        k_states<<<(unsigned)((nJ + TB - 1) / TB), TB, 0, ctx->stream>>>(an, dJ, (int)nr, nJ, (int)(nl + M), 0, js.p);
-        ctx->launches++;
 #define PI_LAUNCH(NSV, KINDV) launch_exact<NSV, KINDV>(ctx, an, rs.p, nI, cs.p, C, js.p, nJ, out->p, out->ld, d_maxbits)
         switch (an.kind) {
         case TCI_TARGET_LORENTZ: PI_LAUNCH(1, TCI_TARGET_LORENTZ); break;
@@ -274,15 +277,21 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
     if (dst && (dst->m != nI * C || col0 < 0 || col0 + nJ > dst->ncap))
         return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_eval_into: destination block does not fit");
 
-    DevBuf<i64> dI(ctx), dJ(ctx);
-    DevBuf<unsigned long long> dmax(ctx);
-    {
-        StageTimer tm(ctx, ST_H2D);
-        TCI_CUDA(ctx, dI.upload(I, (size_t)(nl * nI)));
-        TCI_CUDA(ctx, dJ.upload(J, (size_t)(nr * nJ)));
-        TCI_CUDA(ctx, dmax.alloc(1));
-        TCI_CUDA(ctx, cudaMemsetAsync(dmax.p, 0, sizeof(unsigned long long), ctx->stream));
-    }
+    // one allocation for [max bits 16 B][I nl*nI][J nr*nJ]
+    DevBuf<i64> idx(ctx);
+    TCI_CUDA(ctx, idx.alloc(2 + (size_t)(nl * nI) + (size_t)(nr * nJ)));
+    struct {
+        i64 *p;
+    } dI{idx.p + 2}, dJ{idx.p + 2 + nl * nI};
+    struct {
+        unsigned long long *p;
+    } dmax{reinterpret_cast<unsigned long long *>(idx.p)};
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    TCI_CUDA(ctx, cudaMemsetAsync(idx.p, 0, 16, ctx->stream));
+    if (nl * nI > 0)
+        TCI_CUDA(ctx, cudaMemcpyAsync(dI.p, I, (size_t)(nl * nI) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    if (nr * nJ > 0)
+        TCI_CUDA(ctx, cudaMemcpyAsync(dJ.p, J, (size_t)(nr * nJ) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     tci_dmat *out = nullptr;
     tci_dmat view; // column block of dst
     int rc = 0;
@@ -297,7 +306,6 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
         if (rc) return rc;
     }
     {
-        StageTimer tm(ctx, ST_PI);
         switch (t.kind) {
         case 0: rc = pi_eval_analytic(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, dmax.p); break;
         case 1:
@@ -315,20 +323,23 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
         return rc;
     }
     {
-        StageTimer tm(ctx, ST_D2H);
-        if (maxabs) {
-            unsigned long long bits = 0;
+        unsigned long long bits = 0;
+        cudaEventRecord(ctx->ev1, ctx->stream); // evaluation done (kernel stage), copies follow
+        if (maxabs)
             TCI_CUDA(ctx, cudaMemcpyAsync(&bits, dmax.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
-            TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (out_host)
+            TCI_CUDA(ctx, cudaMemcpy2DAsync(out_host, out->m * sizeof(double), out->p, out->ld * sizeof(double),
+                                            out->m * sizeof(double), out->n, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaEventRecord(ctx->ev3, ctx->stream);
+        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stage_ms[ST_PI] += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_D2H] += ms;
+        if (maxabs) {
             double v;
             memcpy(&v, &bits, sizeof(v));
             *maxabs = v;
         }
-        if (out_host) {
-            TCI_CUDA(ctx, cudaMemcpy2DAsync(out_host, out->m * sizeof(double), out->p, out->ld * sizeof(double),
-                                            out->m * sizeof(double), out->n, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (dst) return TCI_OK;
     if (out_dev)

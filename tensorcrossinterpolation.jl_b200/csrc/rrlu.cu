@@ -28,6 +28,7 @@
 // write); for matrices up to ~100 MB the trailing matrix is L2 resident.
 #include <cstdio>
 #include <cstdlib>
+#include <set>
 
 #include "tci_internal.h"
 
@@ -485,6 +486,18 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
     }
 
     __syncthreads();
+    { // NaN scan of the L and U parts of the own columns (matrixlu.jl:164-169): bit 0 L, bit 1 U
+        int f = 0;
+#pragma unroll 1
+        for (int o = warp; o < nown; o += nwarps) {
+            const int cp = a.colpos[g + o * G];
+            const double *col = RR_COL(o);
+            const int hi = cp < npiv ? m : npiv; // picked column: all rows belong to L or U; otherwise rows < r (U)
+            for (int i = lane; i < hi; i += 32)
+                if (isnan(col[i])) f |= ((cp < npiv && i >= cp) ? 1 : 0) | ((i < npiv && cp >= i) ? 2 : 0);
+        }
+        if (f) atomicOr(&a.result[2], f);
+    }
     if (RES) { // write the factors back
 #pragma unroll 1
         for (int o = warp; o < nown; o += nwarps) {
@@ -513,20 +526,6 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
         *a.result_err = (npiv >= mn) ? 0.0 : lasterr; // matrixlu.jl:176-178
     }
 #undef RR_COL
-}
-
-// any NaN in L = tril(A[:,1:r]) or U = triu(A[1:r,:]) (matrixlu.jl:164-169); flags bit0 L, bit1 U
-__global__ void k_nancheck(const double *__restrict__ A, i64 m, i64 n, i64 ld, const int *__restrict__ colpos, int r,
-                           int *flags)
-{
-    int f = 0;
-    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < m * n; e += (i64)gridDim.x * blockDim.x) {
-        i64 i = e % m, j = e / m;
-        int cp = colpos[j];
-        bool inL = cp < r && i >= cp, inU = i < r && cp >= i;
-        if ((inL || inU) && isnan(A[i + ld * j])) f |= (inL ? 1 : 0) | (inU ? 2 : 0);
-    }
-    if (f) atomicOr(flags, f);
 }
 
 // L (m x r, ldl) / U (r x n, ldu) in position order, as lu.L / lu.U of matrixlu.jl:162-174
@@ -575,7 +574,11 @@ static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bo
 {
     void *kargs[] = {&args};
     const void *fn = exact ? rrlu_fn_mode<true>(mode, args.leftorth != 0) : rrlu_fn_mode<false>(mode, args.leftorth != 0);
-    TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::set<const void *> configured;
+    if (!configured.count(fn)) {
+        TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        configured.insert(fn);
+    }
     cudaEventRecord(ctx->ev2, ctx->stream);
     TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), kargs, smem, ctx->stream));
     cudaEventRecord(ctx->ev3, ctx->stream);
@@ -659,30 +662,25 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     args.maxown = maxown;
     args.lds = lds;
 
-    DevBuf<int> colpos(ctx), result(ctx), pivrows(ctx);
-    DevBuf<i64> d_rowperm(ctx), d_colperm(ctx);
-    DevBuf<double> pivvals(ctx), xbuf(ctx), d_err(ctx);
-    DevBuf<RRCand> cand(ctx);
-    TCI_CUDA(ctx, colpos.alloc(n));
-    TCI_CUDA(ctx, result.alloc(4));
-    TCI_CUDA(ctx, d_rowperm.alloc(m));
-    TCI_CUDA(ctx, d_colperm.alloc(n));
-    TCI_CUDA(ctx, pivvals.alloc(mr));
-    TCI_CUDA(ctx, pivrows.alloc(mr));
-    TCI_CUDA(ctx, xbuf.alloc((size_t)2 * G * args.ldx));
-    TCI_CUDA(ctx, d_err.alloc(1));
-    TCI_CUDA(ctx, cand.alloc((size_t)2 * G));
-    TCI_CUDA(ctx, cudaMemsetAsync(cand.p, 0, (size_t)2 * G * sizeof(RRCand), ctx->stream));
-    TCI_CUDA(ctx, cudaMemsetAsync(result.p, 0, 4 * sizeof(int), ctx->stream));
-    args.colpos = colpos.p;
-    args.rowperm = d_rowperm.p;
-    args.colperm = d_colperm.p;
-    args.pivvals = pivvals.p;
-    args.pivrows = pivrows.p;
-    args.cand = cand.p;
+    // One scratch arena: [result 4 int | err | pad][cand 2G x 16 B][pivvals][rowperm][colperm] (this prefix is
+    // what comes back in ONE device-to-host copy) [colpos][pivrows]; the posted columns are separate.
+    const size_t o_cand = 32, o_piv = o_cand + (size_t)2 * G * sizeof(RRCand), o_rp = o_piv + (size_t)mr * 8,
+                 o_cp = o_rp + (size_t)m * 8, o_back = o_cp + (size_t)n * 8, o_pos = o_back,
+                 o_prow = o_pos + (((size_t)n * 4 + 15) & ~(size_t)15), o_end = o_prow + (size_t)mr * 4 + 16;
+    DevBuf<char> arena(ctx);
+    DevBuf<double> xbuf(ctx);
+    TCI_CUDA(ctx, arena.alloc(o_end));
+    if (!(G == 1 && resident)) TCI_CUDA(ctx, xbuf.alloc((size_t)2 * G * args.ldx)); // mode 0 posts nothing
+    TCI_CUDA(ctx, cudaMemsetAsync(arena.p, 0, o_piv, ctx->stream));
+    args.result = reinterpret_cast<int *>(arena.p);
+    args.result_err = reinterpret_cast<double *>(arena.p + 16);
+    args.cand = reinterpret_cast<RRCand *>(arena.p + o_cand);
+    args.pivvals = reinterpret_cast<double *>(arena.p + o_piv);
+    args.rowperm = reinterpret_cast<i64 *>(arena.p + o_rp);
+    args.colperm = reinterpret_cast<i64 *>(arena.p + o_cp);
+    args.colpos = reinterpret_cast<int *>(arena.p + o_pos);
+    args.pivrows = reinterpret_cast<int *>(arena.p + o_prow);
     args.xbuf = xbuf.p;
-    args.result = result.p;
-    args.result_err = d_err.p;
 
     DevBuf<long long> dbg(ctx);
     const char *dbgenv = getenv("TCI_RRLU_DEBUG");
@@ -692,44 +690,41 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         args.dbg = dbg.p;
         args.dbg_cta = atoi(dbgenv) % G;
     }
-    int res[4] = {0, 0, 0, 0};
-    double lu_error = 0.0;
-    std::vector<double> pv;
+    std::vector<char> back(o_back);
+    cudaEventRecord(ctx->ev0, ctx->stream);
     {
-        StageTimer tm(ctx, ST_RRLU);
-        int rc = rrlu_launch(ctx, args, G, T, smem, exact_mode != 0, G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
+        int rc = rrlu_launch(ctx, args, G, T, smem, exact_mode != 0,
+                             G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
         if (rc) return rc;
-        TCI_CUDA(ctx, cudaMemcpyAsync(res, result.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        TCI_CUDA(ctx, cudaMemcpyAsync(&lu_error, d_err.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        {
-            float kms = 0.f;
-            if (cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_RRLU_KERNEL] += kms;
-        }
-        if (dbgenv) {
-            long long h[16];
-            cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[rrlu dbg] m=%lld n=%lld r=%d G=%d T=%d res=%d cycles/pivot: wait+reduce %lld (poll %lld acqfence %lld payload %lld) | swap+x %lld | ys+L %lld | update %lld | blockreduce %lld | post %lld | fence %lld\n",
-                    (long long)m, (long long)n, res[0], G, T, (int)resident, h[0] / (res[0] + 1), h[7] / (res[0] + 1), h[8] / (res[0] + 1), h[9] / (res[0] + 1), h[1] / (res[0] + 1), h[2] / (res[0] + 1),
-                    h[3] / (res[0] + 1), h[4] / (res[0] + 1), h[5] / (res[0] + 1), h[6] / (res[0] + 1));
-        }
-        const int r = res[0];
-        unsigned blocks = (unsigned)std::min<i64>((m * n + 255) / 256, (i64)ctx->sm_count * 8);
-        k_nancheck<<<blocks, 256, 0, ctx->stream>>>(A->p, m, n, A->ld, colpos.p, r, result.p + 2);
-        ctx->launches++;
-        pv.resize(r);
-        TCI_CUDA(ctx, cudaMemcpyAsync(res + 2, result.p + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        if (r > 0)
-            TCI_CUDA(ctx, cudaMemcpyAsync(pv.data(), pivvals.p, r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        TCI_CUDA(ctx, cudaMemcpyAsync(rowperm, d_rowperm.p, m * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
-        TCI_CUDA(ctx, cudaMemcpyAsync(colperm, d_colperm.p, n * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
-        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    TCI_CUDA(ctx, cudaMemcpyAsync(back.data(), arena.p, o_back, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_RRLU_KERNEL] += ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stage_ms[ST_RRLU] += ms;
+    }
+    const int *res = reinterpret_cast<const int *>(back.data());
+    const double lu_error = *reinterpret_cast<const double *>(back.data() + 16);
     const int r = res[0];
+    if (dbgenv) {
+        long long h[16];
+        cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr,
+                "[rrlu dbg] m=%lld n=%lld r=%d G=%d T=%d res=%d cycles/pivot: wait+reduce %lld (poll %lld acqfence %lld "
+                "payload %lld) | swap+x %lld | ys+L %lld | update %lld | blockreduce %lld | post %lld | fence %lld\n",
+                (long long)m, (long long)n, r, G, T, (int)resident, h[0] / (r + 1), h[7] / (r + 1), h[8] / (r + 1),
+                h[9] / (r + 1), h[1] / (r + 1), h[2] / (r + 1), h[3] / (r + 1), h[4] / (r + 1), h[5] / (r + 1),
+                h[6] / (r + 1));
+    }
     if ((res[1] & 1) || (res[2] & 1)) return tci_fail(ctx, TCI_ERR_NAN_L, "lu.L contains NaNs");
     if (res[2] & 2) return tci_fail(ctx, TCI_ERR_NAN_U, "lu.U contains NaNs");
-    for (i64 i = 0; i < m; ++i) rowperm[i] += 1;
-    for (i64 j = 0; j < n; ++j) colperm[j] += 1;
+    const double *pv = reinterpret_cast<const double *>(back.data() + o_piv);
+    const i64 *rp = reinterpret_cast<const i64 *>(back.data() + o_rp);
+    const i64 *cp = reinterpret_cast<const i64 *>(back.data() + o_cp);
+    for (i64 i = 0; i < m; ++i) rowperm[i] = rp[i] + 1;
+    for (i64 j = 0; j < n; ++j) colperm[j] = cp[j] + 1;
     *npivot = r;
     *error = lu_error;
     if (pivoterrors) {
@@ -744,12 +739,11 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         lu->n = n;
         lu->r = r;
         lu->leftorthogonal = leftorthogonal != 0;
-        lu->d_rowperm = d_rowperm.p;
-        lu->d_colperm = d_colperm.p;
-        lu->d_colpos = colpos.p;
-        d_rowperm.p = nullptr; // ownership moves to the handle
-        d_colperm.p = nullptr;
-        colpos.p = nullptr;
+        lu->arena = arena.p; // ownership of the arena moves to the handle
+        lu->d_rowperm = args.rowperm;
+        lu->d_colperm = args.colperm;
+        lu->d_colpos = args.colpos;
+        arena.p = nullptr;
         cleanup.armed = false;
         *factors = lu;
     }
@@ -800,9 +794,7 @@ extern "C" int tci_lu_destroy(tci_lu *lu)
     if (!lu) return TCI_OK;
     tci_ctx *ctx = lu->ctx;
     cudaSetDevice(ctx->device);
-    dev_free(ctx, lu->d_rowperm);
-    dev_free(ctx, lu->d_colperm);
-    dev_free(ctx, lu->d_colpos);
+    dev_free(ctx, lu->arena);
     tci_dmat_destroy(lu->A);
     delete lu;
     return TCI_OK;

@@ -63,6 +63,7 @@ struct tci_lu {
     tci_dmat *A = nullptr; // factorised in place (rows physically permuted, columns virtually)
     i64 m = 0, n = 0, r = 0;
     bool leftorthogonal = true;
+    void *arena = nullptr;    // owns the three arrays below
     i64 *d_rowperm = nullptr; // 0-based, device
     i64 *d_colperm = nullptr; // position -> physical column, 0-based, device
     int *d_colpos = nullptr;  // physical column -> position
