@@ -354,10 +354,17 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
             // RR_U 16-byte loads back to back so that enough bytes are in flight to cover HBM latency.
             const int i0 = lo & ~1;
             const int ntr = (m - i0 + U * 64 - 1) / (U * 64);
-            int e = warp / ntr, rt = warp - e * ntr; // tile t = e*ntr + rt, advanced by nwarps without divisions
+            // tile t = e*ntr + rt, t = warp, warp + nwarps, ...  Odd steps walk the same tiles backwards: what
+            // was touched last in the previous step is touched first now and is still in L2 (the trailing
+            // matrix is swept once per pivot, so a fixed order would evict everything before it is reused).
             const int de = nwarps / ntr, dr = nwarps - de * ntr;
+            const int ntiles = nact * ntr;
+            const bool backward = !RES && (s & 1);
+            int t0 = warp;
+            if (backward && ntiles > warp) t0 = warp + ((ntiles - 1 - warp) / nwarps) * nwarps;
+            int e = t0 / ntr, rt = t0 - e * ntr;
 #pragma unroll 1
-            while (e < nact) {
+            while (e < nact && e >= 0) {
                 const int cp = actp[e];
                 const double y = do_update ? ys[e] : 0.0;
                 double *const cptr = RR_COL(acto[e]);
@@ -420,11 +427,20 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
                     bcpv = cp;
                     browv = trow;
                 }
-                e += de;
-                rt += dr;
-                if (rt >= ntr) {
-                    rt -= ntr;
-                    ++e;
+                if (backward) {
+                    e -= de;
+                    rt -= dr;
+                    if (rt < 0) {
+                        rt += ntr;
+                        --e;
+                    }
+                } else {
+                    e += de;
+                    rt += dr;
+                    if (rt >= ntr) {
+                        rt -= ntr;
+                        ++e;
+                    }
                 }
             }
         }
