@@ -310,6 +310,28 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
                                     "shape": [nI, nJ], "hbm_gbs": 8 * evals / (ms * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": 8 * evals / (ms * 1e-3) / 1e9 / peaks()[0] / world,
                                     "sharding": f"column blocks over {world} rank(s), kernel time only"}
+        if world > 1:
+            # fused form: every rank's evaluation kernel stores its column block straight into rank 0's HBM
+            # through an IPC-mapped pointer (NVLink peer stores), then one barrier
+            from tci_b200.parallel import ShardedEvaluator
+            sf = ShardedEvaluator(f, dist, torch, mode="peer")
+            for it in range(4):
+                if it == 1:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                dev, mx = sf.batchevaluate_device(I, J, 0)
+                del dev
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            sf.release()
+            extra[f"pi_eval_{name}_sharded_peer_writes"] = {
+                "mevals_per_s": nI * nJ / dt / 1e6, "ms": dt * 1e3,
+                "note": "Pi assembled in rank 0's HBM by peer stores from the evaluation kernels (wall clock incl. "
+                        "index upload, barrier and max all-reduce)"}
         if world > 1 and name == "lorentz":
             # the same evaluation written into the shared buffer + ONE in-place NCCL all-gather
             full = T.DeviceMatrix.empty(ctx, nI, blk * world)

@@ -66,6 +66,18 @@ int tci_dmat_destroy(tci_dmat *a);
 /* shrink the logical column count (n <= allocated columns); used after an all-gather of padded blocks */
 int tci_dmat_resize_cols(tci_dmat *a, int64_t n);
 
+/* ---- peer-shared buffers (multi-GPU: one process per GPU) -------------------------------------
+ * The rrLU owner allocates the Pi buffer with tci_shared_alloc and hands the 64-byte IPC handle to the
+ * other ranks (any host transport); they map it with tci_shared_open and evaluate their column block
+ * with tci_pi_eval_into on a tci_dmat_wrap view, i.e. the evaluation kernel stores straight into the
+ * owner's HBM over NVLink (peer st.global) -- compute and transfer are one kernel, no staging copy.  */
+int tci_shared_alloc(tci_ctx *ctx, int64_t bytes, void **dptr, char handle[64]);
+int tci_shared_open(tci_ctx *ctx, const char handle[64], void **dptr);
+int tci_shared_close(tci_ctx *ctx, void *dptr);
+int tci_shared_free(tci_ctx *ctx, void *dptr);
+/* non-owning device matrix on caller-managed memory (ld >= m, ld % 2 == 0, 16-byte aligned base) */
+int tci_dmat_wrap(tci_ctx *ctx, void *dptr, int64_t m, int64_t n, int64_t ld, tci_dmat **out);
+
 /* ---- targets: the function f being interpolated ------------------------- */
 /* Replaces the Julia closure / BatchEvaluator object `f` (cachedtensortrain.jl:1,
  * batcheval.jl:67-83, docs/src/index.md:174-241).  kind_id: tci_targets.h.       */

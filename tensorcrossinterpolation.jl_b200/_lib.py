@@ -34,6 +34,11 @@ SYMBOLS = {
     "tci_dmat_fetch": (C.c_int, [VP, P_f64]),
     "tci_dmat_destroy": (C.c_int, [VP]),
     "tci_dmat_resize_cols": (C.c_int, [VP, i64]),
+    "tci_dmat_wrap": (C.c_int, [VP, VP, i64, i64, i64, C.POINTER(VP)]),
+    "tci_shared_alloc": (C.c_int, [VP, i64, C.POINTER(VP), C.c_char_p]),
+    "tci_shared_open": (C.c_int, [VP, C.c_char_p, C.POINTER(VP)]),
+    "tci_shared_close": (C.c_int, [VP, VP]),
+    "tci_shared_free": (C.c_int, [VP, VP]),
     "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
@@ -165,6 +170,13 @@ class DeviceMatrix:
         a = np.asfortranarray(a, dtype=np.float64)
         h = VP()
         ctx.check(lib().tci_dmat_create(ctx.h, a.shape[0], a.shape[1], pf(a), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap(cls, ctx, dptr, m, n, ld):
+        """Non-owning view on caller-managed device memory (tci_dmat_wrap)."""
+        h = VP()
+        ctx.check(lib().tci_dmat_wrap(ctx.h, VP(dptr), m, n, ld, C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

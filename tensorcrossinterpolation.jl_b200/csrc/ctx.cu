@@ -1,4 +1,6 @@
 // ctx.cu -- context, device matrices, target registry, timers.
+#include <cstring>
+
 #include "tci_internal.h"
 
 static thread_local std::string g_create_error;
@@ -145,6 +147,66 @@ extern "C" int tci_dmat_resize_cols(tci_dmat *a, int64_t n)
 {
     if (!a || n < 0 || n > a->ncap) return TCI_ERR_ARG;
     a->n = n;
+    return TCI_OK;
+}
+
+extern "C" int tci_dmat_wrap(tci_ctx *ctx, void *dptr, int64_t m, int64_t n, int64_t ld, tci_dmat **out)
+{
+    if (!ctx || !out || !dptr || m < 0 || n < 0 || ld < m || (ld & 1) || ((size_t)dptr & 15))
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_dmat_wrap: bad arguments");
+    tci_dmat *a = new tci_dmat();
+    a->ctx = ctx;
+    a->p = static_cast<double *>(dptr);
+    a->m = m;
+    a->n = n;
+    a->ncap = n;
+    a->ld = ld;
+    a->owned = false;
+    *out = a;
+    return TCI_OK;
+}
+
+extern "C" int tci_shared_alloc(tci_ctx *ctx, int64_t bytes, void **dptr, char handle[64])
+{
+    TCI_ENTER(ctx);
+    if (!dptr || !handle || bytes <= 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_shared_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TCI_CUDA(ctx, cudaMalloc(dptr, (size_t)bytes)); // pool (async) allocations cannot be exported
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dptr);
+        *dptr = nullptr;
+        return tci_fail(ctx, TCI_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    return TCI_OK;
+}
+
+extern "C" int tci_shared_open(tci_ctx *ctx, const char handle[64], void **dptr)
+{
+    TCI_ENTER(ctx);
+    if (!dptr || !handle) return tci_fail(ctx, TCI_ERR_ARG, "tci_shared_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    TCI_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TCI_OK;
+}
+
+extern "C" int tci_shared_close(tci_ctx *ctx, void *dptr)
+{
+    TCI_ENTER(ctx);
+    if (dptr) TCI_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+    return TCI_OK;
+}
+
+extern "C" int tci_shared_free(tci_ctx *ctx, void *dptr)
+{
+    TCI_ENTER(ctx);
+    if (dptr) {
+        cudaStreamSynchronize(ctx->stream);
+        TCI_CUDA(ctx, cudaFree(dptr));
+    }
     return TCI_OK;
 }
 

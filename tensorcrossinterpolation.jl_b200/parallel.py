@@ -81,8 +81,14 @@ def broadcast_pivots(dist, result, owner, group=None):
 class ShardedEvaluator(BatchEvaluator):
     """Wraps a BatchEvaluator for world_size > 1: Pi is evaluated in column blocks (GPU path)."""
 
-    def __init__(self, f, dist, torch, owner=0, group=None):
+    def __init__(self, f, dist, torch, owner=0, group=None, mode="peer"):
+        """mode "peer": every rank's evaluation kernel stores its column block straight into the rrLU
+        owner's HBM through an IPC-mapped pointer (NVLink peer st.global; compute and transfer are the
+        same kernel).  mode "allgather": per-rank blocks + one NCCL all-gather (every rank ends with Pi)."""
         self.f, self.dist, self.torch, self.owner, self.group = f, dist, torch, owner, group
+        self.local = f  # unsharded evaluator for the small replicated stages (sweep1site)
+        self.mode = mode
+        self._ptr, self._cap = None, 0
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.ctx = f.ctx
@@ -103,16 +109,64 @@ class ShardedEvaluator(BatchEvaluator):
     def _pi(self, *a):
         return self.f._pi(*a)
 
+    def _ensure_shared(self, nbytes):
+        """(Re)allocate the peer-shared Pi arena on the owner and map it on the other ranks."""
+        import ctypes as C
+        from ._lib import lib
+        if nbytes <= self._cap:
+            return
+        L, ctx, dist = lib(), self.ctx, self.dist
+        self.release()
+        cap = max(int(nbytes), 2 * self._cap, 1 << 22)
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        if self.rank == self.owner:
+            ctx.check(L.tci_shared_alloc(ctx.h, cap, C.byref(ptr), handle))
+        obj = [handle.raw if self.rank == self.owner else None]
+        dist.broadcast_object_list(obj, src=self.owner, group=self.group)
+        if self.rank != self.owner:
+            ctx.check(L.tci_shared_open(ctx.h, obj[0], C.byref(ptr)))
+        self._ptr, self._cap = ptr.value, cap
+
+    def release(self):
+        import ctypes as C
+        from ._lib import lib
+        if self._ptr:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            if self.rank == self.owner:
+                lib().tci_shared_free(self.ctx.h, C.c_void_p(self._ptr))
+            else:
+                lib().tci_shared_close(self.ctx.h, C.c_void_p(self._ptr))
+            self._ptr, self._cap = None, 0
+
+    def _batch_peer(self, I, J, M, rows):
+        from ._lib import DeviceMatrix
+        torch, dist = self.torch, self.dist
+        nJ = len(J)
+        ld = (rows + 15) // 16 * 16
+        self._ensure_shared(ld * nJ * 8)
+        view = DeviceMatrix.wrap(self.ctx, self._ptr, rows, nJ, ld)
+        blk, ranges = column_blocks(nJ, self.world)
+        lo, hi = ranges[self.rank]
+        mx = self.f.batchevaluate_into(view, lo, I, J[lo:hi], M) if hi > lo else 0.0
+        torch.cuda.synchronize()  # the block is in the owner's HBM when the kernel has retired
+        dist.barrier(group=self.group)
+        mx = maxabs_allreduce(dist, torch, mx, torch.device("cuda", self.ctx.device), self.group)
+        return view, mx
+
     def batchevaluate_device(self, Iset, Jset, M):
         from ._lib import DeviceMatrix
         from .util import as_indexset
         torch, dist = self.torch, self.dist
         I, J = as_indexset(Iset), as_indexset(Jset)
         nJ = len(J)
-        blk, ranges = column_blocks(nJ, self.world)
-        lo, hi = ranges[self.rank]
         nl = I.shape[1]
         rows = len(I) * int(np.prod(self.localdims[nl:nl + M], dtype=np.int64))
+        if self.mode == "peer" and self.world > 1:
+            return self._batch_peer(I, J, M, rows)
+        blk, ranges = column_blocks(nJ, self.world)
+        lo, hi = ranges[self.rank]
         full = DeviceMatrix.empty(self.ctx, rows, blk * self.world)
         mx = self.f.batchevaluate_into(full, self.rank * blk, I, J[lo:hi], M) if hi > lo else 0.0
         dev = torch.device("cuda", self.ctx.device)

@@ -202,6 +202,7 @@ def sweep1site(tci, f, sweepdirection="forward", reltol=1e-14, abstol=0.0, maxbo
     """sweep1site! (tensorci2.jl:402-461)."""
     flushpivoterror(tci)
     invalidatesitetensors(tci)
+    f = getattr(f, "local", f)  # the small T-tensor factorisations are replicated on every rank, not sharded
     if sweepdirection not in ("forward", "backward"):
         raise ValueError(f"Unknown sweep direction {sweepdirection}: choose between :forward, :backward.")
     fwd = sweepdirection == "forward"

@@ -27,15 +27,16 @@ def main():
     ]:
         f = T.BuiltinTarget(kind, params, ld)
         ref, rr, re = T.crossinterpolate2(f, ld, rng=T.CounterRNG(3), **kw)
-        sf = ShardedEvaluator(f, dist, torch)
-        tci, ranks, errors = T.crossinterpolate2(sf, ld, rng=T.CounterRNG(3), **kw)
-        same = ranks == rr and errors == re and all(
-            np.array_equal(a, b) for a, b in zip(tci.Iset + tci.Jset, ref.Iset + ref.Jset)) and all(
-            np.array_equal(a, b) for a, b in zip(tci.sitetensors, ref.sitetensors))
-        ok = ok and same
-        if rank == 0:
-            print(f"{name}: world={world} rank={ranks[-1]} identical_to_single_gpu={same} "
-                  f"allgather_ms={sf.gather_ms:.2f}")
+        for mode in ("peer", "allgather"):
+            sf = ShardedEvaluator(f, dist, torch, mode=mode)
+            tci, ranks, errors = T.crossinterpolate2(sf, ld, rng=T.CounterRNG(3), **kw)
+            sf.release()
+            same = ranks == rr and errors == re and all(
+                np.array_equal(a, b) for a, b in zip(tci.Iset + tci.Jset, ref.Iset + ref.Jset)) and all(
+                np.array_equal(a, b) for a, b in zip(tci.sitetensors, ref.sitetensors))
+            ok = ok and same
+            if rank == 0:
+                print(f"{name}/{mode}: world={world} rank={ranks[-1]} identical_to_single_gpu={same}")
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -539,3 +539,19 @@ def test_argument_errors(T):  # test_tensorci2.jl:215-245
     z = T.BuiltinTarget(TABLE, np.zeros(4), [2, 2])
     with pytest.raises(RuntimeError, match="maxsamplevalue is zero!"):
         T.TensorCI2(z, [2, 2])
+
+
+def test_multigpu_sharded_tci_identical_to_single_gpu():
+    """world_size 2 over NCCL / NVLink peer stores (needs >= 2 visible GPUs; the 1-GPU box skips it)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577",
+                          os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
