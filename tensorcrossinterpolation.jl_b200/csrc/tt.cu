@@ -63,6 +63,32 @@ __global__ void k_fill(double *p, i64 n, double v)
     if (e < n) p[e] = v;
 }
 
+// GEMM form of a chain step for small site dimension d: Y = T^T * prev for ALL d slices at once
+// (d x the flops of the gather form, but on the DMMA GEMM), then the slice sigma_q of point q is picked.
+// left:  Y[(sig + d*b) + d*Dr*q]  -> out[b + Dr*q]      right: Y[(a + Dl*sig) + Dl*d*q] -> out[a + Dl*q]
+__global__ void k_env_select_left(const double *__restrict__ Y, int d, int Dr, const i64 *__restrict__ idx, int len,
+                                  int pos, i64 count, double *__restrict__ out)
+{
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= (i64)Dr * count) return;
+    const int b = (int)(e % Dr);
+    const i64 q = e / Dr;
+    const i64 sig = idx[(i64)len * q + pos] - 1;
+    out[e] = Y[(sig + (i64)d * b) + (i64)d * Dr * q];
+}
+__global__ void k_env_select_right(const double *__restrict__ Y, int Dl, int d, const i64 *__restrict__ idx, int len,
+                                   int pos, i64 count, double *__restrict__ out)
+{
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= (i64)Dl * count) return;
+    const int a = (int)(e % Dl);
+    const i64 q = e / Dl;
+    const i64 sig = idx[(i64)len * q + pos] - 1;
+    out[e] = Y[(a + (i64)Dl * sig) + (i64)Dl * d * q];
+}
+
+#define TT_GEMM_MAX_D 8
+
 struct CoreView {
     const double *p;
     int Dl, d, Dr;
@@ -71,7 +97,7 @@ struct CoreView {
 // Left environment over sites [0, nsteps) of a chain; idx is (len x count), site s reads idx[s + off].
 // Result (D x count) in *out (allocated here, caller frees with dev_free).
 static int env_left_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int nsteps, const i64 *d_idx, int len,
-                          int off, i64 count, double **out, int *Dout)
+                          int off, i64 count, double **out, int *Dout, bool ordered = true)
 {
     double *prev = nullptr;
     int D = 1;
@@ -80,8 +106,18 @@ static int env_left_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int 
         double *nxt = nullptr;
         TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)c.Dr * count * sizeof(double)));
         i64 total = (i64)c.Dr * count;
-        k_env_left_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(prev, c.p, c.Dl, c.d, c.Dr, d_idx,
-                                                                                 len, s + off, count, nxt);
+        if (!ordered && prev && c.d <= TT_GEMM_MAX_D && c.Dl >= 32 && count >= 64) {
+            double *Y = nullptr;
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&Y, (size_t)c.d * c.Dr * count * sizeof(double)));
+            int rc = dgemm_dev(ctx, true, false, (i64)c.d * c.Dr, count, c.Dl, 1.0, c.p, c.Dl, prev, c.Dl, 0.0, Y,
+                               (i64)c.d * c.Dr);
+            if (rc) return rc;
+            k_env_select_left<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(Y, c.d, c.Dr, d_idx, len,
+                                                                                       s + off, count, nxt);
+            dev_free(ctx, Y);
+        } else
+            k_env_left_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(prev, c.p, c.Dl, c.d, c.Dr,
+                                                                                     d_idx, len, s + off, count, nxt);
         ctx->launches++;
         dev_free(ctx, prev);
         prev = nxt;
@@ -100,7 +136,7 @@ static int env_left_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int 
 
 // Right environment over the last nsteps sites; site s (global) reads idx[s - (N - nsteps) + off].
 static int env_right_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int nsteps, const i64 *d_idx, int len,
-                           int off, i64 count, double **out, int *Dout)
+                           int off, i64 count, double **out, int *Dout, bool ordered = true)
 {
     const int N = (int)cores.size();
     double *prev = nullptr;
@@ -110,8 +146,18 @@ static int env_right_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int
         double *nxt = nullptr;
         TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)c.Dl * count * sizeof(double)));
         i64 total = (i64)c.Dl * count;
-        k_env_right_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
-            prev, c.p, c.Dl, c.d, c.Dr, d_idx, len, s - (N - nsteps) + off, count, nxt);
+        if (!ordered && prev && c.d <= TT_GEMM_MAX_D && c.Dr >= 32 && count >= 64) {
+            double *Y = nullptr;
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&Y, (size_t)c.Dl * c.d * count * sizeof(double)));
+            int rc = dgemm_dev(ctx, false, false, (i64)c.Dl * c.d, count, c.Dr, 1.0, c.p, (i64)c.Dl * c.d, prev, c.Dr,
+                               0.0, Y, (i64)c.Dl * c.d);
+            if (rc) return rc;
+            k_env_select_right<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+                Y, c.Dl, c.d, d_idx, len, s - (N - nsteps) + off, count, nxt);
+            dev_free(ctx, Y);
+        } else
+            k_env_right_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+                prev, c.p, c.Dl, c.d, c.Dr, d_idx, len, s - (N - nsteps) + off, count, nxt);
         ctx->launches++;
         dev_free(ctx, prev);
         prev = nxt;
@@ -142,9 +188,10 @@ int pi_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const 
     std::vector<CoreView> cv = views(t);
     double *lenv = nullptr, *renv = nullptr;
     int DL = 1, DR = 1;
-    int rc = env_left_chain(ctx, cv, (int)nl, dI, (int)nl, 0, nI, &lenv, &DL);
+    // the batched Pi is a GEMM product anyway (1e-10 bar): small-d chain steps go through the GEMM as well
+    int rc = env_left_chain(ctx, cv, (int)nl, dI, (int)nl, 0, nI, &lenv, &DL, false);
     if (rc) return rc;
-    rc = env_right_chain(ctx, cv, (int)nr, dJ, (int)nr, 0, nJ, &renv, &DR);
+    rc = env_right_chain(ctx, cv, (int)nr, dJ, (int)nr, 0, nJ, &renv, &DR, false);
     if (rc) {
         dev_free(ctx, lenv);
         return rc;
