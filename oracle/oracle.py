@@ -134,6 +134,31 @@ def luci(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True):
     return out
 
 
+def arrlu(A, I0=(), J0=(), maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True, seed=1):
+    """arrlu(Float64, (i, j) -> A[i, j], size(A), I0, J0; ...) with injected random subsets."""
+    A = _f(A)
+    m, n = A.shape
+    maxrank = I64MAX if maxrank is None else int(maxrank)
+    mr = max(0, min(maxrank, m, n))
+    I0 = np.ascontiguousarray(I0, dtype=np.int64)
+    J0 = np.ascontiguousarray(J0, dtype=np.int64)
+    rowperm = np.zeros(m, dtype=np.int64)
+    colperm = np.zeros(n, dtype=np.int64)
+    npiv, err = i64(0), f64(0.0)
+    L = np.zeros(m * mr, dtype=np.float64)
+    U = np.zeros(mr * n, dtype=np.float64)
+    _check(lib().orc_arrlu(_pf(A), i64(m), i64(n), _pi(I0), i64(I0.size), _pi(J0), i64(J0.size), i64(maxrank),
+                           f64(reltol), f64(abstol), C.c_int(int(leftorthogonal)), C.c_uint64(seed), _pi(rowperm),
+                           _pi(colperm), C.byref(npiv), C.byref(err), _pf(L), _pf(U)))
+    r = npiv.value
+    out = LU()
+    out.rowpermutation, out.colpermutation, out.npivot, out.error = rowperm, colperm, r, err.value
+    out.L = L[: m * r].reshape((m, r), order="F")
+    out.U = U[: r * n].reshape((r, n), order="F")
+    out.leftorthogonal = leftorthogonal
+    return out
+
+
 def argmax_abs2(A, k=1):
     A = _f(A)
     r, c = i64(0), i64(0)
@@ -255,7 +280,7 @@ class _Options(C.Structure):
     _fields_ = [("tolerance", f64), ("maxbonddim", i64), ("maxiter", i64), ("sweepstrategy", C.c_int),
                 ("normalizeerror", C.c_int), ("ncheckhistory", i64), ("maxnglobalpivot", i64),
                 ("nsearchglobalpivot", i64), ("tolmarginglobalsearch", f64), ("strictlynested", C.c_int),
-                ("checkconvglobalpivot", C.c_int), ("seed", C.c_uint64)]
+                ("checkconvglobalpivot", C.c_int), ("seed", C.c_uint64), ("pivotsearch", C.c_int)]
 
 
 _STRATEGY = {"backandforth": 0, "forward": 1, "backward": 2}
@@ -317,7 +342,7 @@ class TCIResult:
 def crossinterpolate2(target, localdims, initialpivots=None, tolerance=1e-8, maxbonddim=None, maxiter=20,
                       sweepstrategy="backandforth", normalizeerror=True, ncheckhistory=3, maxnglobalpivot=5,
                       nsearchglobalpivot=5, tolmarginglobalsearch=10.0, strictlynested=False,
-                      checkconvglobalpivot=True, seed=1):
+                      checkconvglobalpivot=True, seed=1, pivotsearch="full"):
     ld = np.ascontiguousarray(localdims, dtype=np.int64)
     n = ld.size
     if initialpivots is None:
@@ -325,7 +350,7 @@ def crossinterpolate2(target, localdims, initialpivots=None, tolerance=1e-8, max
     pv = _flat_idx(initialpivots, n)
     o = _Options(tolerance, I64MAX if maxbonddim is None else int(maxbonddim), maxiter, _STRATEGY[sweepstrategy],
                  int(normalizeerror), ncheckhistory, maxnglobalpivot, nsearchglobalpivot, tolmarginglobalsearch,
-                 int(strictlynested), int(checkconvglobalpivot), seed)
+                 int(strictlynested), int(checkconvglobalpivot), seed, {"full": 0, "rook": 1}[pivotsearch])
     st = C.c_int(0)
     h = lib().orc_crossinterpolate2(target.h, _pi(ld), i64(n), _pi(pv), i64(pv.shape[1]), C.byref(o), C.byref(st))
     if st.value != 0:

@@ -223,6 +223,143 @@ static void luci_right(const RRLU &lu, std::vector<double> &out)
         for (i64 i = 0; i < r; ++i) out[i + (lu.colperm[c] - 1) * r] = res[i + c * r];
 }
 
+// ------------------------------------------------------------ rook search ---
+// Injected replacement of Julia's rand(1:len) in randomsubset (util.jl:36-52): counter based.
+struct RookRng {
+    uint64_t seed = 0, counter = 0;
+    i64 draw(i64 len)
+    {
+        i64 v = 1 + (i64)(tci_uniform01(seed ^ 0x726f6f6bull, counter++) * (double)len);
+        return v > len ? len : v;
+    }
+};
+
+// pushrandomsubset!(subset, 1:N, cnt)  util.jl:54-58
+static void pushrandomsubset(std::vector<i64> &subset, i64 N, i64 cnt, RookRng &rng)
+{
+    std::vector<i64> c;
+    for (i64 v = 1; v <= N; ++v)
+        if (std::find(subset.begin(), subset.end(), v) == subset.end()) c.push_back(v);
+    i64 nn = std::min<i64>(cnt, (i64)c.size());
+    for (i64 q = 0; q < nn; ++q) {
+        i64 index = rng.draw((i64)c.size());
+        subset.push_back(c[index - 1]);
+        c.erase(c.begin() + (index - 1));
+    }
+}
+
+// cols2Lmatrix! / rows2Umatrix!  matrixlu.jl:314-358 (C: rows x r, R: r x cols, P: r x r, column-major)
+static void cols2Lmatrix(std::vector<double> &C, i64 rows, const std::vector<double> &P, i64 r)
+{
+    for (i64 k = 0; k < r; ++k) {
+        for (i64 i = 0; i < rows; ++i) C[i + k * rows] /= P[k + k * r];
+        for (i64 j = k + 1; j < r; ++j) {
+            double y = P[k + j * r];
+            for (i64 i = 0; i < rows; ++i) C[i + j * rows] -= C[i + k * rows] * y;
+        }
+    }
+}
+static void rows2Umatrix(std::vector<double> &R, i64 cols, const std::vector<double> &P, i64 r)
+{
+    for (i64 k = 0; k < r; ++k) {
+        for (i64 j = 0; j < cols; ++j) R[k + j * r] /= P[k + k * r];
+        for (i64 j = 0; j < cols; ++j) {
+            double y = R[k + j * r];
+            for (i64 i = k + 1; i < r; ++i) R[i + j * r] -= P[i + k * r] * y;
+        }
+    }
+}
+
+// f(rows, cols) -> |rows| x |cols| matrix (1-based indices), the `_batchf` of matrixlu.jl:243
+typedef void (*MatEval)(void *user, const std::vector<i64> &rows, const std::vector<i64> &cols,
+                        std::vector<double> &out);
+
+// arrlu  matrixlu.jl:227-293
+static int arrlu(RRLU &lu, MatEval f, void *user, i64 m, i64 n, std::vector<i64> I0, std::vector<i64> J0, i64 maxrank,
+                 double reltol, double abstol, bool leftorth, int numrookiter, RookRng &rng)
+{
+    lu = RRLU();
+    lu.leftorthogonal = leftorth;
+    lu.rowperm.resize(m);
+    lu.colperm.resize(n);
+    for (i64 i = 0; i < m; ++i) lu.rowperm[i] = i + 1;
+    for (i64 j = 0; j < n; ++j) lu.colperm[j] = j + 1;
+    bool islowrank = false;
+    maxrank = std::min(maxrank, std::min(m, n));
+    i64 Lrows = m, Ucols = n; // shape of the last factorised submatrix
+    std::vector<double> sub;
+    while (true) {
+        if (leftorth)
+            pushrandomsubset(J0, n, std::max<i64>(1, (i64)J0.size()), rng);
+        else
+            pushrandomsubset(I0, m, std::max<i64>(1, (i64)I0.size()), rng);
+        for (int rookiter = 1; rookiter <= numrookiter; ++rookiter) {
+            bool colmove = ((rookiter % 2 == 0) == leftorth);
+            if (colmove)
+                f(user, I0, lu.colperm, sub);
+            else
+                f(user, lu.rowperm, J0, sub);
+            i64 sr = colmove ? (i64)I0.size() : m, sc = colmove ? n : (i64)J0.size();
+            lu.npivot = 0;
+            lu.m = sr;
+            lu.n = sc;
+            int rc = optimizerrlu(lu, sub.data(), sr, sc, maxrank, reltol, abstol);
+            if (rc) return rc;
+            Lrows = sr;
+            Ucols = sc;
+            islowrank = islowrank || lu.npivot < std::min(sr, sc);
+            std::vector<i64> ri(lu.rowperm.begin(), lu.rowperm.begin() + lu.npivot);
+            std::vector<i64> ci(lu.colperm.begin(), lu.colperm.begin() + lu.npivot);
+            if (ri == I0 && ci == J0) break;
+            J0 = ci;
+            I0 = ri;
+        }
+        if (islowrank || (i64)I0.size() >= maxrank) break;
+    }
+    const i64 r = lu.npivot;
+    std::vector<double> L11((size_t)(r * r)), U11((size_t)(r * r));
+    for (i64 c = 0; c < r; ++c)
+        for (i64 i = 0; i < r; ++i) {
+            L11[i + c * r] = lu.L[i + c * Lrows];
+            U11[i + c * r] = lu.U[i + c * r];
+        }
+    if (Lrows < m) { // :274-280
+        std::vector<i64> I2;
+        for (i64 v = 1; v <= m; ++v)
+            if (std::find(I0.begin(), I0.end(), v) == I0.end()) I2.push_back(v);
+        lu.rowperm = I0;
+        lu.rowperm.insert(lu.rowperm.end(), I2.begin(), I2.end());
+        std::vector<double> L2;
+        if (!I2.empty() && !J0.empty()) f(user, I2, J0, L2);
+        cols2Lmatrix(L2, (i64)I2.size(), U11, r);
+        std::vector<double> L((size_t)(m * r));
+        for (i64 c = 0; c < r; ++c) {
+            for (i64 i = 0; i < r; ++i) L[i + c * m] = L11[i + c * r];
+            for (i64 i = 0; i < (i64)I2.size(); ++i) L[r + i + c * m] = L2[i + c * (i64)I2.size()];
+        }
+        lu.L = L;
+    }
+    if (Ucols < n) { // :282-288
+        std::vector<i64> J2;
+        for (i64 v = 1; v <= n; ++v)
+            if (std::find(J0.begin(), J0.end(), v) == J0.end()) J2.push_back(v);
+        lu.colperm = J0;
+        lu.colperm.insert(lu.colperm.end(), J2.begin(), J2.end());
+        std::vector<double> U2;
+        if (!J2.empty() && !I0.empty()) f(user, I0, J2, U2);
+        rows2Umatrix(U2, (i64)J2.size(), L11, r);
+        std::vector<double> U((size_t)(r * n));
+        for (i64 c = 0; c < r; ++c)
+            for (i64 i = 0; i < r; ++i) U[i + c * r] = U11[i + c * r];
+        for (i64 c = 0; c < (i64)J2.size(); ++c)
+            for (i64 i = 0; i < r; ++i) U[i + (r + c) * r] = U2[i + c * r];
+        lu.U = U;
+    }
+    lu.m = m;
+    lu.n = n;
+    return 0;
+}
+
 // ============================================================ targets ======
 struct TT3 { // TensorTrain{Float64,3}: cores (Dl, d, Dr) column-major
     std::vector<std::vector<double>> cores;
@@ -620,6 +757,7 @@ struct TCI2 { // tensorci2.jl:6-40
     std::vector<double> errors; // already divided by the normalisation
     // trace of every 2-site bond update, for bond-by-bond parity checks
     std::vector<i64> trace; // (iter, bond, m, n, npivot) quintuples
+    RookRng rook;           // injected random subsets of the rook search
 };
 
 static void pushunique(IndexList &c, const MultiIndex &x)
@@ -694,19 +832,57 @@ static void updateerrors(TCI2 &tci, i64 b, const std::vector<double> &e)
     tci.pivoterrors = out;
 }
 
-// tensorci2.jl:510-607, pivotsearch = :full
+// SubMatrix (tensorci2.jl:476-503): lazily evaluated Pi with a running max |value|
+struct SubMatrixCtx {
+    Target *f;
+    const IndexList *rows, *cols;
+    double maxsamplevalue = 0.0;
+};
+static void submatrix_eval(void *user, const std::vector<i64> &ir, const std::vector<i64> &ic, std::vector<double> &out)
+{
+    SubMatrixCtx *c = static_cast<SubMatrixCtx *>(user);
+    IndexList I, J;
+    for (i64 i : ir) I.push_back((*c->rows)[i - 1]);
+    for (i64 j : ic) J.push_back((*c->cols)[j - 1]);
+    filltensor(*c->f, I, J, 0, out);
+    double mx = -INFINITY; // maximum(abs, res)
+    for (double v : out) mx = jl_max(mx, std::fabs(v));
+    if (!out.empty()) c->maxsamplevalue = jl_max(c->maxsamplevalue, mx);
+}
+
+// tensorci2.jl:510-607 ; pivotsearch 0 = :full, 1 = :rook
 static int updatepivots(TCI2 &tci, Target &f, i64 b, bool leftorth, double reltol, double abstol, i64 maxbonddim,
-                        const IndexList &extraI, const IndexList &extraJ, i64 iter)
+                        const IndexList &extraI, const IndexList &extraJ, i64 iter, int pivotsearch = 0)
 {
     for (auto &T : tci.sitetensors) T.clear();
     IndexList Ic = union_lists(kron_left(tci.Iset[b], tci.localdims[b]), extraI);
     IndexList Jc = union_lists(kron_right(tci.localdims[b + 1], tci.Jset[b + 1]), extraJ);
-    std::vector<double> Pi;
-    filltensor(f, Ic, Jc, 0, Pi);
-    updatemaxsample(tci, Pi);
     RRLU lu;
-    int rc = rrlu(lu, Pi.data(), (i64)Ic.size(), (i64)Jc.size(), maxbonddim, reltol, abstol, leftorth);
-    if (rc) return rc;
+    bool need_full = true;
+    if (pivotsearch == 1) { // :552-595
+        std::vector<i64> I0, J0;
+        for (const MultiIndex &x : tci.Iset[b + 1]) {
+            auto it = std::find(Ic.begin(), Ic.end(), x);
+            if (it != Ic.end()) I0.push_back((i64)(it - Ic.begin()) + 1);
+        }
+        for (const MultiIndex &x : tci.Jset[b]) {
+            auto it = std::find(Jc.begin(), Jc.end(), x);
+            if (it != Jc.end()) J0.push_back((i64)(it - Jc.begin()) + 1);
+        }
+        SubMatrixCtx sm{&f, &Ic, &Jc};
+        int rc = arrlu(lu, submatrix_eval, &sm, (i64)Ic.size(), (i64)Jc.size(), I0, J0, maxbonddim, reltol, abstol,
+                       leftorth, 5, tci.rook);
+        if (rc) return rc;
+        tci.maxsamplevalue = jl_max(std::fabs(tci.maxsamplevalue), std::fabs(sm.maxsamplevalue)); // :569
+        need_full = lu.npivot == 0; // fall back to the full search if the rook search fails (:573-588)
+    }
+    if (need_full) {
+        std::vector<double> Pi;
+        filltensor(f, Ic, Jc, 0, Pi);
+        updatemaxsample(tci, Pi);
+        int rc = rrlu(lu, Pi.data(), (i64)Ic.size(), (i64)Jc.size(), maxbonddim, reltol, abstol, leftorth);
+        if (rc) return rc;
+    }
     IndexList In, Jn;
     for (i64 k = 0; k < lu.npivot; ++k) In.push_back(Ic[lu.rowperm[k] - 1]);
     for (i64 k = 0; k < lu.npivot; ++k) Jn.push_back(Jc[lu.colperm[k] - 1]);
@@ -800,7 +976,7 @@ static bool forwardsweep(int strategy, i64 iter) { return strategy == 1 || (stra
 
 // tensorci2.jl:855-916
 static int sweep2site(TCI2 &tci, Target &f, i64 niter, i64 iter1, double abstol, i64 maxbonddim, int strategy,
-                      bool strictlynested, i64 outer_iter)
+                      bool strictlynested, i64 outer_iter, int pivotsearch = 0)
 {
     for (auto &T : tci.sitetensors) T.clear();
     i64 n = tci.n;
@@ -817,13 +993,13 @@ static int sweep2site(TCI2 &tci, Target &f, i64 niter, i64 iter1, double abstol,
         if (forwardsweep(strategy, iter)) {
             for (i64 b = 0; b < n - 1; ++b) {
                 int rc = updatepivots(tci, f, b, true, 1e-14, abstol, maxbonddim, extraI[b + 1], extraJ[b],
-                                      outer_iter * 100 + iter);
+                                      outer_iter * 100 + iter, pivotsearch);
                 if (rc) return rc;
             }
         } else {
             for (i64 b = n - 2; b >= 0; --b) {
                 int rc = updatepivots(tci, f, b, false, 1e-14, abstol, maxbonddim, extraI[b + 1], extraJ[b],
-                                      outer_iter * 100 + iter);
+                                      outer_iter * 100 + iter, pivotsearch);
                 if (rc) return rc;
             }
         }
@@ -957,6 +1133,7 @@ struct Options { // tensorci2.jl:700-720
     int strictlynested = 0;
     int checkconvglobalpivot = 1;
     uint64_t seed = 1;
+    int pivotsearch = 0; // 0 :full, 1 :rook
 };
 
 // tensorci2.jl:42-53 + 700-850
@@ -977,6 +1154,7 @@ static int crossinterpolate2(TCI2 &tci, Target &f, const std::vector<i64> &local
     tci.tdl.assign(n, 0);
     tci.tdr.assign(n, 0);
     tci.bonderrors.assign(n - 1, 0.0);
+    tci.rook.seed = o.seed;
     addglobalpivots(tci, initialpivots);
     double ms = 0.0;
     for (const MultiIndex &p : initialpivots) ms = jl_max(ms, std::fabs(target_eval(f, p.data())));
@@ -998,7 +1176,8 @@ static int crossinterpolate2(TCI2 &tci, Target &f, const std::vector<i64> &local
     for (i64 iter = 1; iter <= o.maxiter; ++iter) {
         double norm = o.normalizeerror ? tci.maxsamplevalue : 1.0;
         double abstol = o.tolerance * norm;
-        int rc = sweep2site(tci, f, 2, 1, abstol, o.maxbonddim, o.sweepstrategy, o.strictlynested != 0, iter);
+        int rc = sweep2site(tci, f, 2, 1, abstol, o.maxbonddim, o.sweepstrategy, o.strictlynested != 0, iter,
+                            o.pivotsearch);
         if (rc) return rc;
         double pe = -INFINITY;
         for (double e : tci.bonderrors) pe = jl_max(pe, e);
@@ -1087,6 +1266,36 @@ int orc_luci(const double *A, i64 m, i64 n, i64 maxrank, double reltol, double a
         luci_right(lu, r);
         std::copy(r.begin(), r.end(), right);
     }
+    return 0;
+}
+
+static void dense_eval(void *user, const std::vector<i64> &ir, const std::vector<i64> &ic, std::vector<double> &out)
+{
+    const double *A = static_cast<const double *const *>(user)[0];
+    i64 m = (i64)(intptr_t) static_cast<const double *const *>(user)[1];
+    out.resize(ir.size() * ic.size());
+    for (size_t j = 0; j < ic.size(); ++j)
+        for (size_t i = 0; i < ir.size(); ++i) out[i + j * ir.size()] = A[(ir[i] - 1) + (ic[j] - 1) * m];
+}
+
+// arrlu on a dense matrix (test_matrixlu.jl:71-86); I0/J0 1-based, nI0/nJ0 may be 0
+int orc_arrlu(const double *A, i64 m, i64 n, const i64 *I0, i64 nI0, const i64 *J0, i64 nJ0, i64 maxrank, double reltol,
+              double abstol, int leftorthogonal, uint64_t seed, i64 *rowperm, i64 *colperm, i64 *npivot, double *error,
+              double *L, double *U)
+{
+    RRLU lu;
+    RookRng rng;
+    rng.seed = seed;
+    const void *user[2] = {A, (const void *)(intptr_t)m};
+    int rc = arrlu(lu, dense_eval, (void *)user, m, n, std::vector<i64>(I0, I0 + nI0), std::vector<i64>(J0, J0 + nJ0),
+                   maxrank, reltol, abstol, leftorthogonal != 0, 5, rng);
+    if (rc) return rc;
+    std::copy(lu.rowperm.begin(), lu.rowperm.end(), rowperm);
+    std::copy(lu.colperm.begin(), lu.colperm.end(), colperm);
+    *npivot = lu.npivot;
+    *error = lu.error;
+    if (L) std::copy(lu.L.begin(), lu.L.end(), L);
+    if (U) std::copy(lu.U.begin(), lu.U.end(), U);
     return 0;
 }
 
@@ -1242,6 +1451,7 @@ struct orc_options {
     int strictlynested;
     int checkconvglobalpivot;
     uint64_t seed;
+    int pivotsearch;
 };
 
 TCI2 *orc_crossinterpolate2(Target *f, const i64 *localdims, i64 n, const i64 *pivots, i64 npivots,
@@ -1260,6 +1470,7 @@ TCI2 *orc_crossinterpolate2(Target *f, const i64 *localdims, i64 n, const i64 *p
     o.strictlynested = opt->strictlynested;
     o.checkconvglobalpivot = opt->checkconvglobalpivot;
     o.seed = opt->seed;
+    o.pivotsearch = opt->pivotsearch;
     TCI2 *tci = new TCI2();
     *status = crossinterpolate2(*tci, *f, std::vector<i64>(localdims, localdims + n), unflatten(pivots, n, npivots),
                                 o);

@@ -11,7 +11,7 @@ from .contraction import (Contraction, _contractsitetensors, _factorize, contrac
                           contract_TCI, contract_zipup)
 from .globalpivotfinder import (AbstractGlobalPivotFinder, DefaultGlobalPivotFinder,  # noqa: F401
                                 GlobalPivotSearchInput)
-from .matrixlu import (MatrixLUCI, colindices, lastpivoterror, left, npivots, pivoterrors, right,  # noqa: F401
+from .matrixlu import (MatrixLUCI, RookLU, arrlu, colindices, lastpivoterror, left, npivots, pivoterrors, right,  # noqa: F401
                        rowindices, rrLU, rrlu, size)
 from .tensorci2 import (TensorCI2, addglobalpivots, convergencecriterion, crossinterpolate2, evaluate,  # noqa: F401
                         fillsitetensors, filltensor, linkdims, optimize, pivoterror, rank, sweep1site, sweep2site,

@@ -185,3 +185,99 @@ class MatrixLUCI:
         out = np.zeros((r, n), dtype=np.float64, order="F")
         self.lu.ctx.check(lib().tci_luci_right(self.lu._h, pf(out), None))
         return out
+
+
+class RookLU:
+    """rrLU produced by the rook search arrlu (matrixlu.jl:227-293).  Permutations, npivot, error and
+    pivoterrors are available immediately; L and U (which need the remaining rows / columns of the
+    matrix, matrixlu.jl:274-288) are completed lazily on first access."""
+
+    def __init__(self, last, rowperm, colperm, I0, J0, fsub, shape, leftorthogonal):
+        self._last, self._fsub = last, fsub
+        self.rowpermutation, self.colpermutation = rowperm, colperm
+        self._I0, self._J0 = I0, J0
+        self.npivot, self.error = last.npivot, last.error
+        self._pivoterrors = last._pivoterrors
+        self.leftorthogonal = leftorthogonal
+        self._shape = shape
+        self._L = self._U = None
+
+    def _complete(self):
+        m, n = self._shape
+        r = self.npivot
+        L, U = self._last.L, self._last.U
+        L11, U11 = L[:r, :r], U[:r, :r]
+        if L.shape[0] < m:
+            I2 = self.rowpermutation[r:]
+            A21 = self._fsub(I2, np.asarray(self._J0, dtype=np.int64), device=False) if len(I2) and r else \
+                np.zeros((len(I2), r))
+            L2 = np.linalg.solve(U11.T, A21.T).T if r else A21  # cols2Lmatrix!: A21 * U11^-1
+            L = np.vstack([L11, L2])
+        if U.shape[1] < n:
+            J2 = self.colpermutation[r:]
+            A12 = self._fsub(np.asarray(self._I0, dtype=np.int64), J2, device=False) if len(J2) and r else \
+                np.zeros((r, len(J2)))
+            U2 = np.linalg.solve(L11, A12) if r else A12  # rows2Umatrix!: L11^-1 * A12
+            U = np.hstack([U11, U2])
+        self._L, self._U = np.asfortranarray(L), np.asfortranarray(U)
+
+    @property
+    def L(self):
+        if self._L is None:
+            self._complete()
+        return self._L
+
+    @property
+    def U(self):
+        if self._U is None:
+            self._complete()
+        return self._U
+
+
+def arrlu(fsub, matrixsize, I0=(), J0=(), maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True,
+          numrookiter=5, rng=None):
+    """arrlu(ValueType, f, matrixsize, I0, J0; ...) (matrixlu.jl:227-293): rook pivot search that only ever
+    evaluates whole rows / columns of the matrix.  `fsub(irows, icols, device=True)` returns the submatrix
+    (1-based index arrays) as a DeviceMatrix -- each rook move is one evaluation kernel plus one rrLU kernel.
+    The random subsets are drawn from `rng.randindex` (injected, shared with the oracle)."""
+    from .util import CounterRNG, pushrandomsubset
+    rng = rng or CounterRNG(1)
+    m, n = matrixsize
+    I0, J0 = [int(x) for x in I0], [int(x) for x in J0]
+    rowperm = np.arange(1, m + 1, dtype=np.int64)
+    colperm = np.arange(1, n + 1, dtype=np.int64)
+    islowrank = False
+    maxrank = min(m, n) if maxrank is None else min(int(maxrank), m, n)
+    last = None
+    while True:
+        if leftorthogonal:
+            pushrandomsubset(J0, n, max(1, len(J0)), rng)
+        else:
+            pushrandomsubset(I0, m, max(1, len(I0)), rng)
+        for rookiter in range(1, numrookiter + 1):
+            colmove = (rookiter % 2 == 0) == leftorthogonal
+            if colmove:
+                sub = fsub(np.asarray(I0, dtype=np.int64), colperm, device=True)
+            else:
+                sub = fsub(rowperm, np.asarray(J0, dtype=np.int64), device=True)
+            sr, sc = (len(I0), n) if colmove else (m, len(J0))
+            last = rrlu(sub, maxrank=maxrank, reltol=reltol, abstol=abstol, leftorthogonal=leftorthogonal)
+            pr, pc = last.rowpermutation - 1, last.colpermutation - 1
+            # _optimizerrlu! keeps permuting lu.rowpermutation / lu.colpermutation in place (their prefixes)
+            rowperm[:sr] = rowperm[:sr][pr]
+            colperm[:sc] = colperm[:sc][pc]
+            islowrank = islowrank or last.npivot < min(sr, sc)
+            ri, ci = rowperm[: last.npivot].tolist(), colperm[: last.npivot].tolist()
+            if ri == I0 and ci == J0:
+                break
+            J0, I0 = ci, ri
+        if islowrank or len(I0) >= maxrank:
+            break
+    r = last.npivot
+    if last._shape[0] < m:  # lu.rowpermutation = vcat(I0, setdiff(1:m, I0))
+        have = set(I0)
+        rowperm = np.array(I0 + [v for v in range(1, m + 1) if v not in have], dtype=np.int64)
+    if last._shape[1] < n:
+        have = set(J0)
+        colperm = np.array(J0 + [v for v in range(1, n + 1) if v not in have], dtype=np.int64)
+    return RookLU(last, rowperm, colperm, I0, J0, fsub, (m, n), leftorthogonal)

@@ -239,8 +239,37 @@ def sweep1site(tci, f, sweepdirection="forward", reltol=1e-14, abstol=0.0, maxbo
             (tci.Iset[last].shape[0], tci.localdims[last], tci.Jset[last].shape[0]), order="F")
 
 
+class SubMatrix:
+    """mutable struct SubMatrix (tensorci2.jl:476-503): Pi evaluated lazily on row / column subsets,
+    with the running max |value| the rook branch feeds into maxsamplevalue (:569)."""
+
+    def __init__(self, f, rows, cols):
+        self.f, self.rows, self.cols = f, rows, cols
+        self.maxsamplevalue = 0.0
+
+    def __call__(self, irows, icols, device=True):
+        I = np.ascontiguousarray(self.rows[np.asarray(irows) - 1])
+        J = np.ascontiguousarray(self.cols[np.asarray(icols) - 1])
+        host, dev, mx = self.f._pi(I, J, 0, not device, device)
+        self.maxsamplevalue = jl_max(self.maxsamplevalue, mx)
+        return dev if device else host.reshape((len(I), len(J)), order="F")
+
+
+def _positions(subset, combined):
+    """[findfirst(isequal(i), combined) for i in subset], dropping the ones that are absent (:554-555)."""
+    from .util import _rowkeys
+    if subset.shape[0] == 0 or combined.shape[0] == 0 or subset.shape[1] != combined.shape[1]:
+        return []
+    if combined.shape[1] == 0:
+        return [1] * subset.shape[0]
+    where = {}
+    for i, k in enumerate(_rowkeys(combined)):
+        where.setdefault(k, i + 1)
+    return [where[k] for k in _rowkeys(subset) if k in where]
+
+
 def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim=I64MAX, sweepdirection="forward",
-                 pivotsearch="full", verbosity=0, extraIset=None, extraJset=None, set_sitetensors=False):
+                 pivotsearch="full", verbosity=0, extraIset=None, extraJset=None, set_sitetensors=False, rng=None):
     """updatepivots! (tensorci2.jl:510-607), pivotsearch = :full.  b is 0-based here."""
     invalidatesitetensors(tci)
     n = len(tci)
@@ -250,25 +279,35 @@ def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim
         extraJset = np.zeros((0, n - 1 - b), dtype=np.int64)
     Icombined = union(kronecker_left(tci.Iset[b], tci.localdims[b]), extraIset)
     Jcombined = union(kronecker_right(tci.localdims[b + 1], tci.Jset[b + 1]), extraJset)
-    if pivotsearch != "full":
-        if pivotsearch == "rook":
-            raise NotImplementedError("pivotsearch=:rook is listed as next in SURVEY 8(f); use :full")
+    if pivotsearch not in ("full", "rook"):
         raise ValueError(f"Unknown pivot search strategy {pivotsearch}. Choose from :rook, :full.")
-    t1 = time.perf_counter()
-    Pi, mx = filltensor(f, tci.localdims, Icombined, Jcombined, 0, device=True)
-    t2 = time.perf_counter()
-    updatemaxsample(tci, mx)
     world = getattr(f, "world", 1)
-    luci = None
-    if world == 1 or f.rank == f.owner:  # the per-bond rrLU stays on one GPU
-        luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
-                          leftorthogonal=leftorthogonal)
-        res = PivotResult(luci.npivot, rowindices(luci), colindices(luci), pivoterrors(luci))
-    else:
-        res = None
-        del Pi
-    if world > 1:
-        res = broadcast_pivots(f.dist, res, f.owner, f.group)
+    luci = res = None
+    t1 = time.perf_counter()
+    if pivotsearch == "rook":  # :552-595 (replicated on every rank: only rows / columns are evaluated)
+        from .matrixlu import arrlu
+        g = getattr(f, "local", f)
+        I0 = _positions(tci.Iset[b + 1], Icombined)
+        J0 = _positions(tci.Jset[b], Jcombined)
+        Pif = SubMatrix(g, Icombined, Jcombined)
+        lu = arrlu(Pif, (len(Icombined), len(Jcombined)), I0, J0, reltol=reltol, abstol=abstol,
+                   maxrank=min(maxbonddim, I64MAX), leftorthogonal=leftorthogonal, rng=rng)
+        updatemaxsample(tci, Pif.maxsamplevalue)
+        if lu.npivot > 0:
+            res = PivotResult(lu.npivot, rowindices(lu), colindices(lu), pivoterrors(lu))
+    t2 = time.perf_counter()
+    if res is None:  # :full, or the fall back of :573-588
+        Pi, mx = filltensor(f, tci.localdims, Icombined, Jcombined, 0, device=True)
+        t2 = time.perf_counter()
+        updatemaxsample(tci, mx)
+        if world == 1 or f.rank == f.owner:  # the per-bond rrLU stays on one GPU
+            luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
+                              leftorthogonal=leftorthogonal)
+            res = PivotResult(luci.npivot, rowindices(luci), colindices(luci), pivoterrors(luci))
+        else:
+            del Pi
+        if world > 1:
+            res = broadcast_pivots(f.dist, res, f.owner, f.group)
     t3 = time.perf_counter()
     if verbosity > 2:
         print(f"    Computing Pi ({len(Icombined)} x {len(Jcombined)}) at bond {b + 1}: {t2 - t1} sec, "
@@ -296,7 +335,7 @@ def convergencecriterion(ranks, errors, nglobalpivots, tolerance, maxbonddim, nc
 
 
 def sweep2site(tci, f, niter, iter1=1, abstol=1e-8, maxbonddim=I64MAX, sweepstrategy="backandforth",
-               pivotsearch="full", verbosity=0, strictlynested=False, fillsitetensors_=True):
+               pivotsearch="full", verbosity=0, strictlynested=False, fillsitetensors_=True, rng=None):
     """sweep2site! (tensorci2.jl:855-916)."""
     invalidatesitetensors(tci)
     n = len(tci)
@@ -316,7 +355,7 @@ def sweep2site(tci, f, niter, iter1=1, abstol=1e-8, maxbonddim=I64MAX, sweepstra
         for b in (range(n - 1) if fwd else range(n - 2, -1, -1)):
             updatepivots(tci, b, f, fwd, abstol=abstol, maxbonddim=maxbonddim,
                          sweepdirection="forward" if fwd else "backward", pivotsearch=pivotsearch,
-                         verbosity=verbosity, extraIset=extraI[b + 1], extraJset=extraJ[b])
+                         verbosity=verbosity, extraIset=extraI[b + 1], extraJset=extraJ[b], rng=rng)
     if fillsitetensors_:
         fillsitetensors(tci, f)
 
@@ -360,7 +399,7 @@ def optimize(tci, f, tolerance=None, pivottolerance=None, maxbonddim=I64MAX, max
             print(f"  Walltime {time.perf_counter() - tstart} sec: starting 2site sweep", flush=True)
         sweep2site(tci, f, 2, iter1=1, abstol=abstol, maxbonddim=maxbonddim, pivotsearch=pivotsearch,
                    strictlynested=strictlynested, verbosity=verbosity, sweepstrategy=sweepstrategy,
-                   fillsitetensors_=True)
+                   fillsitetensors_=True, rng=rng)
         errors.append(pivoterror(tci))
         if verbosity > 1:
             print(f"  Walltime {time.perf_counter() - tstart} sec: start searching global pivots", flush=True)

@@ -87,6 +87,15 @@ def uniform01(seed, index):  # tci_uniform01 of include/tci_targets.h
     return (h >> 11) * (1.0 / 9007199254740992.0)
 
 
+def pushrandomsubset(subset, N, cnt, rng):
+    """pushrandomsubset!(subset, 1:N, cnt) (util.jl:36-58); subset is a list of 1-based ints."""
+    have = set(subset)
+    c = [v for v in range(1, N + 1) if v not in have]
+    for _ in range(min(cnt, len(c))):
+        index = rng.randindex(len(c))
+        subset.append(c.pop(index - 1))
+
+
 class CounterRNG:
     """Injected replacement for `rng` in the global pivot finder (globalpivotfinder.jl:156): the
     reference draws start points from Julia's Xoshiro, which cannot be reproduced here, so the
@@ -95,6 +104,13 @@ class CounterRNG:
     def __init__(self, seed=1):
         self.seed = int(seed)
         self.calls = 0
+        self.rook_draws = 0
+
+    def randindex(self, length):
+        """rand(1:length) of randomsubset (util.jl:47), shared with the oracle's RookRng."""
+        v = 1 + int(uniform01(self.seed ^ 0x726F6F6B, self.rook_draws) * float(length))
+        self.rook_draws += 1
+        return min(v, int(length))
 
     def start_points(self, nsearch, localdims):
         self.calls += 1

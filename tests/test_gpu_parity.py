@@ -310,6 +310,33 @@ def test_rrlu_device_input_from_pi_eval(T, oracle):
     assert np.array_equal(T.pivoterrors(luci), ref.pivoterrors)
 
 
+# ------------------------------------------------------------ rook search ---
+@pytest.mark.parametrize("leftorth", [True, False])
+def test_arrlu_matches_oracle(T, oracle, leftorth):  # test_matrixlu.jl:71-86 + matrixlu.jl:227-293
+    ctx = T.default_context()
+    cases = [(G.RRLU_4x4, [1], [1], {}), (lowrank_matrix(60, 45, 5, seed=1, decay=8.0), [3], [7], {"reltol": 1e-10}),
+             (lowrank_matrix(200, 300, 12, seed=2, decay=20.0), [5, 9], [1, 2, 3], {"reltol": 1e-9, "maxrank": 10})]
+    for A, I0, J0, kw in cases:
+        A = np.asfortranarray(A)
+
+        def fsub(ir, ic, device=True):
+            blk = np.asfortranarray(A[np.ix_(np.asarray(ir) - 1, np.asarray(ic) - 1)])
+            return T.DeviceMatrix.from_host(ctx, blk) if device else blk
+
+        lu = T.arrlu(fsub, A.shape, I0, J0, leftorthogonal=leftorth, rng=T.CounterRNG(4), **kw)
+        ref = oracle.arrlu(A, I0, J0, leftorthogonal=leftorth, seed=4, **kw)
+        assert lu.npivot == ref.npivot
+        assert np.array_equal(lu.rowpermutation, ref.rowpermutation)
+        assert np.array_equal(lu.colpermutation, ref.colpermutation)
+        assert lu.error == ref.error
+        # the completed rows / columns go through a triangular solve with the (ill-conditioned) pivot block
+        np.testing.assert_allclose(lu.L, ref.L, rtol=1e-8, atol=1e-10 * np.max(np.abs(ref.L)))
+        np.testing.assert_allclose(lu.U, ref.U, rtol=1e-8, atol=1e-10 * np.max(np.abs(ref.U)))
+        if A.shape == (4, 4):
+            assert np.all(lu.L == np.tril(lu.L)) and np.all(lu.U == np.triu(lu.U))
+            np.testing.assert_allclose(T.left(lu) @ T.right(lu), A, rtol=1.5e-8)
+
+
 # ------------------------------------------------------------------ K3 ------
 @pytest.mark.parametrize("leftorth", [True, False])
 @pytest.mark.parametrize("m,n,r", [(8, 6, 4), (40, 70, 33), (300, 200, 64), (129, 515, 100), (700, 90, 90)])
@@ -509,6 +536,23 @@ def test_crossinterpolate2_sepcos_matches_oracle(T, oracle):  # config 4 family,
     tci, ranks, errors = T.crossinterpolate2(f, ld, **kw, rng=T.CounterRNG(4))
     res = oracle.crossinterpolate2(o, ld, seed=4, **kw)
     compare_tci(tci, ranks, errors, res, T)
+
+
+@pytest.mark.parametrize("name", ["lorentz", "quantics2d"])
+def test_crossinterpolate2_rook_matches_oracle(T, oracle, name):  # test_tensorci2.jl:247-340 with pivotsearch=:rook
+    if name == "lorentz":
+        ld, kw = [10] * 5, dict(tolerance=1e-10, maxiter=30)
+        f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
+    else:
+        ld, kw = [4] * 8, dict(tolerance=1e-9, maxbonddim=40, maxiter=6)
+        f, o = make_target(T, oracle, Q2D, [0, 8], ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, pivotsearch="rook", rng=T.CounterRNG(5), **kw)
+    res = oracle.crossinterpolate2(o, ld, pivotsearch="rook", seed=5, **kw)
+    compare_tci(tci, ranks, errors, res, T)
+    if name == "lorentz":
+        for v in itertools.product(range(1, 4), repeat=5):
+            fv = 1.0 / (1.0 + sum(x * x for x in v))
+            assert abs(tci(list(v)) - fv) <= 1e-8 * fv
 
 
 def test_crossinterpolate2_ttcache(T, oracle):  # test_tensorci2.jl:477-502
