@@ -7,7 +7,7 @@ from ._lib import Context, DeviceMatrix, TCIError, default_context, lib  # noqa:
 from .batcheval import (GKCOSEXP, LORENTZ, QUANTICS1D, QUANTICS2D, SEPCOS, SUM, TABLE, BatchEvaluator,  # noqa: F401
                         BuiltinTarget, makebatchevaluatable)
 from .cachedtensortrain import TTCache, isbatchevaluable  # noqa: F401
-from .contraction import (Contraction, _contractsitetensors, _factorize, contract, contract_naive,  # noqa: F401
+from .contraction import (Contraction, _contractsitetensors, _factorize, compress, contract, contract_naive,  # noqa: F401
                           contract_TCI, contract_zipup)
 from .globalpivotfinder import (AbstractGlobalPivotFinder, DefaultGlobalPivotFinder,  # noqa: F401
                                 GlobalPivotSearchInput)

@@ -87,10 +87,36 @@ def _factorize(A, method, tolerance, maxbonddim, leftorthogonal=False, normalize
     raise RuntimeError("Not implemented yet.")
 
 
+def compress(tt, method="LU", tolerance=1e-12, maxbonddim=I64MAX, normalizeerror=True, ctx=None):
+    """compress!(tt, method; tolerance, maxbonddim, normalizeerror) (tensortrain.jl:149-183): a left-to-right
+    sweep without truncation followed by a truncating right-to-left sweep.  :LU / :CI factorise on the GPU
+    (tci_rrlu + tci_luci_*), :SVD on the host."""
+    cores = tt.sitetensors
+    n = len(cores)
+    for ell in range(n - 1):  # :157-167
+        shl = cores[ell].shape
+        lft, rgt, newd = _factorize(cores[ell].reshape((-1, shl[-1]), order="F"), method, tolerance=0.0,
+                                    maxbonddim=I64MAX, leftorthogonal=True, ctx=ctx)
+        cores[ell] = np.asfortranarray(lft).reshape((*shl[:-1], newd), order="F")
+        shr = cores[ell + 1].shape
+        nxt = rgt @ cores[ell + 1].reshape((shr[0], -1), order="F")
+        cores[ell + 1] = np.asfortranarray(nxt).reshape((newd, *shr[1:]), order="F")
+    for ell in range(n - 1, 0, -1):  # :170-180
+        shr = cores[ell].shape
+        lft, rgt, newd = _factorize(cores[ell].reshape((shr[0], -1), order="F"), method, tolerance=tolerance,
+                                    maxbonddim=maxbonddim, normalizeerror=normalizeerror, leftorthogonal=False,
+                                    ctx=ctx)
+        cores[ell] = np.asfortranarray(rgt).reshape((newd, *shr[1:]), order="F")
+        shl = cores[ell - 1].shape
+        nxt = cores[ell - 1].reshape((-1, shl[-1]), order="F") @ lft
+        cores[ell - 1] = np.asfortranarray(nxt).reshape((*shl[:-1], newd), order="F")
+    return tt
+
+
 def contract_naive(a, b, tolerance=0.0, maxbonddim=I64MAX, ctx=None):  # contraction.jl:351-372
     tt = TensorTrain([_contractsitetensors(x, y, ctx) for x, y in zip(a.sitetensors, b.sitetensors)])
     if tolerance > 0 or maxbonddim < I64MAX:
-        raise NotImplementedError("SVD recompression (compress!) is outside the accelerated path (SURVEY 8f-3)")
+        compress(tt, "SVD", tolerance=tolerance, maxbonddim=maxbonddim, ctx=ctx)
     return tt
 
 

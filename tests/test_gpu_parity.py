@@ -467,6 +467,29 @@ def test_contract_zipup_and_tci_vs_dense(T):  # test_contraction.jl:68-99, 185-1
     np.testing.assert_allclose(dense(ttn.sitetensors), ref, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("method", ["LU", "CI", "SVD"])
+def test_compress(T, method):  # tensortrain.jl:149-183 ; test_tensortrain.jl compress tests (structure re-used)
+    rng = np.random.default_rng(12)
+    dims = [3, 4, 3, 4, 3]
+    small = _rand_tt(rng, [1, 3, 4, 4, 3, 1], dims)
+    # embed the rank-(3,4,4,3) train into bond dimension 9 so that exact compression must find it again
+    big = []
+    for i, c in enumerate(small):
+        Dl, d, Dr = c.shape
+        L = np.eye(Dl) if i == 0 else Q_prev
+        Q = rng.standard_normal((Dr, 9)) if i < len(small) - 1 else np.eye(Dr)
+        core = np.einsum("al,ldr,rb->adb", L, c, Q)
+        Q_prev = np.linalg.pinv(Q) if i < len(small) - 1 else None
+        big.append(np.asfortranarray(core))
+    tt = T.TensorTrain(big)
+    full = T.fulltensor(tt)
+    T.compress(tt, method, tolerance=1e-11)
+    assert max(c.shape[0] for c in tt.sitetensors[1:]) <= 4
+    np.testing.assert_allclose(T.fulltensor(tt), full, rtol=1e-8, atol=1e-10 * np.max(np.abs(full)))
+    T.compress(tt, method, tolerance=1e-11, maxbonddim=2)
+    assert max(c.shape[0] for c in tt.sitetensors[1:]) <= 2
+
+
 # ------------------------------------------------------- K7 + the driver ----
 def test_globalsearch_matches_oracle(T, oracle):  # test_globalsearch.jl:7-36
     R = 10

@@ -113,6 +113,19 @@ def test_rrlu_not_leftorthogonal(oracle):  # matrixlu.jl:117-123,170-174
     np.testing.assert_allclose(left @ right, A, rtol=1.5e-8)
 
 
+def test_arrlu_4x4(oracle):  # test_matrixlu.jl:71-86 "Implementation of approximate rank-revealing LU"
+    A = G.RRLU_4x4
+    lu = oracle.arrlu(A, [1], [1])
+    assert lu.L.shape == (4, lu.npivot) and lu.U.shape == (lu.npivot, 4)
+    assert np.all(lu.L == np.tril(lu.L)) and np.all(np.diag(lu.L) == 1.0)
+    assert np.all(lu.U == np.triu(lu.U))
+    left = np.zeros_like(lu.L)
+    left[lu.rowpermutation - 1, :] = lu.L
+    right = np.zeros_like(lu.U)
+    right[:, lu.colpermutation - 1] = lu.U
+    np.testing.assert_allclose(left @ right, A, rtol=1.5e-8)
+
+
 # ------------------------------------------------------------------ LUCI ----
 @pytest.mark.parametrize("leftorth", [True, False])
 def test_luci_matches_ci(oracle, leftorth):  # test_matrixluci.jl:6-38
@@ -208,6 +221,28 @@ def test_lorentz_5x10(oracle):  # test_tensorci2.jl:247-340 (ValueType Float64, 
         assert abs(res.evaluate(v) - f) <= 1.5e-8 * abs(f)
     res8 = oracle.crossinterpolate2(t, [10] * n, tolerance=1e-8, maxiter=8, sweepstrategy="forward")
     assert max(res8.linkdims) >= 3
+
+
+def test_lorentz_5x10_rook(oracle):  # test_tensorci2.jl:247-340 with pivotsearch = :rook
+    n = 5
+    t = oracle.Target.builtin(LORENTZ, [1.0], [10] * n)
+    res = oracle.crossinterpolate2(t, [10] * n, tolerance=1e-12, maxiter=200, pivotsearch="rook")
+    assert max(res.bonderrors) <= 2e-12 and max(res.linkdims) <= 200
+    for v in itertools.product(range(1, 4), repeat=n):
+        f = 1.0 / (1.0 + sum(x * x for x in v))
+        assert abs(res.evaluate(v) - f) <= 1.5e-8 * abs(f)
+
+
+def test_trivial_mps_exp_rook(oracle):  # test_tensorci2.jl:55-102 with pivotsearch = :rook
+    R = 8
+    t = oracle.Target.builtin(Q1D, [R, 0], [2] * R)
+    res = oracle.crossinterpolate2(t, [2] * R, [[1] * R, [1] + [2] * (R - 1)], tolerance=1e-4, maxbonddim=1, maxiter=2,
+                                   normalizeerror=False, nsearchglobalpivot=0, maxnglobalpivot=0, pivotsearch="rook")
+    assert res.linkdims == [1] * (R - 1)
+    for x in (0.1, 0.3, 0.6, 0.9):
+        q = int(x * 2**R)
+        bits = [((q >> (R - 1 - b)) & 1) + 1 for b in range(R)]
+        assert abs(res.evaluate(bits) - t(bits)) < 1e-4
 
 
 def test_lorentz_sum_docs_example(oracle):  # docs/src/index.md:15-43 (sum vs brute force)
