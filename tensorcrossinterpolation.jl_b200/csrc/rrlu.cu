@@ -9,23 +9,24 @@
 // position the reference's physically swapped matrix would hold column j at), so no
 // CTA ever writes another CTA's data.  One pivot step is:
 //
-//   1. every CTA reads the G posted candidates (|a|^2, value, row, column position)
-//      and reduces them with the reference's tie-break: larger abs2, then smaller
-//      column position, then smaller row  == "columns outer, rows inner, strict >"
-//      of matrixlu.jl:16-29 on the physically swapped matrix;
+//   1. warp 0 of every CTA polls the G posted candidate records (one aligned 16-byte word each:
+//      value, row | phase bit, column position); the phase bit flips every second step, so the
+//      polling loop IS the grid barrier and returns the candidates in the same round trip.  The
+//      winner is reduced with the reference's tie-break: larger abs2, then smaller column position,
+//      then smaller row == "columns outer, rows inner, strict >" of matrixlu.jl:16-29 on the
+//      physically swapped matrix;
 //   2. stop rule (matrixlu.jl:153-158), evaluated redundantly and identically;
-//   3. row swap s <-> pr in the own columns; colpos update; y_j = A[s, j];
+//   3. row swap s <-> pr in the own columns; position update; y_j = A[s, j];
 //   4. x = the winner's *posted* pivot column (already divided by the pivot when
-//      leftorthogonal) -- every CTA posts the column of its own candidate together
-//      with the candidate, so that after ONE grid barrier all CTAs have the pivot
-//      column without a second synchronisation;
+//      leftorthogonal) -- every CTA posts the column of its own candidate before its record,
+//      so after ONE synchronisation all CTAs have the pivot column;
 //   5. trailing update a -= x_i * y_j (rounded multiply, rounded subtract in exact
 //      mode: Julia does not contract) fused with the arg-max search for
 //      the next pivot;
-//   6. post candidate + its column for the next step; grid barrier.
+//   6. post the column, fence, then the record.
 //
 // HBM traffic is the algorithmic 16 B per trailing element per pivot (one read, one
-// write); for matrices up to ~100 MB the trailing matrix is L2 resident.
+// write); matrices up to ~30 MB live in shared memory for the whole factorisation.
 #include <cstdio>
 #include <cstdlib>
 #include <set>
