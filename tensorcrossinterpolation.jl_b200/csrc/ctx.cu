@@ -38,13 +38,11 @@ extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
-        cudaMalloc(&c->rr_barrier, 64 * sizeof(unsigned)) != cudaSuccess) {
+        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
         delete c;
         return tci_fail(nullptr, TCI_ERR_CUDA, "context setup failed: " + m);
     }
-    cudaMemset(c->rr_barrier, 0, 64 * sizeof(unsigned));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
         unsigned long long keep = ~0ull; // keep freed scratch in the pool
@@ -69,8 +67,6 @@ extern "C" void tci_ctx_destroy(tci_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->targets) target_free(*kv.second);
-    cudaFree(ctx->rr_scratch);
-    cudaFree(ctx->rr_barrier);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2);

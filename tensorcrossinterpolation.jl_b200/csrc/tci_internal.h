@@ -52,10 +52,6 @@ struct tci_ctx {
     double stage_ms[ST_COUNT] = {0};
     std::map<i64, std::unique_ptr<TargetDev>> targets;
     i64 next_target = 1;
-    // reusable scratch for the rrLU persistent kernel
-    void *rr_scratch = nullptr;
-    size_t rr_scratch_bytes = 0;
-    unsigned *rr_barrier = nullptr;
 };
 
 struct tci_lu {

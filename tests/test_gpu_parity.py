@@ -505,6 +505,19 @@ def test_globalsearch_matches_oracle(T, oracle):  # test_globalsearch.jl:7-36
     assert np.array_equal(finder.last_errors, errs)
 
 
+def test_estimatetrueerror(T):  # test_globalsearch.jl:7-36
+    R = 20
+    f = T.BuiltinTarget(Q1D, [R, 1], [2] * R)  # exp(-x) + 1e-3 sin(1000 x)
+    tci, ranks, errors = T.crossinterpolate2(f, [2] * R, [[1] * R, [1] + [2] * (R - 1)], tolerance=1e-4, maxbonddim=1,
+                                             normalizeerror=False)
+    pivoterrors = T.estimatetrueerror(T.TensorTrain(tci.sitetensors), f, nsearch=12, rng=T.CounterRNG(9))
+    errs = [e for _, e in pivoterrors]
+    for p, e in pivoterrors:
+        assert abs(abs(f(p) - tci(p)) - e) <= 1e-12 * max(1.0, e) + 1e-15
+    assert all(a >= b for a, b in zip(errs[:-1], errs[1:]))  # sorted in descending order
+    assert len(set((tuple(p), e) for p, e in pivoterrors)) == len(pivoterrors)
+
+
 def compare_tci(tci, ranks, errors, res, T):
     n = len(tci)
     assert [int(r) for r in ranks] == res.ranks.tolist()
@@ -622,3 +635,97 @@ def test_multigpu_sharded_tci_identical_to_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29577",
                           os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_config4_scale_pi_and_rrlu_vs_oracle_on_pivot_submatrix(T, oracle):
+    """BASELINE config 4 at its full size: 12 sites, d = 64, Pi = 32768 x 32768 (8.6 GB, stays in HBM),
+    config-4 target, rrLU truncated at 16 pivots.  Size-independent check: full pivoting on Pi and on any
+    order-preserving submatrix S that contains all chosen pivot rows and columns must pick the same pivots with
+    bit-identical values (the Schur updates of S only involve pivot rows / columns, all inside S).  S is
+    evaluated and factorised by the CPU oracle."""
+    ld = [64] * 12
+    p = sepcos_params(12)
+    f, o = T.BuiltinTarget(SEPCOS, p, ld), oracle.Target.builtin(SEPCOS, p, ld)
+    rng = np.random.default_rng(44)
+    chi = 512
+
+    def distinct(count, length):
+        seen, out = set(), []
+        while len(out) < count:
+            v = tuple(int(x) for x in rng.integers(1, 65, length))
+            if v not in seen:
+                seen.add(v)
+                out.append(v)
+        return np.array(out, dtype=np.int64)
+
+    I = T.kronecker_left(distinct(chi, 5), 64)   # 32768 x 6
+    J = T.kronecker_right(64, distinct(chi, 5))  # 32768 x 6
+    assert I.shape == (32768, 6) and J.shape == (32768, 6)
+    dev, mx = f.batchevaluate_device(I, J, 0)
+    assert dev.shape == (32768, 32768)
+    r = 16
+    lu = T.rrlu(dev, maxrank=r, reltol=1e-14)
+    assert lu.npivot == r
+    prow, pcol = T.rowindices(lu) - 1, T.colindices(lu) - 1
+    rows = np.array(sorted(set(prow.tolist()) | set(rng.integers(0, 32768, 150).tolist())))
+    cols = np.array(sorted(set(pcol.tolist()) | set(rng.integers(0, 32768, 150).tolist())))
+    S, omx = o.pi_eval(I[rows].tolist(), J[cols].tolist(), 0, 0.0)
+    ref = oracle.rrlu(S, maxrank=r, reltol=1e-14)
+    assert rows[ref.rowpermutation[:r] - 1].tolist() == prow.tolist()
+    assert cols[ref.colpermutation[:r] - 1].tolist() == pcol.tolist()
+    assert np.array_equal(T.pivoterrors(lu)[:r], ref.pivoterrors[:r])
+    assert mx >= omx  # the fused max-abs covers all of Pi, the oracle's only S
+
+
+# ---------------------------------------------------------------- edge cases ----
+def test_rrlu_degenerate_shapes(T, oracle):
+    """Empty, single-row / single-column and maxrank corner cases (matrixlu.jl:141-181)."""
+    for shape in [(0, 5), (5, 0), (0, 0)]:
+        lu = T.rrlu(np.zeros(shape))
+        assert lu.npivot == 0 and lu.error == 0.0 and lu.L.shape == (shape[0], 0) and lu.U.shape == (0, shape[1])
+        assert T.pivoterrors(lu).tolist() == [0.0]
+    for A in [np.array([[3.0]]), np.array([[1.0, -4.0, 2.0]]), np.array([[1.0], [-4.0], [2.0]]),
+              np.array([[0.0, 0.0], [0.0, 5.0]])]:
+        for lo in (True, False):
+            assert_lu_equal(T.rrlu(A, leftorthogonal=lo), oracle.rrlu(A, leftorthogonal=lo))
+    A = np.random.default_rng(1).random((6, 9))
+    assert_lu_equal(T.rrlu(A, maxrank=100), oracle.rrlu(A, maxrank=100))  # maxrank above min(m, n)
+    assert_lu_equal(T.rrlu(A, maxrank=1), oracle.rrlu(A, maxrank=1))
+    assert_lu_equal(T.rrlu(A, reltol=0.9), oracle.rrlu(A, reltol=0.9))  # stops after the first pivots
+    assert_lu_equal(T.rrlu(A, abstol=10.0), oracle.rrlu(A, abstol=10.0))  # at least one pivot is always taken
+    with pytest.raises(ValueError):
+        T.rrlu(A, maxrank=0)
+    with pytest.raises(ValueError):
+        T.rrlu(np.zeros(3))
+
+
+def test_rrlu_inf_and_huge_values(T, oracle):
+    """abs2 overflows to Inf for |x| > 1.3e154: ties on Inf are broken by scan order (Appendix A.4)."""
+    A = np.random.default_rng(2).random((12, 10))
+    A[3, 4] = 1e200
+    A[7, 2] = -1e200
+    lu, ref = T.rrlu(A, maxrank=3), oracle.rrlu(A, maxrank=3)
+    assert_lu_equal(lu, ref)
+    assert (lu.rowpermutation[0], lu.colpermutation[0]) == (8, 3)  # column 3 is scanned before column 5
+    B = A * 1e-300  # squares underflow to 0 except the two large entries
+    assert_lu_equal(T.rrlu(B, maxrank=4), oracle.rrlu(B, maxrank=4))
+
+
+def test_pi_eval_single_point_and_full_tensor(T, oracle):
+    """nl = nr = 0 (the whole tensor as one Pi) and 1 x 1 requests."""
+    ld = [3, 4, 2]
+    f, o = make_target(T, oracle, TABLE, "table", ld)
+    full = f(np.zeros((1, 0), dtype=np.int64), np.zeros((1, 0), dtype=np.int64), 3)
+    assert full.shape == (1, 3, 4, 2, 1)
+    table = np.random.default_rng(11).standard_normal(24).reshape(ld, order="F")
+    assert np.array_equal(full[0, ..., 0], table)
+    one = f([[2, 3]], [[1]], 0)
+    assert one.shape == (1, 1) and one[0, 0] == table[1, 2, 0] == f([2, 3, 1])
+
+
+def test_context_reports_launches_and_timers(T, ctx):
+    l0 = ctx.launches
+    T.rrlu(np.eye(3))
+    assert ctx.launches > l0
+    tm = ctx.timers()
+    assert set(tm) >= {"pi_eval", "rrlu", "luci", "rrlu_kernel"} and tm["rrlu_kernel"] > 0.0
