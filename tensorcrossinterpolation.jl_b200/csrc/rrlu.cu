@@ -656,6 +656,8 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         G = 1;
         resident = true;
     } else {
+        // (measured: the full grid is best from 1024^2 up; a persisting-L2 access-policy window over the
+        //  matrix was tried for the streaming regime and halved the bandwidth, so it is not used)
         G = (int)std::min<i64>(std::min<i64>(ctx->sm_count, 32 * RR_MAXQ), std::max<i64>(1, n / 2));
         resident = xs_in_smem && smem_need(G, true) <= SMEM_BUDGET;
     }
