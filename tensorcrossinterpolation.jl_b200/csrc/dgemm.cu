@@ -236,6 +236,166 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
         }
 }
 
+// ---- DMMA kernel with a 3-stage cp.async pipeline ---------------------------------------------
+// Same tiling as k_dgemm_mma, but the operand tiles go global -> shared with 16-byte cp.async (no
+// register staging, one __syncthreads per k-tile, two tiles in flight while the third is consumed).
+// The shared layout follows the contiguous direction of each operand in global memory so that every
+// 16-byte chunk is two adjacent doubles on both sides:
+//   A not transposed (m contiguous): As[k][BM+4]      A transposed (k contiguous): As[m][MK+4]
+//   B not transposed (k contiguous): Bs[n][MK+4]      B transposed (n contiguous): Bs[k][BN+4]
+// (+4 padding: the 8-byte fragment loads of a half warp hit 16 different bank pairs in all four cases).
+// Needs 16-byte aligned operands: even leading dimensions / strides / offsets, checked by the launcher.
+#define ASTAGES 3
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int BM, int BN, int NWM, int NWN, bool TA, bool TB>
+__global__ void __launch_bounds__(32 * NWM * NWN)
+    k_dgemm_mma_async(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
+                      const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
+                      i64 strideC, const i64 *__restrict__ offA, const i64 *__restrict__ offB)
+{
+    constexpr int NT = 32 * NWM * NWN;
+    constexpr int TI = BM / NWM / 8, TJ = BN / NWN / 8;
+    constexpr int A_ROW = TA ? MK + 4 : BM + 4, A_ROWS = TA ? BM : MK; // shared tile of A: A_ROWS x A_ROW
+    constexpr int B_ROW = TB ? BN + 4 : MK + 4, B_ROWS = TB ? MK : BN;
+    constexpr int A_SZ = A_ROW * A_ROWS, B_SZ = B_ROW * B_ROWS;
+    extern __shared__ __align__(16) double dsm[];
+    double *const Asm = dsm;                   // [ASTAGES][A_SZ]
+    double *const Bsm = dsm + ASTAGES * A_SZ;  // [ASTAGES][B_SZ]
+
+    A += strideA * blockIdx.z + (offA ? offA[blockIdx.z] : 0);
+    B += strideB * blockIdx.z + (offB ? offB[blockIdx.z] : 0);
+    C += strideC * blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp % NWM) * (BM / NWM), wn = (warp / NWM) * (BN / NWN);
+    const int fr = lane >> 2, fk = lane & 3;
+    const i64 m0 = (i64)blockIdx.x * BM, n0 = (i64)blockIdx.y * BN;
+
+    auto load_stage = [&](int stage, i64 k0) {
+        double *as = Asm + stage * A_SZ, *bs = Bsm + stage * B_SZ;
+        // A: chunks of two doubles along the contiguous direction
+        constexpr int ACH = BM * MK / 2;
+#pragma unroll
+        for (int c = tid; c < ACH; c += NT) {
+            if (!TA) { // pairs along m
+                const int mm = (c % (BM / 2)) * 2, kk = c / (BM / 2);
+                const i64 gm = m0 + mm, gk = k0 + kk;
+                const int bytes = (gk < K && gm < M) ? (gm + 1 < M ? 16 : 8) : 0;
+                cp_async16(as + kk * A_ROW + mm, A + (bytes ? gm + lda * gk : 0), bytes);
+            } else { // pairs along k
+                const int kk = (c % (MK / 2)) * 2, mm = c / (MK / 2);
+                const i64 gm = m0 + mm, gk = k0 + kk;
+                const int bytes = (gm < M && gk < K) ? (gk + 1 < K ? 16 : 8) : 0;
+                cp_async16(as + mm * A_ROW + kk, A + (bytes ? gk + lda * gm : 0), bytes);
+            }
+        }
+        constexpr int BCH = BN * MK / 2;
+#pragma unroll
+        for (int c = tid; c < BCH; c += NT) {
+            if (!TB) { // B is K x N: pairs along k
+                const int kk = (c % (MK / 2)) * 2, nn = c / (MK / 2);
+                const i64 gn = n0 + nn, gk = k0 + kk;
+                const int bytes = (gn < N && gk < K) ? (gk + 1 < K ? 16 : 8) : 0;
+                cp_async16(bs + nn * B_ROW + kk, B + (bytes ? gk + ldb * gn : 0), bytes);
+            } else { // B is N x K: pairs along n
+                const int nn = (c % (BN / 2)) * 2, kk = c / (BN / 2);
+                const i64 gn = n0 + nn, gk = k0 + kk;
+                const int bytes = (gk < K && gn < N) ? (gn + 1 < N ? 16 : 8) : 0;
+                cp_async16(bs + kk * B_ROW + nn, B + (bytes ? gn + ldb * gk : 0), bytes);
+            }
+        }
+    };
+
+    double acc[TI][TJ][2];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const i64 nkt = (K + MK - 1) / MK;
+#pragma unroll
+    for (int st = 0; st < ASTAGES - 1; ++st) {
+        if (st < nkt) load_stage(st, (i64)st * MK);
+        cp_async_commit();
+    }
+    for (i64 kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<ASTAGES - 2>(); // tile kt has landed
+        __syncthreads();              // ... for everybody, and everybody is done with tile kt-1
+        if (kt + ASTAGES - 1 < nkt) load_stage((int)((kt + ASTAGES - 1) % ASTAGES), (kt + ASTAGES - 1) * MK);
+        cp_async_commit();
+        const double *as = Asm + (kt % ASTAGES) * A_SZ, *bs = Bsm + (kt % ASTAGES) * B_SZ;
+#pragma unroll
+        for (int k4 = 0; k4 < MK; k4 += 4) {
+            double af[TI], bf[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+                af[i] = TA ? as[(wm + 8 * i + fr) * A_ROW + k4 + fk] : as[(k4 + fk) * A_ROW + wm + 8 * i + fr];
+#pragma unroll
+            for (int j = 0; j < TJ; ++j)
+                bf[j] = TB ? bs[(k4 + fk) * B_ROW + wn + 8 * j + fr] : bs[(wn + 8 * j + fr) * B_ROW + k4 + fk];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const i64 gn = n0 + wn + 8 * j + 2 * fk + c;
+            if (gn >= N) continue;
+#pragma unroll
+            for (int i = 0; i < TI; ++i) {
+                const i64 gm = m0 + wm + 8 * i + fr;
+                if (gm >= M) continue;
+                const double v = alpha * acc[i][j][c];
+                double *cp = C + gm + ldc * gn;
+                *cp = (beta == 0.0) ? v : fma(beta, *cp, v);
+            }
+        }
+}
+
+template <int BM, int BN, int NWM, int NWN, bool TA, bool TB>
+static int launch_async_one(tci_ctx *ctx, dim3 grid, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda, i64 sA,
+                            const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC,
+                            const i64 *offA, const i64 *offB)
+{
+    constexpr int A_SZ = (TA ? MK + 4 : BM + 4) * (TA ? BM : MK), B_SZ = (TB ? BN + 4 : MK + 4) * (TB ? MK : BN);
+    constexpr size_t smem = (size_t)ASTAGES * (A_SZ + B_SZ) * sizeof(double);
+    auto fn = k_dgemm_mma_async<BM, BN, NWM, NWN, TA, TB>;
+    static bool configured = false;
+    if (!configured) {
+        TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    fn<<<grid, 32 * NWM * NWN, smem, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    ctx->launches++;
+    return TCI_OK;
+}
+
+template <int BM, int BN, int NWM, int NWN>
+static int launch_dgemm_mma_async(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A,
+                                  i64 lda, i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc,
+                                  i64 sC, i64 batch, const i64 *offA, const i64 *offB)
+{
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch);
+    if (!tA && !tB)
+        return launch_async_one<BM, BN, NWM, NWN, false, false>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    if (tA && !tB)
+        return launch_async_one<BM, BN, NWM, NWN, true, false>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    if (!tA && tB)
+        return launch_async_one<BM, BN, NWM, NWN, false, true>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    return launch_async_one<BM, BN, NWM, NWN, true, true>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+}
+
 template <int BM, int BN, int NWM, int NWN>
 static void launch_dgemm_mma(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A,
                              i64 lda, i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc,
@@ -282,7 +442,7 @@ __global__ void k_scale(double *C, i64 M, i64 N, i64 ldc, i64 strideC, double be
 
 int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
                           i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
-                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB)
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB, bool offsets_even)
 {
     if (M <= 0 || N <= 0 || batch <= 0) return TCI_OK;
     if (batch > 65535) { // gridDim.z limit
@@ -290,7 +450,7 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
             i64 nb = std::min<i64>(65535, batch - b0);
             int rc = dgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A + strideA * b0, lda, strideA,
                                            B + strideB * b0, ldb, strideB, beta, C + strideC * b0, ldc, strideC, nb,
-                                           offA ? offA + b0 : nullptr, offB ? offB + b0 : nullptr);
+                                           offA ? offA + b0 : nullptr, offB ? offB + b0 : nullptr, offsets_even);
             if (rc) return rc;
         }
         return TCI_OK;
@@ -313,7 +473,23 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         else if (use_mma && force_tile == 6432)
             launch_dgemm_mma<64, 32, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
                                            strideC, batch, offA, offB);
-        else if (use_mma && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96)
+        if (use_mma && force_tile) {
+            TCI_CUDA(ctx, cudaGetLastError());
+            return TCI_OK;
+        }
+        // cp.async pipeline variant: operands must be 16-byte aligned along their contiguous direction
+        const bool aligned16 = (((size_t)A | (size_t)B) & 15) == 0 && !((lda | ldb | strideA | strideB) & 1) &&
+                               ((!offA && !offB) || offsets_even);
+        static const int use_async = getenv("TCI_DGEMM_NO_ASYNC") ? 0 : 1;
+        if (use_mma && use_async && aligned16 && !force_tile && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96) {
+            int rc = launch_dgemm_mma_async<128, 128, 2, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
+                                                            beta, C, ldc, strideC, batch, offA, offB);
+            if (rc) return rc;
+        } else if (use_mma && use_async && aligned16 && !force_tile && mid_ctas >= 16 && M >= 32 && N >= 32) {
+            int rc = launch_dgemm_mma_async<64, 64, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
+                                                          beta, C, ldc, strideC, batch, offA, offB);
+            if (rc) return rc;
+        } else if (use_mma && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96)
             launch_dgemm_mma<128, 128, 2, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C,
                                              ldc, strideC, batch, offA, offB);
         else if (use_mma && mid_ctas >= 16 && M >= 32 && N >= 32)
@@ -335,7 +511,7 @@ int dgemm_dev_batched(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, doubl
                       i64 batch)
 {
     return dgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
-                                 batch, nullptr, nullptr);
+                                 batch, nullptr, nullptr, false);
 }
 
 int dgemm_dev(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,

@@ -8,10 +8,6 @@
 // A per-point environment is the (La x Lb) matrix env[a + La*(b + Lb*q)].
 #include "tci_internal.h"
 
-int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
-                          i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
-                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB);
-
 struct MpoSite {
     const double *A, *B;
     i64 La, d1, S, Lan; // A: (La, d1, S, Lan)
@@ -62,12 +58,13 @@ static int mpo_left_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i6
         TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * count * sizeof(double)));
         // tmp[q] (Lb x S*Lan) = env[q]^T (Lb x La) * A_i (La x S*Lan)       contraction.jl:105
         int rc = dgemm_dev_batched_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, m.La * m.Lb, m.A,
-                                       m.La * m.d1, 0, 0.0, tmp, m.Lb, m.Lb * m.S * m.Lan, count, nullptr, offA.p);
+                                       m.La * m.d1, 0, 0.0, tmp, m.Lb, m.Lb * m.S * m.Lan, count, nullptr, offA.p,
+                                       m.La % 2 == 0);
         // nxt[q] (Lan x Lbn) = tmp[q]^T (Lan x Lb*S) * B_j (Lb*S x Lbn)       contraction.jl:108
         if (!rc)
             rc = dgemm_dev_batched_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
                                        m.Lb * m.S * m.Lan, m.B, m.Lb * m.S * m.d3, 0, 0.0, nxt, m.Lan, m.Lan * m.Lbn,
-                                       count, nullptr, offB.p);
+                                       count, nullptr, offB.p, (m.Lb * m.S) % 2 == 0);
         dev_free(ctx, tmp);
         dev_free(ctx, env);
         env = nxt;
@@ -110,12 +107,12 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
         for (i64 h = 0; h < m.S && !rc; ++h) // (Lbn x La) = env^T (Lbn x Lan) * A_{i,h}^T (Lan x La)
             rc = dgemm_dev_batched_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, m.Lan * m.Lbn,
                                        m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h, m.Lbn * m.S,
-                                       m.Lbn * m.S * m.La, count, nullptr, offA.p);
+                                       m.Lbn * m.S * m.La, count, nullptr, offA.p, m.La % 2 == 0);
         // nxt[q][al, bl] = sum_{br,h} tmp[br, h, al] * B[bl, h, j, br]
         for (i64 h = 0; h < m.S && !rc; ++h) // (La x Lb) += tmp_h^T (La x Lbn) * B_{j,h}^T (Lbn x Lb)
             rc = dgemm_dev_batched_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
                                        m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0, nxt,
-                                       m.La, m.La * m.Lb, count, nullptr, offB.p);
+                                       m.La, m.La * m.Lb, count, nullptr, offB.p, (m.Lb * m.S) % 2 == 0);
         dev_free(ctx, tmp);
         dev_free(ctx, env);
         env = nxt;

@@ -159,7 +159,7 @@ int dgemm_dev_batched(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, doubl
 // per-batch element offsets added to A / B (device arrays, nullable)
 int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
                           i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
-                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB);
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB, bool offsets_even = false);
 
 // pi_eval.cu / tt.cu / mpo.cu
 int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
