@@ -261,7 +261,9 @@ def main():
                           "parallelism": "replicas only (rrLU does not shard)" if world > 1 else "single GPU",
                           "exact_mode": True},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": which,
+                            "frac": achieved / peak, "traffic": RRLU_DRAM_TRAFFIC.get((m, n, r)),
+                            "traffic_source": "profiles/r1_rrlu_8192_1024_dram.csv (ncu dram__bytes_read.sum + "
+                                              "dram__bytes_write.sum, one launch)", "peak_source": which,
                             "kernel": "k_rrlu<true>", "kernel_ms": kernel_ms,
                             "algorithmic_bytes": rrlu_bytes(m, n, r),
                             "fp64_gflops_kernel": flops / (kernel_ms * 1e-3) / 1e9},
@@ -270,6 +272,12 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# DRAM bytes of one k_rrlu launch measured under ncu (profiles/r1_rrlu_8192_1024_dram.csv): 436.26 GB read +
+# 462.19 GB written; below the 967.4 GB algorithmic figure because alternate pivots sweep the tiles in
+# opposite order and the tail of one sweep is still in L2 for the next.
+RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 436260853504 + 462192695040}
 
 
 def run_extra(T, ctx, torch, dist, rank, world, stream):

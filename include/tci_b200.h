@@ -133,6 +133,11 @@ int tci_lu_fetch(tci_lu *lu, double *L /* nullable */, double *U /* nullable */)
 /* left(luci) (m x r) / right(luci) (r x n)  matrixluci.jl:40-84 */
 int tci_luci_left(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
 int tci_luci_right(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+/* B * A^-1 for a square A factorised to full rank by tci_rrlu (npivot == m == n): the solve of
+ * setsitetensor!, T = Pi1 * P^-1, `transpose(transpose(P) \\ transpose(Pi1))` at tensorci2.jl:391.
+ * The reference leaves it to LAPACK gesv (partial pivoting, version unpinned -- SURVEY 8c); here the
+ * full-pivot factors are reused: X[:, rowperm] = B[:, colperm] U^-1 L^-1.  B (rows x m) is not modified. */
+int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
 int tci_lu_destroy(tci_lu *lu);
 
 /* ---- dense FP64 GEMM on device matrices (building block of (b),(c)) ------- */

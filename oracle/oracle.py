@@ -358,3 +358,61 @@ def crossinterpolate2(target, localdims, initialpivots=None, tolerance=1e-8, max
         lib().orc_tci_destroy(C.c_void_p(h))
         raise OracleError(msg)
     return TCIResult(h, n)
+
+
+# ---- TensorTrain -> TensorCI2 conversion (conversion.jl:73-176), restated on the C oracle's LUCI ----
+def _kron_rows(Iset, d):  # kronecker(Iset, d) tensorci2.jl:315-320
+    return np.array([list(i) + [s] for s in range(1, d + 1) for i in Iset], dtype=np.int64).reshape(len(Iset) * d, -1)
+
+
+def _kron_cols(d, Jset):  # kronecker(d, Jset) tensorci2.jl:322-327
+    return np.array([[s] + list(j) for j in Jset for s in range(1, d + 1)], dtype=np.int64).reshape(len(Jset) * d, -1)
+
+
+def tt_sweep1sitegetindices(cores, forward, spectators=None, maxbonddim=None, tolerance=0.0):
+    """conversion.jl:73-139 on a list of (chi, d, chi') Fortran-ordered arrays (modified in place)."""
+    L = len(cores)
+    sets = [np.zeros((1, 0), dtype=np.int64)]
+    errs = np.zeros(max(c.shape[0] for c in cores[1:]) + 1)
+    for step in range(1, L):
+        here = step - 1 if forward else L - step
+        nxt = step if forward else L - step - 1
+        sh, shn = cores[here].shape, cores[nxt].shape
+        if forward:
+            f = luci(cores[here].reshape((sh[0] * sh[1], sh[2]), order="F"), maxrank=maxbonddim, abstol=tolerance,
+                     leftorthogonal=True)
+            sets.append(_kron_rows(sets[-1], sh[1])[f.rowindices - 1])
+            if spectators:
+                spectators[here] = spectators[here][f.colindices - 1]
+            cores[here] = np.asfortranarray(f.left).reshape((sh[0], sh[1], f.npivot), order="F")
+            cores[nxt] = np.asfortranarray(f.right @ cores[nxt].reshape((shn[0], -1), order="F")).reshape(
+                (f.npivot, shn[1], shn[2]), order="F")
+        else:
+            f = luci(cores[here].reshape((sh[0], sh[1] * sh[2]), order="F"), maxrank=maxbonddim, abstol=tolerance,
+                     leftorthogonal=False)
+            sets.append(_kron_cols(sh[1], sets[-1])[f.colindices - 1])
+            if spectators:
+                spectators[here] = spectators[here][f.rowindices - 1]
+            cores[here] = np.asfortranarray(f.right).reshape((f.npivot, sh[1], sh[2]), order="F")
+            cores[nxt] = np.asfortranarray(cores[nxt].reshape((-1, shn[2]), order="F") @ f.left).reshape(
+                (shn[0], shn[1], f.npivot), order="F")
+        errs[: f.npivot + 1] = np.maximum(errs[: f.npivot + 1], f.pivoterrors)
+    return (sets if forward else sets[::-1]), errs
+
+
+def tensorci2_from_tt(cores, tolerance=1e-12, maxbonddim=None, maxiter=3):
+    """conversion.jl:141-176.  Returns (Iset, Jset, cores, pivoterrors, maxsamplevalue)."""
+    cores = [np.asfortranarray(c, dtype=np.float64).copy(order="F") for c in cores]
+    Iset, _ = tt_sweep1sitegetindices(cores, True, None, maxbonddim, tolerance)
+    Jset, pe = tt_sweep1sitegetindices(cores, False, None, maxbonddim, tolerance)
+    same = lambda a, b: len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))  # noqa: E731
+    for it in range(3, maxiter + 1):
+        if it % 2:
+            new, pe = tt_sweep1sitegetindices(cores, True, Jset)
+            if same(new, Iset):
+                break
+        else:
+            new, pe = tt_sweep1sitegetindices(cores, False, Iset)
+            if same(new, Jset):
+                break
+    return Iset, Jset, cores, pe, max(float(np.abs(c).max()) for c in cores)

@@ -51,6 +51,7 @@ SYMBOLS = {
     "tci_lu_fetch": (C.c_int, [VP, P_f64, P_f64]),
     "tci_luci_left": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
     "tci_luci_right": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
+    "tci_lu_rdiv": (C.c_int, [VP, VP, P_f64, C.POINTER(VP)]),
     "tci_lu_destroy": (C.c_int, [VP]),
     "tci_dgemm_host": (C.c_int, [VP, C.c_int, C.c_int, i64, i64, i64, f64, P_f64, P_f64, f64, P_f64]),
     "tci_contract_zipup_site": (C.c_int, [VP, P_f64, i64, i64, i64, P_f64, i64, i64, i64, P_f64, i64, i64, P_f64,
@@ -155,6 +156,22 @@ def default_context():
     if _default is None:
         _default = Context(int(os.environ.get("LOCAL_RANK", "0")))
     return _default
+
+
+def gemm(A, B, ctx=None):
+    """A * B for host Float64 matrices through tci_dgemm_host (the library's DMMA GEMM); the host mirror
+    never multiplies matrices itself."""
+    ctx = ctx or default_context()
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    if A.shape[1] != B.shape[0]:
+        raise ValueError(f"DimensionMismatch: A has dimensions {A.shape}, B has dimensions {B.shape}")
+    M, K = A.shape
+    N = B.shape[1]
+    out = np.zeros((M, N), dtype=np.float64, order="F")
+    if M and N and K:
+        ctx.check(lib().tci_dgemm_host(ctx.h, 0, 0, M, N, K, 1.0, pf(A), pf(B), 0.0, pf(out)))
+    return out
 
 
 class DeviceMatrix:

@@ -99,7 +99,7 @@ def compress(tt, method="LU", tolerance=1e-12, maxbonddim=I64MAX, normalizeerror
                                     maxbonddim=I64MAX, leftorthogonal=True, ctx=ctx)
         cores[ell] = np.asfortranarray(lft).reshape((*shl[:-1], newd), order="F")
         shr = cores[ell + 1].shape
-        nxt = rgt @ cores[ell + 1].reshape((shr[0], -1), order="F")
+        nxt = _lib.gemm(rgt, cores[ell + 1].reshape((shr[0], -1), order="F"), ctx)
         cores[ell + 1] = np.asfortranarray(nxt).reshape((newd, *shr[1:]), order="F")
     for ell in range(n - 1, 0, -1):  # :170-180
         shr = cores[ell].shape
@@ -108,7 +108,7 @@ def compress(tt, method="LU", tolerance=1e-12, maxbonddim=I64MAX, normalizeerror
                                     ctx=ctx)
         cores[ell] = np.asfortranarray(rgt).reshape((newd, *shr[1:]), order="F")
         shl = cores[ell - 1].shape
-        nxt = cores[ell - 1].reshape((-1, shl[-1]), order="F") @ lft
+        nxt = _lib.gemm(cores[ell - 1].reshape((-1, shl[-1]), order="F"), lft, ctx)
         cores[ell - 1] = np.asfortranarray(nxt).reshape((*shl[:-1], newd), order="F")
     return tt
 

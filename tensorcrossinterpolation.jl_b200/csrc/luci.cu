@@ -9,8 +9,9 @@ int lu_extract(tci_lu *lu, double *dL, i64 ldl, double *dU, i64 ldu); // rrlu.cu
 #define TB_NB 32
 #define TB_THREADS 128
 
-// X[:, 0:nb] * T = X[:, 0:nb] with T (nb x nb) unit lower triangular:
-// x_j -= sum_{k>j} x_k T[k,j], j = nb-1 .. 0.  One thread per row of X.
+// X[:, 0:nb] * T = X[:, 0:nb] with T (nb x nb) lower triangular (unit diagonal if UNIT):
+// x_j = (x_j - sum_{k>j} x_k T[k,j]) / T[j,j], j = nb-1 .. 0.  One thread per row of X.
+template <bool UNIT>
 __global__ void __launch_bounds__(TB_THREADS)
     k_trsm_rl_block(double *__restrict__ X, i64 rows, i64 ldx, const double *__restrict__ T, i64 ldt, int nb)
 {
@@ -24,9 +25,40 @@ __global__ void __launch_bounds__(TB_THREADS)
     for (int j = nb - 1; j >= 0; --j) {
         double acc = xs[j][threadIdx.x];
         for (int k = j + 1; k < nb; ++k) acc = fma(-xs[k][threadIdx.x], Ts[k][j], acc);
-        xs[j][threadIdx.x] = acc;
+        xs[j][threadIdx.x] = UNIT ? acc : acc / Ts[j][j];
     }
     for (int j = 0; j < nb; ++j) X[row + ldx * j] = xs[j][threadIdx.x];
+}
+
+// X[:, 0:nb] * T = X[:, 0:nb] with T (nb x nb) upper triangular (unit diagonal if UNIT):
+// x_j = (x_j - sum_{k<j} x_k T[k,j]) / T[j,j], j = 0 .. nb-1.  One thread per row of X.
+template <bool UNIT>
+__global__ void __launch_bounds__(TB_THREADS)
+    k_trsm_ru_block(double *__restrict__ X, i64 rows, i64 ldx, const double *__restrict__ T, i64 ldt, int nb)
+{
+    __shared__ double Ts[TB_NB][TB_NB + 1];
+    __shared__ double xs[TB_NB][TB_THREADS];
+    for (int e = threadIdx.x; e < nb * nb; e += TB_THREADS) Ts[e % nb][e / nb] = T[(e % nb) + ldt * (e / nb)];
+    __syncthreads();
+    i64 row = blockIdx.x * (i64)TB_THREADS + threadIdx.x;
+    if (row >= rows) return;
+    for (int j = 0; j < nb; ++j) xs[j][threadIdx.x] = X[row + ldx * j];
+    for (int j = 0; j < nb; ++j) {
+        double acc = xs[j][threadIdx.x];
+        for (int k = 0; k < j; ++k) acc = fma(-xs[k][threadIdx.x], Ts[k][j], acc);
+        xs[j][threadIdx.x] = UNIT ? acc : acc / Ts[j][j];
+    }
+    for (int j = 0; j < nb; ++j) X[row + ldx * j] = xs[j][threadIdx.x];
+}
+
+// dst[:, q] = src[:, perm[q]]
+__global__ void k_gather_cols(const double *__restrict__ src, i64 lds, i64 rows, i64 n, const i64 *__restrict__ perm,
+                              double *__restrict__ dst, i64 ldd)
+{
+    i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= rows * n) return;
+    i64 i = e % rows, q = e / rows;
+    dst[i + ldd * q] = src[i + lds * perm[q]];
 }
 
 // T * X[0:nb, :] = X[0:nb, :] with T (nb x nb) unit upper triangular:
@@ -108,7 +140,7 @@ extern "C" int tci_luci_left(tci_lu *lu, double *out_host, tci_dmat **out_dev)
                 if (j1 < r) // X[:, j0:j1] -= X[:, j1:r] * L11[j1:r, j0:j1]
                     rc = dgemm_dev(ctx, false, false, rows, nb, r - j1, -1.0, X + m * j1, m, L.p + j1 + m * j0, m, 1.0,
                                    X + m * j0, m);
-                k_trsm_rl_block<<<(unsigned)((rows + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
+                k_trsm_rl_block<true><<<(unsigned)((rows + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
                     X + m * j0, rows, m, L.p + j0 + m * j0, m, (int)nb);
                 ctx->launches++;
             }
@@ -182,6 +214,76 @@ extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
             }
         }
         if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "luci_right launch failed");
+    }
+    if (rc) {
+        tci_dmat_destroy(res);
+        return rc;
+    }
+    return finish(ctx, res, out_host, out_dev);
+}
+
+// B * A^-1 for the square, fully factorised A = lu (the `\` of setsitetensor!, tensorci2.jl:391, which the
+// reference leaves to LAPACK gesv; here the full-pivot factors of K2 are reused):
+//   A[rowperm, colperm] = L U  =>  X[:, rowperm] = B[:, colperm] U^-1 L^-1
+extern "C" int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host, tci_dmat **out_dev)
+{
+    if (!lu || !B) return TCI_ERR_ARG;
+    tci_ctx *ctx = lu->ctx;
+    TCI_ENTER(ctx);
+    if (out_dev) *out_dev = nullptr;
+    const i64 k = lu->r, rows = B->m;
+    if (lu->m != lu->n || k != lu->m)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_lu_rdiv: the factorised matrix must be square and of full rank");
+    if (B->n != k) return tci_fail(ctx, TCI_ERR_ARG, "tci_lu_rdiv: DimensionMismatch between B and the factorised matrix");
+    tci_dmat *res = nullptr;
+    int rc = dmat_alloc(ctx, rows, k, &res);
+    if (rc) return rc;
+    if (rows == 0 || k == 0) return finish(ctx, res, out_host, out_dev);
+    {
+        StageTimer tm(ctx, ST_LUCI);
+        DevBuf<double> L(ctx), U(ctx), W(ctx);
+        TCI_CUDA(ctx, L.alloc((size_t)(k * k)));
+        TCI_CUDA(ctx, U.alloc((size_t)(k * k)));
+        TCI_CUDA(ctx, W.alloc((size_t)(rows * k)));
+        rc = lu_extract(lu, L.p, k, U.p, k);
+        const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
+        if (!rc) {
+            k_gather_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(B->p, B->ld, rows, k, lu->d_colperm,
+                                                                                   W.p, rows);
+            ctx->launches++;
+        }
+        for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) { // Y U = W, left to right
+            const i64 nb = std::min<i64>(TB_NB, k - j0);
+            if (j0 > 0)
+                rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W.p, rows, U.p + k * j0, k, 1.0, W.p + rows * j0,
+                               rows);
+            if (lu->leftorthogonal)
+                k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
+                                                                          U.p + j0 + k * j0, k, (int)nb);
+            else
+                k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
+                                                                         U.p + j0 + k * j0, k, (int)nb);
+            ctx->launches++;
+        }
+        for (i64 j1 = k; j1 > 0 && !rc; j1 -= TB_NB) { // X' L = Y, right to left
+            const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
+            if (j1 < k)
+                rc = dgemm_dev(ctx, false, false, rows, nb, k - j1, -1.0, W.p + rows * j1, rows, L.p + j1 + k * j0, k,
+                               1.0, W.p + rows * j0, rows);
+            if (lu->leftorthogonal)
+                k_trsm_rl_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
+                                                                         L.p + j0 + k * j0, k, (int)nb);
+            else
+                k_trsm_rl_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
+                                                                          L.p + j0 + k * j0, k, (int)nb);
+            ctx->launches++;
+        }
+        if (!rc) {
+            k_scatter_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(W.p, rows, rows, k, lu->d_rowperm,
+                                                                                    res->p, res->ld, 0);
+            ctx->launches++;
+        }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "lu_rdiv launch failed");
     }
     if (rc) {
         tci_dmat_destroy(res);

@@ -48,6 +48,20 @@ class rrLU:
             self._fetch()
         return self._U
 
+    def rdiv(self, B, device=False):
+        """B / A for the square matrix A this object factorises to full rank (tci_lu_rdiv): the solve of
+        setsitetensor! (tensorci2.jl:391).  B: DeviceMatrix or host matrix with size(A, 1) columns."""
+        if not isinstance(B, DeviceMatrix):
+            B = DeviceMatrix.from_host(self.ctx, np.asfortranarray(B, dtype=np.float64))
+        rows, k = B.shape
+        if device:
+            h = C.c_void_p()
+            self.ctx.check(lib().tci_lu_rdiv(self._h, B.h, None, C.byref(h)))
+            return DeviceMatrix(self.ctx, h)
+        out = np.zeros((rows, k), dtype=np.float64, order="F")
+        self.ctx.check(lib().tci_lu_rdiv(self._h, B.h, pf(out), None))
+        return out
+
     def __del__(self):
         try:
             if self._h:

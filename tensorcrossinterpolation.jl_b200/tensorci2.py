@@ -13,7 +13,7 @@ import numpy as np
 
 from .batcheval import BatchEvaluator
 from .globalpivotfinder import AbstractGlobalPivotFinder, DefaultGlobalPivotFinder, GlobalPivotSearchInput
-from .matrixlu import MatrixLUCI, colindices, pivoterrors, rowindices
+from .matrixlu import MatrixLUCI, colindices, pivoterrors, rowindices, rrlu
 from .parallel import PivotResult, broadcast_pivots
 from .tensortrain import TensorTrain, evaluate_points, tt_sum
 from .util import (CounterRNG, as_indexset, forwardsweep, jl_max, kronecker_left, kronecker_right, pushunique, union)
@@ -167,22 +167,27 @@ def updatemaxsample(tci, mx):  # :397-399 with the max-abs fused into the evalua
 
 
 def setsitetensor_fill(tci, f, b):
-    """setsitetensor!(tci, f, b) (tensorci2.jl:367-394): T_b = Pi1 * P^-1, solved on the host by
-    LAPACK gesv exactly as the reference's `\\` does."""
+    """setsitetensor!(tci, f, b) (tensorci2.jl:367-394): T_b = Pi1 * P^-1.  Pi1 and P are evaluated into HBM,
+    P is factorised to full rank by the K2 kernel and the solve runs on the device (tci_lu_rdiv) in place of
+    the reference's LAPACK `\\` (:391); only T_b comes back to the host."""
     n = len(tci)
-    Pi1, mx = f._pi(tci.Iset[b], tci.Jset[b], 1, True, False)[::2]
+    f = getattr(f, "local", f)  # the T tensors are small: replicated on every rank, not sharded
     nI, d, nJ = tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]
-    Pi1 = Pi1.reshape((nI * d, nJ), order="F")
-    updatemaxsample(tci, mx)
     if b == n - 1:
+        Pi1, _, mx = f._pi(tci.Iset[b], tci.Jset[b], 1, True, False)
+        updatemaxsample(tci, mx)
         tci.sitetensors[b] = Pi1.reshape((nI, d, nJ), order="F")
         return tci.sitetensors[b]
-    P = f(tci.Iset[b + 1], tci.Jset[b], 0)
+    Pi1, mx = f.batchevaluate_device(tci.Iset[b], tci.Jset[b], 1)
+    updatemaxsample(tci, mx)
     k = tci.Iset[b + 1].shape[0]
     if k != nJ:
         raise RuntimeError(f"Pivot matrix at bond {b + 1} is not square!")  # :388
-    Tmat = np.linalg.solve(P.T, Pi1.T).T  # transpose(transpose(P) \ transpose(Pi1))  :391
-    tci.sitetensors[b] = np.asfortranarray(Tmat).reshape((nI, d, k), order="F")
+    P, _ = f.batchevaluate_device(tci.Iset[b + 1], tci.Jset[b], 0)
+    lu = rrlu(P, reltol=0.0, abstol=0.0)  # never truncates; a singular P surfaces as the NaN error of rrlu
+    if lu.npivot != k:
+        raise RuntimeError(f"Pivot matrix at bond {b + 1} is singular!")
+    tci.sitetensors[b] = lu.rdiv(Pi1).reshape((nI, d, k), order="F")
     return tci.sitetensors[b]
 
 

@@ -490,6 +490,61 @@ def test_compress(T, method):  # tensortrain.jl:149-183 ; test_tensortrain.jl co
     assert max(c.shape[0] for c in tt.sitetensors[1:]) <= 2
 
 
+@pytest.mark.parametrize("k,rows,lo", [(1, 5, True), (37, 300, True), (70, 129, False), (300, 2000, True)])
+def test_lu_rdiv_matches_host_solve(T, k, rows, lo):  # the `\\` of setsitetensor! tensorci2.jl:391
+    rng = np.random.default_rng(k)
+    P = np.asfortranarray(rng.standard_normal((k, k)))
+    B = np.asfortranarray(rng.standard_normal((rows, k)))
+    lu = T.rrlu(P, reltol=0.0, abstol=0.0, leftorthogonal=lo)
+    assert lu.npivot == k
+    X = lu.rdiv(B)
+    ref = np.linalg.solve(P.T, B.T).T
+    np.testing.assert_allclose(X, ref, rtol=1e-9, atol=1e-10 * np.abs(ref).max())
+    np.testing.assert_allclose(X @ P, B, rtol=0, atol=1e-10 * np.abs(B).max() * np.linalg.cond(P))
+    Xd = lu.rdiv(T.DeviceMatrix.from_host(lu.ctx, B), device=True).to_host()
+    assert np.array_equal(Xd, X)
+    with pytest.raises(ValueError):  # TCI_ERR_ARG
+        T.rrlu(np.ones((4, 6), order="F"), maxrank=2).rdiv(np.ones((3, 4)))
+
+
+def test_tt_to_tci2_conversion_matches_oracle(T, oracle):  # conversion.jl:73-176
+    rng = np.random.default_rng(21)
+    dims = [3, 4, 2, 4, 3]
+    cores = _rand_tt(rng, [1, 3, 7, 6, 3, 1], dims)
+    full = T.fulltensor(T.TensorTrain([c.copy(order="F") for c in cores]))
+    for kw in (dict(tolerance=1e-13), dict(tolerance=1e-13, maxiter=4), dict(tolerance=1e-3, maxbonddim=4)):
+        tt = T.TensorTrain([c.copy(order="F") for c in cores])
+        tci = T.tensorci2_from_tensortrain(tt, **kw)
+        I, J, ocores, pe, mx = oracle.tensorci2_from_tt(cores, **{k: v for k, v in kw.items()})
+        for a, b in zip(tci.Iset, I):
+            assert np.array_equal(a, b)
+        for a, b in zip(tci.Jset, J):
+            assert np.array_equal(a, b)
+        np.testing.assert_allclose(tci.pivoterrors, pe, rtol=1e-10, atol=1e-13)
+        assert abs(tci.maxsamplevalue - mx) <= 1e-10 * mx
+        for a, b in zip(tci.sitetensors, ocores):
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-10 * mx)
+        assert tci.sitetensors is tt.sitetensors  # conversion.jl:170
+        if "maxbonddim" not in kw:
+            np.testing.assert_allclose(T.fulltensor(T.TensorTrain(tci.sitetensors)), full, rtol=1e-9, atol=1e-11)
+        else:
+            assert max(T.linkdims(tci)) <= 4
+
+
+def test_tt_to_tci2_then_optimize(T):  # test_conversion.jl:76-99 (real-valued)
+    ld = [4] * 4
+    f = T.BuiltinTarget(LORENTZ, [1.0], ld)
+    tci, _, _ = T.crossinterpolate2(f, ld, tolerance=1e-14, maxbonddim=5)
+    tt = T.TensorTrain([c.copy(order="F") for c in tci.sitetensors])
+    tcib = T.tensorci2_from_tensortrain(tt, tolerance=1e-14)
+    assert T.rank(tcib) == 5 and T.linkdims(tcib) == T.linkdims(tci)
+    for v in itertools.product(range(1, 5), repeat=4):
+        assert abs(tcib(list(v)) - tci(list(v))) < 1e-13
+    T.optimize(tcib, f, tolerance=1e-14)
+    for v in itertools.product(range(1, 5), repeat=4):
+        assert abs(tcib(list(v)) - 1.0 / (1.0 + sum(x * x for x in v))) < 1e-13
+
+
 # ------------------------------------------------------- K7 + the driver ----
 def test_globalsearch_matches_oracle(T, oracle):  # test_globalsearch.jl:7-36
     R = 10

@@ -391,3 +391,25 @@ def test_globalsearch_errors(oracle):  # test_globalsearch.jl:7-36 (reported err
     assert len(piv) > 0
     for p, e in zip(piv, errs):
         assert abs(abs(t(p) - oracle.tt_evaluate(res.sitetensors, p)) - e) < 1e-15
+
+
+def test_oracle_tt_to_tci2_conversion(oracle):  # test_conversion.jl:76-92 structure (real-valued)
+    rng = np.random.default_rng(5)
+    bonds, dims = [1, 3, 5, 3, 1], [4, 4, 4, 4]
+    cores = [np.asfortranarray(rng.uniform(-1, 1, (bonds[i], dims[i], bonds[i + 1]))) for i in range(4)]
+
+    def dense(cs):
+        t = cs[0]
+        for c in cs[1:]:
+            t = np.tensordot(t, c, axes=([-1], [0]))
+        return t.reshape(t.shape[1:-1])
+
+    I, J, out, pe, mx = oracle.tensorci2_from_tt(cores, tolerance=1e-14)
+    assert [len(i) for i in I[1:]] == bonds[1:-1] == [len(j) for j in J[:-1]]
+    assert np.abs(dense(out) - dense(cores)).max() < 1e-13
+    assert pe.shape == (max(bonds) + 1,) and pe[-1] == 0.0
+    # the pivots are interpolation points of the converted train: T[I_{b+1}, J_b] is invertible
+    D = dense(cores)
+    for b in range(3):
+        P = np.array([[D[tuple(np.concatenate([i, j]) - 1)] for j in J[b]] for i in I[b + 1]])
+        assert np.linalg.matrix_rank(P) == bonds[b + 1]
