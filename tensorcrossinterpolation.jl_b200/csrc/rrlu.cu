@@ -33,84 +33,7 @@
 
 #include "tci_internal.h"
 
-#define RR_MAX_THREADS 1024
-#define RR_XS_CAP 24576 // doubles of shared memory for the pivot column
-#define RR_U 4          // 16-byte loads in flight per lane in the trailing update
-
-// One candidate record = ONE aligned 16-byte word, written with a single 16-byte store and polled
-// with single 16-byte loads: the phase bit (top bit of rowphase) flips every second step, so a
-// reader can tell a fresh record from the one left two steps earlier in the same parity buffer
-// without a separate flag word and without a second round trip through L2.
-struct __align__(16) RRCand {
-    double val;        // value of the candidate (abs2 is recomputed by the reader)
-    unsigned rowphase; // row | phase << 31
-    int colpos;        // column position, -1: this CTA has no finite candidate
-};
-#define RR_MAXQ 5 // candidate records per lane of the polling warp (G <= 160)
-
-struct RRArgs {
-    double *A;
-    i64 m, n, ld;
-    int maxrank;
-    double reltol, abstol;
-    int leftorth;
-    int *colpos;     // [n]
-    i64 *rowperm;    // [m] 0-based
-    i64 *colperm;    // [n] position -> physical column
-    double *pivvals; // [maxrank]
-    int *pivrows;    // [maxrank] row picked at every step
-    RRCand *cand;    // [2][G], zero initialised
-    double *xbuf;    // [2][G][ldx]
-    i64 ldx;
-    int *result;        // [0] npivot, [1] flags (1: no finite candidate left)
-    double *result_err; // lu.error
-    int xs_in_smem;
-    int maxown;
-    i64 lds; // leading dimension of the shared-memory resident columns (RES mode)
-    long long *dbg; // optional per-phase cycle counters (TCI_RRLU_DEBUG)
-    int dbg_cta;
-};
-
-__device__ __forceinline__ void ld_relaxed_16(const RRCand *p, double &val, unsigned &rowphase, int &colpos)
-{
-    unsigned long long a, b;
-    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    val = __longlong_as_double((long long)a);
-    rowphase = (unsigned)(b & 0xffffffffull);
-    colpos = (int)(b >> 32);
-}
-__device__ __forceinline__ void st_relaxed_16(RRCand *p, double val, unsigned rowphase, int colpos)
-{
-    unsigned long long a = (unsigned long long)__double_as_longlong(val);
-    unsigned long long b = (unsigned long long)rowphase | ((unsigned long long)(unsigned)colpos << 32);
-    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-
-template <bool EXACT> __device__ __forceinline__ double schur(double a, double x, double y)
-{
-    if (EXACT) return __dsub_rn(a, __dmul_rn(x, y)); // matrixlu.jl:132
-    return fma(-x, y, a);
-}
-
-// abs2 value -> ordered integer (0 = no candidate); squares are >= 0 so the bit pattern is monotonic
-__device__ __forceinline__ unsigned long long vbits(double v)
-{
-    return v == -INFINITY ? 0ull : (unsigned long long)__double_as_longlong(v) + 1ull;
-}
-// Warp arg-max with the reference's tie-break: max value bits, then min key.  Four REDUX operations
-// instead of a five-step shuffle tree; every lane returns the winner.
-__device__ __forceinline__ void warp_argmax(unsigned long long &vb, unsigned long long &key)
-{
-    const unsigned hi = (unsigned)(vb >> 32), lo = (unsigned)vb;
-    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-    const bool top = hi == mhi && lo == mlo;
-    const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
-    const unsigned nhi = __reduce_min_sync(0xffffffffu, top ? khi : 0xffffffffu);
-    const unsigned nlo = __reduce_min_sync(0xffffffffu, (top && khi == nhi) ? klo : 0xffffffffu);
-    vb = ((unsigned long long)mhi << 32) | mlo;
-    key = ((unsigned long long)nhi << 32) | nlo;
-}
+#include "rrlu_common.cuh"
 
 #define RR_MARK(ph)                                                      \
     do {                                                                 \
@@ -662,10 +585,18 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         resident = xs_in_smem && smem_need(G, true) <= SMEM_BUDGET;
     }
     if (getenv("TCI_RRLU_NO_RES")) resident = false;
+    // streaming regime: deferred updates (rrlu_lazy.cu) unless disabled
+    const bool no_lazy = getenv("TCI_RRLU_NO_LAZY") != nullptr;
+    // (its tiles are moved by cp.async.bulk: columns must start on 16-byte boundaries)
+    // (measured: 4096^2 13.3 ms deferred vs 10.6 ms in place, 6144^2 22.7 vs 25.1 ms; below ~5000^2 most of the
+    //  matrix stays in the 126 MB L2 and the in-place kernel's smaller fixed cost per pivot wins)
+    const char *lazy_min_env = getenv("TCI_RRLU_LAZY_MIN");
+    const double lazy_min = lazy_min_env ? atof(lazy_min_env) : 28e6;
+    const bool lazy = !resident && !no_lazy && (double)m * (double)n >= lazy_min && (A->ld % 2 == 0) && (reinterpret_cast<size_t>(A->p) % 16 == 0);
     const i64 per_cta = m * ((n + G - 1) / G);
     int T = (m >= 1024 || per_cta >= 32768) ? 1024 : ((m >= 384 || per_cta >= 8192) ? 512 : 256);
     const int maxown = (int)((n + G - 1) / G);
-    size_t smem = smem_need(G, resident);
+    size_t smem = lazy ? rrlu_lazy_smem(maxown, RRLU_LAZY_NB) : smem_need(G, resident);
 
     RRArgs args{};
     args.A = A->p;
@@ -689,7 +620,8 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     DevBuf<char> arena(ctx);
     DevBuf<double> xbuf(ctx);
     TCI_CUDA(ctx, arena.alloc(o_end));
-    if (!(G == 1 && resident)) TCI_CUDA(ctx, xbuf.alloc((size_t)2 * G * args.ldx)); // mode 0 posts nothing
+    args.nxslots = lazy ? RRLU_LAZY_NB + 1 : 2;
+    if (!(G == 1 && resident)) TCI_CUDA(ctx, xbuf.alloc((size_t)args.nxslots * G * args.ldx)); // mode 0 posts nothing
     TCI_CUDA(ctx, cudaMemsetAsync(arena.p, 0, o_piv, ctx->stream));
     args.result = reinterpret_cast<int *>(arena.p);
     args.result_err = reinterpret_cast<double *>(arena.p + 16);
@@ -712,8 +644,9 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     std::vector<char> back(o_back);
     cudaEventRecord(ctx->ev0, ctx->stream);
     {
-        int rc = rrlu_launch(ctx, args, G, T, smem, exact_mode != 0,
-                             G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
+        int rc = lazy ? rrlu_lazy_launch(ctx, args, G, smem, exact_mode != 0)
+                      : rrlu_launch(ctx, args, G, T, smem, exact_mode != 0,
+                                    G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
         if (rc) return rc;
     }
     TCI_CUDA(ctx, cudaMemcpyAsync(back.data(), arena.p, o_back, cudaMemcpyDeviceToHost, ctx->stream));
@@ -730,6 +663,13 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     if (dbgenv) {
         long long h[16];
         cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+        if (lazy)
+            fprintf(stderr,
+                    "[rrlu lazy dbg] m=%lld n=%lld r=%d G=%d cycles/pivot: wait+reduce %lld | bookkeeping+y %lld | pass %lld | "
+                    "pass imbalance %lld | special+commit %lld | blockreduce %lld | post %lld\n",
+                    (long long)m, (long long)n, r, G, h[0] / (r + 1), h[1] / (r + 1), h[2] / (r + 1), h[3] / (r + 1),
+                    h[4] / (r + 1), h[5] / (r + 1), h[6] / (r + 1));
+        else
         fprintf(stderr,
                 "[rrlu dbg] m=%lld n=%lld r=%d G=%d T=%d res=%d cycles/pivot: wait+reduce %lld (poll %lld acqfence %lld "
                 "payload %lld) | swap+x %lld | ys+L %lld | update %lld | blockreduce %lld | post %lld | fence %lld\n",

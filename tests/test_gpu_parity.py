@@ -250,6 +250,52 @@ def test_rrlu_streaming_forced(T, oracle, m, n, r, monkeypatch):
                         oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo))
 
 
+LAZY_SHAPES = [(2, 3, 2), (17, 33, 9), (64, 64, 20), (100, 37, 30), (130, 257, 41), (300, 300, 64), (513, 700, 47),
+               (1000, 130, 33), (64, 3000, 21), (2100, 2050, 24)]
+
+
+@pytest.mark.parametrize("m,n,r", LAZY_SHAPES)
+def test_rrlu_deferred_update_kernel(T, oracle, m, n, r, monkeypatch):
+    """rrlu_lazy.cu (Schur updates deferred, committed every 4 pivots; normally used from ~6000^2 up) forced at
+    small sizes: block boundaries, ranks that are not multiples of the block, row swaps inside a block."""
+    monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
+    monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
+    A = lowrank_matrix(m, n, r, seed=m * 1000 + n)
+    for lo in (True, False):
+        assert_lu_equal(T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo),
+                        oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo))
+    for mr in (1, 2, 3, 4, 5):  # stop inside / at the end of the first block
+        if mr <= min(m, n):
+            assert_lu_equal(T.rrlu(A, maxrank=mr), oracle.rrlu(A, maxrank=mr))
+    assert_lu_equal(T.rrlu(A, reltol=1e-6), oracle.rrlu(A, reltol=1e-6))  # stop rule with pending updates
+
+
+def test_rrlu_deferred_update_kernel_special_cases(T, oracle, monkeypatch):
+    monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
+    monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
+    rng = np.random.default_rng(99)
+    # full rank (every row and column becomes a pivot; the last block is partial)
+    for m, n in ((50, 50), (121, 83), (83, 121)):
+        A = rng.random((m, n))
+        for lo in (True, False):
+            assert_lu_equal(T.rrlu(A, leftorthogonal=lo), oracle.rrlu(A, leftorthogonal=lo))
+    # exact ties and exact zeros: small-integer matrix (first maximum in column-major order must win)
+    A = rng.integers(-3, 4, (90, 70)).astype(np.float64)
+    assert_lu_equal(T.rrlu(A), oracle.rrlu(A))
+    assert_lu_equal(T.rrlu(A, leftorthogonal=False), oracle.rrlu(A, leftorthogonal=False))
+    # pivots already on the diagonal (no row swaps) and in reverse order (every pivot swaps)
+    D = np.diag(np.arange(40, 0, -1.0))
+    assert_lu_equal(T.rrlu(D), oracle.rrlu(D))
+    assert_lu_equal(T.rrlu(D[::-1].copy()), oracle.rrlu(D[::-1].copy()))
+    # NaN in the matrix: never selected while finite entries remain (matrixlu.jl:16-29), error at the end
+    B = rng.random((60, 60))
+    B[7, 9] = np.nan
+    with pytest.raises(T.TCIError):
+        T.rrlu(B)
+    lu = T.rrlu(rng.random((6, 5000)), maxrank=4)  # more CTAs than rows
+    assert lu.npivot == 4
+
+
 @pytest.mark.parametrize("m,n", [(50, 50), (120, 80), (257, 300)])
 def test_rrlu_full_rank_random(T, oracle, m, n):  # benchmark/rrlu.jl:12-17 shape
     A = np.random.default_rng(m).random((m, n))
