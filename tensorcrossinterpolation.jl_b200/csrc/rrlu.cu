@@ -27,6 +27,7 @@
 //
 // HBM traffic is the algorithmic 16 B per trailing element per pivot (one read, one
 // write); matrices up to ~30 MB live in shared memory for the whole factorisation.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -585,6 +586,8 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         resident = xs_in_smem && smem_need(G, true) <= SMEM_BUDGET;
     }
     if (getenv("TCI_RRLU_NO_RES")) resident = false;
+    if (const char *ge = getenv("TCI_RRLU_G")) // experiments only
+        if (!resident && atoi(ge) >= 1 && atoi(ge) <= G) G = atoi(ge);
     // streaming regime: deferred updates (rrlu_lazy.cu) unless disabled
     const bool no_lazy = getenv("TCI_RRLU_NO_LAZY") != nullptr;
     // (its tiles are moved by cp.async.bulk: columns must start on 16-byte boundaries)
@@ -592,10 +595,48 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     //  matrix stays in the 126 MB L2 and the in-place kernel's smaller fixed cost per pivot wins)
     const char *lazy_min_env = getenv("TCI_RRLU_LAZY_MIN");
     const double lazy_min = lazy_min_env ? atof(lazy_min_env) : 28e6;
-    const bool lazy = !resident && !no_lazy && (double)m * (double)n >= lazy_min && (A->ld % 2 == 0) && (reinterpret_cast<size_t>(A->p) % 16 == 0);
+    const bool lazy = !resident && !no_lazy && (double)m * (double)n >= lazy_min &&
+                      rrlu_lazy_smem((int)((n + G - 1) / G) + 8, RRLU_LAZY_NB) <= SMEM_BUDGET && (A->ld % 2 == 0) && (reinterpret_cast<size_t>(A->p) % 16 == 0);
     const i64 per_cta = m * ((n + G - 1) / G);
     int T = (m >= 1024 || per_cta >= 32768) ? 1024 : ((m >= 384 || per_cta >= 8192) ? 512 : 256);
-    const int maxown = (int)((n + G - 1) / G);
+    int maxown = (int)((n + G - 1) / G);
+    // Deferred-update kernel on the full grid: the SMs do not stream from HBM equally fast (measured spread
+    // of the pass time per SM: -13% .. +10%, stable per %smid), and every pivot waits for the slowest CTA.
+    // Columns are therefore dealt in proportion to the speeds learned from earlier factorisations on this
+    // context.  The result does not depend on who owns which column.
+    const bool ranked = lazy && G == ctx->sm_count && G <= 256 && !getenv("TCI_RRLU_NO_BALANCE");
+    const bool use_speeds = getenv("TCI_RRLU_BALANCE") != nullptr; // (see the note on read / write speeds below)
+    std::vector<int> h_colmap, h_colcnt;
+    if (ranked && getenv("TCI_RRLU_TEST_SPEEDS")) { // tests: a strongly uneven, reproducible speed table
+        for (int q = 0; q < G; ++q) ctx->sm_speed[q] = 0.7 + 0.6 * ((q * 37) % G) / (double)G;
+        ctx->sm_speed_valid = true;
+    }
+    if (ranked && ctx->sm_speed_valid && (use_speeds || getenv("TCI_RRLU_TEST_SPEEDS"))) {
+        double tot = 0.0;
+        for (int q = 0; q < G; ++q) tot += ctx->sm_speed[q];
+        h_colcnt.assign(G, 0);
+        std::vector<std::pair<double, int>> rem(G);
+        i64 given = 0;
+        for (int q = 0; q < G; ++q) {
+            const double share = (double)n * ctx->sm_speed[q] / tot;
+            h_colcnt[q] = (int)share;
+            rem[q] = {share - h_colcnt[q], q};
+            given += h_colcnt[q];
+        }
+        std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &x, const std::pair<double, int> &y) {
+            return x.first > y.first || (x.first == y.first && x.second < y.second);
+        });
+        for (i64 k = 0; k < n - given; ++k) h_colcnt[rem[k % G].second]++;
+        maxown = *std::max_element(h_colcnt.begin(), h_colcnt.end());
+        h_colmap.assign((size_t)G * maxown, 0);
+        std::vector<int> fill(G, 0);
+        int q = 0;
+        for (i64 j = 0; j < n; ++j) { // round-robin over the CTAs that still have room
+            while (fill[q] >= h_colcnt[q]) q = (q + 1) % G;
+            h_colmap[(size_t)q * maxown + fill[q]++] = (int)j;
+            q = (q + 1) % G;
+        }
+    }
     size_t smem = lazy ? rrlu_lazy_smem(maxown, RRLU_LAZY_NB) : smem_need(G, resident);
 
     RRArgs args{};
@@ -616,7 +657,10 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     // what comes back in ONE device-to-host copy) [colpos][pivrows]; the posted columns are separate.
     const size_t o_cand = 32, o_piv = o_cand + (size_t)2 * G * sizeof(RRCand), o_rp = o_piv + (size_t)mr * 8,
                  o_cp = o_rp + (size_t)m * 8, o_back = o_cp + (size_t)n * 8, o_pos = o_back,
-                 o_prow = o_pos + (((size_t)n * 4 + 15) & ~(size_t)15), o_end = o_prow + (size_t)mr * 4 + 16;
+                 o_prow = o_pos + (((size_t)n * 4 + 15) & ~(size_t)15),
+                 o_rank = (o_prow + (size_t)mr * 4 + 31) & ~(size_t)15, // [startbar 16 B][smids G][passstats 2G]
+                 o_stat = (o_rank + 16 + (size_t)G * 4 + 15) & ~(size_t)15, o_cmap = o_stat + (size_t)2 * G * 8,
+                 o_end = o_cmap + (h_colmap.size() + h_colcnt.size()) * 4 + 16;
     DevBuf<char> arena(ctx);
     DevBuf<double> xbuf(ctx);
     TCI_CUDA(ctx, arena.alloc(o_end));
@@ -632,18 +676,35 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     args.colpos = reinterpret_cast<int *>(arena.p + o_pos);
     args.pivrows = reinterpret_cast<int *>(arena.p + o_prow);
     args.xbuf = xbuf.p;
+    if (ranked) {
+        TCI_CUDA(ctx, cudaMemsetAsync(arena.p + o_rank, 0, o_cmap - o_rank, ctx->stream));
+        args.startbar = reinterpret_cast<unsigned *>(arena.p + o_rank);
+        args.smids = reinterpret_cast<int *>(arena.p + o_rank + 16);
+        args.passstats = reinterpret_cast<long long *>(arena.p + o_stat);
+        if (!h_colmap.empty()) {
+            TCI_CUDA(ctx, cudaMemcpyAsync(arena.p + o_cmap, h_colmap.data(), h_colmap.size() * 4, cudaMemcpyHostToDevice,
+                                          ctx->stream));
+            TCI_CUDA(ctx, cudaMemcpyAsync(arena.p + o_cmap + h_colmap.size() * 4, h_colcnt.data(), h_colcnt.size() * 4,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+            args.colmap = reinterpret_cast<const int *>(arena.p + o_cmap);
+            args.colcnt = reinterpret_cast<const int *>(arena.p + o_cmap + h_colmap.size() * 4);
+        }
+    }
 
     DevBuf<long long> dbg(ctx);
     const char *dbgenv = getenv("TCI_RRLU_DEBUG");
     if (dbgenv) {
-        TCI_CUDA(ctx, dbg.alloc(16));
-        TCI_CUDA(ctx, cudaMemsetAsync(dbg.p, 0, 16 * sizeof(long long), ctx->stream));
+        TCI_CUDA(ctx, dbg.alloc(16 + 41 * (size_t)G));
+        TCI_CUDA(ctx, cudaMemsetAsync(dbg.p, 0, (16 + 41 * (size_t)G) * sizeof(long long), ctx->stream));
         args.dbg = dbg.p;
         args.dbg_cta = atoi(dbgenv) % G;
     }
     std::vector<char> back(o_back);
     cudaEventRecord(ctx->ev0, ctx->stream);
     {
+        if (getenv("TCI_RRLU_DEBUG"))
+            fprintf(stderr, "[rrlu launch] m=%lld n=%lld G=%d lazy=%d ranked=%d maxown=%d smem=%zu\n", (long long)m,
+                    (long long)n, G, (int)lazy, (int)ranked, maxown, smem);
         int rc = lazy ? rrlu_lazy_launch(ctx, args, G, smem, exact_mode != 0)
                       : rrlu_launch(ctx, args, G, T, smem, exact_mode != 0,
                                     G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
@@ -657,12 +718,72 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_RRLU_KERNEL] += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stage_ms[ST_RRLU] += ms;
     }
+    if (ranked) { // learn the per-SM streaming speed from this run (tiles per cycle, normalised to mean 1)
+        std::vector<long long> st(2 * (size_t)G);
+        TCI_CUDA(ctx, cudaMemcpy(st.data(), arena.p + o_stat, st.size() * 8, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        double mean = 0.0;
+        std::vector<double> sp(G);
+        for (int q = 0; q < G; ++q) {
+            if (st[q] <= 0 || st[G + q] < 4096) ok = false; // too little work to say anything
+            sp[q] = ok ? (double)st[G + q] / (double)st[q] : 1.0;
+            mean += sp[q];
+        }
+        mean /= G;
+        if (ok) {
+            for (int q = 0; q < G; ++q) {
+                double v = sp[q] / mean;
+                v = v < 0.7 ? 0.7 : (v > 1.3 ? 1.3 : v);
+                ctx->sm_speed[q] = ctx->sm_speed_valid ? 0.5 * (ctx->sm_speed[q] + v) : v;
+            }
+            ctx->sm_speed_valid = true;
+        }
+    }
     const int *res = reinterpret_cast<const int *>(back.data());
     const double lu_error = *reinterpret_cast<const double *>(back.data() + 16);
     const int r = res[0];
     if (dbgenv) {
         long long h[16];
         cudaMemcpy(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+        if (lazy && getenv("TCI_RRLU_DEBUG_CTAS")) {
+            std::vector<long long> pc(2 * (size_t)G);
+            cudaMemcpy(pc.data(), dbg.p + 16, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[rrlu lazy pass cycles/pivot per CTA (cta:smid:cycles)]");
+            for (int q = 0; q < G; ++q) fprintf(stderr, " %d:%lld:%lld", q, pc[G + q], pc[q] / (r + 1));
+            fprintf(stderr, "\n");
+            {
+                std::vector<long long> ts(32 * (size_t)G);
+                cudaMemcpy(ts.data(), dbg.p + 16 + 9 * G, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                for (int pz = 0; pz < 16 && pz + 16 < r; ++pz) {
+                    const long long *b = &ts[(size_t)pz * 2 * G], *e = b + G;
+                    long long b0 = *std::min_element(b, b + G), b1 = *std::max_element(b, b + G);
+                    long long e0 = *std::min_element(e, e + G), e1 = *std::max_element(e, e + G);
+                    long long dmin = 1LL << 60, dmax = 0;
+                    for (int q = 0; q < G; ++q) {
+                        dmin = std::min(dmin, e[q] - b[q]);
+                        dmax = std::max(dmax, e[q] - b[q]);
+                    }
+                    fprintf(stderr, "[rrlu lazy pivot %d] pass start spread %lld ns, end spread %lld ns, first start -> last end %lld ns, "
+                                    "per-CTA duration min %lld max %lld ns, last-ending cta %d\n",
+                            pz + 16, b1 - b0, e1 - e0, e1 - b0, dmin, dmax, (int)(std::max_element(e, e + G) - e));
+                }
+            }
+            std::vector<long long> ph(7 * (size_t)G);
+            cudaMemcpy(ph.data(), dbg.p + 16 + 2 * G, ph.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            const char *nm[7] = {"wait", "book", "pass", "imbal", "special", "reduce", "post"};
+            for (int k = 0; k < 7; ++k) {
+                long long mn = ph[(size_t)k * G], mx = mn, sum = 0;
+                int amx = 0;
+                for (int q = 0; q < G; ++q) {
+                    const long long v = ph[(size_t)k * G + q];
+                    sum += v;
+                    if (v < mn) mn = v;
+                    if (v > mx) mx = v, amx = q;
+                }
+                fprintf(stderr, "[rrlu lazy phase %-8s cycles/pivot over CTAs] min %lld mean %lld max %lld (cta %d)\n", nm[k],
+                        mn / (r + 1), sum / G / (r + 1), mx / (r + 1), amx);
+            }
+        }
         if (lazy)
             fprintf(stderr,
                     "[rrlu lazy dbg] m=%lld n=%lld r=%d G=%d cycles/pivot: wait+reduce %lld | bookkeeping+y %lld | pass %lld | "

@@ -41,6 +41,12 @@ struct RRArgs {
     long long *dbg; // optional per-phase cycle counters (TCI_RRLU_DEBUG)
     int dbg_cta;
     int nxslots; // lazy kernel: xbuf is [nxslots][G][ldx]
+    // lazy kernel, speed-weighted column ownership (all null: CTA g owns columns g, g+G, ...)
+    const int *colmap;    // [G][maxown] physical column of (logical CTA, own slot)
+    const int *colcnt;    // [G] columns owned by the logical CTA
+    int *smids;           // [G] zeroed; smid+1 of every CTA, to rank the CTAs by the SM they run on
+    unsigned *startbar;   // zeroed
+    long long *passstats; // [2][G] cycles spent in the streaming passes, column tiles streamed
 };
 
 __device__ __forceinline__ void ld_relaxed_16(const RRCand *p, double &val, unsigned &rowphase, int &colpos)

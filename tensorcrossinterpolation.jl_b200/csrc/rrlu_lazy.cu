@@ -26,7 +26,12 @@
 #define RL_THREADS 512
 #define RL_R 2               // 16-byte loads per lane per column tile
 #define RL_RG (RL_R * 64)    // rows of a column tile
-#define RL_S 8               // ring stages (1 KB tiles in flight) per warp
+// ring stages (1 KB tiles in flight) per warp.  Measured at 8192^2 r=1024 / 16384^2 r=128 (ms): 4: 140.5 / 66.6,
+// 6: 140.3 / 65.7, 8: 142.3 / 69.8, 12: 149.1 / 82.1 -- deeper queues cost bandwidth instead of hiding latency.
+#ifndef RL_S
+#define RL_S 6
+#endif
+
 
 
 // One active column as the streaming pass sees it (rebuilt in entry order before every pass).
@@ -83,17 +88,16 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned addr)
 
 // The tile stream of one warp in one pass: for every work item (RL_RG rows x a chunk of active columns) first the
 // nd pending pivot columns x_i restricted to those rows, then the chunk's column tiles.  The producer side
-// of the ring walks this stream RL_S tiles ahead of the consumer.
+// of the ring walks this stream RL_S tiles ahead of the consumer.  All source pointers come from one shared
+// table: entries [-nd, 0) are the pivot columns, entries [0, nact) the active columns.
 struct RLStream {
     // pass constants
-    const RLEnt *ent;
-    const double *const *xptr;
-    int nd, m, i0, ntr, CH, nact, nitems, step;
-    bool backward;
-    // ring
-    unsigned ring0, bar0, pcnt, ccnt;
-    // producer cursor
-    int pt, pj, p_row, p_c0, p_cnt;
+    unsigned tab;  // shared address of table entry 0 (16-byte entries, pointer first)
+    int nd, m, i0, ntr, CH, nact, nitems, step, estep; // estep = +1 / -1: direction of the sweep
+    // ring: shared addresses of this warp's stage 0 / barrier 0, consumer and producer stage, consumer parity
+    unsigned ring0, bar0, cs, cpar, ps;
+    // producer cursor: item, tile within the item, item length, current table entry, row offset, bytes
+    int pt, pj, p_len, p_e, p_efirst, p_row;
     unsigned p_bytes;
 
     __device__ __forceinline__ void item(int t, int &row, int &c0, int &cnt) const
@@ -106,48 +110,52 @@ struct RLStream {
     __device__ __forceinline__ void p_set()
     {
         if (pt >= 0 && pt < nitems) {
-            item(pt, p_row, p_c0, p_cnt);
+            int c0, cnt;
+            item(pt, p_row, c0, cnt);
             const int rows = (m - p_row < RL_RG) ? m - p_row : RL_RG;
             p_bytes = ((unsigned)rows * 8u + 15u) & ~15u;
-        }
+            p_len = nd + cnt;
+            p_efirst = estep > 0 ? c0 : c0 + cnt - 1;
+            p_e = nd ? -nd : p_efirst;
+            pj = 0;
+        } else
+            p_len = 0; // end of the stream
     }
     __device__ __forceinline__ void produce(int lane)
     {
-        if (pt < 0 || pt >= nitems) return;
+        if (p_len == 0) return;
         if (lane == 0) {
-            const double *src;
-            if (pj < nd)
-                src = xptr[pj] + p_row;
-            else {
-                const int idx = pj - nd;
-                src = ent[backward ? p_c0 + p_cnt - 1 - idx : p_c0 + idx].ptr + p_row;
-            }
-            const unsigned stage = pcnt % RL_S;
-            mbar_expect_tx(bar0 + 8u * stage, p_bytes);
-            bulk_g2s(ring0 + stage * (RL_RG * 8u), src, p_bytes, bar0 + 8u * stage);
+            unsigned long long base;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(tab + 16u * (unsigned)p_e) : "memory");
+            const unsigned bar = bar0 + (ps << 3);
+            mbar_expect_tx(bar, p_bytes);
+            bulk_g2s(ring0 + (ps << 10), reinterpret_cast<const double *>(base) + p_row, p_bytes, bar);
         }
-        ++pcnt;
-        if (++pj == nd + p_cnt) {
-            pj = 0;
+        ps = (ps + 1u == RL_S) ? 0u : ps + 1u;
+        ++pj;
+        p_e = (pj < nd) ? p_e + 1 : (pj == nd ? p_efirst : p_e + estep);
+        if (pj == p_len) {
             pt += step;
             p_set();
         }
     }
-    // wait for the next tile; returns the shared address of this lane's first 16 bytes
-    __device__ __forceinline__ unsigned acquire(int lane)
+    // wait for the next tile; returns the shared address of its first byte
+    __device__ __forceinline__ unsigned acquire()
     {
-        const unsigned stage = ccnt % RL_S, parity = (ccnt / RL_S) & 1u;
-        while (!mbar_try_wait(bar0 + 8u * stage, parity)) {}
-        return ring0 + stage * (RL_RG * 8u) + 16u * lane;
+        const unsigned bar = bar0 + (cs << 3);
+        while (!mbar_try_wait(bar, cpar)) {}
+        return ring0 + (cs << 10);
     }
-    // the lane has its values in registers: hand the stage back and keep the ring full
+    // the lanes have their values in registers: hand the stage back and keep the ring full
     __device__ __forceinline__ void release(int lane)
     {
         __syncwarp();
-        ++ccnt;
+        cs = (cs + 1u == RL_S) ? 0u : cs + 1u;
+        cpar ^= (cs == 0u) ? 1u : 0u;
         produce(lane);
     }
 };
+static_assert(RL_RG * 8 == 1024, "ring addressing uses shifts");
 
 // The column tiles of one work item.  The lane's 2*RL_R rows are fixed, so the pending pivot columns x_i live
 // in registers; per column only the tile itself and the y_i move.  NDV >= nd updates are always applied:
@@ -156,11 +164,11 @@ struct RLStream {
 // Arg-max: the squares are non-negative, so their high words order them coarsely; the exact (value, column
 // position, row) comparison of matrixlu.jl:16-29 only runs when a tile reaches the lane's current best.
 template <bool EXACT, int NB, int NDV, bool COMMIT>
-__device__ __forceinline__ void rl_item(RLStream &st, const RLEnt *__restrict__ ent, const double *__restrict__ yE,
-                                        int c0, int cnt, bool backward, int rbase, int m, unsigned negm, int lane,
-                                        const double2 (&xr)[NB][RL_R], unsigned long long &bvb, int &bhi, int &bcpv,
-                                        int &browv)
+__device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, int cnt, int rbase, int m, unsigned negm,
+                                        int lane, const double2 (&xr)[NB][RL_R], unsigned long long &bvb, int &bhi,
+                                        int &bcpv, int &browv)
 {
+    static_assert(NB == 4 && (NDV == 2 || NDV == 4), "y_i are fetched as 16-byte pairs");
     int nmw[2 * RL_R];
     bool inb[RL_R];
 #pragma unroll
@@ -174,19 +182,32 @@ __device__ __forceinline__ void rl_item(RLStream &st, const RLEnt *__restrict__ 
         asm volatile("" : "+r"(ib));
         inb[u] = ib != 0;
     }
-#pragma unroll 2
-    for (int idx = 0; idx < cnt; ++idx) {
-        const int e = backward ? c0 + cnt - 1 - idx : c0 + idx;
-        const RLEnt en = ent[e];
-        double y[NDV > 0 ? NDV : 1];
-#pragma unroll
-        for (int i = 0; i < NDV; ++i) y[i] = yE[e * NB + i];
-        const unsigned sa = st.acquire(lane);
+    unsigned lane16 = 16u * (unsigned)lane;
+    asm volatile("" : "+r"(lane16));
+    int e = efirst;
+#pragma unroll 1
+    for (int idx = 0; idx < cnt; ++idx, e += st.estep) {
+        unsigned long long cbase;
+        int cp;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cbase) : "r"(st.tab + 16u * (unsigned)e) : "memory");
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cp) : "r"(st.tab + 16u * (unsigned)e + 8u) : "memory");
+        double y[NDV];
+        {
+            const double2 y01 = lds_f64x2(yEs + 32u * (unsigned)e);
+            y[0] = y01.x;
+            y[1] = y01.y;
+            if (NDV == 4) {
+                const double2 y23 = lds_f64x2(yEs + 32u * (unsigned)e + 16u);
+                y[2] = y23.x;
+                y[3] = y23.y;
+            }
+        }
+        const unsigned sa = st.acquire() + lane16;
         double2 d[RL_R];
 #pragma unroll
         for (int u = 0; u < RL_R; ++u) d[u] = lds_f64x2(sa + 512u * u);
         st.release(lane);
-        double *const cptr = en.ptr + rbase;
+        double *const cptr = reinterpret_cast<double *>(cbase) + rbase;
         double q[2 * RL_R];
         int tmax = -1;
 #pragma unroll
@@ -215,9 +236,9 @@ __device__ __forceinline__ void rl_item(RLStream &st, const RLEnt *__restrict__ 
                 }
             }
             const int trow = rbase + (tj >> 1) * 64 + (tj & 1);
-            if (tb > bvb || (tb == bvb && tb != 0ull && (en.cp < bcpv || (en.cp == bcpv && trow < browv)))) {
+            if (tb > bvb || (tb == bvb && tb != 0ull && (cp < bcpv || (cp == bcpv && trow < browv)))) {
                 bvb = tb;
-                bcpv = en.cp;
+                bcpv = cp;
                 browv = trow;
                 bhi = (int)((tb - 1ull) >> 32);
             }
@@ -228,30 +249,56 @@ __device__ __forceinline__ void rl_item(RLStream &st, const RLEnt *__restrict__ 
 template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_THREADS, 1) k_rrlu_lazy(RRArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int G = gridDim.x, g = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+    const int G = gridDim.x, T = blockDim.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int m = (int)a.m, n = (int)a.n;
     const int MO = a.maxown;
+    // Logical CTA index.  With speed-weighted ownership the CTAs are ranked by the SM they run on (one CTA per
+    // SM), so that a table indexed by the rank always addresses the same SM; otherwise it is blockIdx.x.
+    int g = blockIdx.x;
+    if (a.smids) {
+        __shared__ int sh_rank;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (tid == 0) {
+            sh_rank = 0;
+            a.smids[blockIdx.x] = (int)smid + 1;
+            __threadfence();
+            atomicAdd(a.startbar, 1u);
+            while (*reinterpret_cast<volatile unsigned *>(a.startbar) < (unsigned)G) {}
+            __threadfence();
+        }
+        __syncthreads();
+        int below = 0;
+        for (int b = tid; b < G; b += T) {
+            const int sb = __ldcg(a.smids + b);
+            below += (sb < (int)smid + 1 || (sb == (int)smid + 1 && b < (int)blockIdx.x)) ? 1 : 0;
+        }
+        if (below) atomicAdd(&sh_rank, below);
+        __syncthreads();
+        g = sh_rank;
+    }
 
     double *ys = reinterpret_cast<double *>(smem_raw); // [NB][MO]: pivot row j in the own column slot o
     int *acto = reinterpret_cast<int *>(ys + (size_t)NB * MO);
     int *actp = acto + MO;    // position of the active entry
     int *slotpos = actp + MO; // position of every own slot
-    RLEnt *ent = reinterpret_cast<RLEnt *>(smem_raw + (((size_t)NB * MO * 8 + (size_t)3 * MO * 4 + 15) & ~(size_t)15));
+    int *pcol = slotpos + MO; // physical column of every own slot
+    // table of streamed columns: entries [-NB, 0) pending pivot columns, [0, MO) active columns in entry order
+    RLEnt *ent = reinterpret_cast<RLEnt *>(smem_raw + (((size_t)NB * MO * 8 + (size_t)4 * MO * 4 + 15) & ~(size_t)15)) + NB;
     double *yE = reinterpret_cast<double *>(ent + MO); // [MO][NB] pivot-row values in entry order
     unsigned char *ringp = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<size_t>(yE + (size_t)NB * MO) + 127) & ~(size_t)127); // [nwarps][RL_S][RL_RG] doubles
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ringp + (size_t)nwarps * RL_S * RL_RG * 8);
-    double *const W = a.A + (size_t)a.ld * g;
-    const i64 wstride = a.ld * G;
-#define RL_COL(o) (W + (size_t)wstride * (o))
+#define RL_COL(o) (a.A + (size_t)a.ld * pcol[o])
 
     long long tmark = clock64();
+    long long pass_total = 0, pass_t0 = 0, pass_work = 0;
     __shared__ long long dbg_acc[8];
     if (tid < 8) dbg_acc[tid] = 0;
 #define RL_MARK(ph)                                    \
     do {                                               \
-        if (a.dbg && g == a.dbg_cta && tid == 0) {     \
+        if (a.dbg && tid == 0) {                       \
             long long now__ = clock64();               \
             dbg_acc[ph] += now__ - tmark;              \
             tmark = now__;                             \
@@ -267,9 +314,10 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
     __shared__ double pval[NB];
     __shared__ const double *xptr[NB]; // posted pivot columns of the pending pivots (indexed by base row)
 
-    const int nown = (g < n) ? (n - g + G - 1) / G : 0;
+    const int nown = a.colmap ? a.colcnt[g] : ((g < n) ? (n - g + G - 1) / G : 0);
     _Pragma("unroll 1") for (int e = tid; e < nown; e += T) {
-        const int j = g + e * G;
+        const int j = a.colmap ? a.colmap[(size_t)g * MO + e] : g + e * G;
+        pcol[e] = j;
         acto[e] = e;
         actp[e] = j;
         slotpos[e] = j;
@@ -285,7 +333,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
     RLStream st;
     st.ring0 = smem_u32(ringp + (size_t)warp * RL_S * RL_RG * 8);
     st.bar0 = smem_u32(mbar + warp * RL_S);
-    st.pcnt = st.ccnt = 0u;
+    st.cs = st.cpar = st.ps = 0u;
     if (lane == 0) {
         for (int k = 0; k < RL_S; ++k) mbar_init(st.bar0 + 8u * k, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -418,7 +466,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                     } else if (actp[e] == s) {
                         actp[e] = pcpos;
                         slotpos[acto[e]] = pcpos;
-                        a.colpos[g + acto[e] * G] = pcpos;
+                        a.colpos[pcol[acto[e]]] = pcpos;
                     }
                 }
                 __syncthreads();
@@ -427,7 +475,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                     const int oslot = acto[rem];
                     __syncthreads();
                     if (tid == 0) {
-                        const int jp = g + oslot * G;
+                        const int jp = pcol[oslot];
                         a.colpos[jp] = s;
                         a.colperm[s] = jp;
                         slotpos[oslot] = s;
@@ -463,6 +511,12 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
         }
 
         RL_MARK(1); // bookkeeping + pivot row
+        if (tid == 0) pass_t0 = clock64();
+        if (a.dbg && tid == 0 && s >= 16 && s < 32) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            a.dbg[16 + 9 * G + (size_t)(s - 16) * 2 * G + g] = (long long)gt;
+        }
         const int lo = k0 + nd; // first trailing position
         const bool commit = fin ? (nd > 0) : (nd == NB);
         unsigned long long bvb = 0ull;
@@ -479,6 +533,12 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                 ent[e] = en;
                 for (int i = 0; i < NB; ++i) yE[e * NB + i] = (i < nd) ? ys[i * MO + o] : 0.0;
             }
+            if (tid < nd) { // the pending pivot columns precede the active columns in the stream table
+                RLEnt en;
+                en.ptr = const_cast<double *>(xptr[tid]);
+                en.cp = en.slot = -1;
+                ent[tid - nd] = en;
+            }
             __syncthreads();
             int pr_[NB];
 #pragma unroll
@@ -486,18 +546,27 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
             int bhi = -1;
             const int i0 = lo & ~1;
             const int ntr = (m - i0 + RL_RG - 1) / RL_RG;
-            int nch = (8 * nwarps + ntr - 1) / ntr;
-            const int nchmax = (nact + 5) / 6;
-            nch = nch > nchmax ? nchmax : nch;
-            nch = nch < 1 ? 1 : nch;
+            // Split the active columns into nch chunks so that the ntr*nch items deal evenly over the warps: every
+            // item costs its chunk plus the nd pivot-column tiles it has to pull through the ring first.
+            int nch = 1;
+            {
+                int best = 0x7fffffff;
+                const int nchmax = (nact + 5) / 6;
+                for (int c = 1; c <= 8 && c <= nchmax; ++c) {
+                    const int cost = ((ntr * c + nwarps - 1) / nwarps) * ((nact + c - 1) / c + nd + 1);
+                    if (cost < best) {
+                        best = cost;
+                        nch = c;
+                    }
+                }
+            }
             const int CH = (nact + nch - 1) / nch;
             nch = (nact + CH - 1) / CH;
             const int nitems = ntr * nch;
             const bool backward = (s & 1);
             int t = warp;
             if (backward && nitems > warp) t = warp + ((nitems - 1 - warp) / nwarps) * nwarps;
-            st.ent = ent;
-            st.xptr = xptr;
+            st.tab = smem_u32(ent);
             st.nd = nd;
             st.m = m;
             st.i0 = i0;
@@ -506,10 +575,10 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
             st.nact = nact;
             st.nitems = nitems;
             st.step = backward ? -nwarps : nwarps;
-            st.backward = backward;
+            st.estep = backward ? -1 : 1;
             st.pt = t;
-            st.pj = 0;
             st.p_set();
+            const unsigned yEs = smem_u32(yE);
 #pragma unroll 1
             for (int k = 0; k < RL_S; ++k) st.produce(lane); // fill the ring
 #pragma unroll 1
@@ -536,7 +605,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     if (i < nd) { // the x_i tile of this item comes through the ring first
-                        const unsigned sa = st.acquire(lane);
+                        const unsigned sa = st.acquire() + 16u * (unsigned)lane;
 #pragma unroll
                         for (int u = 0; u < RL_R; ++u) {
                             const double2 xx = lds_f64x2(sa + 512u * u);
@@ -549,16 +618,26 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                         for (int u = 0; u < RL_R; ++u) xr[i][u] = make_double2(0.0, 0.0);
                     }
                 }
+                const int efirst = backward ? c0 + cnt - 1 : c0;
                 if (nd <= NB / 2)
-                    rl_item<EXACT, NB, NB / 2, false>(st, ent, yE, c0, cnt, backward, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, NB / 2, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
                 else if (!commit)
-                    rl_item<EXACT, NB, NB, false>(st, ent, yE, c0, cnt, backward, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, NB, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
                 else
-                    rl_item<EXACT, NB, NB, true>(st, ent, yE, c0, cnt, backward, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, NB, true>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
             }
         }
         RL_MARK(2); // streaming pass (this warp)
         __syncthreads();
+        if (a.dbg && tid == 0 && s >= 16 && s < 32) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            a.dbg[16 + 9 * G + (size_t)(s - 16) * 2 * G + G + g] = (long long)gt;
+        }
+        if (tid == 0 && !fin) {
+            pass_total += clock64() - pass_t0;
+            pass_work += (long long)nact * ((m - (lo & ~1) + RL_RG - 1) / RL_RG) * (commit ? 2 : 1);
+        }
         RL_MARK(3); // wait for the other warps
 
         // ---- 6. special rows: displaced rows take part in the arg-max; at a commit every special row of
@@ -723,6 +802,17 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
         }
     }
     if (a.dbg && g == a.dbg_cta && tid < 8) a.dbg[tid] = dbg_acc[tid];
+    if (a.passstats && tid == 0) {
+        a.passstats[g] = pass_total;
+        a.passstats[G + g] = pass_work;
+    }
+    if (a.dbg && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.dbg[16 + g] = pass_total;
+        a.dbg[16 + G + g] = smid;
+        for (int k = 0; k < 7; ++k) a.dbg[16 + (2 + k) * G + g] = dbg_acc[k];
+    }
 
     __syncthreads();
     { // NaN scan of the L and U parts of the own columns (matrixlu.jl:164-169): bit 0 L, bit 1 U
@@ -739,7 +829,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
     }
     {
         const int nact = sh_nact;
-        _Pragma("unroll 1") for (int e = tid; e < nact; e += T) a.colperm[actp[e]] = g + acto[e] * G;
+        _Pragma("unroll 1") for (int e = tid; e < nact; e += T) a.colperm[actp[e]] = pcol[acto[e]];
     }
     if (g == 0 && tid == 0) {
         for (int q = 0; q < npiv; ++q) { // swaprow! bookkeeping, matrixlu.jl:99-100
@@ -758,7 +848,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
 
 size_t rrlu_lazy_smem(int maxown, int nb)
 {
-    return (size_t)nb * maxown * 8 + (size_t)3 * maxown * 4 + 16 + (size_t)maxown * sizeof(RLEnt) + (size_t)nb * maxown * 8 +
+    return (size_t)nb * maxown * 8 + (size_t)4 * maxown * 4 + 16 + (size_t)(maxown + nb) * sizeof(RLEnt) + (size_t)nb * maxown * 8 +
            128 + (size_t)(RL_THREADS / 32) * RL_S * (RL_RG * 8 + 8) + 64;
 }
 

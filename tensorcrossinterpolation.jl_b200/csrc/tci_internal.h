@@ -50,6 +50,9 @@ struct tci_ctx {
     bool busy = false;
     i64 launches = 0;
     double stage_ms[ST_COUNT] = {0};
+    // relative HBM streaming speed of the SMs in %smid order, learned from the rrLU streaming passes (rrlu.cu)
+    double sm_speed[256];
+    bool sm_speed_valid = false;
     std::map<i64, std::unique_ptr<TargetDev>> targets;
     i64 next_target = 1;
 };

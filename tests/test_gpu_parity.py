@@ -270,6 +270,21 @@ def test_rrlu_deferred_update_kernel(T, oracle, m, n, r, monkeypatch):
     assert_lu_equal(T.rrlu(A, reltol=1e-6), oracle.rrlu(A, reltol=1e-6))  # stop rule with pending updates
 
 
+@pytest.mark.parametrize("m,n,r", [(64, 3000, 21), (700, 1500, 37), (2100, 2050, 24)])
+def test_rrlu_deferred_update_kernel_uneven_ownership(T, oracle, m, n, r, monkeypatch):
+    """Speed-weighted column ownership (CTAs ranked by %smid, columns dealt by a quota table) with a strongly
+    uneven artificial speed table: who owns a column must not change a single bit of the result."""
+    monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
+    monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
+    monkeypatch.setenv("TCI_RRLU_TEST_SPEEDS", "1")
+    A = lowrank_matrix(m, n, r, seed=m * 1000 + n)
+    for lo in (True, False):
+        assert_lu_equal(T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo),
+                        oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo))
+    B = np.random.default_rng(5).integers(-2, 3, (40, 400)).astype(np.float64)  # ties across CTAs
+    assert_lu_equal(T.rrlu(B), oracle.rrlu(B))
+
+
 def test_rrlu_deferred_update_kernel_special_cases(T, oracle, monkeypatch):
     monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
     monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
