@@ -43,6 +43,16 @@ def rrlu_bytes(m, n, r):
     return float(8 * m * n + sum(16 * (m - k) * (n - k) for k in range(1, r)))
 
 
+LAZY_NB = 4  # pivots per commit of the deferred-update kernel (csrc/rrlu_common.cuh RRLU_LAZY_NB)
+LAZY_MIN = 28e6  # m*n from which tci_rrlu uses it (csrc/rrlu.cu)
+
+
+def rrlu_bytes_deferred(m, n, r, nb=LAZY_NB):
+    """HBM bytes the deferred-update kernel (csrc/rrlu_lazy.cu) has to move: the first arg-max scan, then after
+    pivot k one read of the trailing block, and a write of it only at every nb-th pivot (the commit)."""
+    return float(8 * m * n + sum((8 + (8 if k % nb == 0 else 0)) * (m - k) * (n - k) for k in range(1, r)))
+
+
 def factors(m, n, r, seed):
     rng = np.random.default_rng(seed)
     p = rng.random((m, r))
@@ -209,7 +219,9 @@ def main():
     value = world * K * flops / (ms * 1e-3) / 1e9
     kernel_ms = tm["rrlu_kernel"] / K
     peak, which = peaks()
-    achieved = rrlu_bytes(m, n, r) / (kernel_ms * 1e-3) / 1e9
+    deferred = m * n >= LAZY_MIN
+    model_bytes = rrlu_bytes_deferred(m, n, r) if deferred else rrlu_bytes(m, n, r)
+    achieved = model_bytes / (kernel_ms * 1e-3) / 1e9
     del mats
 
     # ---------------- end to end: host buffers through the C ABI, copies inside -------------
@@ -262,10 +274,16 @@ def main():
                           "exact_mode": True},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": RRLU_DRAM_TRAFFIC.get((m, n, r)),
-                            "traffic_source": "profiles/r1_rrlu_8192_1024_dram.csv (ncu dram__bytes_read.sum + "
+                            "traffic_source": "profiles/r1_rrlu_lazy_8192_1024_dram.csv (ncu dram__bytes_read.sum + "
                                               "dram__bytes_write.sum, one launch)", "peak_source": which,
-                            "kernel": "k_rrlu<true>", "kernel_ms": kernel_ms,
-                            "algorithmic_bytes": rrlu_bytes(m, n, r),
+                            "kernel": "k_rrlu_lazy<exact, left, 4>" if deferred else "k_rrlu<true>",
+                            "kernel_ms": kernel_ms, "algorithmic_bytes": model_bytes,
+                            "bytes_model": ("deferred updates: 8 B per trailing element per pivot + 8 B at every 4th "
+                                            "pivot (DESIGN.md 4)") if deferred else "16 B per trailing element per pivot",
+                            # the per-pivot read+write model of SURVEY 8d (what the in-place kernel and the
+                            # reference's loops move); > 1 means fewer bytes were moved than that model needs
+                            "survey_model_bytes": rrlu_bytes(m, n, r),
+                            "survey_model_frac": rrlu_bytes(m, n, r) / (kernel_ms * 1e-3) / 1e9 / peak,
                             "fp64_gflops_kernel": flops / (kernel_ms * 1e-3) / 1e9},
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "stage_ms_per_step": {k: v / K for k, v in tm.items()}, "extra": extra}
@@ -274,10 +292,11 @@ def main():
         dist.destroy_process_group()
 
 
-# DRAM bytes of one k_rrlu launch measured under ncu (profiles/r1_rrlu_8192_1024_dram.csv): 436.26 GB read +
-# 462.19 GB written; below the 967.4 GB algorithmic figure because alternate pivots sweep the tiles in
-# opposite order and the tail of one sweep is still in L2 for the next.
-RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 436260853504 + 462192695040}
+# DRAM bytes of one k_rrlu_lazy launch measured under ncu (profiles/r1_rrlu_lazy_8192_1024_dram.csv): 444.39 GB
+# read + 130.37 GB written (the in-place kernel moved 436.26 + 462.19 GB, profiles/r1_rrlu_8192_1024_dram.csv).
+# Below the 604.6 GB of the model because alternate passes sweep the tiles in opposite order and the tail of one
+# sweep is still in L2 for the next.
+RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 444391724032 + 130372776960}
 
 
 def run_extra(T, ctx, torch, dist, rank, world, stream):
