@@ -225,12 +225,20 @@ def main():
     del mats
 
     # ---------------- end to end: host buffers through the C ABI, copies inside -------------
+    # Every step uploads its matrix from page-locked host memory and brings L, U and the permutations back to
+    # page-locked host arrays.  The upload of step k+1 is enqueued on the library's copy stream before step k is
+    # factorised (tci_dmat_create_async), the way a host driver would double-buffer its Pi matrices.
+    L_pin = torch.empty((r, m), dtype=torch.float64, pin_memory=True).numpy().T
+    U_pin = torch.empty((n, r), dtype=torch.float64, pin_memory=True).numpy().T
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        lu = T.rrlu(A_host, maxrank=r, reltol=1e-12)
-        L, U = lu.L, lu.U
-        del lu
+    nxt = T.DeviceMatrix.from_host_async(ctx, A_host)
+    for k in range(K):
+        cur = nxt
+        nxt = T.DeviceMatrix.from_host_async(ctx, A_host) if k + 1 < K else None
+        lu = T.rrlu(cur, maxrank=r, reltol=1e-12)
+        lu.fetch_into(L_pin, U_pin)
+        del lu, cur
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -239,8 +247,8 @@ def main():
         e2e_s = float(t.item())
     e2e = {"value": world * K * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(8 * m * n),
            "d2h_bytes_per_step": int(8 * (m * r + r * n) + 8 * (m + n) + 8 * (r + 1)),
-           "ms_per_step": e2e_s / K * 1e3}
-    del L, U
+           "ms_per_step": e2e_s / K * 1e3,
+           "pipelining": "upload of step k+1 overlaps the factorisation of step k (copy stream); pinned in/out"}
 
     extra = {}
     if not args.no_extra:

@@ -59,6 +59,12 @@ int tci_timers(tci_ctx *ctx, double *out, int64_t n, int reset);
 
 /* ---- device matrices ---------------------------------------------------- */
 int tci_dmat_create(tci_ctx *ctx, int64_t m, int64_t n, const double *host /* nullable */, tci_dmat **out);
+/* As tci_dmat_create with a host matrix, but the upload runs on the context's copy stream and the call returns
+ * once it is enqueued, so that it overlaps with a factorisation in flight (double buffering of the Julia-side
+ * `Matrix{Float64}` handed to rrlu, matrixlu.jl:217-225).  `host` must stay valid -- and should be page-locked --
+ * until the matrix is first consumed (tci_rrlu, tci_lu_rdiv, tci_dmat_fetch, tci_dmat_destroy order themselves
+ * after the copy).                                                                                         */
+int tci_dmat_create_async(tci_ctx *ctx, int64_t m, int64_t n, const double *host, tci_dmat **out);
 int tci_dmat_shape(tci_dmat *a, int64_t *m, int64_t *n, int64_t *ld);
 void *tci_dmat_ptr(tci_dmat *a); /* raw device pointer, for collectives on the host layer */
 int tci_dmat_fetch(tci_dmat *a, double *host /* m x n, tight */);

@@ -29,6 +29,7 @@ SYMBOLS = {
     "tci_ctx_stream": (VP, [VP]),
     "tci_timers": (C.c_int, [VP, P_f64, i64, C.c_int]),
     "tci_dmat_create": (C.c_int, [VP, i64, i64, P_f64, C.POINTER(VP)]),
+    "tci_dmat_create_async": (C.c_int, [VP, i64, i64, P_f64, C.POINTER(VP)]),
     "tci_dmat_shape": (C.c_int, [VP, P_i64, P_i64, P_i64]),
     "tci_dmat_ptr": (VP, [VP]),
     "tci_dmat_fetch": (C.c_int, [VP, P_f64]),
@@ -188,6 +189,19 @@ class DeviceMatrix:
         h = VP()
         ctx.check(lib().tci_dmat_create(ctx.h, a.shape[0], a.shape[1], pf(a), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def from_host_async(cls, ctx, a):
+        """Upload on the context's copy stream (tci_dmat_create_async): returns once the copy is enqueued, so it
+        overlaps with whatever the context's main stream is running.  `a` must be Fortran-ordered Float64 (ideally
+        page-locked) and is kept alive by the returned object until it is released."""
+        if not (a.dtype == np.float64 and a.flags.f_contiguous and a.ndim == 2):
+            raise ValueError("from_host_async needs a Fortran-ordered Float64 matrix")
+        h = VP()
+        ctx.check(lib().tci_dmat_create_async(ctx.h, a.shape[0], a.shape[1], pf(a), C.byref(h)))
+        out = cls(ctx, h)
+        out._src = a
+        return out
 
     @classmethod
     def wrap(cls, ctx, dptr, m, n, ld):

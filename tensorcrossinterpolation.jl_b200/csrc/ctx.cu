@@ -37,6 +37,7 @@ extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
     cudaGetDeviceProperties(&prop, device_id);
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
@@ -71,6 +72,8 @@ extern "C" void tci_ctx_destroy(tci_ctx *ctx)
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2);
     cudaEventDestroy(ctx->ev3);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -124,6 +127,44 @@ extern "C" int tci_dmat_create(tci_ctx *ctx, int64_t m, int64_t n, const double 
         if (e != cudaSuccess) {
             tci_dmat_destroy(a);
             return tci_fail(ctx, TCI_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = a;
+    return TCI_OK;
+}
+
+void dmat_wait_ready(tci_ctx *ctx, tci_dmat *a)
+{
+    if (a && a->ready) {
+        cudaStreamWaitEvent(ctx->stream, a->ready, 0);
+        cudaEventDestroy(a->ready); // released once the wait has been satisfied
+        a->ready = nullptr;
+    }
+}
+
+// Upload on the context's copy stream; returns as soon as the copy is enqueued.  `host` must stay valid (and
+// should be pinned) until the matrix is first used; every consumer orders itself after the copy.
+extern "C" int tci_dmat_create_async(tci_ctx *ctx, int64_t m, int64_t n, const double *host, tci_dmat **out)
+{
+    TCI_ENTER(ctx);
+    if (!out || !host || m < 0 || n < 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_dmat_create_async: bad arguments");
+    tci_dmat *a = nullptr;
+    int rc = dmat_alloc(ctx, m, n, &a);
+    if (rc) return rc;
+    if (m * n > 0) {
+        cudaEvent_t alloc_done = nullptr;
+        cudaError_t e = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(alloc_done, ctx->stream); // the allocation is stream ordered
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(a->p, a->ld * sizeof(double), host, m * sizeof(double), m * sizeof(double), n,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(a->ready, ctx->copy_stream);
+        if (alloc_done) cudaEventDestroy(alloc_done);
+        if (e != cudaSuccess) {
+            tci_dmat_destroy(a);
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("async H2D: ") + cudaGetErrorString(e));
         }
     }
     *out = a;
@@ -214,6 +255,7 @@ extern "C" int tci_dmat_fetch(tci_dmat *a, double *host)
     tci_ctx *ctx = a->ctx;
     TCI_ENTER(ctx);
     if (a->m * a->n == 0) return TCI_OK;
+    dmat_wait_ready(ctx, a);
     StageTimer tm(ctx, ST_D2H);
     TCI_CUDA(ctx, cudaMemcpy2DAsync(host, a->m * sizeof(double), a->p, a->ld * sizeof(double), a->m * sizeof(double),
                                     a->n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -224,10 +266,9 @@ extern "C" int tci_dmat_fetch(tci_dmat *a, double *host)
 extern "C" int tci_dmat_destroy(tci_dmat *a)
 {
     if (!a) return TCI_OK;
-    if (a->owned) {
-        cudaSetDevice(a->ctx->device);
-        dev_free(a->ctx, a->p);
-    }
+    cudaSetDevice(a->ctx->device);
+    dmat_wait_ready(a->ctx, a);
+    if (a->owned) dev_free(a->ctx, a->p);
     delete a;
     return TCI_OK;
 }

@@ -235,6 +235,7 @@ extern "C" int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host, tci_dmat *
     if (lu->m != lu->n || k != lu->m)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_lu_rdiv: the factorised matrix must be square and of full rank");
     if (B->n != k) return tci_fail(ctx, TCI_ERR_ARG, "tci_lu_rdiv: DimensionMismatch between B and the factorised matrix");
+    dmat_wait_ready(ctx, B);
     tci_dmat *res = nullptr;
     int rc = dmat_alloc(ctx, rows, k, &res);
     if (rc) return rc;

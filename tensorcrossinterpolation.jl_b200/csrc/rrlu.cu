@@ -543,6 +543,7 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         if (rc) return rc;
     }
     TCI_ENTER(ctx);
+    dmat_wait_ready(ctx, A);
     struct Cleanup {
         tci_dmat *a;
         bool armed;

@@ -22,7 +22,10 @@ struct tci_dmat {
     i64 m = 0, n = 0, ld = 0;
     i64 ncap = 0; // allocated columns
     bool owned = true;
+    cudaEvent_t ready = nullptr; // set by tci_dmat_create_async: the upload on the copy stream has finished
 };
+// make ctx->stream wait for a pending asynchronous upload of `a` (no-op otherwise)
+void dmat_wait_ready(tci_ctx *ctx, tci_dmat *a);
 
 struct TargetDev {
     int kind = 0; // 0 analytic, 1 TT, 2 MPO pair
@@ -44,6 +47,7 @@ struct tci_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // uploads that overlap with kernels on `stream` (tci_dmat_create_async)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     std::mutex mu;

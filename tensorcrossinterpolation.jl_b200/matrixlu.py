@@ -36,6 +36,17 @@ class rrLU:
             self.ctx.check(lib().tci_lu_fetch(self._h, pf(L), pf(U)))
         self._L, self._U = L, U
 
+    def fetch_into(self, L, U):
+        """lu.L / lu.U written into caller-provided Fortran-ordered arrays (e.g. views of page-locked memory)."""
+        m, n = self._shape
+        r = self.npivot
+        for a, shp in ((L, (m, r)), (U, (r, n))):
+            if not (a.shape == shp and a.dtype == np.float64 and a.flags.f_contiguous):
+                raise ValueError(f"fetch_into expects a Fortran-ordered Float64 array of shape {shp}")
+        if r:
+            self.ctx.check(lib().tci_lu_fetch(self._h, pf(L), pf(U)))
+        self._L, self._U = L, U
+
     @property
     def L(self):
         if self._L is None:

@@ -355,6 +355,31 @@ def test_rrlu_fast_mode_same_pivots(T, oracle):
     assert np.max(np.abs(T.left(lu) @ T.right(lu) - A)) <= 10 * lu.error
 
 
+def test_rrlu_async_upload_and_fetch_into(T, oracle):
+    """tci_dmat_create_async (upload on the copy stream, consumers order themselves after it) + fetch_into."""
+    import torch
+    ctx = T.default_context()
+    mats, refs = [], []
+    for k in range(3):  # several uploads in flight before the first one is consumed
+        m, n, r = 300 + 50 * k, 200 + 30 * k, 40
+        pinned = torch.empty((n, m), dtype=torch.float64, pin_memory=True).numpy().T
+        pinned[:] = lowrank_matrix(m, n, r, seed=70 + k)
+        mats.append((T.DeviceMatrix.from_host_async(ctx, pinned), pinned, r))
+    for dm, host, r in mats:
+        ref = oracle.rrlu(host, maxrank=r, reltol=1e-12)
+        lu = T.rrlu(dm, maxrank=r, reltol=1e-12)
+        L = np.zeros((host.shape[0], lu.npivot), order="F")
+        U = np.zeros((lu.npivot, host.shape[1]), order="F")
+        lu.fetch_into(L, U)
+        assert_lu_equal(lu, ref)
+        assert np.array_equal(L, ref.L) and np.array_equal(U, ref.U)
+    dm = T.DeviceMatrix.from_host_async(ctx, np.asfortranarray(np.arange(12.0).reshape(3, 4)))
+    assert np.array_equal(dm.to_host(), np.arange(12.0).reshape(3, 4))  # fetch waits for the upload
+    T.DeviceMatrix.from_host_async(ctx, np.asfortranarray(np.ones((5, 5))))  # destroyed before first use
+    with pytest.raises(ValueError):
+        T.DeviceMatrix.from_host_async(ctx, np.ones((3, 4)))  # not Fortran-ordered
+
+
 def test_rrlu_device_input_from_pi_eval(T, oracle):
     ld = [10] * 6
     f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
