@@ -451,6 +451,30 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         tci, ranks, errors = T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
         extra["crossinterpolate2_config1"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks[-1]),
                                               "iterations": len(ranks), "error": float(errors[-1])}
+    if rank == 0:
+        # --- config 4 scale: one bond's rrLU, 32768 x 32768 (8.6 GB, 12 sites d=64 at chi=512), maxrank 512.
+        # The config-4 target itself is numerically of rank ~23, so its Pi never needs 512 pivots; the kernel is
+        # measured at that scale on a synthetic rank-512 matrix formed on the device (untimed).
+        try:
+            m4, r4 = 32768, 512
+            g4 = torch.Generator(device="cuda").manual_seed(4)
+            p4 = torch.rand((m4, r4), dtype=torch.float64, device="cuda", generator=g4) * \
+                (2.0 ** (-40.0 * torch.arange(1, r4 + 1, dtype=torch.float64, device="cuda") / r4))
+            q4 = torch.rand((r4, m4), dtype=torch.float64, device="cuda", generator=g4)
+            A4 = (p4 @ q4).t().contiguous()  # column-major m4 x m4
+            del p4, q4
+            torch.cuda.synchronize()
+            view = T.DeviceMatrix.wrap(ctx, A4.data_ptr(), m4, m4, m4)
+            ctx.timers(reset=True)
+            lu4 = T.rrlu(view, maxrank=r4, reltol=1e-12)
+            ms4 = ctx.timers(reset=True)["rrlu_kernel"]
+            extra["rrlu_config4_scale"] = {"shape": [m4, m4], "maxrank": r4, "npivot": int(lu4.npivot), "ms": ms4,
+                                           "gflops": rrlu_flops(m4, m4, lu4.npivot) / ms4 / 1e6,
+                                           "gbs_deferred_model": rrlu_bytes_deferred(m4, m4, lu4.npivot) / ms4 / 1e6}
+            del lu4, view, A4
+            torch.cuda.empty_cache()
+        except Exception as e:  # never let an extra take the headline line down
+            extra["rrlu_config4_scale"] = {"error": str(e)[:200]}
     return extra
 
 
