@@ -578,7 +578,10 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
             st.estep = backward ? -1 : 1;
             st.pt = t;
             st.p_set();
-            const unsigned yEs = smem_u32(yE);
+            unsigned yEs = smem_u32(yE);
+            // opaque copies: otherwise the shared-memory addresses are re-derived from the carve-up in every
+            // iteration of the tile loop (a dozen integer instructions per tile)
+            asm volatile("" : "+r"(yEs), "+r"(st.tab), "+r"(st.ring0), "+r"(st.bar0));
 #pragma unroll 1
             for (int k = 0; k < RL_S; ++k) st.produce(lane); // fill the ring
 #pragma unroll 1
