@@ -223,25 +223,31 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
             q[2 * u + 1] = v1 * v1;
             tmax = max(tmax, max(hi32(q[2 * u]) | nmw[2 * u], hi32(q[2 * u + 1]) | nmw[2 * u + 1]));
         }
-        if (tmax >= bhi) { // rare: exact comparison
-            unsigned long long tb = 0ull;
-            int tj = 0;
+        // bhi is warp-uniform: the high word of the best square any lane of this warp has seen.  An element below it
+        // cannot win, so the exact path runs about once per new warp-wide maximum instead of once per lane maximum
+        // (a lane-local threshold sent 21 % of the tiles through it, because one lane is enough to divert the warp).
+        if (__any_sync(0xffffffffu, tmax >= bhi)) {
+            if (tmax >= bhi) { // exact comparison
+                unsigned long long tb = 0ull;
+                int tj = 0;
 #pragma unroll
-            for (int w = 0; w < 2 * RL_R; ++w) {
-                const bool ok = nmw[w] == 0 && q[w] == q[w];
-                const unsigned long long ob = ok ? (unsigned long long)__double_as_longlong(q[w]) + 1ull : 0ull;
-                if (ob > tb) {
-                    tb = ob;
-                    tj = w;
+                for (int w = 0; w < 2 * RL_R; ++w) {
+                    const bool ok = nmw[w] == 0 && q[w] == q[w];
+                    const unsigned long long ob = ok ? (unsigned long long)__double_as_longlong(q[w]) + 1ull : 0ull;
+                    if (ob > tb) {
+                        tb = ob;
+                        tj = w;
+                    }
+                }
+                const int trow = rbase + (tj >> 1) * 64 + (tj & 1);
+                if (tb > bvb || (tb == bvb && tb != 0ull && (cp < bcpv || (cp == bcpv && trow < browv)))) {
+                    bvb = tb;
+                    bcpv = cp;
+                    browv = trow;
                 }
             }
-            const int trow = rbase + (tj >> 1) * 64 + (tj & 1);
-            if (tb > bvb || (tb == bvb && tb != 0ull && (cp < bcpv || (cp == bcpv && trow < browv)))) {
-                bvb = tb;
-                bcpv = cp;
-                browv = trow;
-                bhi = (int)((tb - 1ull) >> 32);
-            }
+            const int mine = bvb ? (int)((bvb - 1ull) >> 32) : -1;
+            bhi = max(bhi, (int)__reduce_max_sync(0xffffffffu, mine));
         }
     }
 }
