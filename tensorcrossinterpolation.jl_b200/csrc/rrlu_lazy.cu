@@ -168,7 +168,7 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
                                         int lane, const double2 (&xr)[NB][RL_R], unsigned long long &bvb, int &bhi,
                                         int &bcpv, int &browv)
 {
-    static_assert(NB == 4 && (NDV == 2 || NDV == 4), "y_i are fetched as 16-byte pairs");
+    static_assert(NB == 4 && NDV >= 1 && NDV <= 4, "y_i are fetched as one or two 16-byte pairs");
     int nmw[2 * RL_R];
     bool inb[RL_R];
 #pragma unroll
@@ -195,11 +195,11 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
         {
             const double2 y01 = lds_f64x2(yEs + 32u * (unsigned)e);
             y[0] = y01.x;
-            y[1] = y01.y;
-            if (NDV == 4) {
+            if (NDV >= 2) y[1] = y01.y;
+            if (NDV >= 3) {
                 const double2 y23 = lds_f64x2(yEs + 32u * (unsigned)e + 16u);
                 y[2] = y23.x;
-                y[3] = y23.y;
+                if (NDV >= 4) y[3] = y23.y;
             }
         }
         const unsigned sa = st.acquire() + lane16;
@@ -628,12 +628,17 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                     }
                 }
                 const int efirst = backward ? c0 + cnt - 1 : c0;
-                if (nd <= NB / 2)
-                    rl_item<EXACT, NB, NB / 2, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
-                else if (!commit)
-                    rl_item<EXACT, NB, NB, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
-                else
+                // one instantiation per number of pending updates (nd == NB is always the commit)
+                if (nd <= 1)
+                    rl_item<EXACT, NB, 1, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                else if (nd == 2)
+                    rl_item<EXACT, NB, 2, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                else if (nd == 3)
+                    rl_item<EXACT, NB, 3, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                else if (commit)
                     rl_item<EXACT, NB, NB, true>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                else
+                    rl_item<EXACT, NB, NB, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
             }
         }
         RL_MARK(2); // streaming pass (this warp)
