@@ -29,7 +29,7 @@
 // ring stages (1 KB tiles in flight) per warp.  Measured at 8192^2 r=1024 / 16384^2 r=128 (ms): 4: 140.5 / 66.6,
 // 6: 140.3 / 65.7, 8: 142.3 / 69.8, 12: 149.1 / 82.1 -- deeper queues cost bandwidth instead of hiding latency.
 #ifndef RL_S
-#define RL_S 6
+#define RL_S 4 // slots of two tiles (2 KB)
 #endif
 
 
@@ -97,7 +97,7 @@ struct RLStream {
     // ring: shared addresses of this warp's stage 0 / barrier 0, consumer and producer stage, consumer parity
     unsigned ring0, bar0, cs, cpar, ps;
     // producer cursor: item, tile within the item, item length, current table entry, row offset, bytes
-    int pt, pj, p_len, p_e, p_efirst, p_row;
+    int pt, pj, p_len, p_efirst, p_row;
     unsigned p_bytes;
 
     __device__ __forceinline__ void item(int t, int &row, int &c0, int &cnt) const
@@ -116,37 +116,42 @@ struct RLStream {
             p_bytes = ((unsigned)rows * 8u + 15u) & ~15u;
             p_len = nd + cnt;
             p_efirst = estep > 0 ? c0 : c0 + cnt - 1;
-            p_e = nd ? -nd : p_efirst;
             pj = 0;
         } else
             p_len = 0; // end of the stream
     }
+    // entry of tile number j of the item the producer is in: pivot columns first, then the chunk's columns
+    __device__ __forceinline__ int p_entry(int j) const { return j < nd ? j - nd : p_efirst + (j - nd) * estep; }
+    // A ring slot holds TWO consecutive tiles of the stream (the last slot of an item only one when the item has
+    // an odd number of tiles): one mbarrier phase, one acquire / release and one cursor step per pair.
     __device__ __forceinline__ void produce(int lane)
     {
         if (p_len == 0) return;
+        const bool two = pj + 1 < p_len;
         if (lane == 0) {
-            unsigned long long base;
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(tab + 16u * (unsigned)p_e) : "memory");
-            const unsigned bar = bar0 + (ps << 3);
-            mbar_expect_tx(bar, p_bytes);
-            bulk_g2s(ring0 + (ps << 10), reinterpret_cast<const double *>(base) + p_row, p_bytes, bar);
+            const unsigned bar = bar0 + (ps << 3), dst = ring0 + (ps << 11);
+            unsigned long long b0, b1 = 0ull;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(b0) : "r"(tab + 16u * (unsigned)p_entry(pj)) : "memory");
+            if (two) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(b1) : "r"(tab + 16u * (unsigned)p_entry(pj + 1)) : "memory");
+            mbar_expect_tx(bar, two ? 2u * p_bytes : p_bytes);
+            bulk_g2s(dst, reinterpret_cast<const double *>(b0) + p_row, p_bytes, bar);
+            if (two) bulk_g2s(dst + 1024u, reinterpret_cast<const double *>(b1) + p_row, p_bytes, bar);
         }
         ps = (ps + 1u == RL_S) ? 0u : ps + 1u;
-        ++pj;
-        p_e = (pj < nd) ? p_e + 1 : (pj == nd ? p_efirst : p_e + estep);
-        if (pj == p_len) {
+        pj += 2;
+        if (pj >= p_len) {
             pt += step;
             p_set();
         }
     }
-    // wait for the next tile; returns the shared address of its first byte
+    // wait for the next slot; returns the shared address of its first byte
     __device__ __forceinline__ unsigned acquire()
     {
         const unsigned bar = bar0 + (cs << 3);
         while (!mbar_try_wait(bar, cpar)) {}
-        return ring0 + (cs << 10);
+        return ring0 + (cs << 11);
     }
-    // the lanes have their values in registers: hand the stage back and keep the ring full
+    // the lanes have their values in registers: hand the slot back and keep the ring full
     __device__ __forceinline__ void release(int lane)
     {
         __syncwarp();
@@ -165,8 +170,8 @@ static_assert(RL_RG * 8 == 1024, "ring addressing uses shifts");
 // position, row) comparison of matrixlu.jl:16-29 only runs when a tile reaches the lane's current best.
 template <bool EXACT, int NB, int NDV, bool COMMIT>
 __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, int cnt, int rbase, int m, unsigned negm,
-                                        int lane, const double2 (&xr)[NB][RL_R], unsigned long long &bvb, int &bhi,
-                                        int &bcpv, int &browv)
+                                        int lane, unsigned open_slot, const double2 (&xr)[NB][RL_R],
+                                        unsigned long long &bvb, int &bhi, int &bcpv, int &browv)
 {
     static_assert(NB == 4 && NDV >= 1 && NDV <= 4, "y_i are fetched as one or two 16-byte pairs");
     int nmw[2 * RL_R];
@@ -184,12 +189,11 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
     }
     unsigned lane16 = 16u * (unsigned)lane;
     asm volatile("" : "+r"(lane16));
-    int e = efirst;
-#pragma unroll 1
-    for (int idx = 0; idx < cnt; ++idx, e += st.estep) {
-        unsigned long long cbase;
+    // one column tile whose 1 KB sits at shared address `sa`
+    auto tile = [&](int e, unsigned sa) {
+        unsigned long long cbase = 0ull;
         int cp;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cbase) : "r"(st.tab + 16u * (unsigned)e) : "memory");
+        if (COMMIT) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(cbase) : "r"(st.tab + 16u * (unsigned)e) : "memory");
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cp) : "r"(st.tab + 16u * (unsigned)e + 8u) : "memory");
         double y[NDV];
         {
@@ -202,11 +206,9 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
                 if (NDV >= 4) y[3] = y23.y;
             }
         }
-        const unsigned sa = st.acquire() + lane16;
         double2 d[RL_R];
 #pragma unroll
-        for (int u = 0; u < RL_R; ++u) d[u] = lds_f64x2(sa + 512u * u);
-        st.release(lane);
+        for (int u = 0; u < RL_R; ++u) d[u] = lds_f64x2(sa + lane16 + 512u * u);
         double *const cptr = reinterpret_cast<double *>(cbase) + rbase;
         double q[2 * RL_R];
         int tmax = -1;
@@ -249,6 +251,25 @@ __device__ __forceinline__ void rl_item(RLStream &st, unsigned yEs, int efirst, 
             const int mine = bvb ? (int)((bvb - 1ull) >> 32) : -1;
             bhi = max(bhi, (int)__reduce_max_sync(0xffffffffu, mine));
         }
+    };
+    int e = efirst, idx = 0;
+    if (open_slot) { // the slot's first half was the last pivot-column tile of this item
+        tile(e, open_slot + 1024u);
+        st.release(lane);
+        e += st.estep;
+        idx = 1;
+    }
+#pragma unroll 1
+    for (; idx + 1 < cnt; idx += 2, e += 2 * st.estep) {
+        const unsigned sa = st.acquire();
+        tile(e, sa);
+        tile(e + st.estep, sa + 1024u);
+        st.release(lane);
+    }
+    if (idx < cnt) { // an odd tile closes the item: it has a slot of its own
+        const unsigned sa = st.acquire();
+        tile(e, sa);
+        st.release(lane);
     }
 }
 
@@ -295,7 +316,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
     double *yE = reinterpret_cast<double *>(ent + MO); // [MO][NB] pivot-row values in entry order
     unsigned char *ringp = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<size_t>(yE + (size_t)NB * MO) + 127) & ~(size_t)127); // [nwarps][RL_S][RL_RG] doubles
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ringp + (size_t)nwarps * RL_S * RL_RG * 8);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(ringp + (size_t)nwarps * RL_S * RL_RG * 16);
 #define RL_COL(o) (a.A + (size_t)a.ld * pcol[o])
 
     long long tmark = clock64();
@@ -337,7 +358,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
     if (g == 0)
         _Pragma("unroll 1") for (int i = tid; i < m; i += T) a.rowperm[i] = i;
     RLStream st;
-    st.ring0 = smem_u32(ringp + (size_t)warp * RL_S * RL_RG * 8);
+    st.ring0 = smem_u32(ringp + (size_t)warp * RL_S * RL_RG * 16);
     st.bar0 = smem_u32(mbar + warp * RL_S);
     st.cs = st.cpar = st.ps = 0u;
     if (lane == 0) {
@@ -611,17 +632,22 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                     negm |= (ok0 ? 0u : 1u) << (2 * u) | (ok1 ? 0u : 2u) << (2 * u);
                 }
                 double2 xr[NB][RL_R];
+                unsigned open_slot = 0u; // shared address of a slot whose second half is still to be consumed
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
-                    if (i < nd) { // the x_i tile of this item comes through the ring first
-                        const unsigned sa = st.acquire() + 16u * (unsigned)lane;
+                    if (i < nd) { // the x_i tiles of this item come through the ring first, two per slot
+                        if ((i & 1) == 0) open_slot = st.acquire();
+                        const unsigned sa = open_slot + ((i & 1) ? 1024u : 0u) + 16u * (unsigned)lane;
 #pragma unroll
                         for (int u = 0; u < RL_R; ++u) {
                             const double2 xx = lds_f64x2(sa + 512u * u);
                             xr[i][u].x = okr[2 * u] ? xx.x : 0.0;
                             xr[i][u].y = okr[2 * u + 1] ? xx.y : 0.0;
                         }
-                        st.release(lane);
+                        if (i & 1) {
+                            st.release(lane);
+                            open_slot = 0u;
+                        }
                     } else {
 #pragma unroll
                         for (int u = 0; u < RL_R; ++u) xr[i][u] = make_double2(0.0, 0.0);
@@ -630,15 +656,15 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                 const int efirst = backward ? c0 + cnt - 1 : c0;
                 // one instantiation per number of pending updates (nd == NB is always the commit)
                 if (nd <= 1)
-                    rl_item<EXACT, NB, 1, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, 1, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, open_slot, xr, bvb, bhi, bcpv, browv);
                 else if (nd == 2)
-                    rl_item<EXACT, NB, 2, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, 2, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, open_slot, xr, bvb, bhi, bcpv, browv);
                 else if (nd == 3)
-                    rl_item<EXACT, NB, 3, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, 3, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, open_slot, xr, bvb, bhi, bcpv, browv);
                 else if (commit)
-                    rl_item<EXACT, NB, NB, true>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, NB, true>(st, yEs, efirst, cnt, rbase, m, negm, lane, open_slot, xr, bvb, bhi, bcpv, browv);
                 else
-                    rl_item<EXACT, NB, NB, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, xr, bvb, bhi, bcpv, browv);
+                    rl_item<EXACT, NB, NB, false>(st, yEs, efirst, cnt, rbase, m, negm, lane, open_slot, xr, bvb, bhi, bcpv, browv);
             }
         }
         RL_MARK(2); // streaming pass (this warp)
@@ -863,7 +889,7 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
 size_t rrlu_lazy_smem(int maxown, int nb)
 {
     return (size_t)nb * maxown * 8 + (size_t)4 * maxown * 4 + 16 + (size_t)(maxown + nb) * sizeof(RLEnt) + (size_t)nb * maxown * 8 +
-           128 + (size_t)(RL_THREADS / 32) * RL_S * (RL_RG * 8 + 8) + 64;
+           128 + (size_t)(RL_THREADS / 32) * RL_S * (RL_RG * 16 + 8) + 64;
 }
 
 template <bool EXACT, int NB> static const void *lazy_fn(bool left)
