@@ -44,7 +44,7 @@ def rrlu_bytes(m, n, r):
 
 
 LAZY_NB = 4  # pivots per commit of the deferred-update kernel (csrc/rrlu_common.cuh RRLU_LAZY_NB)
-LAZY_MIN = 20e6  # m*n from which tci_rrlu uses it (csrc/rrlu.cu)
+LAZY_MIN = 13e6  # m*n from which tci_rrlu uses it (csrc/rrlu.cu)
 
 
 def rrlu_bytes_deferred(m, n, r, nb=LAZY_NB):

@@ -592,11 +592,11 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     // streaming regime: deferred updates (rrlu_lazy.cu) unless disabled
     const bool no_lazy = getenv("TCI_RRLU_NO_LAZY") != nullptr;
     // (its tiles are moved by cp.async.bulk: columns must start on 16-byte boundaries)
-    // (measured, ms deferred / in place: 3072^2 7.6 / 5.8, 4096^2 10.3 / 10.6, 4608^2 13.7 / 13.7, 5120^2 15.5 / 17.2,
-    //  6144^2 20.0 / 25.1; below ~4500^2 most of the matrix stays in the 126 MB L2 and the in-place kernel's smaller
-    //  fixed cost per pivot wins)
+    // (measured, ms deferred / in place: 2048^2 4.7 / 3.6, 3072^2 6.8 / 5.9, 3584^2 7.9 / 8.0, 4096^2 9.5 / 10.6,
+    //  5120^2 15.5 / 17.2, 6144^2 18.8 / 25.1; below ~3600^2 the matrix stays in the 126 MB L2 and the in-place
+    //  kernel's smaller fixed cost per pivot wins)
     const char *lazy_min_env = getenv("TCI_RRLU_LAZY_MIN");
-    const double lazy_min = lazy_min_env ? atof(lazy_min_env) : 20e6;
+    const double lazy_min = lazy_min_env ? atof(lazy_min_env) : 13e6;
     const bool lazy = !resident && !no_lazy && (double)m * (double)n >= lazy_min &&
                       rrlu_lazy_smem((int)((n + G - 1) / G) + 8, RRLU_LAZY_NB) <= SMEM_BUDGET && (A->ld % 2 == 0) && (reinterpret_cast<size_t>(A->p) % 16 == 0);
     const i64 per_cta = m * ((n + G - 1) / G);
