@@ -300,11 +300,11 @@ def main():
         dist.destroy_process_group()
 
 
-# DRAM bytes of one k_rrlu_lazy launch measured under ncu (profiles/r1_rrlu_lazy_8192_1024_dram.csv): 444.39 GB
+# DRAM bytes of one k_rrlu_lazy launch measured under ncu (profiles/r1_rrlu_lazy_8192_1024_dram.csv): 445.87 GB
 # read + 130.37 GB written (the in-place kernel moved 436.26 + 462.19 GB, profiles/r1_rrlu_8192_1024_dram.csv).
 # Below the 604.6 GB of the model because alternate passes sweep the tiles in opposite order and the tail of one
 # sweep is still in L2 for the next.
-RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 444391724032 + 130372776960}
+RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 445872222720 + 130370041856}
 
 
 def run_extra(T, ctx, torch, dist, rank, world, stream):
