@@ -799,23 +799,30 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
                     yb[i] = (i < nd) ? ys[i * MO + bslot] : 0.0;
                     xq[i] = (i < nd) ? xptr[i] : nullptr;
                 }
+                double *xo = a.xbuf + ((size_t)((s + 1) % a.nxslots) * G + g) * a.ldx;
+                constexpr int PB = 4; // rows in flight per thread: the loop is latency bound (64 KB per CTA)
+                int r0 = (k0 & ~1) + 2 * tid;
+                double2 d[PB], xx[NB][PB];
+                // the first batch of column loads is issued before the candidate's own value is waited for
+#pragma unroll
+                for (int k = 0; k < PB; ++k)
+                    if (r0 + 2 * T * k < m) d[k] = *reinterpret_cast<const double2 *>(col + r0 + 2 * T * k);
                 cval = col[b];
 #pragma unroll
                 for (int i = 0; i < NB; ++i)
                     if (i < nd) cval = schur<EXACT>(cval, __ldcg(xq[i] + b), yb[i]);
-                double *xo = a.xbuf + ((size_t)((s + 1) % a.nxslots) * G + g) * a.ldx;
-                constexpr int PB = 4; // rows in flight per thread: the loop is latency bound (64 KB per CTA)
-                _Pragma("unroll 1") for (int r0 = (k0 & ~1) + 2 * tid; r0 < m; r0 += 2 * T * PB) {
-                    double2 d[PB], xx[NB][PB];
+                bool preloaded = true;
+                _Pragma("unroll 1") for (; r0 < m; r0 += 2 * T * PB) {
 #pragma unroll
                     for (int k = 0; k < PB; ++k) {
                         const int r = r0 + 2 * T * k;
-                        if (r < m) d[k] = *reinterpret_cast<const double2 *>(col + r);
+                        if (!preloaded && r < m) d[k] = *reinterpret_cast<const double2 *>(col + r);
 #pragma unroll
                         for (int i = 0; i < NB; ++i)
                             xx[i][k] = (i < nd && r < m) ? __ldcg(reinterpret_cast<const double2 *>(xq[i] + r))
                                                          : make_double2(0.0, 0.0);
                     }
+                    preloaded = false;
 #pragma unroll
                     for (int k = 0; k < PB; ++k) {
                         const int r = r0 + 2 * T * k;
