@@ -285,6 +285,16 @@ def test_rrlu_deferred_update_kernel_uneven_ownership(T, oracle, m, n, r, monkey
     assert_lu_equal(T.rrlu(B), oracle.rrlu(B))
 
 
+@pytest.mark.parametrize("m,n,r", [(120000, 300, 11), (300, 120000, 11), (6000, 5000, 13)])
+def test_rrlu_deferred_update_kernel_natural_sizes(T, oracle, m, n, r):
+    """Shapes that take the deferred-update kernel without forcing (m*n >= 13e6): very tall, very wide and square;
+    the rank is not a multiple of the commit block."""
+    A = lowrank_matrix(m, n, r + 3, seed=m + n)
+    for lo in (True, False):
+        assert_lu_equal(T.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo),
+                        oracle.rrlu(A, maxrank=r, reltol=1e-12, leftorthogonal=lo))
+
+
 def test_rrlu_deferred_update_kernel_special_cases(T, oracle, monkeypatch):
     monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
     monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
