@@ -286,12 +286,13 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
     struct {
         unsigned long long *p;
     } dmax{reinterpret_cast<unsigned long long *>(idx.p)};
-    cudaEventRecord(ctx->ev0, ctx->stream);
+    cudaEventRecord(ctx->ev2, ctx->stream); // index upload is accounted as H2D, the kernels as the Pi stage
     TCI_CUDA(ctx, cudaMemsetAsync(idx.p, 0, 16, ctx->stream));
     if (nl * nI > 0)
         TCI_CUDA(ctx, cudaMemcpyAsync(dI.p, I, (size_t)(nl * nI) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
     if (nr * nJ > 0)
         TCI_CUDA(ctx, cudaMemcpyAsync(dJ.p, J, (size_t)(nr * nJ) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev0, ctx->stream);
     tci_dmat *out = nullptr;
     tci_dmat view; // column block of dst
     int rc = 0;
@@ -333,6 +334,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
         cudaEventRecord(ctx->ev3, ctx->stream);
         TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev0) == cudaSuccess) ctx->stage_ms[ST_H2D] += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stage_ms[ST_PI] += ms;
         if (cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev3) == cudaSuccess) ctx->stage_ms[ST_D2H] += ms;
         if (maxabs) {
