@@ -319,6 +319,18 @@ def test_rrlu_deferred_update_kernel_special_cases(T, oracle, monkeypatch):
         T.rrlu(B)
     lu = T.rrlu(rng.random((6, 5000)), maxrank=4)  # more CTAs than rows
     assert lu.npivot == 4
+    # all zeros: the first pivot is 0, 0/0 reaches L (matrixlu.jl:164-169)
+    with pytest.raises(T.TCIError, match="contains NaNs"):
+        T.rrlu(np.zeros((40, 30)))
+    # huge entries: abs2 overflows to Inf, ties on Inf are broken by scan order; Inf * 0 must not leak anywhere
+    H = rng.random((70, 90))
+    H[3, 4], H[60, 2], H[33, 80] = 1e200, -1e200, 1e200
+    for mr in (3, 6, 9):
+        assert_lu_equal(T.rrlu(H, maxrank=mr), oracle.rrlu(H, maxrank=mr))
+    assert_lu_equal(T.rrlu(H * 1e-300, maxrank=6), oracle.rrlu(H * 1e-300, maxrank=6))
+    # a matrix with exactly representable entries and rank 5: the trailing block becomes exactly zero
+    Z = (rng.integers(-4, 5, (64, 5)) @ rng.integers(-4, 5, (5, 48))).astype(np.float64)
+    assert_lu_equal(T.rrlu(Z), oracle.rrlu(Z))
 
 
 @pytest.mark.parametrize("m,n", [(50, 50), (120, 80), (257, 300)])
