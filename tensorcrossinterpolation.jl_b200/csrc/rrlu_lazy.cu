@@ -579,9 +579,11 @@ template <bool EXACT, bool LEFT, int NB> __global__ void __launch_bounds__(RL_TH
             {
                 int best = 0x7fffffff;
                 const int nchmax = (nact + 5) / 6;
-                for (int c = 1; c <= 8 && c <= nchmax; ++c) {
-                    const int cost = ((ntr * c + nwarps - 1) / nwarps) * ((nact + c - 1) / c + nd + 1);
-                    if (cost < best) {
+                constexpr int NW = RL_THREADS / 32; // == nwarps (the kernel is always launched with RL_THREADS)
+#pragma unroll
+                for (int c = 1; c <= 8; ++c) { // constant divisors: this runs once per pivot in every thread
+                    const int cost = ((ntr * c + NW - 1) / NW) * ((nact + c - 1) / c + nd + 1);
+                    if (c <= nchmax && cost < best) {
                         best = cost;
                         nch = c;
                     }
