@@ -272,7 +272,7 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
         // abs2, then smaller column position, then smaller row.  All compares are on integers (the squares
         // are non-negative, so their bit patterns are ordered) and the eight elements of a tile are reduced
         // as a tree, which keeps the dependent chain short.
-        unsigned long long bvb = 0ull;
+        double bq = -1.0; // this thread's best square (-1: none)
         int bcpv = 0x7fffffff, browv = 0x7fffffff;
         if (nact > 0) {
             // Tiles of RR_U*64 rows x 1 column are dealt round-robin to the warps; a lane issues its
@@ -295,7 +295,8 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
                 double *const cptr = RR_COL(acto[e]);
                 const int base = i0 + rt * (U * 64) + 2 * lane;
                 double2 d[U];
-                unsigned long long ob[2 * U];
+                double tq = -1.0; // best square of this tile (-1: none)
+                int tj = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = base + u * 64;
@@ -319,36 +320,21 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
                         if (v1ok) d[u].y = schur<EXACT>(d[u].y, x1, y);
                         *reinterpret_cast<double2 *>(cptr + i) = d[u]; // masked entries are written back unchanged
                     }
+                    // arg-max over the tile on the squares themselves: a strict > in row order keeps the first
+                    // maximum and never selects a NaN (matrixlu.jl:16-29); masked entries do not take part
                     const double q0 = d[u].x * d[u].x, q1 = d[u].y * d[u].y;
-                    ob[2 * u] = (v0ok && q0 == q0) ? (unsigned long long)__double_as_longlong(q0) + 1ull : 0ull;
-                    ob[2 * u + 1] = (v1ok && q1 == q1) ? (unsigned long long)__double_as_longlong(q1) + 1ull : 0ull;
-                }
-                // tree arg-max over the 2*RR_U elements, lower element index (= smaller row) wins ties
-                unsigned long long tb = ob[0];
-                int tj = 0;
-                {
-                    unsigned long long v1[U];
-                    int j1[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const bool hi = ob[2 * u + 1] > ob[2 * u];
-                        v1[u] = hi ? ob[2 * u + 1] : ob[2 * u];
-                        j1[u] = hi ? 2 * u + 1 : 2 * u;
+                    if (v0ok && q0 > tq) {
+                        tq = q0;
+                        tj = 2 * u;
                     }
-#pragma unroll
-                    for (int w = 1; w < U; w *= 2)
-#pragma unroll
-                        for (int u = 0; u + w < U; u += 2 * w) {
-                            const bool hi = v1[u + w] > v1[u];
-                            v1[u] = hi ? v1[u + w] : v1[u];
-                            j1[u] = hi ? j1[u + w] : j1[u];
-                        }
-                    tb = v1[0];
-                    tj = j1[0];
+                    if (v1ok && q1 > tq) {
+                        tq = q1;
+                        tj = 2 * u + 1;
+                    }
                 }
                 const int trow = base + (tj >> 1) * 64 + (tj & 1);
-                if (tb > bvb || (tb == bvb && tb != 0ull && (cp < bcpv || (cp == bcpv && trow < browv)))) {
-                    bvb = tb;
+                if (tq > bq || (tq == bq && tq >= 0.0 && (cp < bcpv || (cp == bcpv && trow < browv)))) {
+                    bq = tq;
                     bcpv = cp;
                     browv = trow;
                 }
@@ -371,8 +357,8 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
         }
         unsigned long long bkey = ((unsigned long long)(unsigned)bcpv << 32) | (unsigned)browv;
         RR_MARK(3);
-        // block reduction of the candidate (value bits, key)
-        unsigned long long vb = bvb;
+        // block reduction of the candidate (ordered value bits: the squares are non-negative; key)
+        unsigned long long vb = bq < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(bq) + 1ull;
         warp_argmax(vb, bkey);
         if (lane == 0) {
             red_v[warp] = vb;
