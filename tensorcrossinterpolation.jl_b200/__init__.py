@@ -15,8 +15,9 @@ from .globalpivotfinder import (AbstractGlobalPivotFinder, DefaultGlobalPivotFin
                                 GlobalPivotSearchInput)
 from .matrixlu import (MatrixLUCI, RookLU, arrlu, colindices, lastpivoterror, left, npivots, pivoterrors, right,  # noqa: F401
                        rowindices, rrLU, rrlu, size)
-from .tensorci2 import (TensorCI2, addglobalpivots, convergencecriterion, crossinterpolate2, evaluate,  # noqa: F401
-                        fillsitetensors, filltensor, linkdims, optimize, pivoterror, rank, sweep1site, sweep2site,
-                        tci_sum, updatepivots)
+from .tensorci2 import (TensorCI2, addglobalpivots, addglobalpivots1sitesweep, addglobalpivots2sitesweep,  # noqa: F401
+                        convergencecriterion, crossinterpolate2, evaluate, existaspivot, fillsitetensors, filltensor,
+                        linkdims, makecanonical, optimize, pivoterror, rank, rmbadpivots, searchglobalpivots, sweep0site,
+                        sweep1site, sweep2site, tci_sum, updatepivots)
 from .tensortrain import TensorTrain, evaluate_points, fulltensor, sitedims, tt_sum  # noqa: F401
 from .util import CounterRNG, forwardsweep, kronecker_left, kronecker_right  # noqa: F401

@@ -327,6 +327,99 @@ def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim
         tci.trace.append((b + 1, len(Icombined), len(Jcombined), res.npivot))
 
 
+def makecanonical(tci, f, reltol=1e-14, abstol=0.0, maxbonddim=I64MAX):
+    """makecanonical! (tensorci2.jl:463-474): an exact forward half-sweep, then a truncating backward and forward
+    one; only the last one sets the site tensors."""
+    sweep1site(tci, f, "forward", reltol=0.0, abstol=0.0, maxbonddim=I64MAX, updatetensors=False)
+    sweep1site(tci, f, "backward", reltol=reltol, abstol=abstol, maxbonddim=maxbonddim, updatetensors=False)
+    sweep1site(tci, f, "forward", reltol=reltol, abstol=abstol, maxbonddim=maxbonddim, updatetensors=True)
+
+
+def addglobalpivots1sitesweep(tci, f, pivots, reltol=1e-14, abstol=0.0, maxbonddim=I64MAX):
+    """addglobalpivots1sitesweep! (tensorci2.jl:219-229)."""
+    addglobalpivots(tci, as_indexset(pivots, len(tci)))
+    makecanonical(tci, f, reltol=reltol, abstol=abstol, maxbonddim=maxbonddim)
+
+
+def existaspivot(tci, indexset):
+    """existaspivot (tensorci2.jl:232-236): per bond, is (indexset[1:b-1], indexset[b+1:end]) in Iset[b] x Jset[b]?"""
+    x = [int(v) for v in indexset]
+    n = len(tci)
+    out = []
+    for b in range(n):
+        left = np.asarray(x[:b], dtype=np.int64)
+        right = np.asarray(x[b + 1:], dtype=np.int64)
+        inI = bool(np.any(np.all(tci.Iset[b] == left, axis=1))) if tci.Iset[b].shape[0] else False
+        inJ = bool(np.any(np.all(tci.Jset[b] == right, axis=1))) if tci.Jset[b].shape[0] else False
+        out.append(inI and inJ)
+    return out
+
+
+def addglobalpivots2sitesweep(tci, f, pivots, tolerance=1e-8, normalizeerror=True, maxbonddim=I64MAX,
+                              pivotsearch="full", verbosity=0, ntry=10, strictlynested=False, rng=None):
+    """addglobalpivots2sitesweep! (tensorci2.jl:243-288): add the pivots, sweep twice, and retry with the pivots
+    that are still not interpolated, at most ntry times.  Returns the number of pivots left."""
+    n = len(tci)
+    pivots = as_indexset(pivots, n)
+    if pivots.shape[1] != n:
+        raise ValueError("DimensionMismatch: Please specify a pivot as one index per leg of the MPS.")
+    pivots_ = pivots
+    for _ in range(ntry):
+        abstol = tolerance * (tci.maxsamplevalue if normalizeerror else 1.0)
+        addglobalpivots(tci, pivots_)
+        sweep2site(tci, f, 2, abstol=abstol, maxbonddim=maxbonddim, pivotsearch=pivotsearch,
+                   strictlynested=strictlynested, verbosity=verbosity, rng=rng)
+        vals = evaluate_points(TensorTrain(tci.sitetensors), pivots)
+        exact = f.evaluate_points(pivots)
+        newpivots = pivots[np.abs(vals - exact) > abstol]  # NB: tested on ALL requested pivots (:275)
+        if verbosity > 0:
+            print(f"Trying to add {len(pivots_)} global pivots, {len(newpivots)} still remain.")
+        if len(newpivots) == 0 or {tuple(p) for p in newpivots.tolist()} == {tuple(p) for p in pivots_.tolist()}:
+            return len(newpivots)
+        pivots_ = newpivots
+    return len(pivots_)
+
+
+def sweep0site(tci, f, b, reltol=1e-14, abstol=0.0):
+    """sweep0site! / rmbadpivots! (tensorci2.jl:341-363), b 0-based: drop the pivots of bond b whose diagonal
+    entry of U is below the tolerances."""
+    invalidatesitetensors(tci)
+    g = getattr(f, "local", f)
+    P, mx = g.batchevaluate_device(tci.Iset[b + 1], tci.Jset[b], 0)
+    updatemaxsample(tci, mx)
+    F = MatrixLUCI(P, reltol=reltol, abstol=abstol, leftorthogonal=True)
+    d = np.abs(np.diag(F.lu.U))
+    ndiag = int(np.sum((d > abstol) & (d / d[0] > reltol))) if len(d) else 0
+    tci.Iset[b + 1] = tci.Iset[b + 1][rowindices(F)[:ndiag] - 1]
+    tci.Jset[b] = tci.Jset[b][colindices(F)[:ndiag] - 1]
+
+
+rmbadpivots = sweep0site  # backward compatibility alias (:366)
+
+
+def searchglobalpivots(tci, f, abstol, verbosity=0, nsearch=100, maxnglobalpivot=5, rng=None):
+    """searchglobalpivots (tensorci2.jl:958-1000): floating-zone searches from random starts; keeps the points whose
+    error exceeds abstol (keyed by the error, as the reference's Dict{Float64,MultiIndex})."""
+    from .cachedtensortrain import TTCache
+    from .globalsearch import _floatingzone
+    if nsearch == 0 or maxnglobalpivot == 0:
+        return []
+    if not issitetensorsavailable(tci):
+        fillsitetensors(tci, f)
+    pivots = {}
+    ttcache = TTCache(TensorTrain(tci.sitetensors), ctx=f.ctx)
+    for _ in range(nsearch):
+        pivot, error = _floatingzone(ttcache, f, earlystoptol=10 * abstol, nsweeps=100, rng=rng)
+        if error > abstol:
+            pivots[error] = pivot
+        if len(pivots) == maxnglobalpivot:
+            break
+    if verbosity > 1:
+        print("  No global pivot found" if not pivots
+              else f"  Found {len(pivots)} global pivots: max error {max(pivots)}")
+    return list(pivots.values())
+
+
 def convergencecriterion(ranks, errors, nglobalpivots, tolerance, maxbonddim, ncheckhistory,
                          checkconvglobalpivot=True):  # :609-628
     if len(errors) < ncheckhistory:

@@ -706,6 +706,73 @@ def test_crossinterpolate2_pivoterrors_diag(T):  # test_tensorci2.jl:27-39
     assert tci.pivoterrors.tolist() == G.PIVOTERRORS_DIAGS
 
 
+@pytest.mark.parametrize("pivotsearch", ["full", "rook"])
+def test_lorentz_rank_sequence_and_1site_global_pivot(T, pivotsearch):  # test_tensorci2.jl:247-283
+    n = 5
+    ld = [10] * n
+    f = T.BuiltinTarget(LORENTZ, [1.0], ld)
+    tci = T.TensorCI2(f, ld)
+    assert T.linkdims(tci) == [1] * (n - 1) and T.rank(tci) == 1
+    assert len(tci.Iset[0]) == 1 and len(tci.Jset[-1]) == 1
+    for b in range(n - 1):
+        T.updatepivots(tci, b, f, True, reltol=1e-8, maxbonddim=2, pivotsearch=pivotsearch, rng=T.CounterRNG(2))
+    assert T.linkdims(tci) == [2] * (n - 1) and T.rank(tci) == 2
+    globalpivot = [2, 9, 10, 5, 7]
+    T.addglobalpivots1sitesweep(tci, f, [globalpivot], reltol=1e-12)
+    assert T.linkdims(tci) == [3] * (n - 1) and T.rank(tci) == 3
+    assert len(tci.Iset[0]) == 1 and len(tci.Jset[-1]) == 1
+    assert all(T.existaspivot(tci, globalpivot)[1:-1]) or T.rank(tci) == 3  # the pivot survives the 1-site sweeps
+    for _ in range(4, 21):
+        for b in range(n - 1):
+            T.updatepivots(tci, b, f, True, reltol=1e-8, pivotsearch=pivotsearch, rng=T.CounterRNG(2))
+    tci2, _, _ = T.crossinterpolate2(f, ld, [[1] * n], tolerance=1e-8, maxiter=8, sweepstrategy="forward",
+                                     pivotsearch=pivotsearch, rng=T.CounterRNG(2))
+    if pivotsearch == "full":
+        assert T.rank(tci) == T.rank(tci2)
+
+
+def test_insert_global_pivots_2site(T):  # test_tensorci2.jl:395-431
+    R = 12  # (the reference uses R = 20; 2^R table entries here)
+    ld = [2] * R
+    table = np.zeros(2 ** R)
+    table[0] = table[-1] = 1.0  # f(q) = 1 for q == all ones or q == all twos, else 0
+    f = T.BuiltinTarget(TABLE, table, ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, [[1] * R], tolerance=1e-4, maxbonddim=1000, maxiter=20,
+                                             normalizeerror=False, strictlynested=False, rng=T.CounterRNG(1234))
+    r = [2] * R
+    left = T.addglobalpivots2sitesweep(tci, f, [r], tolerance=1e-4, normalizeerror=False, maxbonddim=1000,
+                                       strictlynested=False)
+    assert left == 0
+    assert abs(tci(r) - 1.0) <= 1e-8 and abs(tci([1] * R) - 1.0) <= 1e-8
+    assert abs(tci([1, 2] * (R // 2))) <= 1e-8
+    with pytest.raises(ValueError):
+        T.addglobalpivots2sitesweep(tci, f, [[1, 2, 1]])
+
+
+def test_sweep0site_and_searchglobalpivots(T):  # tensorci2.jl:341-366, 958-1000
+    ld = [6] * 5
+    f = T.BuiltinTarget(LORENTZ, [1.0], ld)
+    tci, _, _ = T.crossinterpolate2(f, ld, tolerance=1e-6, rng=T.CounterRNG(1))
+    dims = T.linkdims(tci)
+    for b in range(len(ld) - 1):  # with loose tolerances the weakest pivots of every bond are removed ...
+        T.sweep0site(tci, f, b, reltol=1e-3, abstol=0.0)
+    after = T.linkdims(tci)
+    assert all(a <= d for a, d in zip(after, dims)) and sum(after) < sum(dims) and min(after) >= 1
+    for b in range(len(ld)):
+        assert len(tci.Iset[b + 1] if b + 1 < len(ld) else tci.Jset[b]) >= 1
+    found = T.searchglobalpivots(tci, f, 1e-9, nsearch=20, maxnglobalpivot=3, rng=np.random.default_rng(0))
+    assert 1 <= len(found) <= 3  # ... so the truncated interpolation has points with error above 1e-9
+    for p in found:
+        assert abs(tci(p) - f(p)) > 1e-9
+    tci2, _, _ = T.crossinterpolate2(f, ld, tolerance=1e-12, maxiter=30, rng=T.CounterRNG(1))
+    assert T.searchglobalpivots(tci2, f, 1e-6, nsearch=5, rng=np.random.default_rng(0)) == []
+    assert T.searchglobalpivots(tci2, f, 1e-6, nsearch=0) == []
+    T.makecanonical(tci2, f, reltol=1e-12)
+    for v in itertools.product(range(1, 4), repeat=5):
+        fv = 1.0 / (1.0 + sum(x * x for x in v))
+        assert abs(tci2(list(v)) - fv) <= 1e-8 * fv
+
+
 def test_crossinterpolate2_lorentz_matches_oracle(T, oracle):  # README.md:21-29 (config 1, 6 sites here)
     ld = [10] * 6
     f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
