@@ -19,5 +19,6 @@ from .tensorci2 import (TensorCI2, addglobalpivots, addglobalpivots1sitesweep, a
                         convergencecriterion, crossinterpolate2, evaluate, existaspivot, fillsitetensors, filltensor,
                         linkdims, makecanonical, optimize, pivoterror, rank, rmbadpivots, searchglobalpivots, sweep0site,
                         sweep1site, sweep2site, tci_sum, updatepivots)
-from .tensortrain import TensorTrain, evaluate_points, fulltensor, sitedims, tt_sum  # noqa: F401
+from .tensortrain import (TensorTrain, add, divide, evaluate_points, fulltensor, multiply, norm, norm2, reverse,  # noqa: F401
+                          sitedims, subtract, sum_dims, tensortrain, tt_sum)
 from .util import CounterRNG, forwardsweep, kronecker_left, kronecker_right  # noqa: F401

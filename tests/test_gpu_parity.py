@@ -653,6 +653,41 @@ def test_tt_to_tci2_then_optimize(T):  # test_conversion.jl:76-99 (real-valued)
         assert abs(tcib(list(v)) - 1.0 / (1.0 + sum(x * x for x in v))) < 1e-13
 
 
+def test_tensortrain_arithmetic(T):  # test_tensortrain.jl (add / subtract / multiply / divide / reverse / norm / sum)
+    rng = np.random.default_rng(31)
+    dims = [3, 2, 4, 3]
+    a = T.TensorTrain(_rand_tt(rng, [1, 3, 4, 2, 1], dims))
+    b = T.TensorTrain(_rand_tt(rng, [1, 2, 5, 3, 1], dims))
+    A, B = T.fulltensor(a), T.fulltensor(b)
+    c = T.add(a, b)
+    # bond dimensions add up (abstracttensortrain.jl:238) before the lossless recompression caps them at 3, 6, 3
+    assert [t.shape[0] for t in c.sitetensors[1:]] == [3, 6, 3]
+    np.testing.assert_allclose(T.fulltensor(c), A + B, rtol=1e-12, atol=1e-13)
+    c2 = T.add(a, b, factorlhs=2.0, factorrhs=-0.5, tolerance=1e-12)
+    np.testing.assert_allclose(T.fulltensor(c2), 2.0 * A - 0.5 * B, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(T.fulltensor(a - b), A - B, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(T.fulltensor(a + a), 2.0 * A, rtol=1e-12, atol=1e-13)
+    z = T.subtract(a, a, tolerance=1e-10)  # exact cancellation compresses to bond dimension 1
+    assert max(t.shape[0] for t in z.sitetensors[1:]) <= 1 or np.max(np.abs(T.fulltensor(z))) < 1e-12
+    np.testing.assert_allclose(T.fulltensor(3.0 * a), 3.0 * A, rtol=1e-14)
+    np.testing.assert_allclose(T.fulltensor(a * 3.0), 3.0 * A, rtol=1e-14)
+    np.testing.assert_allclose(T.fulltensor(a / 4.0), A / 4.0, rtol=1e-14)
+    np.testing.assert_allclose(T.fulltensor(T.reverse(a)), np.transpose(A, (3, 2, 1, 0)), rtol=1e-14)
+    assert abs(T.norm2(a) - np.sum(A * A)) <= 1e-12 * np.sum(A * A)
+    assert abs(T.norm(b) - np.linalg.norm(B)) <= 1e-12 * np.linalg.norm(B)
+    assert abs(T.sum_dims(a) - A.sum()) <= 1e-12 * abs(A).sum()
+    assert abs(T.sum_dims(a) - T.tt_sum(a)) <= 1e-12 * abs(A).sum()
+    s2 = T.sum_dims(a, dims=(2, 4))
+    np.testing.assert_allclose(T.fulltensor(s2), A.sum(axis=(1, 3)), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(T.fulltensor(T.sum_dims(a, dims=1)), A.sum(axis=0), rtol=1e-12, atol=1e-13)
+    assert abs(a([2, 1, 3, 2]) - A[1, 0, 2, 1]) <= 1e-14 * np.max(np.abs(A))
+    tt2 = T.tensortrain(a)
+    tt2.sitetensors[0][0, 0, 0] += 1.0  # tensortrain() copies
+    assert a.sitetensors[0][0, 0, 0] != tt2.sitetensors[0][0, 0, 0]
+    with pytest.raises(ValueError):
+        T.add(a, T.TensorTrain(_rand_tt(rng, [1, 2, 1], [3, 2])))
+
+
 # ------------------------------------------------------- K7 + the driver ----
 def test_globalsearch_matches_oracle(T, oracle):  # test_globalsearch.jl:7-36
     R = 10
