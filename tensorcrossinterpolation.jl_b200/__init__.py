@@ -17,7 +17,7 @@ from .matrixlu import (MatrixLUCI, RookLU, arrlu, colindices, lastpivoterror, le
                        rowindices, rrLU, rrlu, size)
 from .tensorci2 import (TensorCI2, addglobalpivots, addglobalpivots1sitesweep, addglobalpivots2sitesweep,  # noqa: F401
                         convergencecriterion, crossinterpolate2, evaluate, existaspivot, fillsitetensors, filltensor,
-                        linkdims, makecanonical, optimize, pivoterror, rank, rmbadpivots, searchglobalpivots, sweep0site,
+                        linkdims, makecanonical, optfirstpivot, optimize, pivoterror, rank, rmbadpivots, searchglobalpivots, sweep0site,
                         sweep1site, sweep2site, tci_sum, updatepivots)
 from .tensortrain import (TensorTrain, add, divide, evaluate_points, fulltensor, multiply, norm, norm2, reverse,  # noqa: F401
                           sitedims, subtract, sum_dims, tensortrain, tt_sum)

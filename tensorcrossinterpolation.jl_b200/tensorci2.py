@@ -327,6 +327,29 @@ def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim
         tci.trace.append((b + 1, len(Icombined), len(Jcombined), res.npivot))
 
 
+def optfirstpivot(f, localdims, firstpivot=None, maxsweep=1000):
+    """optfirstpivot (util.jl:78-109): coordinate ascent on |f| from `firstpivot`.  The reference evaluates one point
+    at a time (and notes "TODO: use batch evaluation"); here every site is one M = 1 fill on the device.  Accepting
+    `newval > valf` for d = 1, 2, ... in turn ends at the first index that attains the site's maximum, provided that
+    maximum exceeds the current value."""
+    n = len(localdims)
+    pivot = [1] * n if firstpivot is None else [int(v) for v in firstpivot]
+    valf = abs(float(f(pivot)))
+    for _ in range(maxsweep):
+        prev = valf
+        for i in range(n):
+            left = np.asarray([pivot[:i]], dtype=np.int64).reshape(1, i)
+            right = np.asarray([pivot[i + 1:]], dtype=np.int64).reshape(1, n - i - 1)
+            vals = np.abs(np.asarray(f(left, right, 1)).reshape(-1))
+            best = float(np.max(vals))
+            if best > valf:
+                valf = best
+                pivot[i] = int(np.argmax(vals)) + 1  # first maximum
+        if prev == valf:
+            break
+    return pivot
+
+
 def makecanonical(tci, f, reltol=1e-14, abstol=0.0, maxbonddim=I64MAX):
     """makecanonical! (tensorci2.jl:463-474): an exact forward half-sweep, then a truncating backward and forward
     one; only the last one sets the site tensors."""

@@ -766,6 +766,36 @@ def test_lorentz_rank_sequence_and_1site_global_pivot(T, pivotsearch):  # test_t
         assert T.rank(tci) == T.rank(tci2)
 
 
+def test_optfirstpivot(T):  # util.jl:78-109, used at test_tensorci2.jl:444
+    ld = [5, 4, 6, 3]
+    table = np.random.default_rng(8).standard_normal(int(np.prod(ld)))
+    f = T.BuiltinTarget(TABLE, table, ld)
+    tab = table.reshape(ld, order="F")
+
+    def reference(first, maxsweep=1000):  # the reference's point-by-point loop
+        pivot = list(first)
+        valf = abs(tab[tuple(p - 1 for p in pivot)])
+        for _ in range(maxsweep):
+            prev = valf
+            for i in range(len(ld)):
+                for d in range(1, ld[i] + 1):
+                    bak = pivot[i]
+                    pivot[i] = d
+                    newval = abs(tab[tuple(p - 1 for p in pivot)])
+                    if newval > valf:
+                        valf = newval
+                    else:
+                        pivot[i] = bak
+            if prev == valf:
+                break
+        return pivot
+
+    for first in ([1, 1, 1, 1], [5, 4, 6, 3], [2, 3, 1, 2]):
+        assert T.optfirstpivot(f, ld, first) == reference(first)
+    assert T.optfirstpivot(f, ld) == reference([1, 1, 1, 1])
+    assert T.optfirstpivot(f, ld, [2, 3, 1, 2], maxsweep=1) == reference([2, 3, 1, 2], maxsweep=1)
+
+
 def test_insert_global_pivots_2site(T):  # test_tensorci2.jl:395-431
     R = 12  # (the reference uses R = 20; 2^R table entries here)
     ld = [2] * R
