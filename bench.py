@@ -307,6 +307,66 @@ def main():
 RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 445872222720 + 130370041856}
 
 
+def extra_mpo_1024(T, ctx, torch, dist, rank, world):
+    extra = {}
+    # --- config 5 shape, the two-site Pi of the MPO x MPO target at the middle bond with nL = nR = 1024,
+    # at N > 1 sharded by ROW blocks of the left index set: every rank extends the left environments of its own rows,
+    # the right environments are replicated, the block goes into rank 0's HBM by peer stores ---
+    try:
+        nsites, Dm, nL = 40, 256, 1024
+        g5, g6, g7 = np.random.default_rng(5), np.random.default_rng(6), np.random.default_rng(8)
+
+        def mpo5(g):
+            bonds = [1] + [Dm] * (nsites - 1) + [1]
+            return [np.asfortranarray((g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(nsites)]
+
+        fm = T.Contraction(T.TensorTrain(mpo5(g5)), T.TensorTrain(mpo5(g6)))
+        Il = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
+        Jr = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
+        step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm
+        fl = 2 * nL * 19 * step + 2.0 * nL * Dm * Dm * nL
+        if world == 1:
+            dev, mx = fm.batchevaluate_device(Il, Jr, 0)
+            del dev
+            ctx.timers(reset=True)
+            dev, mx = fm.batchevaluate_device(Il, Jr, 0)
+            ms = ctx.timers(reset=True)["pi_eval"]
+            del dev
+            extra["mpo_pi_eval_config5_1024"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms,
+                                                 "shape": "40 sites, bonds 256, nL=nR=1024, M=0 (Pi 1024 x 1024)",
+                                                 "flop_model": "19 full environment extensions per row and per "
+                                                               "column + final (1024 x 65536) x (65536 x 1024) product"}
+        else:
+            from tci_b200.parallel import ShardedEvaluator
+            for shard in ("rows", "cols"):
+                sm = ShardedEvaluator(fm, dist, torch, mode="peer", shard=shard)
+                for it in range(3):
+                    if it == 1:
+                        torch.cuda.synchronize()
+                        dist.barrier()
+                        t0 = time.perf_counter()
+                    dev, mx = sm.batchevaluate_device(Il, Jr, 0)
+                    del dev
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / 2
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+                sm.release()
+                # per rank: its own share of one chain, the whole of the other chain, its share of the product
+                extra[f"mpo_pi_eval_config5_1024_sharded_{shard}"] = {
+                    "ms": dt * 1e3, "tflops_useful": fl / dt / 1e12,
+                    "note": (f"row blocks over {world} ranks: left environments of the rank's rows, right environments "
+                             "of its column block + one NCCL all-gather, block product stored into rank 0's HBM"
+                             if shard == "rows" else
+                             f"column blocks over {world} ranks, left environments recomputed on every rank") +
+                            "; wall clock incl. index upload, barrier and max all-reduce"}
+        del fm
+    except Exception as e:  # never let an extra take the headline line down
+        extra["mpo_pi_eval_config5_1024"] = {"error": str(e)[:200]}
+    return extra
+
+
 def run_extra(T, ctx, torch, dist, rank, world, stream):
     """Secondary numbers of the composite metric: Pi-eval Mevals/s (config 4 shape, column blocks
     sharded over ranks), DGEMM GFLOP/s (the contraction building block), and the README config 1
@@ -451,6 +511,7 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         tci, ranks, errors = T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
         extra["crossinterpolate2_config1"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks[-1]),
                                               "iterations": len(ranks), "error": float(errors[-1])}
+    extra.update(extra_mpo_1024(T, ctx, torch, dist, rank, world))
     if rank == 0:
         # --- config 4 scale: one bond's rrLU, 32768 x 32768 (8.6 GB, 12 sites d=64 at chi=512), maxrank 512.
         # The config-4 target itself is numerically of rank ~23, so its Pi never needs 512 pivots; the kernel is

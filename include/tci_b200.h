@@ -120,6 +120,21 @@ int tci_pi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, i
 int tci_pi_eval_into(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
                      int64_t nr, int64_t nJ, int64_t M, tci_dmat *dst, int64_t col0, double *maxabs);
 
+/* Environments of a TT / MPO-pair target as device matrices of their own, so that the two chains of a
+ * contraction Pi can be sharded independently over GPUs ("MPO x MPO contraction: row blocks"):
+ * side 0 = evaluateleft over the first `len` sites, side 1 = evaluateright over the last `len` sites
+ * (cachedtensortrain.jl:77-128, contraction.jl:112-176).  idx is (len x count), entry q contiguous.  Column
+ * col0+q of dst receives the environment of entry q; dst->m must equal tci_env_dim (the bond dimension of a
+ * TT, Da*Db of an MPO pair, 1 for len == 0).  Analytic targets: TCI_ERR_ARG.                          */
+int tci_env_dim(tci_ctx *ctx, int64_t target_id, int side, int64_t len, int64_t *D);
+int tci_env_eval(tci_ctx *ctx, int64_t target_id, int side, const int64_t *idx, int64_t len, int64_t count,
+                 tci_dmat *dst, int64_t col0);
+/* The M = 0 Pi from such environments (cachedtensortrain.jl:211-212, contraction.jl:328):
+ * dst[:, col0 + j] = left[:, l0 + i]^T right[:, r0 + j], i < nI, j < nJ; dst->m must be nI.  *maxabs as in
+ * tci_pi_eval (nullable).                                                                              */
+int tci_pi_from_envs(tci_ctx *ctx, tci_dmat *left, int64_t l0, int64_t nI, tci_dmat *right, int64_t r0, int64_t nJ,
+                     tci_dmat *dst, int64_t col0, double *maxabs);
+
 /* ---- (b) rank-revealing LU / MatrixLUCI ---------------------------------- */
 /* rrlu(A; maxrank, reltol, abstol, leftorthogonal) (matrixlu.jl:194-225) with the
  * full-pivot search and Schur updates of matrixlu.jl:1-32,98-181.  Exactly one of

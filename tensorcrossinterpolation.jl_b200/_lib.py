@@ -47,6 +47,9 @@ SYMBOLS = {
     "tci_target_eval": (C.c_int, [VP, i64, P_i64, i64, P_f64]),
     "tci_pi_eval": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, P_f64, C.POINTER(VP), P_f64]),
     "tci_pi_eval_into": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, VP, i64, P_f64]),
+    "tci_env_dim": (C.c_int, [VP, i64, C.c_int, i64, P_i64]),
+    "tci_env_eval": (C.c_int, [VP, i64, C.c_int, P_i64, i64, i64, VP, i64]),
+    "tci_pi_from_envs": (C.c_int, [VP, VP, i64, i64, VP, i64, i64, VP, i64, P_f64]),
     "tci_rrlu": (C.c_int, [VP, P_f64, VP, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64, P_i64, P_i64, P_f64,
                            P_f64, C.POINTER(VP)]),
     "tci_lu_fetch": (C.c_int, [VP, P_f64, P_f64]),

@@ -80,6 +80,30 @@ class BatchEvaluator:
                                               J.shape[0], M, dst.h, int(col0), C.byref(mx)))
         return mx.value
 
+    # ---- environments of TT / MPO-pair targets as objects of their own (tci_env_eval) ----
+    has_environments = False  # TTCache and Contraction set this
+
+    def env_dim(self, side, length):
+        D = C.c_int64(0)
+        self.ctx.check(lib().tci_env_dim(self.ctx.h, self.id, int(side), int(length), C.byref(D)))
+        return D.value
+
+    def env_eval_into(self, dst, col0, side, indexset):
+        """Environments (side 0: evaluateleft, side 1: evaluateright) of the entries of `indexset` into
+        dst[:, col0:col0+len(indexset)]."""
+        idx = as_indexset(indexset)
+        if len(idx):
+            self.ctx.check(lib().tci_env_eval(self.ctx.h, self.id, int(side), pi(idx), idx.shape[1], idx.shape[0],
+                                              dst.h, int(col0)))
+
+    def pi_from_envs(self, left, l0, nI, right, r0, nJ, dst, col0):
+        """dst[:, col0:col0+nJ] = left[:, l0:l0+nI]^T right[:, r0:r0+nJ]; returns max|block|."""
+        mx = C.c_double(0.0)
+        self.ctx.check(lib().tci_pi_from_envs(self.ctx.h, left.h, int(l0), int(nI), right.h, int(r0), int(nJ), dst.h,
+                                              int(col0), C.byref(mx)))
+        self.nevals += int(nI) * int(nJ)
+        return mx.value
+
     def __del__(self):
         try:
             lib().tci_target_destroy(self.ctx.h, self.id)

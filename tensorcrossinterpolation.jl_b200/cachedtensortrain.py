@@ -11,6 +11,8 @@ from .batcheval import BatchEvaluator
 
 
 class TTCache(BatchEvaluator):
+    has_environments = True
+
     def __init__(self, tt, sitedims=None, ctx=None):
         ctx = ctx or _lib.default_context()
         cores = tt.sitetensors if hasattr(tt, "sitetensors") else list(tt)

@@ -17,6 +17,7 @@ I64MAX = 2**63 - 1
 
 class Contraction(BatchEvaluator):
     """struct Contraction (contraction.jl:5-62); f (elementwise function) is not supported on device."""
+    has_environments = True
 
     def __init__(self, a, b, f=None, ctx=None):
         ctx = ctx or _lib.default_context()

@@ -129,6 +129,16 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
     return TCI_OK;
 }
 
+// environments alone (tci_env_eval): evaluateleft / evaluateright of contraction.jl:112-176 for `count` entries
+int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D)
+{
+    i64 a = 1, b = 1;
+    int rc = side == 0 ? mpo_left_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b)
+                       : mpo_right_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b);
+    *D = a * b;
+    return rc;
+}
+
 // batchevaluate(::Contraction) contraction.jl:236-335 (projector = nothing, f = nothing)
 int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
                 tci_dmat *out)

@@ -367,6 +367,87 @@ extern "C" int tci_pi_eval_into(tci_ctx *ctx, int64_t target_id, const int64_t *
     return pi_eval_core(ctx, target_id, I, nl, nI, J, nr, nJ, M, nullptr, nullptr, dst, col0, maxabs);
 }
 
+// ---- environments of TT / MPO-pair targets as objects of their own (sharded contraction) ----
+static i64 env_dim_of(const TargetDev &t, int side, i64 len)
+{
+    if (len == 0) return 1;
+    const i64 n = t.nsites;
+    if (t.kind == 1) return side == 0 ? t.dr[len - 1] : t.dl[n - len];
+    return side == 0 ? t.adr[len - 1] * t.bdr[len - 1] : t.adl[n - len] * t.bdl[n - len];
+}
+
+extern "C" int tci_env_dim(tci_ctx *ctx, int64_t target_id, int side, int64_t len, int64_t *D)
+{
+    TCI_ENTER(ctx);
+    auto it = ctx->targets.find(target_id);
+    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    TargetDev &t = *it->second;
+    if (t.kind == 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
+    if (!D || (side != 0 && side != 1) || len < 0 || len > t.nsites)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: bad arguments");
+    *D = env_dim_of(t, side, len);
+    return TCI_OK;
+}
+
+extern "C" int tci_env_eval(tci_ctx *ctx, int64_t target_id, int side, const int64_t *idx, int64_t len, int64_t count,
+                            tci_dmat *dst, int64_t col0)
+{
+    TCI_ENTER(ctx);
+    auto it = ctx->targets.find(target_id);
+    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    TargetDev &t = *it->second;
+    if (t.kind == 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: an analytic target has no environments");
+    if (!dst || (side != 0 && side != 1) || len < 0 || len > t.nsites || count < 0 || (len > 0 && count > 0 && !idx))
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: bad arguments");
+    if (dst->m != env_dim_of(t, side, len) || col0 < 0 || col0 + count > dst->ncap)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: destination block does not fit");
+    if (count == 0) return TCI_OK;
+    dmat_wait_ready(ctx, dst);
+    DevBuf<i64> d_idx(ctx);
+    TCI_CUDA(ctx, d_idx.upload(idx, (size_t)(len * count)));
+    StageTimer tm(ctx, ST_ENV);
+    double *env = nullptr;
+    i64 D = 1;
+    int rc = t.kind == 1 ? env_eval_tt(ctx, t, side, d_idx.p, (int)len, count, &env, &D)
+                         : env_eval_mpo(ctx, t, side, d_idx.p, (int)len, count, &env, &D);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy2DAsync(dst->p + dst->ld * col0, dst->ld * sizeof(double), env, D * sizeof(double),
+                                      D * sizeof(double), count, cudaMemcpyDeviceToDevice, ctx->stream);
+    dev_free(ctx, env);
+    TCI_CUDA(ctx, e);
+    tm.stop();
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
+}
+
+extern "C" int tci_pi_from_envs(tci_ctx *ctx, tci_dmat *left, int64_t l0, int64_t nI, tci_dmat *right, int64_t r0,
+                                int64_t nJ, tci_dmat *dst, int64_t col0, double *maxabs)
+{
+    TCI_ENTER(ctx);
+    if (!left || !right || !dst || nI < 0 || nJ < 0 || l0 < 0 || r0 < 0 || col0 < 0)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_from_envs: bad arguments");
+    if (left->m != right->m || l0 + nI > left->ncap || r0 + nJ > right->ncap || dst->m != nI || col0 + nJ > dst->ncap)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_from_envs: shapes do not fit");
+    if (maxabs) *maxabs = 0.0;
+    if (nI * nJ == 0) return TCI_OK;
+    DevBuf<unsigned long long> dmax(ctx);
+    TCI_CUDA(ctx, dmax.alloc(2));
+    TCI_CUDA(ctx, cudaMemsetAsync(dmax.p, 0, 16, ctx->stream));
+    StageTimer tm(ctx, ST_PI);
+    double *out = dst->p + dst->ld * col0;
+    // Pi[i, j] = sum_a left[a, i] * right[a, j]     cachedtensortrain.jl:211-212, contraction.jl:328
+    int rc = dgemm_dev(ctx, true, false, nI, nJ, left->m, 1.0, left->p + left->ld * l0, left->ld,
+                       right->p + right->ld * r0, right->ld, 0.0, out, dst->ld);
+    if (!rc && maxabs) rc = maxabs_dev(ctx, out, nI, nJ, dst->ld, dmax.p);
+    if (rc) return rc;
+    tm.stop();
+    unsigned long long bits = 0;
+    if (maxabs) TCI_CUDA(ctx, cudaMemcpyAsync(&bits, dmax.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (maxabs) memcpy(maxabs, &bits, sizeof(double));
+    return TCI_OK;
+}
+
 // ---- scalar evaluation f(x) for a batch of full multi-indices ---------------
 __global__ void k_eval_points(tci_analytic_t t, const i64 *__restrict__ idx, i64 count, double *__restrict__ out)
 {

@@ -175,4 +175,6 @@ int pi_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const 
                tci_dmat *out);
 int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
                 tci_dmat *out);
+int env_eval_tt(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D);
+int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D);
 int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits);

@@ -181,6 +181,18 @@ static std::vector<CoreView> views(const TargetDev &t)
     return v;
 }
 
+// environments alone (tci_env_eval): side 0 = evaluateleft over the first len sites, side 1 = evaluateright over the
+// last len sites (cachedtensortrain.jl:77-128), GEMM form as in the batched Pi
+int env_eval_tt(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D)
+{
+    std::vector<CoreView> cv = views(t);
+    int d = 1;
+    int rc = side == 0 ? env_left_chain(ctx, cv, len, d_idx, len, 0, count, out, &d, false)
+                       : env_right_chain(ctx, cv, len, d_idx, len, 0, count, out, &d, false);
+    *D = d;
+    return rc;
+}
+
 // batchevaluate(::TTCache) cachedtensortrain.jl:151-215 (projector = nothing)
 int pi_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
                tci_dmat *out)

@@ -4,6 +4,11 @@
 * Pi evaluation: contiguous column blocks of Jcombined.  Every rank evaluates its block with
   K1/K4/K5 straight into its slice of the full buffer (tci_pi_eval_into), ONE in-place
   all-gather assembles Pi on every rank, and an 8-byte all-reduce(max) combines max|Pi|.
+* MPO x MPO contraction (and TT) targets shard by ROW blocks of Icombined (`shard="rows"`): every
+  rank extends the left environments of its own rows and the right environments of its own column block
+  (tci_env_eval), ONE NCCL all-gather shares the right environments, and the rank's block Pi = left^T right
+  (tci_pi_from_envs) is stored into the owner's Pi at its row offset -- so both chains, which carry nearly all the
+  flops, scale with the number of GPUs.
 * The per-bond rrLU stays on one GPU (rank `owner`), which broadcasts the chosen pivots
   (npivot, row/column indices, pivot errors) -- the only other collective of a bond update.
 * Global pivot search: the independent start points are dealt round-robin; the accepted
@@ -23,6 +28,14 @@ def column_blocks(ncols, world):
     """Equal-width contiguous column blocks (the last ones may be short or empty)."""
     blk = (ncols + world - 1) // world if ncols else 0
     return blk, [(min(r * blk, ncols), min((r + 1) * blk, ncols)) for r in range(world)]
+
+
+def row_blocks(nrows, world, align=16):
+    """Contiguous row blocks whose starts are multiples of `align` rows (128-byte lines of the column-major Pi, so
+    the evaluation kernels' 16-byte stores stay aligned); the last ones may be short or empty."""
+    blk = (nrows + world - 1) // world if nrows else 0
+    blk = (blk + align - 1) // align * align
+    return blk, [(min(r * blk, nrows), min((r + 1) * blk, nrows)) for r in range(world)]
 
 
 def maxabs_allreduce(dist, torch, value, device, group=None):
@@ -81,13 +94,18 @@ def broadcast_pivots(dist, result, owner, group=None):
 class ShardedEvaluator(BatchEvaluator):
     """Wraps a BatchEvaluator for world_size > 1: Pi is evaluated in column blocks (GPU path)."""
 
-    def __init__(self, f, dist, torch, owner=0, group=None, mode="peer"):
-        """mode "peer": every rank's evaluation kernel stores its column block straight into the rrLU
+    def __init__(self, f, dist, torch, owner=0, group=None, mode="peer", shard="cols"):
+        """shard "cols": column blocks of Jcombined; shard "rows" (peer mode, M = 0 calls): row blocks of Icombined,
+        the partitioning of the MPO x MPO contraction -- other calls fall back to column blocks.
+        mode "peer": every rank's evaluation kernel stores its column block straight into the rrLU
         owner's HBM through an IPC-mapped pointer (NVLink peer st.global; compute and transfer are the
         same kernel).  mode "allgather": per-rank blocks + one NCCL all-gather (every rank ends with Pi)."""
         self.f, self.dist, self.torch, self.owner, self.group = f, dist, torch, owner, group
         self.local = f  # unsharded evaluator for the small replicated stages (sweep1site)
         self.mode = mode
+        if shard not in ("cols", "rows"):
+            raise ValueError(f"Unknown sharding {shard}. Choose from cols, rows.")
+        self.shard = shard
         self._ptr, self._cap = None, 0
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -147,9 +165,36 @@ class ShardedEvaluator(BatchEvaluator):
         ld = (rows + 15) // 16 * 16
         self._ensure_shared(ld * nJ * 8)
         view = DeviceMatrix.wrap(self.ctx, self._ptr, rows, nJ, ld)
-        blk, ranges = column_blocks(nJ, self.world)
-        lo, hi = ranges[self.rank]
-        mx = self.f.batchevaluate_into(view, lo, I, J[lo:hi], M) if hi > lo else 0.0
+        if self.shard == "rows" and M == 0:
+            blk, ranges = row_blocks(rows, self.world)
+            lo, hi = ranges[self.rank]
+            mx = 0.0
+            # rows lo..hi of every column: a view that starts lo rows into the owner's buffer
+            mine = DeviceMatrix.wrap(self.ctx, self._ptr + 8 * lo, hi - lo, nJ, ld) if hi > lo else None
+            if getattr(self.f, "has_environments", False):
+                # TT / MPO x MPO target: BOTH environment chains are sharded.  Every rank extends the right
+                # environments of its column block, one NCCL all-gather (in place, over NVLink) gives every rank all
+                # of them, then the rank extends the left environments of its own rows and its block of
+                # Pi = left^T right goes to the owner by peer stores from the GEMM.
+                D = self.f.env_dim(1, J.shape[1])
+                cblk, cr = column_blocks(nJ, self.world)
+                renv = DeviceMatrix.empty(self.ctx, D, cblk * self.world)
+                self.f.env_eval_into(renv, self.rank * cblk, 1, J[cr[self.rank][0]:cr[self.rank][1]])
+                rv = torch.as_tensor(renv, device=torch.device("cuda", self.ctx.device))
+                gather_column_blocks(dist, torch, rv, cblk, self.rank, self.group)
+                torch.cuda.current_stream().synchronize()
+                if mine is not None:
+                    lenv = DeviceMatrix.empty(self.ctx, self.f.env_dim(0, I.shape[1]), hi - lo)
+                    self.f.env_eval_into(lenv, 0, 0, I[lo:hi])
+                    mx = self.f.pi_from_envs(lenv, 0, hi - lo, renv, 0, nJ, mine, 0)
+                    del lenv
+                del rv, renv
+            elif mine is not None:
+                mx = self.f.batchevaluate_into(mine, 0, I[lo:hi], J, 0)
+        else:
+            blk, ranges = column_blocks(nJ, self.world)
+            lo, hi = ranges[self.rank]
+            mx = self.f.batchevaluate_into(view, lo, I, J[lo:hi], M) if hi > lo else 0.0
         torch.cuda.synchronize()  # the block is in the owner's HBM when the kernel has retired
         dist.barrier(group=self.group)
         mx = maxabs_allreduce(dist, torch, mx, torch.device("cuda", self.ctx.device), self.group)

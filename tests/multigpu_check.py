@@ -27,8 +27,8 @@ def main():
     ]:
         f = T.BuiltinTarget(kind, params, ld)
         ref, rr, re = T.crossinterpolate2(f, ld, rng=T.CounterRNG(3), **kw)
-        for mode in ("peer", "allgather"):
-            sf = ShardedEvaluator(f, dist, torch, mode=mode)
+        for mode, shard in (("peer", "cols"), ("allgather", "cols"), ("peer", "rows")):
+            sf = ShardedEvaluator(f, dist, torch, mode=mode, shard=shard)
             tci, ranks, errors = T.crossinterpolate2(sf, ld, rng=T.CounterRNG(3), **kw)
             sf.release()
             same = ranks == rr and errors == re and all(
@@ -36,7 +36,37 @@ def main():
                 np.array_equal(a, b) for a, b in zip(tci.sitetensors, ref.sitetensors))
             ok = ok and same
             if rank == 0:
-                print(f"{name}/{mode}: world={world} rank={ranks[-1]} identical_to_single_gpu={same}")
+                print(f"{name}/{mode}/{shard}: world={world} rank={ranks[-1]} identical_to_single_gpu={same}")
+    # MPO x MPO contraction target (config-5 family, reduced): Pi sharded by row blocks of the left index set, every
+    # rank's block stored into rank 0's HBM; the assembled Pi must equal the unsharded evaluation to 1e-12 (the GEMM tiling
+    # may depend on the block height), and crossinterpolate2 driven through the sharded evaluator must pick the same pivots.
+    g = np.random.default_rng(11)
+    ns, D = 8, 12
+    bonds = [1] + [D] * (ns - 1) + [1]
+    A = [np.asfortranarray(g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) for i in range(ns)]
+    B = [np.asfortranarray(g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) for i in range(ns)]
+    fm = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    I = np.stack([g.integers(1, 5, 150) for _ in range(4)], axis=1).astype(np.int64)
+    J = np.stack([g.integers(1, 5, 130) for _ in range(4)], axis=1).astype(np.int64)
+    full, mx0 = fm.batchevaluate_device(I, J, 0)
+    for shard in ("rows", "cols"):
+        sm = ShardedEvaluator(fm, dist, torch, mode="peer", shard=shard)
+        view, mx = sm.batchevaluate_device(I, J, 0)
+        same = abs(mx - mx0) <= 1e-12 * mx0 and (
+            rank != 0 or np.max(np.abs(view.to_host() - full.to_host())) <= 1e-12 * mx0)
+        ok = ok and same
+        if rank == 0:
+            print(f"mpo Pi {I.shape[0]}x{J.shape[0]}/peer/{shard}: world={world} identical_to_single_gpu={same}")
+        del view
+        ld = fm.localdims
+        ref, rr, re = T.crossinterpolate2(fm, ld, rng=T.CounterRNG(5), tolerance=1e-8, maxbonddim=30, maxiter=4)
+        tci, ranks, errors = T.crossinterpolate2(sm, ld, rng=T.CounterRNG(5), tolerance=1e-8, maxbonddim=30, maxiter=4)
+        same = ranks == rr and np.allclose(errors, re, rtol=1e-6, atol=0) and all(
+            np.array_equal(a, b) for a, b in zip(tci.Iset + tci.Jset, ref.Iset + ref.Jset))
+        ok = ok and same
+        if rank == 0:
+            print(f"mpo crossinterpolate2/peer/{shard}: world={world} rank={ranks[-1]} identical_to_single_gpu={same}")
+        sm.release()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

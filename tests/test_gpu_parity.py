@@ -529,6 +529,49 @@ def test_mpo_target(T, oracle):  # test_contraction.jl:68-146 (real-valued)
         np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
 
 
+def test_environments_abi(T, oracle):
+    """tci_env_eval / tci_pi_from_envs (the pieces the row-block sharding of the contraction is made of): the M = 0
+    Pi assembled from separately evaluated left / right environment blocks equals the oracle's batchevaluate
+    (cachedtensortrain.jl:151-215, contraction.jl:236-335) for every split, also block by block."""
+    rng = np.random.default_rng(15)
+    dims = [2, 3, 3, 2, 4]
+    cores = _rand_tt(rng, [1, 2, 5, 3, 2, 1], dims)
+    d1, d2, d3 = [2, 2, 3, 2, 2], [2, 3, 2, 2, 3], [3, 2, 2, 2, 2]
+    A = _rand_mpo(rng, [1, 2, 3, 4, 2, 1], d1, d2)
+    B = _rand_mpo(rng, [1, 3, 2, 3, 3, 1], d2, d3)
+    for f, o in ((T.TTCache(T.TensorTrain(cores)), oracle.Target.tt(cores)),
+                 (T.Contraction(T.TensorTrain(A), T.TensorTrain(B)), oracle.Target.mpo_pair(A, B))):
+        ld, N = f.localdims, len(f.localdims)
+        assert f.has_environments
+        for nl in range(N + 1):
+            nr = N - nl
+            I = rand_indexset(rng, ld[:nl], 37 if nl else 1)
+            J = rand_indexset(rng, ld[nl:], 21 if nr else 1)
+            oref, omx = o.pi_eval(I.tolist(), J.tolist(), 0)
+            Dl, Dr = f.env_dim(0, nl), f.env_dim(1, nr)
+            assert Dl == Dr
+            lenv = T.DeviceMatrix.empty(f.ctx, Dl, len(I))
+            renv = T.DeviceMatrix.empty(f.ctx, Dr, len(J))
+            h = len(J) // 2
+            f.env_eval_into(lenv, 0, 0, I)
+            f.env_eval_into(renv, h, 1, J[h:])  # two column blocks, as two ranks would fill them
+            f.env_eval_into(renv, 0, 1, J[:h])
+            out = T.DeviceMatrix.empty(f.ctx, len(I), len(J))
+            mx = f.pi_from_envs(lenv, 0, len(I), renv, 0, len(J), out, 0)
+            got = out.to_host()
+            np.testing.assert_allclose(got, oref, rtol=RTOL, atol=1e-13)
+            assert abs(mx - omx) <= RTOL * omx
+            # a row block of Pi written into its place of a larger matrix through a wrapped view
+            if len(I) > 16:
+                big = T.DeviceMatrix.empty(f.ctx, len(I), len(J))
+                view = T.DeviceMatrix.wrap(f.ctx, big.ptr + 8 * 16, len(I) - 16, len(J), big.ld)
+                f.pi_from_envs(lenv, 16, len(I) - 16, renv, 0, len(J), view, 0)
+                assert np.array_equal(big.to_host()[16:], got[16:])
+    g = T.BuiltinTarget(T.LORENTZ, [1.0], [3, 3])
+    with pytest.raises(ValueError, match="no environments"):
+        g.env_dim(0, 1)
+
+
 def test_zipup_and_naive_site(T):  # contraction.jl:338-349, 455-464
     import ctypes as C
     from tci_b200 import _lib

@@ -51,6 +51,18 @@ def _worker(rank, world, port, q):
         res["maxabs"] = P.maxabs_allreduce(dist, torch, mx, "cpu") == refmx
         nanmax = P.maxabs_allreduce(dist, torch, float("nan") if rank == 1 else 1.0, "cpu")
         res["nan"] = nanmax != nanmax
+        # ---- sharded Pi: row blocks (the MPO x MPO partitioning), each rank's rows written at their offset ----
+        rblk, rranges = P.row_blocks(len(I), world)
+        rlo, rhi = rranges[rank]
+        part = torch.zeros((len(J), ldm), dtype=torch.float64)
+        if rhi > rlo:
+            blockv, bmx = o.pi_eval(I[rlo:rhi].tolist(), J.tolist(), 0, 0.0)
+            part[:, rlo:rhi] = torch.from_numpy(np.ascontiguousarray(blockv.T))
+        else:
+            bmx = 0.0
+        dist.all_reduce(part)  # stands in for the peer stores into the owner's buffer (disjoint row ranges)
+        res["pi_rows_equal"] = bool(np.array_equal(part[:, :23].numpy().T, ref))
+        res["maxabs_rows"] = P.maxabs_allreduce(dist, torch, bmx, "cpu") == refmx
         # ---- sharded global search ----
         R = 10
         t = orc.Target.builtin(6, [R, 1], [2] * R)
@@ -103,5 +115,10 @@ def test_column_blocks():
     assert column_blocks(10, 4) == (3, [(0, 3), (3, 6), (6, 9), (9, 10)])
     assert column_blocks(2, 4) == (1, [(0, 1), (1, 2), (2, 2), (2, 2)])
     assert column_blocks(0, 2) == (0, [(0, 0), (0, 0)])
+    from tci_b200.parallel import row_blocks
+    assert row_blocks(100, 2) == (64, [(0, 64), (64, 100)])
+    assert row_blocks(10, 4) == (16, [(0, 10), (10, 10), (10, 10), (10, 10)])
+    assert row_blocks(4096, 8) == (512, [(512 * r, 512 * (r + 1)) for r in range(8)])
+    assert row_blocks(0, 2) == (0, [(0, 0), (0, 0)])
     pts, es = select_global_pivots([(3, [1, 1], 0.3), (0, [2, 2], 0.1), (2, [1, 2], 0.2)], 2)
     assert pts == [[2, 2], [1, 2]] and es == [0.1, 0.2]
