@@ -307,6 +307,96 @@ def main():
 RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 445872222720 + 130370041856}
 
 
+def cpu_baselines_secondary():
+    """CPU numbers for the secondary stages on this box's host cores: Pi-eval through the oracle port on
+    one core (the reference's filltensor loop is single threaded, batcheval.jl:50-58), and the OpenBLAS DGEMM that
+    stands behind the reference's TT / MPO contractions (cachedtensortrain.jl:207-212, contraction.jl:92) at 1 and at
+    all threads.  Reported baselines, not targets."""
+    out = {}
+    try:
+        from oracle import oracle as orc
+        ld = [64] * 12
+        g = np.random.default_rng(7)
+        I = np.stack([g.integers(1, 65, 1024) for _ in range(6)], axis=1).tolist()
+        J = np.stack([g.integers(1, 65, 1024) for _ in range(6)], axis=1).tolist()
+        o = orc.Target.builtin(1, [1.0], ld)
+        o.pi_eval(I[:64], J[:64], 0, 0.0)
+        t0 = time.perf_counter()
+        o.pi_eval(I, J, 0, 0.0)
+        dt = time.perf_counter() - t0
+        out["pi_eval_lorentz"] = {"mevals_per_s": 1024 * 1024 / dt / 1e6, "cores": 1, "kind": "port",
+                                  "sample": "1024 x 1024 block of the 12-site d=64 Lorentzian Pi"}
+    except Exception as e:
+        out["pi_eval_lorentz"] = {"error": str(e)[:200]}
+    try:
+        import threadpoolctl
+        N = 2048
+        g = np.random.default_rng(8)
+        A, B = g.standard_normal((N, N)), g.standard_normal((N, N))
+        nproc = os.cpu_count() or 1
+        for nt in sorted({1, nproc}):
+            with threadpoolctl.threadpool_limits(limits=nt, user_api="blas"):
+                A @ B
+                t0 = time.perf_counter()
+                reps = 1 if nt == 1 else 3
+                for _ in range(reps):
+                    A @ B
+                dt = (time.perf_counter() - t0) / reps
+            out[f"openblas_dgemm_2048_threads{nt}"] = {"gflops": 2.0 * N ** 3 / dt / 1e9, "threads": nt}
+        info = [d for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
+        out["blas"] = {"library": info[0].get("internal_api") if info else None,
+                       "version": info[0].get("version") if info else None, "host_cores": nproc}
+    except Exception as e:
+        out["openblas_dgemm"] = {"error": str(e)[:200]}
+    return out
+
+
+def extra_globalsearch(T, ctx, torch, dist, rank, world):
+    """Default global pivot finder (globalpivotfinder.jl:143-195) at config-4 shape: 12 sites d=64, current TT of bond
+    dimension 128, 2048 random starts = 1.57 M star probes |f - tt|, the starts dealt round-robin over the ranks and the
+    accepted candidates all-gathered."""
+    extra = {}
+    try:
+        ld, chi, nsearch = [64] * 12, 128, 2048
+        g = np.random.default_rng(4)
+        params = np.concatenate([[4], g.integers(1, 1025, 12) / 256.0, g.integers(-512, 513, 4) / 1024.0,
+                                 (g.integers(-1024, 1025, (4, 12)) / 32.0).flatten()])
+        f = T.BuiltinTarget(T.SEPCOS, params, ld)
+        bonds = [1] + [chi] * 11 + [1]
+        g9 = np.random.default_rng(9)
+        tt = T.TensorTrain([np.asfortranarray((g9.random((bonds[i], 64, bonds[i + 1])) * 2 - 1) / np.sqrt(bonds[i]))
+                            for i in range(12)])
+        finder = T.DefaultGlobalPivotFinder(nsearch=nsearch, maxnglobalpivot=5)
+        inp = T.GlobalPivotSearchInput(ld, tt, 1.0, None, None)
+        if world > 1:
+            from tci_b200.parallel import ShardedEvaluator
+            sf = ShardedEvaluator(f, dist, torch)
+        else:
+            sf = f
+        found = None
+        for it in range(3):
+            if it == 1:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+            found = finder(inp, sf, 1e-3, rng=T.CounterRNG(1))
+        dt = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        probes = nsearch * sum(ld)
+        extra["globalsearch_config4"] = {
+            "mprobes_per_s": probes / dt / 1e6, "ms": dt * 1e3, "nsearch": nsearch, "probes": probes,
+            "found": int(len(found)), "ranks": world,
+            "note": "12 sites d=64, TT bond 128; wall clock per finder call incl. upload of the TT cores (replicated), "
+                    "candidate all-gather and selection"}
+    except Exception as e:
+        extra["globalsearch_config4"] = {"error": str(e)[:200]}
+    return extra
+
+
 def extra_mpo_1024(T, ctx, torch, dist, rank, world):
     extra = {}
     # --- config 5 shape, the two-site Pi of the MPO x MPO target at the middle bond with nL = nR = 1024 (SURVEY 8d),
@@ -498,6 +588,29 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
                                         "shape": f"40 sites, bonds 256, nL=nR={nL}, M=2 (Pi {nL * 16} x {nR})",
                                         "flop_model": "env extensions + centre folds + final product"}
         del dev, fm
+        # --- config 5 shape: one zip-up site step (contraction.jl:455-464) at chi = Da = Db = 256, s = 2x2x2:
+        # R (256,256,256), A, B (256,2,2,256) -> C (1024 x 65536), the matrix _factorize gets next ---
+        try:
+            chi = Da = Db = 256
+            Rz = np.asfortranarray(rng.standard_normal((chi, Da, Db)))
+            Az = np.asfortranarray(rng.standard_normal((Da, 2, 2, Da)))
+            Bz = np.asfortranarray(rng.standard_normal((Db, 2, 2, Db)))
+            import ctypes as C
+            for it in range(2):
+                h = C.c_void_p()
+                ctx.timers(reset=True)
+                ctx.check(_lib.lib().tci_contract_zipup_site(ctx.h, _lib.pf(Rz), chi, Da, Db, _lib.pf(Az), 2, 2, Da,
+                                                             _lib.pf(Bz), 2, Db, None, C.byref(h)))
+                tmz = ctx.timers(reset=True)
+                Cz = _lib.DeviceMatrix(ctx, h)
+                del Cz
+            flz = 2.0 * chi * Da * Db * 4 * Da + 2.0 * (chi * 2) * (Db * 2) * (2 * Da * Db)
+            extra["zipup_site_config5"] = {"tflops": flz / (tmz["gemm"] * 1e-3) / 1e12, "ms": tmz["gemm"],
+                                           "h2d_ms": tmz["h2d"], "shape": "chi=Da=Db=256, site dims 2x2x2, C 1024 x 65536",
+                                           "flop_model": "R*A (chi*Db x Da x s1*s2*Da') + RA*B (chi*s1 x Db*s2 x s3*Da'*Db')"}
+            del Rz, Az, Bz
+        except Exception as e:
+            extra["zipup_site_config5"] = {"error": str(e)[:200]}
         # --- config 3: quantics 2-D, R=20 fused (20 sites d=4), maxbonddim 256, tolerance 1e-10 ---
         f3 = T.BuiltinTarget(T.QUANTICS2D, [0, 20], [4] * 20)
         t0 = time.perf_counter()
@@ -512,6 +625,9 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         extra["crossinterpolate2_config1"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks[-1]),
                                               "iterations": len(ranks), "error": float(errors[-1])}
     extra.update(extra_mpo_1024(T, ctx, torch, dist, rank, world))
+    extra.update(extra_globalsearch(T, ctx, torch, dist, rank, world))
+    if rank == 0 and world == 1 and not os.environ.get("TCI_BENCH_NO_CPU"):
+        extra["cpu_baselines"] = cpu_baselines_secondary()
     if rank == 0:
         # --- config 4 scale: one bond's rrLU, 32768 x 32768 (8.6 GB, 12 sites d=64 at chi=512), maxrank 512.
         # The config-4 target itself is numerically of rank ~23, so its Pi never needs 512 pivots; the kernel is

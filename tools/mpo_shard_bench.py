@@ -21,6 +21,7 @@ if world > 1:
 rank = dist.get_rank() if dist else 0
 ctx = T.default_context()
 out = bench.extra_mpo_1024(T, ctx, torch, dist, rank, world)
+out.update(bench.extra_globalsearch(T, ctx, torch, dist, rank, world))
 if rank == 0:
     print(json.dumps(out))
 if dist:
