@@ -28,6 +28,133 @@ __global__ void k_env_left_step(const double *__restrict__ prev, const double *_
     out[e] = acc;
 }
 
+// The same ordered step for a tile of ENV_PT consecutive points per CTA (thread = output bond index b).  The probes of
+// a global-search star, and the rows of any index set that was expanded site by site, are consecutive points that
+// mostly share sigma at a given site: then the slice value T[a, sig, b] is loaded once and applied to all ENV_PT
+// vectors, which sit in shared memory and are read as broadcasts (two bond indices per 16-byte read).  Every output
+// is still acc = acc + p[a]*t[a] for a = 0, 1, ... with a rounded multiply and a rounded add, so the result is
+// bit-identical to k_env_left_step.  Tiles with mixed sigma take the point-by-point path.
+#define ENV_PT 32
+#define ENV_AC 64
+__global__ void __launch_bounds__(128, 5)
+    k_env_left_step_tiled(const double *__restrict__ prev, const double *__restrict__ T, int Dl, int d, int Dr,
+                          const i64 *__restrict__ idx, int len, int pos, i64 count, double *__restrict__ out,
+                          const int *__restrict__ perm)
+{
+    __shared__ __align__(16) double ps[ENV_PT][ENV_AC];
+    __shared__ int sg[ENV_PT];
+    __shared__ i64 pq[ENV_PT]; // the points of this tile (through the bucket order when there is one)
+    __shared__ int mixed;
+    const i64 q0 = (i64)blockIdx.x * ENV_PT;
+    const int np = (int)min((i64)ENV_PT, count - q0);
+    const int b = blockIdx.y * 128 + threadIdx.x;
+    if (threadIdx.x == 0) mixed = 0;
+    if (threadIdx.x < ENV_PT) {
+        const i64 q = threadIdx.x < np ? (perm ? (i64)perm[q0 + threadIdx.x] : q0 + threadIdx.x) : 0;
+        pq[threadIdx.x] = q;
+        sg[threadIdx.x] = threadIdx.x < np ? (int)(idx[(i64)len * q + pos] - 1) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < np && sg[threadIdx.x] != sg[0]) mixed = 1;
+    __syncthreads();
+    const bool uniform = !mixed;
+    double acc[ENV_PT];
+#pragma unroll
+    for (int j = 0; j < ENV_PT; ++j) acc[j] = 0.0;
+    const bool live = b < Dr;
+    const double *tcol = T + (i64)Dl * (sg[0] + (i64)d * (live ? b : 0));
+    for (int a0 = 0; a0 < Dl; a0 += ENV_AC) {
+        const int alen = min(ENV_AC, Dl - a0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < ENV_PT * ENV_AC; t += 128) {
+            const int j = t / ENV_AC, a = t % ENV_AC;
+            ps[j][a] = (j < np && a < alen) ? prev[(a0 + a) + (i64)Dl * pq[j]] : 0.0;
+        }
+        __syncthreads();
+        if (!live) continue;
+        if (uniform) {
+            int a = 0;
+            // the slice values of the NEXT pair of bond indices are requested before this pair is used
+            double n0 = alen > 1 ? __ldg(tcol + a0) : 0.0, n1 = alen > 1 ? __ldg(tcol + a0 + 1) : 0.0;
+            for (; a + 1 < alen; a += 2) {
+                const double t0 = n0, t1 = n1;
+                if (a + 3 < alen) {
+                    n0 = __ldg(tcol + a0 + a + 2);
+                    n1 = __ldg(tcol + a0 + a + 3);
+                }
+#pragma unroll
+                for (int j = 0; j < ENV_PT; ++j) {
+                    const double2 pv = *reinterpret_cast<const double2 *>(&ps[j][a]);
+                    acc[j] = __dadd_rn(acc[j], __dmul_rn(pv.x, t0));
+                    acc[j] = __dadd_rn(acc[j], __dmul_rn(pv.y, t1));
+                }
+            }
+            if (a < alen) {
+                const double t0 = __ldg(tcol + a0 + a);
+#pragma unroll
+                for (int j = 0; j < ENV_PT; ++j) acc[j] = __dadd_rn(acc[j], __dmul_rn(ps[j][a], t0));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < ENV_PT; ++j) {
+                const double *tj = T + (i64)Dl * (sg[j] + (i64)d * b) + a0;
+                double v = acc[j];
+                for (int a = 0; a < alen; ++a) v = __dadd_rn(v, __dmul_rn(ps[j][a], __ldg(tj + a)));
+                acc[j] = v;
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < ENV_PT; ++j)
+            if (j < np) out[b + (i64)Dr * pq[j]] = acc[j];
+    }
+}
+
+// Bucket order of the points by their index at one site (counting sort, d <= ENV_MAXD buckets): tiles of the tiled
+// step then hold points with ONE sigma whatever the order of the point set (the arm of a global-search star that
+// varies this very site is the worst case: consecutive probes differ in nothing but sigma).  The order inside a
+// bucket is arbitrary and does not matter: every point's result is computed independently.
+#define ENV_MAXD 1024
+__global__ void k_bucket_count(const i64 *__restrict__ idx, int len, int pos, i64 count, int d, int *__restrict__ hist)
+{
+    __shared__ int lh[ENV_MAXD];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) lh[t] = 0;
+    __syncthreads();
+    const i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q < count) atomicAdd(&lh[(int)(idx[(i64)len * q + pos] - 1)], 1);
+    __syncthreads();
+    for (int t = threadIdx.x; t < d; t += blockDim.x)
+        if (lh[t]) atomicAdd(&hist[t], lh[t]);
+}
+__global__ void k_bucket_scan(int *hist, int d) // hist -> exclusive prefix sums (the scatter cursors)
+{
+    int run = 0;
+    for (int t = 0; t < d; ++t) {
+        const int c = hist[t];
+        hist[t] = run;
+        run += c;
+    }
+}
+__global__ void k_bucket_scatter(const i64 *__restrict__ idx, int len, int pos, i64 count, int d,
+                                 int *__restrict__ cursor, int *__restrict__ perm)
+{
+    __shared__ int lh[ENV_MAXD], base[ENV_MAXD];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) lh[t] = 0;
+    __syncthreads();
+    const i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    int sig = 0, r = 0;
+    if (q < count) {
+        sig = (int)(idx[(i64)len * q + pos] - 1);
+        r = atomicAdd(&lh[sig], 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < d; t += blockDim.x)
+        if (lh[t]) base[t] = atomicAdd(&cursor[t], lh[t]);
+    __syncthreads();
+    if (q < count) perm[base[sig] + r] = (int)q;
+}
+
 // out[a + Dl*q] = sum_b T[a, sig_q, b] * prev[b + Dr*q]   (prev == nullptr: Dr == 1, prev = 1)
 __global__ void k_env_right_step(const double *__restrict__ prev, const double *__restrict__ T, int Dl, int d, int Dr,
                                  const i64 *__restrict__ idx, int len, int pos, i64 count, double *__restrict__ out)
@@ -101,6 +228,8 @@ static int env_left_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int 
 {
     double *prev = nullptr;
     int D = 1;
+    DevBuf<int> permbuf(ctx), histbuf(ctx); // bucket order of the tiled step (allocated on first use)
+    int *perm = nullptr, *hist = nullptr;
     for (int s = 0; s < nsteps; ++s) {
         const CoreView &c = cores[s];
         double *nxt = nullptr;
@@ -115,6 +244,25 @@ static int env_left_chain(tci_ctx *ctx, const std::vector<CoreView> &cores, int 
             k_env_select_left<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(Y, c.d, c.Dr, d_idx, len,
                                                                                        s + off, count, nxt);
             dev_free(ctx, Y);
+        } else if (prev && count >= 4 * ENV_PT && c.Dl >= 8 && !getenv("TCI_TT_NO_TILED")) {
+            dim3 grid((unsigned)((count + ENV_PT - 1) / ENV_PT), (unsigned)((c.Dr + 127) / 128));
+            const bool bucket = c.d > 1 && c.d <= ENV_MAXD && count < 0x7fffffff && !getenv("TCI_TT_NO_BUCKETS");
+            if (bucket) {
+                if (!perm) {
+                    TCI_CUDA(ctx, permbuf.alloc((size_t)count));
+                    TCI_CUDA(ctx, histbuf.alloc(ENV_MAXD));
+                    perm = permbuf.p;
+                    hist = histbuf.p;
+                }
+                const unsigned nb = (unsigned)((count + 255) / 256);
+                TCI_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)c.d * sizeof(int), ctx->stream));
+                k_bucket_count<<<nb, 256, 0, ctx->stream>>>(d_idx, len, s + off, count, c.d, hist);
+                k_bucket_scan<<<1, 1, 0, ctx->stream>>>(hist, c.d);
+                k_bucket_scatter<<<nb, 256, 0, ctx->stream>>>(d_idx, len, s + off, count, c.d, hist, perm);
+                ctx->launches += 3;
+            }
+            k_env_left_step_tiled<<<grid, 128, 0, ctx->stream>>>(prev, c.p, c.Dl, c.d, c.Dr, d_idx, len, s + off,
+                                                                count, nxt, bucket ? perm : nullptr);
         } else
             k_env_left_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(prev, c.p, c.Dl, c.d, c.Dr,
                                                                                      d_idx, len, s + off, count, nxt);
@@ -315,6 +463,21 @@ __global__ void k_abs_diff(const double *__restrict__ f, const double *__restric
     if (e < n) out[e] = fabs(__dsub_rn(f[e], g[e]));
 }
 
+// the star of probes around every start point (globalpivotfinder.jl:167-177), expanded on the device:
+// probe q = s*star + off[p] + (v-1) is start s with x_p replaced by v
+__global__ void k_star_points(const i64 *__restrict__ starts, const i64 *__restrict__ off, int nsites, i64 star,
+                              i64 count, i64 *__restrict__ pts)
+{
+    i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const i64 s = q / star, r = q % star;
+    int p = 0;
+    while (p + 1 < nsites && off[p + 1] <= r) ++p;
+    i64 *x = pts + q * nsites;
+    for (int k = 0; k < nsites; ++k) x[k] = starts[k + s * nsites];
+    x[p] = r - off[p] + 1;
+}
+
 extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
                                 const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
                                 int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out,
@@ -333,21 +496,19 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites,
     i64 star = 0;
     for (i64 p = 0; p < nsites; ++p) star += dims3[3 * p + 1];
     const i64 count = star * nsearch;
-    std::vector<i64> pts((size_t)(count * nsites));
-    i64 q = 0;
-    for (i64 s = 0; s < nsearch; ++s)
-        for (i64 p = 0; p < nsites; ++p)
-            for (i64 v = 1; v <= dims3[3 * p + 1]; ++v, ++q) {
-                i64 *x = pts.data() + q * nsites;
-                for (i64 k = 0; k < nsites; ++k) x[k] = starts[k + s * nsites];
-                x[p] = v;
-            }
+    std::vector<i64> off((size_t)nsites + 1, 0);
+    for (i64 p = 0; p < nsites; ++p) off[p + 1] = off[p] + dims3[3 * p + 1];
     HostTT tt(ctx);
     int rc = tt.upload(nsites, dims3, cores);
     if (rc) return rc;
-    DevBuf<i64> d_idx(ctx);
+    DevBuf<i64> d_idx(ctx), d_starts(ctx), d_off(ctx);
     DevBuf<double> d_f(ctx), d_g(ctx), d_e(ctx);
-    TCI_CUDA(ctx, d_idx.upload(pts.data(), pts.size()));
+    TCI_CUDA(ctx, d_starts.upload(starts, (size_t)(nsites * nsearch)));
+    TCI_CUDA(ctx, d_off.upload(off.data(), off.size()));
+    TCI_CUDA(ctx, d_idx.alloc((size_t)(count * nsites)));
+    k_star_points<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d_starts.p, d_off.p, (int)nsites, star,
+                                                                           count, d_idx.p);
+    ctx->launches++;
     TCI_CUDA(ctx, d_f.alloc((size_t)count));
     TCI_CUDA(ctx, d_g.alloc((size_t)count));
     TCI_CUDA(ctx, d_e.alloc((size_t)count));
@@ -371,8 +532,13 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites,
                 bestq = e;
             }
         if (best > threshold) {
-            const i64 *x = bestq >= 0 ? pts.data() + bestq * nsites : starts + s * nsites;
-            for (i64 k = 0; k < nsites; ++k) pivots_out[k + found * nsites] = x[k];
+            for (i64 k = 0; k < nsites; ++k) pivots_out[k + found * nsites] = starts[k + s * nsites];
+            if (bestq >= 0) {
+                const i64 r = bestq - s * star;
+                i64 p = 0;
+                while (p + 1 < nsites && off[p + 1] <= r) ++p;
+                pivots_out[p + found * nsites] = r - off[p] + 1;
+            }
             errs_out[found] = best;
             if (start_idx_out) start_idx_out[found] = s;
             ++found;

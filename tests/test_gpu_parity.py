@@ -504,6 +504,40 @@ def test_tt_target_all_splits(T, oracle):  # test_tensortrain.jl:113-140, test_c
             np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-14)
 
 
+def test_tt_evaluate_tiled_chain_bit_exact(T, oracle, monkeypatch):
+    """The tiled, bucket-ordered chain step (k_env_left_step_tiled) against the oracle's left-to-right product
+    (abstracttensortrain.jl:124-132), bit for bit: ragged point counts, bond dimensions that are neither even nor
+    multiples of the staging chunk, a site of dimension 1, star-shaped point sets (consecutive points that differ in
+    one site only) and random ones; the untiled kernel must give the same bits."""
+    rng = np.random.default_rng(21)
+    dims = [3, 5, 1, 4, 6, 2]
+    cores = _rand_tt(rng, [1, 9, 70, 131, 130, 17, 1], dims)
+    tt = T.TensorTrain(cores)
+    rnd = rand_indexset(rng, dims, 1003)
+    start = rand_indexset(rng, dims, 40)
+    star = []
+    for x in start:
+        for p, d in enumerate(dims):
+            for v in range(1, d + 1):
+                y = x.copy()
+                y[p] = v
+                star.append(y)
+    star = np.array(star, dtype=np.int64)
+    for pts in (rnd, star, rnd[:129], star[:257]):
+        ref = np.array([oracle.tt_evaluate(cores, p) for p in pts])
+        got = T.evaluate_points(tt, pts)
+        assert np.array_equal(got, ref)
+        monkeypatch.setenv("TCI_TT_NO_BUCKETS", "1")
+        assert np.array_equal(T.evaluate_points(tt, pts), ref)
+        monkeypatch.setenv("TCI_TT_NO_TILED", "1")
+        assert np.array_equal(T.evaluate_points(tt, pts), ref)
+        monkeypatch.delenv("TCI_TT_NO_BUCKETS")
+        monkeypatch.delenv("TCI_TT_NO_TILED")
+    f = T.TTCache(tt)  # TTCache.evaluate: left half through the same chain
+    o = oracle.Target.tt(cores)
+    assert np.array_equal(f.evaluate_points(rnd[:300]), np.array([o(p) for p in rnd[:300]]))
+
+
 def _rand_mpo(rng, bonds, d1, d2):
     return [np.asfortranarray(rng.random((bonds[i], d1[i], d2[i], bonds[i + 1])) - 0.5) for i in range(len(d1))]
 
