@@ -111,6 +111,26 @@ class BatchEvaluator:
             pass
 
 
+def apply_projector(res, centre_sitedims, projector):
+    """The projected batchevaluate of TTCache / Contraction (cachedtensortrain.jl:170-215, contraction.jl:247-335):
+    `projector[n][k] == 0` keeps sub-index k of centre site n free, a value v > 0 fixes it to v
+    (projector_to_slice, util.jl:124-126).  `res` is the unprojected result (nI, d_1, ..., d_M, nJ) from the
+    device; the projected one is its slice, with the free sub-indices of every centre site fused (first fastest)
+    into one dimension, as the reference's `reshape(s, size(s)[1], :, size(s)[end])` leaves it."""
+    nI, nJ = res.shape[0], res.shape[-1]
+    full = res.reshape([nI] + [int(d) for sd in centre_sitedims for d in sd] + [nJ], order="F")
+    index = [slice(None)]
+    outdims = []
+    for sd, pr in zip(centre_sitedims, projector):
+        free = 1
+        for d, v in zip(sd, pr):
+            index.append(slice(None) if v == 0 else int(v) - 1)
+            free *= int(d) if v == 0 else 1
+        outdims.append(free)
+    index.append(slice(None))
+    return np.asfortranarray(full[tuple(index)]).reshape([nI] + outdims + [nJ], order="F")
+
+
 class BuiltinTarget(BatchEvaluator):
     """A device-resident analytic target registered by kind id (include/tci_targets.h)."""
 

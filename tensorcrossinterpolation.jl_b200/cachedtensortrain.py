@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import core_ptrs, lib, pi
-from .batcheval import BatchEvaluator
+from .batcheval import BatchEvaluator, apply_projector
 
 
 class TTCache(BatchEvaluator):
@@ -32,6 +32,26 @@ class TTCache(BatchEvaluator):
         super().__init__(ctx, tid.value, d3[:, 1].tolist())
         self.sitetensors = keep
         self.sitedims = [list(s) for s in sitedims]
+
+    def batchevaluate(self, leftindexset, rightindexset, M, projector=None):
+        """batchevaluate(tt::TTCache, leftindexset, rightindexset, Val(M), projector) (cachedtensortrain.jl:151-215)."""
+        if len(leftindexset) * len(rightindexset) == 0:  # :156-158
+            return np.zeros((0,) * (M + 2), order="F")
+        nl = len(leftindexset[0])
+        if len(self.localdims) - nl - len(rightindexset[0]) != M:
+            raise RuntimeError(f"Invalid parameter M: {M}")  # :167-169
+        if projector is None:
+            return super().batchevaluate(leftindexset, rightindexset, M)
+        projector = [[int(v) for v in pr] for pr in projector]
+        if len(projector) != M:
+            raise RuntimeError(f"Invalid length of projector: {projector}, correct length should be M={M}")  # :173-175
+        for k, pr in enumerate(projector):
+            sd = self.sitedims[nl + k]
+            if len(pr) != len(sd):
+                raise RuntimeError(f"Invalid projector at {nl + k + 1}: {pr}, the length must be {len(sd)}")  # :177
+            if not all(0 <= v <= d for v, d in zip(pr, sd)):
+                raise RuntimeError(f"Invalid projector: {pr}")  # :178
+        return apply_projector(super().batchevaluate(leftindexset, rightindexset, M), self.sitedims[nl:nl + M], projector)
 
 
 def isbatchevaluable(f):  # cachedtensortrain.jl:228-229

@@ -40,6 +40,22 @@ class Contraction(BatchEvaluator):
         super().__init__(ctx, tid.value, [s[0] * s[1] for s in self.sitedims])
         self.mpo = (ka, kb)
 
+    def batchevaluate(self, leftindexset, rightindexset, M, projector=None):
+        """batchevaluate(obj::Contraction, leftindexset, rightindexset, Val(M), projector) (contraction.jl:236-335)."""
+        if projector is None:
+            return super().batchevaluate(leftindexset, rightindexset, M)
+        nl = len(leftindexset[0])
+        projector = [[int(v) for v in pr] for pr in projector]
+        if len(projector) != M:
+            raise RuntimeError(f"Length mismatch: length of projector (={len(projector)}) must be {M}")  # :250
+        for k, pr in enumerate(projector):
+            if len(pr) != 2:
+                raise RuntimeError(f"Invalid projector at {nl + k + 1}: {pr}, the length must be 2")  # :252
+            if not all(0 <= v <= d for v, d in zip(pr, self.sitedims[nl + k])):
+                raise RuntimeError(f"Invalid projector: {pr}")  # :253
+        from .batcheval import apply_projector
+        return apply_projector(super().batchevaluate(leftindexset, rightindexset, M), self.sitedims[nl:nl + M], projector)
+
 
 def _contractsitetensors(a, b, ctx=None):  # contraction.jl:338-349
     ctx = ctx or _lib.default_context()

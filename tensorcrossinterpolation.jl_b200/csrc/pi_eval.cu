@@ -79,15 +79,16 @@ __device__ __forceinline__ void block_max_commit(unsigned long long mx, unsigned
 template <int NS, int KIND>
 __global__ void __launch_bounds__(PI_THREADS)
     k_pi_exact(tci_analytic_t targ, const double *__restrict__ rs, i64 nI, const double *__restrict__ cs, i64 C,
-               const double *__restrict__ js, i64 nJ, double *__restrict__ out, i64 ld, unsigned long long *gmax)
+               const double *__restrict__ js, i64 nJ, double *__restrict__ out, i64 ld, unsigned long long *gmax,
+               int tcols)
 {
     __shared__ double colst[NS][PI_TCOLS];
     __shared__ i64 coloff[PI_TCOLS];
     tci_analytic_t t = targ;
     t.kind = KIND; // compile-time kind: the switch in tci_target_finalize folds away
     const i64 ncols = C * nJ;
-    const i64 q0 = (i64)blockIdx.y * PI_TCOLS;
-    if (threadIdx.x < PI_TCOLS) {
+    const i64 q0 = (i64)blockIdx.y * tcols;
+    if (threadIdx.x < tcols) {
         i64 q = q0 + threadIdx.x;
         if (q < ncols) {
             i64 c = q % C, j = q / C;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(PI_THREADS)
             a0[k] = rs[(i64)k * nI + r0];
             a1[k] = two ? rs[(i64)k * nI + r0 + 1] : 0.0;
         }
-        const int nq = (int)(ncols - q0 < PI_TCOLS ? ncols - q0 : PI_TCOLS);
+        const int nq = (int)(ncols - q0 < tcols ? ncols - q0 : tcols);
 #pragma unroll 4
         for (int qq = 0; qq < nq; ++qq) {
             double s0[NS], s1[NS];
@@ -144,16 +145,16 @@ __global__ void __launch_bounds__(PI_THREADS)
 __global__ void __launch_bounds__(PI_THREADS)
     k_pi_sequential(tci_analytic_t t, const double *__restrict__ rs, i64 nI, int nl, int M, i64 C,
                     const int *__restrict__ csig, const i64 *__restrict__ J, int nr, i64 nJ, double *__restrict__ out,
-                    i64 ld, unsigned long long *gmax)
+                    i64 ld, unsigned long long *gmax, int tcols)
 {
     const i64 ncols = C * nJ;
-    const i64 q0 = (i64)blockIdx.y * PI_TCOLS;
+    const i64 q0 = (i64)blockIdx.y * tcols;
     const i64 r = (i64)blockIdx.x * PI_THREADS + threadIdx.x;
     unsigned long long mx = 0ull;
     if (r < nI) {
         double a[TCI_MAX_STATE];
         for (int k = 0; k < TCI_MAX_STATE; ++k) a[k] = k < t.nstate ? rs[(i64)k * nI + r] : 0.0;
-        const int nq = (int)(ncols - q0 < PI_TCOLS ? ncols - q0 : PI_TCOLS);
+        const int nq = (int)(ncols - q0 < tcols ? ncols - q0 : tcols);
         for (int qq = 0; qq < nq; ++qq) {
             i64 q = q0 + qq, c = q % C, j = q / C;
             double s[TCI_MAX_STATE];
@@ -169,12 +170,24 @@ __global__ void __launch_bounds__(PI_THREADS)
     block_max_commit(mx, gmax);
 }
 
+// Columns per CTA: PI_TCOLS for large Pi (the column states are staged once per CTA); small matrices -- what a TCI run
+// at chi <= 256 produces -- get fewer columns per thread so that the grid still covers the SMs a few times over
+// (a 1126 x 524 Pi was 51 CTAs with 64 serial evaluations per thread).
+static int pick_tcols(tci_ctx *ctx, i64 rowblocks, i64 ncols)
+{
+    int t = PI_TCOLS;
+    while (t > 2 && rowblocks * ((ncols + t - 1) / t) < 4 * (i64)ctx->sm_count) t >>= 1;
+    return t;
+}
+
 template <int NS, int KIND>
 static void launch_exact(tci_ctx *ctx, const tci_analytic_t &an, const double *rs, i64 nI, const double *cs, i64 C,
                          const double *js, i64 nJ, double *out, i64 ld, unsigned long long *gmax)
 {
-    dim3 grid((unsigned)((nI + 2 * PI_THREADS - 1) / (2 * PI_THREADS)), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
-    k_pi_exact<NS, KIND><<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs, nI, cs, C, js, nJ, out, ld, gmax);
+    const i64 rb = (nI + 2 * PI_THREADS - 1) / (2 * PI_THREADS);
+    const int tc = pick_tcols(ctx, rb, C * nJ);
+    dim3 grid((unsigned)rb, (unsigned)((C * nJ + tc - 1) / tc));
+    k_pi_exact<NS, KIND><<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs, nI, cs, C, js, nJ, out, ld, gmax, tc);
     ctx->launches++;
 }
 
@@ -224,9 +237,11 @@ int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, 
         }
 #undef PI_LAUNCH
     } else {
-        dim3 grid((unsigned)((nI + PI_THREADS - 1) / PI_THREADS), (unsigned)((C * nJ + PI_TCOLS - 1) / PI_TCOLS));
+        const i64 rb = (nI + PI_THREADS - 1) / PI_THREADS;
+        const int tc = pick_tcols(ctx, rb, C * nJ);
+        dim3 grid((unsigned)rb, (unsigned)((C * nJ + tc - 1) / tc));
         k_pi_sequential<<<grid, PI_THREADS, 0, ctx->stream>>>(an, rs.p, nI, (int)nl, (int)M, C, csig.p, dJ, (int)nr,
-                                                              nJ, out->p, out->ld, d_maxbits);
+                                                              nJ, out->p, out->ld, d_maxbits, tc);
         ctx->launches++;
     }
     TCI_CUDA(ctx, cudaGetLastError());

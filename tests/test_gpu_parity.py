@@ -563,6 +563,51 @@ def test_mpo_target(T, oracle):  # test_contraction.jl:68-146 (real-valued)
         np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
 
 
+def test_batchevaluate_projector(T, oracle):  # test_contraction.jl:101-139 (real-valued), cachedtensortrain.jl:170-215
+    rng = np.random.default_rng(31)
+    N = 4
+    A = _rand_mpo(rng, [1, 2, 3, 2, 1], [2] * N, [3] * N)
+    B = _rand_mpo(rng, [1, 2, 3, 2, 1], [3] * N, [2] * N)
+    ab = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    o = oracle.Target.mpo_pair(A, B)
+    left, right = np.array([[1]]), np.array([[1]])
+    ref = ab(left, right, 2)
+    oref, _ = o.pi_eval(left.tolist(), right.tolist(), 2)
+    np.testing.assert_allclose(ref, oref, rtol=RTOL, atol=1e-14)
+    mi = oref.reshape((1, 2, 2, 2, 2, 1), order="F")
+    for proj, sl in (([[0, 0], [1, 0]], mi[:, :, :, 0, :, :]), ([[0, 0], [1, 1]], mi[:, :, :, 0, 0, :]),
+                     ([[0, 1], [1, 0]], mi[:, :, 0, 0, :, :]), ([[2, 0], [0, 2]], mi[:, 1, :, :, 1, :])):
+        res = ab.batchevaluate(left, right, 2, proj)
+        np.testing.assert_allclose(res.flatten(order="F"), sl.flatten(order="F"), rtol=RTOL, atol=1e-14)
+        assert res.ndim == 4
+    with pytest.raises(RuntimeError, match="Length mismatch"):
+        ab.batchevaluate(left, right, 2, [[0, 0]])
+    with pytest.raises(RuntimeError, match="the length must be 2"):
+        ab.batchevaluate(left, right, 2, [[0, 0], [1]])
+    with pytest.raises(RuntimeError, match="Invalid projector"):
+        ab.batchevaluate(left, right, 2, [[0, 0], [3, 0]])
+    # TTCache with multi-dimensional sites
+    cores = [np.asfortranarray(rng.random((b0, 2, 3, b1)) - 0.4) for b0, b1 in ((1, 3), (3, 4), (4, 2), (2, 1))]
+    f = T.TTCache(T.TensorTrain(cores))
+    assert f.sitedims == [[2, 3]] * 4 and f.localdims == [6] * 4
+    ot = oracle.Target.tt([c.reshape((c.shape[0], 6, c.shape[-1]), order="F") for c in cores])
+    I, J = rand_indexset(rng, [6], 5), rand_indexset(rng, [6], 4)
+    full, _ = ot.pi_eval(I.tolist(), J.tolist(), 2)
+    mi = full.reshape((5, 2, 3, 2, 3, 4), order="F")
+    res = f.batchevaluate(I, J, 2, [[0, 2], [1, 0]])
+    assert res.shape == (5, 2, 3, 4)
+    np.testing.assert_allclose(res, mi[:, :, 1, 0, :, :], rtol=RTOL, atol=1e-14)
+    res = f.batchevaluate(I, J, 2, [[1, 2], [2, 3]])
+    assert res.shape == (5, 1, 1, 4)
+    np.testing.assert_allclose(res[:, 0, 0, :], mi[:, 0, 1, 1, 2, :], rtol=RTOL, atol=1e-14)
+    with pytest.raises(RuntimeError, match="Invalid parameter M"):
+        f.batchevaluate(I, J, 1)
+    with pytest.raises(RuntimeError, match="Invalid length of projector"):
+        f.batchevaluate(I, J, 2, [[0, 0]])
+    with pytest.raises(RuntimeError, match="Invalid projector"):
+        f.batchevaluate(I, J, 2, [[0, 4], [0, 0]])
+
+
 def test_environments_abi(T, oracle):
     """tci_env_eval / tci_pi_from_envs (the pieces the row-block sharding of the contraction is made of): the M = 0
     Pi assembled from separately evaluated left / right environment blocks equals the oracle's batchevaluate

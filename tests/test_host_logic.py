@@ -62,3 +62,17 @@ def test_counter_rng_matches_oracle(T, oracle):
         ref = oracle.start_points(5, it, 6, ld)
         assert np.array_equal(got, ref.T)
     assert got.min() >= 1 and all(got[:, p].max() <= ld[p] for p in range(5))
+
+
+def test_apply_projector(T):  # projector_to_slice util.jl:124-126; cachedtensortrain.jl:198-205; contraction.jl:290-302
+    from tci_b200.batcheval import apply_projector
+    rng = np.random.default_rng(0)
+    full = np.asfortranarray(rng.random((3, 2, 3, 2, 2, 4)))  # (nI, [2,3], [2,2], nJ)
+    res = full.reshape((3, 6, 4, 4), order="F")
+    out = apply_projector(res, [[2, 3], [2, 2]], [[0, 0], [1, 0]])
+    assert out.shape == (3, 6, 2, 4)
+    assert np.array_equal(out, full[:, :, :, 0, :, :].reshape((3, 6, 2, 4), order="F"))
+    out = apply_projector(res, [[2, 3], [2, 2]], [[0, 2], [1, 2]])
+    assert out.shape == (3, 2, 1, 4) and np.array_equal(out[:, :, 0, :], full[:, :, 1, 0, 1, :])
+    out = apply_projector(res, [[2, 3], [2, 2]], [[0, 0], [0, 0]])
+    assert np.array_equal(out, res)
