@@ -416,3 +416,73 @@ def tensorci2_from_tt(cores, tolerance=1e-12, maxbonddim=None, maxiter=3):
             if same(new, Jset):
                 break
     return Iset, Jset, cores, pe, max(float(np.abs(c).max()) for c in cores)
+
+
+# ---- projected batchevaluate (numpy restatement; small cases) ---------------------------------------------------
+def _projector_to_slice(p):  # util.jl:124-126
+    return tuple(slice(None) if x == 0 else int(x) - 1 for x in p)
+
+
+def tt_batchevaluate_projected(cores, sitedims, I, J, M, projector=None):
+    """batchevaluate(tt::TTCache, leftindexset, rightindexset, Val(M), projector), cachedtensortrain.jl:151-215:
+    cores are (Dl, d, Dr) with d = prod(sitedims[n]); the centre cores are sliced by the projector BEFORE they are
+    contracted (:198-205), left/right environments are the chains of :77-128."""
+    N = len(cores)
+    nl, nr = len(I[0]), len(J[0])
+    if N - nl - nr != M:
+        raise OracleError(f"Invalid parameter M: {M}")  # :167-169
+    if projector is None:
+        projector = [[0] * len(sitedims[n]) for n in range(nl, N - nr)]  # :170-172
+    if len(projector) != M:
+        raise OracleError(f"Invalid length of projector: {projector}, correct length should be M={M}")
+    lenv = np.ones((len(I), 1))
+    if nl > 0:  # evaluateleft :77-100
+        rows = []
+        for idx in I:
+            v = np.ones((1, 1))
+            for s in range(nl):
+                v = v @ cores[s][:, idx[s] - 1, :]
+            rows.append(v[0])
+        lenv = np.array(rows)
+    renv = np.ones((1, len(J)))
+    if nr > 0:  # evaluateright :102-128
+        cols = []
+        for idx in J:
+            v = np.ones((1, 1))
+            for s in range(nr - 1, -1, -1):
+                v = cores[N - nr + s][:, idx[s] - 1, :] @ v
+            cols.append(v[:, 0])
+        renv = np.array(cols).T
+    localdim = []
+    for n in range(nl, N - nr):  # :196-208
+        c = np.asarray(cores[n])
+        c4 = c.reshape((c.shape[0], *sitedims[n], c.shape[-1]), order="F")
+        sl = c4[(slice(None),) + _projector_to_slice(projector[n - nl]) + (slice(None),)]
+        kept = [d for d, x in zip(sitedims[n], projector[n - nl]) if x == 0]
+        T_ = sl.reshape((c.shape[0], int(np.prod(kept, dtype=np.int64)) if kept else 1, c.shape[-1]), order="F")
+        localdim.append(T_.shape[1])
+        lenv = lenv.reshape((-1, T_.shape[0]), order="F") @ T_.reshape((T_.shape[0], -1), order="F")
+    lenv = lenv.reshape((-1, renv.shape[0]), order="F") @ renv  # :211-212
+    return lenv.reshape((len(I), *localdim, len(J)), order="F")
+
+
+def mpo_batchevaluate_projected(A, B, I, J, M, projector=None):
+    """batchevaluate(obj::Contraction, ..., projector), contraction.jl:236-335 with f = nothing: the product MPO's
+    site tensor (Da*Db, d1*d3, Da'*Db') with fused index i + d1*(k-1) (:95-101), its A / B factors sliced by the
+    projector (:290-302) -- restated through the product core, which is what the slices of A and B multiply to."""
+    prod, sitedims = [], []
+    for a, b in zip(A, B):
+        Da, d1, S, Dan = a.shape
+        Db, _, d3, Dbn = b.shape
+        # out[(la, lb), (x, z), (lan, lbn)] = sum_h a[la, x, h, lan] * b[lb, h, z, lbn]   contraction.jl:338-349
+        c = np.einsum("axhc,bhzd->abxzcd", a, b)
+        prod.append(np.asfortranarray(c.reshape((Da * Db, d1 * d3, Dan * Dbn), order="F")))
+        sitedims.append([d1, d3])
+    nl = len(I[0])
+    if projector is not None:
+        if len(projector) != M:
+            raise OracleError(f"Length mismatch: length of projector (={len(projector)}) must be {M}")  # :250
+        for k, pr in enumerate(projector):
+            if len(pr) != 2:
+                raise OracleError(f"Invalid projector at {nl + k + 1}: {list(pr)}, the length must be 2")  # :252
+    return tt_batchevaluate_projected(prod, sitedims, I, J, M, projector)

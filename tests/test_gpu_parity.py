@@ -580,6 +580,10 @@ def test_batchevaluate_projector(T, oracle):  # test_contraction.jl:101-139 (rea
         res = ab.batchevaluate(left, right, 2, proj)
         np.testing.assert_allclose(res.flatten(order="F"), sl.flatten(order="F"), rtol=RTOL, atol=1e-14)
         assert res.ndim == 4
+        # the oracle's restatement slices the cores before contracting, as contraction.jl:290-302 does
+        oproj = oracle.mpo_batchevaluate_projected(A, B, left.tolist(), right.tolist(), 2, proj)
+        assert res.shape == oproj.shape
+        np.testing.assert_allclose(res, oproj, rtol=RTOL, atol=1e-14)
     with pytest.raises(RuntimeError, match="Length mismatch"):
         ab.batchevaluate(left, right, 2, [[0, 0]])
     with pytest.raises(RuntimeError, match="the length must be 2"):
@@ -1095,6 +1099,53 @@ def test_config4_scale_pi_and_rrlu_vs_oracle_on_pivot_submatrix(T, oracle):
 
 
 # ---------------------------------------------------------------- edge cases ----
+def test_config5_full_shape_mpo_properties(T):
+    """BASELINE config 5 at its full shape (40 sites, bond dimension 256, site dimensions 2 x 2): the oracle does not
+    finish this size in seconds, so parity goes through size-independent properties.  (i) the three evaluation
+    paths agree to 1e-10 of max|Pi|: tci_pi_eval (M = 0), separately evaluated environments + tci_pi_from_envs, and
+    the pointwise evaluate with its mid-chain split (contraction.jl:189-207); (ii) linearity: doubling one core of A
+    doubles Pi bit for bit; (iii) the M = 2 Pi equals the M = 0 Pi over the kronecker-expanded index sets
+    (tensorci2.jl:315-327 order: left index fastest in the rows, site index fastest in the columns)."""
+    rng = np.random.default_rng(55)
+    ns, D, n = 40, 256, 48
+    bonds = [1] + [D] * (ns - 1) + [1]
+    A = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(ns)]
+    B = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(ns)]
+    f = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    I = rand_indexset(rng, [4] * 20, n)
+    J = rand_indexset(rng, [4] * 20, n)
+    Pi = f(I, J, 0)
+    scale = np.max(np.abs(Pi))
+    assert np.all(np.isfinite(Pi)) and scale > 0
+    # (i) environments + product, and pointwise evaluation
+    Dl = f.env_dim(0, 20)
+    assert Dl == D * D == f.env_dim(1, 20)
+    lenv, renv = T.DeviceMatrix.empty(f.ctx, Dl, n), T.DeviceMatrix.empty(f.ctx, Dl, n)
+    f.env_eval_into(lenv, 0, 0, I)
+    f.env_eval_into(renv, 0, 1, J)
+    out = T.DeviceMatrix.empty(f.ctx, n, n)
+    mx = f.pi_from_envs(lenv, 0, n, renv, 0, n, out, 0)
+    assert np.max(np.abs(out.to_host() - Pi)) <= RTOL * scale and abs(mx - scale) <= RTOL * scale
+    del lenv, renv, out
+    pts = np.array([np.concatenate([I[i], J[j]]) for j in range(8) for i in range(8)], dtype=np.int64)
+    vals = f.evaluate_points(pts).reshape((8, 8), order="F")
+    assert np.max(np.abs(vals - Pi[:8, :8])) <= RTOL * scale
+    # (ii) linearity in one core (a power of two commutes with every rounding)
+    A2 = [a.copy(order="F") for a in A]
+    A2[7] *= 2.0
+    f2 = T.Contraction(T.TensorTrain(A2), T.TensorTrain(B))
+    assert np.array_equal(f2(I, J, 0), 2.0 * Pi)
+    del f2
+    # (iii) M = 2 against M = 0 on the expanded sets
+    I19, J19 = I[:16, :19], J[:16, 1:]
+    Pi2 = f(I19, J19, 2)  # (16, 4, 4, 16)
+    assert Pi2.shape == (16, 4, 4, 16)
+    Ie = T.kronecker_left(I19, 4)
+    Je = T.kronecker_right(4, J19)
+    Pi0 = f(Ie, Je, 0)
+    assert np.max(np.abs(Pi0 - Pi2.reshape((64, 64), order="F"))) <= RTOL * np.max(np.abs(Pi0))
+
+
 def test_rrlu_degenerate_shapes(T, oracle):
     """Empty, single-row / single-column and maxrank corner cases (matrixlu.jl:141-181)."""
     for shape in [(0, 5), (5, 0), (0, 0)]:

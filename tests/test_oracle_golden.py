@@ -413,3 +413,35 @@ def test_oracle_tt_to_tci2_conversion(oracle):  # test_conversion.jl:76-92 struc
     for b in range(3):
         P = np.array([[D[tuple(np.concatenate([i, j]) - 1)] for j in J[b]] for i in I[b + 1]])
         assert np.linalg.matrix_rank(P) == bonds[b + 1]
+
+
+def test_projected_batchevaluate(oracle):
+    """test_contraction.jl:101-139 ("Contraction, batchevaluate", real-valued): the projected result is the slice of
+    the unprojected one; the same for a TTCache with two-index sites (cachedtensortrain.jl:170-215).  The projected
+    restatement slices the cores BEFORE contracting, as the reference does."""
+    rng = np.random.default_rng(3)
+    N = 4
+    bd = [1, 2, 3, 2, 1]
+    A = [np.asfortranarray(rng.random((bd[n], 2, 3, bd[n + 1]))) for n in range(N)]
+    B = [np.asfortranarray(rng.random((bd[n], 3, 2, bd[n + 1]))) for n in range(N)]
+    ab = oracle.Target.mpo_pair(A, B)
+    ref, _ = ab.pi_eval([[1]], [[1]], 2)
+    mi = ref.reshape((1, 2, 2, 2, 2, 1), order="F")
+    cases = [([[0, 0], [1, 0]], mi[:, :, :, 0, :, :]), ([[0, 0], [1, 1]], mi[:, :, :, 0, 0, :]),
+             ([[0, 1], [1, 0]], mi[:, :, 0, 0, :, :])]
+    for proj, sl in cases:
+        res = oracle.mpo_batchevaluate_projected(A, B, [[1]], [[1]], 2, proj)
+        assert res.ndim == 4
+        np.testing.assert_allclose(res.flatten(order="F"), sl.flatten(order="F"), rtol=1e-13)
+    np.testing.assert_allclose(oracle.mpo_batchevaluate_projected(A, B, [[1]], [[1]], 2), ref, rtol=1e-13)
+    with pytest.raises(oracle.OracleError, match="Length mismatch"):
+        oracle.mpo_batchevaluate_projected(A, B, [[1]], [[1]], 2, [[0, 0]])
+    cores = [np.asfortranarray(rng.random((b0, 6, b1)) - 0.4) for b0, b1 in ((1, 3), (3, 4), (4, 2), (2, 1))]
+    I, J = [[1], [3], [6]], [[2], [5]]
+    full, _ = oracle.Target.tt(cores).pi_eval(I, J, 2)
+    mi = full.reshape((3, 2, 3, 2, 3, 2), order="F")
+    res = oracle.tt_batchevaluate_projected(cores, [[2, 3]] * 4, I, J, 2, [[0, 2], [1, 0]])
+    assert res.shape == (3, 2, 3, 2)
+    np.testing.assert_allclose(res, mi[:, :, 1, 0, :, :], rtol=1e-13)
+    with pytest.raises(oracle.OracleError, match="Invalid parameter M"):
+        oracle.tt_batchevaluate_projected(cores, [[2, 3]] * 4, I, J, 1)
