@@ -82,6 +82,13 @@ def _splitmix64(x):
     return x ^ (x >> 31)
 
 
+def _splitmix64_np(x):  # the same on uint64 arrays (wrapping arithmetic)
+    x = x + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
 def uniform01(seed, index):  # tci_uniform01 of include/tci_targets.h
     h = _splitmix64(_splitmix64(seed & M64) ^ _splitmix64((index + 0x632BE59BD9B4E019) & M64))
     return (h >> 11) * (1.0 / 9007199254740992.0)
@@ -115,10 +122,11 @@ class CounterRNG:
     def start_points(self, nsearch, localdims):
         self.calls += 1
         n = len(localdims)
-        out = np.empty((nsearch, n), dtype=np.int64)
-        for s in range(nsearch):
-            for p in range(n):
-                idx = ((self.calls * 1000003 + s) * 1009 + p) & M64
-                v = 1 + int(uniform01(self.seed, idx) * float(localdims[p]))
-                out[s, p] = min(v, int(localdims[p]))
-        return out
+        ld = np.asarray(localdims, dtype=np.int64)
+        with np.errstate(over="ignore"):  # uint64 arithmetic wraps, as the C generator's does
+            s = np.arange(nsearch, dtype=np.uint64)[:, None]
+            p = np.arange(n, dtype=np.uint64)[None, :]
+            idx = (np.uint64(self.calls * 1000003 & M64) + s) * np.uint64(1009) + p
+            h = _splitmix64_np(np.uint64(_splitmix64(self.seed & M64)) ^ _splitmix64_np(idx + np.uint64(0x632BE59BD9B4E019)))
+        u = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        return np.minimum(1 + (u * ld[None, :].astype(np.float64)).astype(np.int64), ld[None, :])

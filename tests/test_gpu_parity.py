@@ -1099,6 +1099,32 @@ def test_config4_scale_pi_and_rrlu_vs_oracle_on_pivot_submatrix(T, oracle):
 
 
 # ---------------------------------------------------------------- edge cases ----
+@pytest.mark.parametrize("name", ["config1", "config3", "config4"])
+def test_crossinterpolate2_full_size_matches_oracle(T, oracle, name):
+    """BASELINE configs 1, 3 (fused: 20 sites d=4, R=20 bits per dimension, maxbonddim 256, tolerance 1e-10) and 4
+    (12 sites d=64, maxbonddim 512, tolerance 1e-12) at their FULL sizes against the CPU oracle (0.01 s, ~3 s, ~11 s
+    on the box): identical ranks per iteration and identical Iset / Jset at every bond, site tensors, sum(tci) and
+    the sampled interpolation error within 1e-10 (measured: <= 5e-15, tools/fullsize_parity.py)."""
+    if name == "config1":
+        kind, params, ld, kw = LORENTZ, [1.0], [10] * 8, dict(tolerance=1e-8)
+    elif name == "config3":
+        kind, params, ld, kw = Q2D, [0, 20], [4] * 20, dict(tolerance=1e-10, maxbonddim=256)
+    else:
+        kind, params, ld, kw = SEPCOS, sepcos_params(12), [64] * 12, dict(tolerance=1e-12, maxbonddim=512)
+    f, o = T.BuiltinTarget(kind, params, ld), oracle.Target.builtin(kind, params, ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)
+    res = oracle.crossinterpolate2(o, ld, seed=1, **kw)
+    compare_tci(tci, ranks, errors, res, T)
+    rng = np.random.default_rng(0)
+    pts = rand_indexset(rng, ld, 500)
+    fv = f.evaluate_points(pts)
+    tg = T.evaluate_points(T.TensorTrain(tci.sitetensors), pts)
+    to = np.array([oracle.tt_evaluate(res.sitetensors, q) for q in pts])
+    scale = tci.maxsamplevalue
+    assert np.max(np.abs(tg - to)) <= RTOL * scale
+    assert abs(np.max(np.abs(fv - tg)) - np.max(np.abs(fv - to))) <= RTOL * scale
+
+
 def test_config5_full_shape_mpo_properties(T):
     """BASELINE config 5 at its full shape (40 sites, bond dimension 256, site dimensions 2 x 2): the oracle does not
     finish this size in seconds, so parity goes through size-independent properties.  (i) the three evaluation
