@@ -416,7 +416,12 @@ def extra_mpo_1024(T, ctx, torch, dist, rank, world):
         Il = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
         Jr = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
         step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm
-        fl = 2 * nL * 19 * step + 2.0 * nL * Dm * Dm * nL
+
+        def chain_steps(S, right):  # full-bond environment extensions actually evaluated: distinct partial indices
+            n = S.shape[1]
+            return sum(len(np.unique(S[:, n - k:] if right else S[:, :k], axis=0)) for k in range(2, n + 1))
+
+        fl = (chain_steps(Il, False) + chain_steps(Jr, True)) * step + 2.0 * nL * Dm * Dm * nL
         if world == 1:
             dev, mx = fm.batchevaluate_device(Il, Jr, 0)
             del dev
@@ -424,10 +429,41 @@ def extra_mpo_1024(T, ctx, torch, dist, rank, world):
             dev, mx = fm.batchevaluate_device(Il, Jr, 0)
             ms = ctx.timers(reset=True)["pi_eval"]
             del dev
+            # the same Pi size over NESTED index sets, as a TCI run produces them (Icombined = kronecker(Iset, d), Iset
+            # grown site by site, chi = 256): shared prefixes / suffixes are evaluated once (ChainPlan, csrc/mpo.cu),
+            # which is what the reference's Dict memo does within one call (contraction.jl:112-176)
+            from tci_b200.util import kronecker_left, kronecker_right
+            Sl = np.arange(1, 5, dtype=np.int64)[:, None]
+            Sr = Sl.copy()
+            for _ in range(18):
+                cl, cr = kronecker_left(Sl, 4), kronecker_right(4, Sr)
+                Sl = cl[np.sort(g7.choice(len(cl), min(256, len(cl)), replace=False))]
+                Sr = cr[np.sort(g7.choice(len(cr), min(256, len(cr)), replace=False))]
+            In, Jn = kronecker_left(Sl, 4), kronecker_right(4, Sr)
+            res = {}
+            for label, env in (("dedup", None), ("plain", "1")):
+                if env:
+                    os.environ["TCI_MPO_NO_DEDUP"] = env
+                try:
+                    dev, mxn = fm.batchevaluate_device(In, Jn, 0)
+                    del dev
+                    ctx.timers(reset=True)
+                    dev, mxn = fm.batchevaluate_device(In, Jn, 0)
+                    res[label] = (ctx.timers(reset=True)["pi_eval"], mxn)
+                    del dev
+                finally:
+                    os.environ.pop("TCI_MPO_NO_DEDUP", None)
+            fln = (chain_steps(In, False) + chain_steps(Jn, True)) * step + 2.0 * nL * Dm * Dm * nL
+            extra["mpo_pi_eval_config5_1024_nested"] = {
+                "ms": res["dedup"][0], "ms_without_prefix_sharing": res["plain"][0],
+                "tflops": fln / (res["dedup"][0] * 1e-3) / 1e12,
+                "maxabs_rel_dev": abs(res["dedup"][1] - res["plain"][1]) / abs(res["plain"][1]),
+                "shape": "40 sites, bonds 256, Pi 1024 x 1024 over nested index sets (256 distinct parents per level)"}
             extra["mpo_pi_eval_config5_1024"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms,
                                                  "shape": "40 sites, bonds 256, nL=nR=1024, M=0 (Pi 1024 x 1024)",
-                                                 "flop_model": "19 full environment extensions per row and per "
-                                                               "column + final (1024 x 65536) x (65536 x 1024) product"}
+                                                 "flop_model": "one environment extension per DISTINCT partial index "
+                                                               "(random sets: 4, 16, 64, 256 at the first levels, 1024 "
+                                                               "after) + final (1024 x 65536) x (65536 x 1024) product"}
         else:
             from tci_b200.parallel import ShardedEvaluator
             for shard in ("rows", "cols"):

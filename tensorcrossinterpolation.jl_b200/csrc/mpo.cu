@@ -8,6 +8,8 @@
 // A per-point environment is the (La x Lb) matrix env[a + La*(b + Lb*q)].
 #include "tci_internal.h"
 
+#include <algorithm>
+
 struct MpoSite {
     const double *A, *B;
     i64 La, d1, S, Lan; // A: (La, d1, S, Lan)
@@ -36,10 +38,180 @@ __global__ void k_fill1(double *p, i64 n, double v)
     if (e < n) p[e] = v;
 }
 
+// ---- shared prefixes -----------------------------------------------------------------------------------------
+// The reference memoises environments in a Dict keyed by the partial index (contraction.jl:112-176): entries of an
+// index set that share a prefix (left) or suffix (right) share the environment.  The index sets of a TCI run are
+// nested (Icombined = kronecker(Iset, d), Iset itself grown site by site), so at chi = 256, d = 4 only a quarter of
+// the chain steps are distinct.  ChainPlan finds, level by level, the distinct partial indices of ONE call on the
+// host (direct-address table on (parent id, sigma)); the chain then runs one batched GEMM pair per level over the
+// distinct entries only, reading the parent's environment through a per-batch offset, and a gather expands the last
+// level to the entries of the index set.  (The Dict also persists across calls; this does not.)
+struct ChainPlan {
+    int nsteps = 0;
+    std::vector<i64> cnt;                 // distinct entries per level
+    std::vector<std::vector<i64>> parent; // per level: id of the parent entry at the previous level
+    std::vector<std::vector<i64>> sigma;  // per level: fused site index (0-based)
+    std::vector<i64> last_id;             // entry of the index set -> id at the last level
+    bool identity = true;                 // last_id[q] == q: no gather needed after the last level
+    bool shared = false;                  // some level has fewer distinct entries than the index set
+};
+
+// pos(k) = position inside an index entry read at level k: left chain off + k, right chain off + nsteps - 1 - k
+static bool plan_chain(const i64 *h_idx, int len, int off, int nsteps, i64 count, bool right, const i64 *dims,
+                       ChainPlan &P)
+{
+    if (!h_idx || nsteps <= 0 || count < 2 || count > (i64)1 << 22) return false;
+    P.nsteps = nsteps;
+    std::vector<i64> id((size_t)count, 0), nid((size_t)count);
+    i64 nprev = 1;
+    std::vector<i64> table;
+    for (int k = 0; k < nsteps; ++k) {
+        const int pos = right ? off + nsteps - 1 - k : off + k;
+        const i64 d = dims[k];
+        if (d <= 0 || nprev > ((i64)1 << 22) / d) return false; // table too large: fall back to the plain chain
+        table.assign((size_t)(nprev * d), -1);
+        std::vector<i64> par, sig;
+        for (i64 q = 0; q < count; ++q) {
+            const i64 f = h_idx[(i64)len * q + pos] - 1;
+            if (f < 0 || f >= d) return false; // out-of-range index: let the plain path deal with it
+            i64 &slot = table[(size_t)(id[q] * d + f)];
+            if (slot < 0) {
+                slot = (i64)par.size();
+                par.push_back(id[q]);
+                sig.push_back(f);
+            }
+            nid[q] = slot;
+        }
+        id.swap(nid);
+        nprev = (i64)par.size();
+        if (nprev < count) P.shared = true;
+        P.cnt.push_back(nprev);
+        P.parent.push_back(std::move(par));
+        P.sigma.push_back(std::move(sig));
+    }
+    P.identity = nprev == count;
+    if (P.identity)
+        for (i64 q = 0; q < count; ++q)
+            if (id[q] != q) {
+                P.identity = false;
+                break;
+            }
+    P.last_id.swap(id);
+    return true;
+}
+
+__global__ void k_gather_cols(const double *__restrict__ src, i64 D, const i64 *__restrict__ ids, i64 count,
+                              double *__restrict__ dst)
+{
+    const i64 total = D * count;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x)
+        dst[e] = src[(e % D) + D * ids[e / D]];
+}
+
+// chain over the distinct entries of a plan; `right` selects the step formulas of mpo_right_chain
+static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &P, bool right, i64 count, double **out,
+                             i64 *Da_out, i64 *Db_out)
+{
+    const int N = (int)t.nsites, nsteps = P.nsteps;
+    // one upload: per level [env offset of the parent][offset into A][offset into B]
+    std::vector<i64> host;
+    std::vector<size_t> base((size_t)nsteps);
+    {
+        i64 ea = 1, eb = 1; // dimensions of the environment that enters the level
+        for (int k = 0; k < nsteps; ++k) {
+            MpoSite m = site_of(t, right ? N - 1 - k : k);
+            const i64 c = P.cnt[k];
+            base[k] = host.size();
+            host.resize(host.size() + 3 * (size_t)c);
+            i64 *g = host.data() + base[k], *oa = g + c, *ob = oa + c;
+            for (i64 u = 0; u < c; ++u) {
+                const i64 f = P.sigma[k][u];
+                g[u] = P.parent[k][u] * ea * eb;
+                oa[u] = m.La * (f % m.d1);
+                ob[u] = m.Lb * m.S * (f / m.d1);
+            }
+            ea = right ? m.La : m.Lan;
+            eb = right ? m.Lb : m.Lbn;
+        }
+    }
+    DevBuf<i64> dev(ctx), ids(ctx);
+    TCI_CUDA(ctx, dev.upload(host.data(), host.size()));
+    double *env = nullptr;
+    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, sizeof(double)));
+    k_fill1<<<1, 32, 0, ctx->stream>>>(env, 1, 1.0);
+    ctx->launches++;
+    i64 Ea = 1, Eb = 1;
+    for (int k = 0; k < nsteps; ++k) {
+        MpoSite m = site_of(t, right ? N - 1 - k : k);
+        const i64 c = P.cnt[k];
+        const i64 *g = dev.p + base[k], *oa = g + c, *ob = oa + c;
+        double *tmp = nullptr, *nxt = nullptr;
+        int rc = 0;
+        if (!right) {
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * m.S * m.Lan) * c * sizeof(double)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * c * sizeof(double)));
+            // the two products of mpo_left_chain, the environment read at the parent's offset
+            rc = dgemm_dev_batched_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, 0, m.A, m.La * m.d1, 0,
+                                       0.0, tmp, m.Lb, m.Lb * m.S * m.Lan, c, g, oa, m.La % 2 == 0);
+            if (!rc)
+                rc = dgemm_dev_batched_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
+                                           m.Lb * m.S * m.Lan, m.B, m.Lb * m.S * m.d3, 0, 0.0, nxt, m.Lan,
+                                           m.Lan * m.Lbn, c, nullptr, ob, (m.Lb * m.S) % 2 == 0);
+            Ea = m.Lan;
+            Eb = m.Lbn;
+        } else {
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lbn * m.S * m.La) * c * sizeof(double)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.La * m.Lb) * c * sizeof(double)));
+            for (i64 h = 0; h < m.S && !rc; ++h)
+                rc = dgemm_dev_batched_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, 0,
+                                           m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h,
+                                           m.Lbn * m.S, m.Lbn * m.S * m.La, c, g, oa,
+                                           m.La % 2 == 0 && (m.Lan * m.Lbn) % 2 == 0);
+            for (i64 h = 0; h < m.S && !rc; ++h)
+                rc = dgemm_dev_batched_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
+                                           m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0,
+                                           nxt, m.La, m.La * m.Lb, c, nullptr, ob, (m.Lb * m.S) % 2 == 0);
+            Ea = m.La;
+            Eb = m.Lb;
+        }
+        dev_free(ctx, tmp);
+        dev_free(ctx, env);
+        env = nxt;
+        if (rc) {
+            dev_free(ctx, env);
+            return rc;
+        }
+    }
+    if (!P.identity) { // expand the distinct environments of the last level to the entries of the index set
+        double *full = nullptr;
+        const i64 D = Ea * Eb;
+        TCI_CUDA(ctx, ids.upload(P.last_id.data(), P.last_id.size()));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&full, (size_t)(D * count) * sizeof(double)));
+        const i64 total = D * count;
+        k_gather_cols<<<(unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            env, D, ids.p, count, full);
+        ctx->launches++;
+        dev_free(ctx, env);
+        env = full;
+    }
+    TCI_CUDA(ctx, cudaGetLastError());
+    *out = env;
+    *Da_out = Ea;
+    *Db_out = Eb;
+    return TCI_OK;
+}
+
 // evaluateleft (contraction.jl:112-139) for `count` points over sites [0, nsteps)
 static int mpo_left_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i64 *d_idx, int len, int off, i64 count,
-                          double **out, i64 *La_out, i64 *Lb_out)
+                          double **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
 {
+    if (h_idx && !getenv("TCI_MPO_NO_DEDUP")) {
+        ChainPlan P;
+        std::vector<i64> dims((size_t)std::max(nsteps, 0));
+        for (int k = 0; k < nsteps; ++k) dims[k] = t.localdims[k];
+        if (plan_chain(h_idx, len, off, nsteps, count, false, dims.data(), P) && P.shared)
+            return mpo_chain_planned(ctx, t, P, false, count, out, La_out, Lb_out);
+    }
     double *env = nullptr;
     TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(double)));
     k_fill1<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, 1.0);
@@ -83,9 +255,16 @@ static int mpo_left_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i6
 
 // evaluateright (contraction.jl:144-176) over the last nsteps sites
 static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i64 *d_idx, int len, int off, i64 count,
-                           double **out, i64 *La_out, i64 *Lb_out)
+                           double **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
 {
     const int N = (int)t.nsites;
+    if (h_idx && !getenv("TCI_MPO_NO_DEDUP")) {
+        ChainPlan P;
+        std::vector<i64> dims((size_t)std::max(nsteps, 0));
+        for (int k = 0; k < nsteps; ++k) dims[k] = t.localdims[N - 1 - k];
+        if (plan_chain(h_idx, len, off, nsteps, count, true, dims.data(), P) && P.shared)
+            return mpo_chain_planned(ctx, t, P, true, count, out, La_out, Lb_out);
+    }
     double *env = nullptr;
     TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(double)));
     k_fill1<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, 1.0);
@@ -130,24 +309,25 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
 }
 
 // environments alone (tci_env_eval): evaluateleft / evaluateright of contraction.jl:112-176 for `count` entries
-int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D)
+int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D,
+                 const i64 *h_idx)
 {
     i64 a = 1, b = 1;
-    int rc = side == 0 ? mpo_left_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b)
-                       : mpo_right_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b);
+    int rc = side == 0 ? mpo_left_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx)
+                       : mpo_right_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx);
     *D = a * b;
     return rc;
 }
 
 // batchevaluate(::Contraction) contraction.jl:236-335 (projector = nothing, f = nothing)
 int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
-                tci_dmat *out)
+                tci_dmat *out, const i64 *hI, const i64 *hJ)
 {
     double *X = nullptr, *right = nullptr;
     i64 La = 1, Lb = 1, Ra = 1, Rb = 1;
-    int rc = mpo_left_chain(ctx, t, (int)nl, dI, (int)nl, 0, nI, &X, &La, &Lb);
+    int rc = mpo_left_chain(ctx, t, (int)nl, dI, (int)nl, 0, nI, &X, &La, &Lb, hI);
     if (rc) return rc;
-    rc = mpo_right_chain(ctx, t, (int)nr, dJ, (int)nr, 0, nJ, &right, &Ra, &Rb);
+    rc = mpo_right_chain(ctx, t, (int)nr, dJ, (int)nr, 0, nJ, &right, &Ra, &Rb, hJ);
     if (rc) {
         dev_free(ctx, X);
         return rc;

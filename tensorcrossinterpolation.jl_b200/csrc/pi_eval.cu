@@ -329,7 +329,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
             if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
             break;
         default:
-            rc = pi_eval_mpo(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out);
+            rc = pi_eval_mpo(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, I, J);
             if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
             break;
         }
@@ -424,7 +424,7 @@ extern "C" int tci_env_eval(tci_ctx *ctx, int64_t target_id, int side, const int
     double *env = nullptr;
     i64 D = 1;
     int rc = t.kind == 1 ? env_eval_tt(ctx, t, side, d_idx.p, (int)len, count, &env, &D)
-                         : env_eval_mpo(ctx, t, side, d_idx.p, (int)len, count, &env, &D);
+                         : env_eval_mpo(ctx, t, side, d_idx.p, (int)len, count, &env, &D, idx);
     if (rc) return rc;
     cudaError_t e = cudaMemcpy2DAsync(dst->p + dst->ld * col0, dst->ld * sizeof(double), env, D * sizeof(double),
                                       D * sizeof(double), count, cudaMemcpyDeviceToDevice, ctx->stream);

@@ -173,8 +173,10 @@ int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, 
                      tci_dmat *out, unsigned long long *d_maxbits);
 int pi_eval_tt(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
                tci_dmat *out);
+// hI / hJ: host copies of the index sets (nullable) -- shared prefixes / suffixes are evaluated once (mpo.cu)
 int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
-                tci_dmat *out);
+                tci_dmat *out, const i64 *hI = nullptr, const i64 *hJ = nullptr);
 int env_eval_tt(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D);
-int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D);
+int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D,
+                 const i64 *h_idx = nullptr);
 int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits);

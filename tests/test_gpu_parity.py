@@ -563,6 +563,56 @@ def test_mpo_target(T, oracle):  # test_contraction.jl:68-146 (real-valued)
         np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
 
 
+def _nested_sets(T, rng, N, d, keep):
+    """left[k] / right[k]: nested sets of prefixes / suffixes of length k, grown site by site as TCI grows Iset / Jset."""
+    left, right = {1: np.arange(1, d + 1, dtype=np.int64)[:, None]}, {1: np.arange(1, d + 1, dtype=np.int64)[:, None]}
+    for k in range(2, N):
+        cl, cr = T.kronecker_left(left[k - 1], d), T.kronecker_right(d, right[k - 1])
+        left[k] = cl[np.sort(rng.choice(len(cl), min(keep, len(cl)), replace=False))]
+        right[k] = cr[np.sort(rng.choice(len(cr), min(keep, len(cr)), replace=False))]
+    return left, right
+
+
+def test_mpo_shared_prefixes(T, oracle, monkeypatch):
+    """Nested index sets (Icombined = kronecker(Iset, d) with Iset grown site by site, as a TCI run produces them): the
+    chain evaluates every distinct prefix / suffix once (ChainPlan in csrc/mpo.cu -- the within-call effect of the
+    reference's Dict memo, contraction.jl:112-176).  Same Pi as the oracle, and as the plain chain."""
+    rng = np.random.default_rng(77)
+    N = 10
+    d1, d2, d3 = [2] * N, [2, 3] * (N // 2), [2] * N
+    bonds = [1, 3, 5, 6, 6, 7, 6, 6, 5, 3, 1]
+    A = _rand_mpo(rng, bonds, d1, d2)
+    B = _rand_mpo(rng, bonds, d2, d3)
+    f = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    o = oracle.Target.mpo_pair(A, B)
+    left, right = _nested_sets(T, rng, N, 4, 13)
+    for nl in range(1, N):
+        nr = N - nl
+        I = T.kronecker_left(left[nl - 1], 4) if nl > 1 else left[1]
+        J = T.kronecker_right(4, right[nr - 1]) if nr > 1 else right[1]
+        assert I.shape[1] == nl and J.shape[1] == nr
+        res = f(I, J, 0)
+        oref, _ = o.pi_eval(I.tolist(), J.tolist(), 0)
+        np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
+        monkeypatch.setenv("TCI_MPO_NO_DEDUP", "1")
+        plain = f(I, J, 0)
+        monkeypatch.delenv("TCI_MPO_NO_DEDUP")
+        np.testing.assert_allclose(res, plain, rtol=1e-12, atol=1e-15)
+        # duplicated entries in the index sets (the gather after the last level)
+        Id, Jd = np.concatenate([I, I[:3]]), np.concatenate([J[-2:], J])
+        resd = f(Id, Jd, 0)
+        tol = dict(rtol=1e-12, atol=1e-15)  # (the final GEMM may tile the larger matrix differently)
+        np.testing.assert_allclose(resd[:len(I), 2:], res, **tol)
+        np.testing.assert_allclose(resd[len(I):, 2:], res[:3], **tol)
+        np.testing.assert_allclose(resd[:len(I), :2], res[:, -2:], **tol)
+    # M = 1 and M = 2 calls go through the same chains
+    I, J = T.kronecker_left(left[3], 4), T.kronecker_right(4, right[3])
+    for M, Jm in ((2, J), (1, T.kronecker_right(4, right[4]))):
+        res = f(I, Jm, M)
+        oref, _ = o.pi_eval(I.tolist(), Jm.tolist(), M)
+        np.testing.assert_allclose(res, oref, rtol=RTOL, atol=1e-13)
+
+
 def test_batchevaluate_projector(T, oracle):  # test_contraction.jl:101-139 (real-valued), cachedtensortrain.jl:170-215
     rng = np.random.default_rng(31)
     N = 4
