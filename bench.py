@@ -399,6 +399,13 @@ def extra_globalsearch(T, ctx, torch, dist, rank, world):
     return extra
 
 
+def chain_steps(S, right):
+    """Full-bond environment extensions a chain evaluates for the index set S: one per DISTINCT partial index
+    (prefixes of the left set, suffixes of the right set), levels 2..n (level 1 starts from the bond of dimension 1)."""
+    n = S.shape[1]
+    return sum(len(np.unique(S[:, n - k:] if right else S[:, :k], axis=0)) for k in range(2, n + 1))
+
+
 def extra_mpo_1024(T, ctx, torch, dist, rank, world):
     extra = {}
     # --- config 5 shape, the two-site Pi of the MPO x MPO target at the middle bond with nL = nR = 1024 (SURVEY 8d),
@@ -416,10 +423,6 @@ def extra_mpo_1024(T, ctx, torch, dist, rank, world):
         Il = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
         Jr = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
         step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm
-
-        def chain_steps(S, right):  # full-bond environment extensions actually evaluated: distinct partial indices
-            n = S.shape[1]
-            return sum(len(np.unique(S[:, n - k:] if right else S[:, :k], axis=0)) for k in range(2, n + 1))
 
         fl = (chain_steps(Il, False) + chain_steps(Jr, True)) * step + 2.0 * nL * Dm * Dm * nL
         if world == 1:
@@ -620,11 +623,11 @@ def run_extra(T, ctx, torch, dist, rank, world, stream):
         dev, mx = fm.batchevaluate_device(Il, Jr, 2)
         ms = ctx.timers(reset=True)["pi_eval"]
         step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm  # one environment extension (contraction.jl:103-109)
-        fl = (nL + nR) * 18 * step + 2 * (nL * (2.0 * Dm * Dm * 8 * Dm) + nL * 4 * 8 * 2.0 * Dm * Dm * Dm / 4) \
-            + 2.0 * nL * 16 * Dm * Dm * nR
+        fl = (chain_steps(Il, False) + chain_steps(Jr, True)) * step \
+            + 2 * (nL * (2.0 * Dm * Dm * 8 * Dm) + nL * 4 * 8 * 2.0 * Dm * Dm * Dm / 4) + 2.0 * nL * 16 * Dm * Dm * nR
         extra["mpo_pi_eval_config5"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms, "launches": ctx.launches - l0,
                                         "shape": f"40 sites, bonds 256, nL=nR={nL}, M=2 (Pi {nL * 16} x {nR})",
-                                        "flop_model": "env extensions + centre folds + final product"}
+                                        "flop_model": "one env extension per distinct partial index + centre folds + final product"}
         del dev, fm
         # --- config 5 shape: one zip-up site step (contraction.jl:455-464) at chi = Da = Db = 256, s = 2x2x2:
         # R (256,256,256), A, B (256,2,2,256) -> C (1024 x 65536), the matrix _factorize gets next ---
