@@ -96,6 +96,12 @@ int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const doub
 int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,
                         const int64_t *dimsB4, const double *const *B, int64_t *target_id);
 int tci_target_destroy(tci_ctx *ctx, int64_t target_id);
+/* The elementwise function of a Contraction (`f` of contraction.jl:5-62, applied at :203-205 and :330-332).  A
+ * device kernel cannot call a Julia closure, so functions are registered by id like the targets themselves:
+ * TCI_F_NONE, TCI_F_AFFINE (a*x + b, rounded multiply then rounded add), TCI_F_ABS (|x|), TCI_F_SQUARE (x*x).
+ * Only MPO-pair targets accept one (TCI_ERR_ARG otherwise).                                               */
+enum { TCI_F_NONE = 0, TCI_F_AFFINE = 1, TCI_F_ABS = 2, TCI_F_SQUARE = 3 };
+int tci_target_set_elementwise(tci_ctx *ctx, int64_t target_id, int kind, double a, double b);
 /* f(x) for `count` full multi-indices (nsites x count): the scalar call
  * (bf::BatchEvaluatorAdapter)(indexset) batcheval.jl:11-13, TTCache/Contraction
  * evaluate cachedtensortrain.jl:130-146, contraction.jl:189-207.                  */

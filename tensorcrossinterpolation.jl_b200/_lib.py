@@ -44,6 +44,7 @@ SYMBOLS = {
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
     "tci_target_destroy": (C.c_int, [VP, i64]),
+    "tci_target_set_elementwise": (C.c_int, [VP, i64, C.c_int, f64, f64]),
     "tci_target_eval": (C.c_int, [VP, i64, P_i64, i64, P_f64]),
     "tci_pi_eval": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, P_f64, C.POINTER(VP), P_f64]),
     "tci_pi_eval_into": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, VP, i64, P_f64]),

@@ -16,13 +16,20 @@ I64MAX = 2**63 - 1
 
 
 class Contraction(BatchEvaluator):
-    """struct Contraction (contraction.jl:5-62); f (elementwise function) is not supported on device."""
+    """struct Contraction (contraction.jl:5-62).  The elementwise function `f` (applied to the product at
+    contraction.jl:203-205, 330-332) is registered by id, as the targets are -- a device kernel cannot call a host
+    closure: ("affine", a, b) for x -> a*x + b (the reference's test function x -> 2x is ("affine", 2.0, 0.0)),
+    ("abs",), ("square",)."""
     has_environments = True
+    ELEMENTWISE = {"affine": 1, "abs": 2, "square": 3}
 
     def __init__(self, a, b, f=None, ctx=None):
         ctx = ctx or _lib.default_context()
         if f is not None:
-            raise NotImplementedError("Contraction with an elementwise function f is not available on the device")
+            if callable(f) or not f or f[0] not in self.ELEMENTWISE:
+                raise NotImplementedError("Contraction: the elementwise function f must be one of the device functions "
+                                          '("affine", a, b), ("abs",), ("square",); host closures cannot run on the GPU')
+            f = (f[0], float(f[1]) if len(f) > 1 else 1.0, float(f[2]) if len(f) > 2 else 0.0)
         A = a.sitetensors if hasattr(a, "sitetensors") else list(a)
         B = b.sitetensors if hasattr(b, "sitetensors") else list(b)
         if len(A) != len(B):
@@ -39,6 +46,10 @@ class Contraction(BatchEvaluator):
         self.sitedims = [[int(x.shape[1]), int(y.shape[2])] for x, y in zip(ka, kb)]
         super().__init__(ctx, tid.value, [s[0] * s[1] for s in self.sitedims])
         self.mpo = (ka, kb)
+        self.f = f
+        if f is not None:
+            ctx.check(lib().tci_target_set_elementwise(ctx.h, self.id, self.ELEMENTWISE[f[0]], f[1], f[2]))
+            self.has_environments = False  # Pi is f(left^T right): not a product of environments any more
 
     def batchevaluate(self, leftindexset, rightindexset, M, projector=None):
         """batchevaluate(obj::Contraction, leftindexset, rightindexset, Val(M), projector) (contraction.jl:236-335)."""
@@ -186,7 +197,20 @@ def contract_TCI(A, B, initialpivots=None, f=None, ctx=None, **kwargs):
     return TensorTrain(cores)
 
 
-def contract(A, B, algorithm="TCI", tolerance=1e-12, maxbonddim=I64MAX, f=None, **kwargs):  # :515-542
+def contract(A, B, algorithm="TCI", tolerance=1e-12, maxbonddim=I64MAX, f=None, **kwargs):  # :515-560
+    # MPS x MPO and MPO x MPS (contraction.jl:544-560): a three-leg train gets a site leg of size 1 on the side that is
+    # not contracted -- (Dl, 1, s, Dr) on the left, (Dl, s, 1, Dr) on the right -- and the result is folded back
+    ca = A.sitetensors if hasattr(A, "sitetensors") else list(A)
+    cb = B.sitetensors if hasattr(B, "sitetensors") else list(B)
+    a3, b3 = all(c.ndim == 3 for c in ca), all(c.ndim == 3 for c in cb)
+    if a3 != b3:
+        if a3:
+            A = TensorTrain([np.asfortranarray(c).reshape((c.shape[0], 1, c.shape[1], c.shape[2]), order="F") for c in ca])
+        else:
+            B = TensorTrain([np.asfortranarray(c).reshape((c.shape[0], c.shape[1], 1, c.shape[2]), order="F") for c in cb])
+        tt = contract(A, B, algorithm=algorithm, tolerance=tolerance, maxbonddim=maxbonddim, f=f, **kwargs)
+        return TensorTrain([np.asfortranarray(c).reshape((c.shape[0], -1, c.shape[-1]), order="F")
+                            for c in tt.sitetensors])
     if algorithm == "TCI":
         return contract_TCI(A, B, tolerance=tolerance, maxbonddim=maxbonddim, f=f, **kwargs)
     if algorithm == "naive":

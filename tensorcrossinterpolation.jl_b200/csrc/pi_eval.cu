@@ -248,6 +248,42 @@ int pi_eval_analytic(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, 
     return TCI_OK;
 }
 
+// Contraction.f: the elementwise function of the product (contraction.jl:203-205, 330-332), by id
+__global__ void k_apply_f(double *__restrict__ p, i64 m, i64 n, i64 ld, int kind, double a, double b)
+{
+    const i64 total = m * n;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        double *x = p + (e % m) + ld * (e / m);
+        const double v = *x;
+        *x = kind == TCI_F_AFFINE ? __dadd_rn(__dmul_rn(a, v), b) : (kind == TCI_F_ABS ? fabs(v) : __dmul_rn(v, v));
+    }
+}
+
+int apply_elementwise(tci_ctx *ctx, const TargetDev &t, double *p, i64 m, i64 n, i64 ld)
+{
+    if (t.fkind == TCI_F_NONE || m * n == 0) return TCI_OK;
+    const unsigned blocks = (unsigned)std::min<i64>((m * n + 255) / 256, (i64)ctx->sm_count * 8);
+    k_apply_f<<<blocks, 256, 0, ctx->stream>>>(p, m, n, ld, t.fkind, t.fa, t.fb);
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
+extern "C" int tci_target_set_elementwise(tci_ctx *ctx, int64_t target_id, int kind, double a, double b)
+{
+    TCI_ENTER(ctx);
+    auto it = ctx->targets.find(target_id);
+    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    TargetDev &t = *it->second;
+    if (t.kind != 2) return tci_fail(ctx, TCI_ERR_ARG, "tci_target_set_elementwise: only a Contraction carries a function f");
+    if (kind < TCI_F_NONE || kind > TCI_F_SQUARE)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_target_set_elementwise: unknown function id");
+    t.fkind = kind;
+    t.fa = a;
+    t.fb = b;
+    return TCI_OK;
+}
+
 // max |x| over an m x n matrix (for targets whose Pi comes out of a GEMM)
 __global__ void k_maxabs(const double *__restrict__ p, i64 m, i64 n, i64 ld, unsigned long long *gmax)
 {
@@ -330,6 +366,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
             break;
         default:
             rc = pi_eval_mpo(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, I, J);
+            if (!rc) rc = apply_elementwise(ctx, t, out->p, out->m, out->n, out->ld);
             if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
             break;
         }
@@ -484,7 +521,10 @@ int target_eval_dev(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, dou
         TCI_CUDA(ctx, cudaGetLastError());
         return TCI_OK;
     case 1: return target_eval_tt(ctx, t, d_idx, count, d_out);
-    default: return target_eval_mpo(ctx, t, d_idx, count, d_out);
+    default: {
+        int rc = target_eval_mpo(ctx, t, d_idx, count, d_out);
+        return rc ? rc : apply_elementwise(ctx, t, d_out, count, 1, count);
+    }
     }
 }
 

@@ -41,7 +41,12 @@ struct TargetDev {
     // MPO pair
     std::vector<double *> A, B;
     std::vector<i64> adl, as1, as2, adr, bdl, bs1, bs2, bdr;
+    // elementwise function applied to the product (Contraction.f, contraction.jl:330-332): TCI_F_* id + parameters
+    int fkind = 0;
+    double fa = 1.0, fb = 0.0;
 };
+// applies the target's elementwise function to an m x n block (no-op for fkind == 0)   pi_eval.cu
+int apply_elementwise(tci_ctx *ctx, const TargetDev &t, double *p, i64 m, i64 n, i64 ld);
 
 struct tci_ctx {
     int device = 0;

@@ -751,6 +751,81 @@ def test_contract_zipup_and_tci_vs_dense(T):  # test_contraction.jl:68-99, 185-1
     np.testing.assert_allclose(dense(ttn.sitetensors), ref, rtol=1e-10, atol=1e-12)
 
 
+def test_contraction_elementwise_function(T, oracle):
+    """Contraction with an elementwise f (contraction.jl:203-205, 330-332; the reference tests use f = x -> 2x,
+    test_contraction.jl:148-181): registered by id on the device.  f(Pi) against the oracle's Pi with f applied on
+    the host, pointwise evaluation, and contract(...; algorithm=:TCI, f) against the dense product."""
+    rng = np.random.default_rng(41)
+    N = 4
+    d1, d2, d3 = [2, 2, 2, 2], [2, 3, 2, 2], [2, 2, 3, 2]
+    A = _rand_mpo(rng, [1, 2, 3, 2, 1], d1, d2)
+    B = _rand_mpo(rng, [1, 3, 2, 3, 1], d2, d3)
+    o = oracle.Target.mpo_pair(A, B)
+    ld = o.localdims
+    pts = rand_indexset(rng, ld, 50)
+    for spec, fn in ((("affine", 2.0, 0.0), lambda x: 2.0 * x), (("affine", -0.5, 0.25), lambda x: -0.5 * x + 0.25),
+                     (("abs",), np.abs), (("square",), lambda x: x * x)):
+        f = T.Contraction(T.TensorTrain(A), T.TensorTrain(B), f=spec)
+        assert not f.has_environments
+        for nl, nr in ((1, 1), (2, 2), (0, 3), (4, 0)):
+            M = N - nl - nr
+            I = rand_indexset(rng, ld[:nl], 7 if nl else 1)
+            J = rand_indexset(rng, ld[N - nr:], 5 if nr else 1)
+            oref, _ = o.pi_eval(I.tolist(), J.tolist(), M)
+            np.testing.assert_allclose(f(I, J, M), fn(oref), rtol=RTOL, atol=1e-13)
+            dev, mx = f.batchevaluate_device(I, J, M)
+            assert abs(mx - np.max(np.abs(fn(oref)))) <= RTOL * max(mx, 1e-300)
+        np.testing.assert_allclose(f.evaluate_points(pts), fn(np.array([o(p) for p in pts])), rtol=RTOL, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        T.Contraction(T.TensorTrain(A), T.TensorTrain(B), f=lambda x: 2 * x)
+
+    def dense(cores):
+        out = cores[0]
+        for c in cores[1:]:
+            out = np.tensordot(out, c, axes=([-1], [0]))
+        return out[0, ..., 0]
+
+    la = "".join(chr(97 + 2 * s) + chr(97 + 2 * s + 1) for s in range(N))
+    lb = "".join(chr(97 + 2 * s + 1) + chr(65 + s) for s in range(N))
+    lc = "".join(chr(97 + 2 * s) + chr(65 + s) for s in range(N))
+    ref = np.einsum(f"{la},{lb}->{lc}", dense(A), dense(B))
+    tt = T.contract(T.TensorTrain(A), T.TensorTrain(B), algorithm="TCI", tolerance=1e-12, maxbonddim=60,
+                    f=("affine", 2.0, 0.0))
+    np.testing.assert_allclose(dense(tt.sitetensors), 2.0 * ref, rtol=1e-8, atol=1e-10)
+    with pytest.raises(RuntimeError, match="Naive contraction implementation cannot contract"):
+        T.contract(T.TensorTrain(A), T.TensorTrain(B), algorithm="naive", f=("affine", 2.0, 0.0))
+
+
+@pytest.mark.parametrize("algorithm", ["TCI", "naive", "zipup"])
+def test_contract_mpo_mps(T, algorithm):  # test_contraction.jl:148-181, 190-194 (real-valued; f = nothing and x -> 2x)
+    rng = np.random.default_rng(43)
+    N = 4
+    A = _rand_mpo(rng, [1, 2, 3, 2, 1], [3] * N, [3] * N)
+    b = _rand_tt(rng, [1, 2, 3, 2, 1], [3] * N)
+
+    def dense(cores):
+        out = cores[0]
+        for c in cores[1:]:
+            out = np.tensordot(out, c, axes=([-1], [0]))
+        return out[0, ..., 0]
+
+    mat = dense(A).transpose([0, 2, 4, 6, 1, 3, 5, 7]).reshape(81, 81)  # rows: first site legs, columns: second site legs
+    vec = dense(b).reshape(81)
+    kw = dict(tolerance=1e-12, maxbonddim=40) if algorithm == "TCI" else {}
+    ab = T.contract(T.TensorTrain(A), T.TensorTrain(b), algorithm=algorithm, **kw)
+    ba = T.contract(T.TensorTrain(b), T.TensorTrain(A), algorithm=algorithm, **kw)
+    assert [c.shape[1] for c in ab.sitetensors] == [3] * N and all(c.ndim == 3 for c in ab.sitetensors)
+    np.testing.assert_allclose(dense(ab.sitetensors).reshape(81), mat @ vec, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(dense(ba.sitetensors).reshape(81), vec @ mat, rtol=1e-8, atol=1e-10)
+    f2 = ("affine", 2.0, 0.0)
+    if algorithm == "TCI":
+        ab2 = T.contract(T.TensorTrain(A), T.TensorTrain(b), algorithm=algorithm, f=f2, **kw)
+        np.testing.assert_allclose(dense(ab2.sitetensors).reshape(81), 2.0 * (mat @ vec), rtol=1e-8, atol=1e-10)
+    else:
+        with pytest.raises(RuntimeError, match="cannot contract matrix product with a function"):
+            T.contract(T.TensorTrain(A), T.TensorTrain(b), algorithm=algorithm, f=f2)
+
+
 @pytest.mark.parametrize("method", ["LU", "CI", "SVD"])
 def test_compress(T, method):  # tensortrain.jl:149-183 ; test_tensortrain.jl compress tests (structure re-used)
     rng = np.random.default_rng(12)
