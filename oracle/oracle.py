@@ -486,3 +486,76 @@ def mpo_batchevaluate_projected(A, B, I, J, M, projector=None):
             if len(pr) != 2:
                 raise OracleError(f"Invalid projector at {nl + k + 1}: {list(pr)}, the length must be 2")  # :252
     return tt_batchevaluate_projected(prod, sitedims, I, J, M, projector)
+
+
+# ---- ComplexF64 groundwork (numpy restatement, small cases; NO product path uses it yet) -----------
+def _abs2c(z):  # abs2(z::Complex) = real(z)*real(z) + imag(z)*imag(z)   (Base complex.jl)
+    return z.real * z.real + z.imag * z.imag
+
+
+def submatrixargmax_abs2_complex(A, rows=None, cols=None):
+    """submatrixargmax(abs2, A, rows, cols), matrixlu.jl:1-32, for a complex matrix: columns outer, rows inner,
+    strict '>' from typemin, first maximum wins.  rows / cols are 1-based lists (None = all).  Returns 1-based (r, c)."""
+    A = np.asarray(A, dtype=np.complex128)
+    rows = list(range(1, A.shape[0] + 1)) if rows is None else list(rows)
+    cols = list(range(1, A.shape[1] + 1)) if cols is None else list(cols)
+    if not rows:
+        raise OracleError("rows must not be empty")  # :10
+    if not cols:
+        raise OracleError("cols must not be empty")  # :11
+    m, mr, mc = -np.inf, rows[0], cols[0]
+    for c in cols:
+        for r in rows:
+            v = _abs2c(A[r - 1, c - 1])
+            if v > m:
+                m, mr, mc = v, r, c
+    return mr, mc
+
+
+def rrlu_complex(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True):
+    """_optimizerrlu! (matrixlu.jl:141-181) with swaprow!/swapcol!/addpivot! (:98-136) for a ComplexF64 matrix, element by
+    element in numpy complex128: pivot metric abs2, stop rule on abs(pivot), physical swaps, scaling by true division,
+    trailing update a - x*y (complex multiply then subtract).  Python's complex division is Smith's algorithm, Julia's
+    `/` is a scaled variant of it: the quotients can differ in the last bit, so L/U are pinned to ~1e-15, the pivot
+    ORDER exactly wherever candidates are not within rounding of each other.  Returns
+    (rowperm, colperm, L, U, npivot, error), permutations 1-based."""
+    A = np.array(A, dtype=np.complex128, order="F")
+    m, n = A.shape
+    mr = min(m, n) if maxrank is None else min(maxrank, m, n)
+    rowperm, colperm = list(range(1, m + 1)), list(range(1, n + 1))
+    npivot, maxerror, error = 0, 0.0, 0.0
+    while npivot < mr:
+        k = npivot
+        pr, pc = submatrixargmax_abs2_complex(A, range(k + 1, m + 1), range(k + 1, n + 1))
+        error = abs(A[pr - 1, pc - 1])
+        if (error < reltol * maxerror or error < abstol) and npivot > 0:  # :155 (abs(rtol*maxerror) == rtol*maxerror)
+            break
+        maxerror = max(maxerror, error)
+        A[[k, pr - 1], :] = A[[pr - 1, k], :]  # swaprow! :98-104
+        rowperm[k], rowperm[pr - 1] = rowperm[pr - 1], rowperm[k]
+        A[:, [k, pc - 1]] = A[:, [pc - 1, k]]  # swapcol! :106-112
+        colperm[k], colperm[pc - 1] = colperm[pc - 1], colperm[k]
+        if leftorthogonal:  # addpivot! :114-136
+            for i in range(k + 1, m):
+                A[i, k] = A[i, k] / A[k, k]
+        else:
+            for j in range(k + 1, n):
+                A[k, j] = A[k, j] / A[k, k]
+        for j in range(k + 1, n):
+            for i in range(k + 1, m):
+                A[i, j] = A[i, j] - A[i, k] * A[k, j]
+        npivot += 1
+    r = npivot
+    L = np.tril(A[:, :r])
+    U = np.triu(A[:r, :])
+    if np.isnan(L).any():
+        raise OracleError("lu.L contains NaNs")  # :164-166
+    if np.isnan(U).any():
+        raise OracleError("lu.U contains NaNs")
+    if leftorthogonal:
+        L[np.arange(r), np.arange(r)] = 1.0
+    else:
+        U[np.arange(r), np.arange(r)] = 1.0
+    if r >= min(m, n):
+        error = 0.0  # :176-178
+    return np.array(rowperm), np.array(colperm), L, U, r, float(error)

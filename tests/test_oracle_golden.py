@@ -445,3 +445,39 @@ def test_projected_batchevaluate(oracle):
     np.testing.assert_allclose(res, mi[:, :, 1, 0, :, :], rtol=1e-13)
     with pytest.raises(oracle.OracleError, match="Invalid parameter M"):
         oracle.tt_batchevaluate_projected(cores, [[2, 3]] * 4, I, J, 1)
+
+
+def test_complex_groundwork_argmax_and_rrlu(oracle):
+    """ComplexF64 groundwork for SURVEY 8f-4 (no product path yet).  The reference's complex arg-max literal
+    (test_matrixlu.jl:39-52) and the real-valued rrLU testsets re-used with complex data: L*U reproduces the permuted
+    matrix, the first pivot is the largest element, rank-3 data stops at 3 pivots (test_matrixlu.jl:142-165 structure), and on
+    real input the complex restatement picks exactly the pivots of the Float64 oracle."""
+    A = np.array([[0, 1, 2, 3, 4, 5],
+                  [1, 1 + 1j, 2 + 1j, 3 + 1j, 4 + 1j, 5 + 1j],
+                  [1, 1 + 2j, 2 + 2j, 3 + 2j, 4 + 2j, 5 + 2j]], dtype=np.complex128)
+    am = oracle.submatrixargmax_abs2_complex
+    assert am(A, [3], [5]) == (3, 5)
+    ref = np.unravel_index(np.argmax((np.abs(A) ** 2).flatten(order="F")), A.shape, order="F")  # Julia argmax: column-major
+    assert am(A) == (ref[0] + 1, ref[1] + 1)
+    assert am(A, [1], None) == (1, int(np.argmax(np.abs(A[0]) ** 2)) + 1)
+    assert am(A, None, [1]) == (int(np.argmax(np.abs(A[:, 0]) ** 2)) + 1, 1)
+    with pytest.raises(oracle.OracleError, match="rows must not be empty"):
+        am(A, [], [1])
+    rng = np.random.default_rng(12)
+    for lo in (True, False):
+        B = rng.standard_normal((9, 7)) + 1j * rng.standard_normal((9, 7))
+        rp, cp, L, U, r, err = oracle.rrlu_complex(B, leftorthogonal=lo)
+        assert r == 7 and err == 0.0
+        np.testing.assert_allclose(L @ U, B[rp - 1][:, cp - 1], rtol=1e-13, atol=1e-13)
+        assert abs((U if lo else L)[0, 0]) == np.max(np.abs(B))  # the first pivot is the largest element
+        p = rng.standard_normal((10, 3)) + 1j * rng.standard_normal((10, 3))
+        q = rng.standard_normal((3, 12)) + 1j * rng.standard_normal((3, 12))
+        rp, cp, L, U, r, err = oracle.rrlu_complex(p @ q, reltol=1e-10, leftorthogonal=lo)
+        assert r == 3 and err < 1e-10 * np.max(np.abs(p @ q)) * 100
+        np.testing.assert_allclose(L @ U, (p @ q)[rp - 1][:, cp - 1], rtol=1e-10, atol=1e-12)
+        R = rng.standard_normal((8, 6))
+        ref = oracle.rrlu(R, leftorthogonal=lo)
+        rp, cp, L, U, r, err = oracle.rrlu_complex(R, leftorthogonal=lo)
+        assert r == ref.npivot and np.array_equal(rp, ref.rowpermutation) and np.array_equal(cp, ref.colpermutation)
+        np.testing.assert_allclose(L.real, ref.L, rtol=1e-13, atol=1e-14)
+        assert np.max(np.abs(L.imag)) == 0.0
