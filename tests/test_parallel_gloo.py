@@ -63,6 +63,44 @@ def _worker(rank, world, port, q):
         dist.all_reduce(part)  # stands in for the peer stores into the owner's buffer (disjoint row ranges)
         res["pi_rows_equal"] = bool(np.array_equal(part[:, :23].numpy().T, ref))
         res["maxabs_rows"] = P.maxabs_allreduce(dist, torch, bmx, "cpu") == refmx
+        # ---- contraction Pi sharded by rows with BOTH environment chains sharded (ShardedEvaluator shard="rows"):
+        # right environments of the rank's column block -> all-gather -> left environments of its rows -> block
+        # product at its row offset.  Environments from a numpy chain here (the device computes them on the GPU box).
+        g2 = np.random.default_rng(5)
+        bonds, dims = [1, 3, 4, 3, 2, 1], [2, 3, 2, 3, 2]
+        cores = [np.asfortranarray(g2.random((bonds[k], dims[k], bonds[k + 1])) - 0.4) for k in range(5)]
+        It = np.stack([g2.integers(1, dims[k] + 1, 37) for k in range(2)], axis=1)
+        Jt = np.stack([g2.integers(1, dims[2 + k] + 1, 21) for k in range(3)], axis=1)
+        reft, _ = orc.Target.tt(cores).pi_eval(It.tolist(), Jt.tolist(), 0)
+
+        def lenv(idx):  # evaluateleft, cachedtensortrain.jl:77-100
+            v = np.ones((1, 1))
+            for k2, sgm in enumerate(idx):
+                v = v @ cores[k2][:, sgm - 1, :]
+            return v[0]
+
+        def renv(idx):  # evaluateright, :102-128
+            v = np.ones((1, 1))
+            for k2 in range(len(idx) - 1, -1, -1):
+                v = cores[2 + k2][:, idx[k2] - 1, :] @ v
+            return v[:, 0]
+
+        D = bonds[2]
+        cblk, cranges = P.column_blocks(len(Jt), world)
+        clo, chi = cranges[rank]
+        rfull = torch.zeros((cblk * world, 8), dtype=torch.float64)  # (columns, padded D): one environment per row
+        for jj in range(clo, chi):
+            rfull[rank * cblk + (jj - clo), :D] = torch.from_numpy(renv(Jt[jj]))
+        P.gather_column_blocks(dist, torch, rfull, cblk, rank)
+        R = rfull[:len(Jt), :D].numpy().T  # D x nJ on every rank
+        rb, rr = P.row_blocks(len(It), world)
+        rlo2, rhi2 = rr[rank]
+        acc = torch.zeros((len(It), len(Jt)), dtype=torch.float64)
+        if rhi2 > rlo2:
+            Lb = np.array([lenv(It[ii]) for ii in range(rlo2, rhi2)])
+            acc[rlo2:rhi2] = torch.from_numpy(Lb @ R)
+        dist.all_reduce(acc)  # stands in for the peer stores into the owner's Pi (disjoint row ranges)
+        res["tt_rows_two_chains"] = bool(np.max(np.abs(acc.numpy() - reft)) <= 1e-13 * np.max(np.abs(reft)))
         # ---- sharded global search ----
         R = 10
         t = orc.Target.builtin(6, [R, 1], [2] * R)
@@ -84,6 +122,10 @@ def _worker(rank, world, port, q):
         pr = P.broadcast_pivots(dist, pr, 0)
         res["bcast"] = pr.npivot == 3 and pr.rowindices.tolist() == [4, 1, 2] and pr.pivoterrors[-1] == 0.0
         q.put((rank, res))
+    except Exception as e:  # report instead of leaving the parent waiting on the queue
+        import traceback
+        q.put((rank, {"exception: " + repr(e) + "\n" + traceback.format_exc(): False}))
+        raise
     finally:
         dist.destroy_process_group()
 
