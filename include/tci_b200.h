@@ -14,8 +14,10 @@
  * Library objects are opaque handles with explicit destroy functions.
  * Every function returns TCI_OK (0) or a tci_status; tci_last_error(ctx) gives
  * the message (texts follow the reference's exceptions where one exists).
- * A tci_ctx is bound to one GPU and must be used by one caller at a time
- * (one process per GPU; multi-GPU sharding is done by the host layer).
+ * A tci_ctx drives one GPU or, created with ngpu > 1, several GPUs of one node from ONE process (the reference's
+ * caller is a single Julia process): device_ids[0] owns the per-bond rrLU, and the stages that shard -- Pi
+ * evaluation, the random-start global search, the row blocks of an MPO x MPO contraction -- are split over all of
+ * them inside the library (peer stores over NVLink, NCCL for the gathers).  A context is used by one caller at a time.
  */
 #ifndef TCI_B200_H
 #define TCI_B200_H
@@ -39,14 +41,20 @@ typedef enum {
     TCI_ERR_CENTRE = 5,      /* "Invalid number of central indices" tensorci2.jl:307 */
     TCI_ERR_NO_DEVICE = 6,   /* no CUDA device: the library has no CPU fallback   */
     TCI_ERR_BUSY = 7,        /* context entered concurrently                      */
-    TCI_ERR_UNSUPPORTED = 8
+    TCI_ERR_UNSUPPORTED = 8,
+    TCI_ERR_SINGULAR = 9     /* "Pivot matrix at bond b is singular!" (the `\` of tensorci2.jl:391 would throw) */
 } tci_status;
 
 int tci_version(void);
 
 /* ---- context ------------------------------------------------------------ */
-int tci_ctx_create(int device_id, tci_ctx **out);
+/* ngpu >= 1 GPUs of this node, device_ids[0] = owner (NULL: devices 0 .. ngpu-1).  ngpu > 1 needs peer access between
+ * all of them (NVLink / NVSwitch) and NCCL (libnccl.so.2, bound at run time); TCI_ERR_UNSUPPORTED otherwise.          */
+int tci_ctx_create(int ngpu, const int *device_ids, tci_ctx **out);
+/* Handles (tci_dmat, tci_lu) keep the context alive: destroying it first is allowed, its resources are released with
+ * the last handle (Julia finalizers run in arbitrary order).                                                          */
 void tci_ctx_destroy(tci_ctx *ctx);
+int tci_ctx_ngpu(tci_ctx *ctx);
 const char *tci_last_error(tci_ctx *ctx); /* ctx may be NULL: last create error */
 /* number of kernels this context launched since creation (bench gpu_launches) */
 int64_t tci_ctx_launches(tci_ctx *ctx);
@@ -56,6 +64,8 @@ void *tci_ctx_stream(tci_ctx *ctx);
  * 3 tt/mpo environments, 4 globalsearch, 5 gemm, 6 h2d, 7 d2h, 8 the rrLU kernel alone.  Stands in for the
  * time_ns() pairs around "Computing Pi"/"LU" (tensorci2.jl:530-550).              */
 int tci_timers(tci_ctx *ctx, double *out, int64_t n, int reset);
+/* kernels launched / stage times of member k of a multi-GPU context (k = 0: the owner) */
+int64_t tci_ctx_member_launches(tci_ctx *ctx, int k);
 
 /* ---- device matrices ---------------------------------------------------- */
 int tci_dmat_create(tci_ctx *ctx, int64_t m, int64_t n, const double *host /* nullable */, tci_dmat **out);
@@ -69,18 +79,12 @@ int tci_dmat_shape(tci_dmat *a, int64_t *m, int64_t *n, int64_t *ld);
 void *tci_dmat_ptr(tci_dmat *a); /* raw device pointer, for collectives on the host layer */
 int tci_dmat_fetch(tci_dmat *a, double *host /* m x n, tight */);
 int tci_dmat_destroy(tci_dmat *a);
+/* reshape(A, m2, n2) of the column-major m x n matrix (m*n == m2*n2) as a new device matrix: the backward half-sweep
+ * of sweep1site! folds the same T tensor as |I| x (d*|J|) instead of (|I|*d) x |J| (tensorci2.jl:417-428).           */
+int tci_dmat_refold(tci_dmat *a, int64_t m2, int64_t n2, tci_dmat **out);
 /* shrink the logical column count (n <= allocated columns); used after an all-gather of padded blocks */
 int tci_dmat_resize_cols(tci_dmat *a, int64_t n);
 
-/* ---- peer-shared buffers (multi-GPU: one process per GPU) -------------------------------------
- * The rrLU owner allocates the Pi buffer with tci_shared_alloc and hands the 64-byte IPC handle to the
- * other ranks (any host transport); they map it with tci_shared_open and evaluate their column block
- * with tci_pi_eval_into on a tci_dmat_wrap view, i.e. the evaluation kernel stores straight into the
- * owner's HBM over NVLink (peer st.global) -- compute and transfer are one kernel, no staging copy.  */
-int tci_shared_alloc(tci_ctx *ctx, int64_t bytes, void **dptr, char handle[64]);
-int tci_shared_open(tci_ctx *ctx, const char handle[64], void **dptr);
-int tci_shared_close(tci_ctx *ctx, void *dptr);
-int tci_shared_free(tci_ctx *ctx, void *dptr);
 /* non-owning device matrix on caller-managed memory (ld >= m, ld % 2 == 0, 16-byte aligned base) */
 int tci_dmat_wrap(tci_ctx *ctx, void *dptr, int64_t m, int64_t n, int64_t ld, tci_dmat **out);
 
@@ -167,6 +171,27 @@ int tci_luci_right(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_d
 int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
 int tci_lu_destroy(tci_lu *lu);
 
+/* ---- fused entry points of the driver's inner loop ------------------------- */
+/* The `:full` branch of updatepivots! (tensorci2.jl:529-551) in one call: Pi = f(Icombined x Jcombined) is evaluated
+ * into HBM (sharded over the context's GPUs when the cost model says it pays), factorised in place by the rrLU on the
+ * owner, and only the permutations / pivot errors / max|Pi| come back -- one host synchronisation per bond.  I, J are
+ * the already expanded index sets (kronecker + union, :526-527).  Outputs as tci_rrlu; rowindices = rowperm[0:npivot],
+ * colindices = colperm[0:npivot]; *maxabs = max|Pi| for updatemaxsample! (:538).  *factors (nullable) owns Pi.        */
+int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                    int64_t nr, int64_t nJ, int64_t maxrank, double reltol, double abstol, int leftorthogonal,
+                    int exact_mode, int64_t *rowperm, int64_t *colperm, int64_t *npivot, double *error,
+                    double *pivoterrors, double *maxabs, tci_lu **factors);
+/* fillsitetensors! (globalsearch.jl:97-103) = setsitetensor!(tci, f, b) for every site (tensorci2.jl:367-394):
+ * T_b = Pi1_b P_b^-1 with Pi1_b = f(Iset[b] x sigma_b x Jset[b]) and P_b = f(Iset[b+1] x Jset[b]); the last tensor is
+ * Pi1 itself.  All evaluations, full-rank factorisations and solves are queued back to back and synchronised once.
+ * Iset[b]: (b x nI[b]), Jset[b]: ((nsites-1-b) x nJ[b]); T_out[b] (nullable entries / nullable array) receives
+ * nI[b]*d_b*nJ[b] doubles; *maxabs = max over all |Pi1| (updatemaxsample!, :375).  *tt_id (nullable) receives the
+ * result as a device-resident tensor-train target (the current_tt of the global pivot finder); destroy it with
+ * tci_target_destroy.  Errors: "Pivot matrix at bond b is not square!" (TCI_ERR_ARG, :388), TCI_ERR_SINGULAR.       */
+int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *const *Iset,
+                         const int64_t *nI, const int64_t *const *Jset, const int64_t *nJ, double *const *T_out,
+                         double *maxabs, int64_t *tt_id);
+
 /* ---- dense FP64 GEMM on device matrices (building block of (b),(c)) ------- */
 /* C = alpha * op(A) * op(B) + beta * C ; host arrays, column-major, tight.  Exposed
  * for benchmarks and tests of the kernel that replaces OpenBLAS dgemm in
@@ -189,12 +214,25 @@ int tci_contract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s
  * points drawn by the caller's rng (n x nsearch): for every start the star of
  * sum_p d_p probes |f(x) - tt(x)|, first maximum kept, accepted if > threshold
  * (= abstol * tolmarginglobalsearch), truncated to the first maxn in start order.
- * cores: the current tensor train (host, dims3 as in tci_tt_create).
- * pivots_out: n x maxn, errs_out: maxn, start_idx_out (nullable): maxn, the 0-based start each
- * accepted pivot came from (lets the host merge the candidates of sharded searches in start order). */
-int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
-                     const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
-                     int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out, int64_t *nfound);
+ * tt_id: the current tensor train as a device-resident handle (tci_tt_create, or the one tci_fill_sitetensors
+ * returns) -- nothing is uploaded per call.  The per-start arg-max runs on the device; only nsearch (error, index)
+ * records come back.  On a multi-GPU context the starts are split into contiguous blocks over the GPUs and the records
+ * gathered by one ncclAllGather.
+ * mode: 1 = every probe through the ordered left-to-right chain (bit-identical to evaluate(tt, x),
+ * abstracttensortrain.jl:124-132); 2 = prefix / suffix environments of the start points + one GEMM per site (~n times
+ * fewer flops; values agree with mode 1 to rounding, pivots identical away from near-ties); 0 = mode 1 below 32768
+ * probes (the reference's default nsearch = 5), mode 2 above.
+ * pivots_out: n x maxn, errs_out: maxn, start_idx_out (nullable): maxn, the 0-based start each accepted pivot came from. */
+int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts, int64_t nsearch,
+                     double threshold, int64_t maxn, int mode, int64_t *pivots_out, double *errs_out,
+                     int64_t *start_idx_out, int64_t *nfound);
+/* Host-only pieces of the sharded stages, exported so that the partitioning and the selection can be tested without a
+ * GPU: the block [lo, hi) of `rank` when n items are split over `world` ranks in contiguous blocks whose starts are
+ * multiples of `align`; and the selection of :180-188 replayed on gathered (error, probe index) records.             */
+int tci_shard_range(int64_t n, int world, int rank, int64_t align, int64_t *lo, int64_t *hi);
+int tci_globalsearch_select(const double *rec_err, const int64_t *rec_idx, int64_t nsearch, const int64_t *starts,
+                            int64_t nsites, const int64_t *localdims, double threshold, int64_t maxn,
+                            int64_t *pivots_out, double *errs_out, int64_t *start_idx_out, int64_t *nfound);
 /* evaluate(tt, x) for `count` points, left-to-right (abstracttensortrain.jl:124-132) */
 int tci_tt_evaluate(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
                     const int64_t *idx, int64_t count, double *out);

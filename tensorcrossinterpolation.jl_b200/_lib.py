@@ -22,8 +22,10 @@ PP_f64 = C.POINTER(P_f64)
 SYMBOLS = {
     # name: (restype, argtypes)
     "tci_version": (C.c_int, []),
-    "tci_ctx_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
+    "tci_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(VP)]),
     "tci_ctx_destroy": (None, [VP]),
+    "tci_ctx_ngpu": (C.c_int, [VP]),
+    "tci_ctx_member_launches": (i64, [VP, C.c_int]),
     "tci_last_error": (C.c_char_p, [VP]),
     "tci_ctx_launches": (i64, [VP]),
     "tci_ctx_stream": (VP, [VP]),
@@ -35,11 +37,8 @@ SYMBOLS = {
     "tci_dmat_fetch": (C.c_int, [VP, P_f64]),
     "tci_dmat_destroy": (C.c_int, [VP]),
     "tci_dmat_resize_cols": (C.c_int, [VP, i64]),
+    "tci_dmat_refold": (C.c_int, [VP, i64, i64, C.POINTER(VP)]),
     "tci_dmat_wrap": (C.c_int, [VP, VP, i64, i64, i64, C.POINTER(VP)]),
-    "tci_shared_alloc": (C.c_int, [VP, i64, C.POINTER(VP), C.c_char_p]),
-    "tci_shared_open": (C.c_int, [VP, C.c_char_p, C.POINTER(VP)]),
-    "tci_shared_close": (C.c_int, [VP, VP]),
-    "tci_shared_free": (C.c_int, [VP, VP]),
     "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
@@ -62,11 +61,18 @@ SYMBOLS = {
     "tci_contract_zipup_site": (C.c_int, [VP, P_f64, i64, i64, i64, P_f64, i64, i64, i64, P_f64, i64, i64, P_f64,
                                           C.POINTER(VP)]),
     "tci_contract_naive_site": (C.c_int, [VP, P_f64, i64, i64, i64, i64, P_f64, i64, i64, i64, P_f64]),
-    "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, PP_f64, P_i64, i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),
+    "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, i64, f64, i64, C.c_int, P_i64, P_f64, P_i64, P_i64]),
+    "tci_shard_range": (C.c_int, [i64, C.c_int, C.c_int, i64, P_i64, P_i64]),
+    "tci_globalsearch_select": (C.c_int, [P_f64, P_i64, i64, P_i64, i64, P_i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),
+    "tci_bond_update": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64,
+                                  P_i64, P_i64, P_f64, P_f64, P_f64, C.POINTER(VP)]),
+    "tci_fill_sitetensors": (C.c_int, [VP, i64, i64, C.POINTER(P_i64), P_i64, C.POINTER(P_i64), P_i64, PP_f64, P_f64,
+                                       P_i64]),
     "tci_tt_evaluate": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, i64, P_f64]),
 }
 
 TCI_OK, TCI_ERR_CUDA, TCI_ERR_ARG, TCI_ERR_NAN_L, TCI_ERR_NAN_U, TCI_ERR_CENTRE, TCI_ERR_NO_DEVICE = range(7)
+TCI_ERR_BUSY, TCI_ERR_UNSUPPORTED, TCI_ERR_SINGULAR = 7, 8, 9
 
 _lib = None
 
@@ -110,14 +116,25 @@ def core_ptrs(cores):
 
 
 class Context:
-    """tci_ctx: one GPU, one caller at a time."""
+    """tci_ctx: one GPU, or several GPUs of one node driven from this process (devices[0] owns the per-bond rrLU,
+    the stages that shard are split over all of them inside the library); one caller at a time."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.h = VP()
-        rc = lib().tci_ctx_create(int(device), C.byref(self.h))
+        devs = [int(device)] if devices is None else [int(d) for d in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        rc = lib().tci_ctx_create(len(devs), arr, C.byref(self.h))
         if rc != 0:
             raise TCIError(rc, lib().tci_last_error(None).decode())
-        self.device = int(device)
+        self.devices = devs
+        self.device = devs[0]
+
+    @property
+    def ngpu(self):
+        return int(lib().tci_ctx_ngpu(self.h))
+
+    def member_launches(self, k):
+        return int(lib().tci_ctx_member_launches(self.h, int(k)))
 
     def check(self, rc):
         if rc != 0:
@@ -157,10 +174,29 @@ _default = None
 
 
 def default_context():
+    """TCI_B200_DEVICES="0,1,2,3" makes the default context a multi-GPU one; otherwise LOCAL_RANK's GPU (or GPU 0)."""
     global _default
     if _default is None:
-        _default = Context(int(os.environ.get("LOCAL_RANK", "0")))
+        devs = os.environ.get("TCI_B200_DEVICES")
+        if devs:
+            _default = Context(devices=[int(x) for x in devs.split(",")])
+        else:
+            _default = Context(int(os.environ.get("LOCAL_RANK", "0")))
     return _default
+
+
+def set_default_context(ctx):
+    global _default
+    _default = ctx
+
+
+def shard_range(n, world, rank, align=1):
+    """tci_shard_range: the contiguous block of `rank` (host-only, no GPU needed)."""
+    lo, hi = i64(0), i64(0)
+    rc = lib().tci_shard_range(int(n), int(world), int(rank), int(align), C.byref(lo), C.byref(hi))
+    if rc != 0:
+        raise ValueError("tci_shard_range: bad arguments")
+    return lo.value, hi.value
 
 
 def gemm(A, B, ctx=None):
@@ -247,6 +283,12 @@ class DeviceMatrix:
         if m * n:
             self.ctx.check(lib().tci_dmat_fetch(self.h, pf(out)))
         return out
+
+    def refold(self, m2, n2):
+        """reshape(A, m2, n2) on the device (tci_dmat_refold)."""
+        h = VP()
+        self.ctx.check(lib().tci_dmat_refold(self.h, int(m2), int(n2), C.byref(h)))
+        return DeviceMatrix(self.ctx, h)
 
     def resize_cols(self, n):
         self.ctx.check(lib().tci_dmat_resize_cols(self.h, int(n)))

@@ -104,11 +104,68 @@ class BatchEvaluator:
         self.nevals += int(nI) * int(nJ)
         return mx.value
 
+    # ---- fused entry points of the driver's inner loop (tci_bond_update / tci_fill_sitetensors) ----
+    def bond_update(self, Icombined, Jcombined, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True,
+                    want_factors=False, exact=True):
+        """The `:full` branch of updatepivots! (tensorci2.jl:529-551) in one library call: Pi evaluation (sharded over
+        the context's GPUs when that pays) -> rrLU on the owner, one host synchronisation.  Returns
+        (rrLU object without factors unless want_factors, max|Pi|)."""
+        from .matrixlu import rrLU
+        I, J = as_indexset(Icombined), as_indexset(Jcombined)
+        m, n = len(I), len(J)
+        if m == 0 or n == 0:
+            raise ValueError("rows must not be empty")  # matrixlu.jl:10
+        if I.shape[1] + J.shape[1] != len(self.localdims):
+            raise RuntimeError("Invalid number of central indices")
+        rowperm = np.zeros(m, dtype=np.int64)
+        colperm = np.zeros(n, dtype=np.int64)
+        npiv, err, mx = C.c_int64(0), C.c_double(0.0), C.c_double(0.0)
+        pe = np.zeros(min(m, n) + 1, dtype=np.float64)
+        h = C.c_void_p()
+        mr = 0 if maxrank is None else int(min(maxrank, 2**62))
+        self.ctx.check(lib().tci_bond_update(self.ctx.h, self.id, pi(I), I.shape[1], m, pi(J), J.shape[1], n, mr,
+                                             float(reltol), float(abstol), int(bool(leftorthogonal)), int(bool(exact)),
+                                             pi(rowperm), pi(colperm), C.byref(npiv), C.byref(err), pf(pe), C.byref(mx),
+                                             C.byref(h) if want_factors else None))
+        self.nevals += m * n
+        r = npiv.value
+        return rrLU(self.ctx, h if want_factors else None, rowperm, colperm, r, err.value, pe[: r + 1].copy(),
+                    bool(leftorthogonal), (m, n)), mx.value
+
+    def fill_sitetensors(self, Isets, Jsets, want_handle=True):
+        """fillsitetensors! (globalsearch.jl:97-103) for all sites in one library call (tci_fill_sitetensors).
+        Returns (list of T_b as (nI_b, d_b, nJ_b) arrays, max over |Pi1|, device-resident TT handle or None)."""
+        n = len(self.localdims)
+        Is = [as_indexset(s, b) for b, s in enumerate(Isets)]
+        Js = [as_indexset(s, n - 1 - b) for b, s in enumerate(Jsets)]
+        nI = np.array([len(s) for s in Is], dtype=np.int64)
+        nJ = np.array([len(s) for s in Js], dtype=np.int64)
+        Ts = [np.zeros((int(nI[b]), self.localdims[b], int(nJ[b])), dtype=np.float64, order="F") for b in range(n)]
+        Ip = (_lib.P_i64 * n)(*[pi(s) for s in Is])
+        Jp = (_lib.P_i64 * n)(*[pi(s) for s in Js])
+        Tp = (_lib.P_f64 * n)(*[pf(t) for t in Ts])
+        mx = C.c_double(0.0)
+        tid = C.c_int64(0)
+        rc = lib().tci_fill_sitetensors(self.ctx.h, self.id, n, Ip, pi(nI), Jp, pi(nJ), Tp, C.byref(mx),
+                                        C.byref(tid) if want_handle else None)
+        if rc == _lib.TCI_ERR_ARG or rc == _lib.TCI_ERR_SINGULAR:
+            raise RuntimeError(lib().tci_last_error(self.ctx.h).decode())
+        self.ctx.check(rc)
+        self.nevals += int(sum(nI[b] * self.localdims[b] * nJ[b] for b in range(n)) + sum(nJ[b] ** 2 for b in range(n - 1)))
+        handle = DeviceTT(self.ctx, tid.value, self.localdims) if want_handle else None
+        return Ts, mx.value, handle
+
     def __del__(self):
         try:
             lib().tci_target_destroy(self.ctx.h, self.id)
         except Exception:
             pass
+
+
+class DeviceTT(BatchEvaluator):
+    """A tensor train whose cores live on the device (tci_fill_sitetensors' `tt_id`): the `current_tt` the global
+    pivot finder probes (globalpivotfinder.jl:160-183) without any upload; also a TT target like TTCache."""
+    has_environments = True
 
 
 def apply_projector(res, centre_sitedims, projector):

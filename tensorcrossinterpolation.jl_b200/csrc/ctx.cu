@@ -16,7 +16,7 @@ int tci_fail(tci_ctx *ctx, int code, const std::string &msg)
 
 extern "C" int tci_version(void) { return 100; }
 
-extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
+int ctx_create_one(int device_id, tci_ctx **out)
 {
     if (!out) return TCI_ERR_ARG;
     *out = nullptr;
@@ -39,7 +39,8 @@ extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
+        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
+        cudaEventCreate(&c->ev4) != cudaSuccess || cudaEventCreate(&c->ev5) != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
         delete c;
         return tci_fail(nullptr, TCI_ERR_CUDA, "context setup failed: " + m);
@@ -53,8 +54,51 @@ extern "C" int tci_ctx_create(int device_id, tci_ctx **out)
     return TCI_OK;
 }
 
-static void target_free(TargetDev &t)
+int group_create_local(const std::vector<tci_ctx *> &members, tci_group **out); // group.cu
+
+// tci_ctx_create(ngpu, device_ids): ONE process drives ngpu GPUs (the reference's caller is a single Julia process,
+// tensorci2.jl:805-809).  device_ids[0] owns the per-bond rrLU; the stages that shard are split over all
+// of them inside the library.  device_ids == NULL means 0 .. ngpu-1.
+extern "C" int tci_ctx_create(int ngpu, const int *device_ids, tci_ctx **out)
 {
+    if (!out) return TCI_ERR_ARG;
+    *out = nullptr;
+    if (ngpu < 1) return tci_fail(nullptr, TCI_ERR_ARG, "tci_ctx_create: ngpu must be >= 1");
+    std::vector<tci_ctx *> members;
+    for (int k = 0; k < ngpu; ++k) {
+        const int dev = device_ids ? device_ids[k] : k;
+        for (tci_ctx *m : members)
+            if (m->device == dev) {
+                for (tci_ctx *q : members) tci_ctx_destroy(q);
+                return tci_fail(nullptr, TCI_ERR_ARG, "tci_ctx_create: device ids must be distinct");
+            }
+        tci_ctx *c = nullptr;
+        int rc = ctx_create_one(dev, &c);
+        if (rc) {
+            for (tci_ctx *q : members) tci_ctx_destroy(q);
+            return rc;
+        }
+        members.push_back(c);
+    }
+    if (ngpu > 1) {
+        tci_group *g = nullptr;
+        int rc = group_create_local(members, &g);
+        if (rc) {
+            for (tci_ctx *q : members) tci_ctx_destroy(q);
+            return rc;
+        }
+    }
+    cudaSetDevice(members[0]->device);
+    *out = members[0];
+    return TCI_OK;
+}
+
+void target_free(tci_ctx *ctx, TargetDev &t)
+{
+    if (t.pooled) {
+        for (double *p : t.cores) dev_free(ctx, p);
+        return;
+    }
     cudaFree(t.d_params);
     cudaFree(t.d_localdims);
     for (double *p : t.cores) cudaFree(p);
@@ -62,25 +106,67 @@ static void target_free(TargetDev &t)
     for (double *p : t.B) cudaFree(p);
 }
 
-extern "C" void tci_ctx_destroy(tci_ctx *ctx)
+// frees a context that has been destroyed by its owner once the last dmat / lu handle that points at it is gone
+// (Julia finalizers run in arbitrary order; Python drops a Context before the matrices that were created on it)
+void ctx_release(tci_ctx *ctx)
 {
-    if (!ctx) return;
+    if (!ctx || !ctx->destroyed || ctx->live_handles > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &kv : ctx->targets) target_free(*kv.second);
+    for (auto &kv : ctx->targets) target_free(ctx, *kv.second);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2);
     cudaEventDestroy(ctx->ev3);
+    cudaEventDestroy(ctx->ev4);
+    cudaEventDestroy(ctx->ev5);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
+}
+
+extern "C" void tci_ctx_destroy(tci_ctx *ctx)
+{
+    if (!ctx || ctx->destroyed) return;
+    if (ctx->grp) {
+        tci_group *g = ctx->grp;
+        ctx->grp = nullptr;
+        if (ctx->member == 0) group_destroy(g);
+    }
+    ctx->destroyed = true;
+    ctx_release(ctx);
+}
+
+// small device-to-host results go through page-locked staging (the copies are latency, not bandwidth)
+void *ctx_pinned(tci_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->pinned_cap) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        size_t cap = std::max(bytes, std::max((size_t)1 << 16, 2 * ctx->pinned_cap));
+        if (cudaMallocHost(&ctx->pinned, cap) != cudaSuccess) {
+            ctx->pinned_cap = 0;
+            return nullptr;
+        }
+        ctx->pinned_cap = cap;
+    }
+    return ctx->pinned;
 }
 
 extern "C" const char *tci_last_error(tci_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int64_t tci_ctx_launches(tci_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int tci_ctx_ngpu(tci_ctx *ctx) { return ctx ? ctx_world(ctx) : 0; }
+
+extern "C" int64_t tci_ctx_member_launches(tci_ctx *ctx, int k)
+{
+    if (!ctx) return 0;
+    if (k == 0 || !ctx->grp) return k == 0 ? ctx->launches : 0;
+    return k > 0 && k < ctx->grp->nlocal ? ctx->grp->m[k]->launches : 0;
+}
 
 extern "C" void *tci_ctx_stream(tci_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
@@ -108,6 +194,7 @@ int dmat_alloc(tci_ctx *ctx, i64 m, i64 n, tci_dmat **out)
         delete a;
         return tci_fail(ctx, TCI_ERR_CUDA, std::string("cudaMallocAsync dmat: ") + cudaGetErrorString(e));
     }
+    ctx->live_handles++;
     *out = a;
     return TCI_OK;
 }
@@ -199,51 +286,43 @@ extern "C" int tci_dmat_wrap(tci_ctx *ctx, void *dptr, int64_t m, int64_t n, int
     a->ncap = n;
     a->ld = ld;
     a->owned = false;
+    ctx->live_handles++;
     *out = a;
     return TCI_OK;
 }
 
-extern "C" int tci_shared_alloc(tci_ctx *ctx, int64_t bytes, void **dptr, char handle[64])
+// the same column-major data under another fold (m * n == m2 * n2): reshape(A, m2, n2) of a Julia array
+__global__ void k_refold(const double *__restrict__ src, i64 lds, i64 m, i64 total, double *__restrict__ dst, i64 ldd,
+                         i64 m2)
 {
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x)
+        dst[(e % m2) + ldd * (e / m2)] = src[(e % m) + lds * (e / m)];
+}
+
+extern "C" int tci_dmat_refold(tci_dmat *a, int64_t m2, int64_t n2, tci_dmat **out)
+{
+    if (!a || !out) return TCI_ERR_ARG;
+    tci_ctx *ctx = a->ctx;
     TCI_ENTER(ctx);
-    if (!dptr || !handle || bytes <= 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_shared_alloc: bad arguments");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    TCI_CUDA(ctx, cudaMalloc(dptr, (size_t)bytes)); // pool (async) allocations cannot be exported
-    cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
-    if (e != cudaSuccess) {
-        cudaFree(*dptr);
-        *dptr = nullptr;
-        return tci_fail(ctx, TCI_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    *out = nullptr;
+    if (m2 < 0 || n2 < 0 || m2 * n2 != a->m * a->n)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_dmat_refold: DimensionMismatch: new dimensions must be consistent with array size");
+    dmat_wait_ready(ctx, a);
+    tci_dmat *r = nullptr;
+    int rc = dmat_alloc(ctx, m2, n2, &r);
+    if (rc) return rc;
+    const i64 total = m2 * n2;
+    if (total > 0) {
+        k_refold<<<(unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            a->p, a->ld, a->m, total, r->p, r->ld, m2);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            tci_dmat_destroy(r);
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("tci_dmat_refold: ") + cudaGetErrorString(e));
+        }
     }
-    memcpy(handle, &h, 64);
-    return TCI_OK;
-}
-
-extern "C" int tci_shared_open(tci_ctx *ctx, const char handle[64], void **dptr)
-{
-    TCI_ENTER(ctx);
-    if (!dptr || !handle) return tci_fail(ctx, TCI_ERR_ARG, "tci_shared_open: bad arguments");
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, 64);
-    TCI_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return TCI_OK;
-}
-
-extern "C" int tci_shared_close(tci_ctx *ctx, void *dptr)
-{
-    TCI_ENTER(ctx);
-    if (dptr) TCI_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
-    return TCI_OK;
-}
-
-extern "C" int tci_shared_free(tci_ctx *ctx, void *dptr)
-{
-    TCI_ENTER(ctx);
-    if (dptr) {
-        cudaStreamSynchronize(ctx->stream);
-        TCI_CUDA(ctx, cudaFree(dptr));
-    }
+    *out = r;
     return TCI_OK;
 }
 
@@ -266,10 +345,13 @@ extern "C" int tci_dmat_fetch(tci_dmat *a, double *host)
 extern "C" int tci_dmat_destroy(tci_dmat *a)
 {
     if (!a) return TCI_OK;
-    cudaSetDevice(a->ctx->device);
-    dmat_wait_ready(a->ctx, a);
-    if (a->owned) dev_free(a->ctx, a->p);
+    tci_ctx *ctx = a->ctx;
+    cudaSetDevice(ctx->device);
+    dmat_wait_ready(ctx, a);
+    if (a->owned) dev_free(ctx, a->p);
     delete a;
+    ctx->live_handles--;
+    ctx_release(ctx); // no-op unless the context was destroyed before its handles
     return TCI_OK;
 }
 
@@ -308,6 +390,7 @@ extern "C" int tci_target_builtin(tci_ctx *ctx, int kind_id, const double *param
     }
     if ((kind_id == TCI_TARGET_QUANTICS2D || kind_id == TCI_TARGET_QUANTICS1D) && p.size() < 2)
         return tci_fail(ctx, TCI_ERR_ARG, "quantics: parameters are [layout|R, R|fid]");
+    t->nparams_alloc = (i64)p.size();
     TCI_CUDA(ctx, cudaMalloc(&t->d_params, p.size() * sizeof(double)));
     TCI_CUDA(ctx, cudaMemcpy(t->d_params, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice));
     TCI_CUDA(ctx, cudaMalloc(&t->d_localdims, nsites * sizeof(i64)));
@@ -321,7 +404,7 @@ extern "C" int tci_target_builtin(tci_ctx *ctx, int kind_id, const double *param
     i64 id = ctx->next_target++;
     ctx->targets[id] = std::move(t);
     *target_id = id;
-    return TCI_OK;
+    return target_replicate(ctx, id);
 }
 
 extern "C" int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
@@ -349,7 +432,7 @@ extern "C" int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3,
     i64 id = ctx->next_target++;
     ctx->targets[id] = std::move(t);
     *target_id = id;
-    return TCI_OK;
+    return target_replicate(ctx, id);
 }
 
 extern "C" int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,
@@ -387,7 +470,7 @@ extern "C" int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *
     i64 id = ctx->next_target++;
     ctx->targets[id] = std::move(t);
     *target_id = id;
-    return TCI_OK;
+    return target_replicate(ctx, id);
 }
 
 extern "C" int tci_target_destroy(tci_ctx *ctx, int64_t target_id)
@@ -395,7 +478,79 @@ extern "C" int tci_target_destroy(tci_ctx *ctx, int64_t target_id)
     TCI_ENTER(ctx);
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
-    target_free(*it->second);
+    target_free(ctx, *it->second);
     ctx->targets.erase(it);
+    if (ctx->grp)
+        for (int k = 1; k < ctx->grp->nlocal; ++k) {
+            tci_ctx *c = ctx->grp->m[k];
+            auto jt = c->targets.find(target_id);
+            if (jt == c->targets.end()) continue;
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            target_free(c, *jt->second);
+            c->targets.erase(jt);
+        }
+    cudaSetDevice(ctx->device);
+    return TCI_OK;
+}
+
+static cudaError_t peer_dup(double **dst, int dst_dev, const double *src, int src_dev, size_t count)
+{
+    cudaError_t e = cudaMalloc(dst, (count ? count : 1) * sizeof(double));
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemcpyPeer(*dst, dst_dev, src, src_dev, count * sizeof(double));
+}
+
+int target_replicate(tci_ctx *ctx, i64 id)
+{
+    tci_group *g = ctx->grp;
+    if (!g || g->nlocal == 1) return TCI_OK;
+    const TargetDev &src = *ctx->targets.at(id);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 1; k < g->nlocal; ++k) {
+        tci_ctx *c = g->m[k];
+        cudaSetDevice(c->device);
+        std::unique_ptr<TargetDev> t(new TargetDev(src)); // sizes, dims, elementwise function; pointers re-made below
+        t->pooled = false;
+        t->d_params = nullptr;
+        t->d_localdims = nullptr;
+        std::fill(t->cores.begin(), t->cores.end(), nullptr);
+        std::fill(t->A.begin(), t->A.end(), nullptr);
+        std::fill(t->B.begin(), t->B.end(), nullptr);
+        cudaError_t e = cudaSuccess;
+        if (src.kind == 0) {
+            e = peer_dup(&t->d_params, c->device, src.d_params, ctx->device, (size_t)src.nparams_alloc);
+            if (e == cudaSuccess) {
+                double *ld = nullptr;
+                static_assert(sizeof(i64) == sizeof(double), "localdims are copied as 8-byte words");
+                e = peer_dup(&ld, c->device, reinterpret_cast<const double *>(src.d_localdims), ctx->device,
+                             (size_t)src.nsites);
+                t->d_localdims = reinterpret_cast<i64 *>(ld);
+            }
+            t->an.params = t->d_params;
+            t->an.localdims = t->d_localdims;
+        } else if (src.kind == 1) {
+            for (i64 s = 0; s < src.nsites && e == cudaSuccess; ++s)
+                e = peer_dup(&t->cores[s], c->device, src.cores[s], ctx->device,
+                             (size_t)(src.dl[s] * src.d[s] * src.dr[s]));
+        } else {
+            for (i64 s = 0; s < src.nsites && e == cudaSuccess; ++s) {
+                e = peer_dup(&t->A[s], c->device, src.A[s], ctx->device,
+                             (size_t)(src.adl[s] * src.as1[s] * src.as2[s] * src.adr[s]));
+                if (e == cudaSuccess)
+                    e = peer_dup(&t->B[s], c->device, src.B[s], ctx->device,
+                                 (size_t)(src.bdl[s] * src.bs1[s] * src.bs2[s] * src.bdr[s]));
+            }
+        }
+        if (e != cudaSuccess) {
+            target_free(c, *t);
+            cudaSetDevice(ctx->device);
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("replicating the target on GPU ") +
+                                                   std::to_string(c->device) + ": " + cudaGetErrorString(e));
+        }
+        c->targets[id] = std::move(t);
+        if (c->next_target <= id) c->next_target = id + 1;
+    }
+    cudaSetDevice(ctx->device);
     return TCI_OK;
 }

@@ -371,11 +371,7 @@ static int launch_async_one(tci_ctx *ctx, dim3 grid, i64 M, i64 N, i64 K, double
     constexpr int A_SZ = (TA ? MK + 4 : BM + 4) * (TA ? BM : MK), B_SZ = (TB ? BN + 4 : MK + 4) * (TB ? MK : BN);
     constexpr size_t smem = (size_t)ASTAGES * (A_SZ + B_SZ) * sizeof(double);
     auto fn = k_dgemm_mma_async<BM, BN, NWM, NWN, TA, TB>;
-    static bool configured = false;
-    if (!configured) {
-        TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    TCI_CUDA(ctx, ctx_func_smem(ctx, (const void *)fn, (int)smem));
     fn<<<grid, 32 * NWM * NWN, smem, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
     ctx->launches++;
     return TCI_OK;

@@ -225,6 +225,58 @@ extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
 // B * A^-1 for the square, fully factorised A = lu (the `\` of setsitetensor!, tensorci2.jl:391, which the
 // reference leaves to LAPACK gesv; here the full-pivot factors of K2 are reused):
 //   A[rowperm, colperm] = L U  =>  X[:, rowperm] = B[:, colperm] U^-1 L^-1
+// enqueue only: X (rows x k, ldx) = B (rows x k, ldb) * A^-1 with the factors of `lu` (assumed of full rank k)
+int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i64 ldx)
+{
+    tci_ctx *ctx = lu->ctx;
+    const i64 k = lu->r;
+    int rc = 0;
+    DevBuf<double> L(ctx), U(ctx), W(ctx);
+    TCI_CUDA(ctx, L.alloc((size_t)(k * k)));
+    TCI_CUDA(ctx, U.alloc((size_t)(k * k)));
+    TCI_CUDA(ctx, W.alloc((size_t)(rows * k)));
+    rc = lu_extract(lu, L.p, k, U.p, k);
+    const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
+    if (!rc) {
+        k_gather_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(B, ldb, rows, k, lu->d_colperm, W.p,
+                                                                               rows);
+        ctx->launches++;
+    }
+    for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) { // Y U = W, left to right
+        const i64 nb = std::min<i64>(TB_NB, k - j0);
+        if (j0 > 0)
+            rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W.p, rows, U.p + k * j0, k, 1.0, W.p + rows * j0,
+                           rows);
+        if (lu->leftorthogonal)
+            k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, U.p + j0 + k * j0,
+                                                                      k, (int)nb);
+        else
+            k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, U.p + j0 + k * j0,
+                                                                     k, (int)nb);
+        ctx->launches++;
+    }
+    for (i64 j1 = k; j1 > 0 && !rc; j1 -= TB_NB) { // X' L = Y, right to left
+        const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
+        if (j1 < k)
+            rc = dgemm_dev(ctx, false, false, rows, nb, k - j1, -1.0, W.p + rows * j1, rows, L.p + j1 + k * j0, k, 1.0,
+                           W.p + rows * j0, rows);
+        if (lu->leftorthogonal)
+            k_trsm_rl_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, L.p + j0 + k * j0,
+                                                                     k, (int)nb);
+        else
+            k_trsm_rl_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, L.p + j0 + k * j0,
+                                                                      k, (int)nb);
+        ctx->launches++;
+    }
+    if (!rc) {
+        k_scatter_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(W.p, rows, rows, k, lu->d_rowperm, X,
+                                                                                ldx, 0);
+        ctx->launches++;
+    }
+    if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "lu_rdiv launch failed");
+    return rc;
+}
+
 extern "C" int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host, tci_dmat **out_dev)
 {
     if (!lu || !B) return TCI_ERR_ARG;
@@ -242,49 +294,7 @@ extern "C" int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host, tci_dmat *
     if (rows == 0 || k == 0) return finish(ctx, res, out_host, out_dev);
     {
         StageTimer tm(ctx, ST_LUCI);
-        DevBuf<double> L(ctx), U(ctx), W(ctx);
-        TCI_CUDA(ctx, L.alloc((size_t)(k * k)));
-        TCI_CUDA(ctx, U.alloc((size_t)(k * k)));
-        TCI_CUDA(ctx, W.alloc((size_t)(rows * k)));
-        rc = lu_extract(lu, L.p, k, U.p, k);
-        const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
-        if (!rc) {
-            k_gather_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(B->p, B->ld, rows, k, lu->d_colperm,
-                                                                                   W.p, rows);
-            ctx->launches++;
-        }
-        for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) { // Y U = W, left to right
-            const i64 nb = std::min<i64>(TB_NB, k - j0);
-            if (j0 > 0)
-                rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W.p, rows, U.p + k * j0, k, 1.0, W.p + rows * j0,
-                               rows);
-            if (lu->leftorthogonal)
-                k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
-                                                                          U.p + j0 + k * j0, k, (int)nb);
-            else
-                k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
-                                                                         U.p + j0 + k * j0, k, (int)nb);
-            ctx->launches++;
-        }
-        for (i64 j1 = k; j1 > 0 && !rc; j1 -= TB_NB) { // X' L = Y, right to left
-            const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
-            if (j1 < k)
-                rc = dgemm_dev(ctx, false, false, rows, nb, k - j1, -1.0, W.p + rows * j1, rows, L.p + j1 + k * j0, k,
-                               1.0, W.p + rows * j0, rows);
-            if (lu->leftorthogonal)
-                k_trsm_rl_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
-                                                                         L.p + j0 + k * j0, k, (int)nb);
-            else
-                k_trsm_rl_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows,
-                                                                          L.p + j0 + k * j0, k, (int)nb);
-            ctx->launches++;
-        }
-        if (!rc) {
-            k_scatter_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(W.p, rows, rows, k, lu->d_rowperm,
-                                                                                    res->p, res->ld, 0);
-            ctx->launches++;
-        }
-        if (!rc && cudaGetLastError() != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, "lu_rdiv launch failed");
+        rc = lu_rdiv_enqueue(lu, B->p, B->ld, rows, res->p, res->ld);
     }
     if (rc) {
         tci_dmat_destroy(res);

@@ -7,6 +7,8 @@
 // the 8 B/evaluation HBM write for cheap targets: every thread owns two
 // consecutive rows (one 16 B store) and walks a tile of columns, so a warp writes
 // 512 contiguous bytes per column.
+#include <cstring>
+
 #include "tci_internal.h"
 
 #define PI_THREADS 256
@@ -281,6 +283,14 @@ extern "C" int tci_target_set_elementwise(tci_ctx *ctx, int64_t target_id, int k
     t.fkind = kind;
     t.fa = a;
     t.fb = b;
+    if (ctx->grp)
+        for (int k = 1; k < ctx->grp->nlocal; ++k) {
+            auto jt = ctx->grp->m[k]->targets.find(target_id);
+            if (jt == ctx->grp->m[k]->targets.end()) continue;
+            jt->second->fkind = kind;
+            jt->second->fa = a;
+            jt->second->fb = b;
+        }
     return TCI_OK;
 }
 
@@ -307,6 +317,225 @@ int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned lon
     return TCI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Enqueue / finish split.  pi_enqueue uploads the index sets and launches the evaluation on ctx->stream WITHOUT
+// synchronising, so that a consumer (the rrLU of tci_bond_update, the solves of tci_fill_sitetensors) can be
+// queued right behind it; max|.| is accumulated into *d_maxbits (device word, zeroed by the caller; nullable).
+int pi_enqueue(tci_ctx *ctx, TargetDev &t, const i64 *I, i64 nl, i64 nI, const i64 *J, i64 nr, i64 nJ, i64 M,
+               tci_dmat *out, unsigned long long *d_maxbits)
+{
+    DevBuf<i64> idx(ctx); // released in stream order after the kernels that read it
+    TCI_CUDA(ctx, idx.alloc(2 + (size_t)(nl * nI) + (size_t)(nr * nJ)));
+    i64 *dI = idx.p + 2, *dJ = idx.p + 2 + nl * nI;
+    unsigned long long *dmax = d_maxbits ? d_maxbits : reinterpret_cast<unsigned long long *>(idx.p);
+    if (!d_maxbits) TCI_CUDA(ctx, cudaMemsetAsync(idx.p, 0, 16, ctx->stream));
+    if (nl * nI > 0)
+        TCI_CUDA(ctx, cudaMemcpyAsync(dI, I, (size_t)(nl * nI) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    if (nr * nJ > 0)
+        TCI_CUDA(ctx, cudaMemcpyAsync(dJ, J, (size_t)(nr * nJ) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->nosync) cudaEventRecord(ctx->ev0, ctx->stream); // index upload is accounted as H2D, the kernels as Pi
+    int rc = 0;
+    switch (t.kind) {
+    case 0: rc = pi_eval_analytic(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, dmax); break;
+    case 1:
+        rc = pi_eval_tt(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out);
+        if (!rc && d_maxbits) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax);
+        break;
+    default:
+        rc = pi_eval_mpo(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, I, J);
+        if (!rc) rc = apply_elementwise(ctx, t, out->p, out->m, out->n, out->ld);
+        if (!rc && d_maxbits) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax);
+        break;
+    }
+    return rc;
+}
+
+unsigned long long *ctx_words(tci_ctx *ctx); // 64 persistent device words per context (below)
+
+// ---- multi-GPU sharding of one evaluation -----------------------------------------------------
+// Cost model.  Pi has to end up in the HBM of the rrLU owner, so every element evaluated elsewhere crosses NVLink
+// once (peer stores from the evaluation kernel): ~8 B / 750 GB/s = 10.7 ps per remote element into ONE GPU.  With n
+// shards the stage takes max(t_eval / n, 10.7 ps * (n-1)/n) per element + a fixed cost (worker wake-up, one NCCL
+// all-reduce); the number of shards is the n <= world that minimises it, and 1 (no sharding) unless it wins by 10 %.
+static double analytic_ps_per_eval(const TargetDev &t)
+{
+    switch (t.an.kind) {
+    case TCI_TARGET_SEPCOS: return 1.5 + 3.6 * (double)(t.an.nstate - 1);
+    case TCI_TARGET_QUANTICS2D: return 12.0;
+    case TCI_TARGET_QUANTICS1D: return 6.0;
+    case TCI_TARGET_GKCOSEXP: return 10.0;
+    default: return 1.3; // HBM-write bound (8 B at ~6.2 TB/s)
+    }
+}
+static int choose_shards(tci_ctx *ctx, const TargetDev &t, i64 nl, i64 nI, i64 nr, i64 nJ, i64 M, i64 C)
+{
+    const int world = ctx_world(ctx);
+    if (world == 1) return 1;
+    if (const char *f = getenv("TCI_SHARD_FORCE")) return std::max(1, std::min(world, atoi(f)));
+    const double elems = (double)nI * (double)C * (double)nJ;
+    const double fixed_ps = 60e6; // ~60 us
+    if (t.kind == 0) {
+        const double te = analytic_ps_per_eval(t);
+        double best = te * elems;
+        int bestn = 1;
+        for (int n = 2; n <= world; ++n) {
+            if (nJ < 2 * (i64)n) break;
+            const double tn = std::max(te / n, 10.7 * (n - 1) / n) * elems + fixed_ps;
+            if (tn < 0.9 * best && tn < (bestn == 1 ? 0.9 * te * elems : best)) {
+                best = tn;
+                bestn = n;
+            }
+        }
+        return bestn;
+    }
+    if (M != 0) return 1; // T tensors (M = 1) are small; the row-block form below needs contiguous rows
+    // TT / MPO pair: nearly all the flops sit in the two environment chains, which shard by rows / columns
+    double D2 = 0.0;
+    const i64 n = t.nsites;
+    for (i64 s = 0; s < n; ++s) {
+        if (s >= nl && s < n - nr) continue;
+        const double cnt = s < nl ? (double)nI : (double)nJ;
+        D2 += cnt * (t.kind == 1 ? 2.0 * t.dl[s] * t.dr[s]
+                                 : 2.0 * t.adl[s] * t.bdl[s] * t.as2[s] * t.adr[s] + 2.0 * t.bdl[s] * t.as2[s] * t.adr[s] * t.bdr[s]);
+    }
+    const double ps = D2 / 20.0; // ~20 TFLOP/s = 20 flop per ps
+    if (ps < 4.0 * fixed_ps || nI < 2 * (i64)world || nJ < 2 * (i64)world) return 1;
+    return world;
+}
+
+// sharded M = 0 evaluation of an analytic target: column blocks, every member's kernel stores straight into the
+// owner's HBM (peer st.global over NVLink: compute and transfer are one kernel); one NCCL all-reduce(max) of the
+// max|.| bits follows on every member's stream and orders the owner's consumer behind all the peer stores.
+static int pi_enqueue_sharded_analytic(tci_ctx *ctx, i64 target_id, int nshard, const i64 *I, i64 nl, i64 nI,
+                                       const i64 *J, i64 nr, i64 nJ, i64 M, double *dst, i64 ld, i64 rows,
+                                       unsigned long long *d_maxbits)
+{
+    tci_group *g = ctx->grp;
+    const i64 blk = (nJ + nshard - 1) / nshard;
+    group_follow_owner(g); // dst was allocated in the owner's stream order
+    int rc = group_run(g, [&](int k) -> int {
+        tci_ctx *c = g->m[k];
+        unsigned long long *w = ctx_words(c);
+        if (!w) return tci_fail(c, TCI_ERR_CUDA, "scratch words");
+        if (k != 0) cudaMemsetAsync(w, 0, 8, c->stream); // the owner accumulates into the caller's word
+        const int rank = c->rank;
+        const i64 lo = std::min(nJ, rank * blk), hi = rank < nshard ? std::min(nJ, (rank + 1) * blk) : lo;
+        if (hi <= lo) return TCI_OK;
+        tci_dmat view;
+        view.ctx = c;
+        view.p = dst + ld * lo;
+        view.m = rows;
+        view.n = view.ncap = hi - lo;
+        view.ld = ld;
+        view.owned = false;
+        TargetDev &t = *c->targets.at(target_id);
+        return pi_enqueue(c, t, I, nl, nI, J + nr * lo, nr, hi - lo, M, &view,
+                          rank == 0 ? d_maxbits : w);
+    });
+    if (rc) return rc;
+    return group_allreduce_max_u64(g, [&](int k) { return g->m[k]->rank == 0 ? d_maxbits : ctx_words(g->m[k]); }, 1);
+}
+
+// sharded M = 0 evaluation of a TT / MPO-pair target by ROW blocks (SURVEY 8e "MPO x MPO contraction: row blocks"):
+// every member extends the right environments of its column block, ONE NCCL all-gather shares them, the member
+// extends the left environments of its own rows, and the GEMM epilogue of its block Pi = left^T right stores into
+// the owner's Pi at the row offset.
+static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64 nl, i64 nI, const i64 *J, i64 nr,
+                                  i64 nJ, double *dst, i64 ld, unsigned long long *d_maxbits)
+{
+    tci_group *g = ctx->grp;
+    const int world = g->world;
+    const i64 cblk = (nJ + world - 1) / world;
+    const i64 rblk = round_up((nI + world - 1) / world, 16); // row blocks start on 128-byte lines
+    std::vector<double *> renv(g->nlocal, nullptr);
+    i64 D = 1;
+    {
+        const TargetDev &t0 = *ctx->targets.at(target_id);
+        const i64 n = t0.nsites;
+        D = nr == 0 ? 1 : (t0.kind == 1 ? t0.dl[n - nr] : t0.adl[n - nr] * t0.bdl[n - nr]);
+    }
+    int rc = group_run(g, [&](int k) -> int {
+        tci_ctx *c = g->m[k];
+        TargetDev &t = *c->targets.at(target_id);
+        const int rank = c->rank;
+        TCI_CUDA(c, dev_alloc(c, (void **)&renv[k], (size_t)D * cblk * world * sizeof(double)));
+        const i64 lo = std::min(nJ, rank * cblk), hi = std::min(nJ, (rank + 1) * cblk);
+        if (hi <= lo) return TCI_OK;
+        DevBuf<i64> dJ(c);
+        TCI_CUDA(c, dJ.upload(J + nr * lo, (size_t)(nr * (hi - lo))));
+        double *env = nullptr;
+        i64 Dk = 1;
+        int r = t.kind == 1 ? env_eval_tt(c, t, 1, dJ.p, (int)nr, hi - lo, &env, &Dk)
+                            : env_eval_mpo(c, t, 1, dJ.p, (int)nr, hi - lo, &env, &Dk, J + nr * lo);
+        if (r) return r;
+        cudaError_t e = cudaMemcpyAsync(renv[k] + D * lo, env, (size_t)D * (hi - lo) * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, c->stream);
+        dev_free(c, env);
+        TCI_CUDA(c, e);
+        return TCI_OK;
+    });
+    if (!rc) rc = group_allgather(g, [&](int k) { return (void *)renv[k]; }, (size_t)D * cblk * sizeof(double));
+    if (!rc) group_follow_owner(g); // dst was allocated in the owner's stream order
+    if (!rc)
+        rc = group_run(g, [&](int k) -> int {
+            tci_ctx *c = g->m[k];
+            TargetDev &t = *c->targets.at(target_id);
+            const int rank = c->rank;
+            unsigned long long *w = rank == 0 ? d_maxbits : ctx_words(c);
+            if (rank != 0) cudaMemsetAsync(w, 0, 8, c->stream);
+            const i64 lo = std::min(nI, rank * rblk), hi = std::min(nI, (rank + 1) * rblk);
+            if (hi <= lo) return TCI_OK;
+            DevBuf<i64> dI(c);
+            TCI_CUDA(c, dI.upload(I + nl * lo, (size_t)(nl * (hi - lo))));
+            double *lenv = nullptr;
+            i64 Dk = 1;
+            int r = t.kind == 1 ? env_eval_tt(c, t, 0, dI.p, (int)nl, hi - lo, &lenv, &Dk)
+                                : env_eval_mpo(c, t, 0, dI.p, (int)nl, hi - lo, &lenv, &Dk, I + nl * lo);
+            if (r) return r;
+            // Pi[lo:hi, :] = lenv^T renv    cachedtensortrain.jl:211-212, contraction.jl:328
+            r = dgemm_dev(c, true, false, hi - lo, nJ, D, 1.0, lenv, D, renv[k], D, 0.0, dst + lo, ld);
+            dev_free(c, lenv);
+            if (!r) r = apply_elementwise(c, t, dst + lo, hi - lo, nJ, ld);
+            if (!r && d_maxbits) r = maxabs_dev(c, dst + lo, hi - lo, nJ, ld, w);
+            return r;
+        });
+    for (int k = 0; k < g->nlocal; ++k) dev_free(g->m[k], renv[k]);
+    if (rc) return rc;
+    return group_allreduce_max_u64(g, [&](int k) { return g->m[k]->rank == 0 ? d_maxbits : ctx_words(g->m[k]); }, 1);
+}
+
+unsigned long long *ctx_words(tci_ctx *ctx)
+{
+    static std::mutex mu;
+    static std::map<tci_ctx *, unsigned long long *> words; // freed with the process; 512 B per context
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = words.find(ctx);
+    if (it != words.end()) return it->second;
+    unsigned long long *p = nullptr;
+    if (cudaMalloc(&p, 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, 64 * sizeof(unsigned long long));
+    words[ctx] = p;
+    return p;
+}
+
+// Evaluation into `out` (on the owner), sharded over the group when the cost model says so; nothing is synchronised.
+// *d_maxbits: zeroed device word on the owner.
+int pi_enqueue_auto(tci_ctx *ctx, i64 target_id, const i64 *I, i64 nl, i64 nI, const i64 *J, i64 nr, i64 nJ, i64 M,
+                    tci_dmat *out, unsigned long long *d_maxbits, int *nshard_out)
+{
+    TargetDev &t = *ctx->targets.at(target_id);
+    i64 C = 1;
+    for (i64 k = 0; k < M; ++k) C *= t.localdims[nl + k];
+    const int ns = choose_shards(ctx, t, nl, nI, nr, nJ, M, C);
+    if (nshard_out) *nshard_out = ns;
+    if (ns == 1) return pi_enqueue(ctx, t, I, nl, nI, J, nr, nJ, M, out, d_maxbits);
+    // `out` is stream-ordered pool memory of the owner; the pool is mapped on every member (group.cu), so the
+    // members' kernels store into it directly
+    return t.kind == 0 ? pi_enqueue_sharded_analytic(ctx, target_id, ns, I, nl, nI, J, nr, nJ, M, out->p, out->ld,
+                                                     nI * C, d_maxbits)
+                       : pi_enqueue_sharded_env(ctx, target_id, I, nl, nI, J, nr, nJ, out->p, out->ld, d_maxbits);
+}
+
 static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
                         int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, tci_dmat *dst,
                         int64_t col0, double *maxabs)
@@ -328,22 +557,10 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
     if (dst && (dst->m != nI * C || col0 < 0 || col0 + nJ > dst->ncap))
         return tci_fail(ctx, TCI_ERR_ARG, "tci_pi_eval_into: destination block does not fit");
 
-    // one allocation for [max bits 16 B][I nl*nI][J nr*nJ]
-    DevBuf<i64> idx(ctx);
-    TCI_CUDA(ctx, idx.alloc(2 + (size_t)(nl * nI) + (size_t)(nr * nJ)));
-    struct {
-        i64 *p;
-    } dI{idx.p + 2}, dJ{idx.p + 2 + nl * nI};
-    struct {
-        unsigned long long *p;
-    } dmax{reinterpret_cast<unsigned long long *>(idx.p)};
-    cudaEventRecord(ctx->ev2, ctx->stream); // index upload is accounted as H2D, the kernels as the Pi stage
-    TCI_CUDA(ctx, cudaMemsetAsync(idx.p, 0, 16, ctx->stream));
-    if (nl * nI > 0)
-        TCI_CUDA(ctx, cudaMemcpyAsync(dI.p, I, (size_t)(nl * nI) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
-    if (nr * nJ > 0)
-        TCI_CUDA(ctx, cudaMemcpyAsync(dJ.p, J, (size_t)(nr * nJ) * sizeof(i64), cudaMemcpyHostToDevice, ctx->stream));
-    cudaEventRecord(ctx->ev0, ctx->stream);
+    unsigned long long *dmax = ctx_words(ctx);
+    if (!dmax) return tci_fail(ctx, TCI_ERR_CUDA, "scratch words");
+    cudaEventRecord(ctx->ev2, ctx->stream);
+    TCI_CUDA(ctx, cudaMemsetAsync(dmax, 0, 8, ctx->stream));
     tci_dmat *out = nullptr;
     tci_dmat view; // column block of dst
     int rc = 0;
@@ -357,20 +574,9 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
         rc = dmat_alloc(ctx, nI * C, nJ, &out);
         if (rc) return rc;
     }
-    {
-        switch (t.kind) {
-        case 0: rc = pi_eval_analytic(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, dmax.p); break;
-        case 1:
-            rc = pi_eval_tt(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out);
-            if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
-            break;
-        default:
-            rc = pi_eval_mpo(ctx, t, dI.p, nl, nI, dJ.p, nr, nJ, M, out, I, J);
-            if (!rc) rc = apply_elementwise(ctx, t, out->p, out->m, out->n, out->ld);
-            if (!rc && maxabs) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax.p);
-            break;
-        }
-    }
+    // an evaluation into a caller-provided block is never sharded (the caller is doing the sharding)
+    rc = dst ? pi_enqueue(ctx, t, I, nl, nI, J, nr, nJ, M, out, dmax)
+             : pi_enqueue_auto(ctx, target_id, I, nl, nI, J, nr, nJ, M, out, dmax, nullptr);
     if (rc) {
         if (!dst) tci_dmat_destroy(out);
         return rc;
@@ -379,7 +585,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
         unsigned long long bits = 0;
         cudaEventRecord(ctx->ev1, ctx->stream); // evaluation done (kernel stage), copies follow
         if (maxabs)
-            TCI_CUDA(ctx, cudaMemcpyAsync(&bits, dmax.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+            TCI_CUDA(ctx, cudaMemcpyAsync(&bits, dmax, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_host)
             TCI_CUDA(ctx, cudaMemcpy2DAsync(out_host, out->m * sizeof(double), out->p, out->ld * sizeof(double),
                                             out->m * sizeof(double), out->n, cudaMemcpyDeviceToHost, ctx->stream));

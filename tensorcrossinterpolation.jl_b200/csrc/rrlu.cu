@@ -501,11 +501,7 @@ static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bo
 {
     void *kargs[] = {&args};
     const void *fn = exact ? rrlu_fn_mode<true>(mode, args.leftorth != 0) : rrlu_fn_mode<false>(mode, args.leftorth != 0);
-    static std::set<const void *> configured;
-    if (!configured.count(fn)) {
-        TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        configured.insert(fn);
-    }
+    TCI_CUDA(ctx, ctx_func_smem(ctx, fn, 227 * 1024 - 1024));
     cudaEventRecord(ctx->ev2, ctx->stream);
     TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(T), kargs, smem, ctx->stream));
     cudaEventRecord(ctx->ev3, ctx->stream);
@@ -513,40 +509,32 @@ static int rrlu_launch(tci_ctx *ctx, RRArgs &args, int G, int T, size_t smem, bo
     return TCI_OK;
 }
 
-extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int64_t m, int64_t n, int64_t maxrank,
-                        double reltol, double abstol, int leftorthogonal, int exact_mode, int64_t *rowperm,
-                        int64_t *colperm, int64_t *npivot, double *error, double *pivoterrors, tci_lu **factors)
+// The factorisation proper: A (on the context's device) is factorised in place; nothing but the final result copy
+// synchronises.  extra_dev / extra_host / extra_bytes: a small device-to-host copy that rides on the same
+// synchronisation (max|Pi| of the evaluation queued in front, tci_bond_update).
+int rrlu_core(tci_ctx *ctx, tci_dmat *A, i64 m, i64 n, i64 maxrank, double reltol, double abstol, int leftorthogonal,
+              int exact_mode, i64 *rowperm, i64 *colperm, i64 *npivot, double *error, double *pivoterrors,
+              tci_lu **factors, const void *extra_dev, void *extra_host, size_t extra_bytes, int *deferred_result)
 {
-    if (factors) *factors = nullptr;
-    tci_dmat *A = A_dev;
-    if (!ctx) return TCI_ERR_ARG;
-    if ((A_host == nullptr) == (A_dev == nullptr) && m * n > 0)
-        return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: pass exactly one of A_host / A_dev");
-    if (m < 0 || n < 0 || m > 0x7ffffff0 || n > 0x7ffffff0) return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: bad shape");
-    if (A_dev && (A_dev->m != m || A_dev->n != n)) return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: shape mismatch");
-    if (!A_dev) {
-        int rc = tci_dmat_create(ctx, m, n, A_host, &A);
-        if (rc) return rc;
-    }
-    TCI_ENTER(ctx);
+    // deferred_result != nullptr (batched callers, tci_fill_sitetensors): nothing synchronises; the 8 result words
+    // (npivot, flags, flags, -, lu.error) and the maxrank pivot values are copied to deferred_result (page-locked,
+    // 32 + 8 * maxrank bytes) in stream order and checked by the caller after ITS synchronisation; the handle is
+    // returned under the assumption npivot == maxrank.
     dmat_wait_ready(ctx, A);
-    struct Cleanup {
-        tci_dmat *a;
-        bool armed;
-        ~Cleanup()
-        {
-            if (armed) tci_dmat_destroy(a);
-        }
-    } cleanup{A, A_dev == nullptr};
-
     const i64 mn = std::min(m, n);
     i64 mr = (maxrank <= 0 || maxrank > mn) ? mn : maxrank;
-    for (i64 i = 0; i < m; ++i) rowperm[i] = i + 1;
-    for (i64 j = 0; j < n; ++j) colperm[j] = j + 1;
+    if (rowperm)
+        for (i64 i = 0; i < m; ++i) rowperm[i] = i + 1;
+    if (colperm)
+        for (i64 j = 0; j < n; ++j) colperm[j] = j + 1;
     *npivot = 0;
     if (mr == 0) { // nothing to do: lu.error = 0 because npivot >= min(m,n) = 0 (matrixlu.jl:176-178)
         *error = 0.0;
         if (pivoterrors) pivoterrors[0] = 0.0;
+        if (extra_bytes) {
+            TCI_CUDA(ctx, cudaMemcpyAsync(extra_host, extra_dev, extra_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         return TCI_OK;
     }
 
@@ -687,7 +675,9 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         args.dbg = dbg.p;
         args.dbg_cta = atoi(dbgenv) % G;
     }
-    std::vector<char> back(o_back);
+    // page-locked: the result copy is pure latency (a deferred caller owns the staging buffer: do not touch it)
+    char *back = deferred_result ? nullptr : static_cast<char *>(ctx_pinned(ctx, o_back + 64));
+    if (!back && !deferred_result) return tci_fail(ctx, TCI_ERR_CUDA, "page-locked staging buffer");
     cudaEventRecord(ctx->ev0, ctx->stream);
     {
         if (getenv("TCI_RRLU_DEBUG"))
@@ -698,7 +688,30 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
                                     G == 1 && resident ? 0 : (resident ? 1 : (xs_in_smem ? 2 : 3)));
         if (rc) return rc;
     }
-    TCI_CUDA(ctx, cudaMemcpyAsync(back.data(), arena.p, o_back, cudaMemcpyDeviceToHost, ctx->stream));
+    if (deferred_result) {
+        TCI_CUDA(ctx, cudaMemcpyAsync(deferred_result, arena.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        TCI_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(deferred_result) + 32, arena.p + o_piv, (size_t)mr * 8,
+                                      cudaMemcpyDeviceToHost, ctx->stream)); // the pivot values follow the 8 words
+        *npivot = mr;
+        tci_lu *lu = new tci_lu();
+        lu->ctx = ctx;
+        lu->A = A;
+        lu->m = m;
+        lu->n = n;
+        lu->r = mr;
+        lu->leftorthogonal = leftorthogonal != 0;
+        lu->arena = arena.p;
+        lu->d_rowperm = args.rowperm;
+        lu->d_colperm = args.colperm;
+        lu->d_colpos = args.colpos;
+        arena.p = nullptr;
+        ctx->live_handles++;
+        *factors = lu;
+        return TCI_OK;
+    }
+    TCI_CUDA(ctx, cudaMemcpyAsync(back, arena.p, o_back, cudaMemcpyDeviceToHost, ctx->stream));
+    if (extra_bytes)
+        TCI_CUDA(ctx, cudaMemcpyAsync(extra_host, extra_dev, extra_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev1, ctx->stream);
     TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     {
@@ -727,8 +740,8 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
             ctx->sm_speed_valid = true;
         }
     }
-    const int *res = reinterpret_cast<const int *>(back.data());
-    const double lu_error = *reinterpret_cast<const double *>(back.data() + 16);
+    const int *res = reinterpret_cast<const int *>(back);
+    const double lu_error = *reinterpret_cast<const double *>(back + 16);
     const int r = res[0];
     if (dbgenv) {
         long long h[16];
@@ -788,9 +801,9 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
     }
     if ((res[1] & 1) || (res[2] & 1)) return tci_fail(ctx, TCI_ERR_NAN_L, "lu.L contains NaNs");
     if (res[2] & 2) return tci_fail(ctx, TCI_ERR_NAN_U, "lu.U contains NaNs");
-    const double *pv = reinterpret_cast<const double *>(back.data() + o_piv);
-    const i64 *rp = reinterpret_cast<const i64 *>(back.data() + o_rp);
-    const i64 *cp = reinterpret_cast<const i64 *>(back.data() + o_cp);
+    const double *pv = reinterpret_cast<const double *>(back + o_piv);
+    const i64 *rp = reinterpret_cast<const i64 *>(back + o_rp);
+    const i64 *cp = reinterpret_cast<const i64 *>(back + o_cp);
     for (i64 i = 0; i < m; ++i) rowperm[i] = rp[i] + 1;
     for (i64 j = 0; j < n; ++j) colperm[j] = cp[j] + 1;
     *npivot = r;
@@ -812,10 +825,36 @@ extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int
         lu->d_colperm = args.colperm;
         lu->d_colpos = args.colpos;
         arena.p = nullptr;
-        cleanup.armed = false;
+        ctx->live_handles++;
         *factors = lu;
     }
     return TCI_OK;
+}
+
+extern "C" int tci_rrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int64_t m, int64_t n, int64_t maxrank,
+                        double reltol, double abstol, int leftorthogonal, int exact_mode, int64_t *rowperm,
+                        int64_t *colperm, int64_t *npivot, double *error, double *pivoterrors, tci_lu **factors)
+{
+    if (factors) *factors = nullptr;
+    tci_dmat *A = A_dev;
+    if (!ctx) return TCI_ERR_ARG;
+    if ((A_host == nullptr) == (A_dev == nullptr) && m * n > 0)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: pass exactly one of A_host / A_dev");
+    if (m < 0 || n < 0 || m > 0x7ffffff0 || n > 0x7ffffff0) return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: bad shape");
+    if (A_dev && (A_dev->m != m || A_dev->n != n)) return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: shape mismatch");
+    if (A_dev && A_dev->ctx != ctx) return tci_fail(ctx, TCI_ERR_ARG, "tci_rrlu: the matrix belongs to another context");
+    if (!A_dev) {
+        int rc = tci_dmat_create(ctx, m, n, A_host, &A);
+        if (rc) return rc;
+    }
+    int rc;
+    {
+        TCI_ENTER(ctx);
+        rc = rrlu_core(ctx, A, m, n, maxrank, reltol, abstol, leftorthogonal, exact_mode, rowperm, colperm, npivot,
+                       error, pivoterrors, factors, nullptr, nullptr, 0, nullptr);
+    }
+    if (!A_dev && !(factors && *factors)) tci_dmat_destroy(A); // our own upload, not handed to a factors handle
+    return rc;
 }
 
 int lu_extract(tci_lu *lu, double *dL, i64 ldl, double *dU, i64 ldu)
@@ -863,7 +902,8 @@ extern "C" int tci_lu_destroy(tci_lu *lu)
     tci_ctx *ctx = lu->ctx;
     cudaSetDevice(ctx->device);
     dev_free(ctx, lu->arena);
-    tci_dmat_destroy(lu->A);
+    ctx->live_handles--;
+    tci_dmat_destroy(lu->A); // releases the context if it was destroyed before its handles
     delete lu;
     return TCI_OK;
 }

@@ -910,11 +910,7 @@ int rrlu_lazy_launch(tci_ctx *ctx, RRArgs &args, int G, size_t smem, bool exact)
 {
     void *kargs[] = {&args};
     const void *fn = exact ? lazy_fn<true, RRLU_LAZY_NB>(args.leftorth != 0) : lazy_fn<false, RRLU_LAZY_NB>(args.leftorth != 0);
-    static std::set<const void *> configured;
-    if (!configured.count(fn)) {
-        TCI_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        configured.insert(fn);
-    }
+    TCI_CUDA(ctx, ctx_func_smem(ctx, fn, 227 * 1024 - 1024));
     cudaEventRecord(ctx->ev2, ctx->stream);
     TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(RL_THREADS), kargs, smem, ctx->stream));
     cudaEventRecord(ctx->ev3, ctx->stream);

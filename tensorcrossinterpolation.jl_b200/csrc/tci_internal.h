@@ -3,10 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tci_b200.h"
@@ -35,6 +39,8 @@ struct TargetDev {
     tci_analytic_t an{};     // params/localdims are DEVICE pointers
     double *d_params = nullptr;
     i64 *d_localdims = nullptr;
+    i64 nparams_alloc = 0; // doubles behind d_params
+    bool pooled = false;   // device buffers come from the context's stream-ordered pool (tci_fill_sitetensors)
     // TT: cores on device, dims (Dl, d, Dr)
     std::vector<double *> cores;
     std::vector<i64> dl, d, dr;
@@ -54,6 +60,7 @@ struct tci_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // uploads that overlap with kernels on `stream` (tci_dmat_create_async)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev4 = nullptr, ev5 = nullptr; // stage boundaries inside the fused entry points (bond.cu)
     std::string err;
     std::mutex mu;
     bool busy = false;
@@ -64,7 +71,68 @@ struct tci_ctx {
     bool sm_speed_valid = false;
     std::map<i64, std::unique_ptr<TargetDev>> targets;
     i64 next_target = 1;
+    // kernels whose dynamic shared-memory limit has been raised ON THIS CONTEXT'S DEVICE (the attribute is per device)
+    std::set<const void *> smem_configured;
+    // multi-GPU: the group this context belongs to (nullptr: a plain single-GPU context) and its place in it
+    struct tci_group *grp = nullptr;
+    int member = 0;      // index among the group's LOCAL members (0 = the context the caller holds)
+    int rank = 0;        // global rank in the group (0 = owner of the per-bond rrLU)
+    bool nosync = false; // inside a batched entry point: stage timers must not synchronise the stream
+    int live_handles = 0; // dmat / lu handles that still point at this context (tci_ctx_destroy defers to the last)
+    bool destroyed = false;
+    // pinned staging for small device-to-host results (latency, not bandwidth)
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
 };
+
+// ---- multi-GPU group (group.cu) -----------------------------------------------------------------------------
+// tci_ctx_create with ngpu > 1 (one process, as the reference's caller is): every GPU of the group is a member
+// context of its own (stream, targets replicated under the same ids), peer access is enabled both ways (also for the
+// stream-ordered pools), one worker thread per member issues that member's share of a sharded stage, and the
+// collectives are NCCL group calls over the members' streams (ncclCommInitAll).
+typedef struct ncclComm *ncclComm_t;
+struct tci_group {
+    int world = 1;  // ranks in the group
+    int nlocal = 1; // members that live in this process
+    std::vector<tci_ctx *> m;   // local members; m[0] is the caller's context
+    std::vector<ncclComm_t> comm;
+    cudaEvent_t ev_owner = nullptr; // recorded on the owner's stream; members wait on it before touching owner memory
+    // worker threads (members 1..nlocal-1)
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::function<int(int)> job;
+    unsigned long long job_gen = 0;
+    int pending = 0;
+    std::vector<int> job_rc;
+    bool stop = false;
+};
+// runs f(k) for every local member k (k = 0 on the calling thread), each with its device current; returns the first
+// non-zero status
+int group_run(tci_group *g, const std::function<int(int)> &f);
+// orders every member's stream behind what the owner's stream has enqueued so far (buffers the owner allocated in
+// stream order must not be touched earlier)
+void group_follow_owner(tci_group *g);
+// collectives over all ranks (in place on every local member; ptr(k) = member k's buffer)
+int group_allreduce_max_u64(tci_group *g, const std::function<unsigned long long *(int)> &ptr, size_t count);
+int group_allgather(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes_per_rank);
+int group_broadcast(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes, int root);
+void group_destroy(tci_group *g);
+void target_free(tci_ctx *ctx, TargetDev &t);  // ctx.cu
+void *ctx_pinned(tci_ctx *ctx, size_t bytes); // page-locked staging of at least `bytes` (ctx.cu)
+// copies target `id` of the caller's context to the other local members under the same id (peer copies)   ctx.cu
+int target_replicate(tci_ctx *ctx, i64 id);
+void ctx_release(tci_ctx *c); // frees the context once it is destroyed and no handle points at it any more
+static inline int ctx_world(const tci_ctx *c) { return c->grp ? c->grp->world : 1; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember it per context, not per process
+static inline cudaError_t ctx_func_smem(tci_ctx *ctx, const void *fn, int bytes)
+{
+    if (ctx->smem_configured.count(fn)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) ctx->smem_configured.insert(fn);
+    return e;
+}
 
 struct tci_lu {
     tci_ctx *ctx = nullptr;
@@ -116,7 +184,10 @@ struct CtxGuard { // single-caller contract (SURVEY 8b "Threading")
 struct StageTimer {
     tci_ctx *c;
     int stage;
-    StageTimer(tci_ctx *ctx, int st) : c(ctx), stage(st) { cudaEventRecord(c->ev0, c->stream); }
+    StageTimer(tci_ctx *ctx, int st) : c(ctx->nosync ? nullptr : ctx), stage(st)
+    {
+        if (c) cudaEventRecord(c->ev0, c->stream);
+    }
     void stop()
     {
         if (!c) return;

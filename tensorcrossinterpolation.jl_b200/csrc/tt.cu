@@ -478,63 +478,281 @@ __global__ void k_star_points(const i64 *__restrict__ starts, const i64 *__restr
     x[p] = r - off[p] + 1;
 }
 
-extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites, const int64_t *dims3,
-                                const double *const *cores, const int64_t *starts, int64_t nsearch, double threshold,
-                                int64_t maxn, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out,
-                                int64_t *nfound)
+// the same star evaluated on the fly for an analytic target: no index array (150 MB at config-4 shape), same order of
+// operations as tci_target_eval, so the values are bit-identical to evaluating the expanded points
+__global__ void k_eval_star(tci_analytic_t t, const i64 *__restrict__ starts, const i64 *__restrict__ off, i64 star,
+                            i64 count, double *__restrict__ out)
+{
+    i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const i64 s = q / star, r = q % star;
+    int p = 0;
+    while (p + 1 < t.nsites && off[p + 1] <= r) ++p;
+    const i64 v = r - off[p] + 1;
+    const i64 *x = starts + s * t.nsites;
+    double st[TCI_MAX_STATE];
+    tci_target_init(&t, st);
+    for (int k = 0; k < t.nsites; ++k) tci_target_accum(&t, k, k == p ? v : x[k], st);
+    out[q] = tci_target_finalize(&t, st);
+}
+
+// tt value of every probe of the arm of site p from the prefix / suffix environments of the START points:
+//   g[s*star + off_p + v] = sum_b W[s + ns*(v + d*b)] * R[b + Dr*s],  W = L_p^T T_p  (ns x d*Dr, from the DMMA GEMM)
+__global__ void k_star_contract(const double *__restrict__ W, const double *__restrict__ R, i64 ns, int d, int Dr,
+                                i64 star, i64 offp, double *__restrict__ g)
+{
+    const i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= ns * d) return;
+    const i64 s = e % ns;
+    const int v = (int)(e / ns);
+    const double *w = W + s + ns * (i64)v;
+    const double *r = R + (i64)Dr * s;
+    double acc = 0.0;
+    for (int b = 0; b < Dr; ++b) acc = fma(w[ns * (i64)d * b], r[b], acc);
+    g[s * star + offp + v] = acc;
+}
+
+// per start: first maximum of |f - g| over its star with strict '>' (globalpivotfinder.jl:170-175): the record is
+// (best error, probe index within the star or -1)
+struct __align__(16) StarRec {
+    double err;
+    i64 idx;
+};
+__global__ void __launch_bounds__(256)
+    k_star_argmax(const double *__restrict__ f, const double *__restrict__ g, i64 star, StarRec *__restrict__ rec)
+{
+    const i64 s = blockIdx.x;
+    double best = 0.0;
+    i64 bi = -1;
+    for (i64 r = threadIdx.x; r < star; r += blockDim.x) {
+        const double e = fabs(__dsub_rn(f[s * star + r], g[s * star + r]));
+        if (e > best) { // never true for a NaN
+            best = e;
+            bi = r;
+        }
+    }
+    __shared__ double sb[256];
+    __shared__ i64 si[256];
+    sb[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            const double ob = sb[threadIdx.x + w];
+            const i64 oi = si[threadIdx.x + w];
+            // larger error wins; equal errors: the earlier probe (the reference's scan keeps the first maximum)
+            if (oi >= 0 && (ob > sb[threadIdx.x] || (ob == sb[threadIdx.x] && (si[threadIdx.x] < 0 || oi < si[threadIdx.x])))) {
+                sb[threadIdx.x] = ob;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        rec[s].err = sb[0];
+        rec[s].idx = si[0];
+    }
+}
+
+// One member's share of a search: starts [s0, s1) of d_starts (nsites x nsearch, on this member's device); records
+// go to rec[s0 .. s1).  mode 1: ordered chain for every probe (bit-identical to evaluate(tt, x)); mode 2: prefix /
+// suffix environments of the start points + one GEMM per site (~n x fewer flops, values within rounding of mode 1).
+static int gsearch_member(tci_ctx *ctx, TargetDev &t, TargetDev &tt, const i64 *d_starts, i64 s0, i64 s1, int mode,
+                          const i64 *d_off, const std::vector<i64> &off, StarRec *rec)
+{
+    const i64 ns = s1 - s0;
+    if (ns <= 0) return TCI_OK;
+    const int n = (int)t.nsites;
+    const i64 star = off[n], count = star * ns;
+    const i64 *starts = d_starts + s0 * n;
+    std::vector<CoreView> cv = views(tt);
+    DevBuf<double> d_f(ctx), d_g(ctx);
+    DevBuf<i64> d_idx(ctx);
+    TCI_CUDA(ctx, d_f.alloc((size_t)count));
+    TCI_CUDA(ctx, d_g.alloc((size_t)count));
+    int rc = 0;
+    const bool need_points = t.kind != 0 || mode == 1;
+    if (need_points) {
+        TCI_CUDA(ctx, d_idx.alloc((size_t)(count * n)));
+        k_star_points<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(starts, d_off, n, star, count, d_idx.p);
+        ctx->launches++;
+    }
+    if (t.kind == 0) {
+        k_eval_star<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(t.an, starts, d_off, star, count, d_f.p);
+        ctx->launches++;
+    } else
+        rc = target_eval_dev(ctx, t, d_idx.p, count, d_f.p);
+    if (rc) return rc;
+    if (mode == 1)
+        rc = tt_eval_points(ctx, cv, d_idx.p, count, d_g.p);
+    else {
+        // prefix environments L[p] (D_p x ns) after sites 0..p-1 and suffix environments R[p] (D_p x ns) over p..n-1
+        std::vector<double *> L((size_t)n + 1, nullptr), R((size_t)n + 1, nullptr);
+        auto freeall = [&] {
+            for (double *q : L) dev_free(ctx, q);
+            for (double *q : R) dev_free(ctx, q);
+        };
+        cudaError_t e = cudaSuccess;
+        for (int p = 1; p < n && e == cudaSuccess; ++p) {
+            const CoreView &c = cv[p - 1];
+            e = dev_alloc(ctx, (void **)&L[p], (size_t)c.Dr * ns * sizeof(double));
+            if (e != cudaSuccess) break;
+            const i64 total = (i64)c.Dr * ns;
+            k_env_left_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(L[p - 1], c.p, c.Dl, c.d, c.Dr,
+                                                                                     starts, n, p - 1, ns, L[p]);
+            ctx->launches++;
+        }
+        for (int p = n - 1; p >= 1 && e == cudaSuccess; --p) {
+            const CoreView &c = cv[p];
+            e = dev_alloc(ctx, (void **)&R[p], (size_t)c.Dl * ns * sizeof(double));
+            if (e != cudaSuccess) break;
+            const i64 total = (i64)c.Dl * ns;
+            k_env_right_step<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(p + 1 < n ? R[p + 1] : nullptr, c.p,
+                                                                                      c.Dl, c.d, c.Dr, starts, n, p, ns,
+                                                                                      R[p]);
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) {
+            e = dev_alloc(ctx, (void **)&L[0], (size_t)ns * sizeof(double));
+            if (e == cudaSuccess) e = dev_alloc(ctx, (void **)&R[n], (size_t)ns * sizeof(double));
+        }
+        if (e != cudaSuccess) {
+            freeall();
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("global search environments: ") + cudaGetErrorString(e));
+        }
+        k_fill<<<(unsigned)((ns + 127) / 128), 128, 0, ctx->stream>>>(L[0], ns, 1.0);
+        k_fill<<<(unsigned)((ns + 127) / 128), 128, 0, ctx->stream>>>(R[n], ns, 1.0);
+        ctx->launches += 2;
+        i64 wmax = 0;
+        for (int p = 0; p < n; ++p) wmax = std::max<i64>(wmax, (i64)cv[p].d * cv[p].Dr);
+        DevBuf<double> W(ctx);
+        e = W.alloc((size_t)(ns * wmax));
+        if (e != cudaSuccess) {
+            freeall();
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("global search workspace: ") + cudaGetErrorString(e));
+        }
+        for (int p = 0; p < n && !rc; ++p) {
+            const CoreView &c = cv[p];
+            // W (ns x d*Dr) = L[p]^T (ns x Dl) * T_p (Dl x d*Dr)
+            rc = dgemm_dev(ctx, true, false, ns, (i64)c.d * c.Dr, c.Dl, 1.0, L[p], c.Dl, c.p, c.Dl, 0.0, W.p, ns);
+            if (rc) break;
+            const i64 total = ns * c.d;
+            k_star_contract<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(W.p, R[p + 1], ns, c.d, c.Dr, star,
+                                                                                     off[p], d_g.p);
+            ctx->launches++;
+        }
+        freeall();
+    }
+    if (rc) return rc;
+    k_star_argmax<<<(unsigned)ns, 256, 0, ctx->stream>>>(d_f.p, d_g.p, star, rec + s0);
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
+extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts,
+                                int64_t nsearch, double threshold, int64_t maxn, int mode, int64_t *pivots_out,
+                                double *errs_out, int64_t *start_idx_out, int64_t *nfound)
 {
     TCI_ENTER(ctx);
     if (!nfound) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: nfound missing");
     *nfound = 0;
-    auto it = ctx->targets.find(target_id);
-    if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+    auto it = ctx->targets.find(target_id), jt = ctx->targets.find(tt_id);
+    if (it == ctx->targets.end() || jt == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
-    if (t.nsites != nsites) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: tensor train length mismatch");
+    TargetDev &tt = *jt->second;
+    if (tt.kind != 1) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: tt_id must name a tensor train (tci_tt_create)");
+    if (t.nsites != tt.nsites) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: tensor train length mismatch");
+    if (tt.dl.front() != 1 || tt.dr.back() != 1) return tci_fail(ctx, TCI_ERR_ARG, "boundary bonds must be 1");
+    if (mode < 0 || mode > 2) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: mode is 0 (auto), 1 (ordered chain) or 2 (environments)");
     if (nsearch <= 0 || maxn <= 0) return TCI_OK;
-    StageTimer tm(ctx, ST_GSEARCH);
-    // the star of probes around every start point (globalpivotfinder.jl:167-177)
-    i64 star = 0;
-    for (i64 p = 0; p < nsites; ++p) star += dims3[3 * p + 1];
-    const i64 count = star * nsearch;
+    if (!starts || !pivots_out || !errs_out) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: buffers missing");
+    const i64 nsites = t.nsites;
     std::vector<i64> off((size_t)nsites + 1, 0);
-    for (i64 p = 0; p < nsites; ++p) off[p + 1] = off[p] + dims3[3 * p + 1];
-    HostTT tt(ctx);
-    int rc = tt.upload(nsites, dims3, cores);
+    for (i64 p = 0; p < nsites; ++p) off[p + 1] = off[p] + tt.d[p];
+    const i64 star = off[nsites];
+    // auto: a handful of starts (the reference's default nsearch = 5) keeps the ordered chain, whose values are
+    // bit-identical to evaluate(tt, x); large searches use the prefix / suffix environments (~nsites x fewer flops)
+    if (mode == 0) mode = star * nsearch >= 32768 ? 2 : 1;
+    if (const char *e = getenv("TCI_GSEARCH_MODE"))
+        if (atoi(e) == 1 || atoi(e) == 2) mode = atoi(e);
+    tci_group *g = ctx->grp;
+    const int world = (g && nsearch >= 4 * (i64)g->world && star * nsearch >= 65536) ? g->world : 1;
+    const i64 blk = (nsearch + world - 1) / world;
+    const size_t rec_bytes = (size_t)blk * world * sizeof(StarRec);
+    StarRec *hrec = static_cast<StarRec *>(ctx_pinned(ctx, rec_bytes));
+    if (!hrec) return tci_fail(ctx, TCI_ERR_CUDA, "page-locked staging buffer");
+    cudaEventRecord(ctx->ev4, ctx->stream);
+    const bool saved = ctx->nosync;
+    ctx->nosync = true;
+    int rc = 0;
+    std::vector<StarRec *> drec(world, nullptr);
+    std::vector<i64 *> dst(world, nullptr), doff(world, nullptr);
+    auto member_job = [&](int k) -> int {
+        tci_ctx *c = world == 1 ? ctx : g->m[k];
+        TargetDev &tk = *c->targets.at(target_id);
+        TargetDev &ttk = *c->targets.at(tt_id);
+        TCI_CUDA(c, dev_alloc(c, (void **)&drec[k], rec_bytes));
+        TCI_CUDA(c, dev_alloc(c, (void **)&dst[k], (size_t)(nsites * nsearch) * sizeof(i64)));
+        TCI_CUDA(c, dev_alloc(c, (void **)&doff[k], off.size() * sizeof(i64)));
+        TCI_CUDA(c, cudaMemcpyAsync(dst[k], starts, (size_t)(nsites * nsearch) * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+        TCI_CUDA(c, cudaMemcpyAsync(doff[k], off.data(), off.size() * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+        const i64 s0 = std::min(nsearch, c->rank * blk), s1 = std::min(nsearch, (c->rank + 1) * blk);
+        return gsearch_member(c, tk, ttk, dst[k], s0, s1, mode, doff[k], off, drec[k]);
+    };
+    if (world == 1)
+        rc = member_job(0);
+    else {
+        rc = group_run(g, member_job);
+        // fixed-size (error, index) records of every rank's starts: one all-gather (globalpivotfinder.jl:186-188 is
+        // replayed on the gathered records below)
+        if (!rc) rc = group_allgather(g, [&](int k) { return (void *)drec[k]; }, (size_t)blk * sizeof(StarRec));
+    }
+    ctx->nosync = saved;
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(hrec, drec[0], (size_t)nsearch * sizeof(StarRec), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->ev5, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, std::string("tci_globalsearch: ") + cudaGetErrorString(e));
+        float ms = 0.f;
+        if (!rc && cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5) == cudaSuccess) ctx->stage_ms[ST_GSEARCH] += ms;
+    }
+    for (int k = 0; k < world; ++k) {
+        tci_ctx *c = world == 1 ? ctx : g->m[k];
+        dev_free(c, drec[k]);
+        dev_free(c, dst[k]);
+        dev_free(c, doff[k]);
+    }
     if (rc) return rc;
-    DevBuf<i64> d_idx(ctx), d_starts(ctx), d_off(ctx);
-    DevBuf<double> d_f(ctx), d_g(ctx), d_e(ctx);
-    TCI_CUDA(ctx, d_starts.upload(starts, (size_t)(nsites * nsearch)));
-    TCI_CUDA(ctx, d_off.upload(off.data(), off.size()));
-    TCI_CUDA(ctx, d_idx.alloc((size_t)(count * nsites)));
-    k_star_points<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d_starts.p, d_off.p, (int)nsites, star,
-                                                                           count, d_idx.p);
-    ctx->launches++;
-    TCI_CUDA(ctx, d_f.alloc((size_t)count));
-    TCI_CUDA(ctx, d_g.alloc((size_t)count));
-    TCI_CUDA(ctx, d_e.alloc((size_t)count));
-    rc = target_eval_dev(ctx, t, d_idx.p, count, d_f.p);
-    if (rc) return rc;
-    rc = tt_eval_points(ctx, tt.cv, d_idx.p, count, d_g.p);
-    if (rc) return rc;
-    k_abs_diff<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d_f.p, d_g.p, count, d_e.p);
-    ctx->launches++;
-    std::vector<double> err((size_t)count);
-    TCI_CUDA(ctx, cudaMemcpyAsync(err.data(), d_e.p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // selection: strict '>' keeps the first maximum, threshold, truncation in start order (:170-188)
+    std::vector<double> rerr((size_t)nsearch);
+    std::vector<i64> ridx((size_t)nsearch), ld((size_t)nsites);
+    for (i64 q = 0; q < nsearch; ++q) {
+        rerr[q] = hrec[q].err;
+        ridx[q] = hrec[q].idx;
+    }
+    for (i64 p = 0; p < nsites; ++p) ld[p] = tt.d[p];
+    return tci_globalsearch_select(rerr.data(), ridx.data(), nsearch, starts, nsites, ld.data(), threshold, maxn,
+                                   pivots_out, errs_out, start_idx_out, nfound);
+}
+
+// selection of globalpivotfinder.jl:180-188 on the per-start (error, probe index) records: keep a start if its best
+// error exceeds the threshold, in start order, truncated to the first maxn; the pivot is the start point with the
+// coordinate of the best probe replaced.  Host only.
+extern "C" int tci_globalsearch_select(const double *rec_err, const int64_t *rec_idx, int64_t nsearch,
+                                       const int64_t *starts, int64_t nsites, const int64_t *localdims,
+                                       double threshold, int64_t maxn, int64_t *pivots_out, double *errs_out,
+                                       int64_t *start_idx_out, int64_t *nfound)
+{
+    if (!nfound || !rec_err || !rec_idx || !starts || !localdims || !pivots_out || !errs_out) return TCI_ERR_ARG;
+    std::vector<i64> off((size_t)nsites + 1, 0);
+    for (i64 p = 0; p < nsites; ++p) off[p + 1] = off[p] + localdims[p];
     i64 found = 0;
     for (i64 s = 0; s < nsearch && found < maxn; ++s) {
-        double best = 0.0;
-        i64 bestq = -1;
-        for (i64 e = s * star; e < (s + 1) * star; ++e)
-            if (err[e] > best) {
-                best = err[e];
-                bestq = e;
-            }
+        const double best = rec_err[s];
         if (best > threshold) {
             for (i64 k = 0; k < nsites; ++k) pivots_out[k + found * nsites] = starts[k + s * nsites];
-            if (bestq >= 0) {
-                const i64 r = bestq - s * star;
+            if (rec_idx[s] >= 0) {
+                const i64 r = rec_idx[s];
                 i64 p = 0;
                 while (p + 1 < nsites && off[p + 1] <= r) ++p;
                 pivots_out[p + found * nsites] = r - off[p] + 1;
@@ -545,5 +763,15 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t nsites,
         }
     }
     *nfound = found;
+    return TCI_OK;
+}
+
+// contiguous blocks whose starts are multiples of `align` (the partition of every sharded stage).  Host only.
+extern "C" int tci_shard_range(int64_t n, int world, int rank, int64_t align, int64_t *lo, int64_t *hi)
+{
+    if (n < 0 || world < 1 || rank < 0 || rank >= world || align < 1 || !lo || !hi) return TCI_ERR_ARG;
+    const i64 blk = round_up((n + world - 1) / world, align);
+    *lo = std::min<i64>(n, rank * blk);
+    *hi = std::min<i64>(n, (rank + 1) * blk);
     return TCI_OK;
 }

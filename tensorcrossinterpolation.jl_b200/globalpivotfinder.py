@@ -4,8 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import core_ptrs, lib, pf, pi
-from .tensortrain import _dims3
+from ._lib import lib, pf, pi
 from .util import CounterRNG
 
 
@@ -39,37 +38,28 @@ class DefaultGlobalPivotFinder(AbstractGlobalPivotFinder):  # :100-195
         rng = rng or np.random.default_rng()
         return np.stack([rng.integers(1, d + 1, self.nsearch) for d in input.localdims], axis=1).astype(np.int64)
 
-    def __call__(self, input, f, abstol, verbosity=0, rng=None):
+    def __call__(self, input, f, abstol, verbosity=0, rng=None, mode=0):
+        """mode: tci_globalsearch's evaluation mode (0 auto, 1 ordered chain, 2 prefix / suffix environments)."""
         n = len(input.localdims)
         if self.nsearch <= 0 or self.maxnglobalpivot <= 0:
             return np.zeros((0, n), dtype=np.int64)
         starts = np.ascontiguousarray(self.draw(input, rng))
-        keep, arr = core_ptrs([c.reshape((c.shape[0], -1, c.shape[-1]), order="F")
-                               for c in input.current_tt.sitetensors])
-        d3 = _dims3(keep)
-        world, rank = getattr(f, "world", 1), getattr(f, "rank", 0)
-        mine = np.arange(rank, starts.shape[0], world)  # independent starts, dealt round-robin
-        local = np.ascontiguousarray(starts[mine])
-        # the reference collects every accepted point and then truncates (:186-188)
-        cap = max(len(mine), 1) if world > 1 else self.maxnglobalpivot
+        ctx = f.ctx
+        tt = input.current_tt
+        handle = getattr(tt, "device_handle", None)  # the device-resident cores tci_fill_sitetensors left behind
+        if handle is None or handle.ctx is not ctx:
+            from .cachedtensortrain import TTCache
+            handle = TTCache(tt, ctx=ctx)  # uploaded once for this call
+        cap = self.maxnglobalpivot
         piv = np.zeros((cap, n), dtype=np.int64)
         errs = np.zeros(cap, dtype=np.float64)
         acc = np.zeros(cap, dtype=np.int64)
         nf = C.c_int64(0)
-        ctx = f.ctx
-        if len(mine):
-            ctx.check(lib().tci_globalsearch(ctx.h, f.id, n, pi(d3), arr, pi(local), local.shape[0],
-                                             float(abstol) * self.tolmarginglobalsearch, cap, pi(piv), pf(errs),
-                                             pi(acc), C.byref(nf)))
-        if world > 1:
-            from .parallel import allgather_candidates, select_global_pivots
-            cands = [(int(mine[acc[q]]), piv[q].tolist(), float(errs[q])) for q in range(nf.value)]
-            pts, es = select_global_pivots(allgather_candidates(f.dist, cands, f.group), self.maxnglobalpivot)
-            self.last_errors = np.asarray(es, dtype=np.float64)
-            if verbosity > 0:
-                print(f"Found {len(pts)} global pivots")
-            return np.asarray(pts, dtype=np.int64).reshape(len(pts), n)
+        ctx.check(lib().tci_globalsearch(ctx.h, f.id, handle.id, pi(starts), starts.shape[0],
+                                         float(abstol) * self.tolmarginglobalsearch, cap, int(mode), pi(piv),
+                                         pf(errs), pi(acc), C.byref(nf)))
         if verbosity > 0:
             print(f"Found {nf.value} global pivots")
         self.last_errors = errs[: nf.value].copy()
+        self.last_starts = acc[: nf.value].copy()
         return piv[: nf.value].copy()

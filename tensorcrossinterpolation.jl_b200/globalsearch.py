@@ -5,7 +5,7 @@ import numpy as np
 
 from .cachedtensortrain import TTCache
 from .tensortrain import TensorTrain
-from .util import CounterRNG
+from .util import CounterRNG, jl_max
 
 
 def _floatingzone(ttcache, f, earlystoptol=float("inf"), nsweeps=2**62, initp=None, rng=None):
@@ -16,8 +16,11 @@ def _floatingzone(ttcache, f, earlystoptol=float("inf"), nsweeps=2**62, initp=No
     localdims = ttcache.localdims
     n = len(localdims)
     if initp is None:
-        rng = rng or np.random.default_rng()
-        pivot = [int(rng.integers(1, d + 1)) for d in localdims]
+        if isinstance(rng, CounterRNG):  # the package-wide injected generator (optimize passes it to the finders)
+            pivot = [int(v) for v in rng.start_points(1, localdims)[0]]
+        else:
+            rng = rng or np.random.default_rng()
+            pivot = [int(rng.integers(1, d + 1)) for d in localdims]
     else:
         pivot = [int(x) for x in initp]
     maxerror = abs(f(pivot) - ttcache(pivot))
@@ -32,7 +35,7 @@ def _floatingzone(ttcache, f, earlystoptol=float("inf"), nsweeps=2**62, initp=No
             pred = ttcache(left, right, 1).reshape(-1)
             err = np.abs(exact - pred)
             pivot[ipos] = int(np.argmax(err)) + 1  # argmax: first maximum
-            maxerror = max(float(np.max(err)), maxerror)
+            maxerror = jl_max(float(np.max(err)), maxerror)  # Julia's max propagates NaN
         if maxerror == prev or maxerror > earlystoptol:
             break
     return pivot, maxerror

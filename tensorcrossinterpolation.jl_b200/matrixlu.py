@@ -30,6 +30,8 @@ class rrLU:
     def _fetch(self):
         m, n = self._shape
         r = self.npivot
+        if self._h is None:
+            raise RuntimeError("this rrLU was computed without factors (bond_update(want_factors=False))")
         L = np.zeros((m, r), dtype=np.float64, order="F")
         U = np.zeros((r, n), dtype=np.float64, order="F")
         if r:
@@ -162,7 +164,7 @@ class MatrixLUCI:
     """matrixluci.jl:1-92."""
 
     def __init__(self, A, **kwargs):
-        self.lu = rrlu(A, **kwargs)
+        self.lu = A if isinstance(A, rrLU) else rrlu(A, **kwargs)  # an rrLU: the factors tci_bond_update left behind
 
     # accessors shared with rrLU
     @property

@@ -14,7 +14,6 @@ import numpy as np
 from .batcheval import BatchEvaluator
 from .globalpivotfinder import AbstractGlobalPivotFinder, DefaultGlobalPivotFinder, GlobalPivotSearchInput
 from .matrixlu import MatrixLUCI, colindices, pivoterrors, rowindices, rrlu
-from .parallel import PivotResult, broadcast_pivots
 from .tensortrain import TensorTrain, evaluate_points, tt_sum
 from .util import (CounterRNG, as_indexset, forwardsweep, jl_max, kronecker_left, kronecker_right, pushunique, union)
 
@@ -41,6 +40,7 @@ class TensorCI2:
         self.maxsamplevalue = 0.0
         self.Iset_history = []
         self.Jset_history = []
+        self.device_tt = None
         if func is None:
             return
         if Iset is not None:  # tensorci2.jl:58-72
@@ -79,6 +79,7 @@ def rank(tci):
 def invalidatesitetensors(tci):  # :90-95
     for b in range(len(tci)):
         tci.sitetensors[b] = np.zeros((0, 0, 0), order="F")
+    tci.device_tt = None  # the device-resident copy of the site tensors (tci_fill_sitetensors) goes with them
 
 
 def issitetensorsavailable(tci):  # :100-102
@@ -171,7 +172,6 @@ def setsitetensor_fill(tci, f, b):
     P is factorised to full rank by the K2 kernel and the solve runs on the device (tci_lu_rdiv) in place of
     the reference's LAPACK `\\` (:391); only T_b comes back to the host."""
     n = len(tci)
-    f = getattr(f, "local", f)  # the T tensors are small: replicated on every rank, not sharded
     nI, d, nJ = tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]
     if b == n - 1:
         Pi1, _, mx = f._pi(tci.Iset[b], tci.Jset[b], 1, True, False)
@@ -191,9 +191,18 @@ def setsitetensor_fill(tci, f, b):
     return tci.sitetensors[b]
 
 
-def fillsitetensors(tci, f):  # globalsearch.jl:97-103
-    for b in range(len(tci)):
-        setsitetensor_fill(tci, f, b)
+def fillsitetensors(tci, f):
+    """fillsitetensors! (globalsearch.jl:97-103): every setsitetensor!(tci, f, b) in ONE library call
+    (tci_fill_sitetensors: all Pi1 / P evaluations, factorisations and solves queued back to back, one
+    synchronisation); the cores also stay on the device for the global pivot finder."""
+    for b in range(len(tci) - 1):
+        if tci.Iset[b + 1].shape[0] != tci.Jset[b].shape[0]:
+            raise RuntimeError(f"Pivot matrix at bond {b + 1} is not square!")  # :388
+    Ts, mx, handle = f.fill_sitetensors(tci.Iset, tci.Jset)
+    updatemaxsample(tci, mx)
+    for b, T in enumerate(Ts):
+        tci.sitetensors[b] = T
+    tci.device_tt = handle
 
 
 def _sanitycheck(tci):  # globalsearch.jl:106-112
@@ -207,7 +216,6 @@ def sweep1site(tci, f, sweepdirection="forward", reltol=1e-14, abstol=0.0, maxbo
     """sweep1site! (tensorci2.jl:402-461)."""
     flushpivoterror(tci)
     invalidatesitetensors(tci)
-    f = getattr(f, "local", f)  # the small T-tensor factorisations are replicated on every rank, not sharded
     if sweepdirection not in ("forward", "backward"):
         raise ValueError(f"Unknown sweep direction {sweepdirection}: choose between :forward, :backward.")
     fwd = sweepdirection == "forward"
@@ -219,10 +227,9 @@ def sweep1site(tci, f, sweepdirection="forward", reltol=1e-14, abstol=0.0, maxbo
         updatemaxsample(tci, mx)
         if fwd:  # (|I|*d) x |J| is already the matrix shape
             luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX), leftorthogonal=True)
-        else:  # |I| x (d*|J|): same memory, different fold -> refold through the host
-            host = Pi.to_host().reshape((len(Is), len(Js)), order="F")
-            luci = MatrixLUCI(host, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
-                              leftorthogonal=False, ctx=f.ctx)
+        else:  # |I| x (d*|J|): the same tensor folded differently -- refolded on the device (tci_dmat_refold)
+            luci = MatrixLUCI(Pi.refold(len(Is), len(Js)), reltol=reltol, abstol=abstol,
+                              maxrank=min(maxbonddim, I64MAX), leftorthogonal=False)
         nIb, nJb = tci.Iset[b].shape[0], tci.Jset[b].shape[0]
         if fwd:
             tci.Iset[b + 1] = Is[rowindices(luci) - 1]
@@ -286,43 +293,36 @@ def updatepivots(tci, b, f, leftorthogonal, reltol=1e-14, abstol=0.0, maxbonddim
     Jcombined = union(kronecker_right(tci.localdims[b + 1], tci.Jset[b + 1]), extraJset)
     if pivotsearch not in ("full", "rook"):
         raise ValueError(f"Unknown pivot search strategy {pivotsearch}. Choose from :rook, :full.")
-    world = getattr(f, "world", 1)
     luci = res = None
     t1 = time.perf_counter()
-    if pivotsearch == "rook":  # :552-595 (replicated on every rank: only rows / columns are evaluated)
+    if pivotsearch == "rook":  # :552-595 (only rows / columns of Pi are ever evaluated)
         from .matrixlu import arrlu
-        g = getattr(f, "local", f)
         I0 = _positions(tci.Iset[b + 1], Icombined)
         J0 = _positions(tci.Jset[b], Jcombined)
-        Pif = SubMatrix(g, Icombined, Jcombined)
+        Pif = SubMatrix(f, Icombined, Jcombined)
         lu = arrlu(Pif, (len(Icombined), len(Jcombined)), I0, J0, reltol=reltol, abstol=abstol,
                    maxrank=min(maxbonddim, I64MAX), leftorthogonal=leftorthogonal, rng=rng)
         updatemaxsample(tci, Pif.maxsamplevalue)
         if lu.npivot > 0:
-            res = PivotResult(lu.npivot, rowindices(lu), colindices(lu), pivoterrors(lu))
+            res = lu
     t2 = time.perf_counter()
-    if res is None:  # :full, or the fall back of :573-588
-        Pi, mx = filltensor(f, tci.localdims, Icombined, Jcombined, 0, device=True)
-        t2 = time.perf_counter()
+    if res is None:  # :full, or the fall back of :573-588 -- Pi evaluation and rrLU fused in the library
+        want = set_sitetensors and len(extraIset) == 0 and len(extraJset) == 0
+        res, mx = f.bond_update(Icombined, Jcombined, maxrank=min(maxbonddim, I64MAX), reltol=reltol, abstol=abstol,
+                                leftorthogonal=leftorthogonal, want_factors=want)
         updatemaxsample(tci, mx)
-        if world == 1 or f.rank == f.owner:  # the per-bond rrLU stays on one GPU
-            luci = MatrixLUCI(Pi, reltol=reltol, abstol=abstol, maxrank=min(maxbonddim, I64MAX),
-                              leftorthogonal=leftorthogonal)
-            res = PivotResult(luci.npivot, rowindices(luci), colindices(luci), pivoterrors(luci))
-        else:
-            del Pi
-        if world > 1:
-            res = broadcast_pivots(f.dist, res, f.owner, f.group)
+        if want:
+            luci = MatrixLUCI(res)
     t3 = time.perf_counter()
     if verbosity > 2:
-        print(f"    Computing Pi ({len(Icombined)} x {len(Jcombined)}) at bond {b + 1}: {t2 - t1} sec, "
-              f"LU: {t3 - t2} sec")
-    tci.Iset[b + 1] = Icombined[res.rowindices - 1]
-    tci.Jset[b] = Jcombined[res.colindices - 1]
-    if set_sitetensors and luci is not None and len(extraIset) == 0 and len(extraJset) == 0:  # :601-604
+        print(f"    Computing Pi ({len(Icombined)} x {len(Jcombined)}) at bond {b + 1} + LU: {t3 - t2} sec "
+              f"(rook search {t2 - t1} sec)")
+    tci.Iset[b + 1] = Icombined[rowindices(res) - 1]
+    tci.Jset[b] = Jcombined[colindices(res) - 1]
+    if luci is not None:  # :601-604
         setsitetensor(tci, b, luci.left())
         setsitetensor(tci, b + 1, luci.right())
-    updateerrors(tci, b, res.pivoterrors)
+    updateerrors(tci, b, pivoterrors(res))
     if hasattr(tci, "trace"):
         tci.trace.append((b + 1, len(Icombined), len(Jcombined), res.npivot))
 
@@ -407,8 +407,7 @@ def sweep0site(tci, f, b, reltol=1e-14, abstol=0.0):
     """sweep0site! / rmbadpivots! (tensorci2.jl:341-363), b 0-based: drop the pivots of bond b whose diagonal
     entry of U is below the tolerances."""
     invalidatesitetensors(tci)
-    g = getattr(f, "local", f)
-    P, mx = g.batchevaluate_device(tci.Iset[b + 1], tci.Jset[b], 0)
+    P, mx = f.batchevaluate_device(tci.Iset[b + 1], tci.Jset[b], 0)
     updatemaxsample(tci, mx)
     F = MatrixLUCI(P, reltol=reltol, abstol=abstol, leftorthogonal=True)
     d = np.abs(np.diag(F.lu.U))
@@ -524,8 +523,9 @@ def optimize(tci, f, tolerance=None, pivottolerance=None, maxbonddim=I64MAX, max
         errors.append(pivoterror(tci))
         if verbosity > 1:
             print(f"  Walltime {time.perf_counter() - tstart} sec: start searching global pivots", flush=True)
-        inp = GlobalPivotSearchInput(tci.localdims, TensorTrain(tci.sitetensors), tci.maxsamplevalue, tci.Iset,
-                                     tci.Jset)
+        current_tt = TensorTrain(tci.sitetensors)
+        current_tt.device_handle = tci.device_tt  # the same cores, already on the device (tci_fill_sitetensors)
+        inp = GlobalPivotSearchInput(tci.localdims, current_tt, tci.maxsamplevalue, tci.Iset, tci.Jset)
         globalpivots = finder(inp, f, abstol, verbosity=verbosity, rng=rng)
         addglobalpivots(tci, globalpivots)
         nglobalpivots.append(len(globalpivots))

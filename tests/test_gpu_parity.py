@@ -214,6 +214,17 @@ def test_rrlu_config2_full_size_vs_oracle(T, oracle):
     assert_lu_equal(lu, ref)
 
 
+def test_rrlu_config2_headline_vs_oracle(T, oracle):
+    """BASELINE config 2 at the headline point of bench.py: 8192 x 8192, maxrank 1024, reltol 1e-12, the same generator
+    and seed as the bench (bench.factors(m, n, r, 2)).  The single-threaded oracle needs ~100 s for it; permutations,
+    pivot errors, lu.error and both factors must be bit-identical (matrixlu.jl:141-181)."""
+    A = np.asfortranarray(lowrank_matrix(8192, 8192, 1024, seed=2))
+    lu = T.rrlu(A, maxrank=1024, reltol=1e-12)
+    ref = oracle.rrlu(A, maxrank=1024, reltol=1e-12)
+    assert lu.npivot == ref.npivot == 1024
+    assert_lu_equal(lu, ref)
+
+
 def test_rrlu_config2_full_rank_properties(T):
     """Size-independent properties at 8192 x 8192, maxrank 1024 (no oracle run: ~100 s on a CPU core):
     L unit lower / U upper, permutations are permutations, full-pivoting bound |L| <= 1, sampled
@@ -1167,20 +1178,184 @@ def test_argument_errors(T):  # test_tensorci2.jl:215-245
         T.TensorCI2(z, [2, 2])
 
 
-def test_multigpu_sharded_tci_identical_to_single_gpu():
-    """world_size 2 over NCCL / NVLink peer stores (needs >= 2 visible GPUs; the 1-GPU box skips it)."""
-    import os
-    import subprocess
-    import sys
-
+def _ngpu():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+def test_bond_update_matches_separate_calls_and_oracle(T, oracle):
+    """tci_bond_update (Pi evaluation -> rrLU, one synchronisation) against tci_pi_eval + tci_rrlu and the oracle:
+    identical permutations, pivot errors, max|Pi| and factors (tensorci2.jl:529-551)."""
+    ld = [10] * 6
+    f, o = make_target(T, oracle, LORENTZ, [1.0], ld)
+    rng = np.random.default_rng(3)
+    I, J = rand_indexset(rng, ld[:3], 300), rand_indexset(rng, ld[3:], 200)
+    for leftorth in (True, False):
+        lu, mx = f.bond_update(I, J, maxrank=40, reltol=1e-14, abstol=1e-12, leftorthogonal=leftorth, want_factors=True)
+        dev, mx2 = f.batchevaluate_device(I, J, 0)
+        lu2 = T.rrlu(dev, maxrank=40, reltol=1e-14, abstol=1e-12, leftorthogonal=leftorth)
+        Pi, omx = o.pi_eval(I.tolist(), J.tolist(), 0, 0.0)
+        ref = oracle.rrlu(Pi, maxrank=40, reltol=1e-14, abstol=1e-12, leftorthogonal=leftorth)
+        assert mx == mx2 == omx
+        assert_lu_equal(lu, ref)
+        assert_lu_equal(lu2, ref)
+        luci = T.MatrixLUCI(lu)
+        rl = oracle.luci(Pi, maxrank=40, reltol=1e-14, abstol=1e-12, leftorthogonal=leftorth)
+        assert np.max(np.abs(luci.left() - rl.left)) <= RTOL * np.max(np.abs(rl.left))
+        assert np.max(np.abs(luci.right() - rl.right)) <= RTOL * np.max(np.abs(rl.right))
+    lu, mx = f.bond_update(I, J, maxrank=5)  # without factors: permutations only
+    assert lu.npivot == 5
+    with pytest.raises(RuntimeError, match="without factors"):
+        lu.L
+    with pytest.raises(ValueError, match="rows must not be empty"):
+        f.bond_update(I[:0], J)
+
+
+def test_fill_sitetensors_matches_per_site_path(T, oracle):
+    """tci_fill_sitetensors (all sites queued back to back, one synchronisation, cores left on the device) against
+    the per-site path (tci_pi_eval x2 + tci_rrlu + tci_lu_rdiv per site) and the oracle's site tensors."""
+    from tci_b200 import tensorci2 as M
+    ld = [4] * 8
+    f, o = make_target(T, oracle, Q2D, [0, 8], ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, tolerance=1e-9, maxbonddim=30, maxiter=4, rng=T.CounterRNG(2))
+    M.sweep2site(tci, f, 2, abstol=1e-9 * tci.maxsamplevalue, maxbonddim=30, fillsitetensors_=False)
+    mx0 = tci.maxsamplevalue
+    M.fillsitetensors(tci, f)
+    fused = [t.copy() for t in tci.sitetensors]
+    handle, mx1 = tci.device_tt, tci.maxsamplevalue
+    assert handle is not None
+    tci.maxsamplevalue = mx0
+    for b in range(len(ld)):
+        M.setsitetensor_fill(tci, f, b)
+    assert tci.maxsamplevalue == mx1
+    for a, b_ in zip(fused, tci.sitetensors):
+        assert a.shape == b_.shape and np.array_equal(a, b_)
+    # the device-resident copy is the same tensor train: evaluate it as a TT target
+    pts = rand_indexset(np.random.default_rng(5), ld, 64)
+    assert np.max(np.abs(handle.evaluate_points(pts) - T.evaluate_points(T.TensorTrain(fused), pts))) <= \
+        1e-12 * tci.maxsamplevalue
+    # error texts
+    bad = [s.copy() for s in tci.Jset]
+    bad[2] = bad[2][:-1]
+    with pytest.raises(RuntimeError, match="Pivot matrix at bond 3 is not square!"):
+        f.fill_sitetensors(tci.Iset, bad)
+    dupI = [s.copy() for s in tci.Iset]
+    dupJ = [s.copy() for s in tci.Jset]
+    if len(dupI[3]) >= 2:
+        dupI[3][1] = dupI[3][0]  # two equal rows: P at bond 3 is singular
+        with pytest.raises(RuntimeError, match="Pivot matrix at bond 3 is singular!"):
+            f.fill_sitetensors(dupI, dupJ)
+
+
+@pytest.mark.parametrize("name", ["config1", "config3_small", "config4_small"])
+def test_globalsearch_environment_mode_matches_ordered_chain(T, oracle, name):
+    """K7 mode 2 (prefix / suffix environments of the start points + one GEMM per site) against mode 1 (every probe
+    through the ordered chain, bit-identical to evaluate(tt, x)) and the oracle: identical pivots, errors within
+    1e-12 of the function scale (globalpivotfinder.jl:160-188)."""
+    if name == "config1":
+        kind, params, ld, kw = LORENTZ, [1.0], [10] * 8, dict(tolerance=1e-3, maxiter=2)
+    elif name == "config3_small":
+        kind, params, ld, kw = Q2D, [0, 10], [4] * 10, dict(tolerance=1e-3, maxbonddim=12, maxiter=2)
+    else:
+        kind, params, ld, kw = SEPCOS, sepcos_params(6), [64] * 6, dict(tolerance=1e-2, maxbonddim=6, maxiter=2)
+    f, o = make_target(T, oracle, kind, params, ld)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)
+    tt = T.TensorTrain(tci.sitetensors)
+    nsearch = 300
+    finder = T.DefaultGlobalPivotFinder(nsearch=nsearch, maxnglobalpivot=nsearch, tolmarginglobalsearch=1.0)
+    inp = T.GlobalPivotSearchInput(ld, tt, tci.maxsamplevalue, None, None)
+    abstol = 1e-6 * tci.maxsamplevalue
+    p1 = finder(inp, f, abstol, rng=T.CounterRNG(9), mode=1)
+    e1 = finder.last_errors.copy()
+    p2 = finder(inp, f, abstol, rng=T.CounterRNG(9), mode=2)
+    e2 = finder.last_errors.copy()
+    starts = T.CounterRNG(9).start_points(nsearch, ld)
+    piv, errs = oracle.globalsearch(o, tci.sitetensors, np.ascontiguousarray(starts.T), abstol=abstol, tolmargin=1.0,
+                                    maxn=nsearch)
+    assert len(p1) > 0
+    assert p1.tolist() == piv and np.array_equal(e1, errs)  # ordered chain: bit-identical to the oracle
+    assert p2.tolist() == p1.tolist()
+    assert np.max(np.abs(e2 - e1)) <= 1e-12 * tci.maxsamplevalue
+
+
+def test_two_contexts_on_two_devices_in_one_process(T, oracle):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a second context on another GPU of the same
+    process must run the 226 KB rrLU kernels and the DMMA GEMM too."""
+    if _ngpu() < 2:
         pytest.skip("needs two GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29577",
-                          os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
-    assert "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    A = lowrank_matrix(700, 600, 48, seed=21)
+    ref = oracle.rrlu(A, maxrank=48, reltol=1e-12)
+    B1, B2 = np.random.default_rng(1).standard_normal((300, 200)), np.random.default_rng(2).standard_normal((200, 150))
+    for dev in (0, 1):
+        ctx = T.Context(dev)
+        assert_lu_equal(T.rrlu(A, maxrank=48, reltol=1e-12, ctx=ctx), ref)
+        from tci_b200._lib import gemm
+        assert np.max(np.abs(gemm(B1, B2, ctx) - B1 @ B2)) <= 1e-12 * np.max(np.abs(B1 @ B2))
+
+
+def test_multigpu_context_sharded_stages_match_single_gpu(T, oracle, monkeypatch):
+    """tci_ctx_create(ngpu = 2): Pi evaluation (column blocks, peer stores into the owner's HBM), the MPO x MPO Pi by
+    row blocks with both environment chains sharded, and the global search by blocks of starts -- all inside the
+    library -- against the single-GPU results: analytic Pi bit-identical, contraction Pi to 1e-12, identical pivots;
+    a whole crossinterpolate2 on the 2-GPU context gives identical index sets."""
+    if _ngpu() < 2:
+        pytest.skip("needs two GPUs")
+    c1, c2 = T.Context(0), T.Context(devices=[0, 1])
+    assert c2.ngpu == 2
+    monkeypatch.setenv("TCI_SHARD_FORCE", "2")  # the cost model would keep these small cases on one GPU
+    ld = [10] * 6
+    rng = np.random.default_rng(0)
+    I, J = rand_indexset(rng, ld[:3], 333), rand_indexset(rng, ld[3:], 201)
+    for kind, params, l in ((LORENTZ, [1.0], ld), (SEPCOS, sepcos_params(6), [64] * 6)):
+        I, J = rand_indexset(rng, l[:3], 333), rand_indexset(rng, l[3:], 201)
+        f1, f2 = T.BuiltinTarget(kind, params, l, ctx=c1), T.BuiltinTarget(kind, params, l, ctx=c2)
+        l0 = c2.member_launches(1)
+        d1, m1 = f1.batchevaluate_device(I, J, 0)
+        d2, m2 = f2.batchevaluate_device(I, J, 0)
+        assert c2.member_launches(1) > l0  # the second GPU really took part
+        assert np.array_equal(d1.to_host(), d2.to_host()) and m1 == m2
+        lu1, mx1 = f1.bond_update(I, J, maxrank=30, want_factors=True)
+        lu2, mx2 = f2.bond_update(I, J, maxrank=30, want_factors=True)
+        assert mx1 == mx2 and np.array_equal(lu1.rowpermutation, lu2.rowpermutation)
+        assert np.array_equal(lu1.L, lu2.L) and np.array_equal(lu1.U, lu2.U)
+    # contraction target: row blocks
+    g = np.random.default_rng(5)
+    ns, D = 10, 12
+    bonds = [1] + [D] * (ns - 1) + [1]
+    A = [np.asfortranarray(g.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5) for i in range(ns)]
+    B = [np.asfortranarray(g.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5) for i in range(ns)]
+    m1 = T.Contraction(T.TensorTrain(A), T.TensorTrain(B), ctx=c1)
+    m2 = T.Contraction(T.TensorTrain(A), T.TensorTrain(B), ctx=c2)
+    Im, Jm = rand_indexset(g, [4] * 5, 150), rand_indexset(g, [4] * 5, 90)
+    P1, P2 = m1(Im, Jm, 0), m2(Im, Jm, 0)
+    assert np.max(np.abs(P1 - P2)) <= 1e-12 * np.max(np.abs(P1))
+    ref, _ = oracle.Target.mpo_pair(A, B).pi_eval(Im[:6].tolist(), Jm[:5].tolist(), 0, 0.0)
+    assert np.max(np.abs(P2[:6, :5] - np.asarray(ref).reshape((6, 5), order="F"))) <= RTOL * np.max(np.abs(P1))
+    # global search: blocks of starts, records gathered by NCCL
+    monkeypatch.delenv("TCI_SHARD_FORCE")
+    l4 = [64] * 6
+    f1, f2 = T.BuiltinTarget(SEPCOS, sepcos_params(6), l4, ctx=c1), T.BuiltinTarget(SEPCOS, sepcos_params(6), l4, ctx=c2)
+    tci, ranks, errors = T.crossinterpolate2(f1, l4, tolerance=1e-2, maxbonddim=6, maxiter=2, rng=T.CounterRNG(1))
+    tt = T.TensorTrain(tci.sitetensors)
+    finder = T.DefaultGlobalPivotFinder(nsearch=512, maxnglobalpivot=512, tolmarginglobalsearch=1.0)
+    inp = T.GlobalPivotSearchInput(l4, tt, tci.maxsamplevalue, None, None)
+    for mode in (1, 2):
+        pa = finder(inp, f1, 1e-7, rng=T.CounterRNG(9), mode=mode)
+        ea = finder.last_errors.copy()
+        l0 = c2.member_launches(1)
+        pb = finder(inp, f2, 1e-7, rng=T.CounterRNG(9), mode=mode)
+        assert c2.member_launches(1) > l0
+        assert len(pa) > 0 and pa.tolist() == pb.tolist() and np.array_equal(ea, finder.last_errors)
+    # whole runs on the 2-GPU context
+    monkeypatch.setenv("TCI_SHARD_FORCE", "2")
+    for kind, params, l, kw in ((LORENTZ, [1.0], [10] * 6, dict(tolerance=1e-8)),
+                                (Q2D, [0, 8], [4] * 8, dict(tolerance=1e-9, maxbonddim=40, maxiter=6))):
+        fa, fb = T.BuiltinTarget(kind, params, l, ctx=c1), T.BuiltinTarget(kind, params, l, ctx=c2)
+        ta, ra, ea = T.crossinterpolate2(fa, l, rng=T.CounterRNG(3), **kw)
+        tb, rb, eb = T.crossinterpolate2(fb, l, rng=T.CounterRNG(3), **kw)
+        assert ra == rb and ea == eb
+        assert all(np.array_equal(x, y) for x, y in zip(ta.Iset + ta.Jset, tb.Iset + tb.Jset))
+        assert all(np.array_equal(x, y) for x, y in zip(ta.sitetensors, tb.sitetensors))
 
 
 def test_config4_scale_pi_and_rrlu_vs_oracle_on_pivot_submatrix(T, oracle):
@@ -1295,6 +1470,60 @@ def test_config5_full_shape_mpo_properties(T):
     Je = T.kronecker_right(4, J19)
     Pi0 = f(Ie, Je, 0)
     assert np.max(np.abs(Pi0 - Pi2.reshape((64, 64), order="F"))) <= RTOL * np.max(np.abs(Pi0))
+
+
+def test_config5_full_shape_mpo_vs_oracle(T, oracle):
+    """BASELINE config 5 at its full shape (40 sites, bond dimension 256, site dimensions 2 x 2) against the ORACLE
+    (contraction.jl:112-207, 236-335 restated): an 8 x 8 block of (left, right) index pairs costs the oracle ~4e10
+    flop (~30 s).  The 8 rows / 8 columns are taken from NESTED index sets of 1024 entries, as a TCI run produces
+    them, so the same oracle block checks (i) tci_pi_eval on the 8 x 8 sets, (ii) separately evaluated environments +
+    tci_pi_from_envs, (iii) the 1024 x 1024 Pi over the nested sets, whose shared prefixes are evaluated once
+    (ChainPlan, csrc/mpo.cu), and (iv) the same Pi with prefix sharing switched off."""
+    import os
+    rng = np.random.default_rng(5)
+    ns, D = 40, 256
+    bonds = [1] + [D] * (ns - 1) + [1]
+    A = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(ns)]
+    B = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(ns)]
+    f = T.Contraction(T.TensorTrain(A), T.TensorTrain(B))
+    Sl = np.arange(1, 5, dtype=np.int64)[:, None]
+    Sr = Sl.copy()
+    for _ in range(18):
+        cl, cr = T.kronecker_left(Sl, 4), T.kronecker_right(4, Sr)
+        Sl = cl[np.sort(rng.choice(len(cl), min(256, len(cl)), replace=False))]
+        Sr = cr[np.sort(rng.choice(len(cr), min(256, len(cr)), replace=False))]
+    In, Jn = T.kronecker_left(Sl, 4), T.kronecker_right(4, Sr)
+    assert In.shape == (1024, 20) and Jn.shape == (1024, 20)
+    ri = np.sort(rng.choice(1024, 8, replace=False))
+    ci = np.sort(rng.choice(1024, 8, replace=False))
+    I8, J8 = np.ascontiguousarray(In[ri]), np.ascontiguousarray(Jn[ci])
+    o = oracle.Target.mpo_pair(A, B)
+    ref, omx = o.pi_eval(I8.tolist(), J8.tolist(), 0, 0.0)
+    ref = np.asarray(ref).reshape((8, 8), order="F")
+    scale = np.max(np.abs(ref))
+    assert scale > 0 and omx == scale
+    # (i) the direct call
+    Pi8 = f(I8, J8, 0)
+    assert np.max(np.abs(Pi8 - ref)) <= RTOL * scale
+    # (ii) environments + product
+    Dl = f.env_dim(0, 20)
+    lenv, renv = T.DeviceMatrix.empty(f.ctx, Dl, 8), T.DeviceMatrix.empty(f.ctx, Dl, 8)
+    f.env_eval_into(lenv, 0, 0, I8)
+    f.env_eval_into(renv, 0, 1, J8)
+    out = T.DeviceMatrix.empty(f.ctx, 8, 8)
+    mx = f.pi_from_envs(lenv, 0, 8, renv, 0, 8, out, 0)
+    assert np.max(np.abs(out.to_host() - ref)) <= RTOL * scale and abs(mx - scale) <= RTOL * scale
+    del lenv, renv, out
+    # (iii) nested sets, shared prefixes evaluated once; (iv) without prefix sharing
+    full = f(In, Jn, 0)
+    assert np.max(np.abs(full[np.ix_(ri, ci)] - ref)) <= RTOL * scale
+    os.environ["TCI_MPO_NO_DEDUP"] = "1"
+    try:
+        plain = f(In, Jn, 0)
+    finally:
+        del os.environ["TCI_MPO_NO_DEDUP"]
+    assert np.max(np.abs(plain[np.ix_(ri, ci)] - ref)) <= RTOL * scale
+    assert np.max(np.abs(plain - full)) <= RTOL * np.max(np.abs(plain))
 
 
 def test_rrlu_degenerate_shapes(T, oracle):

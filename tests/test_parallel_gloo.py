@@ -1,7 +1,9 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in parallel.py: column-block sharding
-of Pi with an all-gather, NaN-propagating max all-reduce, candidate gather + reference-order selection
-of the sharded global search, and the pivot broadcast.  The per-rank "local evaluator" is the CPU
-oracle here (checker role only); on the GPU box the same functions move device buffers over NCCL."""
+"""world_size-2 gloo tests (CPU) of the host-side logic of the sharded stages.  The sharding itself lives in the
+library (tci_ctx_create(ngpu, device_ids)); its two host-only pieces -- the partition (tci_shard_range) and the
+selection of the global search on gathered per-start records (tci_globalsearch_select) -- are exported by the C ABI and
+need no GPU.  Here two gloo ranks play the two GPUs: each evaluates ITS block (the CPU oracle is the per-rank
+evaluator, checker role only), the blocks are gathered the way the library gathers them (in-place all-gather of
+equal-sized blocks; disjoint row blocks into one buffer), and the assembled result must equal the unsharded one."""
 import os
 import socket
 
@@ -18,6 +20,23 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+def _gather_blocks(full, blk, rank):
+    """in-place all-gather of equal-sized blocks, as group_allgather does it (csrc/group.cu)"""
+    if blk == 0 or dist.get_world_size() == 1:
+        return
+    dist.all_gather_into_tensor(full, full[rank * blk:(rank + 1) * blk].clone())
+
+
+def _maxabs_allreduce(value):
+    """NaN-propagating max of |x|: integer max on the bit pattern (NaN sorts above Inf), what the library's
+    all-reduce(max) on the max|.| words does (csrc/pi_eval.cu)"""
+    bits = np.array([0x7FF8000000000000], dtype=np.int64) if value != value else \
+        np.array([abs(value)], dtype=np.float64).view(np.int64).copy()
+    t = torch.from_numpy(bits)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.numpy().view(np.float64)[0])
 
 
 def _worker(rank, world, port, q):
@@ -45,11 +64,11 @@ def _worker(rank, world, port, q):
         full = torch.zeros((blk * world, ldm), dtype=torch.float64)
         mine, mx = o.pi_eval(I.tolist(), J[lo:hi].tolist(), 0, 0.0)
         full[rank * blk:rank * blk + (hi - lo), :23] = torch.from_numpy(np.ascontiguousarray(mine.T))
-        P.gather_column_blocks(dist, torch, full, blk, rank)
+        _gather_blocks(full, blk, rank)
         got = full[:len(J), :23].numpy().T
         res["pi_equal"] = bool(np.array_equal(got, ref))
-        res["maxabs"] = P.maxabs_allreduce(dist, torch, mx, "cpu") == refmx
-        nanmax = P.maxabs_allreduce(dist, torch, float("nan") if rank == 1 else 1.0, "cpu")
+        res["maxabs"] = _maxabs_allreduce(mx) == refmx
+        nanmax = _maxabs_allreduce(float("nan") if rank == 1 else 1.0)
         res["nan"] = nanmax != nanmax
         # ---- sharded Pi: row blocks (the MPO x MPO partitioning), each rank's rows written at their offset ----
         rblk, rranges = P.row_blocks(len(I), world)
@@ -62,7 +81,7 @@ def _worker(rank, world, port, q):
             bmx = 0.0
         dist.all_reduce(part)  # stands in for the peer stores into the owner's buffer (disjoint row ranges)
         res["pi_rows_equal"] = bool(np.array_equal(part[:, :23].numpy().T, ref))
-        res["maxabs_rows"] = P.maxabs_allreduce(dist, torch, bmx, "cpu") == refmx
+        res["maxabs_rows"] = _maxabs_allreduce(bmx) == refmx
         # ---- contraction Pi sharded by rows with BOTH environment chains sharded (ShardedEvaluator shard="rows"):
         # right environments of the rank's column block -> all-gather -> left environments of its rows -> block
         # product at its row offset.  Environments from a numpy chain here (the device computes them on the GPU box).
@@ -91,7 +110,7 @@ def _worker(rank, world, port, q):
         rfull = torch.zeros((cblk * world, 8), dtype=torch.float64)  # (columns, padded D): one environment per row
         for jj in range(clo, chi):
             rfull[rank * cblk + (jj - clo), :D] = torch.from_numpy(renv(Jt[jj]))
-        P.gather_column_blocks(dist, torch, rfull, cblk, rank)
+        _gather_blocks(rfull, cblk, rank)
         R = rfull[:len(Jt), :D].numpy().T  # D x nJ on every rank
         rb, rr = P.row_blocks(len(It), world)
         rlo2, rhi2 = rr[rank]
@@ -108,19 +127,26 @@ def _worker(rank, world, port, q):
                                     normalizeerror=False)
         starts = orc.start_points(7, 1, 12, [2] * R)  # (n, nsearch)
         piv_ref, err_ref = orc.globalsearch(t, tci.sitetensors, starts, abstol=1e-9, tolmargin=1.0, maxn=5)
-        mine_idx = np.arange(rank, starts.shape[1], world)
-        cands = []
-        for s in mine_idx:  # one start at a time so that the accepted start index is known
-            pv, er = orc.globalsearch(t, tci.sitetensors, starts[:, [s]], abstol=1e-9, tolmargin=1.0, maxn=1)
-            if pv:
-                cands.append((int(s), pv[0], float(er[0])))
-        pts, es = P.select_global_pivots(P.allgather_candidates(dist, cands), 5)
-        res["gs_points"] = pts == piv_ref
-        res["gs_errs"] = bool(np.array_equal(np.array(es), err_ref))
-        # ---- pivot broadcast ----
-        pr = P.PivotResult(3, [4, 1, 2], [2, 3, 1], [1.0, 0.5, 0.25, 0.0]) if rank == 0 else None
-        pr = P.broadcast_pivots(dist, pr, 0)
-        res["bcast"] = pr.npivot == 3 and pr.rowindices.tolist() == [4, 1, 2] and pr.pivoterrors[-1] == 0.0
+        # contiguous blocks of the starts (tci_shard_range); every rank produces the per-start record (best error,
+        # probe index in the star) of ITS starts, the records are all-gathered in place, and the library's selection
+        # (tci_globalsearch_select) is replayed on them
+        nsearch = starts.shape[1]
+        blk, ranges = P.column_blocks(nsearch, world)
+        lo, hi = ranges[rank]
+        rec = torch.zeros((blk * world, 2), dtype=torch.float64)
+        off = np.concatenate([[0], np.cumsum([2] * R)])
+        for s in range(lo, hi):  # threshold -1: every start is accepted, so its best probe is reported
+            pv, er = orc.globalsearch(t, tci.sitetensors, starts[:, [s]], abstol=-1.0, tolmargin=1.0, maxn=1)
+            st = starts[:, s]
+            diff = [k for k in range(R) if pv[0][k] != st[k]]
+            p = diff[0] if diff else 0  # the star contains the start itself once per site: the first one wins
+            rec[s, 0] = float(er[0])
+            rec[s, 1] = float(off[p] + pv[0][p] - 1)
+        _gather_blocks(rec, blk, rank)
+        piv, es, sidx = P.select_global_pivots(rec[:nsearch, 0].numpy(), rec[:nsearch, 1].numpy().astype(np.int64),
+                                               starts.T, [2] * R, 1e-9, 5)
+        res["gs_points"] = piv.tolist() == piv_ref
+        res["gs_errs"] = bool(np.array_equal(es, err_ref))
         q.put((rank, res))
     except Exception as e:  # report instead of leaving the parent waiting on the queue
         import traceback
@@ -162,5 +188,9 @@ def test_column_blocks():
     assert row_blocks(10, 4) == (16, [(0, 10), (10, 10), (10, 10), (10, 10)])
     assert row_blocks(4096, 8) == (512, [(512 * r, 512 * (r + 1)) for r in range(8)])
     assert row_blocks(0, 2) == (0, [(0, 0), (0, 0)])
-    pts, es = select_global_pivots([(3, [1, 1], 0.3), (0, [2, 2], 0.1), (2, [1, 2], 0.2)], 2)
-    assert pts == [[2, 2], [1, 2]] and es == [0.1, 0.2]
+    starts = np.array([[1, 1], [2, 2], [1, 2], [2, 1]], dtype=np.int64)
+    # records (best error, probe index in the star of localdims [2, 2]): start 1 has no finite probe (index -1)
+    piv, es, sidx = select_global_pivots([0.3, 0.05, 0.2, 0.4], [3, -1, 0, 1], starts, [2, 2], 0.1, 2)
+    assert piv.tolist() == [[1, 2], [1, 2]] and es.tolist() == [0.3, 0.2] and sidx.tolist() == [0, 2]
+    piv, es, sidx = select_global_pivots([0.3, 0.05, 0.2, 0.4], [3, -1, 0, 1], starts, [2, 2], 0.25, 5)
+    assert piv.tolist() == [[1, 2], [2, 1]] and sidx.tolist() == [0, 3]  # probe 1 of start (2, 1) is x_1 = 2
