@@ -1,18 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the TCI2 two-site hot path on B200.
+"""bench.py -- benchmark of the TCI2 two-site hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Headline (BASELINE.json configs[1]): standalone full-pivot rrLU of a synthetic low-rank
-Float64 matrix, 8192 x 8192, maxrank 1024 (the largest single-GPU case of that config).
-A "step" is one rrlu(A; maxrank, reltol) of a fresh matrix that is already in HBM.
-`value` is GFLOP/s of the reference algorithm's flop count sum_k 2(m-k)(n-k).
-The per-bond rrLU does not shard (north_star: "stays on one GPU"), so with N > 1 every rank
-factorises its own replica (weak scaling, no data-path collective); the stages that do shard
-(Pi evaluation column blocks) are reported under "extra".
+Headline, the same at every N (so that the per-N values form one scaling series): BASELINE.json configs[4], the
+MPO x MPO contraction target at its full shape -- 40 sites, bond dimension 256, site dimensions 2 x 2, Float64 -- a
+"step" being one batched evaluation of the two-site Pi matrix at the middle bond with nL = nR = 1024 index-set entries
+(Contraction.batchevaluate, contraction.jl:236-335; M = 0).  `value` is FP64 GFLOP/s of the algorithmic flop count
+(one environment extension per DISTINCT partial index + the final (nL x 65536) x (65536 x nR) product).  This is the
+"contraction FP64 GFLOP/s" component of BASELINE's metric and the stage BASELINE names for row-block sharding, so at
+N > 1 it is a STRONG-scaling number: the same Pi, split over the N GPUs inside the library (tci_ctx_create(ngpu, ...):
+right environments of each GPU's column block, one ncclAllGather, left environments of its own rows, block product
+stored into the owner's HBM by the GEMM epilogue over NVLink).
 
-One JSON line is printed by rank 0.  --impl reference times the CPU oracle (the restatement
-of the reference's Julia path; Julia itself cannot run in this image) on host cores.
+The library's multi-GPU context is single-process (the reference's caller is one Julia process).  Under torchrun every
+rank initialises NCCL and joins the barriers and the max-over-ranks reduction of the contract, and rank 0 drives all N
+GPUs through ONE context; the other ranks' GPUs do their share of the work through rank 0's context.
+
+The other components of the metric are top-level blocks of the same JSON line (N = 1): `rrlu` (configs[1]: 8192^2,
+maxrank 1024, with its HBM roofline), `pi_eval`, `time_to_tol` (configs 1, 3, 4 and a rank-128 variant), `contraction`,
+`luci`, `globalsearch`, `fp64_peak`; at N > 1: `stages` (global search and Pi evaluation sharded, with the 1-GPU time of
+the same stage measured in the same run) and `sharded_parity`.
+
+--impl reference times the CPU restatement of the same step (oracle.ContractionBLAS: numpy / OpenBLAS with all host
+threads, as Julia's BLAS-backed `_contract` is; Julia itself cannot run in this image) on a bounded sample.
 """
 import argparse
 import json
@@ -27,9 +38,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SIZE, RANK = 8192, 1024
-CPU_SAMPLE = (4096, 256)  # bounded CPU sample: ~12 s on one core
-REF_SAMPLE = (2048, 128)  # per-step sample of the reference arm
+NSITES, DM, NL = 40, 256, 1024
+REF_SAMPLE = 8  # index-set entries per side of one reference-arm step
+METRIC = "contraction FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Mevals/s; rrLU GFLOP/s as top-level blocks)"
+WORKLOAD = ("MPO x MPO contraction target (contraction.jl), 40 sites, bond dim 256, site dims 2x2, Float64: batched "
+            "two-site Pi at the middle bond, nL = nR = 1024 (BASELINE configs[4])")
+RRLU_SIZE, RRLU_RANK = 8192, 1024
+
+
+# ----------------------------------------------------------------------------------------------- workload ----
+def mpo_cores(seed, nsites=NSITES, D=DM):
+    g = np.random.default_rng(seed)
+    bonds = [1] + [D] * (nsites - 1) + [1]
+    return [np.asfortranarray((g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(nsites)]
+
+
+def index_sets(n, seed=8):
+    g = np.random.default_rng(seed)
+    I = np.stack([g.integers(1, 5, n) for _ in range(NSITES // 2)], axis=1).astype(np.int64)
+    J = np.stack([g.integers(1, 5, n) for _ in range(NSITES // 2)], axis=1).astype(np.int64)
+    return I, J
+
+
+def chain_steps(S, right):
+    """Full-bond environment extensions a chain evaluates for the index set S: one per DISTINCT partial index
+    (prefixes of the left set, suffixes of the right set), levels 2..n (level 1 starts from the bond of dimension 1)."""
+    n = S.shape[1]
+    return sum(len(np.unique(S[:, n - k:] if right else S[:, :k], axis=0)) for k in range(2, n + 1))
+
+
+EXT_FLOP = 2.0 * DM * DM * 2 * DM + 2.0 * DM * 2 * DM * DM  # one environment extension (contraction.jl:103-109)
+
+
+def pi_flops(I, J):
+    return (chain_steps(I, False) + chain_steps(J, True)) * EXT_FLOP + 2.0 * len(I) * DM * DM * len(J)
 
 
 def rrlu_flops(m, n, r):
@@ -37,9 +79,7 @@ def rrlu_flops(m, n, r):
 
 
 def rrlu_bytes(m, n, r):
-    """Algorithmic HBM bytes of one factorisation when the matrix is not on chip:
-    8mn for the first arg-max scan + 16 (m-k)(n-k) for every trailing update that is needed
-    (the update after the last pivot never reaches L or U and is skipped)."""
+    """SURVEY 8d model: 8mn for the first arg-max scan + 16 (m-k)(n-k) per trailing update that is needed."""
     return float(8 * m * n + sum(16 * (m - k) * (n - k) for k in range(1, r)))
 
 
@@ -72,6 +112,12 @@ def peaks():
             return json.load(f)["hbm_gbs"], "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def sepcos_params(n=12, seed=4, nterms=4):
+    g = np.random.default_rng(seed)
+    return np.concatenate([[nterms], g.integers(1, 1025, n) / 256.0, g.integers(-512, 513, nterms) / 1024.0,
+                           (g.integers(-1024, 1025, (nterms, n)) / 32.0).flatten()])
 
 
 class ClockSampler(threading.Thread):
@@ -112,44 +158,353 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args):
-    """Reference arm: the CPU restatement of matrixlu.jl (single thread, as the Julia loops are)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------- reference arm ----
+def cpu_contraction_sample(steps, warmup, threads=None):
+    """The same step on the CPU: oracle.ContractionBLAS (numpy / OpenBLAS restatement of contraction.jl:71-176,
+    236-335, Dict memo included), a fresh object per step (cold memo, as every GPU step is), REF_SAMPLE entries per
+    side of the same index sets.  Returns (GFLOP/s, seconds per step, threads, sample text)."""
+    import threadpoolctl
     from oracle import oracle as orc
-    orc.build()
-    m, r = REF_SAMPLE
-    A = lowrank_host(m, m, r, 2)
-    for _ in range(max(1, min(args.warmup, 1))):
-        orc.rrlu(A, maxrank=r, reltol=1e-12)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lu = orc.rrlu(A, maxrank=r, reltol=1e-12)
-    dt = time.perf_counter() - t0
-    assert lu.npivot == r
-    val = args.steps * rrlu_flops(m, m, r) / dt / 1e9
-    sample = f"rrlu {m}x{m} maxrank {r} per step (same generator as the {SIZE}x{SIZE} r={RANK} workload)"
-    out = {"metric": "rrLU FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Mevals/s; contraction in extra)",
-           "value": val, "unit": "GFLOP/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"rrlu standalone, synthetic low-rank Float64 {SIZE}x{SIZE}, maxrank {RANK}, "
-                                  "reltol 1e-12 (BASELINE configs[1])", "sample": sample},
-           "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
+    A, B = mpo_cores(5), mpo_cores(6)
+    I, J = index_sets(NL)
+    I, J = I[:REF_SAMPLE], J[:REF_SAMPLE]
+    fl = pi_flops(I, J)
+    nthreads = threads or (os.cpu_count() or 1)
+    with threadpoolctl.threadpool_limits(limits=nthreads, user_api="blas"):
+        for _ in range(max(1, min(warmup, 2))):
+            orc.ContractionBLAS(A, B).batchevaluate0(I.tolist(), J.tolist())
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = orc.ContractionBLAS(A, B).batchevaluate0(I.tolist(), J.tolist())
+        dt = (time.perf_counter() - t0) / steps
+    info = [d for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
+    blas = f"{info[0].get('internal_api')} {info[0].get('version')}" if info else "blas"
+    sample = (f"Pi {REF_SAMPLE} x {REF_SAMPLE} of the same workload per step ({chain_steps(I, False) + chain_steps(J, True)} "
+              f"environment extensions at bond 256 + final product), numpy/{blas}, {nthreads} thread(s), cold memo per step")
+    return fl / dt / 1e9, dt, nthreads, sample, res
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    val, dt, nthreads, sample, _ = cpu_contraction_sample(args.steps, args.warmup)
+    out = {"metric": METRIC, "value": val, "unit": "GFLOP/s", "impl": "reference", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": nthreads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
 
 
+# -------------------------------------------------------------------------------------------------- helpers ----
+def timed_calls(torch, stream, fn, reps, warm=1):
+    """CUDA-event time per call of fn() on the library's stream (the library synchronises inside every call)."""
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def total_launches(ctx):
+    return sum(ctx.member_launches(k) for k in range(ctx.ngpu))
+
+
+def block_rrlu(T, ctx, torch, stream, K):
+    """BASELINE configs[1]: rrLU 8192 x 8192, maxrank 1024, a fresh matrix per step already in HBM (537 MB > L2)."""
+    m = n = RRLU_SIZE
+    r = RRLU_RANK
+    p, q = factors(m, n, r, 2)
+    Ad = (torch.from_numpy(p).cuda() @ torch.from_numpy(q).cuda()).t().contiguous()
+    A_host_t = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
+    A_host_t.copy_(Ad)
+    A_host = A_host_t.numpy().T
+    del Ad
+    torch.cuda.empty_cache()
+    W = 2
+    mats = [T.DeviceMatrix.from_host(ctx, A_host) for _ in range(K + W)]
+    for i in range(W):
+        T.rrlu(mats[i], maxrank=r, reltol=1e-12)
+    ctx.timers(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    npiv = 0
+    for i in range(W, W + K):
+        lu = T.rrlu(mats[i], maxrank=r, reltol=1e-12)
+        npiv = lu.npivot
+        del lu
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    kernel_ms = ctx.timers(reset=True)["rrlu_kernel"] / K
+    del mats
+    assert npiv == r
+    flops = rrlu_flops(m, n, r)
+    peak, which = peaks()
+    model = rrlu_bytes_deferred(m, n, r)
+    # end to end: host buffers through the C ABI, upload of step k+1 overlapping the factorisation of step k
+    L_pin = torch.empty((r, m), dtype=torch.float64, pin_memory=True).numpy().T
+    U_pin = torch.empty((n, r), dtype=torch.float64, pin_memory=True).numpy().T
+    t0 = time.perf_counter()
+    nxt = T.DeviceMatrix.from_host_async(ctx, A_host)
+    for k in range(K):
+        cur = nxt
+        nxt = T.DeviceMatrix.from_host_async(ctx, A_host) if k + 1 < K else None
+        lu = T.rrlu(cur, maxrank=r, reltol=1e-12)
+        lu.fetch_into(L_pin, U_pin)
+        del lu, cur
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / K
+    return {"workload": f"rrlu standalone, synthetic low-rank Float64 {m}x{n}, maxrank {r}, reltol 1e-12 (BASELINE "
+                        "configs[1]); exact mode, bit-identical to the oracle (tests/test_gpu_parity.py)",
+            "gflops": flops / (ms * 1e-3) / 1e9, "ms_per_step": ms, "steps": K,
+            "e2e": {"gflops": flops / e2e_s / 1e9, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(8 * m * n),
+                    "d2h_bytes_per_step": int(8 * (m * r + r * n) + 8 * (m + n) + 8 * (r + 1))},
+            "roofline": {"bound": "hbm", "kernel": "k_rrlu_lazy<exact, left, 4>", "kernel_ms": kernel_ms,
+                         "achieved": model / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": model / (kernel_ms * 1e-3) / 1e9 / peak, "peak_source": which,
+                         "algorithmic_bytes": model,
+                         "bytes_model": "deferred updates: 8 B per trailing element per pivot + 8 B at every 4th pivot",
+                         "traffic": RRLU_DRAM_TRAFFIC.get((m, n, r)),
+                         "traffic_source": "profiles/r1_rrlu_lazy_8192_1024_dram.csv (ncu dram__bytes, one launch; "
+                                           "the kernel is unchanged since)",
+                         "survey_model_bytes": rrlu_bytes(m, n, r),
+                         "survey_model_frac": rrlu_bytes(m, n, r) / (kernel_ms * 1e-3) / 1e9 / peak,
+                         "fp64_gflops": flops / (kernel_ms * 1e-3) / 1e9}}
+
+
+# DRAM bytes of one k_rrlu_lazy launch measured under ncu (profiles/r1_rrlu_lazy_8192_1024_dram.csv)
+RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 445872222720 + 130370041856}
+
+
+def block_rrlu_same_size(T, orc):
+    """rrLU at sizes the CPU oracle also runs, both arms on the SAME matrix: pivots must be identical."""
+    out = {}
+    for (m, r, cpu) in ((2048, 128, True), (4096, 256, True)):
+        A = lowrank_host(m, m, r, 2)
+        T.rrlu(A, maxrank=r, reltol=1e-12)
+        ctx = T.default_context()
+        ctx.timers(reset=True)
+        lu = T.rrlu(A, maxrank=r, reltol=1e-12)
+        kms = ctx.timers(reset=True)["rrlu_kernel"]
+        ent = {"gpu_gflops": rrlu_flops(m, m, r) / (kms * 1e-3) / 1e9, "gpu_kernel_ms": kms}
+        if cpu:
+            t0 = time.perf_counter()
+            ref = orc.rrlu(A, maxrank=r, reltol=1e-12)
+            dt = time.perf_counter() - t0
+            ent.update({"cpu_gflops": rrlu_flops(m, m, r) / dt / 1e9, "cpu_s": dt, "cpu_cores": 1,
+                        "pivots_identical": bool(np.array_equal(lu.rowpermutation, ref.rowpermutation) and
+                                                 np.array_equal(lu.colpermutation, ref.colpermutation))})
+        out[f"{m}x{m}_r{r}"] = ent
+    return out
+
+
+def block_pi_eval(T, ctx):
+    out = {}
+    rng = np.random.default_rng(7)
+    ld = [64] * 12
+    nI = nJ = 16384
+    I = np.stack([rng.integers(1, 65, nI) for _ in range(6)], axis=1).astype(np.int64)
+    J = np.stack([rng.integers(1, 65, nJ) for _ in range(6)], axis=1).astype(np.int64)
+    for name, kind, params in (("lorentz", T.LORENTZ, [1.0]), ("sepcos_config4", T.SEPCOS, sepcos_params())):
+        f = T.BuiltinTarget(kind, params, ld, ctx=ctx)
+        for _ in range(3):
+            dev, mx = f.batchevaluate_device(I, J, 0)
+            del dev
+        ctx.timers(reset=True)
+        reps = 5
+        for _ in range(reps):
+            dev, mx = f.batchevaluate_device(I, J, 0)
+            del dev
+        ms = ctx.timers(reset=True)["pi_eval"] / reps
+        ev = nI * nJ
+        out[name] = {"mevals_per_s": ev / (ms * 1e-3) / 1e6, "ms": ms, "shape": [nI, nJ],
+                     "hbm_gbs": 8 * ev / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8 * ev / (ms * 1e-3) / 1e9 / peaks()[0],
+                     "bound": "HBM write, 8 B per evaluation" if name == "lorentz" else "FP64 pipe (4 cos per evaluation)"}
+    return out
+
+
+def block_time_to_tol(T, orc, with_cpu=True):
+    """crossinterpolate2 wall time to tolerance through the host mirror + C ABI; the oracle on one host core beside
+    it, with the pivots compared (ranks per iteration and every Iset / Jset identical)."""
+    out = {}
+    cases = [("config1", T.LORENTZ, [1.0], [10] * 8, dict(tolerance=1e-8), True),
+             ("config3", T.QUANTICS2D, [0, 20], [4] * 20, dict(tolerance=1e-10, maxbonddim=256), True),
+             ("config4", T.SEPCOS, sepcos_params(), [64] * 12, dict(tolerance=1e-12, maxbonddim=512), True)]
+    for name, kind, params, ld, kw, cpu in cases:
+        f = T.BuiltinTarget(kind, params, ld)
+        T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)  # warm-up (pool growth, kernel attributes)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            tci, ranks, errors = T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        ent = {"time_to_tol_s": best, "rank": int(ranks[-1]), "iterations": len(ranks), "error": float(errors[-1])}
+        if cpu and with_cpu:
+            o = orc.Target.builtin(kind, params, ld)
+            t0 = time.perf_counter()
+            res = orc.crossinterpolate2(o, ld, seed=1, **kw)
+            ent["cpu_oracle_s"] = time.perf_counter() - t0
+            ent["cpu_cores"] = 1
+            ent["pivots_identical_to_oracle"] = bool(
+                [int(r) for r in ranks] == res.ranks.tolist() and
+                all([tuple(x) for x in tci.Iset[b].tolist()] == res.Iset[b] and
+                    [tuple(x) for x in tci.Jset[b].tolist()] == res.Jset[b] for b in range(len(ld))))
+        out[name] = ent
+    # a variant of config 4 whose rank is really large: the target is a random tensor train of bond dimension 128
+    # (12 sites, d = 64), numerically of rank exactly 128 -- Pi up to 8192 x 8192 at every middle bond, i.e. the
+    # deferred-update rrLU kernel and the GEMM-shaped TT Pi evaluation inside an end-to-end run
+    try:
+        g = np.random.default_rng(12)
+        bonds = [1] + [128] * 11 + [1]
+        cores = [np.asfortranarray((g.random((bonds[i], 64, bonds[i + 1])) * 2 - 1) / np.sqrt(bonds[i] * 8.0))
+                 for i in range(12)]
+        ft = T.TTCache(T.TensorTrain(cores))
+        t0 = time.perf_counter()
+        tci, ranks, errors = T.crossinterpolate2(ft, [64] * 12, tolerance=1e-10, maxbonddim=128, maxiter=4,
+                                                 rng=T.CounterRNG(1))
+        dt = time.perf_counter() - t0
+        pts = np.stack([g.integers(1, 65, 256) for _ in range(12)], axis=1).astype(np.int64)
+        dev = np.max(np.abs(ft.evaluate_points(pts) - T.evaluate_points(T.TensorTrain(tci.sitetensors), pts)))
+        out["config4_rank128_tt_target"] = {"time_to_tol_s": dt, "rank": int(ranks[-1]), "iterations": len(ranks),
+                                            "error": float(errors[-1]),
+                                            "sampled_error_rel": float(dev / tci.maxsamplevalue),
+                                            "largest_pi": max(a * b for (_, a, b, _) in tci.trace)}
+    except Exception as e:
+        out["config4_rank128_tt_target"] = {"error": str(e)[:300]}
+    return out
+
+
+def block_contraction(T, ctx, torch, fp64_peak_tf):
+    from tci_b200 import _lib
+    import ctypes as C
+    out = {}
+    rng = np.random.default_rng(7)
+    for N in (4096,):
+        A = np.asfortranarray(rng.standard_normal((N, N)))
+        B = np.asfortranarray(rng.standard_normal((N, N)))
+        Cm = np.zeros((N, N), order="F")
+        for _ in range(2):
+            ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(Cm)))
+        ctx.timers(reset=True)
+        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(Cm)))
+        ms = ctx.timers(reset=True)["gemm"]
+        a = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        b = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            c = a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            c = a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"dgemm_{N}"] = {"tflops": 2.0 * N ** 3 / (ms * 1e-3) / 1e12, "ms": ms,
+                             "kernel": "k_dgemm_mma_async (DMMA m8n8k4)",
+                             "cublas_tflops": 5 * 2.0 * N ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                             "frac_of_fp64_peak": 2.0 * N ** 3 / (ms * 1e-3) / 1e12 / fp64_peak_tf}
+        del a, b, c
+    # one zip-up site step (contraction.jl:455-464) at chi = Da = Db = 256
+    chi = Da = Db = 256
+    Rz = np.asfortranarray(rng.standard_normal((chi, Da, Db)))
+    Az = np.asfortranarray(rng.standard_normal((Da, 2, 2, Da)))
+    Bz = np.asfortranarray(rng.standard_normal((Db, 2, 2, Db)))
+    for it in range(2):
+        h = C.c_void_p()
+        ctx.timers(reset=True)
+        ctx.check(_lib.lib().tci_contract_zipup_site(ctx.h, _lib.pf(Rz), chi, Da, Db, _lib.pf(Az), 2, 2, Da,
+                                                     _lib.pf(Bz), 2, Db, None, C.byref(h)))
+        tmz = ctx.timers(reset=True)
+        Cz = _lib.DeviceMatrix(ctx, h)
+        del Cz
+    flz = 2.0 * chi * Da * Db * 4 * Da + 2.0 * (chi * 2) * (Db * 2) * (2 * Da * Db)
+    out["zipup_site_config5"] = {"tflops": flz / (tmz["gemm"] * 1e-3) / 1e12, "ms": tmz["gemm"],
+                                 "frac_of_fp64_peak": flz / (tmz["gemm"] * 1e-3) / 1e12 / fp64_peak_tf,
+                                 "shape": "chi=Da=Db=256, site dims 2x2x2, C 1024 x 65536"}
+    return out
+
+
+def block_luci(T, ctx, fp64_peak_tf):
+    """K3: MatrixLUCI left / right (matrixluci.jl:40-84) on a 16384 x 16384 rank-512 factorisation."""
+    m = n = 16384
+    r = 512
+    import torch
+    p, q = factors(m, n, r, 3)
+    Ad = (torch.from_numpy(p).cuda() @ torch.from_numpy(q).cuda()).t().contiguous()
+    torch.cuda.synchronize()
+    out = {}
+    for leftorth in (True, False):
+        A2 = Ad.clone()
+        view = T.DeviceMatrix.wrap(ctx, A2.data_ptr(), m, n, m)
+        luci = T.MatrixLUCI(view, maxrank=r, reltol=1e-12, leftorthogonal=leftorth)
+        for side in ("left", "right"):
+            getattr(luci, side)(device=True)
+            ctx.timers(reset=True)
+            getattr(luci, side)(device=True)
+            ms = ctx.timers(reset=True)["luci"]
+            trsm = (side == "left") == leftorth
+            fl = ((m if side == "left" else n) - r) * r * r if trsm else 2.0 * r * r * (m if side == "left" else n)
+            out[f"{side}_leftorth{int(leftorth)}"] = {"ms": ms, "tflops": fl / (ms * 1e-3) / 1e12,
+                                                      "frac_of_fp64_peak": fl / (ms * 1e-3) / 1e12 / fp64_peak_tf,
+                                                      "op": "unit-triangular TRSM" if trsm else "triangular product (GEMM)"}
+        del luci, view, A2
+    out["shape"] = f"{m} x {n}, r = {r}"
+    return out
+
+
+def gsearch_setup(T, ctx):
+    ld, chi, nsearch = [64] * 12, 128, 2048
+    f = T.BuiltinTarget(T.SEPCOS, sepcos_params(), ld, ctx=ctx)
+    bonds = [1] + [chi] * 11 + [1]
+    g9 = np.random.default_rng(9)
+    tt = T.TensorTrain([np.asfortranarray((g9.random((bonds[i], 64, bonds[i + 1])) * 2 - 1) / np.sqrt(bonds[i]))
+                        for i in range(12)])
+    tt.device_handle = T.TTCache(tt, ctx=ctx)  # device resident, as after tci_fill_sitetensors
+    finder = T.DefaultGlobalPivotFinder(nsearch=nsearch, maxnglobalpivot=5)
+    inp = T.GlobalPivotSearchInput(ld, tt, 1.0, None, None)
+    return f, finder, inp, nsearch * sum(ld)
+
+
+def block_globalsearch(T, ctx, mode=0):
+    """Default global pivot finder (globalpivotfinder.jl:143-195) at config-4 shape: 12 sites d = 64, current TT of
+    bond dimension 128, 2048 starts = 1.57 M star probes |f - tt|."""
+    f, finder, inp, probes = gsearch_setup(T, ctx)
+    res = {}
+    for label, md in (("environments", 2), ("ordered_chain", 1)):
+        found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=md)
+        ctx.timers(reset=True)
+        t0 = time.perf_counter()
+        reps = 3 if md == 2 else 1
+        for _ in range(reps):
+            found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=md)
+        dt = (time.perf_counter() - t0) / reps
+        res[label] = {"ms": dt * 1e3, "library_ms": ctx.timers(reset=True)["globalsearch"] / reps,
+                      "mprobes_per_s": probes / dt / 1e6, "found": [p.tolist() for p in found],
+                      "errors": finder.last_errors.tolist()}
+    same = res["environments"]["found"] == res["ordered_chain"]["found"]
+    for v in res.values():
+        v["found"] = len(v["found"])
+        v.pop("errors")
+    return {"shape": "12 sites d=64, TT bond 128, 2048 starts, 1572864 probes", "probes": probes,
+            "environments": res["environments"], "ordered_chain": res["ordered_chain"],
+            "pivots_identical_between_modes": same}
+
+
+# ---------------------------------------------------------------------------------------------------- main ----
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--size", type=int, default=SIZE)
-    ap.add_argument("--rank", type=int, default=RANK)
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -164,536 +519,207 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import tci_b200 as T
-    ctx = T.default_context()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-
-    m = n = args.size
-    r = args.rank
     K, W = args.steps, max(args.warmup, 3)
-    # synthetic input: p (m x r) * q (r x n) formed on the device in FP64 (input generation, untimed)
-    p, q = factors(m, n, r, 2 + rank)
-    Ad = (torch.from_numpy(p).cuda() @ torch.from_numpy(q).cuda()).t().contiguous()  # column-major m x n
-    torch.cuda.synchronize()
-    A_host_t = torch.empty((n, m), dtype=torch.float64, pin_memory=True)
-    A_host_t.copy_(Ad)
-    A_host = A_host_t.numpy().T  # Fortran-ordered view of pinned memory
-    del Ad
-    torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident leg: K fresh matrices already in HBM -----------------
-    mats = [T.DeviceMatrix.from_host(ctx, A_host) for _ in range(K + W)]
-    for i in range(W):
-        lu = T.rrlu(mats[i], maxrank=r, reltol=1e-12)
-        del lu
-    ctx.timers(reset=True)
-    launches0 = ctx.launches
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    out = None
+    if rank == 0:
+        import tci_b200 as T
+        from tci_b200 import _lib
+        ctx = T.Context(devices=list(range(world))) if world > 1 else T.default_context()
+        _lib.set_default_context(ctx)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+        fm = T.Contraction(T.TensorTrain(mpo_cores(5)), T.TensorTrain(mpo_cores(6)), ctx=ctx)
+        I, J = index_sets(NL)
+        flops = pi_flops(I, J)
+        for _ in range(W):
+            dev, mx = fm.batchevaluate_device(I, J, 0)
+            del dev
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    npiv = 0
-    for i in range(W, W + K):
-        lu = T.rrlu(mats[i], maxrank=r, reltol=1e-12)
-        npiv = lu.npivot
-        del lu
-    e1.record(stream)
+    ms = 0.0
+    if rank == 0:
+        # ---------------- device-resident leg: the MPO cores are in HBM, Pi stays in HBM ----------------
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        ctx.timers(reset=True)
+        l0 = total_launches(ctx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            dev, mx = fm.batchevaluate_device(I, J, 0)
+            del dev
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.finish()
+        launches = total_launches(ctx) - l0
+        tm = ctx.timers(reset=True)
     barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.finish()
-    launches = ctx.launches - launches0
-    tm = ctx.timers(reset=True)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    assert npiv == r, (npiv, r)
-    flops = rrlu_flops(m, n, r)
-    value = world * K * flops / (ms * 1e-3) / 1e9
-    kernel_ms = tm["rrlu_kernel"] / K
-    peak, which = peaks()
-    deferred = m * n >= LAZY_MIN
-    model_bytes = rrlu_bytes_deferred(m, n, r) if deferred else rrlu_bytes(m, n, r)
-    achieved = model_bytes / (kernel_ms * 1e-3) / 1e9
-    del mats
-
-    # ---------------- end to end: host buffers through the C ABI, copies inside -------------
-    # Every step uploads its matrix from page-locked host memory and brings L, U and the permutations back to
-    # page-locked host arrays.  The upload of step k+1 is enqueued on the library's copy stream before step k is
-    # factorised (tci_dmat_create_async), the way a host driver would double-buffer its Pi matrices.
-    L_pin = torch.empty((r, m), dtype=torch.float64, pin_memory=True).numpy().T
-    U_pin = torch.empty((n, r), dtype=torch.float64, pin_memory=True).numpy().T
-    barrier()
-    t0 = time.perf_counter()
-    nxt = T.DeviceMatrix.from_host_async(ctx, A_host)
-    for k in range(K):
-        cur = nxt
-        nxt = T.DeviceMatrix.from_host_async(ctx, A_host) if k + 1 < K else None
-        lu = T.rrlu(cur, maxrank=r, reltol=1e-12)
-        lu.fetch_into(L_pin, U_pin)
-        del lu, cur
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * K * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(8 * m * n),
-           "d2h_bytes_per_step": int(8 * (m * r + r * n) + 8 * (m + n) + 8 * (r + 1)),
-           "ms_per_step": e2e_s / K * 1e3,
-           "pipelining": "upload of step k+1 overlaps the factorisation of step k (copy stream); pinned in/out"}
-
-    extra = {}
-    if not args.no_extra:
-        extra = run_extra(T, ctx, torch, dist, rank, world, stream)
-
-    cpu = None
-    if rank == 0 and not args.no_cpu:
-        from oracle import oracle as orc
-        orc.build()
-        cm, cr = CPU_SAMPLE
-        Ac = lowrank_host(cm, cm, cr, 2)
-        t0 = time.perf_counter()
-        ref = orc.rrlu(Ac, maxrank=cr, reltol=1e-12)
-        dt = time.perf_counter() - t0
-        cpu = {"value": rrlu_flops(cm, cm, cr) / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-               "sample": f"one rrlu {cm}x{cm} maxrank {cr} (same generator), {dt:.1f} s on one host core; "
-                         f"the reference's loops are single threaded (matrixlu.jl)"}
-        # the same sample on the GPU must give the same pivots
-        lu = T.rrlu(Ac, maxrank=cr, reltol=1e-12)
-        cpu["pivots_identical_to_gpu"] = bool(np.array_equal(lu.rowpermutation, ref.rowpermutation) and
-                                              np.array_equal(lu.colpermutation, ref.colpermutation))
     if rank == 0:
-        out = {"metric": "rrLU FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Mevals/s; contraction in extra)",
-               "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        value = K * flops / (ms * 1e-3) / 1e9
+        # ---------------- end to end: index sets from host memory, Pi back in page-locked host memory --------
+        Pi_pin = torch.empty((NL, NL), dtype=torch.float64, pin_memory=True).numpy().T
+        t0 = time.perf_counter()
+        for _ in range(K):
+            dev, mx = fm.batchevaluate_device(I, J, 0)
+            ctx.check(_lib.lib().tci_dmat_fetch(dev.h, _lib.pf(Pi_pin)))
+            del dev
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": K * flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(I.nbytes + J.nbytes),
+               "d2h_bytes_per_step": int(8 * NL * NL + 8), "ms_per_step": e2e_s / K * 1e3,
+               "note": "tci_pi_eval with host index sets + tci_dmat_fetch of Pi into page-locked host memory"}
+        # ---------------- FP64 denominators and the roofline of the dominant kernel (DMMA GEMM) ------------
+        dfma, dmma = ctx.fp64_peak()
+        a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        c = a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            c = a @ b
+            f1.record()
+            torch.cuda.synchronize()
+            best = min(best, f0.elapsed_time(f1))
+        cublas_tf = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b, c
+        torch.cuda.empty_cache()
+        fp64_peak = {"dfma_tflops": dfma, "dmma_tflops": dmma, "cublas_dgemm_8192_tflops": cublas_tf,
+                     "how": "register-resident DFMA / mma.sync.m8n8k4.f64 loops (tci_fp64_peak) and torch.matmul "
+                            "float64 8192^3 (cuBLAS, best of 3) measured in this run; MEASURED_PEAKS.json carries no "
+                            "FP64 figure"}
+        peak_tf = max(dmma, cublas_tf)
+        gemm_ms = (tm["pi_eval"]) / K
+        roofline = {"bound": "tensor", "kernel": "k_dgemm_mma_async<128,128> (FP64 DMMA; tcgen05 has no FP64 kind)",
+                    "achieved": flops / (gemm_ms * 1e-3) / 1e12 / (world if world > 1 else 1), "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak_tf / (world if world > 1 else 1),
+                    "peak_source": "max(DMMA loop, cuBLAS DGEMM 8192^3) measured in this run (no FP64 figure in "
+                                   "MEASURED_PEAKS.json)",
+                    "kernel_ms_per_step": gemm_ms, "algorithmic_flops": flops, "traffic": None,
+                    "note": "per GPU; the step is ~150 batched gather-GEMM launches of the same kernel (environment "
+                            "chains) + the final product; kernel time = the library's Pi stage timer (CUDA events)"}
+        out = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"rrlu standalone, synthetic low-rank Float64 {m}x{n}, maxrank {r}, "
-                                      "reltol 1e-12 (BASELINE configs[1])",
-                          "l2": "input 537 MB per step exceeds the 126 MB L2; every step uses a fresh matrix",
-                          "parallelism": "replicas only (rrLU does not shard)" if world > 1 else "single GPU",
-                          "exact_mode": True},
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": RRLU_DRAM_TRAFFIC.get((m, n, r)),
-                            "traffic_source": "profiles/r1_rrlu_lazy_8192_1024_dram.csv (ncu dram__bytes_read.sum + "
-                                              "dram__bytes_write.sum, one launch)", "peak_source": which,
-                            "kernel": "k_rrlu_lazy<exact, left, 4>" if deferred else "k_rrlu<true>",
-                            "kernel_ms": kernel_ms, "algorithmic_bytes": model_bytes,
-                            "bytes_model": ("deferred updates: 8 B per trailing element per pivot + 8 B at every 4th "
-                                            "pivot (DESIGN.md 4)") if deferred else "16 B per trailing element per pivot",
-                            # the per-pivot read+write model of SURVEY 8d (what the in-place kernel and the
-                            # reference's loops move); > 1 means fewer bytes were moved than that model needs
-                            "survey_model_bytes": rrlu_bytes(m, n, r),
-                            "survey_model_frac": rrlu_bytes(m, n, r) / (kernel_ms * 1e-3) / 1e9 / peak,
-                            "fp64_gflops_kernel": flops / (kernel_ms * 1e-3) / 1e9},
-               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-               "stage_ms_per_step": {k: v / K for k, v in tm.items()}, "extra": extra}
+               "config": {"workload": WORKLOAD,
+                          "l2": "inputs exceed L2: MPO cores 168 MB + 2 x 512 MB of environments per step (L2 126 MB)",
+                          "parallelism": (f"one context over {world} GPUs (single process, tci_ctx_create(ngpu)): row "
+                                          "blocks, right environments all-gathered by NCCL, block products stored into "
+                                          "the owner's HBM; driven by rank 0, the other torchrun ranks join the barriers")
+                          if world > 1 else "single GPU", "index_sets": "random, seed 8"},
+               "roofline": roofline, "fp64_peak": fp64_peak, "e2e": e2e, "gpu_launches": int(launches),
+               "clocks": clocks, "stage_ms_per_step": {k: v / K for k, v in tm.items()}}
+        orc = None
+        if not args.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+        if world == 1 and not args.no_extra:
+            for name, fn in (("rrlu", lambda: block_rrlu(T, ctx, torch, stream, 5)),
+                             ("rrlu_same_size", lambda: block_rrlu_same_size(T, orc) if orc else None),
+                             ("pi_eval", lambda: block_pi_eval(T, ctx)),
+                             ("time_to_tol", lambda: block_time_to_tol(T, orc, orc is not None)),
+                             ("contraction", lambda: block_contraction(T, ctx, torch, peak_tf)),
+                             ("luci", lambda: block_luci(T, ctx, peak_tf)),
+                             ("globalsearch", lambda: block_globalsearch(T, ctx))):
+                try:
+                    out[name] = fn()
+                except Exception as e:  # a side block never takes the headline line down
+                    out[name] = {"error": repr(e)[:300]}
+        if world > 1 and not args.no_extra:
+            try:
+                out["stages"], out["sharded_parity"] = sharded_stages(T, ctx, torch, world, fm, I, J)
+            except Exception as e:
+                out["stages"] = {"error": repr(e)[:300]}
+        if orc is not None:
+            try:
+                val, dt, nthreads, sample, res = cpu_contraction_sample(1, 1)
+                v1, dt1, _, _, _ = cpu_contraction_sample(1, 1, threads=1)
+                got = fm(I[:REF_SAMPLE], J[:REF_SAMPLE], 0)
+                out["cpu_baseline"] = {"value": val, "unit": "GFLOP/s", "cores": nthreads, "kind": "port",
+                                       "sample": sample, "value_1_thread": v1,
+                                       "gpu_matches_cpu_rel": float(np.max(np.abs(got - res)) / np.max(np.abs(res)))}
+            except Exception as e:
+                out["cpu_baseline"] = {"error": repr(e)[:300]}
         print(json.dumps(out))
+    barrier()
     if world > 1:
         dist.destroy_process_group()
 
 
-# DRAM bytes of one k_rrlu_lazy launch measured under ncu (profiles/r1_rrlu_lazy_8192_1024_dram.csv): 445.87 GB
-# read + 130.37 GB written (the in-place kernel moved 436.26 + 462.19 GB, profiles/r1_rrlu_8192_1024_dram.csv).
-# Below the 604.6 GB of the model because alternate passes sweep the tiles in opposite order and the tail of one
-# sweep is still in L2 for the next.
-RRLU_DRAM_TRAFFIC = {(8192, 8192, 1024): 445872222720 + 130370041856}
-
-
-def cpu_baselines_secondary():
-    """CPU numbers for the secondary stages on this box's host cores: Pi-eval through the oracle port on
-    one core (the reference's filltensor loop is single threaded, batcheval.jl:50-58), and the OpenBLAS DGEMM that
-    stands behind the reference's TT / MPO contractions (cachedtensortrain.jl:207-212, contraction.jl:92) at 1 and at
-    all threads.  Reported baselines, not targets."""
-    out = {}
-    try:
-        from oracle import oracle as orc
-        ld = [64] * 12
-        g = np.random.default_rng(7)
-        I = np.stack([g.integers(1, 65, 1024) for _ in range(6)], axis=1).tolist()
-        J = np.stack([g.integers(1, 65, 1024) for _ in range(6)], axis=1).tolist()
-        o = orc.Target.builtin(1, [1.0], ld)
-        o.pi_eval(I[:64], J[:64], 0, 0.0)
+def sharded_stages(T, ctx, torch, world, fm, I, J):
+    """N > 1: the other stages that shard, each timed on the N-GPU context and on a 1-GPU context in the same run,
+    and the parity of every sharded result against the unsharded one."""
+    from tci_b200 import _lib
+    c1 = T.Context(0)
+    stages, parity = {}, {}
+    # --- headline stage: MPO Pi, N GPUs against 1 GPU, same index sets ---
+    f1 = T.Contraction(T.TensorTrain(mpo_cores(5)), T.TensorTrain(mpo_cores(6)), ctx=c1)
+    ref = f1(I, J, 0)
+    got = fm(I, J, 0)
+    parity["mpo"] = bool(np.max(np.abs(ref - got)) <= 1e-12 * np.max(np.abs(ref)))
+    t0 = time.perf_counter()
+    d, _ = f1.batchevaluate_device(I, J, 0)
+    t1 = time.perf_counter()
+    del d
+    stages["mpo_pi_config5"] = {"ms_1gpu": (t1 - t0) * 1e3}
+    del f1
+    # --- global search at config-4 shape ---
+    res = {}
+    for label, c in (("n", ctx), ("1", c1)):
+        f, finder, inp, probes = gsearch_setup(T, c)
+        found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=2)
         t0 = time.perf_counter()
-        o.pi_eval(I, J, 0, 0.0)
-        dt = time.perf_counter() - t0
-        out["pi_eval_lorentz"] = {"mevals_per_s": 1024 * 1024 / dt / 1e6, "cores": 1, "kind": "port",
-                                  "sample": "1024 x 1024 block of the 12-site d=64 Lorentzian Pi"}
-    except Exception as e:
-        out["pi_eval_lorentz"] = {"error": str(e)[:200]}
-    try:
-        import threadpoolctl
-        N = 2048
-        g = np.random.default_rng(8)
-        A, B = g.standard_normal((N, N)), g.standard_normal((N, N))
-        nproc = os.cpu_count() or 1
-        for nt in sorted({1, nproc}):
-            with threadpoolctl.threadpool_limits(limits=nt, user_api="blas"):
-                A @ B
-                t0 = time.perf_counter()
-                reps = 1 if nt == 1 else 3
-                for _ in range(reps):
-                    A @ B
-                dt = (time.perf_counter() - t0) / reps
-            out[f"openblas_dgemm_2048_threads{nt}"] = {"gflops": 2.0 * N ** 3 / dt / 1e9, "threads": nt}
-        info = [d for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
-        out["blas"] = {"library": info[0].get("internal_api") if info else None,
-                       "version": info[0].get("version") if info else None, "host_cores": nproc}
-    except Exception as e:
-        out["openblas_dgemm"] = {"error": str(e)[:200]}
-    return out
-
-
-def extra_globalsearch(T, ctx, torch, dist, rank, world):
-    """Default global pivot finder (globalpivotfinder.jl:143-195) at config-4 shape: 12 sites d=64, current TT of bond
-    dimension 128, 2048 random starts = 1.57 M star probes |f - tt|, the starts dealt round-robin over the ranks and the
-    accepted candidates all-gathered."""
-    extra = {}
-    try:
-        ld, chi, nsearch = [64] * 12, 128, 2048
-        g = np.random.default_rng(4)
-        params = np.concatenate([[4], g.integers(1, 1025, 12) / 256.0, g.integers(-512, 513, 4) / 1024.0,
-                                 (g.integers(-1024, 1025, (4, 12)) / 32.0).flatten()])
-        f = T.BuiltinTarget(T.SEPCOS, params, ld)
-        bonds = [1] + [chi] * 11 + [1]
-        g9 = np.random.default_rng(9)
-        tt = T.TensorTrain([np.asfortranarray((g9.random((bonds[i], 64, bonds[i + 1])) * 2 - 1) / np.sqrt(bonds[i]))
-                            for i in range(12)])
-        finder = T.DefaultGlobalPivotFinder(nsearch=nsearch, maxnglobalpivot=5)
-        inp = T.GlobalPivotSearchInput(ld, tt, 1.0, None, None)
-        if world > 1:
-            from tci_b200.parallel import ShardedEvaluator
-            sf = ShardedEvaluator(f, dist, torch)
-        else:
-            sf = f
-        found = None
-        for it in range(3):
-            if it == 1:
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                ctx.timers(reset=True)
-                t0 = time.perf_counter()
-            found = finder(inp, sf, 1e-3, rng=T.CounterRNG(1))
-        dt = (time.perf_counter() - t0) / 2
-        lib_ms = ctx.timers(reset=True)["globalsearch"] / 2
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        probes = nsearch * sum(ld)
-        extra["globalsearch_config4"] = {
-            "mprobes_per_s": probes / dt / 1e6, "ms": dt * 1e3, "nsearch": nsearch, "probes": probes,
-            "found": int(len(found)), "ranks": world, "library_ms": lib_ms,
-            "note": "12 sites d=64, TT bond 128; wall clock per finder call incl. upload of the TT cores (replicated), "
-                    "candidate all-gather and selection"}
-    except Exception as e:
-        extra["globalsearch_config4"] = {"error": str(e)[:200]}
-    return extra
-
-
-def chain_steps(S, right):
-    """Full-bond environment extensions a chain evaluates for the index set S: one per DISTINCT partial index
-    (prefixes of the left set, suffixes of the right set), levels 2..n (level 1 starts from the bond of dimension 1)."""
-    n = S.shape[1]
-    return sum(len(np.unique(S[:, n - k:] if right else S[:, :k], axis=0)) for k in range(2, n + 1))
-
-
-def extra_mpo_1024(T, ctx, torch, dist, rank, world):
-    extra = {}
-    # --- config 5 shape, the two-site Pi of the MPO x MPO target at the middle bond with nL = nR = 1024 (SURVEY 8d),
-    # at N > 1 sharded by ROW blocks of the left index set: every rank extends the left environments of its own rows,
-    # the right environments are replicated, the block goes into rank 0's HBM by peer stores ---
-    try:
-        nsites, Dm, nL = 40, 256, 1024
-        g5, g6, g7 = np.random.default_rng(5), np.random.default_rng(6), np.random.default_rng(8)
-
-        def mpo5(g):
-            bonds = [1] + [Dm] * (nsites - 1) + [1]
-            return [np.asfortranarray((g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(nsites)]
-
-        fm = T.Contraction(T.TensorTrain(mpo5(g5)), T.TensorTrain(mpo5(g6)))
-        Il = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
-        Jr = np.stack([g7.integers(1, 5, nL) for _ in range(20)], axis=1).astype(np.int64)
-        step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm
-
-        fl = (chain_steps(Il, False) + chain_steps(Jr, True)) * step + 2.0 * nL * Dm * Dm * nL
-        if world == 1:
-            dev, mx = fm.batchevaluate_device(Il, Jr, 0)
-            del dev
-            ctx.timers(reset=True)
-            dev, mx = fm.batchevaluate_device(Il, Jr, 0)
-            ms = ctx.timers(reset=True)["pi_eval"]
-            del dev
-            # the same Pi size over NESTED index sets, as a TCI run produces them (Icombined = kronecker(Iset, d), Iset
-            # grown site by site, chi = 256): shared prefixes / suffixes are evaluated once (ChainPlan, csrc/mpo.cu),
-            # which is what the reference's Dict memo does within one call (contraction.jl:112-176)
-            from tci_b200.util import kronecker_left, kronecker_right
-            Sl = np.arange(1, 5, dtype=np.int64)[:, None]
-            Sr = Sl.copy()
-            for _ in range(18):
-                cl, cr = kronecker_left(Sl, 4), kronecker_right(4, Sr)
-                Sl = cl[np.sort(g7.choice(len(cl), min(256, len(cl)), replace=False))]
-                Sr = cr[np.sort(g7.choice(len(cr), min(256, len(cr)), replace=False))]
-            In, Jn = kronecker_left(Sl, 4), kronecker_right(4, Sr)
-            res = {}
-            for label, env in (("dedup", None), ("plain", "1")):
-                if env:
-                    os.environ["TCI_MPO_NO_DEDUP"] = env
-                try:
-                    dev, mxn = fm.batchevaluate_device(In, Jn, 0)
-                    del dev
-                    ctx.timers(reset=True)
-                    dev, mxn = fm.batchevaluate_device(In, Jn, 0)
-                    res[label] = (ctx.timers(reset=True)["pi_eval"], mxn)
-                    del dev
-                finally:
-                    os.environ.pop("TCI_MPO_NO_DEDUP", None)
-            fln = (chain_steps(In, False) + chain_steps(Jn, True)) * step + 2.0 * nL * Dm * Dm * nL
-            extra["mpo_pi_eval_config5_1024_nested"] = {
-                "ms": res["dedup"][0], "ms_without_prefix_sharing": res["plain"][0],
-                "tflops": fln / (res["dedup"][0] * 1e-3) / 1e12,
-                "maxabs_rel_dev": abs(res["dedup"][1] - res["plain"][1]) / abs(res["plain"][1]),
-                "shape": "40 sites, bonds 256, Pi 1024 x 1024 over nested index sets (256 distinct parents per level)"}
-            extra["mpo_pi_eval_config5_1024"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms,
-                                                 "shape": "40 sites, bonds 256, nL=nR=1024, M=0 (Pi 1024 x 1024)",
-                                                 "flop_model": "one environment extension per DISTINCT partial index "
-                                                               "(random sets: 4, 16, 64, 256 at the first levels, 1024 "
-                                                               "after) + final (1024 x 65536) x (65536 x 1024) product"}
-        else:
-            from tci_b200.parallel import ShardedEvaluator
-            for shard in ("rows", "cols"):
-                sm = ShardedEvaluator(fm, dist, torch, mode="peer", shard=shard)
-                for it in range(3):
-                    if it == 1:
-                        torch.cuda.synchronize()
-                        dist.barrier()
-                        t0 = time.perf_counter()
-                    dev, mx = sm.batchevaluate_device(Il, Jr, 0)
-                    del dev
-                torch.cuda.synchronize()
-                dt = (time.perf_counter() - t0) / 2
-                t = torch.tensor([dt], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-                sm.release()
-                # per rank: its own share of one chain, the whole of the other chain, its share of the product
-                extra[f"mpo_pi_eval_config5_1024_sharded_{shard}"] = {
-                    "ms": dt * 1e3, "tflops_useful": fl / dt / 1e12,
-                    "note": (f"row blocks over {world} ranks: left environments of the rank's rows, right environments "
-                             "of its column block + one NCCL all-gather, block product stored into rank 0's HBM"
-                             if shard == "rows" else
-                             f"column blocks over {world} ranks, left environments recomputed on every rank") +
-                            "; wall clock incl. index upload, barrier and max all-reduce"}
-        del fm
-    except Exception as e:  # never let an extra take the headline line down
-        extra["mpo_pi_eval_config5_1024"] = {"error": str(e)[:200]}
-    return extra
-
-
-def run_extra(T, ctx, torch, dist, rank, world, stream):
-    """Secondary numbers of the composite metric: Pi-eval Mevals/s (config 4 shape, column blocks
-    sharded over ranks), DGEMM GFLOP/s (the contraction building block), and the README config 1
-    crossinterpolate2 time-to-tolerance."""
-    extra = {}
-    rng = np.random.default_rng(7)
-    # --- Pi-eval, 12 sites d=64, Lorentzian (cheap target: HBM-write bound) ---
-    ld = [64] * 12
-    nI, nJ = 16384, 16384
-    I = np.stack([rng.integers(1, 65, nI) for _ in range(6)], axis=1).astype(np.int64)
-    J = np.stack([rng.integers(1, 65, nJ) for _ in range(6)], axis=1).astype(np.int64)
-    from tci_b200.parallel import column_blocks, gather_column_blocks
-    blk, ranges = column_blocks(nJ, world)
-    Jloc = np.ascontiguousarray(J[ranges[rank][0]:ranges[rank][1]])
-    for name, kind, params in (("lorentz", T.LORENTZ, [1.0]), ("sepcos", T.SEPCOS, None)):
-        if params is None:
-            g = np.random.default_rng(4)
-            params = np.concatenate([[4], g.integers(1, 1025, 12) / 256.0, g.integers(-512, 513, 4) / 1024.0,
-                                     (g.integers(-1024, 1025, (4, 12)) / 32.0).flatten()])
-        f = T.BuiltinTarget(kind, params, ld)
         for _ in range(3):
-            dev, mx = f.batchevaluate_device(I, Jloc, 0)
-            del dev
-        ctx.timers(reset=True)
-        reps = 5
-        for _ in range(reps):
-            dev, mx = f.batchevaluate_device(I, Jloc, 0)
-            del dev
-        ms = ctx.timers(reset=True)["pi_eval"] / reps
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        evals = nI * nJ
-        extra[f"pi_eval_{name}"] = {"mevals_per_s": evals / (ms * 1e-3) / 1e6, "ms": ms,
-                                    "shape": [nI, nJ], "hbm_gbs": 8 * evals / (ms * 1e-3) / 1e9,
-                                    "frac_of_hbm_peak": 8 * evals / (ms * 1e-3) / 1e9 / peaks()[0] / world,
-                                    "sharding": f"column blocks over {world} rank(s), kernel time only"}
-        if world > 1:
-            # fused form: every rank's evaluation kernel stores its column block straight into rank 0's HBM
-            # through an IPC-mapped pointer (NVLink peer stores), then one barrier
-            from tci_b200.parallel import ShardedEvaluator
-            sf = ShardedEvaluator(f, dist, torch, mode="peer")
-            for it in range(4):
-                if it == 1:
-                    torch.cuda.synchronize()
-                    dist.barrier()
-                    t0 = time.perf_counter()
-                dev, mx = sf.batchevaluate_device(I, J, 0)
-                del dev
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / 3
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-            sf.release()
-            extra[f"pi_eval_{name}_sharded_peer_writes"] = {
-                "mevals_per_s": nI * nJ / dt / 1e6, "ms": dt * 1e3,
-                "note": "Pi assembled in rank 0's HBM by peer stores from the evaluation kernels (wall clock incl. "
-                        "index upload, barrier and max all-reduce)"}
-        if world > 1 and name == "lorentz":
-            # the same evaluation written into the shared buffer + ONE in-place NCCL all-gather
-            full = T.DeviceMatrix.empty(ctx, nI, blk * world)
-            fv = torch.as_tensor(full, device=torch.device("cuda", ctx.device))
-            for it in range(4):
-                if it == 1:
-                    torch.cuda.synchronize()
-                    dist.barrier()
-                    t0 = time.perf_counter()
-                f.batchevaluate_into(full, rank * blk, I, Jloc, 0)
-                gather_column_blocks(dist, torch, fv, blk, rank)
-                torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / 3
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-            extra["pi_eval_lorentz_sharded_gathered"] = {
-                "mevals_per_s": evals / dt / 1e6, "ms": dt * 1e3,
-                "allgather_bytes_per_rank": int(8 * fv.shape[1] * blk * (world - 1)),
-                "note": "evaluate own column block + all-gather so that every rank holds Pi"}
-            del full, fv
-    # --- DGEMM 4096^3 through the device path (GEMM inside tci_dgemm_host is timed by stage) ---
-    if rank == 0:
-        N = 4096
-        A = np.asfortranarray(rng.standard_normal((N, N)))
-        B = np.asfortranarray(rng.standard_normal((N, N)))
-        C = np.zeros((N, N), order="F")
-        from tci_b200 import _lib
-        for _ in range(2):
-            ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
-        ctx.timers(reset=True)
-        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, N, N, N, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
-        ms = ctx.timers(reset=True)["gemm"]
-        extra["dgemm_4096"] = {"gflops": 2.0 * N ** 3 / (ms * 1e-3) / 1e9, "ms": ms, "kernel": "k_dgemm_mma (DMMA m8n8k4)"}
-        a = torch.randn(N, N, dtype=torch.float64, device="cuda")
-        b = torch.randn(N, N, dtype=torch.float64, device="cuda")
-        for _ in range(2):
-            c = a @ b
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            c = a @ b
-        e1.record()
-        torch.cuda.synchronize()
-        extra["cublas_dgemm_4096_gflops"] = 5 * 2.0 * N ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e9
-        # --- config 5 shape: MPO x MPO target, 40 sites, bond 256, site dims 2x2: Pi over the middle bond ---
-        nsites, Dm = 40, 256
-        g5, g6 = np.random.default_rng(5), np.random.default_rng(6)
-
-        def mpo(g):
-            bonds = [1] + [Dm] * (nsites - 1) + [1]
-            return [np.asfortranarray((g.random((bonds[i], 2, 2, bonds[i + 1])) * 2 - 1) / 16.0) for i in range(nsites)]
-
-        fm = T.Contraction(T.TensorTrain(mpo(g5)), T.TensorTrain(mpo(g6)))
-        nL = nR = 256
-        Il = np.stack([rng.integers(1, 5, nL) for _ in range(19)], axis=1).astype(np.int64)
-        Jr = np.stack([rng.integers(1, 5, nR) for _ in range(19)], axis=1).astype(np.int64)
-        dev, mx = fm.batchevaluate_device(Il, Jr, 2)
-        del dev
-        ctx.timers(reset=True)
-        l0 = ctx.launches
-        dev, mx = fm.batchevaluate_device(Il, Jr, 2)
-        ms = ctx.timers(reset=True)["pi_eval"]
-        step = 2.0 * Dm * Dm * 2 * Dm + 2.0 * Dm * 2 * Dm * Dm  # one environment extension (contraction.jl:103-109)
-        fl = (chain_steps(Il, False) + chain_steps(Jr, True)) * step \
-            + 2 * (nL * (2.0 * Dm * Dm * 8 * Dm) + nL * 4 * 8 * 2.0 * Dm * Dm * Dm / 4) + 2.0 * nL * 16 * Dm * Dm * nR
-        extra["mpo_pi_eval_config5"] = {"tflops": fl / (ms * 1e-3) / 1e12, "ms": ms, "launches": ctx.launches - l0,
-                                        "shape": f"40 sites, bonds 256, nL=nR={nL}, M=2 (Pi {nL * 16} x {nR})",
-                                        "flop_model": "one env extension per distinct partial index + centre folds + final product"}
-        del dev, fm
-        # --- config 5 shape: one zip-up site step (contraction.jl:455-464) at chi = Da = Db = 256, s = 2x2x2:
-        # R (256,256,256), A, B (256,2,2,256) -> C (1024 x 65536), the matrix _factorize gets next ---
+            found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=2)
+        res[label] = ((time.perf_counter() - t0) / 3 * 1e3, found.tolist(), finder.last_errors.tolist())
+    stages["globalsearch_config4"] = {"ms": res["n"][0], "ms_1gpu": res["1"][0], "probes": probes,
+                                      "mode": "environments; blocks of starts per GPU, records by one ncclAllGather"}
+    parity["gsearch"] = res["n"][1] == res["1"][1] and res["n"][2] == res["1"][2]
+    # --- Pi evaluation of analytic targets: the cost model decides whether sharding pays ---
+    rng = np.random.default_rng(7)
+    ld = [64] * 12
+    nI = nJ = 16384
+    Ia = np.stack([rng.integers(1, 65, nI) for _ in range(6)], axis=1).astype(np.int64)
+    Ja = np.stack([rng.integers(1, 65, nJ) for _ in range(6)], axis=1).astype(np.int64)
+    ok = True
+    for name, kind, params in (("lorentz", T.LORENTZ, [1.0]), ("sepcos_config4", T.SEPCOS, sepcos_params())):
+        ent = {}
+        for label, c in (("n", ctx), ("1", c1)):
+            f = T.BuiltinTarget(kind, params, ld, ctx=c)
+            for _ in range(2):
+                d, mx = f.batchevaluate_device(Ia, Ja, 0)
+                del d
+            l0 = sum(c.member_launches(k) for k in range(1, c.ngpu))
+            t0 = time.perf_counter()
+            for _ in range(3):
+                d, mx = f.batchevaluate_device(Ia, Ja, 0)
+                del d
+            ent["ms" if label == "n" else "ms_1gpu"] = (time.perf_counter() - t0) / 3 * 1e3
+            if label == "n":
+                ent["sharded"] = bool(sum(c.member_launches(k) for k in range(1, c.ngpu)) > l0)
+        stages[f"pi_eval_{name}"] = ent
+        # parity on a smaller Pi with sharding forced
+        os.environ["TCI_SHARD_FORCE"] = str(world)
         try:
-            chi = Da = Db = 256
-            Rz = np.asfortranarray(rng.standard_normal((chi, Da, Db)))
-            Az = np.asfortranarray(rng.standard_normal((Da, 2, 2, Da)))
-            Bz = np.asfortranarray(rng.standard_normal((Db, 2, 2, Db)))
-            import ctypes as C
-            for it in range(2):
-                h = C.c_void_p()
-                ctx.timers(reset=True)
-                ctx.check(_lib.lib().tci_contract_zipup_site(ctx.h, _lib.pf(Rz), chi, Da, Db, _lib.pf(Az), 2, 2, Da,
-                                                             _lib.pf(Bz), 2, Db, None, C.byref(h)))
-                tmz = ctx.timers(reset=True)
-                Cz = _lib.DeviceMatrix(ctx, h)
-                del Cz
-            flz = 2.0 * chi * Da * Db * 4 * Da + 2.0 * (chi * 2) * (Db * 2) * (2 * Da * Db)
-            extra["zipup_site_config5"] = {"tflops": flz / (tmz["gemm"] * 1e-3) / 1e12, "ms": tmz["gemm"],
-                                           "h2d_ms": tmz["h2d"], "shape": "chi=Da=Db=256, site dims 2x2x2, C 1024 x 65536",
-                                           "flop_model": "R*A (chi*Db x Da x s1*s2*Da') + RA*B (chi*s1 x Db*s2 x s3*Da'*Db')"}
-            del Rz, Az, Bz
-        except Exception as e:
-            extra["zipup_site_config5"] = {"error": str(e)[:200]}
-        # --- config 3: quantics 2-D, R=20 fused (20 sites d=4), maxbonddim 256, tolerance 1e-10 ---
-        f3 = T.BuiltinTarget(T.QUANTICS2D, [0, 20], [4] * 20)
-        t0 = time.perf_counter()
-        tci3, ranks3, errors3 = T.crossinterpolate2(f3, [4] * 20, tolerance=1e-10, maxbonddim=256, rng=T.CounterRNG(1))
-        extra["crossinterpolate2_config3"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks3[-1]),
-                                              "iterations": len(ranks3), "error": float(errors3[-1])}
-        # --- config 1: README 8-d Lorentzian, time to tolerance 1e-8 ---
-        f = T.BuiltinTarget(T.LORENTZ, [1.0], [10] * 8)
-        T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
-        t0 = time.perf_counter()
-        tci, ranks, errors = T.crossinterpolate2(f, [10] * 8, tolerance=1e-8, rng=T.CounterRNG(1))
-        extra["crossinterpolate2_config1"] = {"time_to_tol_s": time.perf_counter() - t0, "rank": int(ranks[-1]),
-                                              "iterations": len(ranks), "error": float(errors[-1])}
-    extra.update(extra_mpo_1024(T, ctx, torch, dist, rank, world))
-    extra.update(extra_globalsearch(T, ctx, torch, dist, rank, world))
-    if rank == 0 and world == 1 and not os.environ.get("TCI_BENCH_NO_CPU"):
-        extra["cpu_baselines"] = cpu_baselines_secondary()
-    if rank == 0:
-        # --- config 4 scale: one bond's rrLU, 32768 x 32768 (8.6 GB, 12 sites d=64 at chi=512), maxrank 512.
-        # The config-4 target itself is numerically of rank ~23, so its Pi never needs 512 pivots; the kernel is
-        # measured at that scale on a synthetic rank-512 matrix formed on the device (untimed).
-        try:
-            m4, r4 = 32768, 512
-            g4 = torch.Generator(device="cuda").manual_seed(4)
-            p4 = torch.rand((m4, r4), dtype=torch.float64, device="cuda", generator=g4) * \
-                (2.0 ** (-40.0 * torch.arange(1, r4 + 1, dtype=torch.float64, device="cuda") / r4))
-            q4 = torch.rand((r4, m4), dtype=torch.float64, device="cuda", generator=g4)
-            A4 = (p4 @ q4).t().contiguous()  # column-major m4 x m4
-            del p4, q4
-            torch.cuda.synchronize()
-            view = T.DeviceMatrix.wrap(ctx, A4.data_ptr(), m4, m4, m4)
-            ctx.timers(reset=True)
-            lu4 = T.rrlu(view, maxrank=r4, reltol=1e-12)
-            ms4 = ctx.timers(reset=True)["rrlu_kernel"]
-            extra["rrlu_config4_scale"] = {"shape": [m4, m4], "maxrank": r4, "npivot": int(lu4.npivot), "ms": ms4,
-                                           "gflops": rrlu_flops(m4, m4, lu4.npivot) / ms4 / 1e6,
-                                           "gbs_deferred_model": rrlu_bytes_deferred(m4, m4, lu4.npivot) / ms4 / 1e6}
-            del lu4, view, A4
-            torch.cuda.empty_cache()
-        except Exception as e:  # never let an extra take the headline line down
-            extra["rrlu_config4_scale"] = {"error": str(e)[:200]}
-    return extra
+            fa, fb = T.BuiltinTarget(kind, params, ld, ctx=ctx), T.BuiltinTarget(kind, params, ld, ctx=c1)
+            da, ma = fa.batchevaluate_device(Ia[:1500], Ja[:1100], 0)
+            db, mb = fb.batchevaluate_device(Ia[:1500], Ja[:1100], 0)
+            ok = ok and bool(np.array_equal(da.to_host(), db.to_host()) and ma == mb)
+        finally:
+            del os.environ["TCI_SHARD_FORCE"]
+    parity["pi"] = ok
+    return stages, parity
 
 
 if __name__ == "__main__":

@@ -199,6 +199,10 @@ int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsites, const 
 int tci_dgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
                    const double *A, const double *B, double beta, double *C);
 
+/* FP64 roofline denominators measured on this GPU: out[0] = DFMA pipe TFLOP/s (register-resident FMA loop),
+ * out[1] = FP64 tensor path TFLOP/s (register-resident mma.sync.m8n8k4.f64 loop; tcgen05 has no FP64 kind).       */
+int tci_fp64_peak(tci_ctx *ctx, double *out /* 2 */);
+
 /* ---- (c) contraction ------------------------------------------------------ */
 /* One zip-up step (contraction.jl:455-464): R (chi,Da,Db), A (Da,s1,s2,Da'),
  * B (Db,s2,s3,Db') -> C as the (chi*s1*s3) x (Da'*Db') matrix that is factorised next. */

@@ -559,3 +559,73 @@ def rrlu_complex(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True)
     if r >= min(m, n):
         error = 0.0  # :176-178
     return np.array(rowperm), np.array(colperm), L, U, r, float(error)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numpy / OpenBLAS restatement of Contraction.batchevaluate for M = 0 (contraction.jl:71-176, 236-335).  The
+# reference's environment extensions and the final product are BLAS dgemm calls on permuted copies
+# (`amat * bmat`, :92), multithreaded by default in Julia; this is the CPU baseline of the contraction stage
+# (bench.py, `--impl reference`), with numpy's OpenBLAS standing in for Julia's.  Checked against the C++ oracle in
+# tests/test_oracle_golden.py.
+def _contract_np(a, b, idx_a, idx_b):  # _contract, contraction.jl:71-93 (0-based axes)
+    rest_a = [k for k in range(a.ndim) if k not in idx_a]
+    rest_b = [k for k in range(b.ndim) if k not in idx_b]
+    amat = np.transpose(a, rest_a + list(idx_a)).reshape(int(np.prod([a.shape[k] for k in rest_a], dtype=np.int64)), -1)
+    bmat = np.transpose(b, list(idx_b) + rest_b).reshape(-1, int(np.prod([b.shape[k] for k in rest_b], dtype=np.int64)))
+    return (amat @ bmat).reshape([a.shape[k] for k in rest_a] + [b.shape[k] for k in rest_b])
+
+
+def _extend_cache_np(old, a_ell, b_ell, i, j):  # _extend_cache, :103-109
+    tmp1 = _contract_np(old, a_ell[:, i, :, :], (0,), (0,))
+    return _contract_np(tmp1, b_ell[:, :, j, :], (0, 1), (0, 1))
+
+
+class ContractionBLAS:
+    """Contraction(a, b) with the reference's Dict memo of left / right environments (:112-176)."""
+
+    def __init__(self, A, B):
+        self.a = [np.asarray(x, dtype=np.float64) for x in A]
+        self.b = [np.asarray(x, dtype=np.float64) for x in B]
+        self.aperm = [np.transpose(x, (3, 1, 2, 0)) for x in self.a]
+        self.bperm = [np.transpose(x, (3, 1, 2, 0)) for x in self.b]
+        self.leftcache, self.rightcache = {}, {}
+        self.extensions = 0
+
+    def _unfuse(self, n, idx):  # _unfuse_idx, :95-97 (idx 1-based, returns 0-based (i, j))
+        d1 = self.a[n].shape[1]
+        return (idx - 1) % d1, (idx - 1) // d1
+
+    def evaluateleft(self, key):  # key: tuple of 0-based (i, j) pairs for sites 0 .. len-1
+        if len(key) == 0:
+            return np.ones((1, 1))
+        if len(key) == 1:
+            i, j = key[0]
+            return self.a[0][0, i, :, :].T @ self.b[0][0, :, j, :]
+        if key not in self.leftcache:
+            i, j = key[-1]
+            ell = len(key) - 1
+            self.leftcache[key] = _extend_cache_np(self.evaluateleft(key[:-1]), self.a[ell], self.b[ell], i, j)
+            self.extensions += 1
+        return self.leftcache[key]
+
+    def evaluateright(self, key):  # key: (i, j) pairs for the last len(key) sites
+        if len(key) == 0:
+            return np.ones((1, 1))
+        if len(key) == 1:
+            i, j = key[0]
+            return self.a[-1][:, i, :, 0] @ self.b[-1][:, :, j, 0].T
+        if key not in self.rightcache:
+            i, j = key[0]
+            ell = len(self.a) - len(key)
+            self.rightcache[key] = _extend_cache_np(self.evaluateright(key[1:]), self.aperm[ell], self.bperm[ell], i, j)
+            self.extensions += 1
+        return self.rightcache[key]
+
+    def batchevaluate0(self, I, J):
+        """M = 0: res[i, j] = sum_{a,b} left_[i, a, b] * right_[a, b, j]   (:268-284, :328)."""
+        N = len(self.a)
+        nr = len(J[0])
+        left = np.stack([self.evaluateleft(tuple(self._unfuse(n, v) for n, v in enumerate(ix))) for ix in I])
+        right = np.stack([self.evaluateright(tuple(self._unfuse(N - nr + n, v) for n, v in enumerate(ix))) for ix in J],
+                         axis=-1)
+        return _contract_np(left, right, (1, 2), (0, 1))

@@ -57,6 +57,7 @@ SYMBOLS = {
     "tci_luci_right": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
     "tci_lu_rdiv": (C.c_int, [VP, VP, P_f64, C.POINTER(VP)]),
     "tci_lu_destroy": (C.c_int, [VP]),
+    "tci_fp64_peak": (C.c_int, [VP, P_f64]),
     "tci_dgemm_host": (C.c_int, [VP, C.c_int, C.c_int, i64, i64, i64, f64, P_f64, P_f64, f64, P_f64]),
     "tci_contract_zipup_site": (C.c_int, [VP, P_f64, i64, i64, i64, P_f64, i64, i64, i64, P_f64, i64, i64, P_f64,
                                           C.POINTER(VP)]),
@@ -151,6 +152,12 @@ class Context:
     @property
     def launches(self):
         return int(lib().tci_ctx_launches(self.h))
+
+    def fp64_peak(self):
+        """(DFMA TFLOP/s, DMMA TFLOP/s) measured by register-resident loops on this GPU (tci_fp64_peak)."""
+        out = np.zeros(2, dtype=np.float64)
+        self.check(lib().tci_fp64_peak(self.h, pf(out)))
+        return float(out[0]), float(out[1])
 
     def timers(self, reset=False):
         out = np.zeros(9, dtype=np.float64)

@@ -544,3 +544,66 @@ extern "C" int tci_dgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, i
     TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TCI_OK;
 }
+
+// ---- FP64 roofline denominators: register-resident DFMA and DMMA loops -----------------------
+// 8 independent accumulator chains per thread; the result is stored so that the loops cannot be removed.
+__global__ void __launch_bounds__(256) k_peak_dfma(double *out, int iters, double x, double y)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y);
+        a1 = fma(a1, x, y);
+        a2 = fma(a2, x, y);
+        a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y);
+        a5 = fma(a5, x, y);
+        a6 = fma(a6, x, y);
+        a7 = fma(a7, x, y);
+    }
+    out[blockIdx.x * (i64)blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double *out, int iters, double x, double y)
+{
+    double d[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) d[q] = threadIdx.x + q;
+    const double a = x + threadIdx.x * 1e-9, b = y;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dmma884(d[2 * q], d[2 * q + 1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += d[q];
+    out[blockIdx.x * (i64)blockDim.x + threadIdx.x] = s;
+}
+
+// out[0] = DFMA pipe TFLOP/s (2 flop per FMA), out[1] = DMMA (mma.sync.m8n8k4.f64: 2*8*8*4 flop per warp instruction)
+extern "C" int tci_fp64_peak(tci_ctx *ctx, double *out)
+{
+    TCI_ENTER(ctx);
+    if (!out) return tci_fail(ctx, TCI_ERR_ARG, "tci_fp64_peak: out missing");
+    const int blocks = ctx->sm_count * 8, iters = 20000;
+    DevBuf<double> buf(ctx);
+    TCI_CUDA(ctx, buf.alloc((size_t)blocks * 256));
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(ctx->ev4, ctx->stream);
+            if (which == 0)
+                k_peak_dfma<<<blocks, 256, 0, ctx->stream>>>(buf.p, iters, 0.999999, 1e-7);
+            else
+                k_peak_dmma<<<blocks, 256, 0, ctx->stream>>>(buf.p, iters, 0.999999, 1e-7);
+            cudaEventRecord(ctx->ev5, ctx->stream);
+            TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5);
+            if (rep > 0 && ms < best) best = ms;
+            ctx->launches++;
+        }
+        const double flop = which == 0 ? (double)blocks * 256 * iters * 8 * 2.0
+                                       : (double)blocks * 8 /*warps*/ * iters * 8 * (2.0 * 8 * 8 * 4);
+        out[which] = flop / (best * 1e-3) / 1e12;
+    }
+    return TCI_OK;
+}

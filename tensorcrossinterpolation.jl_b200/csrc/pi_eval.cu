@@ -560,6 +560,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
     unsigned long long *dmax = ctx_words(ctx);
     if (!dmax) return tci_fail(ctx, TCI_ERR_CUDA, "scratch words");
     cudaEventRecord(ctx->ev2, ctx->stream);
+    cudaEventRecord(ctx->ev0, ctx->stream); // (re-recorded after the index upload when the owner evaluates itself)
     TCI_CUDA(ctx, cudaMemsetAsync(dmax, 0, 8, ctx->stream));
     tci_dmat *out = nullptr;
     tci_dmat view; // column block of dst

@@ -1425,6 +1425,38 @@ def test_crossinterpolate2_full_size_matches_oracle(T, oracle, name):
     assert abs(np.max(np.abs(fv - tg)) - np.max(np.abs(fv - to))) <= RTOL * scale
 
 
+def test_crossinterpolate2_through_the_deferred_update_kernel(T, oracle, monkeypatch):
+    """A whole crossinterpolate2 in which EVERY bond factorisation is forced through the deferred-update streaming
+    kernel (csrc/rrlu_lazy.cu; in production it takes over from ~3600^2, which the low-rank BASELINE targets never
+    reach end to end): ranks per iteration, index sets and site tensors against the oracle."""
+    monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
+    monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
+    for kind, params, ld, kw in ((Q2D, [0, 8], [4] * 8, dict(tolerance=1e-9, maxbonddim=40, maxiter=6)),
+                                 (SEPCOS, sepcos_params(5), [64] * 5, dict(tolerance=1e-10, maxbonddim=24))):
+        f, o = T.BuiltinTarget(kind, params, ld), oracle.Target.builtin(kind, params, ld)
+        tci, ranks, errors = T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)
+        res = oracle.crossinterpolate2(o, ld, seed=1, **kw)
+        compare_tci(tci, ranks, errors, res, T)
+
+
+def test_crossinterpolate2_tt_target_rank_reaches_maxbonddim(T, oracle):
+    """A target whose rank really reaches maxbonddim (a random tensor train of bond dimension 24 on 6 sites, d = 16):
+    every middle bond factorises a (24*16)^2 Pi to its full allowed rank; pivots against the oracle."""
+    g = np.random.default_rng(12)
+    bonds = [1] + [24] * 5 + [1]
+    cores = [np.asfortranarray((g.random((bonds[i], 16, bonds[i + 1])) * 2 - 1) / np.sqrt(bonds[i] * 4.0)) for i in range(6)]
+    ld = [16] * 6
+    f, o = T.TTCache(T.TensorTrain(cores)), oracle.Target.tt(cores)
+    kw = dict(tolerance=1e-10, maxbonddim=24, maxiter=4)
+    tci, ranks, errors = T.crossinterpolate2(f, ld, rng=T.CounterRNG(1), **kw)
+    res = oracle.crossinterpolate2(o, ld, seed=1, **kw)
+    assert int(ranks[-1]) == 24
+    assert [int(r) for r in ranks] == res.ranks.tolist()
+    pts = rand_indexset(g, ld, 300)
+    assert np.max(np.abs(f.evaluate_points(pts) - T.evaluate_points(T.TensorTrain(tci.sitetensors), pts))) <= \
+        1e-8 * tci.maxsamplevalue
+
+
 def test_config5_full_shape_mpo_properties(T):
     """BASELINE config 5 at its full shape (40 sites, bond dimension 256, site dimensions 2 x 2): the oracle does not
     finish this size in seconds, so parity goes through size-independent properties.  (i) the three evaluation

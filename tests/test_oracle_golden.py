@@ -481,3 +481,19 @@ def test_complex_groundwork_argmax_and_rrlu(oracle):
         assert r == ref.npivot and np.array_equal(rp, ref.rowpermutation) and np.array_equal(cp, ref.colpermutation)
         np.testing.assert_allclose(L.real, ref.L, rtol=1e-13, atol=1e-14)
         assert np.max(np.abs(L.imag)) == 0.0
+
+
+def test_contraction_blas_restatement_matches_oracle(oracle):
+    """oracle.ContractionBLAS (numpy / OpenBLAS restatement of contraction.jl:71-176, 236-335 for M = 0: the CPU
+    baseline of the contraction stage) against the C++ oracle's batchevaluate."""
+    rng = np.random.default_rng(3)
+    ns, D = 7, 5
+    bonds = [1] + [D] * (ns - 1) + [1]
+    A = [np.asfortranarray(rng.random((bonds[i], 2, 3, bonds[i + 1])) - 0.5) for i in range(ns)]
+    B = [np.asfortranarray(rng.random((bonds[i], 3, 2, bonds[i + 1])) - 0.5) for i in range(ns)]
+    I = np.stack([rng.integers(1, 5, 9) for _ in range(3)], axis=1)
+    J = np.stack([rng.integers(1, 5, 11) for _ in range(4)], axis=1)
+    ref, _ = oracle.Target.mpo_pair(A, B).pi_eval(I.tolist(), J.tolist(), 0, 0.0)
+    got = oracle.ContractionBLAS(A, B).batchevaluate0(I.tolist(), J.tolist())
+    assert got.shape == (9, 11)
+    assert np.max(np.abs(got - np.asarray(ref).reshape((9, 11), order="F"))) <= 1e-13 * np.max(np.abs(got))

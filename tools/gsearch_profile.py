@@ -1,4 +1,4 @@
-"""One call of the default global pivot finder at config-4 shape (bench.extra_globalsearch), for ncu.
+"""One call of the default global pivot finder at config-4 shape (bench.block_globalsearch), for ncu.
 usage: ncu ... python tools/gsearch_profile.py"""
 import json
 import os
@@ -11,4 +11,4 @@ import bench  # noqa: E402
 import tci_b200 as T  # noqa: E402
 
 torch.cuda.set_device(0)
-print(json.dumps(bench.extra_globalsearch(T, T.default_context(), torch, None, 0, 1)))
+print(json.dumps(bench.block_globalsearch(T, T.default_context())))
