@@ -21,6 +21,7 @@ int rrlu_core(tci_ctx *ctx, tci_dmat *A, i64 m, i64 n, i64 maxrank, double relto
               int exact_mode, i64 *rowperm, i64 *colperm, i64 *npivot, double *error, double *pivoterrors,
               tci_lu **factors, const void *extra_dev, void *extra_host, size_t extra_bytes, int *deferred_result);
 int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i64 ldx);
+int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus, char *const *results);
 
 extern "C" int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI,
                                const int64_t *J, int64_t nr, int64_t nJ, int64_t maxrank, double reltol, double abstol,
@@ -130,6 +131,8 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
     cudaEventRecord(ctx->ev4, ctx->stream);
     int rc = 0;
     cudaError_t ce = cudaMemsetAsync(dmax, 0, 8, ctx->stream);
+    // phase 1: every Pi1 (with the running max|Pi1|, :372-375) and every P (:383-385), back to back
+    std::vector<tci_dmat *> Pi1s((size_t)n, nullptr), Ps((size_t)n, nullptr);
     for (i64 b = 0; b < n && !rc && ce == cudaSuccess; ++b) {
         const i64 d = t.localdims[b], rows = nI[b] * d, k = nJ[b];
         double *core = nullptr;
@@ -140,39 +143,39 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
         tt->d.push_back(d);
         tt->dr.push_back(k);
         tt->localdims.push_back(d);
-        tci_dmat *Pi1 = nullptr;
-        rc = dmat_alloc(ctx, rows, k, &Pi1);
+        rc = dmat_alloc(ctx, rows, k, &Pi1s[b]);
         if (rc) break;
-        tmp.push_back(Pi1);
-        rc = pi_enqueue(ctx, t, Iset[b], b, nI[b], Jset[b], n - 1 - b, k, 1, Pi1, dmax); // Pi1 and max|Pi1| :372-375
+        tmp.push_back(Pi1s[b]);
+        rc = pi_enqueue(ctx, t, Iset[b], b, nI[b], Jset[b], n - 1 - b, k, 1, Pi1s[b], dmax);
+        if (rc || b == n - 1) continue;
+        rc = dmat_alloc(ctx, k, k, &Ps[b]);
         if (rc) break;
-        if (b == n - 1) { // the last tensor is Pi1 itself (:377-381)
-            k_compact<<<(unsigned)std::min<i64>((rows * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(Pi1->p, Pi1->ld, rows,
-                                                                                                  k, core);
+        rc = pi_enqueue(ctx, t, Iset[b + 1], b + 1, k, Jset[b], n - 1 - b, k, 0, Ps[b], nullptr);
+    }
+    // phase 2: the n-1 pivot matrices are independent: factorised to full rank in ONE cooperative launch, each by its
+    // own group of CTAs (reltol = abstol = 0 never truncates; a singular P shows up in the result words / pivot values)
+    std::vector<tci_lu *> lub((size_t)n, nullptr);
+    if (!rc && ce == cudaSuccess && n > 1) {
+        std::vector<char *> res((size_t)n - 1);
+        for (i64 b = 0; b + 1 < n; ++b) res[b] = pin + roff[b];
+        rc = rrlu_batch_fullrank(ctx, (int)(n - 1), Ps.data(), lub.data(), res.data());
+    }
+    for (i64 b = 0; b + 1 < n; ++b) { // a P is released through its factorisation handle, or directly
+        if (lub[b])
+            lus.push_back(lub[b]);
+        else if (Ps[b])
+            tmp.push_back(Ps[b]);
+    }
+    // phase 3: T = Pi1 P^-1 (:391) from the full-pivot factors; the last tensor is Pi1 itself (:377-381)
+    for (i64 b = 0; b < n && !rc && ce == cudaSuccess; ++b) {
+        const i64 d = t.localdims[b], rows = nI[b] * d, k = nJ[b];
+        double *core = tt->cores[b];
+        if (b == n - 1) {
+            k_compact<<<(unsigned)std::min<i64>((rows * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(Pi1s[b]->p, Pi1s[b]->ld,
+                                                                                                  rows, k, core);
             ctx->launches++;
-        } else {
-            tci_dmat *P = nullptr;
-            rc = dmat_alloc(ctx, k, k, &P);
-            if (rc) break;
-            rc = pi_enqueue(ctx, t, Iset[b + 1], b + 1, k, Jset[b], n - 1 - b, k, 0, P, nullptr); // :383-385
-            i64 np = 0;
-            double err = 0.0;
-            tci_lu *lu = nullptr;
-            // T = Pi1 P^-1 (:391) with the full-pivot factors of P; reltol = abstol = 0 never truncates, a singular P
-            // shows up as npivot < k (no finite candidate left) or as the NaN flags, checked after the synchronisation
-            if (!rc)
-                rc = rrlu_core(ctx, P, k, k, k, 0.0, 0.0, 1, 1, nullptr, nullptr, &np, &err, nullptr, &lu, nullptr, nullptr,
-                               0, reinterpret_cast<int *>(pin + roff[b]));
-            if (rc || !lu) {
-                dev_free(ctx, P->p);
-                delete P;
-                ctx->live_handles--;
-                if (!rc) rc = tci_fail(ctx, TCI_ERR_CUDA, "tci_fill_sitetensors: factorisation was not queued");
-                break;
-            }
-            lus.push_back(lu);
-            rc = lu_rdiv_enqueue(lu, Pi1->p, Pi1->ld, rows, core, rows);
-        }
+        } else
+            rc = lu_rdiv_enqueue(lub[b], Pi1s[b]->p, Pi1s[b]->ld, rows, core, rows);
         if (!rc && T_out && T_out[b] && stage_T)
             ce = cudaMemcpyAsync(hT + toff[b], core, (size_t)(rows * k) * sizeof(double), cudaMemcpyDeviceToHost,
                                  ctx->stream);

@@ -51,7 +51,7 @@
 // MODE 3: as 2 for m > RR_XS_CAP, pivot column read from L2
 // The variants are separate instantiations so that the per-pivot loop stays inside the 32 KB
 // instruction cache (a single generic kernel was 61 KB of SASS and refetched itself every step).
-template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrlu(RRArgs a)
+template <bool EXACT, int MODE, bool LEFT> __device__ __forceinline__ void rrlu_body(RRArgs &a, const int Gq, const int gq)
 {
     constexpr bool RES = MODE <= 1, SINGLE = MODE == 0, XS = MODE != 3;
     constexpr int U = RES ? 2 : RR_U; // 16-byte accesses in flight per lane (deep only when streaming)
@@ -59,7 +59,7 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
     __shared__ long long dbg_acc[16];
     if (threadIdx.x < 16) dbg_acc[threadIdx.x] = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int G = SINGLE ? 1 : gridDim.x, g = SINGLE ? 0 : blockIdx.x, T = blockDim.x, tid = threadIdx.x;
+    const int G = SINGLE ? 1 : Gq, g = SINGLE ? 0 : gq, T = blockDim.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int m = (int)a.m, n = (int)a.n;
     const i64 cld = RES ? a.lds : a.ld; // column stride of the working copy
@@ -455,6 +455,21 @@ template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_
 #undef RR_COL
 }
 
+template <bool EXACT, int MODE, bool LEFT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrlu(RRArgs a)
+{
+    rrlu_body<EXACT, MODE, LEFT>(a, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// Several independent small factorisations in ONE cooperative launch: matrix q is factorised by the Gq consecutive
+// CTAs [q*Gq, (q+1)*Gq) with its columns resident in their shared memory (MODE 1); the record polling that
+// synchronises a group never looks outside it.  On-chip factorisations are bound by the per-pivot latency chain, not by
+// throughput, so the ~20 pivot matrices of fillsitetensors! cost the time of the largest one instead of their sum.
+template <bool EXACT, bool LEFT> __global__ void __launch_bounds__(RR_MAX_THREADS, 1) k_rrlu_batch(const RRArgs *batch, int Gq)
+{
+    RRArgs a = batch[blockIdx.x / Gq];
+    rrlu_body<EXACT, 1, LEFT>(a, Gq, (int)(blockIdx.x % Gq));
+}
+
 // L (m x r, ldl) / U (r x n, ldu) in position order, as lu.L / lu.U of matrixlu.jl:162-174
 __global__ void k_extract_L(const double *__restrict__ A, i64 m, i64 ld, const i64 *__restrict__ colperm, int r,
                             int leftorth, double *__restrict__ L, i64 ldl)
@@ -827,6 +842,114 @@ int rrlu_core(tci_ctx *ctx, tci_dmat *A, i64 m, i64 n, i64 maxrank, double relto
         arena.p = nullptr;
         ctx->live_handles++;
         *factors = lu;
+    }
+    return TCI_OK;
+}
+
+// Full-rank factorisations (reltol = abstol = 0, maxrank = k, leftorthogonal, exact) of `nmat` small square matrices
+// in as few cooperative launches as possible (k_rrlu_batch); matrices that do not fit the shared memory of their CTA
+// group take the one-at-a-time deferred path of rrlu_core.  Nothing synchronises: results[q] (page-locked, 32 + 8 k_q
+// bytes: the 8 result words, then the pivot values) is filled in stream order and checked by the caller.
+int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus, char *const *results)
+{
+    const size_t SMEM_BUDGET = 220 * 1024;
+    std::vector<int> todo;
+    for (int q = 0; q < nmat; ++q) {
+        lus[q] = nullptr;
+        todo.push_back(q);
+    }
+    const bool no_batch = getenv("TCI_RRLU_NO_BATCH") != nullptr;
+    while (!todo.empty()) {
+        const int nb = (int)std::min<size_t>(todo.size(), (size_t)ctx->sm_count);
+        i64 kmax = 1;
+        for (int t = 0; t < nb; ++t) kmax = std::max<i64>(kmax, P[todo[t]]->m);
+        int Gq = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(16, ctx->sm_count / nb), kmax / 2));
+        auto smem_of = [&](i64 k) {
+            const i64 lds = (k + 1) & ~(i64)1, mo = (k + Gq - 1) / Gq;
+            return (size_t)lds * 8 + (size_t)((mo + 1) & ~(i64)1) * 8 + (size_t)mo * 8 + (size_t)mo * lds * 8 + 64;
+        };
+        std::vector<int> batch, rest;
+        for (int t = 0; t < nb; ++t)
+            (!no_batch && P[todo[t]]->m <= RR_XS_CAP && smem_of(P[todo[t]]->m) <= SMEM_BUDGET ? batch : rest).push_back(todo[t]);
+        for (int q : rest) { // too large for a CTA group: one at a time, still without synchronising
+            i64 np = 0;
+            double err = 0.0;
+            const i64 k = P[q]->m;
+            int rc = rrlu_core(ctx, P[q], k, k, k, 0.0, 0.0, 1, 1, nullptr, nullptr, &np, &err, nullptr, &lus[q], nullptr,
+                               nullptr, 0, reinterpret_cast<int *>(results[q]));
+            if (rc) return rc;
+        }
+        if (!batch.empty()) {
+            const int B = (int)batch.size();
+            std::vector<RRArgs> args((size_t)B);
+            size_t smem = 0;
+            int T = 256;
+            for (int t = 0; t < B; ++t) {
+                tci_dmat *A = P[batch[t]];
+                const i64 k = A->m, lds = (k + 1) & ~(i64)1, mo = (k + Gq - 1) / Gq;
+                dmat_wait_ready(ctx, A);
+                smem = std::max(smem, smem_of(k));
+                const i64 per_cta = k * mo;
+                T = std::max(T, (k >= 1024 || per_cta >= 32768) ? 1024 : ((k >= 384 || per_cta >= 8192) ? 512 : 256));
+                RRArgs &a = args[t];
+                a = RRArgs{};
+                a.A = A->p;
+                a.m = a.n = k;
+                a.ld = A->ld;
+                a.maxrank = (int)k;
+                a.reltol = a.abstol = 0.0;
+                a.leftorth = 1;
+                a.ldx = round_up(k, 16);
+                a.xs_in_smem = 1;
+                a.maxown = (int)mo;
+                a.lds = lds;
+                a.nxslots = 2;
+                const size_t o_cand = 32, o_piv = o_cand + (size_t)2 * Gq * sizeof(RRCand), o_rp = o_piv + (size_t)k * 8,
+                             o_cp = o_rp + (size_t)k * 8, o_pos = o_cp + (size_t)k * 8,
+                             o_prow = o_pos + (((size_t)k * 4 + 15) & ~(size_t)15), o_end = o_prow + (size_t)k * 4 + 32;
+                char *arena = nullptr;
+                double *xbuf = nullptr;
+                TCI_CUDA(ctx, dev_alloc(ctx, (void **)&arena, o_end));
+                TCI_CUDA(ctx, dev_alloc(ctx, (void **)&xbuf, (size_t)2 * Gq * a.ldx * sizeof(double)));
+                TCI_CUDA(ctx, cudaMemsetAsync(arena, 0, o_piv, ctx->stream));
+                a.result = reinterpret_cast<int *>(arena);
+                a.result_err = reinterpret_cast<double *>(arena + 16);
+                a.cand = reinterpret_cast<RRCand *>(arena + o_cand);
+                a.pivvals = reinterpret_cast<double *>(arena + o_piv);
+                a.rowperm = reinterpret_cast<i64 *>(arena + o_rp);
+                a.colperm = reinterpret_cast<i64 *>(arena + o_cp);
+                a.colpos = reinterpret_cast<int *>(arena + o_pos);
+                a.pivrows = reinterpret_cast<int *>(arena + o_prow);
+                a.xbuf = xbuf;
+                tci_lu *lu = new tci_lu();
+                lu->ctx = ctx;
+                lu->A = A;
+                lu->m = lu->n = lu->r = k;
+                lu->leftorthogonal = true;
+                lu->arena = arena;
+                lu->d_rowperm = a.rowperm;
+                lu->d_colperm = a.colperm;
+                lu->d_colpos = a.colpos;
+                ctx->live_handles++;
+                lus[batch[t]] = lu;
+                dev_free(ctx, xbuf); // stream ordered: released after the kernel below
+            }
+            DevBuf<RRArgs> dargs(ctx);
+            TCI_CUDA(ctx, dargs.upload(args.data(), args.size()));
+            const void *fn = (const void *)k_rrlu_batch<true, true>;
+            TCI_CUDA(ctx, ctx_func_smem(ctx, fn, 227 * 1024 - 1024));
+            const RRArgs *dp = dargs.p;
+            void *kargs[] = {(void *)&dp, (void *)&Gq};
+            TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(B * Gq), dim3(T), kargs, smem, ctx->stream));
+            ctx->launches++;
+            for (int t = 0; t < B; ++t) {
+                const RRArgs &a = args[t];
+                TCI_CUDA(ctx, cudaMemcpyAsync(results[batch[t]], a.result, 32, cudaMemcpyDeviceToHost, ctx->stream));
+                TCI_CUDA(ctx, cudaMemcpyAsync(results[batch[t]] + 32, a.pivvals, (size_t)a.m * 8, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+            }
+        }
+        todo.erase(todo.begin(), todo.begin() + nb);
     }
     return TCI_OK;
 }
