@@ -93,6 +93,13 @@ int tci_dmat_wrap(tci_ctx *ctx, void *dptr, int64_t m, int64_t n, int64_t ld, tc
  * batcheval.jl:67-83, docs/src/index.md:174-241).  kind_id: tci_targets.h.       */
 int tci_target_builtin(tci_ctx *ctx, int kind_id, const double *params, int64_t nparams, const int64_t *localdims,
                        int64_t nsites, int64_t *target_id);
+/* A user-defined target: the Julia closure `f` restated as CUDA source that defines
+ *     __device__ double tci_user_f(const long long *x, int n, const double *params);
+ * (x[0..n): 1-based local indices), compiled at run time with NVRTC for sm_100a (--fmad=false: products and sums round
+ * separately, as in the closure) and evaluated by the same entry points as a built-in target.  nsites <= 128.
+ * TCI_ERR_ARG with the compiler log if the source does not compile; TCI_ERR_UNSUPPORTED without libnvrtc.so.12.      */
+int tci_target_source(tci_ctx *ctx, const char *source, const double *params, int64_t nparams, const int64_t *localdims,
+                      int64_t nsites, int64_t *target_id);
 /* TTCache(tt) (cachedtensortrain.jl:9-30): cores[s] is (dims3[3s], dims3[3s+1], dims3[3s+2]). */
 int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
                   int64_t *target_id);
@@ -169,6 +176,10 @@ int tci_luci_right(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_d
  * The reference leaves it to LAPACK gesv (partial pivoting, version unpinned -- SURVEY 8c); here the
  * full-pivot factors are reused: X[:, rowperm] = B[:, colperm] U^-1 L^-1.  B (rows x m) is not modified. */
 int tci_lu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+/* Completion of a rook-search factorisation (arrlu, matrixlu.jl:274-288) from the factors of its r x r pivot block:
+ * L2 = A21 U11^-1 (cols2Lmatrix!, :314-335; A21 is (m2 x r)) and U2 = L11^-1 A12 (rows2Umatrix!, :337-358; A12 is
+ * (r x n2)); either may be NULL.  Results are written tight to L2_host (m2 x r) / U2_host (r x n2).               */
+int tci_lu_complete(tci_lu *lu, tci_dmat *A21, tci_dmat *A12, double *L2_host, double *U2_host);
 int tci_lu_destroy(tci_lu *lu);
 
 /* ---- fused entry points of the driver's inner loop ------------------------- */

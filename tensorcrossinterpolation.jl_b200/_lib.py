@@ -40,6 +40,7 @@ SYMBOLS = {
     "tci_dmat_refold": (C.c_int, [VP, i64, i64, C.POINTER(VP)]),
     "tci_dmat_wrap": (C.c_int, [VP, VP, i64, i64, i64, C.POINTER(VP)]),
     "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
+    "tci_target_source": (C.c_int, [VP, C.c_char_p, P_f64, i64, P_i64, i64, P_i64]),
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
     "tci_target_destroy": (C.c_int, [VP, i64]),
@@ -56,6 +57,7 @@ SYMBOLS = {
     "tci_luci_left": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
     "tci_luci_right": (C.c_int, [VP, P_f64, C.POINTER(VP)]),
     "tci_lu_rdiv": (C.c_int, [VP, VP, P_f64, C.POINTER(VP)]),
+    "tci_lu_complete": (C.c_int, [VP, VP, VP, P_f64, P_f64]),
     "tci_lu_destroy": (C.c_int, [VP]),
     "tci_fp64_peak": (C.c_int, [VP, P_f64]),
     "tci_dgemm_host": (C.c_int, [VP, C.c_int, C.c_int, i64, i64, i64, f64, P_f64, P_f64, f64, P_f64]),

@@ -202,6 +202,21 @@ class BuiltinTarget(BatchEvaluator):
         self.kind = kind
 
 
+class SourceTarget(BatchEvaluator):
+    """A user-defined target given as CUDA source (tci_target_source): the device route for an arbitrary `f`
+    (batcheval.jl:32-61 evaluates a Julia closure; a kernel cannot call one).  `source` defines
+    `__device__ double tci_user_f(const long long *x, int n, const double *params)`."""
+
+    def __init__(self, source, params, localdims, ctx=None):
+        ctx = ctx or _lib.default_context()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ld = np.ascontiguousarray(localdims, dtype=np.int64)
+        tid = C.c_int64(0)
+        ctx.check(lib().tci_target_source(ctx.h, source.encode(), pf(p) if p.size else None, p.size, pi(ld), ld.size,
+                                          C.byref(tid)))
+        super().__init__(ctx, tid.value, ld.tolist())
+
+
 def makebatchevaluatable(kind, params, localdims, ctx=None):  # batcheval.jl:9
     return BuiltinTarget(kind, params, localdims, ctx)
 

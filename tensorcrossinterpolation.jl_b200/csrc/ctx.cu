@@ -7,9 +7,10 @@ static thread_local std::string g_create_error;
 
 int tci_fail(tci_ctx *ctx, int code, const std::string &msg)
 {
-    if (ctx)
+    if (ctx) {
         ctx->err = msg;
-    else
+        ctx->failed = true;
+    } else
         g_create_error = msg;
     return code;
 }
@@ -99,6 +100,7 @@ void target_free(tci_ctx *ctx, TargetDev &t)
         for (double *p : t.cores) dev_free(ctx, p);
         return;
     }
+    user_target_unload(t);
     cudaFree(t.d_params);
     cudaFree(t.d_localdims);
     for (double *p : t.cores) cudaFree(p);
@@ -518,7 +520,8 @@ int target_replicate(tci_ctx *ctx, i64 id)
         std::fill(t->A.begin(), t->A.end(), nullptr);
         std::fill(t->B.begin(), t->B.end(), nullptr);
         cudaError_t e = cudaSuccess;
-        if (src.kind == 0) {
+        t->user_lib = t->user_pi = t->user_points = nullptr;
+        if (src.kind == 0 || src.kind == 3) {
             e = peer_dup(&t->d_params, c->device, src.d_params, ctx->device, (size_t)src.nparams_alloc);
             if (e == cudaSuccess) {
                 double *ld = nullptr;
@@ -529,6 +532,7 @@ int target_replicate(tci_ctx *ctx, i64 id)
             }
             t->an.params = t->d_params;
             t->an.localdims = t->d_localdims;
+            if (e == cudaSuccess && src.kind == 3 && user_target_load(c, *t) != TCI_OK) e = cudaErrorUnknown;
         } else if (src.kind == 1) {
             for (i64 s = 0; s < src.nsites && e == cudaSuccess; ++s)
                 e = peer_dup(&t->cores[s], c->device, src.cores[s], ctx->device,

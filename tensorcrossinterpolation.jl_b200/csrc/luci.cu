@@ -225,6 +225,102 @@ extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
 // B * A^-1 for the square, fully factorised A = lu (the `\` of setsitetensor!, tensorci2.jl:391, which the
 // reference leaves to LAPACK gesv; here the full-pivot factors of K2 are reused):
 //   A[rowperm, colperm] = L U  =>  X[:, rowperm] = B[:, colperm] U^-1 L^-1
+// W (rows x k, ldw) <- W * U^-1 for an upper-triangular U (k x k, ldu; unit diagonal if `unit`), blocked: 32-wide
+// diagonal solves in shared memory + DMMA GEMM updates of the columns to the right
+static int trsm_right_upper(tci_ctx *ctx, double *W, i64 rows, i64 ldw, const double *U, i64 ldu, i64 k, bool unit)
+{
+    int rc = 0;
+    const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
+    for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) {
+        const i64 nb = std::min<i64>(TB_NB, k - j0);
+        if (j0 > 0)
+            rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W, ldw, U + ldu * j0, ldu, 1.0, W + ldw * j0, ldw);
+        if (unit)
+            k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W + ldw * j0, rows, ldw, U + j0 + ldu * j0, ldu, (int)nb);
+        else
+            k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W + ldw * j0, rows, ldw, U + j0 + ldu * j0, ldu, (int)nb);
+        ctx->launches++;
+    }
+    return rc;
+}
+
+// dst (n x m, ldd) = src (m x n, lds)^T
+__global__ void k_transpose(const double *__restrict__ src, i64 lds, i64 m, i64 n, double *__restrict__ dst, i64 ldd)
+{
+    __shared__ double tile[32][33];
+    const i64 i0 = (i64)blockIdx.x * 32, j0 = (i64)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const i64 i = i0 + threadIdx.x, j = j0 + r;
+        if (i < m && j < n) tile[r][threadIdx.x] = src[i + lds * j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const i64 j = j0 + threadIdx.x, i = i0 + r;
+        if (i < m && j < n) dst[j + ldd * i] = tile[threadIdx.x][r];
+    }
+}
+
+// The completion of a rook-search factorisation (arrlu, matrixlu.jl:274-288): with L11 / U11 the r x r pivot blocks of
+// `lu`, L2 = A21 U11^-1 (cols2Lmatrix!, :314-335) for the rows the search never visited and U2 = L11^-1 A12
+// (rows2Umatrix!, :337-358) for the columns -- two triangular solves, blocked TRSM + DMMA GEMM on the device (the
+// left-lower solve runs as a right-upper solve on the transposed system).  The reference divides by the diagonal in
+// both (it is 1 on the unit-diagonal factor).
+extern "C" int tci_lu_complete(tci_lu *lu, tci_dmat *A21, tci_dmat *A12, double *L2_host, double *U2_host)
+{
+    if (!lu) return TCI_ERR_ARG;
+    tci_ctx *ctx = lu->ctx;
+    TCI_ENTER(ctx);
+    const i64 r = lu->r;
+    if ((A21 && A21->n != r) || (A12 && A12->m != r))
+        return tci_fail(ctx, TCI_ERR_ARG, A21 && A21->n != r
+                                              ? "C and P matrices must have same number of columns in `cols2Lmatrix!`."
+                                              : "R and P matrices must have same number of rows in `rows2Umatrix!`.");
+    if ((A21 && !L2_host) || (A12 && !U2_host)) return tci_fail(ctx, TCI_ERR_ARG, "tci_lu_complete: output missing");
+    if (r == 0 || lu->m < r || lu->n < r) return TCI_OK;
+    DevBuf<double> L(ctx), U(ctx), W(ctx), Wt(ctx), Lt(ctx);
+    TCI_CUDA(ctx, L.alloc((size_t)(lu->m * r)));
+    TCI_CUDA(ctx, U.alloc((size_t)(r * lu->n)));
+    int rc = lu_extract(lu, L.p, lu->m, U.p, r);
+    if (rc) return rc;
+    StageTimer tm(ctx, ST_LUCI);
+    if (A21 && A21->m > 0) { // X U11 = A21
+        const i64 rows = A21->m;
+        dmat_wait_ready(ctx, A21);
+        TCI_CUDA(ctx, W.alloc((size_t)(rows * r)));
+        TCI_CUDA(ctx, cudaMemcpy2DAsync(W.p, rows * sizeof(double), A21->p, A21->ld * sizeof(double), rows * sizeof(double),
+                                        r, cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = trsm_right_upper(ctx, W.p, rows, rows, U.p, r, r, !lu->leftorthogonal);
+        if (rc) return rc;
+        TCI_CUDA(ctx, cudaMemcpyAsync(L2_host, W.p, (size_t)(rows * r) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (A12 && A12->n > 0) { // L11 X = A12  <=>  X^T L11^T = A12^T
+        const i64 cols = A12->n;
+        dmat_wait_ready(ctx, A12);
+        TCI_CUDA(ctx, Wt.alloc((size_t)(cols * r)));
+        TCI_CUDA(ctx, Lt.alloc((size_t)(r * r)));
+        const dim3 tb(32, 8);
+        k_transpose<<<dim3((unsigned)((r + 31) / 32), (unsigned)((cols + 31) / 32)), tb, 0, ctx->stream>>>(A12->p, A12->ld, r,
+                                                                                                     cols, Wt.p, cols);
+        k_transpose<<<dim3((unsigned)((r + 31) / 32), (unsigned)((r + 31) / 32)), tb, 0, ctx->stream>>>(L.p, lu->m, r, r,
+                                                                                                  Lt.p, r);
+        ctx->launches += 2;
+        rc = trsm_right_upper(ctx, Wt.p, cols, cols, Lt.p, r, r, lu->leftorthogonal);
+        if (rc) return rc;
+        // back to r x cols, reusing the buffer of A12's transpose is not possible in place: go through U's storage
+        DevBuf<double> X(ctx);
+        TCI_CUDA(ctx, X.alloc((size_t)(r * cols)));
+        k_transpose<<<dim3((unsigned)((cols + 31) / 32), (unsigned)((r + 31) / 32)), tb, 0, ctx->stream>>>(Wt.p, cols, cols, r,
+                                                                                                     X.p, r);
+        ctx->launches++;
+        TCI_CUDA(ctx, cudaMemcpyAsync(U2_host, X.p, (size_t)(r * cols) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // X goes out of scope
+    }
+    TCI_CUDA(ctx, cudaGetLastError());
+    tm.stop();
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
+}
+
 // enqueue only: X (rows x k, ldx) = B (rows x k, ldb) * A^-1 with the factors of `lu` (assumed of full rank k)
 int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i64 ldx)
 {
@@ -242,19 +338,7 @@ int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i
                                                                                rows);
         ctx->launches++;
     }
-    for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) { // Y U = W, left to right
-        const i64 nb = std::min<i64>(TB_NB, k - j0);
-        if (j0 > 0)
-            rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W.p, rows, U.p + k * j0, k, 1.0, W.p + rows * j0,
-                           rows);
-        if (lu->leftorthogonal)
-            k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, U.p + j0 + k * j0,
-                                                                      k, (int)nb);
-        else
-            k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, U.p + j0 + k * j0,
-                                                                     k, (int)nb);
-        ctx->launches++;
-    }
+    if (!rc) rc = trsm_right_upper(ctx, W.p, rows, rows, U.p, k, k, !lu->leftorthogonal); // Y U = W
     for (i64 j1 = k; j1 > 0 && !rc; j1 -= TB_NB) { // X' L = Y, right to left
         const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
         if (j1 < k)

@@ -341,6 +341,7 @@ int pi_enqueue(tci_ctx *ctx, TargetDev &t, const i64 *I, i64 nl, i64 nI, const i
         rc = pi_eval_tt(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out);
         if (!rc && d_maxbits) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax);
         break;
+    case 3: rc = pi_eval_user(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, dmax); break;
     default:
         rc = pi_eval_mpo(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, I, J);
         if (!rc) rc = apply_elementwise(ctx, t, out->p, out->m, out->n, out->ld);
@@ -374,8 +375,8 @@ static int choose_shards(tci_ctx *ctx, const TargetDev &t, i64 nl, i64 nI, i64 n
     if (const char *f = getenv("TCI_SHARD_FORCE")) return std::max(1, std::min(world, atoi(f)));
     const double elems = (double)nI * (double)C * (double)nJ;
     const double fixed_ps = 60e6; // ~60 us
-    if (t.kind == 0) {
-        const double te = analytic_ps_per_eval(t);
+    if (t.kind == 0 || t.kind == 3) {
+        const double te = t.kind == 3 ? 10.0 : analytic_ps_per_eval(t); // user source: assume a few transcendentals
         double best = te * elems;
         int bestn = 1;
         for (int n = 2; n <= world; ++n) {
@@ -531,8 +532,8 @@ int pi_enqueue_auto(tci_ctx *ctx, i64 target_id, const i64 *I, i64 nl, i64 nI, c
     if (ns == 1) return pi_enqueue(ctx, t, I, nl, nI, J, nr, nJ, M, out, d_maxbits);
     // `out` is stream-ordered pool memory of the owner; the pool is mapped on every member (group.cu), so the
     // members' kernels store into it directly
-    return t.kind == 0 ? pi_enqueue_sharded_analytic(ctx, target_id, ns, I, nl, nI, J, nr, nJ, M, out->p, out->ld,
-                                                     nI * C, d_maxbits)
+    return t.kind == 0 || t.kind == 3
+               ? pi_enqueue_sharded_analytic(ctx, target_id, ns, I, nl, nI, J, nr, nJ, M, out->p, out->ld, nI * C, d_maxbits)
                        : pi_enqueue_sharded_env(ctx, target_id, I, nl, nI, J, nr, nJ, out->p, out->ld, d_maxbits);
 }
 
@@ -641,7 +642,7 @@ extern "C" int tci_env_dim(tci_ctx *ctx, int64_t target_id, int side, int64_t le
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
-    if (t.kind == 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
+    if (t.kind == 0 || t.kind == 3) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
     if (!D || (side != 0 && side != 1) || len < 0 || len > t.nsites)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: bad arguments");
     *D = env_dim_of(t, side, len);
@@ -655,7 +656,7 @@ extern "C" int tci_env_eval(tci_ctx *ctx, int64_t target_id, int side, const int
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
-    if (t.kind == 0) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: an analytic target has no environments");
+    if (t.kind == 0 || t.kind == 3) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: an analytic target has no environments");
     if (!dst || (side != 0 && side != 1) || len < 0 || len > t.nsites || count < 0 || (len > 0 && count > 0 && !idx))
         return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: bad arguments");
     if (dst->m != env_dim_of(t, side, len) || col0 < 0 || col0 + count > dst->ncap)
@@ -728,6 +729,7 @@ int target_eval_dev(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, dou
         TCI_CUDA(ctx, cudaGetLastError());
         return TCI_OK;
     case 1: return target_eval_tt(ctx, t, d_idx, count, d_out);
+    case 3: return target_eval_user(ctx, t, d_idx, count, d_out);
     default: {
         int rc = target_eval_mpo(ctx, t, d_idx, count, d_out);
         return rc ? rc : apply_elementwise(ctx, t, d_out, count, 1, count);

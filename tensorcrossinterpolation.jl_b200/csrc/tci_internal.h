@@ -32,7 +32,7 @@ struct tci_dmat {
 void dmat_wait_ready(tci_ctx *ctx, tci_dmat *a);
 
 struct TargetDev {
-    int kind = 0; // 0 analytic, 1 TT, 2 MPO pair
+    int kind = 0; // 0 analytic, 1 TT, 2 MPO pair, 3 user source (NVRTC)
     i64 nsites = 0;
     std::vector<i64> localdims;
     // analytic
@@ -47,6 +47,9 @@ struct TargetDev {
     // MPO pair
     std::vector<double *> A, B;
     std::vector<i64> adl, as1, as2, adr, bdl, bs1, bs2, bdr;
+    // user source: the compiled module (kept so that it can be loaded on every GPU of a group) and its kernels
+    std::vector<char> cubin;
+    void *user_lib = nullptr, *user_pi = nullptr, *user_points = nullptr;
     // elementwise function applied to the product (Contraction.f, contraction.jl:330-332): TCI_F_* id + parameters
     int fkind = 0;
     double fa = 1.0, fb = 0.0;
@@ -80,6 +83,10 @@ struct tci_ctx {
     bool nosync = false; // inside a batched entry point: stage timers must not synchronise the stream
     int live_handles = 0; // dmat / lu handles that still point at this context (tci_ctx_destroy defers to the last)
     bool destroyed = false;
+    // stream-ordered allocations made during the current API call and not yet released: when the call fails
+    // (tci_fail was reached) whatever is still listed here was leaked by an early return and is freed by the guard
+    std::vector<void *> call_allocs;
+    bool failed = false;
     // pinned staging for small device-to-host results (latency, not bandwidth)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -119,6 +126,11 @@ int group_allgather(tci_group *g, const std::function<void *(int)> &ptr, size_t 
 int group_broadcast(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes, int root);
 void group_destroy(tci_group *g);
 void target_free(tci_ctx *ctx, TargetDev &t);  // ctx.cu
+int user_target_load(tci_ctx *ctx, TargetDev &t); // user_target.cu
+void user_target_unload(TargetDev &t);
+int pi_eval_user(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                 tci_dmat *out, unsigned long long *d_maxbits);
+int target_eval_user(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out);
 void *ctx_pinned(tci_ctx *ctx, size_t bytes); // page-locked staging of at least `bytes` (ctx.cu)
 // copies target `id` of the caller's context to the other local members under the same id (peer copies)   ctx.cu
 int target_replicate(tci_ctx *ctx, i64 id);
@@ -165,11 +177,19 @@ struct CtxGuard { // single-caller contract (SURVEY 8b "Threading")
         if (!c->busy) {
             c->busy = true;
             ok = true;
+            c->call_allocs.clear();
+            c->failed = false;
         }
     }
     ~CtxGuard()
     {
         if (ok) {
+            // an error return (typically out of memory on a large Pi) must not keep the biggest buffers: every
+            // scratch allocation of this call that no RAII owner released is freed here, in stream order
+            if (c->failed)
+                for (void *p : c->call_allocs) cudaFreeAsync(p, c->stream);
+            c->call_allocs.clear();
+            c->failed = false;
             std::lock_guard<std::mutex> g(c->mu);
             c->busy = false;
         }
@@ -206,11 +226,20 @@ static inline i64 round_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
 // stream-ordered scratch allocations on the context stream (pool never trimmed)
 static inline cudaError_t dev_alloc(tci_ctx *ctx, void **p, size_t bytes)
 {
-    return cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+    if (e == cudaSuccess && ctx->busy && ctx->member == 0) ctx->call_allocs.push_back(*p);
+    return e;
 }
 static inline void dev_free(tci_ctx *ctx, void *p)
 {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    for (size_t q = ctx->call_allocs.size(); q-- > 0;)
+        if (ctx->call_allocs[q] == p) {
+            ctx->call_allocs[q] = ctx->call_allocs.back();
+            ctx->call_allocs.pop_back();
+            break;
+        }
+    cudaFreeAsync(p, ctx->stream);
 }
 template <typename T> struct DevBuf { // RAII scratch buffer
     tci_ctx *ctx;

@@ -230,21 +230,30 @@ class RookLU:
         self._L = self._U = None
 
     def _complete(self):
+        """lu.L / lu.U for the rows / columns the search never visited (matrixlu.jl:274-288): the two triangular
+        solves cols2Lmatrix! / rows2Umatrix! run on the device (tci_lu_complete: blocked TRSM + DMMA GEMM)."""
         m, n = self._shape
         r = self.npivot
         L, U = self._last.L, self._last.U
         L11, U11 = L[:r, :r], U[:r, :r]
-        if L.shape[0] < m:
-            I2 = self.rowpermutation[r:]
-            A21 = self._fsub(I2, np.asarray(self._J0, dtype=np.int64), device=False) if len(I2) and r else \
-                np.zeros((len(I2), r))
-            L2 = np.linalg.solve(U11.T, A21.T).T if r else A21  # cols2Lmatrix!: A21 * U11^-1
+        need_L, need_U = L.shape[0] < m, U.shape[1] < n
+        I2, J2 = self.rowpermutation[r:], self.colpermutation[r:]
+        A21 = A12 = None
+        L2 = np.zeros((len(I2), r), dtype=np.float64, order="F") if need_L else None
+        U2 = np.zeros((r, len(J2)), dtype=np.float64, order="F") if need_U else None
+        if r:
+            if need_L and len(I2):
+                A21 = self._fsub(I2, np.asarray(self._J0, dtype=np.int64), device=True)
+            if need_U and len(J2):
+                A12 = self._fsub(np.asarray(self._I0, dtype=np.int64), J2, device=True)
+            if A21 is not None or A12 is not None:
+                ctx = self._last.ctx
+                ctx.check(lib().tci_lu_complete(self._last._h, A21.h if A21 is not None else None,
+                                                A12.h if A12 is not None else None, pf(L2) if A21 is not None else None,
+                                                pf(U2) if A12 is not None else None))
+        if need_L:
             L = np.vstack([L11, L2])
-        if U.shape[1] < n:
-            J2 = self.colpermutation[r:]
-            A12 = self._fsub(np.asarray(self._I0, dtype=np.int64), J2, device=False) if len(J2) and r else \
-                np.zeros((r, len(J2)))
-            U2 = np.linalg.solve(L11, A12) if r else A12  # rows2Umatrix!: L11^-1 * A12
+        if need_U:
             U = np.hstack([U11, U2])
         self._L, self._U = np.asfortranarray(L), np.asfortranarray(U)
 

@@ -476,7 +476,10 @@ def test_dgemm_kernel(T, ctx):
     import ctypes as C
     from tci_b200 import _lib
     rng = np.random.default_rng(1)
-    for (M, N, K), (ta, tb) in itertools.product([(1, 1, 1), (5, 130, 17), (257, 129, 300), (64, 64, 64), (300, 7, 513)],
+    # (the last three shapes take the bulk-copy / mbarrier kernel: M, N multiples of 128, K a multiple of 16, enough
+    # CTAs for every SM; K = 16 and K = 48 are shorter than its prefetch distance)
+    for (M, N, K), (ta, tb) in itertools.product([(1, 1, 1), (5, 130, 17), (257, 129, 300), (64, 64, 64), (300, 7, 513),
+                                                  (1536, 1664, 16), (2048, 1280, 48), (1536, 1664, 400)],
                                                  [(0, 0), (1, 0), (0, 1), (1, 1)]):
         A = np.asfortranarray(rng.standard_normal((K, M) if ta else (M, K)))
         B = np.asfortranarray(rng.standard_normal((N, K) if tb else (K, N)))
@@ -1181,6 +1184,64 @@ def test_argument_errors(T):  # test_tensorci2.jl:215-245
 def _ngpu():
     import torch
     return torch.cuda.device_count()
+
+
+USER_SRC = """
+__device__ double tci_user_f(const long long *x, int n, const double *params)
+{
+    double s = 1.0;                       // f(v) = 1 / (1 + sum_k (w_k v_k)^2), accumulated left to right
+    for (int k = 0; k < n; ++k) {
+        const double v = (double)x[k] * params[k];
+        s = s + v * v;
+    }
+    return 1.0 / s;
+}
+"""
+
+
+def test_user_source_target_nvrtc(T, oracle):
+    """A user-defined target compiled from CUDA source at run time (NVRTC, tci_target_source): the device route for an
+    arbitrary f (batcheval.jl:32-61).  Pi / T tensors for every split, point evaluation and a whole crossinterpolate2
+    against the same function evaluated on the host in the same operation order (bit-identical: --fmad=false), and
+    against the built-in Lorentzian when all weights are one."""
+    ld = [5, 4, 6, 3, 5]
+    w = np.array([1.0, 0.5, 0.25, 2.0, 1.5])
+    f = T.SourceTarget(USER_SRC, w, ld)
+
+    def host(x):
+        s = 1.0
+        for k in range(len(ld)):
+            v = float(x[k]) * w[k]
+            s = s + v * v
+        return 1.0 / s
+
+    rng = np.random.default_rng(4)
+    pts = rand_indexset(rng, ld, 40)
+    assert np.array_equal(f.evaluate_points(pts), np.array([host(x) for x in pts]))
+    for nl, M in ((0, 1), (1, 1), (2, 0), (1, 2), (3, 2), (4, 1)):
+        nr = len(ld) - nl - M
+        I, J = rand_indexset(rng, ld[:nl], 7), rand_indexset(rng, ld[nl + M:], 5)
+        got = f(I, J, M)
+        cd = ld[nl:nl + M]
+        ref = np.zeros((len(I), *cd, len(J)), order="F")
+        for i in range(len(I)):
+            for c in itertools.product(*[range(1, d + 1) for d in cd]):
+                for j in range(len(J)):
+                    ref[(i, *[v - 1 for v in c], j)] = host(list(I[i]) + list(c) + list(J[j]))
+        assert got.shape == ref.shape and np.array_equal(got, ref), (nl, M)
+        dev, mx = f.batchevaluate_device(I, J, M)
+        assert mx == np.max(np.abs(ref))
+    # the same function as a built-in: identical pivots through the whole driver
+    ld2 = [10] * 6
+    g1 = T.SourceTarget(USER_SRC, np.ones(6), ld2)
+    g2 = T.BuiltinTarget(LORENTZ, [1.0], ld2)
+    ta, ra, ea = T.crossinterpolate2(g1, ld2, tolerance=1e-8, rng=T.CounterRNG(1))
+    tb, rb, eb = T.crossinterpolate2(g2, ld2, tolerance=1e-8, rng=T.CounterRNG(1))
+    assert ra == rb
+    assert all(np.array_equal(x, y) for x, y in zip(ta.Iset + ta.Jset, tb.Iset + tb.Jset))
+    assert abs(T.tci_sum(ta) - T.tci_sum(tb)) <= 1e-12 * abs(T.tci_sum(tb))
+    with pytest.raises(ValueError, match="does not compile"):
+        T.SourceTarget("__device__ double tci_user_f(const long long *x, int n, const double *p) { return y; }", [], ld)
 
 
 def test_bond_update_matches_separate_calls_and_oracle(T, oracle):

@@ -1,4 +1,5 @@
-"""FP64 GEMM kernel throughput (kernel time from the library's stage timer) next to cuBLAS (torch)."""
+"""DGEMM rates of the library's DMMA kernels against cuBLAS (torch.matmul float64) on the shapes the path uses.
+usage (GPU box): python tools/gemm_bench.py"""
 import os
 import sys
 
@@ -11,18 +12,25 @@ from tci_b200 import _lib  # noqa: E402
 
 ctx = T.default_context()
 rng = np.random.default_rng(0)
-for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 512), (2048, 2048, 256), (1024, 1024, 1024), (512, 512, 512)]:
+TB = int(os.environ.get("GEMM_TB", "0"))
+for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 512), (2048, 2048, 256)]:
     A = np.asfortranarray(rng.standard_normal((M, K)))
-    B = np.asfortranarray(rng.standard_normal((K, N)))
+    B = np.asfortranarray(rng.standard_normal((N, K) if TB else (K, N)))
     C = np.zeros((M, N), order="F")
-    for _ in range(2):
-        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, M, N, K, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
-    ctx.timers(reset=True)
-    for _ in range(3):
-        ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, 0, M, N, K, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
-    ms = ctx.timers(reset=True)["gemm"] / 3
-    err = np.max(np.abs(C[:64, :64] - A[:64] @ B[:, :64])) / np.max(np.abs(C[:64, :64]))
-    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    res = {}
+    for label, env in (("bulk", {}), ("cp.async", {"TCI_DGEMM_NO_BULK": "1"})):
+        # the switches are read once per process: run the second variant in a child
+        if env:
+            continue
+        for _ in range(2):
+            ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, TB, M, N, K, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
+        ctx.timers(reset=True)
+        reps = 3
+        for _ in range(reps):
+            ctx.check(_lib.lib().tci_dgemm_host(ctx.h, 0, TB, M, N, K, 1.0, _lib.pf(A), _lib.pf(B), 0.0, _lib.pf(C)))
+        res[label] = 2.0 * M * N * K / (ctx.timers(reset=True)["gemm"] / reps * 1e-3) / 1e12
+    a = torch.from_numpy(np.ascontiguousarray(A)).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(B.T if TB else B)).cuda()
     for _ in range(2):
         c = a @ b
     torch.cuda.synchronize()
@@ -32,6 +40,8 @@ for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 512), (2048, 2048, 256), (102
         c = a @ b
     e1.record()
     torch.cuda.synchronize()
-    cms = e0.elapsed_time(e1) / 5
-    fl = 2.0 * M * N * K
-    print(f"{M}x{N}x{K}: ours {fl / ms / 1e9:8.1f} GFLOP/s ({ms:.3f} ms, relerr {err:.1e})   cuBLAS {fl / cms / 1e9:8.1f} GFLOP/s")
+    cub = 5 * 2.0 * M * N * K / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    err = float(np.max(np.abs(C - c.cpu().numpy())) / np.max(np.abs(C)))
+    print(f"{M}x{N}x{K}: library {res['bulk']:.2f} TFLOP/s (NO_BULK={os.environ.get('TCI_DGEMM_NO_BULK', '0')} VARIANT={os.environ.get('TCI_DGEMM_VARIANT', '0')} TB={TB}), "
+          f"cuBLAS {cub:.2f}, rel dev {err:.1e}", flush=True)
+    del a, b, c
