@@ -255,7 +255,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int BM, int BN, int NWM, int NWN, bool TA, bool TB, int KT = MK>
+template <int BM, int BN, int NWM, int NWN, bool TA, bool TB, int KT = MK, int NST = ASTAGES>
 __global__ void __launch_bounds__(32 * NWM * NWN)
     k_dgemm_mma_async(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
                       const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
     constexpr int B_ROW = TB ? BN + 4 : KT + 4, B_ROWS = TB ? KT : BN;
     constexpr int A_SZ = A_ROW * A_ROWS, B_SZ = B_ROW * B_ROWS;
     extern __shared__ __align__(16) double dsm[];
-    double *const Asm = dsm;                   // [ASTAGES][A_SZ]
-    double *const Bsm = dsm + ASTAGES * A_SZ;  // [ASTAGES][B_SZ]
+    double *const Asm = dsm;                   // [NST][A_SZ]
+    double *const Bsm = dsm + NST * A_SZ;  // [NST][B_SZ]
 
     A += strideA * blockIdx.z + (offA ? offA[blockIdx.z] : 0);
     B += strideB * blockIdx.z + (offB ? offB[blockIdx.z] : 0);
@@ -321,16 +321,16 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
 
     const i64 nkt = (K + KT - 1) / KT;
 #pragma unroll
-    for (int st = 0; st < ASTAGES - 1; ++st) {
+    for (int st = 0; st < NST - 1; ++st) {
         if (st < nkt) load_stage(st, (i64)st * KT);
         cp_async_commit();
     }
     for (i64 kt = 0; kt < nkt; ++kt) {
-        cp_async_wait<ASTAGES - 2>(); // tile kt has landed
+        cp_async_wait<NST - 2>(); // tile kt has landed
         __syncthreads();              // ... for everybody, and everybody is done with tile kt-1
-        if (kt + ASTAGES - 1 < nkt) load_stage((int)((kt + ASTAGES - 1) % ASTAGES), (kt + ASTAGES - 1) * KT);
+        if (kt + NST - 1 < nkt) load_stage((int)((kt + NST - 1) % NST), (kt + NST - 1) * KT);
         cp_async_commit();
-        const double *as = Asm + (kt % ASTAGES) * A_SZ, *bs = Bsm + (kt % ASTAGES) * B_SZ;
+        const double *as = Asm + (kt % NST) * A_SZ, *bs = Bsm + (kt % NST) * B_SZ;
 #pragma unroll
         for (int k4 = 0; k4 < KT; k4 += 4) {
             double af[TI], bf[TJ];
@@ -363,217 +363,38 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
         }
 }
 
-// ---- DMMA kernel fed by bulk copies (cp.async.bulk, SASS UBLKCP) through an mbarrier ring -------------------------
-// The cp.async variant above spends ~20 % of its time outside the DMMA pipe: every k-tile ends in a __syncthreads (the
-// two warps of an SM sub-partition reach it together, so the pipe drains) followed by 8 cp.async + address arithmetic
-// per thread.  Here the operand tiles move with ONE bulk copy per contiguous tile row (1 KB along the tile's long side,
-// or MK doubles along k), every thread issues at most one copy per k-tile, completion is counted on a per-stage `full`
-// mbarrier, and a stage is handed back through an `empty` mbarrier that is only waited for two tiles later -- the
-// warps never meet at a CTA-wide barrier inside the main loop and may drift a whole tile apart.
-// Shapes: M % 128 == 0, N % 128 == 0, K % 16 == 0, 16-byte aligned operands (the launcher checks; others take the
-// cp.async kernel).  Shared layouts and fragment loads are those of k_dgemm_mma_async.
-#define BSTAGES 5
-__device__ __forceinline__ unsigned g_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void g_mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void g_mbar_arrive(unsigned bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
-                 "bra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
-                 "r"(parity)
-                 : "memory");
-}
-
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
-    k_dgemm_mma_bulk(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
-                     const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
-                     i64 strideC, const i64 *__restrict__ offA, const i64 *__restrict__ offB)
-{
-    constexpr int BM = 128, BN = 128, NWM = 2, NWN = 4, TI = BM / NWM / 8, TJ = BN / NWN / 8, S = BSTAGES;
-    constexpr int A_ROW = TA ? MK + 4 : BM + 4, A_ROWS = TA ? BM : MK;
-    constexpr int B_ROW = TB ? BN + 4 : MK + 4, B_ROWS = TB ? MK : BN;
-    constexpr int A_SZ = A_ROW * A_ROWS, B_SZ = B_ROW * B_ROWS;
-    constexpr int NCA = A_ROWS, NCB = B_ROWS, NCOPY = NCA + NCB; // one bulk copy per tile row; NCOPY <= 256
-    constexpr unsigned A_BYTES = (TA ? MK : BM) * 8, B_BYTES = (TB ? BN : MK) * 8;
-    constexpr int NIW = (NCOPY + 31) / 32; // warps that issue copies
-    extern __shared__ __align__(16) double dsm[];
-    double *const Asm = dsm;
-    double *const Bsm = dsm + S * A_SZ;
-    unsigned long long *const bars = reinterpret_cast<unsigned long long *>(dsm + S * (A_SZ + B_SZ)); // full[S], empty[S]
-
-    A += strideA * blockIdx.z + (offA ? offA[blockIdx.z] : 0);
-    B += strideB * blockIdx.z + (offB ? offB[blockIdx.z] : 0);
-    C += strideC * blockIdx.z;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp % NWM) * (BM / NWM), wn = (warp / NWM) * (BN / NWN);
-    const int fr = lane >> 2, fk = lane & 3;
-    const i64 m0 = (i64)blockIdx.x * BM, n0 = (i64)blockIdx.y * BN;
-    const unsigned bar0 = g_smem_u32(bars);
-    if (tid == 0) {
-        for (int q = 0; q < S; ++q) {
-            g_mbar_init(bar0 + 8 * q, NIW);         // full: one arrive.expect_tx per issuing WARP
-            g_mbar_init(bar0 + 8 * (S + q), 8);     // empty: one arrive per warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // this thread's copy of a stage: source row pointer at k0 = 0, its advance per k-tile, destination offset, size
-    const bool issuer = tid < NCOPY;
-    const bool isA = tid < NCA;
-    const int row = isA ? tid : tid - NCA;
-    const double *src = nullptr;
-    i64 kstep = 0;
-    unsigned dst_off = 0, bytes = 0;
-    if (issuer) {
-        if (isA) {
-            src = TA ? A + lda * (m0 + row) : A + m0 + lda * row;       // TA: row = m, k contiguous ; else row = k
-            kstep = TA ? (i64)MK : lda * MK;
-            dst_off = (unsigned)(row * A_ROW * 8);
-            bytes = A_BYTES;
-        } else {
-            src = TB ? B + n0 + ldb * row : B + ldb * (n0 + row);       // TB: row = k, n contiguous ; else row = n
-            kstep = TB ? ldb * MK : (i64)MK;
-            dst_off = (unsigned)((S * A_SZ + row * B_ROW) * 8);
-            bytes = B_BYTES;
-        }
-    }
-    const unsigned dsm0 = g_smem_u32(dsm);
-    // bytes this WARP moves per stage (one expect_tx per warp: 256 per-thread arrivals on one mbarrier cost more
-    // shared-memory pipe time than the fragment loads)
-    unsigned warp_bytes = bytes;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_bytes += __shfl_xor_sync(0xffffffffu, warp_bytes, o);
-    const bool warp_issues = warp < NIW;
-    auto issue = [&](i64 kt) { // tile kt into stage kt % S (called by all lanes of an issuing warp)
-        const int st = (int)(kt % S);
-        const unsigned full = bar0 + 8 * st;
-        if (lane == 0) g_mbar_expect_tx(full, warp_bytes);
-        __syncwarp();
-        if (issuer) g_bulk_g2s(dsm0 + dst_off + (unsigned)(st * (isA ? A_SZ : B_SZ) * 8), src + kstep * kt, bytes, full);
-    };
-
-    double acc[TI][TJ][2];
-#pragma unroll
-    for (int i = 0; i < TI; ++i)
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    const i64 nkt = K / MK;
-    if (warp_issues)
-        for (i64 kt = 0; kt < S - 2 && kt < nkt; ++kt) issue(kt); // prefetch distance S - 2
-    for (i64 kt = 0; kt < nkt; ++kt) {
-        // refill: tile kt + S - 2 goes into the stage that held tile kt - 2, which every warp has released by now
-        // unless it lags a whole tile behind
-        const i64 nk = kt + S - 2;
-        if (warp_issues && nk < nkt) {
-            if (kt >= 2) g_mbar_wait(bar0 + 8 * (S + (int)(nk % S)), (unsigned)(((kt - 2) / S) & 1));
-            issue(nk);
-        }
-        const int st = (int)(kt % S);
-        g_mbar_wait(bar0 + 8 * st, (unsigned)((kt / S) & 1));
-        const double *as = Asm + st * A_SZ, *bs = Bsm + st * B_SZ;
-#pragma unroll
-        for (int k4 = 0; k4 < MK; k4 += 4) {
-            double af[TI], bf[TJ];
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-                af[i] = TA ? as[(wm + 8 * i + fr) * A_ROW + k4 + fk] : as[(k4 + fk) * A_ROW + wm + 8 * i + fr];
-#pragma unroll
-            for (int j = 0; j < TJ; ++j)
-                bf[j] = TB ? bs[(k4 + fk) * B_ROW + wn + 8 * j + fr] : bs[(wn + 8 * j + fr) * B_ROW + k4 + fk];
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-        __syncwarp();
-        if (lane == 0) g_mbar_arrive(bar0 + 8 * (S + st)); // this warp is done with the stage
-    }
-#pragma unroll
-    for (int j = 0; j < TJ; ++j)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const i64 gn = n0 + wn + 8 * j + 2 * fk + c;
-#pragma unroll
-            for (int i = 0; i < TI; ++i) {
-                const i64 gm = m0 + wm + 8 * i + fr;
-                const double v = alpha * acc[i][j][c];
-                double *cp = C + gm + ldc * gn;
-                *cp = (beta == 0.0) ? v : fma(beta, *cp, v);
-            }
-        }
-}
-
-template <bool TA, bool TB>
-static int launch_bulk_one(tci_ctx *ctx, dim3 grid, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda, i64 sA,
-                           const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, const i64 *offA,
-                           const i64 *offB)
-{
-    constexpr int A_SZ = (TA ? MK + 4 : 128 + 4) * (TA ? 128 : MK), B_SZ = (TB ? 128 + 4 : MK + 4) * (TB ? MK : 128);
-    constexpr size_t smem = (size_t)BSTAGES * (A_SZ + B_SZ) * sizeof(double) + 2 * BSTAGES * 8;
-    auto fn = k_dgemm_mma_bulk<TA, TB>;
-    TCI_CUDA(ctx, ctx_func_smem(ctx, (const void *)fn, (int)smem));
-    fn<<<grid, 256, smem, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-    ctx->launches++;
-    return TCI_OK;
-}
-
-static int launch_dgemm_mma_bulk(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A,
-                                 i64 lda, i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc,
-                                 i64 sC, i64 batch, const i64 *offA, const i64 *offB)
-{
-    dim3 grid((unsigned)(M / 128), (unsigned)(N / 128), (unsigned)batch);
-    if (!tA && !tB) return launch_bulk_one<false, false>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-    if (tA && !tB) return launch_bulk_one<true, false>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-    if (!tA && tB) return launch_bulk_one<false, true>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-    return launch_bulk_one<true, true>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-}
-
-template <int BM, int BN, int NWM, int NWN, bool TA, bool TB, int KT = MK>
+// (A variant fed by cp.async.bulk copies through an mbarrier ring -- one bulk copy per contiguous tile row, no CTA-wide
+// barrier in the main loop -- was built and measured in round 2: 26.0 TFLOP/s at 4096^3 against 29.9 for the cp.async
+// kernel below, also with both operands in 1 KB rows (24.2), so it was dropped.  What did help is halving the CTA:
+// 128 x 64 tiles with 4 warps leave room for TWO CTAs per SM, which drift apart so that one issues DMMAs while the
+// other sits at its barrier or issues its copies: 33.0 TFLOP/s at 4096^3, see dgemm_dev_batched_off.)
+template <int BM, int BN, int NWM, int NWN, bool TA, bool TB, int KT = MK, int NST = ASTAGES>
 static int launch_async_one(tci_ctx *ctx, dim3 grid, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda, i64 sA,
                             const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC,
                             const i64 *offA, const i64 *offB)
 {
     constexpr int A_SZ = (TA ? KT + 4 : BM + 4) * (TA ? BM : KT), B_SZ = (TB ? BN + 4 : KT + 4) * (TB ? KT : BN);
-    constexpr size_t smem = (size_t)ASTAGES * (A_SZ + B_SZ) * sizeof(double);
-    auto fn = k_dgemm_mma_async<BM, BN, NWM, NWN, TA, TB, KT>;
+    constexpr size_t smem = (size_t)NST * (A_SZ + B_SZ) * sizeof(double);
+    auto fn = k_dgemm_mma_async<BM, BN, NWM, NWN, TA, TB, KT, NST>;
     TCI_CUDA(ctx, ctx_func_smem(ctx, (const void *)fn, (int)smem));
     fn<<<grid, 32 * NWM * NWN, smem, ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
     ctx->launches++;
     return TCI_OK;
 }
 
-template <int BM, int BN, int NWM, int NWN, int KT = MK>
+template <int BM, int BN, int NWM, int NWN, int KT = MK, int NST = ASTAGES>
 static int launch_dgemm_mma_async(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A,
                                   i64 lda, i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc,
                                   i64 sC, i64 batch, const i64 *offA, const i64 *offB)
 {
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)batch);
     if (!tA && !tB)
-        return launch_async_one<BM, BN, NWM, NWN, false, false, KT>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+        return launch_async_one<BM, BN, NWM, NWN, false, false, KT, NST>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
     if (tA && !tB)
-        return launch_async_one<BM, BN, NWM, NWN, true, false, KT>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+        return launch_async_one<BM, BN, NWM, NWN, true, false, KT, NST>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
     if (!tA && tB)
-        return launch_async_one<BM, BN, NWM, NWN, false, true, KT>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
-    return launch_async_one<BM, BN, NWM, NWN, true, true, KT>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+        return launch_async_one<BM, BN, NWM, NWN, false, true, KT, NST>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
+    return launch_async_one<BM, BN, NWM, NWN, true, true, KT, NST>(ctx, grid, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB);
 }
 
 template <int BM, int BN, int NWM, int NWN>
@@ -661,28 +482,21 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         const bool aligned16 = (((size_t)A | (size_t)B) & 15) == 0 && !((lda | ldb | strideA | strideB) & 1) &&
                                ((!offA && !offB) || offsets_even);
         static const int use_async = getenv("TCI_DGEMM_NO_ASYNC") ? 0 : 1;
-        static const int use_bulk = getenv("TCI_DGEMM_NO_BULK") ? 0 : 1;
         static const int variant = getenv("TCI_DGEMM_VARIANT") ? atoi(getenv("TCI_DGEMM_VARIANT")) : 0;
-        if (variant == 2 && use_mma && aligned16 && big_ctas >= ctx->sm_count && M >= 96 && N >= 96) { // 32-deep k-tiles
-            int rc = launch_dgemm_mma_async<128, 128, 2, 4, 32>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb,
-                                                                strideB, beta, C, ldc, strideC, batch, offA, offB);
+        // 128 x 64 tiles, 4 warps per CTA, TWO CTAs per SM: the CTAs drift apart, so one issues DMMAs while the other
+        // sits at its barrier or issues its copies (measured: 4096^3 29.9 -> 33.0 TFLOP/s, 8192^2 x 512 28.7 -> 31.5, the
+        // config-5 MPO Pi 27.6 -> 29.4; with fewer than ~4 CTAs per SM the 8-warp 128 x 128 kernel stays ahead:
+        // 2048^2 x 256 24.9 vs 22.7).  Also tried: 16 warps of 32 x 32 (28.2), 32-deep k-tiles (30.8 with 8 warps, 25.9
+        // with 4: shared memory then allows one CTA per SM), 4 stages (32.4), bulk copies + mbarriers (26.0).
+        const i64 half_ctas = ((M + 127) / 128) * ((N + 63) / 64) * batch;
+        if (variant != 9 && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
+            int rc = launch_dgemm_mma_async<128, 64, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
+                                                           beta, C, ldc, strideC, batch, offA, offB);
             if (rc) return rc;
             TCI_CUDA(ctx, cudaGetLastError());
             return TCI_OK;
         }
-        if (variant == 1 && use_mma && aligned16 && big_ctas >= ctx->sm_count && M >= 96 && N >= 96) { // 16 warps, 32x32 each
-            int rc = launch_dgemm_mma_async<128, 128, 4, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
-                                                            beta, C, ldc, strideC, batch, offA, offB);
-            if (rc) return rc;
-            TCI_CUDA(ctx, cudaGetLastError());
-            return TCI_OK;
-        }
-        if (use_mma && use_bulk && aligned16 && !force_tile && M % 128 == 0 && N % 128 == 0 && K % MK == 0 &&
-            big_ctas >= ctx->sm_count) {
-            int rc = launch_dgemm_mma_bulk(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
-                                           strideC, batch, offA, offB);
-            if (rc) return rc;
-        } else if (use_mma && use_async && aligned16 && !force_tile && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96) {
+        if (use_mma && use_async && aligned16 && !force_tile && big_ctas >= 2 * ctx->sm_count && M >= 96 && N >= 96) {
             int rc = launch_dgemm_mma_async<128, 128, 2, 4>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
                                                             beta, C, ldc, strideC, batch, offA, offB);
             if (rc) return rc;

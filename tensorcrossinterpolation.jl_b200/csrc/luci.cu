@@ -101,6 +101,67 @@ __global__ void k_scatter_cols(const double *__restrict__ src, i64 lds, i64 r, i
     out[i + ldo * perm[q]] = v;
 }
 
+// Recursive splitting (the updates between the halves are large GEMMs that run on the DMMA kernel; the leaves are
+// 32-wide triangular solves in shared memory).  A loop over 32-wide blocks would make every update a GEMM with N = 32.
+static i64 trsm_split(i64 k) { return ((k / 2 + TB_NB - 1) / TB_NB) * TB_NB; }
+
+// W (rows x k, ldw) <- W * U^-1 for an upper-triangular U (k x k, ldu; unit diagonal if `unit`)
+static int trsm_right_upper(tci_ctx *ctx, double *W, i64 rows, i64 ldw, const double *U, i64 ldu, i64 k, bool unit)
+{
+    if (k <= 0 || rows <= 0) return TCI_OK;
+    if (k <= TB_NB) {
+        const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
+        if (unit)
+            k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W, rows, ldw, U, ldu, (int)k);
+        else
+            k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W, rows, ldw, U, ldu, (int)k);
+        ctx->launches++;
+        return TCI_OK;
+    }
+    const i64 k1 = trsm_split(k), k2 = k - k1;
+    int rc = trsm_right_upper(ctx, W, rows, ldw, U, ldu, k1, unit);                       // X1 U11 = W1
+    if (!rc) rc = dgemm_dev(ctx, false, false, rows, k2, k1, -1.0, W, ldw, U + ldu * k1, ldu, 1.0, W + ldw * k1, ldw); // W2 -= X1 U12
+    if (!rc) rc = trsm_right_upper(ctx, W + ldw * k1, rows, ldw, U + k1 + ldu * k1, ldu, k2, unit); // X2 U22 = W2
+    return rc;
+}
+
+// W (rows x k, ldw) <- W * L^-1 for a lower-triangular L (k x k, ldl; unit diagonal if `unit`)
+static int trsm_right_lower(tci_ctx *ctx, double *W, i64 rows, i64 ldw, const double *L, i64 ldl, i64 k, bool unit)
+{
+    if (k <= 0 || rows <= 0) return TCI_OK;
+    if (k <= TB_NB) {
+        const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
+        if (unit)
+            k_trsm_rl_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W, rows, ldw, L, ldl, (int)k);
+        else
+            k_trsm_rl_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W, rows, ldw, L, ldl, (int)k);
+        ctx->launches++;
+        return TCI_OK;
+    }
+    const i64 k1 = trsm_split(k), k2 = k - k1;
+    int rc = trsm_right_lower(ctx, W + ldw * k1, rows, ldw, L + k1 + ldl * k1, ldl, k2, unit);   // X2 L22 = W2
+    if (!rc) rc = dgemm_dev(ctx, false, false, rows, k1, k2, -1.0, W + ldw * k1, ldw, L + k1, ldl, 1.0, W, ldw); // W1 -= X2 L21
+    if (!rc) rc = trsm_right_lower(ctx, W, rows, ldw, L, ldl, k1, unit);                           // X1 L11 = W1
+    return rc;
+}
+
+// X (k x cols, ldx) <- U^-1 X for a UNIT upper-triangular U (k x k, ldu)
+static int trsm_left_upper_unit(tci_ctx *ctx, double *X, i64 cols, i64 ldx, const double *U, i64 ldu, i64 k)
+{
+    if (k <= 0 || cols <= 0) return TCI_OK;
+    if (k <= TB_NB) {
+        k_trsm_lu_block<<<(unsigned)((cols + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(X, cols, ldx, U,
+                                                                                                  ldu, (int)k);
+        ctx->launches++;
+        return TCI_OK;
+    }
+    const i64 k1 = trsm_split(k), k2 = k - k1;
+    int rc = trsm_left_upper_unit(ctx, X + k1, cols, ldx, U + k1 + ldu * k1, ldu, k2);            // U22 X2 = B2
+    if (!rc) rc = dgemm_dev(ctx, false, false, k1, cols, k2, -1.0, U + ldu * k1, ldu, X + k1, ldx, 1.0, X, ldx); // B1 -= U12 X2
+    if (!rc) rc = trsm_left_upper_unit(ctx, X, cols, ldx, U, ldu, k1);                            // U11 X1 = B1
+    return rc;
+}
+
 static int finish(tci_ctx *ctx, tci_dmat *res, double *out_host, tci_dmat **out_dev)
 {
     if (out_host && res->m * res->n > 0) {
@@ -135,15 +196,7 @@ extern "C" int tci_luci_left(tci_lu *lu, double *out_host, tci_dmat **out_dev)
             rc = lu_extract(lu, L.p, m, nullptr, 0);
             const i64 rows = m - r;
             double *X = L.p + r;
-            for (i64 j1 = r; j1 > 0 && !rc && rows > 0; j1 -= TB_NB) {
-                const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
-                if (j1 < r) // X[:, j0:j1] -= X[:, j1:r] * L11[j1:r, j0:j1]
-                    rc = dgemm_dev(ctx, false, false, rows, nb, r - j1, -1.0, X + m * j1, m, L.p + j1 + m * j0, m, 1.0,
-                                   X + m * j0, m);
-                k_trsm_rl_block<true><<<(unsigned)((rows + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
-                    X + m * j0, rows, m, L.p + j0 + m * j0, m, (int)nb);
-                ctx->launches++;
-            }
+            if (!rc) rc = trsm_right_lower(ctx, X, rows, m, L.p, m, r, true); // X L11 = L21
             if (!rc) {
                 k_scatter_rows<<<(unsigned)((m * r + 255) / 256), 256, 0, ctx->stream>>>(L.p, m, m, r, lu->d_rowperm,
                                                                                         res->p, res->ld, 1);
@@ -198,15 +251,7 @@ extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
             rc = lu_extract(lu, nullptr, 0, U.p, r);
             const i64 cols = n - r;
             double *X = U.p + r * r;
-            for (i64 i1 = r; i1 > 0 && !rc && cols > 0; i1 -= TB_NB) {
-                const i64 i0 = std::max<i64>(0, i1 - TB_NB), nb = i1 - i0;
-                if (i1 < r) // X[i0:i1, :] -= U11[i0:i1, i1:r] * X[i1:r, :]
-                    rc = dgemm_dev(ctx, false, false, nb, cols, r - i1, -1.0, U.p + i0 + r * i1, r, X + i1, r, 1.0,
-                                   X + i0, r);
-                k_trsm_lu_block<<<(unsigned)((cols + TB_THREADS - 1) / TB_THREADS), TB_THREADS, 0, ctx->stream>>>(
-                    X + i0, cols, r, U.p + i0 + r * i0, r, (int)nb);
-                ctx->launches++;
-            }
+            if (!rc) rc = trsm_left_upper_unit(ctx, X, cols, r, U.p, r, r); // U11 X = U12
             if (!rc) {
                 k_scatter_cols<<<(unsigned)((r * n + 255) / 256), 256, 0, ctx->stream>>>(U.p, r, r, n, lu->d_colperm,
                                                                                         res->p, res->ld, 1);
@@ -227,23 +272,6 @@ extern "C" int tci_luci_right(tci_lu *lu, double *out_host, tci_dmat **out_dev)
 //   A[rowperm, colperm] = L U  =>  X[:, rowperm] = B[:, colperm] U^-1 L^-1
 // W (rows x k, ldw) <- W * U^-1 for an upper-triangular U (k x k, ldu; unit diagonal if `unit`), blocked: 32-wide
 // diagonal solves in shared memory + DMMA GEMM updates of the columns to the right
-static int trsm_right_upper(tci_ctx *ctx, double *W, i64 rows, i64 ldw, const double *U, i64 ldu, i64 k, bool unit)
-{
-    int rc = 0;
-    const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
-    for (i64 j0 = 0; j0 < k && !rc; j0 += TB_NB) {
-        const i64 nb = std::min<i64>(TB_NB, k - j0);
-        if (j0 > 0)
-            rc = dgemm_dev(ctx, false, false, rows, nb, j0, -1.0, W, ldw, U + ldu * j0, ldu, 1.0, W + ldw * j0, ldw);
-        if (unit)
-            k_trsm_ru_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W + ldw * j0, rows, ldw, U + j0 + ldu * j0, ldu, (int)nb);
-        else
-            k_trsm_ru_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W + ldw * j0, rows, ldw, U + j0 + ldu * j0, ldu, (int)nb);
-        ctx->launches++;
-    }
-    return rc;
-}
-
 // dst (n x m, ldd) = src (m x n, lds)^T
 __global__ void k_transpose(const double *__restrict__ src, i64 lds, i64 m, i64 n, double *__restrict__ dst, i64 ldd)
 {
@@ -332,26 +360,13 @@ int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i
     TCI_CUDA(ctx, U.alloc((size_t)(k * k)));
     TCI_CUDA(ctx, W.alloc((size_t)(rows * k)));
     rc = lu_extract(lu, L.p, k, U.p, k);
-    const unsigned gb = (unsigned)((rows + TB_THREADS - 1) / TB_THREADS);
     if (!rc) {
         k_gather_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(B, ldb, rows, k, lu->d_colperm, W.p,
                                                                                rows);
         ctx->launches++;
     }
     if (!rc) rc = trsm_right_upper(ctx, W.p, rows, rows, U.p, k, k, !lu->leftorthogonal); // Y U = W
-    for (i64 j1 = k; j1 > 0 && !rc; j1 -= TB_NB) { // X' L = Y, right to left
-        const i64 j0 = std::max<i64>(0, j1 - TB_NB), nb = j1 - j0;
-        if (j1 < k)
-            rc = dgemm_dev(ctx, false, false, rows, nb, k - j1, -1.0, W.p + rows * j1, rows, L.p + j1 + k * j0, k, 1.0,
-                           W.p + rows * j0, rows);
-        if (lu->leftorthogonal)
-            k_trsm_rl_block<true><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, L.p + j0 + k * j0,
-                                                                     k, (int)nb);
-        else
-            k_trsm_rl_block<false><<<gb, TB_THREADS, 0, ctx->stream>>>(W.p + rows * j0, rows, rows, L.p + j0 + k * j0,
-                                                                      k, (int)nb);
-        ctx->launches++;
-    }
+    if (!rc) rc = trsm_right_lower(ctx, W.p, rows, rows, L.p, k, k, lu->leftorthogonal); // X' L = Y
     if (!rc) {
         k_scatter_cols<<<(unsigned)((rows * k + 255) / 256), 256, 0, ctx->stream>>>(W.p, rows, rows, k, lu->d_rowperm, X,
                                                                                 ldx, 0);

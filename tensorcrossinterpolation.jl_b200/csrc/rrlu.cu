@@ -882,6 +882,7 @@ int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus
         if (!batch.empty()) {
             const int B = (int)batch.size();
             std::vector<RRArgs> args((size_t)B);
+            std::vector<double *> xbufs; // posted pivot columns: released (in stream order) AFTER the launch
             size_t smem = 0;
             int T = 256;
             for (int t = 0; t < B; ++t) {
@@ -932,7 +933,7 @@ int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus
                 lu->d_colpos = a.colpos;
                 ctx->live_handles++;
                 lus[batch[t]] = lu;
-                dev_free(ctx, xbuf); // stream ordered: released after the kernel below
+                xbufs.push_back(xbuf);
             }
             DevBuf<RRArgs> dargs(ctx);
             TCI_CUDA(ctx, dargs.upload(args.data(), args.size()));
@@ -940,7 +941,9 @@ int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus
             TCI_CUDA(ctx, ctx_func_smem(ctx, fn, 227 * 1024 - 1024));
             const RRArgs *dp = dargs.p;
             void *kargs[] = {(void *)&dp, (void *)&Gq};
-            TCI_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(B * Gq), dim3(T), kargs, smem, ctx->stream));
+            cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(B * Gq), dim3(T), kargs, smem, ctx->stream);
+            for (double *xb : xbufs) dev_free(ctx, xb);
+            TCI_CUDA(ctx, le);
             ctx->launches++;
             for (int t = 0; t < B; ++t) {
                 const RRArgs &a = args[t];

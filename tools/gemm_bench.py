@@ -42,6 +42,6 @@ for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 512), (2048, 2048, 256)]:
     torch.cuda.synchronize()
     cub = 5 * 2.0 * M * N * K / (e0.elapsed_time(e1) * 1e-3) / 1e12
     err = float(np.max(np.abs(C - c.cpu().numpy())) / np.max(np.abs(C)))
-    print(f"{M}x{N}x{K}: library {res['bulk']:.2f} TFLOP/s (NO_BULK={os.environ.get('TCI_DGEMM_NO_BULK', '0')} VARIANT={os.environ.get('TCI_DGEMM_VARIANT', '0')} TB={TB}), "
+    print(f"{M}x{N}x{K}: library {res['bulk']:.2f} TFLOP/s (VARIANT={os.environ.get('TCI_DGEMM_VARIANT', '0')} TB={TB}), "
           f"cuBLAS {cub:.2f}, rel dev {err:.1e}", flush=True)
     del a, b, c
