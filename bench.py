@@ -516,15 +516,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+    # N > 1: rank 0 drives all N GPUs through ONE library context (tci_ctx_create(ngpu, ...): NCCL + peer stores inside
+    # the library).  The other torchrun ranks only join the barriers; they must not open their own CUDA context on
+    # "their" GPU (a second process spinning in an NCCL barrier kernel on a GPU the library is using time-slices with
+    # it), so the process group of the launcher is gloo and only rank 0 touches CUDA.
+    pg = os.environ.get("TCI_BENCH_PG", "gloo")
+    if rank == 0 or pg == "nccl":
+        torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if pg == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
     K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if rank == 0 or pg == "nccl":
+            torch.cuda.synchronize()
+            if rank == 0 and world > 1:
+                for d in range(world):
+                    torch.cuda.synchronize(d)
 
     out = None
     if rank == 0:
@@ -561,7 +574,7 @@ def main():
         tm = ctx.timers(reset=True)
     barrier()
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms], device="cuda" if pg == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:

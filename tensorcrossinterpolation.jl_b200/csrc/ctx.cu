@@ -126,6 +126,7 @@ void ctx_release(tci_ctx *ctx)
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->shared_pool) cudaMemPoolDestroy(ctx->shared_pool);
     delete ctx;
 }
 
@@ -191,7 +192,7 @@ int dmat_alloc(tci_ctx *ctx, i64 m, i64 n, tci_dmat **out)
     a->ncap = n;
     a->ld = round_up(m > 0 ? m : 1, 16); // every column starts on a 128 B boundary
     size_t bytes = (size_t)a->ld * (size_t)(n > 0 ? n : 1) * sizeof(double);
-    cudaError_t e = dev_alloc(ctx, (void **)&a->p, bytes);
+    cudaError_t e = dev_alloc_shared(ctx, (void **)&a->p, bytes);
     if (e != cudaSuccess) {
         delete a;
         return tci_fail(ctx, TCI_ERR_CUDA, std::string("cudaMallocAsync dmat: ") + cudaGetErrorString(e));

@@ -226,18 +226,39 @@ int group_create_local(const std::vector<tci_ctx *> &members, tci_group **out)
             cudaSetDevice(members[a]->device);
             cudaError_t e = cudaDeviceEnablePeerAccess(members[b]->device, 0);
             if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            // the default pool of b (cudaMallocAsync memory: Pi, environments) becomes readable / writable from a
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, members[b]->device) == cudaSuccess) {
-                cudaMemAccessDesc desc{};
-                desc.location.type = cudaMemLocationTypeDevice;
-                desc.location.id = members[a]->device;
-                desc.flags = cudaMemAccessFlagsProtReadWrite;
-                cudaError_t e2 = cudaMemPoolSetAccess(pool, &desc, 1);
-                if (e2 != cudaSuccess)
-                    return tci_fail(nullptr, TCI_ERR_CUDA, std::string("cudaMemPoolSetAccess: ") + cudaGetErrorString(e2));
-            }
         }
+    // one explicit pool per member, mapped read/write on every other member: the matrices peers store into (Pi).
+    // Scratch (environments, index lists, LU arenas) stays in the device's private default pool.
+    for (int b = 0; b < n; ++b) {
+        if (members[b]->shared_pool) continue;
+        cudaSetDevice(members[b]->device);
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = members[b]->device;
+        cudaMemPool_t pool = nullptr;
+        cudaError_t e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess)
+            return tci_fail(nullptr, TCI_ERR_CUDA, std::string("cudaMemPoolCreate: ") + cudaGetErrorString(e));
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        std::vector<cudaMemAccessDesc> desc;
+        for (int a = 0; a < n; ++a) {
+            if (a == b) continue;
+            cudaMemAccessDesc d{};
+            d.location.type = cudaMemLocationTypeDevice;
+            d.location.id = members[a]->device;
+            d.flags = cudaMemAccessFlagsProtReadWrite;
+            desc.push_back(d);
+        }
+        e = cudaMemPoolSetAccess(pool, desc.data(), desc.size());
+        if (e != cudaSuccess) {
+            cudaMemPoolDestroy(pool);
+            return tci_fail(nullptr, TCI_ERR_CUDA, std::string("cudaMemPoolSetAccess: ") + cudaGetErrorString(e));
+        }
+        members[b]->shared_pool = pool;
+    }
     tci_group *g = new tci_group();
     g->world = g->nlocal = n;
     g->m = members;

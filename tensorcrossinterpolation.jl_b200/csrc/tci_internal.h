@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <condition_variable>
 #include <functional>
@@ -81,6 +83,10 @@ struct tci_ctx {
     int member = 0;      // index among the group's LOCAL members (0 = the context the caller holds)
     int rank = 0;        // global rank in the group (0 = owner of the per-bond rrLU)
     bool nosync = false; // inside a batched entry point: stage timers must not synchronise the stream
+    // group members: an explicit stream-ordered pool mapped on every other member (Pi buffers that peers store into);
+    // the device's default pool stays private -- growing two peer-mapped default pools from two threads at once
+    // failed with cudaErrorMemoryAllocation on the 2-GPU box with 189 GB free
+    cudaMemPool_t shared_pool = nullptr;
     int live_handles = 0; // dmat / lu handles that still point at this context (tci_ctx_destroy defers to the last)
     bool destroyed = false;
     // stream-ordered allocations made during the current API call and not yet released: when the call fails
@@ -223,12 +229,33 @@ struct StageTimer {
 
 static inline i64 round_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
 
-// stream-ordered scratch allocations on the context stream (pool never trimmed)
-static inline cudaError_t dev_alloc(tci_ctx *ctx, void **p, size_t bytes)
+// stream-ordered allocations on the context stream (pools never trimmed while they work).  A pool that has to grow
+// while it holds cached free blocks can fail with cudaErrorMemoryAllocation although the device is almost empty --
+// reproducibly so for peer-mapped pools on the 2-GPU B200 box (tools/pool_peer_probe.cu) -- and succeeds once the
+// cached blocks have been returned, so a failed allocation is retried once after a synchronise + trim.
+static inline cudaError_t pool_alloc(tci_ctx *ctx, cudaMemPool_t pool, void **p, size_t bytes)
 {
-    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream);
+    bytes = bytes ? bytes : 8;
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(p, bytes, pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cudaMemPool_t pl = pool;
+        if (!pl) cudaDeviceGetDefaultMemPool(&pl, ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (pl) cudaMemPoolTrimTo(pl, 0);
+        e = pool ? cudaMallocFromPoolAsync(p, bytes, pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+        if (getenv("TCI_DEBUG_ALLOC"))
+            fprintf(stderr, "[tci alloc] %zu bytes on device %d: retried after trim: %s\n", bytes, ctx->device,
+                    cudaGetErrorString(e));
+    }
     if (e == cudaSuccess && ctx->busy && ctx->member == 0) ctx->call_allocs.push_back(*p);
     return e;
+}
+static inline cudaError_t dev_alloc(tci_ctx *ctx, void **p, size_t bytes) { return pool_alloc(ctx, nullptr, p, bytes); }
+// matrices other group members may store into (tci_dmat): from the peer-mapped pool when the context has one
+static inline cudaError_t dev_alloc_shared(tci_ctx *ctx, void **p, size_t bytes)
+{
+    return pool_alloc(ctx, ctx->shared_pool, p, bytes);
 }
 static inline void dev_free(tci_ctx *ctx, void *p)
 {
