@@ -281,9 +281,8 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
     auto load_stage = [&](int stage, i64 k0) {
         double *as = Asm + stage * A_SZ, *bs = Bsm + stage * B_SZ;
         // A: chunks of two doubles along the contiguous direction
-        constexpr int ACH = BM * KT / 2;
 #pragma unroll
-        for (int c = tid; c < ACH; c += NT) {
+        for (int c = tid; c < BM * KT / 2; c += NT) {
             if (!TA) { // pairs along m
                 const int mm = (c % (BM / 2)) * 2, kk = c / (BM / 2);
                 const i64 gm = m0 + mm, gk = k0 + kk;
@@ -296,9 +295,8 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
                 cp_async16(as + mm * A_ROW + kk, A + (bytes ? gk + lda * gm : 0), bytes);
             }
         }
-        constexpr int BCH = BN * KT / 2;
 #pragma unroll
-        for (int c = tid; c < BCH; c += NT) {
+        for (int c = tid; c < BN * KT / 2; c += NT) {
             if (!TB) { // B is K x N: pairs along k
                 const int kk = (c % (KT / 2)) * 2, nn = c / (KT / 2);
                 const i64 gn = n0 + nn, gk = k0 + kk;
@@ -320,15 +318,51 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
         for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const i64 nkt = (K + KT - 1) / KT;
+    // Interior CTAs (the whole BM x BN tile inside the matrix, K a multiple of KT) copy through per-thread base
+    // pointers that only advance by a constant per k-tile: a thread's chunks c = tid + q*NT differ by a fixed number
+    // of columns (rows) of the operand, so the ~300 integer instructions of the bounds-checked path per k-tile shrink
+    // to one 64-bit add per copy.  (The DMMA stream of a warp pauses for the copies; two warps share a scheduler.)
+    const bool interior = m0 + BM <= M && n0 + BN <= N && K % KT == 0;
+    constexpr int ACH = BM * KT / 2, BCH = BN * KT / 2;
+    constexpr int AQ = ACH / NT, BQ = BCH / NT;
+    static_assert(ACH % NT == 0 && BCH % NT == 0, "chunks must divide evenly over the threads");
+    // chunk (tid, q) of A: !TA: mm = (tid % (BM/2))*2, kk = tid / (BM/2) + q*(NT/(BM/2)); TA: kk = (tid % (KT/2))*2, mm = tid/(KT/2) + q*(NT/(KT/2))
+    constexpr int A_DIV = TA ? KT / 2 : BM / 2, B_DIV = TB ? BN / 2 : KT / 2;
+    static_assert(NT % A_DIV == 0 && NT % B_DIV == 0, "thread count must be a multiple of the chunk row length");
+    const int a_in = (tid % A_DIV) * 2, a_out = tid / A_DIV; // contiguous-direction element, other-direction index
+    const int b_in = (tid % B_DIV) * 2, b_out = tid / B_DIV;
+    const double *gA = TA ? A + (a_in + lda * (m0 + a_out)) : A + (m0 + a_in + lda * a_out);
+    const double *gB = TB ? B + (n0 + b_in + ldb * b_out) : B + (b_in + ldb * (n0 + b_out));
+    const i64 a_qstep = lda * (NT / A_DIV), b_qstep = ldb * (NT / B_DIV);     // between the chunks of one thread
+    const i64 a_kstep = TA ? KT : (i64)KT * lda, b_kstep = TB ? (i64)KT * ldb : KT; // between k-tiles
+    const int a_soff = a_out * A_ROW + a_in, b_soff = b_out * B_ROW + b_in;   // shared offsets of chunk q = 0
+    auto load_fast = [&](int stage, i64 kt) {
+        double *as = Asm + stage * A_SZ + a_soff, *bs = Bsm + stage * B_SZ + b_soff;
+        const double *pa = gA + kt * a_kstep, *pb = gB + kt * b_kstep;
+#pragma unroll
+        for (int q = 0; q < AQ; ++q) cp_async16(as + q * (NT / A_DIV) * A_ROW, pa + q * a_qstep, 16);
+#pragma unroll
+        for (int q = 0; q < BQ; ++q) cp_async16(bs + q * (NT / B_DIV) * B_ROW, pb + q * b_qstep, 16);
+    };
 #pragma unroll
     for (int st = 0; st < NST - 1; ++st) {
-        if (st < nkt) load_stage(st, (i64)st * KT);
+        if (st < nkt) {
+            if (interior)
+                load_fast(st, st);
+            else
+                load_stage(st, (i64)st * KT);
+        }
         cp_async_commit();
     }
     for (i64 kt = 0; kt < nkt; ++kt) {
         cp_async_wait<NST - 2>(); // tile kt has landed
         __syncthreads();              // ... for everybody, and everybody is done with tile kt-1
-        if (kt + NST - 1 < nkt) load_stage((int)((kt + NST - 1) % NST), (kt + NST - 1) * KT);
+        if (kt + NST - 1 < nkt) {
+            if (interior)
+                load_fast((int)((kt + NST - 1) % NST), kt + NST - 1);
+            else
+                load_stage((int)((kt + NST - 1) % NST), (kt + NST - 1) * KT);
+        }
         cp_async_commit();
         const double *as = Asm + (kt % NST) * A_SZ, *bs = Bsm + (kt % NST) * B_SZ;
 #pragma unroll
@@ -489,6 +523,16 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         // 2048^2 x 256 24.9 vs 22.7).  Also tried: 16 warps of 32 x 32 (28.2), 32-deep k-tiles (30.8 with 8 warps, 25.9
         // with 4: shared memory then allows one CTA per SM), 4 stages (32.4), bulk copies + mbarriers (26.0).
         const i64 half_ctas = ((M + 127) / 128) * ((N + 63) / 64) * batch;
+        // 32-deep k-tiles with two stages (same shared memory, half as many barriers and copy phases per flop) win once
+        // the k-loop is long: 4096^3 33.5 -> 34.1 TFLOP/s, 8192^2 x 512 31.9 -> 32.3; at K = 256 (the MPO environment
+        // steps) the longer pipeline fill loses: config-5 Pi 145.3 vs 147.6 ms
+        if ((variant == 2 || (variant == 0 && K >= 1024)) && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
+            int rc = launch_dgemm_mma_async<128, 64, 2, 2, 32, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
+                                                                  beta, C, ldc, strideC, batch, offA, offB);
+            if (rc) return rc;
+            TCI_CUDA(ctx, cudaGetLastError());
+            return TCI_OK;
+        }
         if (variant != 9 && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
             int rc = launch_dgemm_mma_async<128, 64, 2, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
                                                            beta, C, ldc, strideC, batch, offA, offB);
