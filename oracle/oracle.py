@@ -488,7 +488,62 @@ def mpo_batchevaluate_projected(A, B, I, J, M, projector=None):
     return tt_batchevaluate_projected(prod, sitedims, I, J, M, projector)
 
 
-# ---- ComplexF64 groundwork (numpy restatement, small cases; NO product path uses it yet) -----------
+# ---- ComplexF64 ------------------------------------------------------------------------------------
+def zrrlu(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True):
+    """rrlu on a Matrix{ComplexF64} through the C++ restatement (orc_zrrlu): Julia Base's complex arithmetic of
+    include/tci_zarith.h, operation for operation.  Returns an LU object with complex L / U."""
+    A = np.asfortranarray(A, dtype=np.complex128)
+    m, n = A.shape
+    maxrank = I64MAX if maxrank is None else int(maxrank)
+    mr = max(0, min(maxrank, m, n))
+    rowperm = np.zeros(m, dtype=np.int64)
+    colperm = np.zeros(n, dtype=np.int64)
+    npiv, err = i64(0), f64(0.0)
+    L = np.zeros(m * mr, dtype=np.complex128)
+    U = np.zeros(mr * n, dtype=np.complex128)
+    pe = np.zeros(min(m, n) + 1, dtype=np.float64)
+    fn = lib().orc_zrrlu
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, i64, i64, i64, f64, f64, C.c_int, P_i64, P_i64, C.POINTER(i64), C.POINTER(f64),
+                   C.c_void_p, C.c_void_p, P_f64]
+    _check(fn(A.ctypes.data, m, n, maxrank, reltol, abstol, int(leftorthogonal), _pi(rowperm), _pi(colperm),
+              C.byref(npiv), C.byref(err), L.ctypes.data, U.ctypes.data, _pf(pe)))
+    r = npiv.value
+    out = LU()
+    out.rowpermutation, out.colpermutation = rowperm, colperm
+    out.npivot, out.error = r, err.value
+    out.L = L[: m * r].reshape((m, r), order="F")
+    out.U = U[: r * n].reshape((r, n), order="F")
+    out.pivoterrors = pe[: r + 1].copy()
+    out.leftorthogonal = leftorthogonal
+    return out
+
+
+def zluci(A, **kw):
+    """MatrixLUCI on a complex matrix: left / right (matrixluci.jl:40-84) from the factors of zrrlu; the triangular
+    solves and products are BLAS calls in the reference (ztrsm / zgemm, pinned to sqrt(eps) only), numpy here."""
+    import scipy.linalg as sla
+    lu = zrrlu(A, **kw)
+    m, n = np.asarray(A).shape
+    r = lu.npivot
+    L, U = lu.L, lu.U
+    if lu.leftorthogonal:  # colstimespivotinv :48-57, rowmatrix :44-46
+        left_p = np.vstack([np.eye(r, dtype=np.complex128),
+                            sla.solve_triangular(L[:r, :r].T, L[r:, :].T, lower=False, unit_diagonal=True).T]) if r else L
+        right_p = L[:r, :r] @ U
+    else:  # colmatrix :40-42, pivotinvtimesrows :59-68
+        left_p = L @ U[:r, :r]
+        right_p = np.hstack([np.eye(r, dtype=np.complex128),
+                             sla.solve_triangular(U[:r, :r], U[:, r:], lower=False, unit_diagonal=True)]) if r else U
+    lu.left = np.zeros((m, r), dtype=np.complex128)
+    lu.left[lu.rowpermutation - 1, :] = left_p
+    lu.right = np.zeros((r, n), dtype=np.complex128)
+    lu.right[:, lu.colpermutation - 1] = right_p
+    lu.rowindices, lu.colindices = lu.rowpermutation[:r].copy(), lu.colpermutation[:r].copy()
+    return lu
+
+
+# ---- ComplexF64, numpy restatement for small cases (pinned on the reference's complex arg-max literal) -----------
 def _abs2c(z):  # abs2(z::Complex) = real(z)*real(z) + imag(z)*imag(z)   (Base complex.jl)
     return z.real * z.real + z.imag * z.imag
 

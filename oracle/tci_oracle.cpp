@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../include/tci_targets.h"
+#include "../include/tci_zarith.h"
 
 typedef int64_t i64;
 typedef std::vector<i64> MultiIndex; // abstracttensortrain.jl:6-7 (1-based values)
@@ -1265,6 +1266,89 @@ int orc_luci(const double *A, i64 m, i64 n, i64 maxrank, double reltol, double a
     if (right) {
         luci_right(lu, r);
         std::copy(r.begin(), r.end(), right);
+    }
+    return 0;
+}
+
+// ---- ComplexF64: matrixlu.jl:1-32, 98-181 on a Matrix{ComplexF64}, element by element with Julia
+// Base's complex arithmetic (include/tci_zarith.h: abs2, abs = hypot, robust division, multiply-then-subtract).  A is
+// m x n column-major, interleaved (re, im) -- the memory of a Julia Matrix{ComplexF64}; L (m x r) and U (r x n) come
+// back the same way (2*m*maxr and 2*maxr*n doubles), pe = [abs.(diag); lu.error] (:394-416).
+// Returns 0, 1 ("lu.L contains NaNs") or 2 ("lu.U contains NaNs").
+int orc_zrrlu(const double *Ain, i64 m, i64 n, i64 maxrank, double reltol, double abstol, int leftorthogonal,
+              i64 *rowperm, i64 *colperm, i64 *npivot, double *error, double *L, double *U, double *pe)
+{
+    std::vector<tci_z> A((size_t)(m * n));
+    for (i64 e = 0; e < m * n; ++e) A[e] = tci_zmake(Ain[2 * e], Ain[2 * e + 1]);
+    for (i64 i = 0; i < m; ++i) rowperm[i] = i + 1;
+    for (i64 j = 0; j < n; ++j) colperm[j] = j + 1;
+    maxrank = std::min(maxrank, std::min(m, n));
+    double maxerror = 0.0, err = NAN;
+    i64 np = 0;
+    std::vector<double> diag;
+    while (np < maxrank) { // _optimizerrlu! :150-160
+        const i64 k = np;
+        double best = -INFINITY; // submatrixargmax(abs2, A, k) :1-32: columns outer, rows inner, strict >
+        i64 pr = k, pc = k;
+        for (i64 c = k; c < n; ++c)
+            for (i64 r = k; r < m; ++r) {
+                const double v = tci_zabs2(A[r + c * m]);
+                if (v > best) {
+                    best = v;
+                    pr = r;
+                    pc = c;
+                }
+            }
+        err = tci_zabs(A[pr + pc * m]);
+        if ((std::fabs(err) < reltol * maxerror || std::fabs(err) < abstol) && np > 0) break;
+        maxerror = jl_max(maxerror, err);
+        np++; // addpivot! :114-136
+        std::swap(rowperm[k], rowperm[pr]);
+        for (i64 j = 0; j < n; ++j) std::swap(A[k + j * m], A[pr + j * m]);
+        std::swap(colperm[k], colperm[pc]);
+        for (i64 i = 0; i < m; ++i) std::swap(A[i + k * m], A[i + pc * m]);
+        const tci_z piv = A[k + k * m];
+        diag.push_back(tci_zabs(piv));
+        if (leftorthogonal) {
+            for (i64 i = k + 1; i < m; ++i) A[i + k * m] = tci_zdiv(A[i + k * m], piv);
+        } else {
+            for (i64 j = k + 1; j < n; ++j) A[k + j * m] = tci_zdiv(A[k + j * m], piv);
+        }
+        for (i64 j = k + 1; j < n; ++j) {
+            const tci_z yj = A[k + j * m];
+            for (i64 i = k + 1; i < m; ++i) A[i + j * m] = tci_zsub(A[i + j * m], tci_zmul(A[i + k * m], yj));
+        }
+    }
+    const i64 r = np;
+    std::vector<tci_z> Lz((size_t)(m * r), tci_zmake(0.0, 0.0)), Uz((size_t)(r * n), tci_zmake(0.0, 0.0));
+    for (i64 c = 0; c < r; ++c)
+        for (i64 i = c; i < m; ++i) Lz[i + c * m] = A[i + c * m]; // tril(A[:, 1:r])
+    for (i64 c = 0; c < n; ++c)
+        for (i64 i = 0; i <= std::min(c, r - 1); ++i) Uz[i + c * r] = A[i + c * m]; // triu(A[1:r, :])
+    for (const tci_z &v : Lz)
+        if (std::isnan(v.re) || std::isnan(v.im)) {
+            g_err = "lu.L contains NaNs";
+            return 1;
+        }
+    for (const tci_z &v : Uz)
+        if (std::isnan(v.re) || std::isnan(v.im)) {
+            g_err = "lu.U contains NaNs";
+            return 2;
+        }
+    for (i64 c = 0; c < r; ++c) {
+        if (leftorthogonal)
+            Lz[c + c * m] = tci_zmake(1.0, 0.0);
+        else
+            Uz[c + c * r] = tci_zmake(1.0, 0.0);
+    }
+    if (r >= std::min(m, n)) err = 0.0;
+    *npivot = r;
+    *error = err;
+    if (L) std::memcpy(L, Lz.data(), Lz.size() * sizeof(tci_z));
+    if (U) std::memcpy(U, Uz.data(), Uz.size() * sizeof(tci_z));
+    if (pe) {
+        for (i64 i = 0; i < r; ++i) pe[i] = diag[i];
+        pe[r] = err;
     }
     return 0;
 }

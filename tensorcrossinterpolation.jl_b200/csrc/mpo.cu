@@ -10,16 +10,38 @@
 
 #include <algorithm>
 
-struct MpoSite {
-    const double *A, *B;
+// The chains are templates over the value type V: double (Float64 targets) or double2 = interleaved (re, im) pairs
+// (ComplexF64 targets; the reference's contraction tests are complex, test_contraction.jl:39-46).
+// Leading dimensions, strides and offsets are counted in elements of V.
+template <class V> struct MpoSiteT {
+    const V *A, *B;
     i64 La, d1, S, Lan; // A: (La, d1, S, Lan)
     i64 Lb, d3, Lbn;    // B: (Lb, S, d3, Lbn)
 };
 
-static MpoSite site_of(const TargetDev &t, i64 s)
+template <class V> static MpoSiteT<V> site_of(const TargetDev &t, i64 s)
 {
-    return MpoSite{t.A[s], t.B[s], t.adl[s], t.as1[s], t.as2[s], t.adr[s], t.bdl[s], t.bs2[s], t.bdr[s]};
+    return MpoSiteT<V>{(const V *)t.A[s], (const V *)t.B[s], t.adl[s], t.as1[s], t.as2[s], t.adr[s], t.bdl[s], t.bs2[s], t.bdr[s]};
 }
+
+int zgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double2 *A, i64 lda,
+                          i64 strideA, const double2 *B, i64 ldb, i64 strideB, double beta, double2 *C, i64 ldc,
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB); // zgemm.cu
+static inline int gemm_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                           i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, i64 batch,
+                           const i64 *offA, const i64 *offB, bool even)
+{
+    return dgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, offA, offB, even);
+}
+static inline int gemm_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double2 *A, i64 lda,
+                           i64 sA, const double2 *B, i64 ldb, i64 sB, double beta, double2 *C, i64 ldc, i64 sC, i64 batch,
+                           const i64 *offA, const i64 *offB, bool)
+{
+    return zgemm_dev_batched_off(ctx, tA, tB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, offA, offB);
+}
+template <class V> __host__ __device__ inline V v_one();
+template <> __host__ __device__ inline double v_one<double>() { return 1.0; }
+template <> __host__ __device__ inline double2 v_one<double2>() { return make_double2(1.0, 0.0); }
 
 // unfuse idx = i + d1*(j-1) (contraction.jl:95-101) into element offsets of the two views
 __global__ void k_mpo_offsets(const i64 *__restrict__ idx, int len, int pos, i64 count, i64 d1, i64 mulA, i64 mulB,
@@ -32,7 +54,7 @@ __global__ void k_mpo_offsets(const i64 *__restrict__ idx, int len, int pos, i64
     offB[q] = mulB * (f / d1);
 }
 
-__global__ void k_fill1(double *p, i64 n, double v)
+template <class V> __global__ void k_fill1(V *p, i64 n, V v)
 {
     i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
     if (e < n) p[e] = v;
@@ -100,8 +122,9 @@ static bool plan_chain(const i64 *h_idx, int len, int off, int nsteps, i64 count
     return true;
 }
 
-__global__ void k_gather_cols(const double *__restrict__ src, i64 D, const i64 *__restrict__ ids, i64 count,
-                              double *__restrict__ dst)
+template <class V>
+__global__ void k_gather_cols(const V *__restrict__ src, i64 D, const i64 *__restrict__ ids, i64 count,
+                              V *__restrict__ dst)
 {
     const i64 total = D * count;
     for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x)
@@ -109,7 +132,8 @@ __global__ void k_gather_cols(const double *__restrict__ src, i64 D, const i64 *
 }
 
 // chain over the distinct entries of a plan; `right` selects the step formulas of mpo_right_chain
-static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &P, bool right, i64 count, double **out,
+template <class V>
+static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &P, bool right, i64 count, V **out,
                              i64 *Da_out, i64 *Db_out)
 {
     const int N = (int)t.nsites, nsteps = P.nsteps;
@@ -119,7 +143,7 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
     {
         i64 ea = 1, eb = 1; // dimensions of the environment that enters the level
         for (int k = 0; k < nsteps; ++k) {
-            MpoSite m = site_of(t, right ? N - 1 - k : k);
+            MpoSiteT<V> m = site_of<V>(t, right ? N - 1 - k : k);
             const i64 c = P.cnt[k];
             base[k] = host.size();
             host.resize(host.size() + 3 * (size_t)c);
@@ -136,39 +160,39 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
     }
     DevBuf<i64> dev(ctx), ids(ctx);
     TCI_CUDA(ctx, dev.upload(host.data(), host.size()));
-    double *env = nullptr;
-    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, sizeof(double)));
-    k_fill1<<<1, 32, 0, ctx->stream>>>(env, 1, 1.0);
+    V *env = nullptr;
+    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, sizeof(V)));
+    k_fill1<V><<<1, 32, 0, ctx->stream>>>(env, 1, v_one<V>());
     ctx->launches++;
     i64 Ea = 1, Eb = 1;
     for (int k = 0; k < nsteps; ++k) {
-        MpoSite m = site_of(t, right ? N - 1 - k : k);
+        MpoSiteT<V> m = site_of<V>(t, right ? N - 1 - k : k);
         const i64 c = P.cnt[k];
         const i64 *g = dev.p + base[k], *oa = g + c, *ob = oa + c;
-        double *tmp = nullptr, *nxt = nullptr;
+        V *tmp = nullptr, *nxt = nullptr;
         int rc = 0;
         if (!right) {
-            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * m.S * m.Lan) * c * sizeof(double)));
-            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * c * sizeof(double)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * m.S * m.Lan) * c * sizeof(V)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * c * sizeof(V)));
             // the two products of mpo_left_chain, the environment read at the parent's offset
-            rc = dgemm_dev_batched_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, 0, m.A, m.La * m.d1, 0,
+            rc = gemm_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, 0, m.A, m.La * m.d1, 0,
                                        0.0, tmp, m.Lb, m.Lb * m.S * m.Lan, c, g, oa, m.La % 2 == 0);
             if (!rc)
-                rc = dgemm_dev_batched_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
+                rc = gemm_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
                                            m.Lb * m.S * m.Lan, m.B, m.Lb * m.S * m.d3, 0, 0.0, nxt, m.Lan,
                                            m.Lan * m.Lbn, c, nullptr, ob, (m.Lb * m.S) % 2 == 0);
             Ea = m.Lan;
             Eb = m.Lbn;
         } else {
-            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lbn * m.S * m.La) * c * sizeof(double)));
-            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.La * m.Lb) * c * sizeof(double)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lbn * m.S * m.La) * c * sizeof(V)));
+            TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.La * m.Lb) * c * sizeof(V)));
             for (i64 h = 0; h < m.S && !rc; ++h)
-                rc = dgemm_dev_batched_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, 0,
+                rc = gemm_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, 0,
                                            m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h,
                                            m.Lbn * m.S, m.Lbn * m.S * m.La, c, g, oa,
                                            m.La % 2 == 0 && (m.Lan * m.Lbn) % 2 == 0);
             for (i64 h = 0; h < m.S && !rc; ++h)
-                rc = dgemm_dev_batched_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
+                rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
                                            m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0,
                                            nxt, m.La, m.La * m.Lb, c, nullptr, ob, (m.Lb * m.S) % 2 == 0);
             Ea = m.La;
@@ -183,12 +207,12 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
         }
     }
     if (!P.identity) { // expand the distinct environments of the last level to the entries of the index set
-        double *full = nullptr;
+        V *full = nullptr;
         const i64 D = Ea * Eb;
         TCI_CUDA(ctx, ids.upload(P.last_id.data(), P.last_id.size()));
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&full, (size_t)(D * count) * sizeof(double)));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&full, (size_t)(D * count) * sizeof(V)));
         const i64 total = D * count;
-        k_gather_cols<<<(unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        k_gather_cols<V><<<(unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
             env, D, ids.p, count, full);
         ctx->launches++;
         dev_free(ctx, env);
@@ -202,39 +226,40 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
 }
 
 // evaluateleft (contraction.jl:112-139) for `count` points over sites [0, nsteps)
+template <class V>
 static int mpo_left_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i64 *d_idx, int len, int off, i64 count,
-                          double **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
+                          V **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
 {
     if (h_idx && !getenv("TCI_MPO_NO_DEDUP")) {
         ChainPlan P;
         std::vector<i64> dims((size_t)std::max(nsteps, 0));
         for (int k = 0; k < nsteps; ++k) dims[k] = t.localdims[k];
         if (plan_chain(h_idx, len, off, nsteps, count, false, dims.data(), P) && P.shared)
-            return mpo_chain_planned(ctx, t, P, false, count, out, La_out, Lb_out);
+            return mpo_chain_planned<V>(ctx, t, P, false, count, out, La_out, Lb_out);
     }
-    double *env = nullptr;
-    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(double)));
-    k_fill1<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, 1.0);
+    V *env = nullptr;
+    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(V)));
+    k_fill1<V><<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, v_one<V>());
     ctx->launches++;
     i64 La = 1, Lb = 1;
     DevBuf<i64> offA(ctx), offB(ctx);
     TCI_CUDA(ctx, offA.alloc((size_t)count));
     TCI_CUDA(ctx, offB.alloc((size_t)count));
     for (int s = 0; s < nsteps; ++s) {
-        MpoSite m = site_of(t, s);
+        MpoSiteT<V> m = site_of<V>(t, s);
         k_mpo_offsets<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d_idx, len, s + off, count, m.d1, m.La,
                                                                                m.Lb * m.S, offA.p, offB.p);
         ctx->launches++;
-        double *tmp = nullptr, *nxt = nullptr;
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * m.S * m.Lan) * count * sizeof(double)));
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * count * sizeof(double)));
+        V *tmp = nullptr, *nxt = nullptr;
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * m.S * m.Lan) * count * sizeof(V)));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn) * count * sizeof(V)));
         // tmp[q] (Lb x S*Lan) = env[q]^T (Lb x La) * A_i (La x S*Lan)       contraction.jl:105
-        int rc = dgemm_dev_batched_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, m.La * m.Lb, m.A,
+        int rc = gemm_off(ctx, true, false, m.Lb, m.S * m.Lan, m.La, 1.0, env, m.La, m.La * m.Lb, m.A,
                                        m.La * m.d1, 0, 0.0, tmp, m.Lb, m.Lb * m.S * m.Lan, count, nullptr, offA.p,
                                        m.La % 2 == 0);
         // nxt[q] (Lan x Lbn) = tmp[q]^T (Lan x Lb*S) * B_j (Lb*S x Lbn)       contraction.jl:108
         if (!rc)
-            rc = dgemm_dev_batched_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
+            rc = gemm_off(ctx, true, false, m.Lan, m.Lbn, m.Lb * m.S, 1.0, tmp, m.Lb * m.S,
                                        m.Lb * m.S * m.Lan, m.B, m.Lb * m.S * m.d3, 0, 0.0, nxt, m.Lan, m.Lan * m.Lbn,
                                        count, nullptr, offB.p, (m.Lb * m.S) % 2 == 0);
         dev_free(ctx, tmp);
@@ -254,8 +279,9 @@ static int mpo_left_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i6
 }
 
 // evaluateright (contraction.jl:144-176) over the last nsteps sites
+template <class V>
 static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i64 *d_idx, int len, int off, i64 count,
-                           double **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
+                           V **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
 {
     const int N = (int)t.nsites;
     if (h_idx && !getenv("TCI_MPO_NO_DEDUP")) {
@@ -263,33 +289,33 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
         std::vector<i64> dims((size_t)std::max(nsteps, 0));
         for (int k = 0; k < nsteps; ++k) dims[k] = t.localdims[N - 1 - k];
         if (plan_chain(h_idx, len, off, nsteps, count, true, dims.data(), P) && P.shared)
-            return mpo_chain_planned(ctx, t, P, true, count, out, La_out, Lb_out);
+            return mpo_chain_planned<V>(ctx, t, P, true, count, out, La_out, Lb_out);
     }
-    double *env = nullptr;
-    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(double)));
-    k_fill1<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, 1.0);
+    V *env = nullptr;
+    TCI_CUDA(ctx, dev_alloc(ctx, (void **)&env, (size_t)count * sizeof(V)));
+    k_fill1<V><<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(env, count, v_one<V>());
     ctx->launches++;
     i64 Ra = 1, Rb = 1;
     DevBuf<i64> offA(ctx), offB(ctx);
     TCI_CUDA(ctx, offA.alloc((size_t)count));
     TCI_CUDA(ctx, offB.alloc((size_t)count));
     for (int s = N - 1; s >= N - nsteps; --s) {
-        MpoSite m = site_of(t, s);
+        MpoSiteT<V> m = site_of<V>(t, s);
         k_mpo_offsets<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
             d_idx, len, s - (N - nsteps) + off, count, m.d1, m.La, m.Lb * m.S, offA.p, offB.p);
         ctx->launches++;
-        double *tmp = nullptr, *nxt = nullptr;
+        V *tmp = nullptr, *nxt = nullptr;
         // tmp[q][br + Lbn*(h + S*al)] = sum_ar env[ar, br] * A[al, i, h, ar]
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lbn * m.S * m.La) * count * sizeof(double)));
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.La * m.Lb) * count * sizeof(double)));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lbn * m.S * m.La) * count * sizeof(V)));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.La * m.Lb) * count * sizeof(V)));
         int rc = 0;
         for (i64 h = 0; h < m.S && !rc; ++h) // (Lbn x La) = env^T (Lbn x Lan) * A_{i,h}^T (Lan x La)
-            rc = dgemm_dev_batched_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, m.Lan * m.Lbn,
+            rc = gemm_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, m.Lan * m.Lbn,
                                        m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h, m.Lbn * m.S,
                                        m.Lbn * m.S * m.La, count, nullptr, offA.p, m.La % 2 == 0);
         // nxt[q][al, bl] = sum_{br,h} tmp[br, h, al] * B[bl, h, j, br]
         for (i64 h = 0; h < m.S && !rc; ++h) // (La x Lb) += tmp_h^T (La x Lbn) * B_{j,h}^T (Lbn x Lb)
-            rc = dgemm_dev_batched_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
+            rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
                                        m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0, nxt,
                                        m.La, m.La * m.Lb, count, nullptr, offB.p, (m.Lb * m.S) % 2 == 0);
         dev_free(ctx, tmp);
@@ -313,21 +339,22 @@ int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len
                  const i64 *h_idx)
 {
     i64 a = 1, b = 1;
-    int rc = side == 0 ? mpo_left_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx)
-                       : mpo_right_chain(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx);
+    int rc = side == 0 ? mpo_left_chain<double>(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx)
+                       : mpo_right_chain<double>(ctx, t, len, d_idx, len, 0, count, out, &a, &b, h_idx);
     *D = a * b;
     return rc;
 }
 
-// batchevaluate(::Contraction) contraction.jl:236-335 (projector = nothing, f = nothing)
-int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
-                tci_dmat *out, const i64 *hI, const i64 *hJ)
+// batchevaluate(::Contraction) contraction.jl:236-335 (projector = nothing, f = nothing); outp: (nI*C) x nJ, ld outld
+template <class V>
+static int pi_eval_mpo_t(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                         V *outp, i64 outld, const i64 *hI, const i64 *hJ)
 {
-    double *X = nullptr, *right = nullptr;
+    V *X = nullptr, *right = nullptr;
     i64 La = 1, Lb = 1, Ra = 1, Rb = 1;
-    int rc = mpo_left_chain(ctx, t, (int)nl, dI, (int)nl, 0, nI, &X, &La, &Lb, hI);
+    int rc = mpo_left_chain<V>(ctx, t, (int)nl, dI, (int)nl, 0, nI, &X, &La, &Lb, hI);
     if (rc) return rc;
-    rc = mpo_right_chain(ctx, t, (int)nr, dJ, (int)nr, 0, nJ, &right, &Ra, &Rb, hJ);
+    rc = mpo_right_chain<V>(ctx, t, (int)nr, dJ, (int)nr, 0, nJ, &right, &Ra, &Rb, hJ);
     if (rc) {
         dev_free(ctx, X);
         return rc;
@@ -335,21 +362,22 @@ int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const
     // X: (La x Lb x R), r = i + nI*sacc ; centre sites :290-317
     i64 R = nI;
     for (i64 s = nl; s < nl + M && !rc; ++s) {
-        MpoSite m = site_of(t, s);
+        MpoSiteT<V> m = site_of<V>(t, s);
         const i64 N1 = m.d1 * m.S * m.Lan;
-        double *tmp = nullptr, *nxt = nullptr;
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * R * N1) * sizeof(double)));
-        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn * R * m.d1 * m.d3) * sizeof(double)));
+        V *tmp = nullptr, *nxt = nullptr;
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&tmp, (size_t)(m.Lb * R * N1) * sizeof(V)));
+        TCI_CUDA(ctx, dev_alloc(ctx, (void **)&nxt, (size_t)(m.Lan * m.Lbn * R * m.d1 * m.d3) * sizeof(V)));
         // tmp[(b + Lb*r) + Lb*R*(x + d1*(h + S*an))] = sum_a X[a, b, r] * A[a, x, h, an]
-        rc = dgemm_dev(ctx, true, false, m.Lb * R, N1, m.La, 1.0, X, m.La, m.A, m.La, 0.0, tmp, m.Lb * R);
+        rc = gemm_off(ctx, true, false, m.Lb * R, N1, m.La, 1.0, X, m.La, 0, m.A, m.La, 0, 0.0, tmp, m.Lb * R, 0, 1, nullptr,
+                      nullptr, false);
         // nxt[an + Lan*(bn + Lbn*(r + R*(x + d1*z)))] = sum_{b,h} tmp[b, r, x, h, an] * B[b, h, z, bn]
         for (i64 z = 0; z < m.d3 && !rc; ++z)
             for (i64 x = 0; x < m.d1 && !rc; ++x)
                 for (i64 h = 0; h < m.S && !rc; ++h)
-                    rc = dgemm_dev_batched(ctx, true, false, m.Lan, m.Lbn, m.Lb, 1.0,
-                                           tmp + m.Lb * R * (x + m.d1 * h), m.Lb * R * m.d1 * m.S, m.Lb,
-                                           m.B + m.Lb * (h + m.S * z), m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0,
-                                           nxt + m.Lan * m.Lbn * R * (x + m.d1 * z), m.Lan, m.Lan * m.Lbn, R);
+                    rc = gemm_off(ctx, true, false, m.Lan, m.Lbn, m.Lb, 1.0, tmp + m.Lb * R * (x + m.d1 * h),
+                                  m.Lb * R * m.d1 * m.S, m.Lb, m.B + m.Lb * (h + m.S * z), m.Lb * m.S * m.d3, 0,
+                                  h ? 1.0 : 0.0, nxt + m.Lan * m.Lbn * R * (x + m.d1 * z), m.Lan, m.Lan * m.Lbn, R, nullptr,
+                                  nullptr, false);
         dev_free(ctx, tmp);
         dev_free(ctx, X);
         X = nxt;
@@ -358,10 +386,24 @@ int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const
         R *= m.d1 * m.d3;
     }
     // res[r, j] = sum_{a,b} X[a, b, r] * right[a, b, j]   :328
-    if (!rc) rc = dgemm_dev(ctx, true, false, R, nJ, La * Lb, 1.0, X, La * Lb, right, Ra * Rb, 0.0, out->p, out->ld);
+    if (!rc)
+        rc = gemm_off(ctx, true, false, R, nJ, La * Lb, 1.0, X, La * Lb, 0, right, Ra * Rb, 0, 0.0, outp, outld, 0, 1, nullptr,
+                      nullptr, false);
     dev_free(ctx, X);
     dev_free(ctx, right);
     return rc;
+}
+
+int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                tci_dmat *out, const i64 *hI, const i64 *hJ)
+{
+    return pi_eval_mpo_t<double>(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out->p, out->ld, hI, hJ);
+}
+// ComplexF64 MPO pair: `out` holds interleaved (re, im) pairs, 2 * rows doubles per column
+int pi_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                  tci_dmat *out, const i64 *hI, const i64 *hJ)
+{
+    return pi_eval_mpo_t<double2>(ctx, t, dI, nl, nI, dJ, nr, nJ, M, (double2 *)out->p, out->ld / 2, hI, hJ);
 }
 
 __global__ void k_dot_env(const double *__restrict__ l, const double *__restrict__ r, i64 D, i64 count,
@@ -373,6 +415,20 @@ __global__ void k_dot_env(const double *__restrict__ l, const double *__restrict
     for (i64 a = 0; a < D; ++a) acc = __dadd_rn(acc, __dmul_rn(l[a + D * q], r[a + D * q]));
     out[q] = acc;
 }
+// sum(left .* right) of contraction.jl:196-200 on ComplexF64 (no conjugation), accumulated in order
+__global__ void k_dot_env_z(const double2 *__restrict__ l, const double2 *__restrict__ r, i64 D, i64 count,
+                            double2 *__restrict__ out)
+{
+    i64 q = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    double re = 0.0, im = 0.0;
+    for (i64 a = 0; a < D; ++a) {
+        const double2 x = l[a + D * q], y = r[a + D * q];
+        re = __dadd_rn(re, __dsub_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)));
+        im = __dadd_rn(im, __dadd_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
+    }
+    out[q] = make_double2(re, im);
+}
 
 // evaluate(::Contraction, indexset)  contraction.jl:189-207
 int target_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out)
@@ -380,11 +436,27 @@ int target_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, dou
     const int N = (int)t.nsites, mid = N / 2;
     double *l = nullptr, *r = nullptr;
     i64 La, Lb, Ra, Rb;
-    int rc = mpo_left_chain(ctx, t, mid, d_idx, N, 0, count, &l, &La, &Lb);
+    int rc = mpo_left_chain<double>(ctx, t, mid, d_idx, N, 0, count, &l, &La, &Lb);
     if (rc) return rc;
-    rc = mpo_right_chain(ctx, t, N - mid, d_idx, N, mid, count, &r, &Ra, &Rb);
+    rc = mpo_right_chain<double>(ctx, t, N - mid, d_idx, N, mid, count, &r, &Ra, &Rb);
     if (!rc) {
         k_dot_env<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(l, r, La * Lb, count, d_out);
+        ctx->launches++;
+    }
+    dev_free(ctx, l);
+    dev_free(ctx, r);
+    return rc;
+}
+int target_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out)
+{
+    const int N = (int)t.nsites, mid = N / 2;
+    double2 *l = nullptr, *r = nullptr;
+    i64 La, Lb, Ra, Rb;
+    int rc = mpo_left_chain<double2>(ctx, t, mid, d_idx, N, 0, count, &l, &La, &Lb);
+    if (rc) return rc;
+    rc = mpo_right_chain<double2>(ctx, t, N - mid, d_idx, N, mid, count, &r, &Ra, &Rb);
+    if (!rc) {
+        k_dot_env_z<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(l, r, La * Lb, count, (double2 *)d_out);
         ctx->launches++;
     }
     dev_free(ctx, l);

@@ -42,6 +42,7 @@ struct TargetDev {
     double *d_params = nullptr;
     i64 *d_localdims = nullptr;
     i64 nparams_alloc = 0; // doubles behind d_params
+    bool is_complex = false; // ComplexF64 MPO pair: A / B hold interleaved (re, im) pairs (zpath.cu)
     bool pooled = false;   // device buffers come from the context's stream-ordered pool (tci_fill_sitetensors)
     // TT: cores on device, dims (Dl, d, Dr)
     std::vector<double *> cores;
@@ -157,6 +158,7 @@ struct tci_lu {
     tci_dmat *A = nullptr; // factorised in place (rows physically permuted, columns virtually)
     i64 m = 0, n = 0, r = 0;
     bool leftorthogonal = true;
+    bool is_complex = false;  // A holds interleaved (re, im) pairs: 2m rows of doubles (zpath.cu)
     void *arena = nullptr;    // owns the three arrays below
     i64 *d_rowperm = nullptr; // 0-based, device
     i64 *d_colperm = nullptr; // position -> physical column, 0-based, device
@@ -311,4 +313,13 @@ int pi_eval_mpo(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const
 int env_eval_tt(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D);
 int env_eval_mpo(tci_ctx *ctx, TargetDev &t, int side, const i64 *d_idx, int len, i64 count, double **out, i64 *D,
                  const i64 *h_idx = nullptr);
+// ComplexF64 building blocks (zgemm.cu, mpo.cu): element counts / leading dimensions in (re, im) pairs
+int zgemm_dev(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double2 *A, i64 lda,
+              const double2 *B, i64 ldb, double beta, double2 *C, i64 ldc);
+int zgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double2 *A, i64 lda,
+                          i64 strideA, const double2 *B, i64 ldb, i64 strideB, double beta, double2 *C, i64 ldc,
+                          i64 strideC, i64 batch, const i64 *offA, const i64 *offB);
+int pi_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ, i64 M,
+                  tci_dmat *out, const i64 *hI, const i64 *hJ);
+int target_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out);
 int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits);
