@@ -252,6 +252,47 @@ int tci_globalsearch_select(const double *rec_err, const int64_t *rec_idx, int64
 int tci_tt_evaluate(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
                     const int64_t *idx, int64_t count, double *out);
 
+/* ---- ComplexF64 value type -------------------------------------- */
+/* The reference is generic in the value type and its contraction / conversion tests run on ComplexF64
+ * (test_contraction.jl:39-46, test_matrixlu.jl:39-52).  A Matrix{ComplexF64} crosses the ABI as Julia stores it:
+ * interleaved (re, im) pairs, column-major; on the device a complex m x n matrix is a tci_dmat of 2m x n doubles
+ * (tci_dmat_create(ctx, 2*m, n, ...) / tci_dmat_fetch move it), and a tci_lu made by tci_zrrlu is a complex
+ * factorisation that only the tci_z* accessors accept.  Arithmetic that decides pivots is Julia Base's complex
+ * arithmetic (include/tci_zarith.h: abs2, hypot, the robust division, multiply-then-subtract).                        */
+/* rrlu(A::Matrix{ComplexF64}; maxrank, reltol, abstol, leftorthogonal), matrixlu.jl:141-225; outputs as tci_rrlu
+ * (pivoterrors are the |.| of the pivots, real).                                                                      */
+int tci_zrrlu(tci_ctx *ctx, const double *A_host, tci_dmat *A_dev, int64_t m, int64_t n, int64_t maxrank,
+              double reltol, double abstol, int leftorthogonal, int64_t *rowperm, int64_t *colperm,
+              int64_t *npivot, double *error, double *pivoterrors, tci_lu **factors /* nullable */);
+/* lu.L (m x r) / lu.U (r x n), matrixlu.jl:374-392; left(luci) / right(luci), matrixluci.jl:40-84; B * A^-1 of
+ * setsitetensor!, tensorci2.jl:391 -- for complex factors; matrices interleaved as above.                            */
+int tci_zlu_fetch(tci_lu *lu, double *L /* nullable */, double *U /* nullable */);
+int tci_zluci_left(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+int tci_zluci_right(tci_lu *lu, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+int tci_zlu_rdiv(tci_lu *lu, tci_dmat *B, double *out_host /* nullable */, tci_dmat **out_dev /* nullable */);
+/* Contraction(a, b) of two TensorTrain{ComplexF64,4} (contraction.jl:35-62) and TTCache(tt) of a
+ * TensorTrain{ComplexF64,3} (cachedtensortrain.jl:9-30); cores interleaved.  tci_target_set_elementwise accepts
+ * TCI_F_AFFINE with real a, b on them (the reference's tests use x -> 2x); tci_target_destroy releases them.          */
+int tci_zmpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,
+                         const int64_t *dimsB4, const double *const *B, int64_t *target_id);
+int tci_ztt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
+                   int64_t *target_id);
+/* tci_pi_eval / tci_target_eval on a ComplexF64 target (contraction.jl:189-335, cachedtensortrain.jl:130-215):
+ * out_host holds 2*nI*C*nJ doubles, out_dev is (2*nI*C) x nJ; *maxabs = max(abs.(out)) with abs = hypot.              */
+int tci_zpi_eval(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                 int64_t nr, int64_t nJ, int64_t M, double *out_host, tci_dmat **out_dev, double *maxabs);
+int tci_ztarget_eval(tci_ctx *ctx, int64_t target_id, const int64_t *idx, int64_t count, double *out /* 2*count */);
+/* The `:full` branch of updatepivots! (tensorci2.jl:529-551) on a ComplexF64 target: Pi-eval -> rrLU, Pi never leaves
+ * HBM.  Outputs as tci_bond_update.                                                                                   */
+int tci_zbond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI, const int64_t *J,
+                     int64_t nr, int64_t nJ, int64_t maxrank, double reltol, double abstol, int leftorthogonal,
+                     int64_t *rowperm, int64_t *colperm, int64_t *npivot, double *error, double *pivoterrors,
+                     double *maxabs, tci_lu **factors);
+/* C = op(A) * op(B) on host Matrix{ComplexF64} arrays (plain transposes, as `_contract` permutes without conjugating,
+ * contraction.jl:71-93): the complex FP64 tensor-core GEMM (four DMMA per complex tile) behind the chains above.      */
+int tci_zgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const double *A,
+                   const double *B, double *C);
+
 #ifdef __cplusplus
 }
 #endif

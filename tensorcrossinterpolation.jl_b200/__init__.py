@@ -9,6 +9,7 @@ from .batcheval import (GKCOSEXP, LORENTZ, QUANTICS1D, QUANTICS2D, SEPCOS, SUM, 
 from .cachedtensortrain import TTCache, isbatchevaluable  # noqa: F401
 from .contraction import (Contraction, _contractsitetensors, _factorize, compress, contract, contract_naive,  # noqa: F401
                           contract_TCI, contract_zipup)
+from .complexf64 import ZContraction, ZDeviceMatrix, ZrrLU, ZTTCache, zgemm, zrrlu  # noqa: F401
 from .conversion import sweep1sitegetindices, tensorci2_from_tensortrain  # noqa: F401
 from .globalsearch import _floatingzone, estimatetrueerror  # noqa: F401
 from .globalpivotfinder import (AbstractGlobalPivotFinder, DefaultGlobalPivotFinder,  # noqa: F401

@@ -187,7 +187,11 @@ def contract_TCI(A, B, initialpivots=None, f=None, ctx=None, **kwargs):
     for i in range(len(A)):
         if A[i].shape[2] != B[i].shape[1]:
             raise ValueError("Cannot contract tensor trains with non-matching site dimensions.")
-    mp = Contraction(A, B, f=f, ctx=ctx)
+    if any(np.iscomplexobj(c) for c in list(A) + list(B)):  # TensorTrain{ComplexF64,4}: the complex kernels
+        from .complexf64 import ZContraction
+        mp = ZContraction(A, B, f=f, ctx=ctx)
+    else:
+        mp = Contraction(A, B, f=f, ctx=ctx)
     localdims = mp.localdims
     if initialpivots is None:
         initialpivots = [[1] * len(localdims)]
@@ -213,6 +217,11 @@ def contract(A, B, algorithm="TCI", tolerance=1e-12, maxbonddim=I64MAX, f=None, 
                             for c in tt.sitetensors])
     if algorithm == "TCI":
         return contract_TCI(A, B, tolerance=tolerance, maxbonddim=maxbonddim, f=f, **kwargs)
+    if algorithm != "TCI" and any(np.iscomplexobj(c) for c in ca + cb):
+        if f is not None:
+            raise RuntimeError("Naive contraction implementation cannot contract matrix product with a function. "
+                               "Use algorithm=:TCI instead.")
+        raise NotImplementedError("ComplexF64 tensor trains: only algorithm=:TCI runs on the device so far")
     if algorithm == "naive":
         if f is not None:
             raise RuntimeError("Naive contraction implementation cannot contract matrix product with a function. "

@@ -33,6 +33,7 @@ extern "C" int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     if (!rowperm || !colperm || !npivot || !error) return tci_fail(ctx, TCI_ERR_ARG, "tci_bond_update: outputs missing");
     if (nI <= 0 || nJ <= 0) return tci_fail(ctx, TCI_ERR_ARG, "rows must not be empty"); // matrixlu.jl:10
     if (nI > 0x7ffffff0 || nJ > 0x7ffffff0) return tci_fail(ctx, TCI_ERR_ARG, "tci_bond_update: bad shape");
@@ -79,6 +80,7 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     if (nsites != t.nsites || !Iset || !Jset || !nI || !nJ)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_fill_sitetensors: bad arguments");
     const i64 n = nsites;

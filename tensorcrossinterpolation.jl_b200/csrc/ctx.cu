@@ -539,12 +539,13 @@ int target_replicate(tci_ctx *ctx, i64 id)
                 e = peer_dup(&t->cores[s], c->device, src.cores[s], ctx->device,
                              (size_t)(src.dl[s] * src.d[s] * src.dr[s]));
         } else {
+            const size_t w = src.is_complex ? 2 : 1; // doubles per element
             for (i64 s = 0; s < src.nsites && e == cudaSuccess; ++s) {
                 e = peer_dup(&t->A[s], c->device, src.A[s], ctx->device,
-                             (size_t)(src.adl[s] * src.as1[s] * src.as2[s] * src.adr[s]));
+                             w * (size_t)(src.adl[s] * src.as1[s] * src.as2[s] * src.adr[s]));
                 if (e == cudaSuccess)
                     e = peer_dup(&t->B[s], c->device, src.B[s], ctx->device,
-                                 (size_t)(src.bdl[s] * src.bs1[s] * src.bs2[s] * src.bdr[s]));
+                                 w * (size_t)(src.bdl[s] * src.bs1[s] * src.bs2[s] * src.bdr[s]));
             }
         }
         if (e != cudaSuccess) {

@@ -280,6 +280,8 @@ extern "C" int tci_target_set_elementwise(tci_ctx *ctx, int64_t target_id, int k
     if (t.kind != 2) return tci_fail(ctx, TCI_ERR_ARG, "tci_target_set_elementwise: only a Contraction carries a function f");
     if (kind < TCI_F_NONE || kind > TCI_F_SQUARE)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_target_set_elementwise: unknown function id");
+    if (t.is_complex && kind != TCI_F_NONE && kind != TCI_F_AFFINE)
+        return tci_fail(ctx, TCI_ERR_UNSUPPORTED, "tci_target_set_elementwise: a ComplexF64 contraction takes TCI_F_AFFINE only");
     t.fkind = kind;
     t.fa = a;
     t.fb = b;
@@ -545,6 +547,7 @@ static int pi_eval_core(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     if (nI < 0 || nJ < 0 || nl < 0 || nr < 0 || M < 0) return tci_fail(ctx, TCI_ERR_ARG, "negative size");
     if (nI * nJ == 0) { // batcheval.jl:40-42: empty result, not an error
         if (maxabs) *maxabs = 0.0;
@@ -642,6 +645,7 @@ extern "C" int tci_env_dim(tci_ctx *ctx, int64_t target_id, int side, int64_t le
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     if (t.kind == 0 || t.kind == 3) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
     if (!D || (side != 0 && side != 1) || len < 0 || len > t.nsites)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: bad arguments");
@@ -656,6 +660,7 @@ extern "C" int tci_env_eval(tci_ctx *ctx, int64_t target_id, int side, const int
     auto it = ctx->targets.find(target_id);
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     if (t.kind == 0 || t.kind == 3) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: an analytic target has no environments");
     if (!dst || (side != 0 && side != 1) || len < 0 || len > t.nsites || count < 0 || (len > 0 && count > 0 && !idx))
         return tci_fail(ctx, TCI_ERR_ARG, "tci_env_eval: bad arguments");
@@ -744,6 +749,7 @@ extern "C" int tci_target_eval(tci_ctx *ctx, int64_t target_id, const int64_t *i
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     if (count <= 0) return TCI_OK;
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     DevBuf<i64> d_idx(ctx);
     DevBuf<double> d_out(ctx);
     TCI_CUDA(ctx, d_idx.upload(idx, (size_t)(t.nsites * count)));

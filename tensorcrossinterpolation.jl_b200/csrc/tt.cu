@@ -660,6 +660,7 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, 
     auto it = ctx->targets.find(target_id), jt = ctx->targets.find(tt_id);
     if (it == ctx->targets.end() || jt == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
+    if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
     TargetDev &tt = *jt->second;
     if (tt.kind != 1) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: tt_id must name a tensor train (tci_tt_create)");
     if (t.nsites != tt.nsites) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: tensor train length mismatch");

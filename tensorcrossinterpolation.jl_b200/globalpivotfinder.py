@@ -43,6 +43,9 @@ class DefaultGlobalPivotFinder(AbstractGlobalPivotFinder):  # :100-195
         n = len(input.localdims)
         if self.nsearch <= 0 or self.maxnglobalpivot <= 0:
             return np.zeros((0, n), dtype=np.int64)
+        if getattr(f, "is_complex", False):  # ComplexF64 target: two device batches + the library's selection
+            from .complexf64 import zfind_global_pivots
+            return zfind_global_pivots(self, input, f, abstol, rng=rng, verbosity=verbosity)
         starts = np.ascontiguousarray(self.draw(input, rng))
         ctx = f.ctx
         tt = input.current_tt

@@ -85,7 +85,11 @@ class rrLU:
 
 def rrlu(A, maxrank=None, reltol=1e-14, abstol=0.0, leftorthogonal=True, exact=True, ctx=None):
     """rrlu(A; maxrank, reltol, abstol, leftorthogonal)  matrixlu.jl:217-225.
-    A: host matrix (copied, like the reference's copy(A)) or a DeviceMatrix (consumed in place)."""
+    A: host matrix (copied, like the reference's copy(A)) or a DeviceMatrix (consumed in place).  A ComplexF64 matrix
+    (complex host array or ZDeviceMatrix) takes the complex kernel (complexf64.zrrlu)."""
+    if getattr(A, "is_complex", False) or (not isinstance(A, DeviceMatrix) and np.iscomplexobj(A)):
+        from .complexf64 import zrrlu
+        return zrrlu(A, maxrank=maxrank, reltol=reltol, abstol=abstol, leftorthogonal=leftorthogonal, ctx=ctx)
     if isinstance(A, DeviceMatrix):
         ctx = A.ctx
         m, n = A.shape
@@ -194,6 +198,8 @@ class MatrixLUCI:
     def left(self, device=False):
         m, n = self.lu._shape
         r = self.lu.npivot
+        if getattr(self.lu, "is_complex", False):
+            return self.lu.luci_left(device)
         if device:
             h = C.c_void_p()
             self.lu.ctx.check(lib().tci_luci_left(self.lu._h, None, C.byref(h)))
@@ -205,6 +211,8 @@ class MatrixLUCI:
     def right(self, device=False):
         m, n = self.lu._shape
         r = self.lu.npivot
+        if getattr(self.lu, "is_complex", False):
+            return self.lu.luci_right(device)
         if device:
             h = C.c_void_p()
             self.lu.ctx.check(lib().tci_luci_right(self.lu._h, None, C.byref(h)))

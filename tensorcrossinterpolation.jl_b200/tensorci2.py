@@ -560,7 +560,8 @@ def evaluate(tci, indexset):
     if len(indexset) != len(tci):
         raise ValueError(f"To evaluate a tt of length {len(tci)}, you have to provide {len(tci)} indices, but there "
                          f"were {len(indexset)}.")
-    return float(evaluate_points(TensorTrain(tci.sitetensors), [indexset])[0])
+    v = evaluate_points(TensorTrain(tci.sitetensors), [indexset])[0]
+    return complex(v) if np.iscomplexobj(v) else float(v)
 
 
 def tci_sum(tci):

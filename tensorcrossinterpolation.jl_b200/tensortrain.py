@@ -10,7 +10,8 @@ from ._lib import core_ptrs, lib, pf, pi
 
 class TensorTrain:
     def __init__(self, sitetensors):
-        self.sitetensors = [np.asfortranarray(t, dtype=np.float64) for t in sitetensors]
+        dt = np.complex128 if any(np.iscomplexobj(t) for t in sitetensors) else np.float64  # TensorTrain{ValueType,N}
+        self.sitetensors = [np.asfortranarray(t, dtype=dt) for t in sitetensors]
         for i in range(len(self.sitetensors) - 1):  # tensortrain.jl:21-27
             if self.sitetensors[i].shape[-1] != self.sitetensors[i + 1].shape[0]:
                 raise ValueError(f"The tensors at {i + 1} and {i + 2} must have consistent dimensions for a "
@@ -62,6 +63,9 @@ def evaluate(tt, indexset, ctx=None):
 def evaluate_points(tt, points, ctx=None):
     ctx = ctx or getattr(tt, "ctx", None) or _lib.default_context()
     cores = tt.sitetensors
+    if any(np.iscomplexobj(c) for c in cores):  # TensorTrain{ComplexF64}: through the complex chains
+        from .complexf64 import ZTTCache
+        return ZTTCache(tt, ctx=ctx).evaluate_points(points)
     pts = np.ascontiguousarray(np.asarray(points, dtype=np.int64).reshape(-1, len(cores)))
     keep, arr = core_ptrs(cores)
     d3 = _dims3(keep)
@@ -77,7 +81,7 @@ def tt_sum(tt):
     for T in tt.sitetensors:
         T3 = T.reshape((T.shape[0], -1, T.shape[-1]), order="F")
         v = v @ T3.sum(axis=1)
-    return float(v[0])
+    return complex(v[0]) if np.iscomplexobj(v) else float(v[0])
 
 
 def fulltensor(tt):  # tensortrain.jl:279-292
