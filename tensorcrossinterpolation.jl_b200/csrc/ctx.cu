@@ -37,11 +37,18 @@ int ctx_create_one(int device_id, tci_ctx **out)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device_id);
     c->sm_count = prop.multiProcessorCount;
+    // the side stream (uploads that overlap with kernels; the right-environment chain + all-gather of a sharded
+    // contraction Pi) has the highest priority: its thread blocks are scheduled first, the main stream's kernels fill
+    // whatever it leaves idle
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
-        cudaEventCreate(&c->ev4) != cudaSuccess || cudaEventCreate(&c->ev5) != cudaSuccess) {
+        cudaEventCreate(&c->ev4) != cudaSuccess || cudaEventCreate(&c->ev5) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_g0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_g1, cudaEventDisableTiming) != cudaSuccess) {
         std::string m = cudaGetErrorString(cudaGetLastError());
         delete c;
         return tci_fail(nullptr, TCI_ERR_CUDA, "context setup failed: " + m);
@@ -122,6 +129,8 @@ void ctx_release(tci_ctx *ctx)
     cudaEventDestroy(ctx->ev3);
     cudaEventDestroy(ctx->ev4);
     cudaEventDestroy(ctx->ev5);
+    cudaEventDestroy(ctx->ev_g0);
+    cudaEventDestroy(ctx->ev_g1);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);

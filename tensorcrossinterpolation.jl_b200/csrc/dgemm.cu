@@ -475,6 +475,31 @@ __global__ void k_scale(double *C, i64 M, i64 N, i64 ldc, i64 strideC, double be
     }
 }
 
+// C = alpha * sum_s part[s] + beta * C, slices added in order
+__global__ void k_splitk_reduce(const double *__restrict__ part, i64 M, i64 N, int S, double alpha, double beta,
+                                double *__restrict__ C, i64 ldc)
+{
+    const i64 MN = M * N;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < MN; e += (i64)gridDim.x * blockDim.x) {
+        double acc = part[e];
+        for (int s = 1; s < S; ++s) acc += part[e + MN * s];
+        double *c = C + e % M + ldc * (e / M);
+        *c = beta == 0.0 ? alpha * acc : fma(beta, *c, alpha * acc);
+    }
+}
+// number of k-slices for a single (unbatched) product, 0 = do not split: the output tiles must cover less than two
+// waves of the 128 x 64 kernel (two CTAs per SM) and every slice keeps at least 1024 of the inner dimension
+static int splitk_slices(tci_ctx *ctx, i64 M, i64 N, i64 K, i64 batch, const i64 *offA, const i64 *offB)
+{
+    static const int enabled = getenv("TCI_DGEMM_NO_SPLITK") ? 0 : 1;
+    if (!enabled || batch != 1 || offA || offB || K < 4096 || M < 32 || N < 32) return 0;
+    const i64 tiles = ((M + 127) / 128) * ((N + 63) / 64);
+    const i64 want = 4 * (i64)ctx->sm_count; // two waves of two CTAs per SM
+    if (tiles >= want / 2) return 0;
+    const i64 S = std::min<i64>((want + tiles - 1) / tiles, K / 1024);
+    return S >= 2 ? (int)S : 0;
+}
+
 int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
                           i64 strideA, const double *B, i64 ldb, i64 strideB, double beta, double *C, i64 ldc,
                           i64 strideC, i64 batch, const i64 *offA, const i64 *offB, bool offsets_even)
@@ -493,6 +518,28 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
     if (K <= 0) {
         dim3 grid((unsigned)std::min<i64>((M * N + 255) / 256, 1024), 1, (unsigned)batch);
         k_scale<<<grid, 256, 0, ctx->stream>>>(C, M, N, ldc, strideC, beta);
+        ctx->launches++;
+    } else if (int S = splitk_slices(ctx, M, N, K, batch, offA, offB)) {
+        // Split-K.  A single product with few output tiles and a long inner dimension -- the last step of a contraction
+        // Pi, (nL x Da*Db)(Da*Db x nR) with Da*Db = 65536: 64 tiles of 128 x 128 at nL = nR = 1024, 8 for the row block
+        // of one GPU out of eight -- leaves most SMs idle.  The inner dimension is cut into S slices that run as one
+        // strided-batched launch into S partial products, summed in slice order by k_splitk_reduce (deterministic).
+        const i64 Ks = round_up((K + S - 1) / S, 32);
+        S = (int)((K + Ks - 1) / Ks);
+        DevBuf<double> part(ctx);
+        TCI_CUDA(ctx, part.alloc((size_t)(M * N) * (size_t)S));
+        const i64 kA = tA ? Ks : lda * Ks, kB = tB ? ldb * Ks : Ks;
+        int rc = TCI_OK;
+        if (S > 1)
+            rc = dgemm_dev_batched_off(ctx, tA, tB, M, N, Ks, 1.0, A, lda, kA, B, ldb, kB, 0.0, part.p, M, M * N, S - 1,
+                                       nullptr, nullptr, false);
+        if (!rc)
+            rc = dgemm_dev_batched_off(ctx, tA, tB, M, N, K - Ks * (S - 1), 1.0, A + kA * (S - 1), lda, 0,
+                                       B + kB * (S - 1), ldb, 0, 0.0, part.p + M * N * (S - 1), M, 0, 1, nullptr, nullptr,
+                                       false);
+        if (rc) return rc;
+        k_splitk_reduce<<<(unsigned)std::min<i64>((M * N + 255) / 256, (i64)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+            part.p, M, N, S, alpha, beta, C, ldc);
         ctx->launches++;
     } else {
         i64 big_ctas = ((M + 127) / 128) * ((N + 127) / 128) * batch;

@@ -160,6 +160,48 @@ int group_allgather(tci_group *g, const std::function<void *(int)> &ptr, size_t 
     return TCI_OK;
 }
 
+int group_allgather_side(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes_per_rank)
+{
+    tci_ctx *c0 = g->m[0];
+    if (bytes_per_rank == 0) return TCI_OK;
+    for (int k = 0; k < g->nlocal; ++k) {
+        tci_ctx *c = g->m[k];
+        cudaSetDevice(c->device);
+        cudaEventRecord(c->ev_g0, c->stream);
+        cudaStreamWaitEvent(c->copy_stream, c->ev_g0, 0);
+    }
+    TCI_NCCL(c0, nccl().GroupStart());
+    for (int k = 0; k < g->nlocal; ++k) {
+        char *base = static_cast<char *>(ptr(k));
+        const int rank = g->m[k]->rank;
+        int r = nccl().AllGather(base + (size_t)rank * bytes_per_rank, base, bytes_per_rank, NCCL_U8, g->comm[k],
+                                 g->m[k]->copy_stream);
+        if (r) {
+            nccl().GroupEnd();
+            return tci_fail(c0, TCI_ERR_CUDA, std::string("ncclAllGather: ") + nccl().GetErrorString(r));
+        }
+    }
+    TCI_NCCL(c0, nccl().GroupEnd());
+    for (int k = 0; k < g->nlocal; ++k) {
+        tci_ctx *c = g->m[k];
+        cudaSetDevice(c->device);
+        cudaEventRecord(c->ev_g1, c->copy_stream);
+        c->launches++;
+    }
+    cudaSetDevice(c0->device);
+    return TCI_OK;
+}
+
+void group_allgather_join(tci_group *g)
+{
+    for (int k = 0; k < g->nlocal; ++k) {
+        tci_ctx *c = g->m[k];
+        cudaSetDevice(c->device);
+        cudaStreamWaitEvent(c->stream, c->ev_g1, 0);
+    }
+    cudaSetDevice(g->m[0]->device);
+}
+
 int group_broadcast(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes, int root)
 {
     tci_ctx *c0 = g->m[0];

@@ -451,6 +451,31 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
     const i64 cblk = (nJ + world - 1) / world;
     const i64 rblk = round_up((nI + world - 1) / world, 16); // row blocks start on 128-byte lines
     std::vector<double *> renv(g->nlocal, nullptr);
+    // TCI_SHARD_DEBUG: per-member timeline of the phases (events on the members' main streams)
+    static const bool dbg = getenv("TCI_SHARD_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> dev_ev;
+    auto mark = [&](int k, int phase) {
+        if (!dbg) return;
+        cudaEventRecord(dev_ev[(size_t)k * 5 + phase], g->m[k]->stream);
+    };
+    // Two streams per GPU.  The right-environment chain and the all-gather that follows it run on the member's
+    // high-priority side stream, the left-environment chain on its main stream, concurrently: at 8 GPUs a chain level
+    // is a batch of 128 small GEMMs = 1024 thread blocks = 3.46 waves, and the other chain's blocks fill the idle tail
+    // of every launch (measured per GPU, one after the other: right chain 12.0 ms + left chain 10.5 ms).
+    struct StreamSwap {
+        tci_ctx *c;
+        cudaStream_t main;
+        explicit StreamSwap(tci_ctx *ctx_) : c(ctx_), main(ctx_->stream) { c->stream = c->copy_stream; }
+        ~StreamSwap() { c->stream = main; }
+    };
+    if (dbg) {
+        dev_ev.resize((size_t)g->nlocal * 5);
+        for (int k = 0; k < g->nlocal; ++k) {
+            cudaSetDevice(g->m[k]->device);
+            for (int q = 0; q < 5; ++q) cudaEventCreate(&dev_ev[(size_t)k * 5 + q]);
+        }
+        cudaSetDevice(ctx->device);
+    }
     i64 D = 1;
     {
         const TargetDev &t0 = *ctx->targets.at(target_id);
@@ -462,8 +487,12 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
         TargetDev &t = *c->targets.at(target_id);
         const int rank = c->rank;
         TCI_CUDA(c, dev_alloc(c, (void **)&renv[k], (size_t)D * cblk * world * sizeof(double)));
+        mark(k, 0);
         const i64 lo = std::min(nJ, rank * cblk), hi = std::min(nJ, (rank + 1) * cblk);
         if (hi <= lo) return TCI_OK;
+        cudaEventRecord(c->ev_g0, c->stream); // the side stream starts behind what the main stream holds so far
+        cudaStreamWaitEvent(c->copy_stream, c->ev_g0, 0);
+        StreamSwap side(c);
         DevBuf<i64> dJ(c);
         TCI_CUDA(c, dJ.upload(J + nr * lo, (size_t)(nr * (hi - lo))));
         double *env = nullptr;
@@ -475,10 +504,35 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
                                         cudaMemcpyDeviceToDevice, c->stream);
         dev_free(c, env);
         TCI_CUDA(c, e);
+        mark(k, 1);
         return TCI_OK;
     });
-    if (!rc) rc = group_allgather(g, [&](int k) { return (void *)renv[k]; }, (size_t)D * cblk * sizeof(double));
+    // the all-gather runs on the members' copy streams while their main streams extend the left environments, which do
+    // not need it; the block products wait for it
+    if (!rc) rc = group_allgather_side(g, [&](int k) { return (void *)renv[k]; }, (size_t)D * cblk * sizeof(double));
     if (!rc) group_follow_owner(g); // dst was allocated in the owner's stream order
+    std::vector<double *> lenvs(g->nlocal, nullptr);
+    if (!rc)
+        rc = group_run(g, [&](int k) -> int {
+            tci_ctx *c = g->m[k];
+            TargetDev &t = *c->targets.at(target_id);
+            const int rank = c->rank;
+            const i64 lo = std::min(nI, rank * rblk), hi = std::min(nI, (rank + 1) * rblk);
+            if (hi <= lo) return TCI_OK;
+            DevBuf<i64> dI(c);
+            TCI_CUDA(c, dI.upload(I + nl * lo, (size_t)(nl * (hi - lo))));
+            i64 Dk = 1;
+            int r = t.kind == 1 ? env_eval_tt(c, t, 0, dI.p, (int)nl, hi - lo, &lenvs[k], &Dk)
+                                : env_eval_mpo(c, t, 0, dI.p, (int)nl, hi - lo, &lenvs[k], &Dk, I + nl * lo);
+            mark(k, 2);
+            return r;
+        });
+    group_allgather_join(g);
+    for (int k = 0; k < g->nlocal; ++k) {
+        if (dbg) cudaSetDevice(g->m[k]->device);
+        mark(k, 3);
+    }
+    if (dbg) cudaSetDevice(ctx->device);
     if (!rc)
         rc = group_run(g, [&](int k) -> int {
             tci_ctx *c = g->m[k];
@@ -488,20 +542,29 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
             if (rank != 0) cudaMemsetAsync(w, 0, 8, c->stream);
             const i64 lo = std::min(nI, rank * rblk), hi = std::min(nI, (rank + 1) * rblk);
             if (hi <= lo) return TCI_OK;
-            DevBuf<i64> dI(c);
-            TCI_CUDA(c, dI.upload(I + nl * lo, (size_t)(nl * (hi - lo))));
-            double *lenv = nullptr;
-            i64 Dk = 1;
-            int r = t.kind == 1 ? env_eval_tt(c, t, 0, dI.p, (int)nl, hi - lo, &lenv, &Dk)
-                                : env_eval_mpo(c, t, 0, dI.p, (int)nl, hi - lo, &lenv, &Dk, I + nl * lo);
-            if (r) return r;
             // Pi[lo:hi, :] = lenv^T renv    cachedtensortrain.jl:211-212, contraction.jl:328
-            r = dgemm_dev(c, true, false, hi - lo, nJ, D, 1.0, lenv, D, renv[k], D, 0.0, dst + lo, ld);
-            dev_free(c, lenv);
+            int r = dgemm_dev(c, true, false, hi - lo, nJ, D, 1.0, lenvs[k], D, renv[k], D, 0.0, dst + lo, ld);
             if (!r) r = apply_elementwise(c, t, dst + lo, hi - lo, nJ, ld);
             if (!r && d_maxbits) r = maxabs_dev(c, dst + lo, hi - lo, nJ, ld, w);
+            mark(k, 4);
             return r;
         });
+    if (dbg) {
+        for (int k = 0; k < g->nlocal; ++k) {
+            cudaSetDevice(g->m[k]->device);
+            cudaStreamSynchronize(g->m[k]->stream);
+            float a = 0, b = 0, c2 = 0, d2 = 0;
+            cudaEventElapsedTime(&a, dev_ev[(size_t)k * 5], dev_ev[(size_t)k * 5 + 1]);
+            cudaEventElapsedTime(&b, dev_ev[(size_t)k * 5 + 1], dev_ev[(size_t)k * 5 + 2]);
+            cudaEventElapsedTime(&c2, dev_ev[(size_t)k * 5 + 2], dev_ev[(size_t)k * 5 + 3]);
+            cudaEventElapsedTime(&d2, dev_ev[(size_t)k * 5 + 3], dev_ev[(size_t)k * 5 + 4]);
+            fprintf(stderr, "[shard dbg] member %d: right chain %.2f ms | left chain %.2f | wait for all-gather %.2f | product %.2f\n",
+                    k, a, b, c2, d2);
+            for (int q = 0; q < 5; ++q) cudaEventDestroy(dev_ev[(size_t)k * 5 + q]);
+        }
+        cudaSetDevice(ctx->device);
+    }
+    for (int k = 0; k < g->nlocal; ++k) dev_free(g->m[k], lenvs[k]);
     for (int k = 0; k < g->nlocal; ++k) dev_free(g->m[k], renv[k]);
     if (rc) return rc;
     return group_allreduce_max_u64(g, [&](int k) { return g->m[k]->rank == 0 ? d_maxbits : ctx_words(g->m[k]); }, 1);

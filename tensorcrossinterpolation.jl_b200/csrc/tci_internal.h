@@ -67,6 +67,7 @@ struct tci_ctx {
     cudaStream_t copy_stream = nullptr; // uploads that overlap with kernels on `stream` (tci_dmat_create_async)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t ev4 = nullptr, ev5 = nullptr; // stage boundaries inside the fused entry points (bond.cu)
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr; // ordering between `stream` and a collective on `copy_stream`
     std::string err;
     std::mutex mu;
     bool busy = false;
@@ -130,6 +131,11 @@ void group_follow_owner(tci_group *g);
 // collectives over all ranks (in place on every local member; ptr(k) = member k's buffer)
 int group_allreduce_max_u64(tci_group *g, const std::function<unsigned long long *(int)> &ptr, size_t count);
 int group_allgather(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes_per_rank);
+// the same all-gather on every member's copy stream, ordered behind what its main stream has enqueued so far; the main
+// streams go on without it until group_allgather_join makes them wait for it (a chain that does not need the gathered
+// data overlaps with the transfer)
+int group_allgather_side(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes_per_rank);
+void group_allgather_join(tci_group *g);
 int group_broadcast(tci_group *g, const std::function<void *(int)> &ptr, size_t bytes, int root);
 void group_destroy(tci_group *g);
 void target_free(tci_ctx *ctx, TargetDev &t);  // ctx.cu
