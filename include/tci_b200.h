@@ -103,9 +103,24 @@ int tci_target_source(tci_ctx *ctx, const char *source, const double *params, in
 /* TTCache(tt) (cachedtensortrain.jl:9-30): cores[s] is (dims3[3s], dims3[3s+1], dims3[3s+2]). */
 int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3, const double *const *cores,
                   int64_t *target_id);
+/* Core `site` (0-based) of a device-resident tensor train -- tci_tt_create, or the handle tci_fill_sitetensors returns:
+ * dims3 (nullable) receives (Dl, d, Dr), out (nullable) the Dl*d*Dr values.  tci.sitetensors[site] read lazily: inside
+ * optimize! the site tensors are only consumed by the global pivot finder (tensorci2.jl:788-800), on the device.       */
+int tci_tt_fetch_core(tci_ctx *ctx, int64_t tt_id, int64_t site, int64_t *dims3, double *out);
 /* Contraction(a, b) (contraction.jl:35-62): A[s] is (Da,s1,s2,Da'), B[s] is (Db,s2,s3,Db'). */
 int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,
                         const int64_t *dimsB4, const double *const *B, int64_t *target_id);
+/* CachedFunction{Float64,UInt128}(f, localdims) (cachedfunction.jl:8-63) as a device-resident memo: a target that wraps
+ * target `inner_id` (any real-valued target of this context; it must outlive the wrapper) with a hash table of
+ * 2^capacity_log2 slots (32 B each) in HBM, keyed like the reference by key(x) = sum_n coeffs[n] (x_n - 1), coeffs[n] =
+ * prod_{m<n} localdims[m], as UInt128 ("Overflow in CachedFunction..." -> TCI_ERR_ARG, :22-24).  Every entry point that
+ * takes a target accepts it; an evaluation looks all requested elements up, evaluates the wrapped target on the missing
+ * points only, in one batch, and stores the new values (_batcheval_imp_for_batchevaluator, :117-171).  f must be pure.
+ * Single-GPU contexts only (the memo lives in one GPU's HBM).                                                        */
+int tci_target_cached(tci_ctx *ctx, int64_t inner_id, int capacity_log2, int64_t *target_id);
+/* out[0] = length(cf.cache), out[1] = lookups answered from the memo, out[2] = lookups that evaluated f, out[3] = values
+ * that found no free slot within the probe limit (returned correctly, not memoised).                                 */
+int tci_target_cache_stats(tci_ctx *ctx, int64_t target_id, int64_t *out /* 4 */);
 int tci_target_destroy(tci_ctx *ctx, int64_t target_id);
 /* The elementwise function of a Contraction (`f` of contraction.jl:5-62, applied at :203-205 and :330-332).  A
  * device kernel cannot call a Julia closure, so functions are registered by id like the targets themselves:

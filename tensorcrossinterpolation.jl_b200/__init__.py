@@ -6,6 +6,7 @@ There is no CPU fallback anywhere in this package."""
 from ._lib import Context, DeviceMatrix, TCIError, default_context, lib  # noqa: F401
 from .batcheval import (GKCOSEXP, LORENTZ, QUANTICS1D, QUANTICS2D, SEPCOS, SUM, TABLE, BatchEvaluator,  # noqa: F401
                         BuiltinTarget, SourceTarget, makebatchevaluatable)
+from .cachedfunction import CachedFunction  # noqa: F401
 from .cachedtensortrain import TTCache, isbatchevaluable  # noqa: F401
 from .contraction import (Contraction, _contractsitetensors, _factorize, compress, contract, contract_naive,  # noqa: F401
                           contract_TCI, contract_zipup)

@@ -42,7 +42,10 @@ SYMBOLS = {
     "tci_target_builtin": (C.c_int, [VP, C.c_int, P_f64, i64, P_i64, i64, P_i64]),
     "tci_target_source": (C.c_int, [VP, C.c_char_p, P_f64, i64, P_i64, i64, P_i64]),
     "tci_tt_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64]),
+    "tci_tt_fetch_core": (C.c_int, [VP, i64, i64, P_i64, P_f64]),
     "tci_mpo_pair_create": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, PP_f64, P_i64]),
+    "tci_target_cached": (C.c_int, [VP, i64, C.c_int, P_i64]),
+    "tci_target_cache_stats": (C.c_int, [VP, i64, P_i64]),
     "tci_target_destroy": (C.c_int, [VP, i64]),
     "tci_target_set_elementwise": (C.c_int, [VP, i64, C.c_int, f64, f64]),
     "tci_target_eval": (C.c_int, [VP, i64, P_i64, i64, P_f64]),

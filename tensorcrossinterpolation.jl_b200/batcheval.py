@@ -132,18 +132,20 @@ class BatchEvaluator:
         return rrLU(self.ctx, h if want_factors else None, rowperm, colperm, r, err.value, pe[: r + 1].copy(),
                     bool(leftorthogonal), (m, n)), mx.value
 
-    def fill_sitetensors(self, Isets, Jsets, want_handle=True):
+    def fill_sitetensors(self, Isets, Jsets, want_handle=True, want_host=True):
         """fillsitetensors! (globalsearch.jl:97-103) for all sites in one library call (tci_fill_sitetensors).
-        Returns (list of T_b as (nI_b, d_b, nJ_b) arrays, max over |Pi1|, device-resident TT handle or None)."""
+        Returns (list of T_b as (nI_b, d_b, nJ_b) arrays, max over |Pi1|, device-resident TT handle or None).
+        want_host=False leaves the tensors in HBM (the list is None): they are read through the handle on demand."""
         n = len(self.localdims)
         Is = [as_indexset(s, b) for b, s in enumerate(Isets)]
         Js = [as_indexset(s, n - 1 - b) for b, s in enumerate(Jsets)]
         nI = np.array([len(s) for s in Is], dtype=np.int64)
         nJ = np.array([len(s) for s in Js], dtype=np.int64)
-        Ts = [np.zeros((int(nI[b]), self.localdims[b], int(nJ[b])), dtype=np.float64, order="F") for b in range(n)]
+        Ts = ([np.zeros((int(nI[b]), self.localdims[b], int(nJ[b])), dtype=np.float64, order="F") for b in range(n)]
+              if want_host else None)
         Ip = (_lib.P_i64 * n)(*[pi(s) for s in Is])
         Jp = (_lib.P_i64 * n)(*[pi(s) for s in Js])
-        Tp = (_lib.P_f64 * n)(*[pf(t) for t in Ts])
+        Tp = (_lib.P_f64 * n)(*[pf(t) for t in Ts]) if want_host else None
         mx = C.c_double(0.0)
         tid = C.c_int64(0)
         rc = lib().tci_fill_sitetensors(self.ctx.h, self.id, n, Ip, pi(nI), Jp, pi(nJ), Tp, C.byref(mx),
@@ -166,6 +168,15 @@ class DeviceTT(BatchEvaluator):
     """A tensor train whose cores live on the device (tci_fill_sitetensors' `tt_id`): the `current_tt` the global
     pivot finder probes (globalpivotfinder.jl:160-183) without any upload; also a TT target like TTCache."""
     has_environments = True
+
+    def core(self, b):
+        """Site tensor b as a host array (Dl, d, Dr) (tci_tt_fetch_core)."""
+        d3 = np.zeros(3, dtype=np.int64)
+        self.ctx.check(lib().tci_tt_fetch_core(self.ctx.h, self.id, int(b), pi(d3), None))
+        out = np.zeros(tuple(int(x) for x in d3), dtype=np.float64, order="F")
+        if out.size:
+            self.ctx.check(lib().tci_tt_fetch_core(self.ctx.h, self.id, int(b), None, pf(out)))
+        return out
 
 
 def apply_projector(res, centre_sitedims, projector):

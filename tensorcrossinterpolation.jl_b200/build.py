@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtci_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["ctx.cu", "group.cu", "bond.cu", "pi_eval.cu", "rrlu.cu", "rrlu_lazy.cu", "luci.cu", "dgemm.cu", "tt.cu", "mpo.cu", "zgemm.cu", "zpath.cu", "user_target.cu"]
+SOURCES = ["ctx.cu", "group.cu", "bond.cu", "pi_eval.cu", "rrlu.cu", "rrlu_lazy.cu", "luci.cu", "dgemm.cu", "tt.cu", "mpo.cu", "zgemm.cu", "zpath.cu", "cache.cu", "user_target.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -131,6 +131,10 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
     const bool saved = ctx->nosync;
     ctx->nosync = true;
     cudaEventRecord(ctx->ev4, ctx->stream);
+    static const bool fdbg = getenv("TCI_FILL_DEBUG") != nullptr; // phase timeline of this call on stderr
+    cudaEvent_t fe[3] = {nullptr, nullptr, nullptr};
+    if (fdbg)
+        for (auto &e : fe) cudaEventCreate(&e);
     int rc = 0;
     cudaError_t ce = cudaMemsetAsync(dmax, 0, 8, ctx->stream);
     // phase 1: every Pi1 (with the running max|Pi1|, :372-375) and every P (:383-385), back to back
@@ -154,6 +158,7 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
         if (rc) break;
         rc = pi_enqueue(ctx, t, Iset[b + 1], b + 1, k, Jset[b], n - 1 - b, k, 0, Ps[b], nullptr);
     }
+    if (fdbg) cudaEventRecord(fe[0], ctx->stream);
     // phase 2: the n-1 pivot matrices are independent: factorised to full rank in ONE cooperative launch, each by its
     // own group of CTAs (reltol = abstol = 0 never truncates; a singular P shows up in the result words / pivot values)
     std::vector<tci_lu *> lub((size_t)n, nullptr);
@@ -168,6 +173,7 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
         else if (Ps[b])
             tmp.push_back(Ps[b]);
     }
+    if (fdbg) cudaEventRecord(fe[1], ctx->stream);
     // phase 3: T = Pi1 P^-1 (:391) from the full-pivot factors; the last tensor is Pi1 itself (:377-381)
     for (i64 b = 0; b < n && !rc && ce == cudaSuccess; ++b) {
         const i64 d = t.localdims[b], rows = nI[b] * d, k = nJ[b];
@@ -191,6 +197,14 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
         if (ce != cudaSuccess) rc = tci_fail(ctx, TCI_ERR_CUDA, std::string("tci_fill_sitetensors: ") + cudaGetErrorString(ce));
         float ms = 0.f;
         if (!rc && cudaEventElapsedTime(&ms, ctx->ev4, ctx->ev5) == cudaSuccess) ctx->stage_ms[ST_LUCI] += ms;
+        if (fdbg && !rc) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, ctx->ev4, fe[0]);
+            cudaEventElapsedTime(&b, fe[0], fe[1]);
+            cudaEventElapsedTime(&c, fe[1], ctx->ev5);
+            fprintf(stderr, "[fill dbg] n=%lld: Pi1 / P evaluations %.3f ms | batched rrLU %.3f | solves + D2H %.3f | launches so far %lld\n",
+                    (long long)n, a, b, c, (long long)ctx->launches);
+        }
     } else
         cudaStreamSynchronize(ctx->stream);
     for (i64 b = 0; b + 1 < n && !rc; ++b) {
@@ -211,6 +225,8 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
                 rc = tci_fail(ctx, TCI_ERR_CUDA, "tci_fill_sitetensors: D2H of a site tensor failed");
         }
     if (maxabs) memcpy(maxabs, hbits, sizeof(double));
+    if (fdbg)
+        for (auto &e : fe) cudaEventDestroy(e);
     const bool keep = !rc && tt_id != nullptr;
     cleanup(keep);
     if (rc) return rc;

@@ -103,6 +103,10 @@ extern "C" int tci_ctx_create(int ngpu, const int *device_ids, tci_ctx **out)
 
 void target_free(tci_ctx *ctx, TargetDev &t)
 {
+    if (t.kind == 4) {
+        cache_target_free(ctx, t.cache_id);
+        return;
+    }
     if (t.pooled) {
         for (double *p : t.cores) dev_free(ctx, p);
         return;
@@ -445,6 +449,29 @@ extern "C" int tci_tt_create(tci_ctx *ctx, int64_t nsites, const int64_t *dims3,
     ctx->targets[id] = std::move(t);
     *target_id = id;
     return target_replicate(ctx, id);
+}
+
+// One core of a device-resident tensor train (tci_tt_create, or the handle tci_fill_sitetensors returns): the site
+// tensors stay in HBM between fillsitetensors! and the global pivot search and are fetched only when the host reads them.
+extern "C" int tci_tt_fetch_core(tci_ctx *ctx, int64_t tt_id, int64_t site, int64_t *dims3, double *out)
+{
+    TCI_ENTER(ctx);
+    auto it = ctx->targets.find(tt_id);
+    if (it == ctx->targets.end() || it->second->kind != 1 || it->second->is_complex)
+        return tci_fail(ctx, TCI_ERR_ARG, "tci_tt_fetch_core: not a tensor-train handle");
+    const TargetDev &t = *it->second;
+    if (site < 0 || site >= t.nsites) return tci_fail(ctx, TCI_ERR_ARG, "tci_tt_fetch_core: site out of range");
+    if (dims3) {
+        dims3[0] = t.dl[site];
+        dims3[1] = t.d[site];
+        dims3[2] = t.dr[site];
+    }
+    if (!out) return TCI_OK;
+    StageTimer tm(ctx, ST_D2H);
+    TCI_CUDA(ctx, cudaMemcpyAsync(out, t.cores[site], (size_t)(t.dl[site] * t.d[site] * t.dr[site]) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
 }
 
 extern "C" int tci_mpo_pair_create(tci_ctx *ctx, int64_t nsites, const int64_t *dimsA4, const double *const *A,

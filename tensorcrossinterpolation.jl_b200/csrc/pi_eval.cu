@@ -344,6 +344,7 @@ int pi_enqueue(tci_ctx *ctx, TargetDev &t, const i64 *I, i64 nl, i64 nI, const i
         if (!rc && d_maxbits) rc = maxabs_dev(ctx, out->p, out->m, out->n, out->ld, dmax);
         break;
     case 3: rc = pi_eval_user(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, dmax); break;
+    case 4: rc = pi_eval_cached(ctx, t.cache_id, t, dI, nl, nI, dJ, nr, nJ, M, out, d_maxbits ? dmax : nullptr); break;
     default:
         rc = pi_eval_mpo(ctx, t, dI, nl, nI, dJ, nr, nJ, M, out, I, J);
         if (!rc) rc = apply_elementwise(ctx, t, out->p, out->m, out->n, out->ld);
@@ -709,7 +710,7 @@ extern "C" int tci_env_dim(tci_ctx *ctx, int64_t target_id, int side, int64_t le
     if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
     TargetDev &t = *it->second;
     if (t.is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
-    if (t.kind == 0 || t.kind == 3) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
+    if (t.kind == 0 || t.kind == 3 || t.kind == 4) return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: an analytic target has no environments");
     if (!D || (side != 0 && side != 1) || len < 0 || len > t.nsites)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_env_dim: bad arguments");
     *D = env_dim_of(t, side, len);
@@ -798,6 +799,7 @@ int target_eval_dev(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, dou
         return TCI_OK;
     case 1: return target_eval_tt(ctx, t, d_idx, count, d_out);
     case 3: return target_eval_user(ctx, t, d_idx, count, d_out);
+    case 4: return target_eval_cached(ctx, t.cache_id, t, d_idx, count, d_out);
     default: {
         int rc = target_eval_mpo(ctx, t, d_idx, count, d_out);
         return rc ? rc : apply_elementwise(ctx, t, d_out, count, 1, count);

@@ -34,7 +34,8 @@ struct tci_dmat {
 void dmat_wait_ready(tci_ctx *ctx, tci_dmat *a);
 
 struct TargetDev {
-    int kind = 0; // 0 analytic, 1 TT, 2 MPO pair, 3 user source (NVRTC)
+    int kind = 0; // 0 analytic, 1 TT, 2 MPO pair, 3 user source (NVRTC), 4 memoised wrapper of another target (cache.cu)
+    i64 cache_id = 0; // kind 4: this target's own id, the key of its table
     i64 nsites = 0;
     std::vector<i64> localdims;
     // analytic
@@ -329,3 +330,8 @@ int pi_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *dI, i64 nl, i64 nI, con
                   tci_dmat *out, const i64 *hI, const i64 *hJ);
 int target_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, double *d_out);
 int maxabs_dev(tci_ctx *ctx, const double *p, i64 m, i64 n, i64 ld, unsigned long long *d_maxbits);
+// cache.cu: CachedFunction as a device-resident memo
+int pi_eval_cached(tci_ctx *ctx, i64 target_id, TargetDev &t, const i64 *dI, i64 nl, i64 nI, const i64 *dJ, i64 nr, i64 nJ,
+                   i64 M, tci_dmat *out, unsigned long long *d_maxbits);
+int target_eval_cached(tci_ctx *ctx, i64 target_id, TargetDev &t, const i64 *d_idx, i64 count, double *d_out);
+void cache_target_free(tci_ctx *ctx, i64 id);

@@ -76,13 +76,36 @@ def rank(tci):
     return max(tci.linkdims())
 
 
+class DeviceSiteTensors:
+    """tci.sitetensors while the tensors live in HBM (fillsitetensors! leaves them on the device for the global pivot
+    finder, their only consumer inside optimize!): a sequence that fetches a tensor the first time the host reads it
+    (tci_tt_fetch_core).  Assigning an element turns the object into an ordinary list of host arrays."""
+
+    def __init__(self, handle, n):
+        self.handle, self._cache = handle, [None] * n
+
+    def __len__(self):
+        return len(self._cache)
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        if self._cache[b] is None:
+            self._cache[b] = self.handle.core(b)
+        return self._cache[b]
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self)))
+
+
 def invalidatesitetensors(tci):  # :90-95
-    for b in range(len(tci)):
-        tci.sitetensors[b] = np.zeros((0, 0, 0), order="F")
+    tci.sitetensors = [np.zeros((0, 0, 0), order="F") for _ in range(len(tci))]
     tci.device_tt = None  # the device-resident copy of the site tensors (tci_fill_sitetensors) goes with them
 
 
 def issitetensorsavailable(tci):  # :100-102
+    if isinstance(tci.sitetensors, DeviceSiteTensors):
+        return True
     return all(t.size != 0 for t in tci.sitetensors)
 
 
@@ -158,7 +181,13 @@ def filltensor(f, localdims, Iset, Jset, M, device=False):
     return f(Iset, Jset, M)
 
 
+def _hostsitetensors(tci):
+    if isinstance(tci.sitetensors, DeviceSiteTensors):
+        tci.sitetensors = list(tci.sitetensors)
+
+
 def setsitetensor(tci, b, T):  # :329-338
+    _hostsitetensors(tci)
     tci.sitetensors[b] = np.asfortranarray(T).reshape(
         (tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]), order="F")
 
@@ -172,6 +201,7 @@ def setsitetensor_fill(tci, f, b):
     P is factorised to full rank by the K2 kernel and the solve runs on the device (tci_lu_rdiv) in place of
     the reference's LAPACK `\\` (:391); only T_b comes back to the host."""
     n = len(tci)
+    _hostsitetensors(tci)
     nI, d, nJ = tci.Iset[b].shape[0], tci.localdims[b], tci.Jset[b].shape[0]
     if b == n - 1:
         Pi1, _, mx = f._pi(tci.Iset[b], tci.Jset[b], 1, True, False)
@@ -198,10 +228,10 @@ def fillsitetensors(tci, f):
     for b in range(len(tci) - 1):
         if tci.Iset[b + 1].shape[0] != tci.Jset[b].shape[0]:
             raise RuntimeError(f"Pivot matrix at bond {b + 1} is not square!")  # :388
-    Ts, mx, handle = f.fill_sitetensors(tci.Iset, tci.Jset)
+    lazy = not getattr(f, "is_complex", False)
+    Ts, mx, handle = f.fill_sitetensors(tci.Iset, tci.Jset, want_host=False) if lazy else f.fill_sitetensors(tci.Iset, tci.Jset)
     updatemaxsample(tci, mx)
-    for b, T in enumerate(Ts):
-        tci.sitetensors[b] = T
+    tci.sitetensors = DeviceSiteTensors(handle, len(tci)) if lazy else list(Ts)
     tci.device_tt = handle
 
 
@@ -523,7 +553,11 @@ def optimize(tci, f, tolerance=None, pivottolerance=None, maxbonddim=I64MAX, max
         errors.append(pivoterror(tci))
         if verbosity > 1:
             print(f"  Walltime {time.perf_counter() - tstart} sec: start searching global pivots", flush=True)
-        current_tt = TensorTrain(tci.sitetensors)
+        if isinstance(tci.sitetensors, DeviceSiteTensors):  # the cores are on the device already: nothing is copied
+            current_tt = TensorTrain.__new__(TensorTrain)
+            current_tt.sitetensors = tci.sitetensors
+        else:
+            current_tt = TensorTrain(tci.sitetensors)
         current_tt.device_handle = tci.device_tt  # the same cores, already on the device (tci_fill_sitetensors)
         inp = GlobalPivotSearchInput(tci.localdims, current_tt, tci.maxsamplevalue, tci.Iset, tci.Jset)
         globalpivots = finder(inp, f, abstol, verbosity=verbosity, rng=rng)
