@@ -460,8 +460,8 @@ def block_luci(T, ctx, fp64_peak_tf):
     return out
 
 
-def gsearch_setup(T, ctx):
-    ld, chi, nsearch = [64] * 12, 128, 2048
+def gsearch_setup(T, ctx, nsearch=2048):
+    ld, chi = [64] * 12, 128
     f = T.BuiltinTarget(T.SEPCOS, sepcos_params(), ld, ctx=ctx)
     bonds = [1] + [chi] * 11 + [1]
     g9 = np.random.default_rng(9)
@@ -496,6 +496,91 @@ def block_globalsearch(T, ctx, mode=0):
     return {"shape": "12 sites d=64, TT bond 128, 2048 starts, 1572864 probes", "probes": probes,
             "environments": res["environments"], "ordered_chain": res["ordered_chain"],
             "pivots_identical_between_modes": same}
+
+
+def block_complex(T, ctx, orc):
+    """ComplexF64 value type: the complex DMMA GEMM, the complex rrLU (bit-identical to the oracle's
+    restatement of matrixlu.jl with Julia Base's complex arithmetic; checked here on a small sample) and a complex
+    contraction Pi at a reduced config-5 shape."""
+    rng = np.random.default_rng(3)
+    out = {}
+    M = N = 4096
+    K = 1024
+    A = np.asfortranarray(rng.standard_normal((M, K)) + 1j * rng.standard_normal((M, K)))
+    B = np.asfortranarray(rng.standard_normal((K, N)) + 1j * rng.standard_normal((K, N)))
+    T.zgemm(A, B)
+    ctx.timers(reset=True)
+    for _ in range(3):
+        T.zgemm(A, B)
+    ms = ctx.timers(reset=True)["gemm"] / 3
+    out["zgemm_4096x4096x1024"] = {"ms": ms, "tflops": 8.0 * M * N * K / (ms * 1e-3) / 1e12,
+                                   "kernel": "k_zgemm_mma (four DMMA m8n8k4 per complex tile)",
+                                   "flop_model": "8 real flops per complex multiply-add"}
+    m = n = 2048
+    r = 256
+    s = 2.0 ** (-30.0 * np.arange(r) / r)
+    Z = ((rng.standard_normal((m, r)) + 1j * rng.standard_normal((m, r))) * s) @ (
+        rng.standard_normal((r, n)) + 1j * rng.standard_normal((r, n)))
+    T.rrlu(Z, maxrank=r, reltol=1e-12)
+    ctx.timers(reset=True)
+    lu = T.rrlu(Z, maxrank=r, reltol=1e-12)
+    ms = ctx.timers(reset=True)["rrlu_kernel"]
+    by = 16.0 * m * n + sum(32.0 * (m - k) * (n - k) for k in range(1, lu.npivot))
+    out["zrrlu_2048_r256"] = {"ms": ms, "npivot": int(lu.npivot), "us_per_pivot": ms * 1e3 / max(lu.npivot, 1),
+                              "gflops": sum(8.0 * (m - k) * (n - k) for k in range(1, lu.npivot + 1)) / (ms * 1e-3) / 1e9,
+                              "model_gbs": by / (ms * 1e-3) / 1e9,
+                              "bytes_model": "16 B read + 16 B write per trailing element per pivot (64 MB matrix: L2 resident)"}
+    if orc is not None:
+        Zs = np.asfortranarray(Z[:300, :260])
+        a, b = T.rrlu(Zs, maxrank=40, reltol=1e-12), orc.zrrlu(Zs, maxrank=40, reltol=1e-12)
+        out["zrrlu_2048_r256"]["sample_300x260_bit_identical_to_oracle"] = bool(
+            np.array_equal(a.rowpermutation, b.rowpermutation) and np.array_equal(a.colpermutation, b.colpermutation)
+            and np.array_equal(a.L, b.L) and np.array_equal(a.U, b.U))
+    ns, D, nl = 20, 128, 512
+    bonds = [1] + [D] * (ns - 1) + [1]
+    ca = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5 + 1j * (rng.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5)) / 8.0)
+          for i in range(ns)]
+    cb = [np.asfortranarray((rng.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5 + 1j * (rng.random((bonds[i], 2, 2, bonds[i + 1])) - 0.5)) / 8.0)
+          for i in range(ns)]
+    fz = T.ZContraction(ca, cb, ctx=ctx)
+    I = np.stack([rng.integers(1, 5, nl) for _ in range(ns // 2)], axis=1).astype(np.int64)
+    J = np.stack([rng.integers(1, 5, nl) for _ in range(ns // 2)], axis=1).astype(np.int64)
+    d, mx = fz.batchevaluate_device(I, J, 0)
+    del d
+    ctx.timers(reset=True)
+    d, mx = fz.batchevaluate_device(I, J, 0)
+    del d
+    ms = ctx.timers(reset=True)["pi_eval"]
+    ext = 4.0 * (2.0 * D * D * 2 * D + 2.0 * D * 2 * D * D)  # one complex environment extension, real flops
+    fl = sum(len(np.unique(I[:, :k], axis=0)) for k in range(2, ns // 2 + 1)) * ext + \
+        sum(len(np.unique(J[:, ns // 2 - k:], axis=0)) for k in range(2, ns // 2 + 1)) * ext + 8.0 * nl * D * D * nl
+    out["contraction_pi_20sites_bond128"] = {"ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "shape": "nL = nR = 512, M = 0"}
+    return out
+
+
+def block_cached(T, ctx):
+    """CachedFunction as a device-resident memo (tci_target_cached): a 4096 x 4096 Pi of the config-4 target through the
+    memo, first call (all misses: lookup + evaluation of the wrapped target + insertion) and second call (all hits)."""
+    rng = np.random.default_rng(11)
+    ld = [64] * 12
+    f = T.BuiltinTarget(T.SEPCOS, sepcos_params(), ld, ctx=ctx)
+    cf = T.CachedFunction(f, capacity_log2=26)
+    n = 4096
+    I = np.stack([rng.integers(1, 65, n) for _ in range(6)], axis=1).astype(np.int64)
+    J = np.stack([rng.integers(1, 65, n) for _ in range(6)], axis=1).astype(np.int64)
+    res = {}
+    for label in ("first_call_all_misses", "second_call_all_hits"):
+        t0 = time.perf_counter()
+        d, mx = cf.batchevaluate_device(I, J, 0)
+        res[label] = {"ms": (time.perf_counter() - t0) * 1e3}
+        res[label]["mlookups_per_s"] = n * n / res[label]["ms"] / 1e3
+        del d
+    t0 = time.perf_counter()
+    d, mx = f.batchevaluate_device(I, J, 0)
+    res["uncached_ms"] = (time.perf_counter() - t0) * 1e3
+    res["stats"] = cf.stats()
+    res["table"] = "2^26 slots x 32 B = 2 GiB in HBM, UInt128 keys"
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------- main ----
@@ -644,7 +729,9 @@ def main():
                              ("time_to_tol", lambda: block_time_to_tol(T, orc, orc is not None)),
                              ("contraction", lambda: block_contraction(T, ctx, torch, peak_tf)),
                              ("luci", lambda: block_luci(T, ctx, peak_tf)),
-                             ("globalsearch", lambda: block_globalsearch(T, ctx))):
+                             ("globalsearch", lambda: block_globalsearch(T, ctx)),
+                             ("complex", lambda: block_complex(T, ctx, orc)),
+                             ("cached_function", lambda: block_cached(T, ctx))):
                 try:
                     out[name] = fn()
                 except Exception as e:  # a side block never takes the headline line down
@@ -687,18 +774,21 @@ def sharded_stages(T, ctx, torch, world, fm, I, J):
     del d
     stages["mpo_pi_config5"] = {"ms_1gpu": (t1 - t0) * 1e3}
     del f1
-    # --- global search at config-4 shape ---
-    res = {}
-    for label, c in (("n", ctx), ("1", c1)):
-        f, finder, inp, probes = gsearch_setup(T, c)
-        found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=2)
-        t0 = time.perf_counter()
-        for _ in range(3):
+    # --- global search at config-4 shape: 2048 starts (4.5 ms on one GPU: fixed costs dominate the sharded form) and
+    #     16384 starts (the size at which eight GPUs have something to split) ---
+    parity["gsearch"] = True
+    for nsearch, key in ((2048, "globalsearch_config4"), (16384, "globalsearch_config4_16k_starts")):
+        res = {}
+        for label, c in (("n", ctx), ("1", c1)):
+            f, finder, inp, probes = gsearch_setup(T, c, nsearch)
             found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=2)
-        res[label] = ((time.perf_counter() - t0) / 3 * 1e3, found.tolist(), finder.last_errors.tolist())
-    stages["globalsearch_config4"] = {"ms": res["n"][0], "ms_1gpu": res["1"][0], "probes": probes,
-                                      "mode": "environments; blocks of starts per GPU, records by one ncclAllGather"}
-    parity["gsearch"] = res["n"][1] == res["1"][1] and res["n"][2] == res["1"][2]
+            t0 = time.perf_counter()
+            for _ in range(3):
+                found = finder(inp, f, 1e-3, rng=T.CounterRNG(1), mode=2)
+            res[label] = ((time.perf_counter() - t0) / 3 * 1e3, found.tolist(), finder.last_errors.tolist())
+        stages[key] = {"ms": res["n"][0], "ms_1gpu": res["1"][0], "probes": probes,
+                       "mode": "environments; blocks of starts per GPU, records by one ncclAllGather"}
+        parity["gsearch"] = parity["gsearch"] and res["n"][1] == res["1"][1] and res["n"][2] == res["1"][2]
     # --- Pi evaluation of analytic targets: the cost model decides whether sharding pays ---
     rng = np.random.default_rng(7)
     ld = [64] * 12
