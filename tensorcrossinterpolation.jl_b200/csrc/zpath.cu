@@ -25,6 +25,7 @@ namespace cg = cooperative_groups;
 
 #define ZR_THREADS 512
 #define ZR_XCAP 8192 // pivot-column entries kept in shared memory (16 B each)
+#define ZR_CH 512    // rows of a work item of the trailing update
 
 struct __align__(16) ZCand {
     double val; // abs2 of the candidate (-inf: none)
@@ -164,17 +165,22 @@ template <bool LEFT> __global__ void __launch_bounds__(ZR_THREADS, 1) k_zrrlu(ZA
 
     // first search: the whole matrix
     reset_best();
-    for (int c = g + G * warp; c < n; c += G * nwarps) {
-        const int pos = c;
-        consider_default(pos, c, 0);
-        const double2 *col = A + ld * c;
-        for (int i = lane; i < m; i += 32) {
-            const double v = tci_zabs2(zld(col + i));
-            if (v >= bv && zbetter(v, pos, i, bv, bpos, brow)) {
-                bv = v;
-                bpos = pos;
-                brow = i;
-                bcol = c;
+    {
+        const int nown = (n - g + G - 1) / G, nch = (m + ZR_CH - 1) / ZR_CH;
+        for (int item = warp; item < nown * nch; item += nwarps) {
+            const int oc = item / nch, ch = item - oc * nch;
+            const int c = g + G * oc, pos = c;
+            if (ch == 0) consider_default(pos, c, 0);
+            const double2 *col = A + ld * c;
+            const int r1 = min(m, (ch + 1) * ZR_CH);
+            for (int i = ch * ZR_CH + lane; i < r1; i += 32) {
+                const double v = tci_zabs2(zld(col + i));
+                if (v >= bv && zbetter(v, pos, i, bv, bpos, brow)) {
+                    bv = v;
+                    bpos = pos;
+                    brow = i;
+                    bcol = c;
+                }
             }
         }
     }
@@ -273,24 +279,56 @@ template <bool LEFT> __global__ void __launch_bounds__(ZR_THREADS, 1) k_zrrlu(ZA
         }
         k++;
         if (k >= a.maxrank) break;
-        // trailing update a - x*y (:132) fused with the search of the next pivot
+        // trailing update a - x*y (:132) fused with the search of the next pivot.  Work items = (own column, chunk of
+        // ZR_CH rows), dealt round-robin to the warps: a CTA owns only ~n/G columns, so whole columns per warp would
+        // leave most warps idle.  zbetter is a total order, so the visiting order does not matter.
         reset_best();
-        for (int c = g + G * warp; c < n; c += G * nwarps) {
-            const int pos = a.colpos[c];
-            if (pos < k) continue;
-            consider_default(pos, c, k);
-            double2 *col = A + ld * c;
-            const tci_z y = zld(col + (k - 1));
-            for (int i = k + lane; i < m; i += 32) {
-                const double2 xv = i < ZR_XCAP ? xs[i] : __ldcg(px + (i == pr ? k - 1 : i));
-                const tci_z v = tci_zsub(zld(col + i), tci_zmul(tci_zmake(xv.x, xv.y), y));
-                col[i] = make_double2(v.re, v.im);
-                const double v2 = tci_zabs2(v);
-                if (v2 >= bv && zbetter(v2, pos, i, bv, bpos, brow)) {
-                    bv = v2;
-                    bpos = pos;
-                    brow = i;
-                    bcol = c;
+        {
+            const int nown = (n - g + G - 1) / G, nch = (m - k + ZR_CH - 1) / ZR_CH;
+            for (int item = warp; item < nown * nch; item += nwarps) {
+                const int oc = item / nch, ch = item - oc * nch;
+                const int c = g + G * oc;
+                const int pos = a.colpos[c];
+                if (pos < k) continue;
+                if (ch == 0) consider_default(pos, c, k);
+                double2 *col = A + ld * c;
+                const tci_z y = zld(col + (k - 1));
+                const int r1 = min(m, k + (ch + 1) * ZR_CH);
+                int i = k + ch * ZR_CH + lane;
+                for (; i + 96 < r1; i += 128) { // four independent 16-byte loads in flight per lane
+                    double2 a4[4], x4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a4[u] = col[i + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = i + 32 * u;
+                        x4[u] = r < ZR_XCAP ? xs[r] : __ldcg(px + (r == pr ? k - 1 : r));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = i + 32 * u;
+                        const tci_z v = tci_zsub(tci_zmake(a4[u].x, a4[u].y), tci_zmul(tci_zmake(x4[u].x, x4[u].y), y));
+                        col[r] = make_double2(v.re, v.im);
+                        const double v2 = tci_zabs2(v);
+                        if (v2 >= bv && zbetter(v2, pos, r, bv, bpos, brow)) {
+                            bv = v2;
+                            bpos = pos;
+                            brow = r;
+                            bcol = c;
+                        }
+                    }
+                }
+                for (; i < r1; i += 32) {
+                    const double2 xv = i < ZR_XCAP ? xs[i] : __ldcg(px + (i == pr ? k - 1 : i));
+                    const tci_z v = tci_zsub(zld(col + i), tci_zmul(tci_zmake(xv.x, xv.y), y));
+                    col[i] = make_double2(v.re, v.im);
+                    const double v2 = tci_zabs2(v);
+                    if (v2 >= bv && zbetter(v2, pos, i, bv, bpos, brow)) {
+                        bv = v2;
+                        bpos = pos;
+                        brow = i;
+                        bcol = c;
+                    }
                 }
             }
         }
