@@ -117,6 +117,7 @@ void target_free(tci_ctx *ctx, TargetDev &t)
     for (double *p : t.cores) cudaFree(p);
     for (double *p : t.A) cudaFree(p);
     for (double *p : t.B) cudaFree(p);
+    for (double *p : t.Bp) cudaFree(p);
 }
 
 // frees a context that has been destroyed by its owner once the last dmat / lu handle that points at it is gone
@@ -556,6 +557,7 @@ int target_replicate(tci_ctx *ctx, i64 id)
         std::fill(t->cores.begin(), t->cores.end(), nullptr);
         std::fill(t->A.begin(), t->A.end(), nullptr);
         std::fill(t->B.begin(), t->B.end(), nullptr);
+        t->Bp.clear(); // made again on this device on first use
         cudaError_t e = cudaSuccess;
         t->user_lib = t->user_pi = t->user_points = nullptr;
         if (src.kind == 0 || src.kind == 3) {

@@ -573,7 +573,8 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         // 32-deep k-tiles with two stages (same shared memory, half as many barriers and copy phases per flop) win once
         // the k-loop is long: 4096^3 33.5 -> 34.1 TFLOP/s, 8192^2 x 512 31.9 -> 32.3; at K = 256 (the MPO environment
         // steps) the longer pipeline fill loses: config-5 Pi 145.3 vs 147.6 ms
-        if ((variant == 2 || (variant == 0 && K >= 1024)) && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
+        static const i64 k32_min = getenv("TCI_DGEMM_K32_MIN") ? atoll(getenv("TCI_DGEMM_K32_MIN")) : 1024;
+        if ((variant == 2 || (variant == 0 && K >= k32_min)) && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
             int rc = launch_dgemm_mma_async<128, 64, 2, 2, 32, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
                                                                   beta, C, ldc, strideC, batch, offA, offB);
             if (rc) return rc;

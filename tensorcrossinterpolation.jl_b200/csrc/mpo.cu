@@ -27,6 +27,39 @@ template <class V> static MpoSiteT<V> site_of(const TargetDev &t, i64 s)
 int zgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double2 *A, i64 lda,
                           i64 strideA, const double2 *B, i64 ldb, i64 strideB, double beta, double2 *C, i64 ldc,
                           i64 strideC, i64 batch, const i64 *offA, const i64 *offB); // zgemm.cu
+
+// Bp[bl, br, h, j] = B[bl, h, j, br]: with this copy the second product of a right-environment step,
+//   nxt[al, bl] = sum_{br, h} tmp[(br, h), al] * B[bl, h, j, br]      (contraction.jl:144-176),
+// is ONE GEMM with inner dimension Lbn * S instead of S accumulating GEMMs (the reference permutes its cores once as
+// well: `bperm`, contraction.jl:152-158).
+template <class V>
+__global__ void k_permute_b(const V *__restrict__ B, i64 Lb, i64 S, i64 d3, i64 Lbn, V *__restrict__ Bp)
+{
+    const i64 total = Lb * S * d3 * Lbn;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 bl = e % Lb, br = (e / Lb) % Lbn, h = (e / (Lb * Lbn)) % S, j = e / (Lb * Lbn * S);
+        Bp[e] = B[bl + Lb * (h + S * (j + d3 * br))];
+    }
+}
+template <class V> static int ensure_bperm(tci_ctx *ctx, TargetDev &t)
+{
+    if (!t.Bp.empty()) return TCI_OK;
+    std::vector<double *> bp((size_t)t.nsites, nullptr);
+    for (i64 s = 0; s < t.nsites; ++s) {
+        const i64 total = t.bdl[s] * t.bs1[s] * t.bs2[s] * t.bdr[s];
+        cudaError_t e = cudaMalloc(&bp[s], (size_t)std::max<i64>(total, 1) * sizeof(V));
+        if (e != cudaSuccess) {
+            for (double *p : bp) cudaFree(p);
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("permuted MPO cores: ") + cudaGetErrorString(e));
+        }
+        k_permute_b<V><<<(unsigned)std::min<i64>((total + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+            (const V *)t.B[s], t.bdl[s], t.bs1[s], t.bs2[s], t.bdr[s], (V *)bp[s]);
+        ctx->launches++;
+    }
+    t.Bp = bp;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
 static inline int gemm_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
                            i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, i64 batch,
                            const i64 *offA, const i64 *offB, bool even)
@@ -152,7 +185,7 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
                 const i64 f = P.sigma[k][u];
                 g[u] = P.parent[k][u] * ea * eb;
                 oa[u] = m.La * (f % m.d1);
-                ob[u] = m.Lb * m.S * (f / m.d1);
+                ob[u] = (right ? m.Lb * m.Lbn * m.S : m.Lb * m.S) * (f / m.d1); // right chains read the permuted copy
             }
             ea = right ? m.La : m.Lan;
             eb = right ? m.Lb : m.Lbn;
@@ -191,10 +224,10 @@ static int mpo_chain_planned(tci_ctx *ctx, const TargetDev &t, const ChainPlan &
                                            m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h,
                                            m.Lbn * m.S, m.Lbn * m.S * m.La, c, g, oa,
                                            m.La % 2 == 0 && (m.Lan * m.Lbn) % 2 == 0);
-            for (i64 h = 0; h < m.S && !rc; ++h)
-                rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
-                                           m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0,
-                                           nxt, m.La, m.La * m.Lb, c, nullptr, ob, (m.Lb * m.S) % 2 == 0);
+            if (!rc) // (La x Lb) = tmp^T (La x Lbn*S) * Bp_j^T (Lbn*S x Lb)
+                rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn * m.S, 1.0, tmp, m.Lbn * m.S, m.Lbn * m.S * m.La,
+                              (const V *)t.Bp[right ? N - 1 - k : k], m.Lb, 0, 0.0, nxt, m.La, m.La * m.Lb, c, nullptr, ob,
+                              (m.Lb * m.Lbn * m.S) % 2 == 0);
             Ea = m.La;
             Eb = m.Lb;
         }
@@ -284,6 +317,7 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
                            V **out, i64 *La_out, i64 *Lb_out, const i64 *h_idx = nullptr)
 {
     const int N = (int)t.nsites;
+    if (int rcp = ensure_bperm<V>(ctx, const_cast<TargetDev &>(t))) return rcp; // a cache of the target, made once
     if (h_idx && !getenv("TCI_MPO_NO_DEDUP")) {
         ChainPlan P;
         std::vector<i64> dims((size_t)std::max(nsteps, 0));
@@ -302,7 +336,7 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
     for (int s = N - 1; s >= N - nsteps; --s) {
         MpoSiteT<V> m = site_of<V>(t, s);
         k_mpo_offsets<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(
-            d_idx, len, s - (N - nsteps) + off, count, m.d1, m.La, m.Lb * m.S, offA.p, offB.p);
+            d_idx, len, s - (N - nsteps) + off, count, m.d1, m.La, m.Lb * m.Lbn * m.S, offA.p, offB.p);
         ctx->launches++;
         V *tmp = nullptr, *nxt = nullptr;
         // tmp[q][br + Lbn*(h + S*al)] = sum_ar env[ar, br] * A[al, i, h, ar]
@@ -313,11 +347,11 @@ static int mpo_right_chain(tci_ctx *ctx, const TargetDev &t, int nsteps, const i
             rc = gemm_off(ctx, true, true, m.Lbn, m.La, m.Lan, 1.0, env, m.Lan, m.Lan * m.Lbn,
                                        m.A + m.La * m.d1 * h, m.La * m.d1 * m.S, 0, 0.0, tmp + m.Lbn * h, m.Lbn * m.S,
                                        m.Lbn * m.S * m.La, count, nullptr, offA.p, m.La % 2 == 0);
-        // nxt[q][al, bl] = sum_{br,h} tmp[br, h, al] * B[bl, h, j, br]
-        for (i64 h = 0; h < m.S && !rc; ++h) // (La x Lb) += tmp_h^T (La x Lbn) * B_{j,h}^T (Lbn x Lb)
-            rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn, 1.0, tmp + m.Lbn * h, m.Lbn * m.S,
-                                       m.Lbn * m.S * m.La, m.B + m.Lb * h, m.Lb * m.S * m.d3, 0, h ? 1.0 : 0.0, nxt,
-                                       m.La, m.La * m.Lb, count, nullptr, offB.p, (m.Lb * m.S) % 2 == 0);
+        // nxt[q][al, bl] = sum_{br,h} tmp[br, h, al] * B[bl, h, j, br]: (La x Lb) = tmp^T (La x Lbn*S) * Bp_j^T (Lbn*S x Lb)
+        if (!rc)
+            rc = gemm_off(ctx, true, true, m.La, m.Lb, m.Lbn * m.S, 1.0, tmp, m.Lbn * m.S, m.Lbn * m.S * m.La,
+                          (const V *)t.Bp[s], m.Lb, 0, 0.0, nxt, m.La, m.La * m.Lb, count, nullptr, offB.p,
+                          (m.Lb * m.Lbn * m.S) % 2 == 0);
         dev_free(ctx, tmp);
         dev_free(ctx, env);
         env = nxt;

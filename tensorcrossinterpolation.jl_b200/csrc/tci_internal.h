@@ -50,6 +50,9 @@ struct TargetDev {
     std::vector<i64> dl, d, dr;
     // MPO pair
     std::vector<double *> A, B;
+    // B permuted to (Lb, Lbn, S, d3) per site: the right-environment chain contracts (br, h) as ONE inner dimension
+    // (made on first use, mpo.cu)
+    std::vector<double *> Bp;
     std::vector<i64> adl, as1, as2, adr, bdl, bs1, bs2, bdr;
     // user source: the compiled module (kept so that it can be loaded on every GPU of a group) and its kernels
     std::vector<char> cubin;
