@@ -397,6 +397,149 @@ __global__ void __launch_bounds__(32 * NWM * NWN)
         }
 }
 
+// ---- tile-stream variant for short inner dimensions ---------------------------------------------------------
+// The environment chains of a contraction Pi are batches of ~1000 products with K = 256 or 512: a 128 x 64 tile then has
+// only 16 (32) k-tiles, and the pipeline fill at its start and the drain at its end are a visible fraction of it.  Here
+// a CTA walks TPC consecutive tiles as ONE stream of k-tiles: the copies of the next tile's first k-tiles are issued
+// while the last k-tiles of the current one are multiplied, so the DMMA stream only pauses for the accumulator
+// stores.  Interior tiles only (M % 128 == 0, N % 64 == 0, K % 16 == 0; the launcher checks), 128 x 64 x 16 tiles,
+// 4 warps, 3 stages, two CTAs per SM as in k_dgemm_mma_async<128, 64, 2, 2>.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(128)
+    k_dgemm_mma_stream(i64 M, i64 N, i64 K, double alpha, const double *__restrict__ A, i64 lda, i64 strideA,
+                       const double *__restrict__ B, i64 ldb, i64 strideB, double beta, double *__restrict__ C, i64 ldc,
+                       i64 strideC, const i64 *__restrict__ offA, const i64 *__restrict__ offB, int mx, int ny, i64 total, int TPC)
+{
+    constexpr int BM = 128, BN = 64, NWM = 2, KT = 16, NST = 3, NT = 128;
+    constexpr int TI = BM / NWM / 8, TJ = BN / 2 / 8;
+    constexpr int A_ROW = TA ? KT + 4 : BM + 4, A_ROWS = TA ? BM : KT;
+    constexpr int B_ROW = TB ? BN + 4 : KT + 4, B_ROWS = TB ? KT : BN;
+    constexpr int A_SZ = A_ROW * A_ROWS, B_SZ = B_ROW * B_ROWS;
+    constexpr int AQ = BM * KT / 2 / NT, BQ = BN * KT / 2 / NT;
+    constexpr int A_DIV = TA ? KT / 2 : BM / 2, B_DIV = TB ? BN / 2 : KT / 2;
+    extern __shared__ __align__(16) double dsm[];
+    double *const Asm = dsm, *const Bsm = dsm + NST * A_SZ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp % NWM) * (BM / NWM), wn = (warp / NWM) * (BN / 2);
+    const int fr = lane >> 2, fk = lane & 3;
+    const i64 t0 = (i64)blockIdx.x * TPC;
+    const int nt = (int)(total - t0 < TPC ? total - t0 : TPC);
+    const int nkt = (int)(K / KT), F = nt * nkt;
+    const int a_in = (tid % A_DIV) * 2, a_out = tid / A_DIV, b_in = (tid % B_DIV) * 2, b_out = tid / B_DIV;
+    const i64 a_qstep = lda * (NT / A_DIV), b_qstep = ldb * (NT / B_DIV);
+    const i64 a_kstep = TA ? KT : (i64)KT * lda, b_kstep = TB ? (i64)KT * ldb : KT;
+    const int a_soff = a_out * A_ROW + a_in, b_soff = b_out * B_ROW + b_in;
+    const int mxy = mx * ny;
+
+    // producer cursor: tile lt, k-tile lk, this thread's operand pointers for tile lt
+    int lt = 0, lk = 0;
+    const double *gA = nullptr, *gB = nullptr;
+    auto set_tile = [&](int t) {
+        const i64 g = t0 + t;
+        const i64 z = g / mxy;
+        const int r = (int)(g - z * mxy), y = r / mx, x = r - y * mx;
+        const double *Az = A + strideA * z + (offA ? offA[z] : 0), *Bz = B + strideB * z + (offB ? offB[z] : 0);
+        const i64 m0 = (i64)x * BM, n0 = (i64)y * BN;
+        gA = TA ? Az + (a_in + lda * (m0 + a_out)) : Az + (m0 + a_in + lda * a_out);
+        gB = TB ? Bz + (n0 + b_in + ldb * b_out) : Bz + (b_in + ldb * (n0 + b_out));
+    };
+    auto produce = [&](int stage) { // copies of (lt, lk) into `stage`, then the cursor advances
+        if (lt < nt) {
+            double *as = Asm + stage * A_SZ + a_soff, *bs = Bsm + stage * B_SZ + b_soff;
+            const double *pa = gA + lk * a_kstep, *pb = gB + lk * b_kstep;
+#pragma unroll
+            for (int q = 0; q < AQ; ++q) cp_async16(as + q * (NT / A_DIV) * A_ROW, pa + q * a_qstep, 16);
+#pragma unroll
+            for (int q = 0; q < BQ; ++q) cp_async16(bs + q * (NT / B_DIV) * B_ROW, pb + q * b_qstep, 16);
+            if (++lk == nkt) {
+                lk = 0;
+                if (++lt < nt) set_tile(lt);
+            }
+        }
+        cp_async_commit();
+    };
+    set_tile(0);
+#pragma unroll
+    for (int st = 0; st < NST - 1; ++st) produce(st);
+
+    double acc[TI][TJ][2];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    int ct = 0, ck = 0;
+    for (int f = 0; f < F; ++f) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();
+        produce((f + NST - 1) % NST);
+        const double *as = Asm + (f % NST) * A_SZ, *bs = Bsm + (f % NST) * B_SZ;
+#pragma unroll
+        for (int k4 = 0; k4 < KT; k4 += 4) {
+            double af[TI], bf[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+                af[i] = TA ? as[(wm + 8 * i + fr) * A_ROW + k4 + fk] : as[(k4 + fk) * A_ROW + wm + 8 * i + fr];
+#pragma unroll
+            for (int j = 0; j < TJ; ++j)
+                bf[j] = TB ? bs[(k4 + fk) * B_ROW + wn + 8 * j + fr] : bs[(wn + 8 * j + fr) * B_ROW + k4 + fk];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (++ck == nkt) { // tile ct is complete: store it and start the next accumulator
+            const i64 g = t0 + ct;
+            const i64 z = g / mxy;
+            const int r = (int)(g - z * mxy), y = r / mx, x = r - y * mx;
+            double *Cz = C + strideC * z + ((i64)x * BM + wm + fr) + ldc * ((i64)y * BN + wn + 2 * fk);
+#pragma unroll
+            for (int j = 0; j < TJ; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < TI; ++i) {
+                        double *cp = Cz + 8 * i + ldc * (8 * j + c);
+                        const double v = alpha * acc[i][j][c];
+                        *cp = (beta == 0.0) ? v : fma(beta, *cp, v);
+                        acc[i][j][c] = 0.0;
+                    }
+            ck = 0;
+            ++ct;
+        }
+    }
+}
+
+static int launch_dgemm_stream(tci_ctx *ctx, int TPC, bool tA, bool tB, i64 M, i64 N, i64 K, double alpha, const double *A, i64 lda,
+                               i64 sA, const double *B, i64 ldb, i64 sB, double beta, double *C, i64 ldc, i64 sC, i64 batch,
+                               const i64 *offA, const i64 *offB)
+{
+    const int mx = (int)(M / 128), ny = (int)(N / 64);
+    const i64 total = (i64)mx * ny * batch;
+    const unsigned grid = (unsigned)((total + TPC - 1) / TPC);
+    constexpr int KT = 16, NST = 3;
+    const size_t smemTT = (size_t)NST * ((KT + 4) * 128 + (64 + 4) * KT) * 8, smemTF = (size_t)NST * ((KT + 4) * 128 + (KT + 4) * 64) * 8,
+                 smemFT = (size_t)NST * ((128 + 4) * KT + (64 + 4) * KT) * 8, smemFF = (size_t)NST * ((128 + 4) * KT + (KT + 4) * 64) * 8;
+#define TCI_STREAM_LAUNCH(TA_, TB_, SM_)                                                                                   \
+    {                                                                                                                      \
+        auto fn = k_dgemm_mma_stream<TA_, TB_>;                                                                       \
+        TCI_CUDA(ctx, ctx_func_smem(ctx, (const void *)fn, (int)(SM_)));                                                   \
+        fn<<<grid, 128, (SM_), ctx->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, offA, offB, mx, ny, \
+                                              total, TPC);                                                                      \
+    }
+    if (tA && tB)
+        TCI_STREAM_LAUNCH(true, true, smemTT)
+    else if (tA && !tB)
+        TCI_STREAM_LAUNCH(true, false, smemTF)
+    else if (!tA && tB)
+        TCI_STREAM_LAUNCH(false, true, smemFT)
+    else
+        TCI_STREAM_LAUNCH(false, false, smemFF)
+#undef TCI_STREAM_LAUNCH
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
 // (A variant fed by cp.async.bulk copies through an mbarrier ring -- one bulk copy per contiguous tile row, no CTA-wide
 // barrier in the main loop -- was built and measured in round 2: 26.0 TFLOP/s at 4096^3 against 29.9 for the cp.async
 // kernel below, also with both operands in 1 KB rows (24.2), so it was dropped.  What did help is halving the CTA:
@@ -573,6 +716,13 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         // 32-deep k-tiles with two stages (same shared memory, half as many barriers and copy phases per flop) win once
         // the k-loop is long: 4096^3 33.5 -> 34.1 TFLOP/s, 8192^2 x 512 31.9 -> 32.3; at K = 256 (the MPO environment
         // steps) the longer pipeline fill loses: config-5 Pi 145.3 vs 147.6 ms
+        // short inner dimension, many interior tiles: the tile-stream kernel (see k_dgemm_mma_stream)
+        static const int stream_tpc = getenv("TCI_DGEMM_STREAM") ? atoi(getenv("TCI_DGEMM_STREAM")) : 2;
+        if (stream_tpc > 0 && use_mma && use_async && aligned16 && M % 128 == 0 && N % 64 == 0 && K % 16 == 0 && K <= 1024 &&
+            !(ldc & 1) && half_ctas >= 16 * (i64)ctx->sm_count) {
+            return launch_dgemm_stream(ctx, stream_tpc, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                       strideC, batch, offA, offB);
+        }
         static const i64 k32_min = getenv("TCI_DGEMM_K32_MIN") ? atoll(getenv("TCI_DGEMM_K32_MIN")) : 1024;
         if ((variant == 2 || (variant == 0 && K >= k32_min)) && use_mma && use_async && aligned16 && M >= 96 && N >= 64 && half_ctas >= 4 * (i64)ctx->sm_count) {
             int rc = launch_dgemm_mma_async<128, 64, 2, 2, 32, 2>(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB,
