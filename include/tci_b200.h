@@ -307,6 +307,13 @@ int tci_zbond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t 
  * contraction.jl:71-93): the complex FP64 tensor-core GEMM (four DMMA per complex tile) behind the chains above.      */
 int tci_zgemm_host(tci_ctx *ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const double *A,
                    const double *B, double *C);
+/* tci_contract_zipup_site / tci_contract_naive_site (contraction.jl:455-464, 338-349) on ComplexF64 cores; C_dev is the
+ * (2*chi*s1*s3) x (Da'*Db') device matrix tci_zrrlu factorises next.                                                  */
+int tci_zcontract_zipup_site(tci_ctx *ctx, const double *R, int64_t chi, int64_t Da, int64_t Db, const double *A,
+                             int64_t s1, int64_t s2, int64_t Dan, const double *B, int64_t s3, int64_t Dbn,
+                             double *C_host /* nullable */, tci_dmat **C_dev /* nullable */);
+int tci_zcontract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s1, int64_t s2, int64_t Dan,
+                             const double *B, int64_t Db, int64_t s3, int64_t Dbn, double *out_host);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,10 @@ _SYMS = {
                                    _lib.i64, _lib.f64, _lib.f64, C.c_int, _lib.P_i64, _lib.P_i64, _lib.P_i64,
                                    _lib.P_f64, _lib.P_f64, _lib.P_f64, C.POINTER(_lib.VP)]),
     "tci_zgemm_host": (C.c_int, [_lib.VP, C.c_int, C.c_int, _lib.i64, _lib.i64, _lib.i64, _lib.VP, _lib.VP, _lib.VP]),
+    "tci_zcontract_zipup_site": (C.c_int, [_lib.VP, _lib.VP, _lib.i64, _lib.i64, _lib.i64, _lib.VP, _lib.i64, _lib.i64,
+                                           _lib.i64, _lib.VP, _lib.i64, _lib.i64, _lib.VP, C.POINTER(_lib.VP)]),
+    "tci_zcontract_naive_site": (C.c_int, [_lib.VP, _lib.VP, _lib.i64, _lib.i64, _lib.i64, _lib.i64, _lib.VP, _lib.i64,
+                                           _lib.i64, _lib.i64, _lib.VP]),
 }
 _lib.SYMBOLS.update(_SYMS)
 if _lib._lib is not None:  # the library was bound before this module was imported
@@ -347,3 +351,34 @@ def zfind_global_pivots(finder, input, f, abstol, rng=None, verbosity=0):
     finder.last_errors = errs[: nf.value].copy()
     finder.last_starts = acc[: nf.value].copy()
     return piv[: nf.value].copy()
+
+
+def zcontractsitetensors(a, b, ctx=None):
+    """_contractsitetensors (contraction.jl:338-349) on ComplexF64 cores (tci_zcontract_naive_site)."""
+    ctx = ctx or _lib.default_context()
+    a, b = _zarr(a), _zarr(b)
+    Da, s1, s2, Dan = a.shape
+    Db, s2b, s3, Dbn = b.shape
+    if s2 != s2b:
+        raise ValueError("shared site dimension mismatch")
+    out = np.zeros(Da * Db * s1 * s3 * Dan * Dbn, dtype=np.complex128)
+    ctx.check(lib().tci_zcontract_naive_site(ctx.h, _pz(a), Da, s1, s2, Dan, _pz(b), Db, s3, Dbn, _pz(out)))
+    return out.reshape((Da * Db, s1, s3, Dan * Dbn), order="F")
+
+
+def zzipup_site(ctx, R, a, b, want_dev):
+    """One zip-up step (contraction.jl:455-464) on ComplexF64 data: the (chi*s1*s3) x (Da'*Db') matrix as a host array
+    or as a ZDeviceMatrix for the factorisation that follows."""
+    R, a, b = _zarr(R), _zarr(a), _zarr(b)
+    chi, Da, Db = R.shape
+    _, s1, s2, Dan = a.shape
+    _, _, s3, Dbn = b.shape
+    if want_dev:
+        h = _lib.VP()
+        ctx.check(lib().tci_zcontract_zipup_site(ctx.h, _pz(R), chi, Da, Db, _pz(a), s1, s2, Dan, _pz(b), s3, Dbn, None,
+                                                 C.byref(h)))
+        return ZDeviceMatrix(ctx, h)
+    out = np.zeros(chi * s1 * s3 * Dan * Dbn, dtype=np.complex128)
+    ctx.check(lib().tci_zcontract_zipup_site(ctx.h, _pz(R), chi, Da, Db, _pz(a), s1, s2, Dan, _pz(b), s3, Dbn, _pz(out),
+                                             None))
+    return out

@@ -68,8 +68,18 @@ class Contraction(BatchEvaluator):
         return apply_projector(super().batchevaluate(leftindexset, rightindexset, M), self.sitedims[nl:nl + M], projector)
 
 
+def _gemm(A, B, ctx):
+    if np.iscomplexobj(A) or np.iscomplexobj(B):
+        from .complexf64 import zgemm
+        return zgemm(A, B, ctx=ctx)
+    return _lib.gemm(A, B, ctx)
+
+
 def _contractsitetensors(a, b, ctx=None):  # contraction.jl:338-349
     ctx = ctx or _lib.default_context()
+    if np.iscomplexobj(a) or np.iscomplexobj(b):
+        from .complexf64 import zcontractsitetensors
+        return zcontractsitetensors(a, b, ctx)
     a = np.asfortranarray(a, dtype=np.float64)
     b = np.asfortranarray(b, dtype=np.float64)
     Da, s1, s2, Dan = a.shape
@@ -100,7 +110,7 @@ def _factorize(A, method, tolerance, maxbonddim, leftorthogonal=False, normalize
     if method == "SVD":
         if isinstance(A, DeviceMatrix):
             A = A.to_host()
-        U, S, Vt = np.linalg.svd(A, full_matrices=False)
+        U, S, Vt = np.linalg.svd(A, full_matrices=False)  # (ComplexF64: Vt is V^H, as Julia's svd(A).Vt)
         err = np.array([np.sum(S[n + 1:] ** 2) for n in range(len(S))])
         nerr = err / np.sum(S ** 2)
 
@@ -127,7 +137,7 @@ def compress(tt, method="LU", tolerance=1e-12, maxbonddim=I64MAX, normalizeerror
                                     maxbonddim=I64MAX, leftorthogonal=True, ctx=ctx)
         cores[ell] = np.asfortranarray(lft).reshape((*shl[:-1], newd), order="F")
         shr = cores[ell + 1].shape
-        nxt = _lib.gemm(rgt, cores[ell + 1].reshape((shr[0], -1), order="F"), ctx)
+        nxt = _gemm(rgt, cores[ell + 1].reshape((shr[0], -1), order="F"), ctx)
         cores[ell + 1] = np.asfortranarray(nxt).reshape((newd, *shr[1:]), order="F")
     for ell in range(n - 1, 0, -1):  # :170-180
         shr = cores[ell].shape
@@ -136,7 +146,7 @@ def compress(tt, method="LU", tolerance=1e-12, maxbonddim=I64MAX, normalizeerror
                                     ctx=ctx)
         cores[ell] = np.asfortranarray(rgt).reshape((newd, *shr[1:]), order="F")
         shl = cores[ell - 1].shape
-        nxt = _lib.gemm(cores[ell - 1].reshape((-1, shl[-1]), order="F"), lft, ctx)
+        nxt = _gemm(cores[ell - 1].reshape((-1, shl[-1]), order="F"), lft, ctx)
         cores[ell - 1] = np.asfortranarray(nxt).reshape((*shl[:-1], newd), order="F")
     return tt
 
@@ -156,6 +166,20 @@ def contract_zipup(A, B, tolerance=1e-12, method="SVD", maxbonddim=I64MAX, ctx=N
     R = np.ones((1, 1, 1), order="F")
     out = []
     N = len(A)
+    if any(np.iscomplexobj(c) for c in list(A) + list(B)):  # TensorTrain{ComplexF64,4}
+        from .complexf64 import zzipup_site
+        for n in range(N):
+            chi = R.shape[0]
+            _, s1, _, Dan = A[n].shape
+            _, _, s3, Dbn = B[n].shape
+            if n == N - 1:
+                out.append(zzipup_site(ctx, R, A[n], B[n], False).reshape((chi, s1, s3, 1), order="F"))
+                break
+            lft, rgt, newdim = _factorize(zzipup_site(ctx, R, A[n], B[n], True), method, tolerance=tolerance,
+                                          maxbonddim=maxbonddim)
+            out.append(np.asfortranarray(lft).reshape((chi, s1, s3, newdim), order="F"))
+            R = np.asfortranarray(rgt).reshape((newdim, Dan, Dbn), order="F")
+        return TensorTrain(out)
     for n in range(N):
         a = np.asfortranarray(A[n], dtype=np.float64)
         b = np.asfortranarray(B[n], dtype=np.float64)
@@ -217,11 +241,6 @@ def contract(A, B, algorithm="TCI", tolerance=1e-12, maxbonddim=I64MAX, f=None, 
                             for c in tt.sitetensors])
     if algorithm == "TCI":
         return contract_TCI(A, B, tolerance=tolerance, maxbonddim=maxbonddim, f=f, **kwargs)
-    if algorithm != "TCI" and any(np.iscomplexobj(c) for c in ca + cb):
-        if f is not None:
-            raise RuntimeError("Naive contraction implementation cannot contract matrix product with a function. "
-                               "Use algorithm=:TCI instead.")
-        raise NotImplementedError("ComplexF64 tensor trains: only algorithm=:TCI runs on the device so far")
     if algorithm == "naive":
         if f is not None:
             raise RuntimeError("Naive contraction implementation cannot contract matrix product with a function. "

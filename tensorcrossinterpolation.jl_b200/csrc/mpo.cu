@@ -499,38 +499,42 @@ int target_eval_mpo_z(tci_ctx *ctx, TargetDev &t, const i64 *d_idx, i64 count, d
 }
 
 // ---- K6 -------------------------------------------------------------------------
-extern "C" int tci_contract_zipup_site(tci_ctx *ctx, const double *R, int64_t chi, int64_t Da, int64_t Db,
-                                       const double *A, int64_t s1, int64_t s2, int64_t Dan, const double *B,
-                                       int64_t s3, int64_t Dbn, double *C_host, tci_dmat **C_dev)
+// one zip-up step (contraction.jl:455-464) for value type V (double, or double2 = interleaved ComplexF64); sizes in
+// elements of V; C is a ((W * chi*s1*s3) x Dan*Dbn) device matrix of doubles, W = doubles per element
+template <class V>
+static int zipup_site_t(tci_ctx *ctx, const double *R, i64 chi, i64 Da, i64 Db, const double *A, i64 s1, i64 s2, i64 Dan,
+                        const double *B, i64 s3, i64 Dbn, double *C_host, tci_dmat **C_dev)
 {
-    TCI_ENTER(ctx);
+    constexpr i64 W = sizeof(V) / sizeof(double);
     if (C_dev) *C_dev = nullptr;
     if (chi < 1 || Da < 1 || Db < 1 || s1 < 1 || s2 < 1 || s3 < 1 || Dan < 1 || Dbn < 1 || !R || !A || !B)
         return tci_fail(ctx, TCI_ERR_ARG, "tci_contract_zipup_site: bad arguments");
     DevBuf<double> dR(ctx), dA(ctx), dB(ctx), RA(ctx);
     {
         StageTimer tm(ctx, ST_H2D);
-        TCI_CUDA(ctx, dR.upload(R, (size_t)(chi * Da * Db)));
-        TCI_CUDA(ctx, dA.upload(A, (size_t)(Da * s1 * s2 * Dan)));
-        TCI_CUDA(ctx, dB.upload(B, (size_t)(Db * s2 * s3 * Dbn)));
+        TCI_CUDA(ctx, dR.upload(R, (size_t)(W * chi * Da * Db)));
+        TCI_CUDA(ctx, dA.upload(A, (size_t)(W * Da * s1 * s2 * Dan)));
+        TCI_CUDA(ctx, dB.upload(B, (size_t)(W * Db * s2 * s3 * Dbn)));
     }
     tci_dmat *C = nullptr;
-    int rc = dmat_alloc(ctx, chi * s1 * s3, Dan * Dbn, &C);
+    int rc = dmat_alloc(ctx, W * chi * s1 * s3, Dan * Dbn, &C);
     if (rc) return rc;
     {
         StageTimer tm(ctx, ST_GEMM);
+        const V *pR = (const V *)dR.p, *pA = (const V *)dA.p, *pB = (const V *)dB.p;
+        V *pC = (V *)C->p;
+        const i64 ldC = C->ld / W;
         // RA2[(c + chi*x) + chi*s1*((b + Db*h) + Db*s2*an)] = sum_a R[c, a, b] * A[a, x, h, an]   :458
-        TCI_CUDA(ctx, RA.alloc((size_t)(chi * s1 * Db * s2 * Dan)));
+        TCI_CUDA(ctx, RA.alloc((size_t)(W * chi * s1 * Db * s2 * Dan)));
+        V *pRA = (V *)RA.p;
         for (i64 h = 0; h < s2 && !rc; ++h)
             for (i64 x = 0; x < s1 && !rc; ++x)
-                rc = dgemm_dev_batched(ctx, false, false, chi, Dan, Da, 1.0, dR.p, chi, chi * Da,
-                                       dA.p + Da * (x + s1 * h), Da * s1 * s2, 0, 0.0,
-                                       RA.p + chi * x + chi * s1 * Db * h, chi * s1 * Db * s2, chi * s1, Db);
+                rc = gemm_off(ctx, false, false, chi, Dan, Da, 1.0, pR, chi, chi * Da, pA + Da * (x + s1 * h), Da * s1 * s2, 0,
+                              0.0, pRA + chi * x + chi * s1 * Db * h, chi * s1 * Db * s2, chi * s1, Db, nullptr, nullptr, false);
         // C[(c + chi*(x + s1*z)) + chi*s1*s3*(an + Dan*bn)] = sum_{b,h} RA2[(c,x),(b,h),an] * B[b, h, z, bn]  :464
         for (i64 z = 0; z < s3 && !rc; ++z)
-            rc = dgemm_dev_batched(ctx, false, false, chi * s1, Dbn, Db * s2, 1.0, RA.p, chi * s1, chi * s1 * Db * s2,
-                                   dB.p + Db * s2 * z, Db * s2 * s3, 0, 0.0, C->p + chi * s1 * z, C->ld * Dan,
-                                   C->ld, Dan);
+            rc = gemm_off(ctx, false, false, chi * s1, Dbn, Db * s2, 1.0, pRA, chi * s1, chi * s1 * Db * s2, pB + Db * s2 * z,
+                          Db * s2 * s3, 0, 0.0, pC + chi * s1 * z, ldC * Dan, ldC, Dan, nullptr, nullptr, false);
     }
     if (rc) {
         tci_dmat_destroy(C);
@@ -549,9 +553,36 @@ extern "C" int tci_contract_zipup_site(tci_ctx *ctx, const double *R, int64_t ch
     return TCI_OK;
 }
 
+extern "C" int tci_contract_zipup_site(tci_ctx *ctx, const double *R, int64_t chi, int64_t Da, int64_t Db,
+                                       const double *A, int64_t s1, int64_t s2, int64_t Dan, const double *B,
+                                       int64_t s3, int64_t Dbn, double *C_host, tci_dmat **C_dev)
+{
+    TCI_ENTER(ctx);
+    return zipup_site_t<double>(ctx, R, chi, Da, Db, A, s1, s2, Dan, B, s3, Dbn, C_host, C_dev);
+}
+extern "C" int tci_zcontract_zipup_site(tci_ctx *ctx, const double *R, int64_t chi, int64_t Da, int64_t Db,
+                                        const double *A, int64_t s1, int64_t s2, int64_t Dan, const double *B,
+                                        int64_t s3, int64_t Dbn, double *C_host, tci_dmat **C_dev)
+{
+    TCI_ENTER(ctx);
+    return zipup_site_t<double2>(ctx, R, chi, Da, Db, A, s1, s2, Dan, B, s3, Dbn, C_host, C_dev);
+}
+
+__device__ __forceinline__ double v_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ double2 v_fma(double2 a, double2 b, double2 c)
+{ // c + a*b, complex (BLAS-level arithmetic: the reference's _contract is a zgemm)
+    c.x = fma(a.x, b.x, fma(-a.y, b.y, c.x));
+    c.y = fma(a.x, b.y, fma(a.y, b.x, c.y));
+    return c;
+}
+template <class V> __device__ __forceinline__ V v_zero();
+template <> __device__ __forceinline__ double v_zero<double>() { return 0.0; }
+template <> __device__ __forceinline__ double2 v_zero<double2>() { return make_double2(0.0, 0.0); }
+
 // out[(la + Da*lb), x, z, (lan + Dan*lbn)] = sum_h A[la, x, h, lan] * B[lb, h, z, lbn]   contraction.jl:338-349
-__global__ void k_naive_site(const double *__restrict__ A, const double *__restrict__ B, i64 Da, i64 s1, i64 s2,
-                             i64 Dan, i64 Db, i64 s3, i64 Dbn, double *__restrict__ out)
+template <class V>
+__global__ void k_naive_site(const V *__restrict__ A, const V *__restrict__ B, i64 Da, i64 s1, i64 s2, i64 Dan, i64 Db, i64 s3,
+                             i64 Dbn, V *__restrict__ out)
 {
     i64 total = Da * Db * s1 * s3 * Dan * Dbn;
     for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
@@ -565,28 +596,42 @@ __global__ void k_naive_site(const double *__restrict__ A, const double *__restr
         i64 z = rem % s3;
         rem /= s3;
         i64 lan = rem % Dan, lbn = rem / Dan;
-        double acc = 0.0;
+        V acc = v_zero<V>();
         for (i64 h = 0; h < s2; ++h)
-            acc = fma(A[la + Da * (x + s1 * (h + s2 * lan))], B[lb + Db * (h + s2 * (z + s3 * lbn))], acc);
+            acc = v_fma(A[la + Da * (x + s1 * (h + s2 * lan))], B[lb + Db * (h + s2 * (z + s3 * lbn))], acc);
         out[e] = acc;
     }
+}
+
+template <class V>
+static int naive_site_t(tci_ctx *ctx, const double *A, i64 Da, i64 s1, i64 s2, i64 Dan, const double *B, i64 Db, i64 s3,
+                        i64 Dbn, double *out_host)
+{
+    constexpr i64 W = sizeof(V) / sizeof(double);
+    if (!A || !B || !out_host) return tci_fail(ctx, TCI_ERR_ARG, "tci_contract_naive_site: bad arguments");
+    const i64 total = Da * Db * s1 * s3 * Dan * Dbn;
+    DevBuf<double> dA(ctx), dB(ctx), dO(ctx);
+    TCI_CUDA(ctx, dA.upload(A, (size_t)(W * Da * s1 * s2 * Dan)));
+    TCI_CUDA(ctx, dB.upload(B, (size_t)(W * Db * s2 * s3 * Dbn)));
+    TCI_CUDA(ctx, dO.alloc((size_t)(W * total)));
+    unsigned blocks = (unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16);
+    k_naive_site<V><<<blocks, 256, 0, ctx->stream>>>((const V *)dA.p, (const V *)dB.p, Da, s1, s2, Dan, Db, s3, Dbn, (V *)dO.p);
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    TCI_CUDA(ctx, cudaMemcpyAsync(out_host, dO.p, W * total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TCI_OK;
 }
 
 extern "C" int tci_contract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s1, int64_t s2, int64_t Dan,
                                        const double *B, int64_t Db, int64_t s3, int64_t Dbn, double *out_host)
 {
     TCI_ENTER(ctx);
-    if (!A || !B || !out_host) return tci_fail(ctx, TCI_ERR_ARG, "tci_contract_naive_site: bad arguments");
-    const i64 total = Da * Db * s1 * s3 * Dan * Dbn;
-    DevBuf<double> dA(ctx), dB(ctx), dO(ctx);
-    TCI_CUDA(ctx, dA.upload(A, (size_t)(Da * s1 * s2 * Dan)));
-    TCI_CUDA(ctx, dB.upload(B, (size_t)(Db * s2 * s3 * Dbn)));
-    TCI_CUDA(ctx, dO.alloc((size_t)total));
-    unsigned blocks = (unsigned)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16);
-    k_naive_site<<<blocks, 256, 0, ctx->stream>>>(dA.p, dB.p, Da, s1, s2, Dan, Db, s3, Dbn, dO.p);
-    ctx->launches++;
-    TCI_CUDA(ctx, cudaGetLastError());
-    TCI_CUDA(ctx, cudaMemcpyAsync(out_host, dO.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    TCI_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return TCI_OK;
+    return naive_site_t<double>(ctx, A, Da, s1, s2, Dan, B, Db, s3, Dbn, out_host);
+}
+extern "C" int tci_zcontract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s1, int64_t s2, int64_t Dan,
+                                        const double *B, int64_t Db, int64_t s3, int64_t Dbn, double *out_host)
+{
+    TCI_ENTER(ctx);
+    return naive_site_t<double2>(ctx, A, Da, s1, s2, Dan, B, Db, s3, Dbn, out_host);
 }

@@ -311,3 +311,48 @@ def test_complex_crossinterpolate2_of_tt_target(T):
     for c in cores:
         dense = np.einsum("rb,bxd->rxd", dense, c).reshape((-1, c.shape[2]))
     assert T.tci_sum(tci) == pytest.approx(np.sum(dense), rel=1e-9)
+
+
+@pytest.mark.gpu
+def test_complex_mpo_mpo_contraction_naive_and_zipup(T):
+    """"MPO-MPO contraction" for algorithm = :naive (test_contraction.jl:68-99) and "MPO-MPO contraction (zipup)" for
+    method in [:SVD, :LU] (:185-189) on ComplexF64 data: site contractions, factorisations and recompression products all
+    on the complex kernels; `f` with :naive raises as in the reference."""
+    rng = np.random.default_rng(41)
+    a, b = _tto_tto(rng)
+    ma, mb = _dense_product(a, b)
+    ref = ma @ mb
+    ab = T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="naive")
+    assert T.sitedims(ab) == [[2, 2]] * 4 and ab.sitetensors[0].dtype == np.complex128
+    np.testing.assert_allclose(_dense_product(ab.sitetensors, ab.sitetensors)[0], ref, rtol=1e-10, atol=1e-12 * np.max(np.abs(ref)))
+    ab = T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="naive", tolerance=1e-12)  # + compress(:SVD)
+    np.testing.assert_allclose(_dense_product(ab.sitetensors, ab.sitetensors)[0], ref, rtol=1e-8, atol=1e-9 * np.max(np.abs(ref)))
+    with pytest.raises(RuntimeError, match="Naive contraction implementation cannot contract"):
+        T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="naive", f=("affine", 2.0, 0.0))
+    for method in ("SVD", "LU"):
+        ab = T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="zipup", method=method)
+        np.testing.assert_allclose(_dense_product(ab.sitetensors, ab.sitetensors)[0], ref, rtol=1e-8,
+                                   atol=1e-9 * np.max(np.abs(ref)))
+    tt = T.TensorTrain([c.copy() for c in T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="naive").sitetensors])
+    T.compress(tt, "LU", tolerance=1e-12)  # compress! (:LU) on complex cores: complex rrLU + complex GEMM
+    np.testing.assert_allclose(_dense_product(tt.sitetensors, tt.sitetensors)[0], ref, rtol=1e-8, atol=1e-9 * np.max(np.abs(ref)))
+
+
+@pytest.mark.gpu
+def test_complex_mpo_mps_contraction_zipup(T):
+    """"MPO-MPS contraction (zipup)" (test_contraction.jl:191-195), ComplexF64."""
+    rng = np.random.default_rng(43)
+    bonds = [1, 2, 3, 2, 1]
+    a = [np.asfortranarray(crand(rng, bonds[n], 3, 3, bonds[n + 1])) for n in range(4)]
+    b = [np.asfortranarray(crand(rng, bonds[n], 3, bonds[n + 1])) for n in range(4)]
+    ma, _ = _dense_product(a, a)
+    vb = np.ones((1, 1), dtype=np.complex128)
+    for c in b:
+        vb = np.einsum("rb,bxd->rxd", vb, c).reshape((-1, c.shape[2]))
+    ref = ma @ vb[:, 0]
+    for method in ("SVD", "LU"):
+        ab = T.contract(T.TensorTrain(a), T.TensorTrain(b), algorithm="zipup", method=method)
+        v = np.ones((1, 1), dtype=np.complex128)
+        for c in ab.sitetensors:
+            v = np.einsum("rb,bxd->rxd", v, c).reshape((-1, c.shape[2]))
+        np.testing.assert_allclose(v[:, 0], ref, rtol=1e-8, atol=1e-9 * np.max(np.abs(ref)))
