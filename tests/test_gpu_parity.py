@@ -267,7 +267,7 @@ LAZY_SHAPES = [(2, 3, 2), (17, 33, 9), (64, 64, 20), (100, 37, 30), (130, 257, 4
 
 @pytest.mark.parametrize("m,n,r", LAZY_SHAPES)
 def test_rrlu_deferred_update_kernel(T, oracle, m, n, r, monkeypatch):
-    """rrlu_lazy.cu (Schur updates deferred, committed every 4 pivots; normally used from ~6000^2 up) forced at
+    """rrlu_lazy.cu (Schur updates deferred, committed every 4 pivots; normally used from m*n >= 13e6, about 3600^2, up) forced at
     small sizes: block boundaries, ranks that are not multiples of the block, row swaps inside a block."""
     monkeypatch.setenv("TCI_RRLU_NO_RES", "1")
     monkeypatch.setenv("TCI_RRLU_LAZY_MIN", "0")
