@@ -207,6 +207,22 @@ int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t n
                     int64_t nr, int64_t nJ, int64_t maxrank, double reltol, double abstol, int leftorthogonal,
                     int exact_mode, int64_t *rowperm, int64_t *colperm, int64_t *npivot, double *error,
                     double *pivoterrors, double *maxabs, tci_lu **factors);
+/* The bond loop of one half-sweep of sweep2site! (tensorci2.jl:866-907): updatepivots! (:510-607, `:full` search) for
+ * b = 1 .. n-1 (forward != 0, leftorthogonal factorisations) or n-1 .. 1 (backward) in ONE call.  Per bond:
+ * Icombined = union(kronecker(Iset[b], d_b), extraI[b+1]), Jcombined = union(kronecker(d_{b+1}, Jset[b+1]), extraJ[b])
+ * (:526-527; extra sets nullable = strictlynested), Pi-evaluation -> rrLU with maxrank = maxbonddim (<= 0: none),
+ * Iset[b+1] / Jset[b] replaced by the selected rows / columns (:597-598), updateerrors (:161-169).  Index sets are
+ * ragged arrays: Iset[b] is (b x nI[b]), Jset[b] is ((n-1-b) x nJ[b]), multi-index contiguous, b = 0 .. n-1 (0-based).
+ * The call returns the new set sizes and the length of the pivot-error vector; tci_sweep2site_fetch then copies the
+ * sets into caller-allocated arrays of those sizes, with bonderrors (n-1), pivoterrors, max|Pi| over the bonds
+ * (updatemaxsample!, :538) and, per bond in the order visited, (bond, rows, columns, npivot) (4 (n-1) values).      */
+int tci_sweep2site_half(tci_ctx *ctx, int64_t target_id, int forward, const int64_t *const *Iset, const int64_t *nI,
+                        const int64_t *const *Jset, const int64_t *nJ, const int64_t *const *extraI,
+                        const int64_t *nextraI, const int64_t *const *extraJ, const int64_t *nextraJ, double reltol,
+                        double abstol, int64_t maxbonddim, int exact_mode, int64_t *nI_out, int64_t *nJ_out,
+                        int64_t *npivoterrors);
+int tci_sweep2site_fetch(tci_ctx *ctx, int64_t *const *Iout, int64_t *const *Jout, double *bonderrors,
+                         double *pivoterrors, double *maxsample, int64_t *trace /* nullable */);
 /* fillsitetensors! (globalsearch.jl:97-103) = setsitetensor!(tci, f, b) for every site (tensorci2.jl:367-394):
  * T_b = Pi1_b P_b^-1 with Pi1_b = f(Iset[b] x sigma_b x Jset[b]) and P_b = f(Iset[b+1] x Jset[b]); the last tensor is
  * Pi1 itself.  All evaluations, full-rank factorisations and solves are queued back to back and synchronised once.

@@ -72,6 +72,9 @@ SYMBOLS = {
     "tci_globalsearch_select": (C.c_int, [P_f64, P_i64, i64, P_i64, i64, P_i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),
     "tci_bond_update": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64,
                                   P_i64, P_i64, P_f64, P_f64, P_f64, C.POINTER(VP)]),
+    "tci_sweep2site_half": (C.c_int, [VP, i64, C.c_int, C.POINTER(P_i64), P_i64, C.POINTER(P_i64), P_i64, C.POINTER(P_i64),
+                                      P_i64, C.POINTER(P_i64), P_i64, f64, f64, i64, C.c_int, P_i64, P_i64, P_i64]),
+    "tci_sweep2site_fetch": (C.c_int, [VP, C.POINTER(P_i64), C.POINTER(P_i64), P_f64, P_f64, P_f64, P_i64]),
     "tci_fill_sitetensors": (C.c_int, [VP, i64, i64, C.POINTER(P_i64), P_i64, C.POINTER(P_i64), P_i64, PP_f64, P_f64,
                                        P_i64]),
     "tci_tt_evaluate": (C.c_int, [VP, i64, P_i64, PP_f64, P_i64, i64, P_f64]),

@@ -132,6 +132,47 @@ class BatchEvaluator:
         return rrLU(self.ctx, h if want_factors else None, rowperm, colperm, r, err.value, pe[: r + 1].copy(),
                     bool(leftorthogonal), (m, n)), mx.value
 
+    def sweep2site_half(self, Isets, Jsets, extraI, extraJ, forward, reltol=1e-14, abstol=0.0, maxbonddim=None,
+                        exact=True):
+        """The bond loop of one half-sweep of sweep2site! (tensorci2.jl:866-907) in one library call
+        (tci_sweep2site_half + tci_sweep2site_fetch).  Returns (Isets, Jsets, bonderrors, pivoterrors, max|Pi|, trace)."""
+        n = len(self.localdims)
+        Is = [as_indexset(s, b) for b, s in enumerate(Isets)]
+        Js = [as_indexset(s, n - 1 - b) for b, s in enumerate(Jsets)]
+        nI = np.array([len(s) for s in Is], dtype=np.int64)
+        nJ = np.array([len(s) for s in Js], dtype=np.int64)
+        Ip = (_lib.P_i64 * n)(*[pi(s) for s in Is])
+        Jp = (_lib.P_i64 * n)(*[pi(s) for s in Js])
+        if extraI is not None:
+            eI = [as_indexset(s, b) for b, s in enumerate(extraI)]
+            eJ = [as_indexset(s, n - 1 - b) for b, s in enumerate(extraJ)]
+            neI = np.array([len(s) for s in eI], dtype=np.int64)
+            neJ = np.array([len(s) for s in eJ], dtype=np.int64)
+            eIp = (_lib.P_i64 * n)(*[pi(s) for s in eI])
+            eJp = (_lib.P_i64 * n)(*[pi(s) for s in eJ])
+            extra = (eIp, pi(neI), eJp, pi(neJ))
+        else:
+            extra = (None, None, None, None)
+        nIo = np.zeros(n, dtype=np.int64)
+        nJo = np.zeros(n, dtype=np.int64)
+        npe = C.c_int64(0)
+        mb = 0 if maxbonddim is None or maxbonddim >= 2**62 else int(maxbonddim)
+        rc = lib().tci_sweep2site_half(self.ctx.h, self.id, int(bool(forward)), Ip, pi(nI), Jp, pi(nJ), *extra, float(reltol),
+                                       float(abstol), mb, int(bool(exact)), pi(nIo), pi(nJo), C.byref(npe))
+        self.ctx.check(rc)
+        Io = [np.zeros((int(nIo[b]), b), dtype=np.int64) for b in range(n)]
+        Jo = [np.zeros((int(nJo[b]), n - 1 - b), dtype=np.int64) for b in range(n)]
+        Iop = (_lib.P_i64 * n)(*[pi(s) for s in Io])
+        Jop = (_lib.P_i64 * n)(*[pi(s) for s in Jo])
+        be = np.zeros(max(n - 1, 0), dtype=np.float64)
+        pe = np.zeros(npe.value, dtype=np.float64)
+        mx = C.c_double(0.0)
+        trace = np.zeros(4 * max(n - 1, 0), dtype=np.int64)
+        self.ctx.check(lib().tci_sweep2site_fetch(self.ctx.h, Iop, Jop, pf(be), pf(pe), C.byref(mx), pi(trace)))
+        tr = trace.reshape(-1, 4)
+        self.nevals += int(np.sum(tr[:, 1] * tr[:, 2]))
+        return Io, Jo, be, pe, mx.value, [tuple(int(v) for v in row) for row in tr]
+
     def fill_sitetensors(self, Isets, Jsets, want_handle=True, want_host=True):
         """fillsitetensors! (globalsearch.jl:97-103) for all sites in one library call (tci_fill_sitetensors).
         Returns (list of T_b as (nI_b, d_b, nJ_b) arrays, max over |Pi1|, device-resident TT handle or None).

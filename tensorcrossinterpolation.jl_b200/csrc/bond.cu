@@ -9,6 +9,7 @@
 //                     `current_tt` the global pivot finder probes, globalpivotfinder.jl:160-183).
 #include <cmath>
 #include <cstring>
+#include <unordered_set>
 
 #include "tci_internal.h"
 
@@ -236,5 +237,174 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
         *tt_id = id;
         return target_replicate(ctx, id);
     }
+    return TCI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tci_sweep2site_half: the bond loop of one half-sweep of sweep2site! (tensorci2.jl:866-907) -- updatepivots!
+// (:510-607, `:full` search) for b = 1 .. n-1 (forward) or n-1 .. 1 (backward) -- in ONE call.  Between two bonds the
+// reference only does index bookkeeping (kronecker, union with the history sets, the rows / columns the rrLU picked),
+// which here runs in C++ next to the launches instead of in the caller's interpreter; every bond is still one
+// evaluation -> rrLU -> synchronisation, because the next bond's index sets are this bond's pivots.
+struct SweepResult {
+    std::vector<std::vector<i64>> I, J; // flattened (len x count)
+    std::vector<i64> nI, nJ;
+    std::vector<double> bonderrors, pivoterrors;
+    std::vector<i64> trace; // per bond: bond (1-based), rows, columns, npivot
+    double maxsample = 0.0;
+};
+static std::map<tci_ctx *, SweepResult> g_sweeps;
+static std::mutex g_sweeps_mu;
+
+static void kron_left(const std::vector<i64> &S, i64 len, i64 cnt, i64 d, std::vector<i64> &out) // kronecker(Iset, d) :315-320
+{
+    out.resize((size_t)((len + 1) * cnt * d));
+    for (i64 s = 0; s < d; ++s)
+        for (i64 i = 0; i < cnt; ++i) {
+            i64 *o = out.data() + (len + 1) * (i + cnt * s);
+            for (i64 k = 0; k < len; ++k) o[k] = S[(size_t)(len * i + k)];
+            o[len] = s + 1;
+        }
+}
+static void kron_right(i64 d, const std::vector<i64> &S, i64 len, i64 cnt, std::vector<i64> &out) // kronecker(d, Jset) :322-327
+{
+    out.resize((size_t)((len + 1) * cnt * d));
+    for (i64 j = 0; j < cnt; ++j)
+        for (i64 s = 0; s < d; ++s) {
+            i64 *o = out.data() + (len + 1) * (s + d * j);
+            o[0] = s + 1;
+            for (i64 k = 0; k < len; ++k) o[1 + k] = S[(size_t)(len * j + k)];
+        }
+}
+// Base.union(a, b) on vectors of multi-indices of length len: order preserving, duplicates dropped (:526-527)
+static void union_into(std::vector<i64> &a, i64 len, const i64 *b, i64 nb)
+{
+    if (nb == 0 || len == 0) return;
+    const i64 na = (i64)a.size() / len;
+    a.reserve((size_t)((na + nb) * len)); // rows are referenced by pointer below: no reallocation while inserting
+    struct Hash {
+        i64 len;
+        size_t operator()(const i64 *p) const
+        {
+            unsigned long long h = 0x9e3779b97f4a7c15ull;
+            for (i64 k = 0; k < len; ++k) {
+                h ^= (unsigned long long)p[k] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+                h *= 0xbf58476d1ce4e5b9ull;
+            }
+            return (size_t)(h ^ (h >> 31));
+        }
+    };
+    struct Eq {
+        i64 len;
+        bool operator()(const i64 *x, const i64 *y) const { return std::memcmp(x, y, (size_t)len * sizeof(i64)) == 0; }
+    };
+    std::unordered_set<const i64 *, Hash, Eq> seen((size_t)(2 * (na + nb)), Hash{len}, Eq{len});
+    for (i64 i = 0; i < na; ++i) seen.insert(a.data() + len * i);
+    for (i64 i = 0; i < nb; ++i) {
+        const i64 *row = b + len * i;
+        if (seen.find(row) != seen.end()) continue;
+        a.insert(a.end(), row, row + len);
+        seen.insert(a.data() + a.size() - len);
+    }
+}
+
+extern "C" int tci_sweep2site_half(tci_ctx *ctx, int64_t target_id, int forward, const int64_t *const *Iset,
+                                   const int64_t *nI, const int64_t *const *Jset, const int64_t *nJ,
+                                   const int64_t *const *extraI, const int64_t *nextraI, const int64_t *const *extraJ,
+                                   const int64_t *nextraJ, double reltol, double abstol, int64_t maxbonddim, int exact_mode,
+                                   int64_t *nI_out, int64_t *nJ_out, int64_t *npivoterrors)
+{
+    if (!ctx) return TCI_ERR_ARG;
+    i64 n = 0;
+    std::vector<i64> localdims;
+    {
+        TCI_ENTER(ctx);
+        auto it = ctx->targets.find(target_id);
+        if (it == ctx->targets.end()) return tci_fail(ctx, TCI_ERR_ARG, "unknown target id");
+        if (it->second->is_complex) return tci_fail(ctx, TCI_ERR_ARG, "ComplexF64 target: use the tci_z* entry points");
+        if (!Iset || !Jset || !nI || !nJ || !nI_out || !nJ_out) return tci_fail(ctx, TCI_ERR_ARG, "tci_sweep2site_half: bad arguments");
+        n = it->second->nsites;
+        localdims = it->second->localdims;
+    }
+    SweepResult res;
+    res.I.resize((size_t)n);
+    res.J.resize((size_t)n);
+    for (i64 b = 0; b < n; ++b) {
+        res.I[b].assign(Iset[b], Iset[b] + b * nI[b]);
+        res.J[b].assign(Jset[b], Jset[b] + (n - 1 - b) * nJ[b]);
+    }
+    res.nI.assign(nI, nI + n);
+    res.nJ.assign(nJ, nJ + n);
+    res.bonderrors.assign((size_t)std::max<i64>(n - 1, 0), 0.0);
+    std::vector<i64> Ic, Jc, rowperm, colperm;
+    std::vector<double> pe;
+    const i64 maxrank = maxbonddim <= 0 ? 0 : maxbonddim;
+    for (i64 step = 0; step + 1 < n; ++step) {
+        const i64 b = forward ? step : n - 2 - step;
+        kron_left(res.I[b], b, res.nI[b], localdims[b], Ic);                       // Icombined, :526
+        kron_right(localdims[b + 1], res.J[b + 1], n - 2 - b, res.nJ[b + 1], Jc); // Jcombined, :527
+        if (extraI && nextraI && extraI[b + 1]) union_into(Ic, b + 1, extraI[b + 1], nextraI[b + 1]);
+        if (extraJ && nextraJ && extraJ[b]) union_into(Jc, n - 1 - b, extraJ[b], nextraJ[b]);
+        const i64 m = (i64)Ic.size() / (b + 1), k = (i64)Jc.size() / (n - 1 - b);
+        rowperm.resize((size_t)std::max<i64>(m, 1));
+        colperm.resize((size_t)std::max<i64>(k, 1));
+        pe.assign((size_t)(std::min(m, k) + 1), 0.0);
+        i64 np = 0;
+        double err = 0.0, mx = 0.0;
+        int rc = tci_bond_update(ctx, target_id, Ic.data(), b + 1, m, Jc.data(), n - 1 - b, k, maxrank, reltol, abstol,
+                                 forward ? 1 : 0, exact_mode, rowperm.data(), colperm.data(), &np, &err, pe.data(), &mx,
+                                 nullptr);
+        if (rc) return rc;
+        res.maxsample = (std::isnan(res.maxsample) || std::isnan(mx)) ? NAN : std::max(res.maxsample, mx); // :538
+        std::vector<i64> &In = res.I[b + 1], &Jn = res.J[b];
+        In.resize((size_t)((b + 1) * np)); // Iset[b+1] = Icombined[rowindices], Jset[b] = Jcombined[colindices]  :597-598
+        for (i64 q = 0; q < np; ++q)
+            std::copy(Ic.begin() + (b + 1) * (rowperm[q] - 1), Ic.begin() + (b + 1) * rowperm[q], In.begin() + (b + 1) * q);
+        Jn.resize((size_t)((n - 1 - b) * np));
+        for (i64 q = 0; q < np; ++q)
+            std::copy(Jc.begin() + (n - 1 - b) * (colperm[q] - 1), Jc.begin() + (n - 1 - b) * colperm[q],
+                      Jn.begin() + (n - 1 - b) * q);
+        res.nI[b + 1] = np;
+        res.nJ[b] = np;
+        // updateerrors (:161-169): bonderrors[b] = last pivot error; pivoterrors = elementwise max with zero padding
+        res.bonderrors[b] = pe[np];
+        if ((i64)res.pivoterrors.size() < np + 1) res.pivoterrors.resize((size_t)(np + 1), 0.0);
+        for (i64 q = 0; q <= np; ++q) {
+            double &a = res.pivoterrors[q];
+            a = (std::isnan(a) || std::isnan(pe[q])) ? NAN : std::max(a, pe[q]);
+        }
+        res.trace.insert(res.trace.end(), {b + 1, m, k, np});
+    }
+    for (i64 b = 0; b < n; ++b) {
+        nI_out[b] = res.nI[b];
+        nJ_out[b] = res.nJ[b];
+    }
+    if (npivoterrors) *npivoterrors = (i64)res.pivoterrors.size();
+    std::lock_guard<std::mutex> lk(g_sweeps_mu);
+    g_sweeps[ctx] = std::move(res);
+    return TCI_OK;
+}
+
+// The results of the last tci_sweep2site_half on this context: index sets (Iout[b]: b x nI_out[b], Jout[b]:
+// (n-1-b) x nJ_out[b]; nullable entries are skipped), bonderrors (n-1), pivoterrors (npivoterrors), max |Pi| over the
+// bonds, and per bond (bond, rows, columns, npivot) in the order visited (trace: 4 (n-1), nullable).
+extern "C" int tci_sweep2site_fetch(tci_ctx *ctx, int64_t *const *Iout, int64_t *const *Jout, double *bonderrors,
+                                    double *pivoterrors, double *maxsample, int64_t *trace)
+{
+    if (!ctx) return TCI_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_sweeps_mu);
+    auto it = g_sweeps.find(ctx);
+    if (it == g_sweeps.end()) return tci_fail(ctx, TCI_ERR_ARG, "tci_sweep2site_fetch: no sweep result on this context");
+    const SweepResult &r = it->second;
+    const size_t n = r.I.size();
+    for (size_t b = 0; b < n; ++b) {
+        if (Iout && Iout[b]) std::copy(r.I[b].begin(), r.I[b].end(), Iout[b]);
+        if (Jout && Jout[b]) std::copy(r.J[b].begin(), r.J[b].end(), Jout[b]);
+    }
+    if (bonderrors) std::copy(r.bonderrors.begin(), r.bonderrors.end(), bonderrors);
+    if (pivoterrors) std::copy(r.pivoterrors.begin(), r.pivoterrors.end(), pivoterrors);
+    if (maxsample) *maxsample = r.maxsample;
+    if (trace) std::copy(r.trace.begin(), r.trace.end(), trace);
+    g_sweeps.erase(it);
     return TCI_OK;
 }

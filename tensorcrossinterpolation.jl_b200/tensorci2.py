@@ -502,6 +502,21 @@ def sweep2site(tci, f, niter, iter1=1, abstol=1e-8, maxbonddim=I64MAX, sweepstra
             tci.Jset_history = tci.Jset_history[-2:]
         flushpivoterror(tci)
         fwd = forwardsweep(sweepstrategy, it)
+        if (pivotsearch == "full" and verbosity <= 2 and type(f).sweep2site_half is BatchEvaluator.sweep2site_half
+                and not getattr(f, "is_complex", False) and not getattr(tci, "per_bond_calls", False)):
+            # the bond loop of this half-sweep in ONE library call (tci_sweep2site_half): the same updatepivots!
+            # sequence, with the index bookkeeping between two bonds done next to the launches
+            tci.sitetensors = [np.zeros((0, 0, 0), order="F") for _ in range(n)]
+            tci.device_tt = None
+            Io, Jo, be, pe, mx, tr = f.sweep2site_half(tci.Iset, tci.Jset, extraI, extraJ, fwd, abstol=abstol,
+                                                       maxbonddim=maxbonddim)
+            tci.Iset, tci.Jset = Io, Jo
+            updatemaxsample(tci, mx)
+            tci.bonderrors[:] = be  # every bond is visited: updatebonderror for b = 1 .. n-1
+            updatepivoterror(tci, pe)
+            if hasattr(tci, "trace"):
+                tci.trace.extend(tr)
+            continue
         for b in (range(n - 1) if fwd else range(n - 2, -1, -1)):
             updatepivots(tci, b, f, fwd, abstol=abstol, maxbonddim=maxbonddim,
                          sweepdirection="forward" if fwd else "backward", pivotsearch=pivotsearch,

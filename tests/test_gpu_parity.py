@@ -1670,3 +1670,26 @@ def test_context_reports_launches_and_timers(T, ctx):
     assert ctx.launches > l0
     tm = ctx.timers()
     assert set(tm) >= {"pi_eval", "rrlu", "luci", "rrlu_kernel"} and tm["rrlu_kernel"] > 0.0
+
+
+@pytest.mark.parametrize("strictlynested", [False, True])
+def test_sweep2site_half_fused_equals_per_bond(T, strictlynested):
+    """tci_sweep2site_half (the bond loop of a half-sweep in one library call) against the same loop made of
+    tci_bond_update calls from the host mirror's updatepivots: identical index sets, bond / pivot errors,
+    maxsamplevalue and ranks after every optimize iteration (tensorci2.jl:855-916)."""
+    ld = [6, 5, 7, 4, 6, 5]
+    runs = []
+    for per_bond in (False, True):
+        f = T.BuiltinTarget(LORENTZ, [0.7], ld)
+        tci = T.TensorCI2(f, ld, [[1] * 6, [3, 2, 5, 1, 4, 2]])
+        tci.per_bond_calls = per_bond
+        tci.trace = []
+        ranks, errors = T.optimize(tci, f, tolerance=1e-9, maxiter=4, strictlynested=strictlynested, rng=T.CounterRNG(4))
+        runs.append((tci, ranks, errors))
+    (a, ra, ea), (b, rb, eb) = runs
+    assert ra == rb and ea == eb and a.maxsamplevalue == b.maxsamplevalue
+    assert np.array_equal(a.bonderrors, b.bonderrors) and np.array_equal(a.pivoterrors, b.pivoterrors)
+    assert a.trace == b.trace
+    for s in range(len(ld)):
+        assert np.array_equal(a.Iset[s], b.Iset[s]) and np.array_equal(a.Jset[s], b.Jset[s])
+        assert np.array_equal(a.sitetensors[s], b.sitetensors[s])
