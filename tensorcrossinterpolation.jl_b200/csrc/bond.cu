@@ -7,6 +7,7 @@
 //                     Pi1, P, the full-rank factorisation of P and the solve T = Pi1 P^-1 of every site are queued back
 //                     to back, one synchronisation at the end; the cores can stay on the device as a TT target (the
 //                     `current_tt` the global pivot finder probes, globalpivotfinder.jl:160-183).
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <unordered_set>
@@ -42,6 +43,9 @@ extern "C" int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I
     if ((nl > 0 && !I) || (nr > 0 && !J)) return tci_fail(ctx, TCI_ERR_ARG, "index sets missing");
     unsigned long long *dmax = ctx_words(ctx);
     if (!dmax) return tci_fail(ctx, TCI_ERR_CUDA, "scratch words");
+    static const bool bdbg = getenv("TCI_BOND_DEBUG") != nullptr; // host-side timeline of the call on stderr
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = bdbg ? now() : 0.0;
     tci_dmat *Pi = nullptr;
     int rc = dmat_alloc(ctx, nI, nJ, &Pi);
     if (rc) return rc;
@@ -53,10 +57,14 @@ extern "C" int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I
     rc = pi_enqueue_auto(ctx, target_id, I, nl, nI, J, nr, nJ, 0, Pi, dmax, nullptr);
     ctx->nosync = saved;
     cudaEventRecord(e1, ctx->stream);
+    const double t1 = bdbg ? now() : 0.0;
     unsigned long long bits = 0;
     if (!rc)
         rc = rrlu_core(ctx, Pi, nI, nJ, maxrank, reltol, abstol, leftorthogonal, exact_mode, rowperm, colperm, npivot,
                        error, pivoterrors, factors, dmax, &bits, sizeof(bits), nullptr);
+    if (bdbg)
+        fprintf(stderr, "[bond dbg] %lld x %lld r=%lld: Pi enqueue %.1f us | rrLU launch + sync + results %.1f us\n", (long long)nI,
+                (long long)nJ, (long long)*npivot, t1 - t0, now() - t1);
     float ms = 0.f;
     if (!rc && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ctx->stage_ms[ST_PI] += ms;
     if (maxabs) memcpy(maxabs, &bits, sizeof(double));
