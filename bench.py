@@ -143,14 +143,25 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi's start-up (it touches every GPU of the box) must be over before anything is timed."""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """Only samples taken from now on (the timed region) are reported."""
+        self.first = len(self.rows)
+
     def finish(self):
         self.stop_flag = True
         if self.proc:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 6:
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
                     if v.lower().startswith("active"):
@@ -635,16 +646,24 @@ def main():
         fm = T.Contraction(T.TensorTrain(mpo_cores(5)), T.TensorTrain(mpo_cores(6)), ctx=ctx)
         I, J = index_sets(NL)
         flops = pi_flops(I, J)
-        for _ in range(W):
+        sampler = ClockSampler(local)  # started before the warm-up: nvidia-smi's own start-up stays out of the timing
+        sampler.start()
+        sampler.wait_first()
+        last = None
+        for w in range(W + 6):  # W warm-up steps, then (at most 6 more) until two consecutive steps agree within 5 %
+            t0 = time.perf_counter()
             dev, mx = fm.batchevaluate_device(I, J, 0)
             del dev
+            dt = time.perf_counter() - t0
+            if w + 1 >= W and last is not None and abs(dt - last) <= 0.05 * last:
+                break
+            last = dt
+        warm_run = w + 1
     barrier()
     ms = 0.0
     if rank == 0:
         # ---------------- device-resident leg: the MPO cores are in HBM, Pi stays in HBM ----------------
-        sampler = ClockSampler(local)
-        sampler.start()
-        time.sleep(0.3)
+        sampler.mark()
         ctx.timers(reset=True)
         l0 = total_launches(ctx)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -720,7 +739,7 @@ def main():
                           "parallelism": (f"one context over {world} GPUs (single process, tci_ctx_create(ngpu)): row "
                                           "blocks, right environments all-gathered by NCCL, block products stored into "
                                           "the owner's HBM; driven by rank 0, the other torchrun ranks join the barriers")
-                          if world > 1 else "single GPU", "index_sets": "random, seed 8"},
+                          if world > 1 else "single GPU", "index_sets": "random, seed 8", "warmup_steps_run": warm_run},
                "roofline": roofline, "fp64_peak": fp64_peak, "e2e": e2e, "gpu_launches": int(launches),
                "clocks": clocks, "stage_ms_per_step": {k: v / K for k, v in tm.items()}}
         orc = None

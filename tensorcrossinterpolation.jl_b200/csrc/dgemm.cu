@@ -719,8 +719,10 @@ int dgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
         // short inner dimension, many interior tiles: the tile-stream kernel (see k_dgemm_mma_stream)
         static const int stream_tpc = getenv("TCI_DGEMM_STREAM") ? atoi(getenv("TCI_DGEMM_STREAM")) : 2;
         if (stream_tpc > 0 && use_mma && use_async && aligned16 && M % 128 == 0 && N % 64 == 0 && K % 16 == 0 && K <= 1024 &&
-            !(ldc & 1) && half_ctas >= 16 * (i64)ctx->sm_count) {
-            return launch_dgemm_stream(ctx, stream_tpc, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+            !(ldc & 1) && half_ctas >= 4 * (i64)ctx->sm_count) {
+            // two tiles per CTA only when that still leaves many waves (a sharded chain level has ~1000 tiles)
+            const int tpc = half_ctas >= 16 * (i64)ctx->sm_count ? stream_tpc : 1;
+            return launch_dgemm_stream(ctx, tpc, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
                                        strideC, batch, offA, offB);
         }
         static const i64 k32_min = getenv("TCI_DGEMM_K32_MIN") ? atoll(getenv("TCI_DGEMM_K32_MIN")) : 1024;
