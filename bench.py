@@ -797,6 +797,24 @@ def sharded_stages(T, ctx, torch, world, fm, I, J):
     t1 = time.perf_counter()
     del d
     stages["mpo_pi_config5"] = {"ms_1gpu": (t1 - t0) * 1e3}
+    # the same Pi over index sets shaped like a TCI run's (kronecker(Iset, d): i fastest, then sigma; 256 distinct
+    # parents per side): the prefix-aware partition keeps all sigma of a parent on one GPU
+    g = np.random.default_rng(21)
+    Ik = T.kronecker_left(np.unique(np.stack([g.integers(1, 5, 256) for _ in range(NSITES // 2 - 1)], axis=1), axis=0), 4)
+    Jk = T.kronecker_right(4, np.unique(np.stack([g.integers(1, 5, 256) for _ in range(NSITES // 2 - 1)], axis=1), axis=0))
+    ent = {}
+    for label, fobj in (("ms", fm), ("ms_1gpu", f1)):
+        d, _ = fobj.batchevaluate_device(Ik, Jk, 0)
+        del d
+        t0 = time.perf_counter()
+        for _ in range(3):
+            d, _ = fobj.batchevaluate_device(Ik, Jk, 0)
+            del d
+        ent[label] = (time.perf_counter() - t0) / 3 * 1e3
+    refk, gotk = f1(Ik, Jk, 0), fm(Ik, Jk, 0)
+    parity["mpo_kronecker_sets"] = bool(np.max(np.abs(refk - gotk)) <= 1e-12 * np.max(np.abs(refk)))
+    ent["shape"] = f"{len(Ik)} x {len(Jk)}, kronecker-structured sets"
+    stages["mpo_pi_config5_kronecker_sets"] = ent
     del f1
     # --- global search at config-4 shape: 2048 starts (4.5 ms on one GPU: fixed costs dominate the sharded form) and
     #     16384 starts (the size at which eight GPUs have something to split) ---

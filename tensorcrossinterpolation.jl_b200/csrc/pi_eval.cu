@@ -444,13 +444,47 @@ static int pi_enqueue_sharded_analytic(tci_ctx *ctx, i64 target_id, int nshard, 
 // every member extends the right environments of its column block, ONE NCCL all-gather shares them, the member
 // extends the left environments of its own rows, and the GEMM epilogue of its block Pi = left^T right stores into
 // the owner's Pi at the row offset.
+// dst[rowmap[r] + ld * colmap[c]] = blk[r + rows * c]: a GPU's block of Pi, computed in prefix-sorted order, to the
+// caller's row / column positions of the owner's matrix (8-byte stores; peer stores over NVLink when dst is remote)
+__global__ void k_scatter_block(const double *__restrict__ blk, i64 rows, i64 ncols, const i64 *__restrict__ rowmap,
+                                const i64 *__restrict__ colmap, double *__restrict__ dst, i64 ld)
+{
+    const i64 total = rows * ncols;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const i64 r = e % rows, c = e / rows;
+        dst[rowmap[r] + ld * colmap[c]] = blk[e];
+    }
+}
+
 static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64 nl, i64 nI, const i64 *J, i64 nr,
                                   i64 nJ, double *dst, i64 ld, unsigned long long *d_maxbits)
 {
     tci_group *g = ctx->grp;
     const int world = g->world;
     const i64 cblk = (nJ + world - 1) / world;
-    const i64 rblk = round_up((nI + world - 1) / world, 16); // row blocks start on 128-byte lines
+    const i64 rblk = (nI + world - 1) / world;
+    // Prefix-aware partition.  An environment is shared by all entries with the same partial index (the reference's Dict
+    // memo, contraction.jl:112-176), so the rows a GPU receives should share prefixes with EACH OTHER: the rows are put
+    // in lexicographic order of their multi-indices (first site most significant; the columns by suffix: last site most
+    // significant) and every GPU takes a contiguous block of that order.  For kronecker(Iset, d) -- i fastest, then sigma
+    // -- a block of the caller's order holds one sigma of many different i, and every GPU would extend the whole prefix
+    // chain of the i it touches once per sigma; with the sorted order a GPU holds all sigma of its i.  The block product is
+    // computed in sorted order and scattered to the caller's rows / columns of the owner's Pi (peer stores).
+    std::vector<i64> rperm((size_t)nI), cperm((size_t)nJ), Is((size_t)(nl * nI)), Js((size_t)(nr * nJ));
+    for (i64 q = 0; q < nI; ++q) rperm[q] = q;
+    for (i64 q = 0; q < nJ; ++q) cperm[q] = q;
+    std::stable_sort(rperm.begin(), rperm.end(), [&](i64 a, i64 b) {
+        return std::lexicographical_compare(I + nl * a, I + nl * (a + 1), I + nl * b, I + nl * (b + 1));
+    });
+    std::stable_sort(cperm.begin(), cperm.end(), [&](i64 a, i64 b) {
+        for (i64 s = nr - 1; s >= 0; --s)
+            if (J[nr * a + s] != J[nr * b + s]) return J[nr * a + s] < J[nr * b + s];
+        return false;
+    });
+    for (i64 q = 0; q < nI; ++q) std::copy(I + nl * rperm[q], I + nl * (rperm[q] + 1), Is.begin() + nl * q);
+    for (i64 q = 0; q < nJ; ++q) std::copy(J + nr * cperm[q], J + nr * (cperm[q] + 1), Js.begin() + nr * q);
+    I = Is.data();
+    J = Js.data();
     std::vector<double *> renv(g->nlocal, nullptr);
     // TCI_SHARD_DEBUG: per-member timeline of the phases (events on the members' main streams)
     static const bool dbg = getenv("TCI_SHARD_DEBUG") != nullptr;
@@ -543,10 +577,23 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
             if (rank != 0) cudaMemsetAsync(w, 0, 8, c->stream);
             const i64 lo = std::min(nI, rank * rblk), hi = std::min(nI, (rank + 1) * rblk);
             if (hi <= lo) return TCI_OK;
-            // Pi[lo:hi, :] = lenv^T renv    cachedtensortrain.jl:211-212, contraction.jl:328
-            int r = dgemm_dev(c, true, false, hi - lo, nJ, D, 1.0, lenvs[k], D, renv[k], D, 0.0, dst + lo, ld);
-            if (!r) r = apply_elementwise(c, t, dst + lo, hi - lo, nJ, ld);
-            if (!r && d_maxbits) r = maxabs_dev(c, dst + lo, hi - lo, nJ, ld, w);
+            // block (sorted rows lo:hi) x (sorted columns) = lenv^T renv    cachedtensortrain.jl:211-212, contraction.jl:328
+            const i64 rows = hi - lo;
+            DevBuf<double> blk(c);
+            DevBuf<i64> maps(c);
+            TCI_CUDA(c, blk.alloc((size_t)(rows * nJ)));
+            TCI_CUDA(c, maps.alloc((size_t)(rows + nJ)));
+            TCI_CUDA(c, cudaMemcpyAsync(maps.p, rperm.data() + lo, (size_t)rows * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+            TCI_CUDA(c, cudaMemcpyAsync(maps.p + rows, cperm.data(), (size_t)nJ * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+            int r = dgemm_dev(c, true, false, rows, nJ, D, 1.0, lenvs[k], D, renv[k], D, 0.0, blk.p, rows);
+            if (!r) r = apply_elementwise(c, t, blk.p, rows, nJ, rows);
+            if (!r && d_maxbits) r = maxabs_dev(c, blk.p, rows, nJ, rows, w);
+            if (!r) { // to the caller's rows / columns of the owner's Pi
+                k_scatter_block<<<(unsigned)std::min<i64>((rows * nJ + 255) / 256, (i64)c->sm_count * 8), 256, 0, c->stream>>>(
+                    blk.p, rows, nJ, maps.p, maps.p + rows, dst, ld);
+                c->launches++;
+                if (cudaGetLastError() != cudaSuccess) r = tci_fail(c, TCI_ERR_CUDA, "k_scatter_block launch failed");
+            }
             mark(k, 4);
             return r;
         });
