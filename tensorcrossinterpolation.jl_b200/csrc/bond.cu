@@ -316,6 +316,12 @@ static void union_into(std::vector<i64> &a, i64 len, const i64 *b, i64 nb)
     }
 }
 
+void sweep_results_drop(tci_ctx *ctx) // ctx.cu: a context that goes away takes its unfetched result with it
+{
+    std::lock_guard<std::mutex> lk(g_sweeps_mu);
+    g_sweeps.erase(ctx);
+}
+
 extern "C" int tci_sweep2site_half(tci_ctx *ctx, int64_t target_id, int forward, const int64_t *const *Iset,
                                    const int64_t *nI, const int64_t *const *Jset, const int64_t *nJ,
                                    const int64_t *const *extraI, const int64_t *nextraI, const int64_t *const *extraJ,

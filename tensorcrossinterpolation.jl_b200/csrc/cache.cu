@@ -343,12 +343,19 @@ extern "C" int tci_target_cached(tci_ctx *ctx, int64_t inner_id, int capacity_lo
     cd.inner = inner_id;
     const size_t cap = (size_t)1 << capacity_log2;
     cd.mask = cap - 1;
-    TCI_CUDA(ctx, cudaMalloc(&cd.slots, cap * sizeof(CacheSlot)));
-    TCI_CUDA(ctx, cudaMemset(cd.slots, 0, cap * sizeof(CacheSlot)));
-    TCI_CUDA(ctx, cudaMalloc(&cd.counters, 8 * sizeof(unsigned long long)));
-    TCI_CUDA(ctx, cudaMemset(cd.counters, 0, 8 * sizeof(unsigned long long)));
-    TCI_CUDA(ctx, cudaMalloc(&cd.coeff, coeff.size() * sizeof(unsigned long long)));
-    TCI_CUDA(ctx, cudaMemcpy(cd.coeff, coeff.data(), coeff.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMalloc(&cd.slots, cap * sizeof(CacheSlot));
+    if (e == cudaSuccess) e = cudaMemset(cd.slots, 0, cap * sizeof(CacheSlot));
+    if (e == cudaSuccess) e = cudaMalloc(&cd.counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(cd.counters, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&cd.coeff, coeff.size() * sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(cd.coeff, coeff.data(), coeff.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { // typically out of memory for a large table: nothing is kept
+        cudaFree(cd.slots);
+        cudaFree(cd.counters);
+        cudaFree(cd.coeff);
+        return tci_fail(ctx, TCI_ERR_CUDA, std::string("tci_target_cached: ") + cudaGetErrorString(e));
+    }
     std::unique_ptr<TargetDev> t(new TargetDev());
     t->kind = 4;
     t->nsites = n;

@@ -63,6 +63,7 @@ int ctx_create_one(int device_id, tci_ctx **out)
 }
 
 int group_create_local(const std::vector<tci_ctx *> &members, tci_group **out); // group.cu
+void sweep_results_drop(tci_ctx *ctx);                                             // bond.cu
 
 // tci_ctx_create(ngpu, device_ids): ONE process drives ngpu GPUs (the reference's caller is a single Julia process,
 // tensorci2.jl:805-809).  device_ids[0] owns the per-bond rrLU; the stages that shard are split over all
@@ -128,6 +129,7 @@ void ctx_release(tci_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->targets) target_free(ctx, *kv.second);
+    sweep_results_drop(ctx);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2);

@@ -809,12 +809,16 @@ static int zmpo_create(tci_ctx *ctx, i64 nsites, const i64 *dimsA4, const double
         t->localdims.push_back(da[1] * db[2]);
         const i64 na = 2 * da[0] * da[1] * da[2] * da[3], nb = 2 * db[0] * db[1] * db[2] * db[3];
         double *pa = nullptr, *pb = nullptr;
-        TCI_CUDA(ctx, cudaMalloc(&pa, std::max<i64>(na, 2) * sizeof(double)));
-        t->A.push_back(pa);
-        TCI_CUDA(ctx, cudaMalloc(&pb, std::max<i64>(nb, 2) * sizeof(double)));
-        t->B.push_back(pb);
-        TCI_CUDA(ctx, cudaMemcpy(pa, A[s], na * sizeof(double), cudaMemcpyHostToDevice));
-        TCI_CUDA(ctx, cudaMemcpy(pb, B ? B[s] : one, nb * sizeof(double), cudaMemcpyHostToDevice));
+        cudaError_t e = cudaMalloc(&pa, std::max<i64>(na, 2) * sizeof(double));
+        if (e == cudaSuccess) t->A.push_back(pa);
+        if (e == cudaSuccess) e = cudaMalloc(&pb, std::max<i64>(nb, 2) * sizeof(double));
+        if (e == cudaSuccess) t->B.push_back(pb);
+        if (e == cudaSuccess) e = cudaMemcpy(pa, A[s], na * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pb, B ? B[s] : one, nb * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { // nothing of a half-built target is kept
+            target_free(ctx, *t);
+            return tci_fail(ctx, TCI_ERR_CUDA, std::string("complex target upload: ") + cudaGetErrorString(e));
+        }
     }
     const i64 id = ctx->next_target++;
     ctx->targets[id] = std::move(t);
