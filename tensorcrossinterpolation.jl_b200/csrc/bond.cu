@@ -24,6 +24,8 @@ int rrlu_core(tci_ctx *ctx, tci_dmat *A, i64 m, i64 n, i64 maxrank, double relto
               tci_lu **factors, const void *extra_dev, void *extra_host, size_t extra_bytes, int *deferred_result);
 int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i64 ldx);
 int rrlu_batch_fullrank(tci_ctx *ctx, int nmat, tci_dmat *const *P, tci_lu **lus, char *const *results);
+int lu_rdiv_batched_small(tci_ctx *ctx, int n, tci_lu *const *lus, const double *const *B, const i64 *ldb, const i64 *rows,
+                          double *const *X, const i64 *ldx, std::vector<char> &done);
 
 extern "C" int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t nl, int64_t nI,
                                const int64_t *J, int64_t nr, int64_t nJ, int64_t maxrank, double reltol, double abstol,
@@ -184,10 +186,26 @@ extern "C" int tci_fill_sitetensors(tci_ctx *ctx, int64_t target_id, int64_t nsi
     }
     if (fdbg) cudaEventRecord(fe[1], ctx->stream);
     // phase 3: T = Pi1 P^-1 (:391) from the full-pivot factors; the last tensor is Pi1 itself (:377-381)
+    std::vector<char> solved;
+    if (!rc && ce == cudaSuccess && n > 1) { // all sites with a small pivot matrix: one launch
+        std::vector<const double *> Bp((size_t)n - 1);
+        std::vector<double *> Xp((size_t)n - 1);
+        std::vector<i64> ldb((size_t)n - 1), rws((size_t)n - 1), ldx((size_t)n - 1);
+        for (i64 b = 0; b + 1 < n; ++b) {
+            Bp[b] = Pi1s[b] ? Pi1s[b]->p : nullptr;
+            ldb[b] = Pi1s[b] ? Pi1s[b]->ld : 0;
+            rws[b] = nI[b] * t.localdims[b];
+            Xp[b] = tt->cores[b];
+            ldx[b] = rws[b];
+        }
+        rc = lu_rdiv_batched_small(ctx, (int)(n - 1), lub.data(), Bp.data(), ldb.data(), rws.data(), Xp.data(), ldx.data(), solved);
+    }
     for (i64 b = 0; b < n && !rc && ce == cudaSuccess; ++b) {
         const i64 d = t.localdims[b], rows = nI[b] * d, k = nJ[b];
         double *core = tt->cores[b];
-        if (b == n - 1) {
+        if (b + 1 < n && b < (i64)solved.size() && solved[b]) {
+            // T_b was written by the batched kernel
+        } else if (b == n - 1) {
             k_compact<<<(unsigned)std::min<i64>((rows * k + 255) / 256, 4096), 256, 0, ctx->stream>>>(Pi1s[b]->p, Pi1s[b]->ld,
                                                                                                   rows, k, core);
             ctx->launches++;

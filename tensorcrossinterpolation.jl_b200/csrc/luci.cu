@@ -349,6 +349,155 @@ extern "C" int tci_lu_complete(tci_lu *lu, tci_dmat *A21, tci_dmat *A12, double 
     return TCI_OK;
 }
 
+// ---- batched B * A^-1 for small pivot matrices ------------------------------------------------------------------
+// fillsitetensors! solves T_b = Pi1_b P_b^-1 for every site (tensorci2.jl:391); at chi <= 256 each solve is a chain of ~30
+// tiny launches (extract, gather, recursive TRSM x 2, scatter), and the whole stage is launch-bound (config 3: 2.0 ms
+// for 19 sites).  Here ONE launch handles all sites: a CTA takes RD_RB rows of one site, keeps them in shared memory and
+// runs both triangular solves on them against the factors as they sit in the factorised matrix (rows physically
+// permuted, columns through colperm; L unit lower, U upper: the leftorthogonal form tci_fill_sitetensors uses):
+//   W = B[:, colperm];  W <- W U^-1 (columns left to right);  W <- W L^-1 (right to left);  X[:, rowperm[c]] = W[:, c].
+// Blocked by 32 columns: a thread per row solves the diagonal block, then all threads update the columns still to come.
+#define RD_RB 32
+#define RD_THREADS 256
+struct RdivJob {
+    const double *A; // factorised P, lda
+    i64 lda;
+    const i64 *colperm, *rowperm;
+    const double *B;
+    i64 ldb;
+    double *X;
+    i64 ldx;
+    int rows, k, cta0; // first CTA of this job
+};
+
+__global__ void __launch_bounds__(RD_THREADS) k_rdiv_small(const RdivJob *__restrict__ jobs, int njobs)
+{
+    extern __shared__ __align__(16) double rd_sm[]; // W[c][RD_RB] (column c of the row block contiguous)
+    __shared__ i64 cp_s[256];
+    int lo = 0, hi = njobs - 1; // the job this CTA belongs to
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].cta0 <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const RdivJob jb = jobs[lo];
+    const int k = jb.k, tid = threadIdx.x;
+    const int r0 = ((int)blockIdx.x - jb.cta0) * RD_RB;
+    const int nr = min(RD_RB, jb.rows - r0);
+    for (int c = tid; c < k; c += RD_THREADS) cp_s[c] = jb.colperm[c];
+    __syncthreads();
+    for (int e = tid; e < k * RD_RB; e += RD_THREADS) {
+        const int r = e % RD_RB, c = e / RD_RB;
+        rd_sm[e] = r < nr ? jb.B[r0 + r + jb.ldb * cp_s[c]] : 0.0;
+    }
+    __syncthreads();
+    const int r = tid % RD_RB, cg = tid / RD_RB; // row, column group (RD_THREADS / RD_RB = 8 groups)
+    constexpr int NG = RD_THREADS / RD_RB;
+    __shared__ double dg[32][33]; // the 32 x 32 diagonal block of the factor, dg[j][c - cb]
+    // one column of the trailing update: W[:, c] -= sum_{j in [cb, ce)} W[:, j] * f[j], f = column c of the factor.  The
+    // 32 factor values are fetched first (independent loads: they come from L2, the factor does not fit L1), then used.
+    auto update_col = [&](const double *fcol, int c, int cb, int ce) {
+        double f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = cb + j < ce ? fcol[cb + j] : 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (cb + j < ce) a0 = fma(rd_sm[(cb + j) * RD_RB + r], f[j], a0);
+            if (cb + j + 1 < ce) a1 = fma(rd_sm[(cb + j + 1) * RD_RB + r], f[j + 1], a1);
+            if (cb + j + 2 < ce) a2 = fma(rd_sm[(cb + j + 2) * RD_RB + r], f[j + 2], a2);
+            if (cb + j + 3 < ce) a3 = fma(rd_sm[(cb + j + 3) * RD_RB + r], f[j + 3], a3);
+        }
+        rd_sm[c * RD_RB + r] -= (a0 + a1) + (a2 + a3);
+    };
+    // ---- W <- W U^-1 ----
+    for (int cb = 0; cb < k; cb += 32) {
+        const int ce = min(cb + 32, k);
+        for (int e = tid; e < 32 * 32; e += RD_THREADS) { // stage the diagonal block
+            const int j = e % 32, c = e / 32;
+            dg[j][c] = (cb + j < ce && cb + c < ce) ? jb.A[cb + j + jb.lda * cp_s[cb + c]] : 0.0;
+        }
+        __syncthreads();
+        if (tid < RD_RB) { // diagonal block, a thread per row
+            for (int c = cb; c < ce; ++c) {
+                double acc = rd_sm[c * RD_RB + r];
+                for (int j = cb; j < c; ++j) acc = fma(-rd_sm[j * RD_RB + r], dg[j - cb][c - cb], acc);
+                rd_sm[c * RD_RB + r] = acc / dg[c - cb][c - cb];
+            }
+        }
+        __syncthreads();
+        for (int c = ce + cg; c < k; c += NG) update_col(jb.A + jb.lda * cp_s[c], c, cb, ce); // columns still to come
+        __syncthreads();
+    }
+    // ---- W <- W L^-1 (unit lower; columns right to left) ----
+    for (int ce = k; ce > 0; ce -= 32) {
+        const int cb = max(ce - 32, 0);
+        for (int e = tid; e < 32 * 32; e += RD_THREADS) {
+            const int j = e % 32, c = e / 32;
+            dg[j][c] = (cb + j < ce && cb + c < ce) ? jb.A[cb + j + jb.lda * cp_s[cb + c]] : 0.0;
+        }
+        __syncthreads();
+        if (tid < RD_RB) {
+            for (int c = ce - 1; c >= cb; --c) {
+                double acc = rd_sm[c * RD_RB + r];
+                for (int j = c + 1; j < ce; ++j) acc = fma(-rd_sm[j * RD_RB + r], dg[j - cb][c - cb], acc);
+                rd_sm[c * RD_RB + r] = acc;
+            }
+        }
+        __syncthreads();
+        for (int c = cg; c < cb; c += NG) update_col(jb.A + jb.lda * cp_s[c], c, cb, ce);
+        __syncthreads();
+    }
+    for (int e = tid; e < k * RD_RB; e += RD_THREADS) {
+        const int rr = e % RD_RB, c = e / RD_RB;
+        if (rr < nr) jb.X[r0 + rr + jb.ldx * jb.rowperm[c]] = rd_sm[e];
+    }
+}
+
+// all solves of a fillsitetensors! call whose pivot matrix has k <= 256 in one launch; done[q] tells the caller which
+// jobs were taken (the others go through lu_rdiv_enqueue)
+int lu_rdiv_batched_small(tci_ctx *ctx, int n, tci_lu *const *lus, const double *const *B, const i64 *ldb, const i64 *rows,
+                          double *const *X, const i64 *ldx, std::vector<char> &done)
+{
+    done.assign((size_t)n, 0);
+    static const bool off = getenv("TCI_NO_BATCHED_RDIV") != nullptr;
+    if (off) return TCI_OK;
+    std::vector<RdivJob> jobs;
+    int cta = 0, kmax = 0;
+    for (int q = 0; q < n; ++q) {
+        tci_lu *lu = lus[q];
+        if (!lu || lu->is_complex || !lu->leftorthogonal || lu->r > 256 || lu->r < 1 || lu->m != lu->n || lu->r != lu->m || rows[q] < 1)
+            continue;
+        RdivJob jb;
+        jb.A = lu->A->p;
+        jb.lda = lu->A->ld;
+        jb.colperm = lu->d_colperm;
+        jb.rowperm = lu->d_rowperm;
+        jb.B = B[q];
+        jb.ldb = ldb[q];
+        jb.X = X[q];
+        jb.ldx = ldx[q];
+        jb.rows = (int)rows[q];
+        jb.k = (int)lu->r;
+        jb.cta0 = cta;
+        cta += (int)((rows[q] + RD_RB - 1) / RD_RB);
+        kmax = std::max(kmax, jb.k);
+        jobs.push_back(jb);
+        done[q] = 1;
+    }
+    if (jobs.empty()) return TCI_OK;
+    DevBuf<RdivJob> dj(ctx);
+    TCI_CUDA(ctx, dj.upload(jobs.data(), jobs.size()));
+    const size_t smem = (size_t)kmax * RD_RB * sizeof(double);
+    TCI_CUDA(ctx, ctx_func_smem(ctx, (const void *)k_rdiv_small, 256 * RD_RB * (int)sizeof(double)));
+    k_rdiv_small<<<(unsigned)cta, RD_THREADS, smem, ctx->stream>>>(dj.p, (int)jobs.size());
+    ctx->launches++;
+    TCI_CUDA(ctx, cudaGetLastError());
+    return TCI_OK;
+}
+
 // enqueue only: X (rows x k, ldx) = B (rows x k, ldb) * A^-1 with the factors of `lu` (assumed of full rank k)
 int lu_rdiv_enqueue(tci_lu *lu, const double *B, i64 ldb, i64 rows, double *X, i64 ldx)
 {
