@@ -276,6 +276,12 @@ int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64
  * GPU: the block [lo, hi) of `rank` when n items are split over `world` ranks in contiguous blocks whose starts are
  * multiples of `align`; and the selection of :180-188 replayed on gathered (error, probe index) records.             */
 int tci_shard_range(int64_t n, int world, int rank, int64_t align, int64_t *lo, int64_t *hi);
+/* The order in which a sharded TT / contraction Pi deals rows (side 0) or columns (side 1) to the GPUs: environments are
+ * shared by entries with a common partial index (the Dict memo of contraction.jl:112-176, cachedtensortrain.jl:77-128),
+ * so rows are taken in lexicographic order of their multi-indices (first site most significant), columns with the LAST
+ * site most significant, and every GPU gets a contiguous block (tci_shard_range) of that order.  idx: (len x count);
+ * perm[q] = caller's index of the q-th entry of the order (stable).  Host only.                                        */
+int tci_shard_order(const int64_t *idx, int64_t len, int64_t count, int side, int64_t *perm);
 int tci_globalsearch_select(const double *rec_err, const int64_t *rec_idx, int64_t nsearch, const int64_t *starts,
                             int64_t nsites, const int64_t *localdims, double threshold, int64_t maxn,
                             int64_t *pivots_out, double *errs_out, int64_t *start_idx_out, int64_t *nfound);

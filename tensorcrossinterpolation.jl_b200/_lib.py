@@ -68,6 +68,7 @@ SYMBOLS = {
                                           C.POINTER(VP)]),
     "tci_contract_naive_site": (C.c_int, [VP, P_f64, i64, i64, i64, i64, P_f64, i64, i64, i64, P_f64]),
     "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, i64, f64, i64, C.c_int, P_i64, P_f64, P_i64, P_i64]),
+    "tci_shard_order": (C.c_int, [P_i64, i64, i64, C.c_int, P_i64]),
     "tci_shard_range": (C.c_int, [i64, C.c_int, C.c_int, i64, P_i64, P_i64]),
     "tci_globalsearch_select": (C.c_int, [P_f64, P_i64, i64, P_i64, i64, P_i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),
     "tci_bond_update": (C.c_int, [VP, i64, P_i64, i64, i64, P_i64, i64, i64, i64, f64, f64, C.c_int, C.c_int, P_i64,
@@ -212,6 +213,16 @@ def shard_range(n, world, rank, align=1):
     if rc != 0:
         raise ValueError("tci_shard_range: bad arguments")
     return lo.value, hi.value
+
+
+def shard_order(indexset, side):
+    """tci_shard_order: the prefix- (side 0) / suffix-sorted (side 1) order a sharded Pi deals its rows / columns in."""
+    idx = np.ascontiguousarray(indexset, dtype=np.int64)
+    perm = np.zeros(idx.shape[0], dtype=np.int64)
+    rc = lib().tci_shard_order(pi(idx), idx.shape[1], idx.shape[0], int(side), pi(perm))
+    if rc != 0:
+        raise ValueError("tci_shard_order: bad arguments")
+    return perm
 
 
 def gemm(A, B, ctx=None):

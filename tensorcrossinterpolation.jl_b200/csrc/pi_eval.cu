@@ -444,6 +444,27 @@ static int pi_enqueue_sharded_analytic(tci_ctx *ctx, i64 target_id, int nshard, 
 // every member extends the right environments of its column block, ONE NCCL all-gather shares them, the member
 // extends the left environments of its own rows, and the GEMM epilogue of its block Pi = left^T right stores into
 // the owner's Pi at the row offset.
+// The order in which a sharded TT / contraction Pi deals its rows (side 0: lexicographic in the multi-index, first site
+// most significant -- entries that share a prefix are neighbours) or columns (side 1: last site most significant --
+// shared suffixes) to the GPUs; stable, so equal entries keep the caller's order.  perm[q] = caller's index of the q-th
+// entry of that order.  Host only.
+extern "C" int tci_shard_order(const int64_t *idx, int64_t len, int64_t count, int side, int64_t *perm)
+{
+    if (count < 0 || len < 0 || !perm || (len > 0 && count > 0 && !idx) || (side != 0 && side != 1)) return TCI_ERR_ARG;
+    for (i64 q = 0; q < count; ++q) perm[q] = q;
+    if (side == 0)
+        std::stable_sort(perm, perm + count, [&](i64 a, i64 b) {
+            return std::lexicographical_compare(idx + len * a, idx + len * (a + 1), idx + len * b, idx + len * (b + 1));
+        });
+    else
+        std::stable_sort(perm, perm + count, [&](i64 a, i64 b) {
+            for (i64 s = len - 1; s >= 0; --s)
+                if (idx[len * a + s] != idx[len * b + s]) return idx[len * a + s] < idx[len * b + s];
+            return false;
+        });
+    return TCI_OK;
+}
+
 // dst[rowmap[r] + ld * colmap[c]] = blk[r + rows * c]: a GPU's block of Pi, computed in prefix-sorted order, to the
 // caller's row / column positions of the owner's matrix (8-byte stores; peer stores over NVLink when dst is remote)
 __global__ void k_scatter_block(const double *__restrict__ blk, i64 rows, i64 ncols, const i64 *__restrict__ rowmap,
@@ -471,16 +492,8 @@ static int pi_enqueue_sharded_env(tci_ctx *ctx, i64 target_id, const i64 *I, i64
     // chain of the i it touches once per sigma; with the sorted order a GPU holds all sigma of its i.  The block product is
     // computed in sorted order and scattered to the caller's rows / columns of the owner's Pi (peer stores).
     std::vector<i64> rperm((size_t)nI), cperm((size_t)nJ), Is((size_t)(nl * nI)), Js((size_t)(nr * nJ));
-    for (i64 q = 0; q < nI; ++q) rperm[q] = q;
-    for (i64 q = 0; q < nJ; ++q) cperm[q] = q;
-    std::stable_sort(rperm.begin(), rperm.end(), [&](i64 a, i64 b) {
-        return std::lexicographical_compare(I + nl * a, I + nl * (a + 1), I + nl * b, I + nl * (b + 1));
-    });
-    std::stable_sort(cperm.begin(), cperm.end(), [&](i64 a, i64 b) {
-        for (i64 s = nr - 1; s >= 0; --s)
-            if (J[nr * a + s] != J[nr * b + s]) return J[nr * a + s] < J[nr * b + s];
-        return false;
-    });
+    tci_shard_order(I, nl, nI, 0, rperm.data());
+    tci_shard_order(J, nr, nJ, 1, cperm.data());
     for (i64 q = 0; q < nI; ++q) std::copy(I + nl * rperm[q], I + nl * (rperm[q] + 1), Is.begin() + nl * q);
     for (i64 q = 0; q < nJ; ++q) std::copy(J + nr * cperm[q], J + nr * (cperm[q] + 1), Js.begin() + nr * q);
     I = Is.data();

@@ -5,8 +5,10 @@ tci_globalsearch split their work inside the library:
 * Pi evaluation of an analytic target: column blocks of Jcombined; every GPU's evaluation kernel stores its block
   straight into the rrLU owner's HBM (peer st.global over NVLink), one NCCL all-reduce(max) combines max|Pi| and orders
   the owner's rrLU behind the peer stores.  A cost model shards only when it pays (Pi must cross NVLink once).
-* TT / MPO x MPO targets: row blocks of Icombined -- right environments of each GPU's column block, ONE ncclAllGather,
-  left environments of the GPU's own rows, block product stored into the owner's Pi by the GEMM epilogue.
+* TT / MPO x MPO targets: row blocks of the PREFIX-SORTED Icombined (entries that share partial indices share
+  environments, so they go to the same GPU) -- right environments of each GPU's block of suffix-sorted columns on a
+  high-priority side stream, ONE ncclAllGather, left environments of the GPU's own rows concurrently on the main stream,
+  block product scattered to the caller's rows / columns of the owner's Pi.
 * global pivot search: contiguous blocks of the start points; fixed-size (error, probe) records, ONE ncclAllGather;
   the reference's selection (start order, truncation, globalpivotfinder.jl:180-188) replayed on the records.
 * the per-bond rrLU stays on the owner.
@@ -33,12 +35,21 @@ def column_blocks(ncols, world):
     return blk, ranges
 
 
-def row_blocks(nrows, world, align=16):
-    """Row blocks whose starts are multiples of `align` rows (128-byte lines of the column-major Pi)."""
+def row_blocks(nrows, world, align=1):
+    """The library's row partition of a sharded TT / contraction Pi: contiguous blocks (tci_shard_range) of the
+    prefix-sorted order (tci_shard_order); a block product is scattered to the caller's rows, so no alignment is needed."""
     ranges = [shard_range(nrows, world, r, align) for r in range(world)]
     blk = (nrows + world - 1) // world if nrows else 0
     blk = (blk + align - 1) // align * align
     return blk, ranges
+
+
+def prefix_partition(indexset, world, side=0):
+    """Which caller-order entries every GPU takes: blocks of the prefix- (side 0: rows) or suffix-sorted (side 1: columns)
+    order.  Returns a list of index arrays, one per rank."""
+    from ._lib import shard_order
+    perm = shard_order(indexset, side)
+    return [perm[lo:hi] for lo, hi in (shard_range(len(perm), world, r, 1) for r in range(world))]
 
 
 def select_global_pivots(rec_err, rec_idx, starts, localdims, threshold, maxn):

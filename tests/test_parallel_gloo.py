@@ -184,8 +184,9 @@ def test_column_blocks():
     assert column_blocks(2, 4) == (1, [(0, 1), (1, 2), (2, 2), (2, 2)])
     assert column_blocks(0, 2) == (0, [(0, 0), (0, 0)])
     from tci_b200.parallel import row_blocks
-    assert row_blocks(100, 2) == (64, [(0, 64), (64, 100)])
-    assert row_blocks(10, 4) == (16, [(0, 10), (10, 10), (10, 10), (10, 10)])
+    assert row_blocks(100, 2) == (50, [(0, 50), (50, 100)])
+    assert row_blocks(100, 2, align=16) == (64, [(0, 64), (64, 100)])
+    assert row_blocks(10, 4) == (3, [(0, 3), (3, 6), (6, 9), (9, 10)])
     assert row_blocks(4096, 8) == (512, [(512 * r, 512 * (r + 1)) for r in range(8)])
     assert row_blocks(0, 2) == (0, [(0, 0), (0, 0)])
     starts = np.array([[1, 1], [2, 2], [1, 2], [2, 1]], dtype=np.int64)
@@ -194,3 +195,39 @@ def test_column_blocks():
     assert piv.tolist() == [[1, 2], [1, 2]] and es.tolist() == [0.3, 0.2] and sidx.tolist() == [0, 2]
     piv, es, sidx = select_global_pivots([0.3, 0.05, 0.2, 0.4], [3, -1, 0, 1], starts, [2, 2], 0.25, 5)
     assert piv.tolist() == [[1, 2], [2, 1]] and sidx.tolist() == [0, 3]  # probe 1 of start (2, 1) is x_1 = 2
+
+
+def test_prefix_aware_partition():
+    """tci_shard_order (host only): rows are dealt to the GPUs in lexicographic order of their multi-indices, columns
+    with the last site most significant; the order is stable.  For kronecker(Iset, d) -- i fastest, then sigma
+    (tensorci2.jl:315-320) -- every GPU then holds ALL sigma of its parents, so no prefix environment is extended on
+    two GPUs; the caller-order blocks would put one sigma of many parents on each GPU."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tci_b200 as T
+    from tci_b200._lib import shard_order
+    from tci_b200.parallel import prefix_partition
+    rng = np.random.default_rng(0)
+    S = rng.integers(1, 4, (50, 5)).astype(np.int64)
+    perm = shard_order(S, 0)
+    rows = [tuple(r) for r in S[perm].tolist()]
+    assert rows == sorted(rows) and sorted(perm.tolist()) == list(range(50))
+    assert all(perm[q] < perm[q + 1] for q in range(49) if rows[q] == rows[q + 1])  # stable
+    perm = shard_order(S, 1)
+    cols = [tuple(reversed(r)) for r in S[perm].tolist()]
+    assert cols == sorted(cols)
+    parents = np.unique(rng.integers(1, 5, (64, 6)), axis=0).astype(np.int64)
+    K = T.kronecker_left(parents, 4)  # (i, sigma), i fastest
+    world = 8
+    per_gpu_parents = [set(map(tuple, K[idx][:, :-1].tolist())) for idx in prefix_partition(K, world, 0)]
+    blk = (len(K) + world - 1) // world
+    naive = [set(map(tuple, K[r * blk:(r + 1) * blk][:, :-1].tolist())) for r in range(world)]
+    # parents touched summed over GPUs: the sorted partition splits at most one parent per boundary
+    assert sum(len(p) for p in per_gpu_parents) <= len(parents) + world - 1
+    assert sum(len(p) for p in naive) >= 3 * len(parents)
+    assert sorted(np.concatenate(prefix_partition(K, world, 0)).tolist()) == list(range(len(K)))
+    KJ = T.kronecker_right(4, parents)  # (sigma, j), sigma fastest: suffix = j
+    per_gpu = [set(map(tuple, KJ[idx][:, 1:].tolist())) for idx in prefix_partition(KJ, world, 1)]
+    assert sum(len(p) for p in per_gpu) <= len(parents) + world - 1
+    with pytest.raises(ValueError):
+        shard_order(S, 2)
