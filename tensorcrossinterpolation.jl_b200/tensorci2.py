@@ -153,16 +153,24 @@ def reconstractglobalpivotsfromijset(localdims, Isets, Jsets):  # :171-188
     return as_indexset(out, len(localdims))
 
 
+def _pushunique_all(arr, items):
+    """pushunique!(arr, item) (util.jl:16-20) for every row of `items` in turn."""
+    if items.shape[1] == 0:  # the empty multi-index: present as soon as the set has one entry
+        return arr if arr.shape[0] else np.zeros((1, 0), dtype=np.int64)
+    if arr.shape[0] == 0:
+        arr = np.zeros((0, items.shape[1]), dtype=np.int64)
+    return union(np.ascontiguousarray(arr), np.ascontiguousarray(items))
+
+
 def addglobalpivots(tci, pivots):  # :193-213
     pivots = as_indexset(pivots, len(tci))
     if pivots.shape[0] and pivots.shape[1] != len(tci):
         raise ValueError("Please specify a pivot as one index per leg of the MPS.")
     n = len(tci)
-    for p in pivots:
+    if pivots.shape[0] > 0:  # pushunique! of every pivot's partial indices, pivot by pivot = an order-preserving union
         for b in range(n):
-            tci.Iset[b] = pushunique(tci.Iset[b], p[:b])
-            tci.Jset[b] = pushunique(tci.Jset[b], p[b + 1:])
-    if pivots.shape[0] > 0:
+            tci.Iset[b] = _pushunique_all(tci.Iset[b], pivots[:, :b])
+            tci.Jset[b] = _pushunique_all(tci.Jset[b], pivots[:, b + 1:])
         invalidatesitetensors(tci)
 
 
