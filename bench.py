@@ -44,7 +44,7 @@ METRIC = "contraction FP64 GFLOP/s (crossinterpolate2 time-to-tol; Pi-eval Meval
 WORKLOAD = ("MPO x MPO contraction target (contraction.jl), 40 sites, bond dim 256, site dims 2x2, Float64: batched "
             "two-site Pi at the middle bond, nL = nR = 1024 (BASELINE configs[4])")
 RRLU_SIZE, RRLU_RANK = 8192, 1024
-HEADLINE_DRAM_BYTES = 67177249280 + 54537441280 + 2167770112 + 52046336  # ncu, one step (profiles/r2_headline_dram.csv)
+HEADLINE_DRAM_BYTES = 60937763328 + 46877822720  # ncu, the 108 launches of one step (profiles/r2_headline_dram.csv)
 
 
 # ----------------------------------------------------------------------------------------------- workload ----
@@ -719,7 +719,7 @@ def main():
                             "FP64 figure"}
         peak_tf = max(dmma, cublas_tf)
         gemm_ms = (tm["pi_eval"]) / K
-        roofline = {"bound": "tensor", "kernel": "k_dgemm_mma_async<128,128> (FP64 DMMA; tcgen05 has no FP64 kind)",
+        roofline = {"bound": "tensor", "kernel": "k_dgemm_mma_stream (128x64 tiles, FP64 DMMA m8n8k4; tcgen05 has no FP64 kind)",
                     "achieved": flops / (gemm_ms * 1e-3) / 1e12 / (world if world > 1 else 1), "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak_tf / (world if world > 1 else 1),
                     "peak_source": "max(DMMA loop, cuBLAS DGEMM 8192^3) measured in this run (no FP64 figure in "
@@ -727,9 +727,9 @@ def main():
                     "kernel_ms_per_step": gemm_ms, "algorithmic_flops": flops,
                     "traffic": HEADLINE_DRAM_BYTES if world == 1 else None,
                     "traffic_source": "profiles/r2_headline_dram.csv: ncu dram__bytes_read + dram__bytes_write summed over "
-                                      "the 119 GEMM launches of ONE step (67.2 + 54.5 GB in the 128x64 kernel, 2.2 GB in "
-                                      "the 64x64 one) = 0.86 TB/s at 145 ms: compute bound, not HBM bound",
-                    "note": "per GPU; the step is ~150 batched gather-GEMM launches of the same kernel (environment "
+                                      "the 108 launches of ONE step (60.9 GB read + 46.9 GB written; k_dgemm_mma_stream is "
+                                      "96.5 % of the step) = 0.78 TB/s at 138 ms: compute bound, not HBM bound",
+                    "note": "per GPU; the step is ~100 batched gather-GEMM launches of the same kernel (environment "
                             "chains) + the final product; kernel time = the library's Pi stage timer (CUDA events)"}
         out = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
