@@ -473,19 +473,25 @@ __global__ void __launch_bounds__(128)
         __syncthreads();
         produce((f + NST - 1) % NST);
         const double *as = Asm + (f % NST) * A_SZ, *bs = Bsm + (f % NST) * B_SZ;
-#pragma unroll
-        for (int k4 = 0; k4 < KT; k4 += 4) {
-            double af[TI], bf[TJ];
+        // fragments of k-step k4 + 4 are fetched while the DMMAs of k-step k4 issue (explicit double buffering)
+        double af[2][TI], bf[2][TJ];
+        auto lfrag = [&](int buf, int k4) {
 #pragma unroll
             for (int i = 0; i < TI; ++i)
-                af[i] = TA ? as[(wm + 8 * i + fr) * A_ROW + k4 + fk] : as[(k4 + fk) * A_ROW + wm + 8 * i + fr];
+                af[buf][i] = TA ? as[(wm + 8 * i + fr) * A_ROW + k4 + fk] : as[(k4 + fk) * A_ROW + wm + 8 * i + fr];
 #pragma unroll
             for (int j = 0; j < TJ; ++j)
-                bf[j] = TB ? bs[(k4 + fk) * B_ROW + wn + 8 * j + fr] : bs[(wn + 8 * j + fr) * B_ROW + k4 + fk];
+                bf[buf][j] = TB ? bs[(k4 + fk) * B_ROW + wn + 8 * j + fr] : bs[(wn + 8 * j + fr) * B_ROW + k4 + fk];
+        };
+        lfrag(0, 0);
+#pragma unroll
+        for (int k4 = 0; k4 < KT; k4 += 4) {
+            const int cur = (k4 >> 2) & 1;
+            if (k4 + 4 < KT) lfrag(cur ^ 1, k4 + 4);
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
-                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
         if (++ck == nkt) { // tile ct is complete: store it and start the next accumulator
             const i64 g = t0 + ct;
