@@ -272,6 +272,13 @@ int tci_contract_naive_site(tci_ctx *ctx, const double *A, int64_t Da, int64_t s
 int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts, int64_t nsearch,
                      double threshold, int64_t maxn, int mode, int64_t *pivots_out, double *errs_out,
                      int64_t *start_idx_out, int64_t *nfound);
+/* The same call with the start points drawn inside the library by the injected counter-based generator that replaces
+ * Julia's rng at globalpivotfinder.jl:156 (start s, site p = 1 + floor(tci_uniform01(seed, (call*1000003 + s)*1009 + p)
+ * * d_p), include/tci_targets.h; `call` counts the finder calls of a run, from 1): every GPU draws its own block of
+ * starts on the device, so nothing is generated or uploaded by the host.  Results as tci_globalsearch.               */
+int tci_globalsearch_counter(tci_ctx *ctx, int64_t target_id, int64_t tt_id, uint64_t seed, uint64_t call,
+                             int64_t nsearch, double threshold, int64_t maxn, int mode, int64_t *pivots_out,
+                             double *errs_out, int64_t *start_idx_out, int64_t *nfound);
 /* Host-only pieces of the sharded stages, exported so that the partitioning and the selection can be tested without a
  * GPU: the block [lo, hi) of `rank` when n items are split over `world` ranks in contiguous blocks whose starts are
  * multiples of `align`; and the selection of :180-188 replayed on gathered (error, probe index) records.             */

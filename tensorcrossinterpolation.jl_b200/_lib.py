@@ -68,6 +68,8 @@ SYMBOLS = {
                                           C.POINTER(VP)]),
     "tci_contract_naive_site": (C.c_int, [VP, P_f64, i64, i64, i64, i64, P_f64, i64, i64, i64, P_f64]),
     "tci_globalsearch": (C.c_int, [VP, i64, i64, P_i64, i64, f64, i64, C.c_int, P_i64, P_f64, P_i64, P_i64]),
+    "tci_globalsearch_counter": (C.c_int, [VP, i64, i64, C.c_uint64, C.c_uint64, i64, f64, i64, C.c_int, P_i64, P_f64, P_i64,
+                                           P_i64]),
     "tci_shard_order": (C.c_int, [P_i64, i64, i64, C.c_int, P_i64]),
     "tci_shard_range": (C.c_int, [i64, C.c_int, C.c_int, i64, P_i64, P_i64]),
     "tci_globalsearch_select": (C.c_int, [P_f64, P_i64, i64, P_i64, i64, P_i64, f64, i64, P_i64, P_f64, P_i64, P_i64]),

@@ -564,7 +564,7 @@ static int gsearch_member(tci_ctx *ctx, TargetDev &t, TargetDev &tt, const i64 *
     if (ns <= 0) return TCI_OK;
     const int n = (int)t.nsites;
     const i64 star = off[n], count = star * ns;
-    const i64 *starts = d_starts + s0 * n;
+    const i64 *starts = d_starts; // this member's block of starts (entry 0 = start s0)
     std::vector<CoreView> cv = views(tt);
     DevBuf<double> d_f(ctx), d_g(ctx);
     DevBuf<i64> d_idx(ctx);
@@ -650,9 +650,27 @@ static int gsearch_member(tci_ctx *ctx, TargetDev &t, TargetDev &tt, const i64 *
     return TCI_OK;
 }
 
-extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts,
-                                int64_t nsearch, double threshold, int64_t maxn, int mode, int64_t *pivots_out,
-                                double *errs_out, int64_t *start_idx_out, int64_t *nfound)
+// start point s, site p of the injected counter generator (util.CounterRNG.start_points, oracle start_points):
+// 1 + floor(u * d) with u = tci_uniform01(seed, (call * 1000003 + s) * 1009 + p), clamped to d
+TCI_HD i64 counter_start(unsigned long long seed, unsigned long long call, i64 s, i64 p, i64 d)
+{
+    const unsigned long long idx = (call * 1000003ull + (unsigned long long)s) * 1009ull + (unsigned long long)p;
+    const i64 v = 1 + (i64)(tci_uniform01(seed, idx) * (double)d);
+    return v < d ? v : d;
+}
+__global__ void k_counter_starts(unsigned long long seed, unsigned long long call, i64 s0, i64 ns, int n,
+                                 const i64 *__restrict__ off, i64 *__restrict__ out)
+{
+    const i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (e >= ns * n) return;
+    const i64 s = e / n, p = e % n;
+    out[e] = counter_start(seed, call, s0 + s, p, off[p + 1] - off[p]);
+}
+
+static int globalsearch_core(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts, bool counter,
+                             unsigned long long seed, unsigned long long call, int64_t nsearch, double threshold,
+                             int64_t maxn, int mode, int64_t *pivots_out, double *errs_out, int64_t *start_idx_out,
+                             int64_t *nfound)
 {
     TCI_ENTER(ctx);
     if (!nfound) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: nfound missing");
@@ -667,7 +685,7 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, 
     if (tt.dl.front() != 1 || tt.dr.back() != 1) return tci_fail(ctx, TCI_ERR_ARG, "boundary bonds must be 1");
     if (mode < 0 || mode > 2) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: mode is 0 (auto), 1 (ordered chain) or 2 (environments)");
     if (nsearch <= 0 || maxn <= 0) return TCI_OK;
-    if (!starts || !pivots_out || !errs_out) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: buffers missing");
+    if ((!starts && !counter) || !pivots_out || !errs_out) return tci_fail(ctx, TCI_ERR_ARG, "tci_globalsearch: buffers missing");
     const i64 nsites = t.nsites;
     std::vector<i64> off((size_t)nsites + 1, 0);
     for (i64 p = 0; p < nsites; ++p) off[p + 1] = off[p] + tt.d[p];
@@ -694,11 +712,21 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, 
         TargetDev &tk = *c->targets.at(target_id);
         TargetDev &ttk = *c->targets.at(tt_id);
         TCI_CUDA(c, dev_alloc(c, (void **)&drec[k], rec_bytes));
-        TCI_CUDA(c, dev_alloc(c, (void **)&dst[k], (size_t)(nsites * nsearch) * sizeof(i64)));
-        TCI_CUDA(c, dev_alloc(c, (void **)&doff[k], off.size() * sizeof(i64)));
-        TCI_CUDA(c, cudaMemcpyAsync(dst[k], starts, (size_t)(nsites * nsearch) * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
-        TCI_CUDA(c, cudaMemcpyAsync(doff[k], off.data(), off.size() * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
         const i64 s0 = std::min(nsearch, c->rank * blk), s1 = std::min(nsearch, (c->rank + 1) * blk);
+        // only this member's block of starts: uploaded, or drawn on the device by the counter generator
+        TCI_CUDA(c, dev_alloc(c, (void **)&dst[k], (size_t)std::max<i64>(nsites * (s1 - s0), 1) * sizeof(i64)));
+        TCI_CUDA(c, dev_alloc(c, (void **)&doff[k], off.size() * sizeof(i64)));
+        TCI_CUDA(c, cudaMemcpyAsync(doff[k], off.data(), off.size() * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+        if (s1 > s0) {
+            if (counter) {
+                const i64 tot = nsites * (s1 - s0);
+                k_counter_starts<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(seed, call, s0, s1 - s0, (int)nsites, doff[k],
+                                                                                 dst[k]);
+                c->launches++;
+            } else
+                TCI_CUDA(c, cudaMemcpyAsync(dst[k], starts + nsites * s0, (size_t)(nsites * (s1 - s0)) * sizeof(i64),
+                                            cudaMemcpyHostToDevice, c->stream));
+        }
         return gsearch_member(c, tk, ttk, dst[k], s0, s1, mode, doff[k], off, drec[k]);
     };
     if (world == 1)
@@ -732,8 +760,35 @@ extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, 
         ridx[q] = hrec[q].idx;
     }
     for (i64 p = 0; p < nsites; ++p) ld[p] = tt.d[p];
+    std::vector<i64> drawn;
+    if (counter) { // the selection needs the start points themselves: the same generator on the host
+        drawn.resize((size_t)(nsites * nsearch));
+        for (i64 q = 0; q < nsearch; ++q)
+            if (rerr[q] > threshold) // only accepted starts are read (tci_globalsearch_select)
+                for (i64 p = 0; p < nsites; ++p) drawn[(size_t)(nsites * q + p)] = counter_start(seed, call, q, p, ld[p]);
+        starts = drawn.data();
+    }
     return tci_globalsearch_select(rerr.data(), ridx.data(), nsearch, starts, nsites, ld.data(), threshold, maxn,
                                    pivots_out, errs_out, start_idx_out, nfound);
+}
+
+extern "C" int tci_globalsearch(tci_ctx *ctx, int64_t target_id, int64_t tt_id, const int64_t *starts,
+                                int64_t nsearch, double threshold, int64_t maxn, int mode, int64_t *pivots_out,
+                                double *errs_out, int64_t *start_idx_out, int64_t *nfound)
+{
+    return globalsearch_core(ctx, target_id, tt_id, starts, false, 0ull, 0ull, nsearch, threshold, maxn, mode, pivots_out,
+                             errs_out, start_idx_out, nfound);
+}
+
+// tci_globalsearch with the start points drawn INSIDE the library by the injected counter generator (seed, call): every
+// GPU draws its own block on the device, nothing is generated or uploaded by the host.  Start s, site p is
+// 1 + floor(tci_uniform01(seed, (call * 1000003 + s) * 1009 + p) * d_p), the sequence util.CounterRNG / the oracle use.
+extern "C" int tci_globalsearch_counter(tci_ctx *ctx, int64_t target_id, int64_t tt_id, uint64_t seed, uint64_t call,
+                                        int64_t nsearch, double threshold, int64_t maxn, int mode, int64_t *pivots_out,
+                                        double *errs_out, int64_t *start_idx_out, int64_t *nfound)
+{
+    return globalsearch_core(ctx, target_id, tt_id, nullptr, true, seed, call, nsearch, threshold, maxn, mode, pivots_out,
+                             errs_out, start_idx_out, nfound);
 }
 
 // selection of globalpivotfinder.jl:180-188 on the per-start (error, probe index) records: keep a start if its best

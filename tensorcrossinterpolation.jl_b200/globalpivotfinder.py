@@ -46,7 +46,6 @@ class DefaultGlobalPivotFinder(AbstractGlobalPivotFinder):  # :100-195
         if getattr(f, "is_complex", False):  # ComplexF64 target: two device batches + the library's selection
             from .complexf64 import zfind_global_pivots
             return zfind_global_pivots(self, input, f, abstol, rng=rng, verbosity=verbosity)
-        starts = np.ascontiguousarray(self.draw(input, rng))
         ctx = f.ctx
         tt = input.current_tt
         handle = getattr(tt, "device_handle", None)  # the device-resident cores tci_fill_sitetensors left behind
@@ -58,9 +57,16 @@ class DefaultGlobalPivotFinder(AbstractGlobalPivotFinder):  # :100-195
         errs = np.zeros(cap, dtype=np.float64)
         acc = np.zeros(cap, dtype=np.int64)
         nf = C.c_int64(0)
-        ctx.check(lib().tci_globalsearch(ctx.h, f.id, handle.id, pi(starts), starts.shape[0],
-                                         float(abstol) * self.tolmarginglobalsearch, cap, int(mode), pi(piv),
-                                         pf(errs), pi(acc), C.byref(nf)))
+        if isinstance(rng, CounterRNG):  # the injected generator: the library draws the starts itself, on the device
+            rng.calls += 1
+            ctx.check(lib().tci_globalsearch_counter(ctx.h, f.id, handle.id, rng.seed & (2**64 - 1), rng.calls, self.nsearch,
+                                                     float(abstol) * self.tolmarginglobalsearch, cap, int(mode), pi(piv),
+                                                     pf(errs), pi(acc), C.byref(nf)))
+        else:
+            starts = np.ascontiguousarray(self.draw(input, rng))
+            ctx.check(lib().tci_globalsearch(ctx.h, f.id, handle.id, pi(starts), starts.shape[0],
+                                             float(abstol) * self.tolmarginglobalsearch, cap, int(mode), pi(piv),
+                                             pf(errs), pi(acc), C.byref(nf)))
         if verbosity > 0:
             print(f"Found {nf.value} global pivots")
         self.last_errors = errs[: nf.value].copy()
