@@ -30,8 +30,8 @@ int zgemm_dev_batched_off(tci_ctx *ctx, bool tA, bool tB, i64 M, i64 N, i64 K, d
 
 // Bp[bl, br, h, j] = B[bl, h, j, br]: with this copy the second product of a right-environment step,
 //   nxt[al, bl] = sum_{br, h} tmp[(br, h), al] * B[bl, h, j, br]      (contraction.jl:144-176),
-// is ONE GEMM with inner dimension Lbn * S instead of S accumulating GEMMs (the reference permutes its cores once as
-// well: `bperm`, contraction.jl:152-158).
+// is ONE GEMM with inner dimension Lbn * S instead of S accumulating GEMMs (the reference permutes both cores too, with
+// permutedims on every extension: contraction.jl:170-171).
 template <class V>
 __global__ void k_permute_b(const V *__restrict__ B, i64 Lb, i64 S, i64 d3, i64 Lbn, V *__restrict__ Bp)
 {
