@@ -215,7 +215,9 @@ int tci_bond_update(tci_ctx *ctx, int64_t target_id, const int64_t *I, int64_t n
  * ragged arrays: Iset[b] is (b x nI[b]), Jset[b] is ((n-1-b) x nJ[b]), multi-index contiguous, b = 0 .. n-1 (0-based).
  * The call returns the new set sizes and the length of the pivot-error vector; tci_sweep2site_fetch then copies the
  * sets into caller-allocated arrays of those sizes, with bonderrors (n-1), pivoterrors, max|Pi| over the bonds
- * (updatemaxsample!, :538) and, per bond in the order visited, (bond, rows, columns, npivot) (4 (n-1) values).      */
+ * (updatemaxsample!, :538) and, per bond in the order visited, (bond, rows, columns, npivot) (4 (n-1) values).
+ * Not formed: the two site tensors updatepivots! sets when there are no extra sets (:599-602) -- the next bond
+ * invalidates them and fillsitetensors! (:909-911) rebuilds all of them at the end of sweep2site!.                    */
 int tci_sweep2site_half(tci_ctx *ctx, int64_t target_id, int forward, const int64_t *const *Iset, const int64_t *nI,
                         const int64_t *const *Jset, const int64_t *nJ, const int64_t *const *extraI,
                         const int64_t *nextraI, const int64_t *const *extraJ, const int64_t *nextraJ, double reltol,
