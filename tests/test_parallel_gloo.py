@@ -120,6 +120,29 @@ def _worker(rank, world, port, q):
             acc[rlo2:rhi2] = torch.from_numpy(Lb @ R)
         dist.all_reduce(acc)  # stands in for the peer stores into the owner's Pi (disjoint row ranges)
         res["tt_rows_two_chains"] = bool(np.max(np.abs(acc.numpy() - reft)) <= 1e-13 * np.max(np.abs(reft)))
+        # ---- the same with the library's PREFIX-AWARE partition (tci_shard_order): rows in lexicographic order of their
+        # multi-indices, columns with the last site most significant, contiguous blocks of those orders per rank; the
+        # right environments are gathered in sorted column order and a rank's block product is scattered to the
+        # caller's rows / columns (k_scatter_block on the device)
+        from tci_b200._lib import shard_order
+        myrows = P.prefix_partition(It, world, 0)[rank]
+        cperm = shard_order(Jt, 1)
+        mycols = cperm[rank * cblk:(rank + 1) * cblk]
+        rfull2 = torch.zeros((cblk * world, 8), dtype=torch.float64)
+        for qq, jj in enumerate(mycols):
+            rfull2[rank * cblk + qq, :D] = torch.from_numpy(renv(Jt[jj]))
+        _gather_blocks(rfull2, cblk, rank)
+        R2 = rfull2[:len(Jt), :D].numpy().T  # D x nJ, columns in suffix-sorted order
+        acc2 = torch.zeros((len(It), len(Jt)), dtype=torch.float64)
+        if len(myrows):
+            Lb2 = np.array([lenv(It[ii]) for ii in myrows])
+            blk2 = np.zeros((len(It), len(Jt)))
+            blk2[np.ix_(myrows, cperm)] = Lb2 @ R2
+            acc2 += torch.from_numpy(blk2)
+        dist.all_reduce(acc2)
+        res["tt_prefix_partition"] = bool(np.max(np.abs(acc2.numpy() - reft)) <= 1e-13 * np.max(np.abs(reft)))
+        rows_all = np.concatenate(P.prefix_partition(It, world, 0))
+        res["tt_prefix_partition_covers"] = sorted(rows_all.tolist()) == list(range(len(It)))
         # ---- sharded global search ----
         R = 10
         t = orc.Target.builtin(6, [R, 1], [2] * R)
