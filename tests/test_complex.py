@@ -92,6 +92,29 @@ def test_oracle_zarith_division_and_hypot(oracle):
     assert oracle.zrrlu(tiny).L[1, 0] == pytest.approx(-1j / 3, rel=1e-15)
 
 
+@pytest.mark.parametrize("lo", [True, False])
+def test_oracle_zluci_interpolation_properties(oracle, lo):
+    """MatrixLUCI on complex data (test_matrixluci.jl:7-46 restated on the oracle): A ~ left * right, the pivot rows /
+    columns are reproduced exactly (right[:, J] = A[I, J] when leftorthogonal, left[I, :] = A[I, J] otherwise), and
+    left * right is exact when the rank is reached."""
+    rng = np.random.default_rng(9)
+    A = crand(rng, 12, 4) @ crand(rng, 4, 15)  # rank 4
+    ref = oracle.zluci(A, reltol=1e-10, leftorthogonal=lo)
+    assert ref.npivot == 4
+    I, J = ref.rowindices - 1, ref.colindices - 1
+    np.testing.assert_allclose(ref.left @ ref.right, A, rtol=1e-10, atol=1e-12)
+    if lo:
+        np.testing.assert_allclose(ref.right[:, J], A[I][:, J], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(ref.left[I, :], np.eye(4), atol=1e-12)
+    else:
+        np.testing.assert_allclose(ref.left[I, :], A[I][:, J], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(ref.right[:, J], np.eye(4), atol=1e-12)
+    B = crand(rng, 9, 9)
+    full = oracle.zluci(B, leftorthogonal=lo)
+    assert full.npivot == 9 and full.error == 0.0
+    np.testing.assert_allclose(full.left @ full.right, B, rtol=1e-10, atol=1e-11)
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def T():
