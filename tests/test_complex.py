@@ -115,6 +115,59 @@ def test_oracle_zluci_interpolation_properties(oracle, lo):
     np.testing.assert_allclose(full.left @ full.right, B, rtol=1e-10, atol=1e-11)
 
 
+def test_complex_global_pivot_finder_host_logic():
+    """DefaultGlobalPivotFinder for a ComplexF64 target (complexf64.zfind_global_pivots) against a direct restatement of
+    globalpivotfinder.jl:143-195: star probes from every start, error = abs(f - tt), strict `>` keeps the first maximum,
+    threshold abstol * tolmarginglobalsearch, truncation to the first maxnglobalpivot in start order.  The evaluators are
+    numpy stand-ins (no GPU): only the host logic and the library's host-only selection are exercised."""
+    import tci_b200 as T
+    from tci_b200.complexf64 import zfind_global_pivots
+    ld = [3, 4, 2, 5]
+    rng = np.random.default_rng(77)
+    F = crand(rng, *ld)
+    G = F.copy()
+    bumps = [(0, 1, 1, 2), (2, 3, 0, 4), (1, 0, 1, 1)]
+    for k, b in enumerate(bumps):
+        G[b] += (0.5 + 0.25 * k) * (1 + 1j)
+
+    class Ev:
+        is_complex = True
+        ctx = None
+
+        def __init__(self, arr):
+            self.arr = arr
+
+        def evaluate_points(self, pts):
+            pts = np.asarray(pts)
+            return self.arr[tuple((pts - 1).T)]
+
+    class TT:
+        device_handle = None
+
+    tt = TT()
+    tt.device_handle = Ev(F)
+    finder = T.DefaultGlobalPivotFinder(nsearch=12, maxnglobalpivot=3, tolmarginglobalsearch=10.0)
+    inp = T.GlobalPivotSearchInput(ld, tt, 1.0, None, None)
+    abstol = 0.01
+    got = zfind_global_pivots(finder, inp, Ev(G), abstol, rng=T.CounterRNG(5))
+    starts = T.CounterRNG(5).start_points(12, ld)
+    ref = []
+    for s in starts:  # :156-188
+        best, bestp = 0.0, list(s)
+        for p, d in enumerate(ld):
+            for v in range(1, d + 1):
+                x = list(s)
+                x[p] = v
+                e = abs(G[tuple(np.array(x) - 1)] - F[tuple(np.array(x) - 1)])
+                if e > best:
+                    best, bestp = e, x
+        if best > abstol * 10.0:
+            ref.append([int(v) for v in bestp])
+    assert got.tolist() == ref[:3] and len(ref) >= 1
+    np.testing.assert_allclose(finder.last_errors, [abs(G[tuple(np.array(x) - 1)] - F[tuple(np.array(x) - 1)]) for x in ref[:3]],
+                               rtol=1e-15)
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def T():
